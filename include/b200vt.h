@@ -1,0 +1,121 @@
+/* b200vt.h — C ABI of libb200vt.so: the B200 (sm_100a) attention hot path for VideoTuna-style video denoisers.
+ *
+ * VideoTuna has no C FFI for this path; its "plugin interface" is a set of Python callables.
+ * Every entry point below names the reference callable whose arithmetic it replaces. The Python host layer
+ * (videotuna-dev_b200/ops.py) binds these with ctypes and registers them as torch.library ops.
+ *
+ * Conventions
+ *  - All functions return 0 on success or a negative VT_ERR_* code; they never throw and never exit.
+ *    vt_last_error() returns a thread-local human-readable message for the last failure on this thread.
+ *  - The caller owns every buffer. Pointers are raw device pointers (16-byte aligned) unless stated otherwise.
+ *  - `stream` is a cudaStream_t passed as void*. Nothing synchronises the host.
+ *  - bf16 = __nv_bfloat16 bit pattern. Strides are in ELEMENTS. "(b,l,h)" stride arrays have 3 entries:
+ *    batch, sequence position, head; the head-dim stride is always 1.
+ */
+#ifndef B200VT_H_
+#define B200VT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VT_OK 0
+#define VT_ERR_SHAPE (-1)       /* unsupported or inconsistent shape */
+#define VT_ERR_DTYPE (-2)       /* unsupported dtype / head dim */
+#define VT_ERR_ALIGN (-3)       /* pointer or stride not 16-byte aligned */
+#define VT_ERR_CUDA (-4)        /* CUDA runtime/driver error; see vt_last_error */
+#define VT_ERR_NULL (-5)        /* required pointer is NULL */
+#define VT_ERR_UNSUPPORTED (-6) /* feature not available (e.g. device is not sm_100) */
+
+int vt_version(void);
+/* Copies the calling thread's last error message (NUL-terminated) into buf; returns its length. */
+int vt_last_error(char* buf, size_t n);
+/* Optional: create per-device state eagerly. Returns VT_ERR_UNSUPPORTED if the device is not compute 10.x. */
+int vt_init(int device);
+/* Reads the watchdog words written by a kernel that trapped on a stuck barrier: out[0..3] =
+ * {call-site tag, blockIdx.x, blockIdx.y | blockIdx.z<<16, threadIdx.x}; all zero if none fired. */
+int vt_debug_watchdog(uint32_t out[4]);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Dense non-causal attention forward:  O = softmax(scale * Q K^T) V,  LSE = logsumexp(scale * Q K^T) (natural log)
+ * Replaces: lvdm CrossAttention.forward einsum/softmax/einsum   videotuna/models/lvdm/modules/attention.py:128-144
+ *           hunyuan attention() core                            videotuna/models/hunyuan/hyvideo_t2v/modules/attenion.py:101-120
+ *           wan flash_attention() core                          videotuna/models/wan/wan/modules/attention.py:96-127
+ * q (B,Lq,H,D), k/v (B,Lk,H,D), o (B,Lq,H,D) bf16; lse (B,H,Lq) fp32 contiguous. D in {64,128}.
+ * Sequence modes:
+ *   fixed  (num_segments == 0): keys of batch b are [0, seqlens_k ? seqlens_k[b] : Lk).  (wan k_lens, attention.py:62-71)
+ *   varlen (num_segments  > 0): B must be 1 and the tensors are packed (total,H,D); segment s covers rows
+ *          [cu_seqlens_q[s], cu_seqlens_q[s+1]) and keys [cu_seqlens_k[s], cu_seqlens_k[s+1]); Lq/Lk are the packed
+ *          totals and max_seqlen_q/k bound the longest segment.               (hunyuan get_cu_seqlens, attenion.py:34-57)
+ * cu_seqlens_*, seqlens_k are DEVICE int32 pointers (nullable as described).
+ * ------------------------------------------------------------------------------------------------------------- */
+int vt_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse,
+                const int64_t* q_strides, const int64_t* k_strides, const int64_t* v_strides,
+                const int64_t* o_strides, int B, int H, int Lq, int Lk, int D,
+                const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k, int num_segments, int max_seqlen_q,
+                int max_seqlen_k, const int32_t* seqlens_k, float softmax_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Fused QK-RMSNorm + 3-D RoPE (interleaved pairs) in one pass over q or k, in place of
+ *   hunyuan RMSNorm (norm_layers.py:5-59) + apply_rotary_emb (posemb_layers.py:140-188)      -> norm_mode 1
+ *   wan WanRMSNorm over dim = H*D (model.py:70-86) + rope_apply (model.py:40-67)              -> norm_mode 2
+ *   rope only (CogVideoX-5B style, or q/k already normalised)                                 -> norm_mode 0
+ * x: (B,L,H,D) bf16 with (b,l,h) strides -> y likewise. D in {64,128}.
+ * norm_mode 1: RMS over each head's D values, w is (D) fp32;  2: RMS over the token's H*D values, w is (H*D) fp32.
+ * cos/sin: (L_rope, D) fp32 tables in the reference's repeat_interleave(2) form, or both NULL (no rotation):
+ *   y[2i] = n[2i]*cos[2i] - n[2i+1]*sin[2i];  y[2i+1] = n[2i+1]*cos[2i+1] + n[2i]*sin[2i+1]
+ * Tokens l >= L_rope are not rotated (text tokens). rstd_out (nullable): (B,L,H) for mode 1, (B,L) for mode 2.
+ * Backward accumulates dw into dw_accum (fp32, caller zeroes; nullable).
+ * ------------------------------------------------------------------------------------------------------------- */
+int vt_qk_rmsnorm_rope_fwd(const void* x, void* y, float* rstd_out, const float* w, const float* cos, const float* sin,
+                           const int64_t* x_strides, const int64_t* y_strides, int B, int L, int H, int D, int L_rope,
+                           int norm_mode, float eps, void* stream);
+int vt_qk_rmsnorm_rope_bwd(const void* dy, const void* x, const float* rstd, void* dx, float* dw_accum, const float* w,
+                           const float* cos, const float* sin, const int64_t* dy_strides, const int64_t* x_strides,
+                           const int64_t* dx_strides, int B, int L, int H, int D, int L_rope, int norm_mode,
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * LayerNorm (optional affine) fused with adaLN modulate:  y = LN(x) * (1 + scale[b]) + shift[b]
+ * Replaces hunyuan  modulate(norm(x), shift, scale)   (modulate_layers.py:31-49 with nn.LayerNorm, models.py:161-164)
+ *          wan      norm1(x).float() * (1 + e1) + e0  (wan/modules/model.py:294-296)
+ *          lvdm     nn.LayerNorm(dim) (affine, no modulate: scale == shift == NULL)  (attention.py:299-310)
+ * x,y: (B,L,C) bf16 contiguous rows; gamma/beta: (C) fp32 or NULL; scale/shift: (B,C) fp32 or NULL.
+ * mean/rstd: (B*L) fp32 saved for backward.
+ * ------------------------------------------------------------------------------------------------------------- */
+int vt_ln_modulate_fwd(const void* x, void* y, float* mean, float* rstd, const float* gamma, const float* beta,
+                       const float* scale, const float* shift, int B, int L, int C, float eps, void* stream);
+/* dx; and fp32 accumulators (atomically added, caller zeroes): dgamma,dbeta (C); dscale,dshift (B,C). Nullable. */
+int vt_ln_modulate_bwd(const void* dy, const void* x, const float* mean, const float* rstd, void* dx,
+                       const float* gamma, const float* beta, const float* scale, float* dgamma, float* dbeta,
+                       float* dscale, float* dshift, int B, int L, int C, void* stream);
+
+/* Gated residual: y = x + branch * gate[b]   (hunyuan apply_gate, modulate_layers.py:52-68 & models.py:231;
+ * wan x + y * e2, model.py:298). x, branch, y: (B,L,C) bf16; gate: (B,C) fp32 or NULL (plain add). */
+int vt_gate_residual_fwd(const void* x, const void* branch, void* y, const float* gate, int B, int L, int C,
+                         void* stream);
+/* dbranch = dy * gate; dgate (B,C) fp32 accumulated atomically (caller zeroes); dx = dy is the caller's alias. */
+int vt_gate_residual_bwd(const void* dy, const void* branch, void* dbranch, const float* gate, float* dgate, int B,
+                         int L, int C, void* stream);
+
+/* GroupNorm(G) [+ SiLU] on NCHW-like tensors x: (N, C, S) bf16 or fp32 (S = product of spatial dims), fp32 statistics.
+ * Replaces lvdm normalization()/GroupNormSpecific + nn.SiLU (lvdm/modules/utils.py:192-203, openaimodel3d.py:229-255)
+ * and SpatialTransformer/TemporalTransformer.norm (attention.py:376-392,475-519). dtype: 0 = bf16, 1 = fp32. */
+int vt_groupnorm_silu_fwd(const void* x, void* y, float* mean, float* rstd, const float* gamma, const float* beta,
+                          int N, int C, int S, int G, float eps, int apply_silu, int dtype, void* stream);
+int vt_groupnorm_silu_bwd(const void* dy, const void* x, const float* mean, const float* rstd, void* dx,
+                          const float* gamma, const float* beta, float* dgamma, float* dbeta, int N, int C, int S, int G,
+                          int apply_silu, int dtype, void* stream);
+
+/* Self-test hook used by tests/: one 128x128x128 bf16 GEMM tile through TMA + tcgen05 with selectable operand
+ * sources (see csrc/umma_probe.cu). Not part of the product path. */
+int vt_umma_probe(const void* a, const void* b, float* d, int a_mode, int b_mode, int n, uint32_t a_lbo, uint32_t a_sbo,
+                  uint32_t a_kstep, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200VT_H_ */

@@ -1,0 +1,57 @@
+// attn_common.h — host/device parameter blocks shared by the attention kernels and the C-ABI.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace vt {
+
+// Logical tensors are (B, L, H, D) with arbitrary element strides for B, L, H and unit stride for D.
+// Two sequence modes:
+//   fixed : problem p = batch p; q rows [0,Lq), k rows [0, seqlens_k ? seqlens_k[p] : Lk)
+//   varlen: B == 1, tensors are packed (total, H, D); problem p = segment p with rows
+//           [cu_q[p], cu_q[p+1]) and keys [cu_k[p], cu_k[p+1]).  (reference: flash_attn_varlen_func as called
+//           from hunyuan attenion.py:108 and wan attention.py:113)
+struct AttnSeq {
+  const int32_t* cu_q;       // device, nullable
+  const int32_t* cu_k;       // device, nullable
+  const int32_t* seqlens_k;  // device, nullable (fixed mode only)
+  int Lq, Lk;                // fixed: per-batch lengths; varlen: max_seqlen_q / max_seqlen_k
+  int H;
+  int nprob;                 // batches (fixed) or segments (varlen)
+};
+
+struct AttnFwdParams {
+  AttnSeq seq;
+  __nv_bfloat16* o;
+  float* lse;                // (B, H, Lq_total) fp32, natural-log units
+  int64_t o_sb, o_sl, o_sh;  // element strides of o
+  int64_t lse_sb, lse_sh;    // element strides of lse (row stride 1)
+  float scale;               // softmax scale
+  float scale_log2;          // scale * log2(e)
+};
+
+struct AttnBwdParams {
+  AttnSeq seq;
+  const float* lse;          // from forward
+  const float* delta;        // rowsum(dO * O), same layout as lse
+  int64_t lse_sb, lse_sh;
+  __nv_bfloat16* dk;
+  __nv_bfloat16* dv;
+  int64_t dk_sb, dk_sl, dk_sh;
+  int64_t dv_sb, dv_sl, dv_sh;
+  float scale;
+  float scale_log2;
+};
+
+// Host-side launchers implemented in the kernel translation units. Return cudaError_t of the launch.
+cudaError_t launch_attn_fwd(int D, const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
+                            const AttnFwdParams& p, int q_tiles_hint, cudaStream_t stream);
+cudaError_t launch_attn_bwd(int D, const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
+                            const CUtensorMap& tm_do, const CUtensorMap& tm_dq_acc, const AttnBwdParams& p,
+                            cudaStream_t stream);
+cudaError_t attn_fwd_set_debug_ptr(unsigned int* p);
+cudaError_t attn_bwd_set_debug_ptr(unsigned int* p);
+
+}  // namespace vt

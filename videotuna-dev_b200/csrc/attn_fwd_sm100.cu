@@ -1,0 +1,361 @@
+// attn_fwd_sm100.cu — dense (non-causal) flash-attention forward for sm_100a.
+//
+// Replaces the attention core of
+//   lvdm CrossAttention.forward          (videotuna/models/lvdm/modules/attention.py:126-149)
+//   hunyuan attention(mode="flash"|"torch") (videotuna/models/hunyuan/hyvideo_t2v/modules/attenion.py:101-120)
+//   wan flash_attention                  (videotuna/models/wan/wan/modules/attention.py:96-127)
+//
+// One CTA owns NQ (1 or 2) query tiles of 128 rows for one (problem, head) and streams 128-key tiles:
+//   warp 4*NQ     : TMA producer (Q once; K/V ring, 128B-swizzled boxes of 128 rows x 64 elems)
+//   warp 4*NQ + 1 : tcgen05.mma issuer (single thread).  S_t = Q_t K^T (SS), O_t += P_t V (A = P from TMEM)
+//   warps [0,4*NQ): softmax warpgroups, one thread per query row: tcgen05.ld S -> online softmax (exp2,
+//                   lazy rescale) -> bf16 P written back over S with tcgen05.st -> mbarrier to the issuer.
+// With NQ == 2 the two tiles ping-pong: while warpgroup 0 does softmax on S_0 the tensor core runs
+// P_1 V and Q_1 K^T, so MMA and MUFU work overlap.
+// TMEM columns: S_t at 128*t (P_t aliases its first 64 columns), O_t at 128*NQ + D*t.
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+#include "attn_common.h"
+#include "sm100_ptx.cuh"
+
+namespace vt {
+namespace {
+
+template <int D, int NQ>
+struct FwdCfg {
+  static_assert(D == 64 || D == 128, "head dim must be 64 or 128");
+  static constexpr int KCH = D / 64;               // 128-byte chunks along the head dim
+  static constexpr int CHUNK = 128 * 128;          // bytes: 128 rows x 128 B (one swizzled box)
+  static constexpr int TILE = CHUNK * KCH;         // bytes of a 128 x D bf16 tile
+  static constexpr int KS = 2, VS = 2;             // K / V ring depth
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + NQ * TILE;
+  static constexpr int OFF_V = OFF_K + KS * TILE;
+  static constexpr int OFF_BAR = OFF_V + VS * TILE;
+  static constexpr int NBAR = 1 + 2 * KS + 2 * VS + 3 * NQ;
+  static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+  static constexpr int BYTES = OFF_TMEM + 16 + 1024;  // + alignment slack
+  static constexpr int TMEM_USED = NQ * (128 + D);
+  static constexpr int TMEM_COLS = TMEM_USED <= 256 ? 256 : 512;
+  // NQ == 2: three full warpgroups (warps 10,11 idle) so setmaxnreg can move registers to the softmax warps.
+  static constexpr int THREADS = NQ == 2 ? 384 : 192;
+};
+
+enum : uint32_t {
+  TAG_Q_FULL = 0x100, TAG_K_FULL, TAG_K_EMPTY, TAG_V_FULL, TAG_V_EMPTY, TAG_S_FULL, TAG_P_FULL, TAG_O_FULL
+};
+
+template <int D, int NQ>
+__global__ void __launch_bounds__(FwdCfg<D, NQ>::THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const AttnFwdParams p) {
+  using C = FwdCfg<D, NQ>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  // ---- which problem / rows ------------------------------------------------------------------
+  const int prob = blockIdx.z, h = blockIdx.y;
+  int q_base = 0, q_len = p.seq.Lq, bq = prob;
+  int k_base = 0, k_len = p.seq.Lk, bk = prob;
+  if (p.seq.cu_q != nullptr) {
+    q_base = p.seq.cu_q[prob];
+    q_len = p.seq.cu_q[prob + 1] - q_base;
+    bq = 0;
+  }
+  if (p.seq.cu_k != nullptr) {
+    k_base = p.seq.cu_k[prob];
+    k_len = p.seq.cu_k[prob + 1] - k_base;
+    bk = 0;
+  } else if (p.seq.seqlens_k != nullptr) {
+    k_len = min(max(p.seq.seqlens_k[prob], 0), p.seq.Lk);
+  }
+  const int q0 = blockIdx.x * (NQ * 128);
+  if (q0 >= q_len) return;  // CTA-uniform
+  const int n_kv = (k_len + 127) >> 7;
+
+  if (n_kv == 0) {  // no keys: softmax over the empty set -> zeros, lse = -inf (matches flash-attn)
+    for (int r = threadIdx.x; r < NQ * 128; r += blockDim.x) {
+      const int row = q0 + r;
+      if (row < q_len) {
+        __nv_bfloat16* optr = p.o + bq * p.o_sb + static_cast<int64_t>(q_base + row) * p.o_sl + h * p.o_sh;
+        for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(optr + c) = make_uint4(0, 0, 0, 0);
+        p.lse[bq * p.lse_sb + h * p.lse_sh + q_base + row] = -CUDART_INF_F;
+      }
+    }
+    return;
+  }
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = q_full + 1;
+  uint64_t* k_empty = k_full + C::KS;
+  uint64_t* v_full = k_empty + C::KS;
+  uint64_t* v_empty = v_full + C::VS;
+  uint64_t* s_full = v_empty + C::VS;
+  uint64_t* p_full = s_full + NQ;
+  uint64_t* o_full = p_full + NQ;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM);
+
+  constexpr int PROD_WARP = NQ * 4, MMA_WARP = NQ * 4 + 1;
+
+  if (warp == PROD_WARP && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+  }
+  if (warp == MMA_WARP && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < C::KS; ++i) { mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1); }
+    for (int i = 0; i < C::VS; ++i) { mbar_init(v_full + i, 1); mbar_init(v_empty + i, 1); }
+    for (int i = 0; i < NQ; ++i) { mbar_init(s_full + i, 1); mbar_init(p_full + i, 128); mbar_init(o_full + i, 1); }
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // NQ == 2: 384 threads x 168 regs at launch; the service warpgroup (warps 8..11) gives registers to the two
+  // softmax warpgroups (setmaxnreg is warpgroup-wide, hence the idle warps 10,11 take the first branch too).
+  if (warp >= PROD_WARP) {
+    if constexpr (NQ == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    if (warp == PROD_WARP && lane == 0) {
+    // ================================ TMA producer ============================================
+    {
+      mbar_arrive_expect_tx(q_full, NQ * C::TILE);
+#pragma unroll
+      for (int t = 0; t < NQ; ++t)
+#pragma unroll
+        for (int c = 0; c < C::KCH; ++c)
+          tma_load_4d(smem + C::OFF_Q + t * C::TILE + c * C::CHUNK, &tm_q, q_full, c * 64, q_base + q0 + t * 128, h,
+                      bq);
+      for (int j = 0; j < n_kv; ++j) {
+        const int ks = j % C::KS, vs = j % C::VS;
+        mbar_wait(k_empty + ks, ((j / C::KS) & 1) ^ 1, TAG_K_EMPTY);
+        mbar_arrive_expect_tx(k_full + ks, C::TILE);
+#pragma unroll
+        for (int c = 0; c < C::KCH; ++c)
+          tma_load_4d(smem + C::OFF_K + ks * C::TILE + c * C::CHUNK, &tm_k, k_full + ks, c * 64, k_base + j * 128, h,
+                      bk);
+        mbar_wait(v_empty + vs, ((j / C::VS) & 1) ^ 1, TAG_V_EMPTY);
+        mbar_arrive_expect_tx(v_full + vs, C::TILE);
+#pragma unroll
+        for (int c = 0; c < C::KCH; ++c)
+          tma_load_4d(smem + C::OFF_V + vs * C::TILE + c * C::CHUNK, &tm_v, v_full + vs, c * 64, k_base + j * 128, h,
+                      bk);
+      }
+    }
+    } else if (warp == MMA_WARP && lane == 0) {
+    // ================================ MMA issuer ==============================================
+    {
+      constexpr uint32_t IDESC_QK = umma_idesc_bf16(128, 128, 0, 0);  // A=Q K-major, B=K K-major
+      constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, D, 0, 1);    // A=P (TMEM), B=V MN-major
+      const uint32_t q_smem = smem_u32(smem + C::OFF_Q);
+      const uint32_t k_smem = smem_u32(smem + C::OFF_K);
+      const uint32_t v_smem = smem_u32(smem + C::OFF_V);
+
+      auto issue_qk = [&](int t, int ks) {
+#pragma unroll
+        for (int c = 0; c < C::KCH; ++c)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t a = umma_desc_sw128(q_smem + t * C::TILE + c * C::CHUNK + kk * 32, 16, 1024);
+            const uint64_t b = umma_desc_sw128(k_smem + ks * C::TILE + c * C::CHUNK + kk * 32, 16, 1024);
+            umma_ss(tmem_base + t * 128, a, b, IDESC_QK, (c | kk) != 0);
+          }
+      };
+      auto issue_pv = [&](int t, int vs, bool acc) {
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {  // 16 keys per MMA
+          // V tile: [128 keys][64 d] x KCH boxes. MN-major B: LBO = next 64-d box, SBO = next 8 keys.
+          const uint64_t b = umma_desc_sw128(v_smem + vs * C::TILE + kk * 2048, C::CHUNK, 1024);
+          umma_ts(tmem_base + NQ * 128 + t * D, tmem_base + t * 128 + kk * 8, b, IDESC_PV, acc || kk != 0);
+        }
+      };
+
+      mbar_wait(q_full, 0, TAG_Q_FULL);
+      mbar_wait(k_full + 0, 0, TAG_K_FULL);
+      tc_fence_after();
+#pragma unroll
+      for (int t = 0; t < NQ; ++t) {
+        issue_qk(t, 0);
+        tc_commit(s_full + t);
+      }
+      tc_commit(k_empty + 0);
+
+      for (int j = 0; j < n_kv; ++j) {
+        const int vs = j % C::VS;
+        mbar_wait(v_full + vs, (j / C::VS) & 1, TAG_V_FULL);
+        const bool has_next = (j + 1 < n_kv);
+        const int ksn = (j + 1) % C::KS;
+#pragma unroll
+        for (int t = 0; t < NQ; ++t) {
+          mbar_wait(p_full + t, j & 1, TAG_P_FULL);
+          tc_fence_after();
+          issue_pv(t, vs, j > 0);
+          if (t == NQ - 1) tc_commit(v_empty + vs);
+          if (has_next) {
+            if (t == 0) {
+              mbar_wait(k_full + ksn, ((j + 1) / C::KS) & 1, TAG_K_FULL);
+              tc_fence_after();
+            }
+            issue_qk(t, ksn);
+            tc_commit(s_full + t);
+            if (t == NQ - 1) tc_commit(k_empty + ksn);
+          } else {
+            tc_commit(o_full + t);
+          }
+        }
+      }
+    }
+    }
+  } else {
+    // ================================ softmax warpgroups ======================================
+    if constexpr (NQ == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+    const int t = warp >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t s_addr = tmem_base + lane_addr + t * 128;
+    const uint32_t o_addr = tmem_base + lane_addr + NQ * 128 + t * D;
+    const float sl2 = p.scale_log2;
+
+    float m = -CUDART_INF_F, l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(s_full + t, j & 1, TAG_S_FULL);
+      tc_fence_after();
+      uint32_t su[128];
+      tmem_ld_x32(s_addr + 0, su + 0);
+      tmem_ld_x32(s_addr + 32, su + 32);
+      tmem_ld_x32(s_addr + 64, su + 64);
+      tmem_ld_x32(s_addr + 96, su + 96);
+      tc_wait_ld();
+      float* s = reinterpret_cast<float*>(su);
+      if (j == n_kv - 1) {
+        const int valid = k_len - j * 128;
+        if (valid < 128) {
+#pragma unroll
+          for (int c = 0; c < 128; ++c)
+            if (c >= valid) s[c] = -CUDART_INF_F;
+        }
+      }
+      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+      for (int c = 4; c < 128; c += 4) {
+        mx0 = fmaxf(mx0, s[c]);
+        mx1 = fmaxf(mx1, s[c + 1]);
+        mx2 = fmaxf(mx2, s[c + 2]);
+        mx3 = fmaxf(mx3, s[c + 3]);
+      }
+      const float m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+      if (j == 0) {
+        m = m_new;
+      } else {
+        // Lazy rescale: keep the stale max while it is within 2^8 of the new one.
+        const bool need = (m_new - m) * sl2 > 8.f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float f = need ? ex2_approx((m - m_new) * sl2) : 1.f;
+          if (need) m = m_new;
+          l *= f;
+#pragma unroll
+          for (int c0 = 0; c0 < D; c0 += 32) {
+            uint32_t ou[32];
+            tmem_ld_x32(o_addr + c0, ou);
+            tc_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 32; ++c) ou[c] = __float_as_uint(__uint_as_float(ou[c]) * f);
+            tmem_st_x32(o_addr + c0, ou);
+          }
+        }
+      }
+      const float msc = m * sl2;
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float p0 = ex2_approx(fmaf(s[c0 + c], sl2, -msc));
+          const float p1 = ex2_approx(fmaf(s[c0 + c + 1], sl2, -msc));
+          l0 += p0;
+          l1 += p1;
+          pk[c >> 1] = pack_bf16x2(p0, p1);
+        }
+        tmem_st_x16(s_addr + (c0 >> 1), pk);
+      }
+      l += l0 + l1;
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(p_full + t);
+    }
+
+    // ---- epilogue: O / l -> bf16 -> global; lse ------------------------------------------------
+    mbar_wait(o_full + t, 0, TAG_O_FULL);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const int row_g = q0 + t * 128 + row;
+    const bool valid_row = row_g < q_len;
+    __nv_bfloat16* optr = p.o + bq * p.o_sb + static_cast<int64_t>(q_base + row_g) * p.o_sl + h * p.o_sh;
+#pragma unroll
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      uint32_t ou[32];
+      tmem_ld_x32(o_addr + c0, ou);
+      tc_wait_ld();
+      if (valid_row) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(ou[c + 0]) * inv, __uint_as_float(ou[c + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(ou[c + 2]) * inv, __uint_as_float(ou[c + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(ou[c + 4]) * inv, __uint_as_float(ou[c + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(ou[c + 6]) * inv, __uint_as_float(ou[c + 7]) * inv);
+          *reinterpret_cast<uint4*>(optr + c0 + c) = w;
+        }
+      }
+    }
+    if (valid_row) p.lse[bq * p.lse_sb + h * p.lse_sh + q_base + row_g] = m * p.scale + __logf(l);
+  }
+
+  // ---- teardown ------------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <int D, int NQ>
+cudaError_t launch_one(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
+                       const AttnFwdParams& p, cudaStream_t stream) {
+  using C = FwdCfg<D, NQ>;
+  static bool configured = false;  // benign race: attribute set is idempotent
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<D, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((p.seq.Lq + NQ * 128 - 1) / (NQ * 128), p.seq.H, p.seq.nprob);
+  attn_fwd_kernel<D, NQ><<<grid, C::THREADS, C::BYTES, stream>>>(tm_q, tm_k, tm_v, p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_attn_fwd(int D, const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
+                            const AttnFwdParams& p, int q_tiles_hint, cudaStream_t stream) {
+  // One query tile per CTA when the (max) query length fits a single 128-row tile; two otherwise.
+  const bool single = (q_tiles_hint == 1) || (q_tiles_hint == 0 && p.seq.Lq <= 128);
+  if (D == 128) return single ? launch_one<128, 1>(tm_q, tm_k, tm_v, p, stream) : launch_one<128, 2>(tm_q, tm_k, tm_v, p, stream);
+  if (D == 64) return single ? launch_one<64, 1>(tm_q, tm_k, tm_v, p, stream) : launch_one<64, 2>(tm_q, tm_k, tm_v, p, stream);
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t attn_fwd_set_debug_ptr(unsigned int* ptr) { return cudaMemcpyToSymbol(g_vt_dbg, &ptr, sizeof(ptr)); }
+
+}  // namespace vt

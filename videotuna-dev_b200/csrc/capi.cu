@@ -1,0 +1,172 @@
+// capi.cu — library state, TMA tensor-map construction and the attention entry points of the C ABI.
+#include <cstring>
+#include <mutex>
+
+#include "attn_common.h"
+#include "capi_util.h"
+
+namespace vt {
+
+char* last_error_buf() {
+  static thread_local char buf[kErrBuf] = {0};
+  return buf;
+}
+
+namespace {
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct LibState {
+  std::mutex mu;
+  bool ready = false;
+  int init_rc = 0;
+  EncodeTiledFn encode = nullptr;
+  unsigned int* dbg_host = nullptr;  // pinned, mapped
+  unsigned int* dbg_dev = nullptr;
+};
+LibState g_state;
+
+int ensure_init() {
+  std::lock_guard<std::mutex> lock(g_state.mu);
+  if (g_state.ready) return g_state.init_rc;
+  int dev = 0;
+  VT_CHECK_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  VT_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(VT_ERR_UNSUPPORTED, "device %d is sm_%d%d; libb200vt needs sm_100", dev, prop.major, prop.minor);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  VT_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || fn == nullptr)
+    return fail(VT_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
+  g_state.encode = reinterpret_cast<EncodeTiledFn>(fn);
+  VT_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_state.dbg_host), 64, cudaHostAllocMapped));
+  std::memset(g_state.dbg_host, 0, 64);
+  VT_CHECK_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_state.dbg_dev), g_state.dbg_host, 0));
+  VT_CHECK_CUDA(attn_fwd_set_debug_ptr(g_state.dbg_dev));
+  VT_CHECK_CUDA(attn_bwd_set_debug_ptr(g_state.dbg_dev));
+  g_state.ready = true;
+  g_state.init_rc = 0;
+  return 0;
+}
+
+}  // namespace
+
+// 4-D tensor map over a (B, L, H, D)-logical tensor with element strides (sb, sl, sh, 1):
+// TMA dims innermost-first = (D, L, H, B); box = (box_d, box_rows, 1, 1); 128-byte swizzle; OOB reads as zero.
+int make_tmap_4d(CUtensorMap* out, const void* ptr, CUtensorMapDataType dt, int elem_bytes, int64_t D, int64_t L,
+                 int64_t H, int64_t B, const int64_t* strides /* b,l,h */, int box_d, int box_rows) {
+  VT_REQUIRE(aligned16(ptr), VT_ERR_ALIGN, "tensor base %p is not 16-byte aligned", ptr);
+  const int64_t sb = strides[0], sl = strides[1], sh = strides[2];
+  cuuint64_t dims[4] = {static_cast<cuuint64_t>(D), static_cast<cuuint64_t>(L), static_cast<cuuint64_t>(H),
+                        static_cast<cuuint64_t>(B)};
+  cuuint64_t gstr[3] = {static_cast<cuuint64_t>(sl * elem_bytes), static_cast<cuuint64_t>(sh * elem_bytes),
+                        static_cast<cuuint64_t>(sb * elem_bytes)};
+  // size-1 dims may come with arbitrary (even zero) strides from PyTorch; give them a harmless legal value
+  if (H == 1) gstr[1] = static_cast<cuuint64_t>(D * elem_bytes);
+  if (B == 1) gstr[2] = static_cast<cuuint64_t>(D * elem_bytes);
+  if (L == 1) gstr[0] = static_cast<cuuint64_t>(D * elem_bytes);
+  for (int i = 0; i < 3; ++i)
+    VT_REQUIRE(gstr[i] % 16 == 0 && gstr[i] > 0, VT_ERR_ALIGN, "stride %d (%llu bytes) must be a positive multiple of 16",
+               i, static_cast<unsigned long long>(gstr[i]));
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(box_d), static_cast<cuuint32_t>(box_rows), 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_state.encode(out, dt, 4, const_cast<void*>(ptr), dims, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VT_REQUIRE(r == CUDA_SUCCESS, VT_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (dims %lld,%lld,%lld,%lld)",
+             static_cast<int>(r), (long long)D, (long long)L, (long long)H, (long long)B);
+  return 0;
+}
+
+int lib_init() { return ensure_init(); }
+
+}  // namespace vt
+
+using namespace vt;
+
+extern "C" {
+
+int vt_version(void) { return 100; }
+
+int vt_last_error(char* buf, size_t n) {
+  const char* s = last_error_buf();
+  size_t len = std::strlen(s);
+  if (buf != nullptr && n > 0) {
+    size_t c = len < n - 1 ? len : n - 1;
+    std::memcpy(buf, s, c);
+    buf[c] = 0;
+  }
+  return static_cast<int>(len);
+}
+
+int vt_init(int device) {
+  VT_CHECK_CUDA(cudaSetDevice(device));
+  return ensure_init();
+}
+
+int vt_debug_watchdog(uint32_t out[4]) {
+  VT_REQUIRE(out != nullptr, VT_ERR_NULL, "out is NULL");
+  for (int i = 0; i < 4; ++i) out[i] = g_state.dbg_host ? g_state.dbg_host[i] : 0u;
+  return 0;
+}
+
+static int check_attn_common(int B, int H, int Lq, int Lk, int D, int num_segments, const int32_t* cu_q,
+                             const int32_t* cu_k, int max_q, int max_k) {
+  VT_REQUIRE(D == 64 || D == 128, VT_ERR_DTYPE, "head dim %d unsupported (64 or 128)", D);
+  VT_REQUIRE(B > 0 && H > 0 && Lq > 0 && Lk >= 0, VT_ERR_SHAPE, "bad shape B=%d H=%d Lq=%d Lk=%d", B, H, Lq, Lk);
+  VT_REQUIRE(H <= 65535, VT_ERR_SHAPE, "H=%d exceeds grid.y", H);
+  if (num_segments > 0) {
+    VT_REQUIRE(B == 1, VT_ERR_SHAPE, "varlen mode needs packed tensors with B == 1 (got %d)", B);
+    VT_REQUIRE(cu_q != nullptr && cu_k != nullptr, VT_ERR_NULL, "varlen mode needs cu_seqlens_q and cu_seqlens_k");
+    VT_REQUIRE(max_q > 0 && max_k >= 0, VT_ERR_SHAPE, "varlen mode needs max_seqlen_q/k");
+    VT_REQUIRE(num_segments <= 65535, VT_ERR_SHAPE, "too many segments");
+  } else {
+    VT_REQUIRE(B <= 65535, VT_ERR_SHAPE, "B=%d exceeds grid.z", B);
+  }
+  return 0;
+}
+
+int vt_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const int64_t* q_strides,
+                const int64_t* k_strides, const int64_t* v_strides, const int64_t* o_strides, int B, int H, int Lq,
+                int Lk, int D, const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k, int num_segments,
+                int max_seqlen_q, int max_seqlen_k, const int32_t* seqlens_k, float softmax_scale, void* stream) {
+  VT_REQUIRE(q && k && v && o && lse && q_strides && k_strides && v_strides && o_strides, VT_ERR_NULL,
+             "vt_attn_fwd: NULL argument");
+  if (int rc = check_attn_common(B, H, Lq, Lk, D, num_segments, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k)) return rc;
+  if (int rc = ensure_init()) return rc;
+  VT_REQUIRE(aligned16(o), VT_ERR_ALIGN, "o is not 16-byte aligned");
+  VT_REQUIRE(o_strides[0] % 8 == 0 && o_strides[1] % 8 == 0 && o_strides[2] % 8 == 0, VT_ERR_ALIGN,
+             "o strides must be multiples of 8 elements");
+  VT_REQUIRE(softmax_scale > 0.f, VT_ERR_SHAPE, "softmax_scale must be positive");
+
+  CUtensorMap tm_q, tm_k, tm_v;
+  const int64_t Lk_map = Lk > 0 ? Lk : 1;
+  if (int rc = make_tmap_4d(&tm_q, q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, D, Lq, H, B, q_strides, 64, 128)) return rc;
+  if (int rc = make_tmap_4d(&tm_k, k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, D, Lk_map, H, B, k_strides, 64, 128)) return rc;
+  if (int rc = make_tmap_4d(&tm_v, v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, D, Lk_map, H, B, v_strides, 64, 128)) return rc;
+
+  AttnFwdParams p{};
+  p.seq.cu_q = num_segments > 0 ? cu_seqlens_q : nullptr;
+  p.seq.cu_k = num_segments > 0 ? cu_seqlens_k : nullptr;
+  p.seq.seqlens_k = num_segments > 0 ? nullptr : seqlens_k;
+  p.seq.Lq = num_segments > 0 ? max_seqlen_q : Lq;
+  p.seq.Lk = num_segments > 0 ? max_seqlen_k : Lk;
+  p.seq.H = H;
+  p.seq.nprob = num_segments > 0 ? num_segments : B;
+  p.o = static_cast<__nv_bfloat16*>(o);
+  p.lse = lse;
+  p.o_sb = o_strides[0];
+  p.o_sl = o_strides[1];
+  p.o_sh = o_strides[2];
+  p.lse_sb = static_cast<int64_t>(H) * Lq;
+  p.lse_sh = Lq;
+  p.scale = softmax_scale;
+  p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  VT_CHECK_CUDA(launch_attn_fwd(D, tm_q, tm_k, tm_v, p, 0, static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+}  // extern "C"

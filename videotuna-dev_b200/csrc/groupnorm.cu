@@ -1,0 +1,257 @@
+// groupnorm.cu — GroupNorm(G) [+ SiLU] over (N, C, S) tensors with fp32 statistics, forward and backward.
+// Replaces lvdm GroupNormSpecific + nn.SiLU (videotuna/models/lvdm/modules/utils.py:192-203,
+// networks/openaimodel3d.py:229-255) and the `norm` of Spatial/TemporalTransformer (attention.py:376-392,475-519).
+//
+// One CTA per (sample, group): the group's (C/G)*S elements are contiguous in memory. Pass 1 reads the slab and
+// reduces sum / sum of squares (Welford-free: shifted by the first element for stability); pass 2 re-reads it (an
+// L2 hit: slabs are 50-400 KB, far below the 126 MB L2), normalises, applies SiLU and writes. DRAM traffic is therefore
+// 4 B/elem (bf16) although the kernel is two-pass.
+#include <cuda_bf16.h>
+
+#include "capi_util.h"
+
+namespace vt {
+namespace {
+
+constexpr int GN_THREADS = 512;
+
+template <typename T>
+struct Io;
+template <>
+struct Io<float> {
+  static constexpr int VEC = 4;
+  __device__ static void load(const float* p, float* f) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  __device__ static void store(float* p, const float* f) { *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]); }
+  __device__ static float ld1(const float* p) { return *p; }
+  __device__ static void st1(float* p, float v) { *p = v; }
+};
+template <>
+struct Io<__nv_bfloat16> {
+  static constexpr int VEC = 8;
+  __device__ static void load(const __nv_bfloat16* p, float* f) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __bfloat1622float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+  __device__ static void store(__nv_bfloat16* p, const float* f) {
+    uint4 u;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = u;
+  }
+  __device__ static float ld1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  __device__ static void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
+};
+
+template <int NV>
+__device__ __forceinline__ void cta_sum(float* v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = GN_THREADS / 32;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  __syncthreads();
+  if (lane == 0)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[i * NW + warp] = v[i];
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float t = lane < NW ? red[i * NW + lane] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    v[i] = t;
+  }
+}
+
+__device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
+__device__ __forceinline__ float dsilu_f(float z) {
+  const float s = 1.f / (1.f + __expf(-z));
+  return s * (1.f + z * (1.f - s));
+}
+
+// `vec_ok`: S is a multiple of the vector width and the base is 16-byte aligned -> vector path; else scalar path.
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS)
+groupnorm_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, float* __restrict__ mean_out,
+                     float* __restrict__ rstd_out, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     int C, int S, int G, float eps, int apply_silu, int vec_ok) {
+  __shared__ float red[2 * (GN_THREADS / 32)];
+  constexpr int VEC = Io<T>::VEC;
+  const int n = blockIdx.y, g = blockIdx.x;
+  const int cpg = C / G;
+  const size_t base = (static_cast<size_t>(n) * C + static_cast<size_t>(g) * cpg) * S;
+  const int count = cpg * S;
+  const T* xs = x + base;
+  T* ys = y + base;
+  const float shiftv = Io<T>::ld1(xs);  // shifted sums: avoids cancellation when |mean| >> std
+
+  float acc[2] = {0.f, 0.f};
+  if (vec_ok) {
+    for (int i = threadIdx.x * VEC; i < count; i += GN_THREADS * VEC) {
+      float f[VEC];
+      Io<T>::load(xs + i, f);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float d = f[k] - shiftv;
+        acc[0] += d;
+        acc[1] += d * d;
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < count; i += GN_THREADS) {
+      const float d = Io<T>::ld1(xs + i) - shiftv;
+      acc[0] += d;
+      acc[1] += d * d;
+    }
+  }
+  cta_sum<2>(acc, red);
+  const float inv = 1.f / count;
+  const float md = acc[0] * inv;
+  const float var = fmaxf(acc[1] * inv - md * md, 0.f);
+  const float mean = md + shiftv;
+  const float rstd = rsqrtf(var + eps);
+  if (threadIdx.x == 0) {
+    if (mean_out) mean_out[n * G + g] = mean;
+    if (rstd_out) rstd_out[n * G + g] = rstd;
+  }
+  if (vec_ok) {
+    for (int i = threadIdx.x * VEC; i < count; i += GN_THREADS * VEC) {
+      const int c = g * cpg + i / S;  // a vector never straddles channels because S % VEC == 0
+      const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+      const float a = rstd * ga, bsh = be - mean * a;
+      float f[VEC];
+      Io<T>::load(xs + i, f);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float z = fmaf(f[k], a, bsh);
+        f[k] = apply_silu ? silu_f(z) : z;
+      }
+      Io<T>::store(ys + i, f);
+    }
+  } else {
+    for (int i = threadIdx.x; i < count; i += GN_THREADS) {
+      const int c = g * cpg + i / S;
+      const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+      const float z = (Io<T>::ld1(xs + i) - mean) * rstd * ga + be;
+      Io<T>::st1(ys + i, apply_silu ? silu_f(z) : z);
+    }
+  }
+}
+
+// z = xh*gamma + beta; y = silu(z) or z; gz = dy * silu'(z); gh = gz * gamma
+// dx = rstd * (gh - mean_g(gh) - xh * mean_g(gh * xh)); dgamma[c] += sum gz*xh; dbeta[c] += sum gz
+template <typename T>
+__global__ void __launch_bounds__(GN_THREADS)
+groupnorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean_in,
+                     const float* __restrict__ rstd_in, T* __restrict__ dx, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, float* __restrict__ dgamma, float* __restrict__ dbeta, int C,
+                     int S, int G, int apply_silu) {
+  __shared__ float red[2 * (GN_THREADS / 32)];
+  const int n = blockIdx.y, g = blockIdx.x;
+  const int cpg = C / G;
+  const size_t base = (static_cast<size_t>(n) * C + static_cast<size_t>(g) * cpg) * S;
+  const float mean = mean_in[n * G + g], rstd = rstd_in[n * G + g];
+  float tot[2] = {0.f, 0.f};
+  // pass 1: per-channel sums (also the group sums)
+  for (int cc = 0; cc < cpg; ++cc) {
+    const int c = g * cpg + cc;
+    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    const T* xs = x + base + static_cast<size_t>(cc) * S;
+    const T* ds = dy + base + static_cast<size_t>(cc) * S;
+    float a[2] = {0.f, 0.f};
+    for (int i = threadIdx.x; i < S; i += GN_THREADS) {
+      const float xh = (Io<T>::ld1(xs + i) - mean) * rstd;
+      float gz = Io<T>::ld1(ds + i);
+      if (apply_silu) gz *= dsilu_f(xh * ga + be);
+      a[0] += gz;
+      a[1] += gz * xh;
+    }
+    cta_sum<2>(a, red);
+    if (threadIdx.x == 0) {
+      if (dbeta) atomicAdd(dbeta + c, a[0]);
+      if (dgamma) atomicAdd(dgamma + c, a[1]);
+    }
+    tot[0] += a[0] * ga;
+    tot[1] += a[1] * ga;
+  }
+  const float inv = 1.f / (cpg * S);
+  const float m1 = tot[0] * inv, m2 = tot[1] * inv;
+  // pass 2
+  for (int cc = 0; cc < cpg; ++cc) {
+    const int c = g * cpg + cc;
+    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    const T* xs = x + base + static_cast<size_t>(cc) * S;
+    const T* ds = dy + base + static_cast<size_t>(cc) * S;
+    T* os = dx + base + static_cast<size_t>(cc) * S;
+    for (int i = threadIdx.x; i < S; i += GN_THREADS) {
+      const float xh = (Io<T>::ld1(xs + i) - mean) * rstd;
+      float gz = Io<T>::ld1(ds + i);
+      if (apply_silu) gz *= dsilu_f(xh * ga + be);
+      Io<T>::st1(os + i, rstd * (gz * ga - m1 - xh * m2));
+    }
+  }
+}
+
+}  // namespace
+}  // namespace vt
+
+using namespace vt;
+
+extern "C" {
+
+int vt_groupnorm_silu_fwd(const void* x, void* y, float* mean, float* rstd, const float* gamma, const float* beta,
+                          int N, int C, int S, int G, float eps, int apply_silu, int dtype, void* stream) {
+  VT_REQUIRE(x && y, VT_ERR_NULL, "vt_groupnorm_silu_fwd: NULL argument");
+  VT_REQUIRE(N > 0 && C > 0 && S > 0 && G > 0 && C % G == 0, VT_ERR_SHAPE, "bad shape N=%d C=%d S=%d G=%d", N, C, S, G);
+  VT_REQUIRE(N <= 65535, VT_ERR_SHAPE, "N=%d exceeds grid.y", N);
+  VT_REQUIRE(static_cast<long long>(C / G) * S < (1LL << 31), VT_ERR_SHAPE, "group too large");
+  VT_REQUIRE(dtype == 0 || dtype == 1, VT_ERR_DTYPE, "dtype %d (0=bf16, 1=fp32)", dtype);
+  auto st = static_cast<cudaStream_t>(stream);
+  dim3 grid(G, N);
+  if (dtype == 0) {
+    const int vec_ok = (S % 8 == 0) && aligned16(x) && aligned16(y);
+    groupnorm_fwd_kernel<__nv_bfloat16><<<grid, GN_THREADS, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), mean, rstd, gamma, beta, C, S, G, eps,
+        apply_silu, vec_ok);
+  } else {
+    const int vec_ok = (S % 4 == 0) && aligned16(x) && aligned16(y);
+    groupnorm_fwd_kernel<float><<<grid, GN_THREADS, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(y), mean,
+                                                             rstd, gamma, beta, C, S, G, eps, apply_silu, vec_ok);
+  }
+  VT_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int vt_groupnorm_silu_bwd(const void* dy, const void* x, const float* mean, const float* rstd, void* dx,
+                          const float* gamma, const float* beta, float* dgamma, float* dbeta, int N, int C, int S, int G,
+                          int apply_silu, int dtype, void* stream) {
+  VT_REQUIRE(dy && x && mean && rstd && dx, VT_ERR_NULL, "vt_groupnorm_silu_bwd: NULL argument");
+  VT_REQUIRE(N > 0 && C > 0 && S > 0 && G > 0 && C % G == 0, VT_ERR_SHAPE, "bad shape N=%d C=%d S=%d G=%d", N, C, S, G);
+  VT_REQUIRE(N <= 65535, VT_ERR_SHAPE, "N=%d exceeds grid.y", N);
+  VT_REQUIRE(dtype == 0 || dtype == 1, VT_ERR_DTYPE, "dtype %d (0=bf16, 1=fp32)", dtype);
+  auto st = static_cast<cudaStream_t>(stream);
+  dim3 grid(G, N);
+  if (dtype == 0)
+    groupnorm_bwd_kernel<__nv_bfloat16><<<grid, GN_THREADS, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), mean, rstd,
+        static_cast<__nv_bfloat16*>(dx), gamma, beta, dgamma, dbeta, C, S, G, apply_silu);
+  else
+    groupnorm_bwd_kernel<float><<<grid, GN_THREADS, 0, st>>>(static_cast<const float*>(dy), static_cast<const float*>(x),
+                                                             mean, rstd, static_cast<float*>(dx), gamma, beta, dgamma,
+                                                             dbeta, C, S, G, apply_silu);
+  VT_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,301 @@
+"""Generate tests/golden/*.pt by running the UNMODIFIED reference code (/root/reference) on seeded CPU inputs.
+
+Run in the development container only (`python tests/golden/make_golden.py`); the GPU box has no /root/reference and
+only reads the committed fixtures. Import shims cover wheels that are absent here: colorama,
+omegaconf, diffusers — none of them takes part in the arithmetic being recorded.
+"""
+from __future__ import annotations
+
+import importlib
+import importlib.util
+import os
+import sys
+import types
+
+import torch
+
+REF = "/root/reference"
+OUT = os.path.dirname(os.path.abspath(__file__))
+SEED = 20230211  # the reference's default --seed (scripts/train_new.py:34)
+
+
+def install_shims():
+    sys.path.insert(0, REF)
+    col = types.ModuleType("colorama")
+    col.Fore = types.SimpleNamespace(**{k: "" for k in ("RED", "GREEN", "YELLOW", "BLUE", "CYAN", "MAGENTA", "WHITE", "RESET")})
+    col.Style = types.SimpleNamespace(RESET_ALL="", BRIGHT="", DIM="", NORMAL="")
+    col.init = lambda *a, **k: None
+    sys.modules.setdefault("colorama", col)
+    om = types.ModuleType("omegaconf")
+    om.DictConfig = dict
+    om.ListConfig = list
+    om.OmegaConf = type("OmegaConf", (), {})
+    sys.modules.setdefault("omegaconf", om)
+    dif = types.ModuleType("diffusers")
+    difm = types.ModuleType("diffusers.models")
+    difm.ModelMixin = torch.nn.Module
+    difc = types.ModuleType("diffusers.configuration_utils")
+    difc.ConfigMixin = object
+    difc.register_to_config = lambda f: f
+    difm.__path__ = []
+    difmu = types.ModuleType("diffusers.models.modeling_utils")
+    difmu.ModelMixin = torch.nn.Module
+    dif.models, dif.configuration_utils, difm.modeling_utils = difm, difc, difmu
+    sys.modules.setdefault("diffusers", dif)
+    sys.modules.setdefault("diffusers.models", difm)
+    sys.modules.setdefault("diffusers.models.modeling_utils", difmu)
+    sys.modules.setdefault("diffusers.configuration_utils", difc)
+
+
+def dezero(module: torch.nn.Module, gen: torch.Generator):
+    """Re-draw every all-zero parameter (zero_module / ModulateDiT / FinalLayer init) so parity is not vacuous."""
+    with torch.no_grad():
+        for p in module.parameters():
+            if p.numel() > 0 and float(p.abs().max()) == 0.0:
+                p.copy_(RN(p.shape, generator=gen) * 0.02)
+
+
+def _compact(obj):
+    """Store tensors whose values are exactly bf16-representable (inputs, weights) as bf16; keep the rest (outputs)."""
+    if isinstance(obj, torch.Tensor):
+        if obj.dtype == torch.float32 and torch.equal(obj, obj.to(torch.bfloat16).to(torch.float32)):
+            return obj.to(torch.bfloat16)
+        return obj.clone()
+    if isinstance(obj, dict):
+        return {k: _compact(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_compact(v) for v in obj)
+    return obj
+
+
+def save(name, obj):
+    path = os.path.join(OUT, name + ".pt")
+    torch.save(_compact(obj), path)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def r16(t: torch.Tensor) -> torch.Tensor:
+    """Round to bf16-representable values, keep fp32 storage: the reference then runs in fp32 on exactly the values a
+    bf16 CUDA kernel will see, so fixtures carry no input-rounding error."""
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def RN(*shape, generator=None):
+    return r16(torch.randn(*shape, generator=generator))
+
+
+def round_params(module: torch.nn.Module):
+    with torch.no_grad():
+        for p in module.parameters():
+            p.copy_(r16(p))
+        for b in module.buffers():
+            if b.is_floating_point():
+                b.copy_(r16(b))
+    return module
+
+
+def sd(module):
+    """state dict stored as bf16 (values are bf16-representable, see round_params) to keep fixtures small."""
+    return {k: (v.detach().to(torch.bfloat16) if v.is_floating_point() else v.detach().clone())
+            for k, v in module.state_dict().items()}
+
+
+def golden_lvdm(gen):
+    from videotuna.models.lvdm.modules import attention as A
+    assert not A.XFORMERS_IS_AVAILBLE
+    cases = {}
+    # spatial self-attention (ragged N), cross-attention with 77-token truncation, temporal w/ relative position + mask
+    m = round_params(A.CrossAttention(query_dim=128, context_dim=None, heads=2, dim_head=64))
+    x = RN(2, 200, 128, generator=gen)
+    cases["self"] = dict(kw=dict(query_dim=128, context_dim=None, heads=2, dim_head=64), sd=sd(m), x=x, context=None,
+                         mask=None, out=m(x).detach())
+    m = round_params(A.CrossAttention(query_dim=128, context_dim=96, heads=2, dim_head=64))
+    ctx = RN(2, 90, 96, generator=gen)  # > 77: reference truncates (attention.py:120-121)
+    cases["cross"] = dict(kw=dict(query_dim=128, context_dim=96, heads=2, dim_head=64), sd=sd(m), x=x, context=ctx,
+                          mask=None, out=m(x, context=ctx).detach())
+    m = A.CrossAttention(query_dim=128, context_dim=None, heads=2, dim_head=64, relative_position=True,
+                         temporal_length=16)
+    round_params(m)
+    xt = RN(6, 16, 128, generator=gen)
+    mask = torch.tril(torch.ones(1, 16, 16))
+    cases["temporal_relpos"] = dict(kw=dict(query_dim=128, context_dim=None, heads=2, dim_head=64,
+                                            relative_position=True, temporal_length=16), sd=sd(m), x=xt, context=None,
+                                    mask=None, out=m(xt).detach())
+    cases["temporal_relpos_causal"] = dict(kw=cases["temporal_relpos"]["kw"], sd=sd(m), x=xt, context=None, mask=mask,
+                                           out=m(xt, mask=mask.expand(6, -1, -1)).detach())
+    m = A.CrossAttention(query_dim=128, context_dim=96, heads=2, dim_head=64, img_cross_attention=True,
+                         img_cross_attention_scale=0.7)
+    round_params(m)
+    ctx2 = RN(2, 77 + 16, 96, generator=gen)
+    cases["img_cross"] = dict(kw=dict(query_dim=128, context_dim=96, heads=2, dim_head=64, img_cross_attention=True,
+                                      img_cross_attention_scale=0.7), sd=sd(m), x=x, context=ctx2, mask=None,
+                              out=m(x, context=ctx2).detach())
+    save("lvdm_cross_attention", cases)
+
+    # whole transformer wrappers (GroupNorm + permutes + LayerNorm + attention + GEGLU), de-zeroed
+    st = A.SpatialTransformer(in_channels=128, n_heads=2, d_head=64, depth=1, context_dim=96, use_linear=True,
+                              use_checkpoint=False)
+    dezero(st, gen)
+    round_params(st)
+    xs = RN(3, 128, 5, 8, generator=gen)
+    ctxs = RN(3, 77, 96, generator=gen)
+    tt = A.TemporalTransformer(in_channels=128, n_heads=2, d_head=64, depth=1, use_linear=True, use_checkpoint=False,
+                               only_self_att=True, temporal_length=16)
+    dezero(tt, gen)
+    round_params(tt)
+    xtt = RN(1, 128, 16, 3, 4, generator=gen)
+    save("lvdm_transformers", dict(
+        spatial=dict(kw=dict(in_channels=128, n_heads=2, d_head=64, depth=1, context_dim=96, use_linear=True,
+                             use_checkpoint=False), sd=sd(st), x=xs, context=ctxs, out=st(xs, ctxs).detach()),
+        temporal=dict(kw=dict(in_channels=128, n_heads=2, d_head=64, depth=1, use_linear=True, use_checkpoint=False,
+                              only_self_att=True, temporal_length=16), sd=sd(tt), x=xtt, out=tt(xtt).detach())))
+
+    from videotuna.models.lvdm.modules.utils import GroupNormSpecific
+    gn = GroupNormSpecific(32, 128)
+    with torch.no_grad():
+        gn.weight.copy_(RN(128, generator=gen))
+        gn.bias.copy_(RN(128, generator=gen))
+    round_params(gn)
+    xg = r16(RN(2, 128, 6, 10, generator=gen) * 2 + 0.5)
+    save("lvdm_groupnorm", dict(weight=gn.weight.detach().clone(), bias=gn.bias.detach().clone(), x=xg, eps=gn.eps,
+                                out=gn(xg).detach(), out_silu=torch.nn.functional.silu(gn(xg)).detach()))
+
+
+def golden_hunyuan(gen):
+    M = importlib.import_module("videotuna.models.hunyuan.hyvideo_t2v.modules.models")
+    att = importlib.import_module("videotuna.models.hunyuan.hyvideo_t2v.modules.attenion")
+    pos = importlib.import_module("videotuna.models.hunyuan.hyvideo_t2v.modules.posemb_layers")
+    nrm = importlib.import_module("videotuna.models.hunyuan.hyvideo_t2v.modules.norm_layers")
+    mod = importlib.import_module("videotuna.models.hunyuan.hyvideo_t2v.modules.modulate_layers")
+
+    B, S, H, D = 2, 150, 2, 128
+    q, k, v = (RN(B, S, H, D, generator=gen) for _ in range(3))
+    out_plain = att.attention(q, k, v, mode="torch")
+    # two-segment block-diagonal mask = what mode="flash" computes through cu_seqlens (valid text 20 of 30, img 120)
+    img_len, txt_len = 120, 30
+    text_mask = torch.zeros(B, txt_len, dtype=torch.long)
+    text_mask[0, :20] = 1
+    text_mask[1, :30] = 1
+    seg = torch.zeros(B, S, dtype=torch.long)
+    for b in range(B):
+        seg[b, img_len + int(text_mask[b].sum()):] = 1
+    mask = (seg[:, :, None] == seg[:, None, :])[:, None]
+    out_mask = att.attention(q, k, v, mode="torch", attn_mask=mask)
+    save("hunyuan_attention", dict(q=q, k=k, v=v, out_plain=out_plain, text_mask=text_mask, img_len=img_len,
+                                   attn_mask=mask, out_mask=out_mask))
+
+    rn = nrm.RMSNorm(D, elementwise_affine=True, eps=1e-6)
+    with torch.no_grad():
+        rn.weight.copy_(1 + 0.1 * RN(D, generator=gen))
+    round_params(rn)
+    cos, sin = pos.get_nd_rotary_pos_embed([16, 56, 56], (3, 4, 10), theta=256, use_real=True, theta_rescale_factor=1)
+    xq, xk = RN(1, 120, H, D, generator=gen), RN(1, 120, H, D, generator=gen)
+    rq, rk = pos.apply_rotary_emb(rn(xq), rn(xk), (cos, sin), head_first=False)
+    shift, scale, gate = (RN(B, 64, generator=gen) for _ in range(3))
+    xm = RN(B, 10, 64, generator=gen)
+    save("hunyuan_norm_rope", dict(w=rn.weight.detach().clone(), eps=1e-6, cos=cos, sin=sin, xq=xq, xk=xk,
+                                   norm_q=rn(xq).detach(), rope_q=rq.detach(), rope_k=rk.detach(), xm=xm, shift=shift,
+                                   scale=scale, gate=gate, modulated=mod.modulate(xm, shift=shift, scale=scale),
+                                   gated=mod.apply_gate(xm, gate=gate), rope_sizes=(3, 4, 10),
+                                   rope_dim_list=[16, 56, 56], theta=256))
+
+    hidden, heads = 256, 2
+    dbl = M.MMDoubleStreamBlock(hidden, heads, mlp_width_ratio=1.0, qk_norm=True, qk_norm_type="rms", qkv_bias=True)
+    sgl = M.MMSingleStreamBlock(hidden, heads, mlp_width_ratio=1.0, qk_norm=True, qk_norm_type="rms")
+    dezero(dbl, gen)
+    dezero(sgl, gen)
+    with torch.no_grad():
+        for mm in (dbl, sgl):
+            for n_, p_ in mm.named_parameters():
+                if n_.endswith("norm.weight"):
+                    p_.copy_(1 + 0.1 * RN(p_.shape, generator=gen))
+    round_params(dbl)
+    round_params(sgl)
+    # patch the name the blocks call so CPU runs take mode="torch" with the same segment mask flash would use
+    img = RN(1, 120, hidden, generator=gen)
+    txt = RN(1, 30, hidden, generator=gen)
+    vec = RN(1, hidden, generator=gen)
+    cu = torch.tensor([0, 140, 150], dtype=torch.int32)
+    segm = torch.zeros(150, dtype=torch.long)
+    segm[140:] = 1
+    bmask = (segm[:, None] == segm[None, :])[None, None]
+    orig = M.attention
+    M.attention = lambda q_, k_, v_, **kw: orig(q_, k_, v_, mode="torch", attn_mask=bmask)
+    try:
+        img_o, txt_o = dbl(img, txt, vec, cu_seqlens_q=cu, cu_seqlens_kv=cu, max_seqlen_q=150, max_seqlen_kv=150,
+                           freqs_cis=(cos, sin))
+        x_cat = torch.cat([img, txt], 1)
+        sgl_o = sgl(x_cat, vec, 30, cu_seqlens_q=cu, cu_seqlens_kv=cu, max_seqlen_q=150, max_seqlen_kv=150,
+                    freqs_cis=(cos, sin))
+    finally:
+        M.attention = orig
+    save("hunyuan_blocks", dict(hidden=hidden, heads=heads, mlp_width_ratio=1.0, dbl_sd=sd(dbl), sgl_sd=sd(sgl), img=img,
+                                txt=txt, vec=vec, cu_seqlens=cu, cos=cos, sin=sin, img_out=img_o.detach(),
+                                txt_out=txt_o.detach(), single_out=sgl_o.detach()))
+
+
+def golden_wan(gen):
+    pkg = types.ModuleType("wan_ref_modules")
+    pkg.__path__ = [os.path.join(REF, "videotuna/models/wan/wan/modules")]
+    sys.modules["wan_ref_modules"] = pkg
+    attn = importlib.import_module("wan_ref_modules.attention")
+    model = importlib.import_module("wan_ref_modules.model")
+
+    B, L, N, D = 2, 60, 2, 128
+    q, k, v = (RN(B, L, N, D, generator=gen) for _ in range(3))
+    # flash_attn is importable in this image but needs CUDA; clear the reference's own availability flags so that
+    # attention() takes its SDPA fallback branch (attention.py:164-179), as it would on a machine without flash-attn.
+    attn.FLASH_ATTN_2_AVAILABLE = False
+    attn.FLASH_ATTN_3_AVAILABLE = False
+    out = attn.attention(q, k, v)
+    freqs = torch.cat([model.rope_params(1024, D - 4 * (D // 6)), model.rope_params(1024, 2 * (D // 6)),
+                       model.rope_params(1024, 2 * (D // 6))], dim=1)
+    grid = torch.tensor([[3, 4, 5], [2, 4, 5]])
+    roped = model.rope_apply(q, grid, freqs)
+    rms = model.WanRMSNorm(N * D, eps=1e-6)
+    with torch.no_grad():
+        rms.weight.copy_(1 + 0.1 * RN(N * D, generator=gen))
+    round_params(rms)
+    xr = RN(B, L, N * D, generator=gen)
+    ln = model.WanLayerNorm(N * D, eps=1e-6)
+    save("wan_ops", dict(q=q, k=k, v=v, sdpa_out=out,
+                         grid=grid, roped=roped, rms_w=rms.weight.detach().clone(), xr=xr, rms_out=rms(xr).detach(),
+                         ln_out=ln(xr).detach()))
+
+    # one WanAttentionBlock; flash_attention rebound to the reference's own SDPA fallback body (needs no CUDA)
+    def sdpa_flash(q, k, v, q_lens=None, k_lens=None, dropout_p=0.0, softmax_scale=None, q_scale=None, causal=False,
+                   window_size=(-1, -1), deterministic=False, dtype=torch.bfloat16, version=None):
+        o = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2))
+        return o.transpose(1, 2).contiguous()
+
+    model.flash_attention = sdpa_flash
+    dim, heads, ffn = 256, 2, 512
+    blk = model.WanAttentionBlock("t2v_cross_attn", dim, ffn, heads, window_size=(-1, -1), qk_norm=True,
+                                  cross_attn_norm=True, eps=1e-6)
+    dezero(blk, gen)
+    with torch.no_grad():
+        blk.modulation.copy_(RN(1, 6, dim, generator=gen) / dim ** 0.5)
+    round_params(blk)
+    Lb = 3 * 4 * 5
+    x = RN(1, Lb, dim, generator=gen)
+    e = r16(RN(1, 6, dim, generator=gen) * 0.1)
+    ctx = RN(1, 20, dim, generator=gen)
+    freqs_b = torch.cat([model.rope_params(1024, 128 - 4 * (128 // 6)), model.rope_params(1024, 2 * (128 // 6)),
+                         model.rope_params(1024, 2 * (128 // 6))], dim=1)
+    y = blk(x, e, torch.tensor([Lb]), torch.tensor([[3, 4, 5]]), freqs_b, ctx, None)
+    save("wan_block", dict(dim=dim, heads=heads, ffn=ffn, sd=sd(blk), x=x, e=e, context=ctx, grid=torch.tensor([[3, 4, 5]]),
+                           out=y.detach()))
+
+
+def main():
+    install_shims()
+    torch.manual_seed(SEED)
+    gen = torch.Generator().manual_seed(SEED)
+    torch.set_grad_enabled(False)
+    golden_lvdm(gen)
+    golden_hunyuan(gen)
+    golden_wan(gen)
+
+
+if __name__ == "__main__":
+    main()

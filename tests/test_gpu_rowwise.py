@@ -1,0 +1,171 @@
+"""Memory-bound kernels (LN+modulate, gated residual, QK-RMSNorm+RoPE, GroupNorm+SiLU) vs the CPU oracle, fwd + bwd.
+Tolerances: bf16 outputs max|y-ref|/max|ref| <= 2e-2 (observed ~4e-3 = bf16 rounding); gradient cosine >= 0.999."""
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import ref_ops as R
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+COS = 0.999
+
+
+def _r(shape, seed, scale=1.0, shift=0.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale + shift).to(torch.bfloat16)
+
+
+def _leaf(t, dev=None, dtype=None):
+    t = t.detach().clone()
+    if dtype is not None:
+        t = t.to(dtype)
+    if dev is not None:
+        t = t.to(dev)
+    return t.requires_grad_(True)
+
+
+@pytest.mark.parametrize("B,L,C,affine,mod", [(2, 37, 3072, False, True), (1, 130, 5120, False, True),
+                                              (3, 50, 320, True, False), (2, 9, 1920, True, True),
+                                              (1, 64, 1280, True, False)])
+def test_ln_modulate_fwd_bwd(B, L, C, affine, mod):
+    import b200vt.functional as Fn
+    x = _r((B, L, C), 1, 2.0, 0.3)
+    gamma = _r((C,), 2, 0.2, 1.0).float() if affine else None
+    beta = _r((C,), 3, 0.2).float() if affine else None
+    scale = _r((B, C), 4, 0.3).float() if mod else None
+    shift = _r((B, C), 5, 0.3).float() if mod else None
+    dy = _r((B, L, C), 6)
+    # oracle (fp32 CPU)
+    xr = _leaf(x, dtype=torch.float32)
+    pr = [None if t is None else _leaf(t) for t in (gamma, beta, scale, shift)]
+    yr = R.ln_modulate(xr, pr[0], pr[1], pr[2], pr[3], 1e-6)
+    yr.backward(dy.float())
+    # CUDA
+    xc = _leaf(x, "cuda")
+    pc = [None if t is None else _leaf(t, "cuda") for t in (gamma, beta, scale, shift)]
+    yc = Fn.ln_modulate(xc, shift=pc[3], scale=pc[2], weight=pc[0], bias=pc[1], eps=1e-6)
+    yc.backward(dy.cuda())
+    assert R.max_rel_err(yc.float().cpu(), yr) < TOL
+    assert R.cosine(xc.grad.float().cpu(), xr.grad) > COS
+    assert R.max_rel_err(xc.grad.float().cpu(), xr.grad) < TOL
+    for a, b_ in zip(pc, pr):
+        if a is not None:
+            assert R.cosine(a.grad.cpu(), b_.grad) > COS
+            assert R.max_rel_err(a.grad.cpu(), b_.grad) < TOL
+
+
+@pytest.mark.parametrize("B,L,C,gated", [(2, 33, 3072, True), (1, 77, 5120, True), (2, 10, 320, False)])
+def test_gate_residual_fwd_bwd(B, L, C, gated):
+    import b200vt.functional as Fn
+    x, br, dy = _r((B, L, C), 1), _r((B, L, C), 2), _r((B, L, C), 3)
+    gate = _r((B, C), 4).float() if gated else None
+    xr, brr = _leaf(x, dtype=torch.float32), _leaf(br, dtype=torch.float32)
+    gr = None if gate is None else _leaf(gate)
+    yr = R.gate_residual(xr, brr, gr)
+    yr.backward(dy.float())
+    xc, brc = _leaf(x, "cuda"), _leaf(br, "cuda")
+    gc = None if gate is None else _leaf(gate, "cuda")
+    yc = Fn.gate_residual(xc, brc, gc)
+    yc.backward(dy.cuda())
+    assert R.max_rel_err(yc.float().cpu(), yr) < TOL
+    assert R.max_rel_err(xc.grad.float().cpu(), xr.grad) < TOL
+    assert R.max_rel_err(brc.grad.float().cpu(), brr.grad) < TOL
+    if gated:
+        assert R.cosine(gc.grad.cpu(), gr.grad) > COS and R.max_rel_err(gc.grad.cpu(), gr.grad) < TOL
+
+
+def _rope_ref(x, w, cos, sin, per_head, eps):
+    """oracle: hunyuan RMSNorm + apply_rotary_emb (per head) or wan RMSNorm over H*D + rope, in fp32."""
+    B, L, H, D = x.shape
+    if w is None:
+        n = x
+    elif per_head:
+        n = R.hunyuan_rmsnorm(x, w, eps)
+    else:
+        n = R.wan_rmsnorm(x.reshape(B, L, H * D), w, eps).view(B, L, H, D)
+    if cos is None:
+        return n
+    Lr = cos.shape[0]
+    return torch.cat([R.hunyuan_apply_rotary_emb(n[:, :Lr], cos, sin), n[:, Lr:]], dim=1)
+
+
+@pytest.mark.parametrize("B,L,H,D,per_head,use_w,Lr", [(1, 150, 3, 128, True, True, 120), (2, 70, 24, 128, True, True, 70),
+                                                       (1, 61, 5, 128, False, True, 60), (2, 33, 2, 64, True, False, 33),
+                                                       (1, 40, 40, 128, False, True, 40), (1, 20, 2, 128, True, True, 0)])
+def test_qk_rmsnorm_rope_fwd_bwd(B, L, H, D, per_head, use_w, Lr):
+    import b200vt.functional as Fn
+    x = _r((B, L, H, D), 1, 1.5)
+    w = (_r((D if per_head else H * D,), 2, 0.1, 1.0).float()) if use_w else None
+    cos = sin = None
+    if Lr > 0:
+        ang = torch.rand(Lr, D // 2, generator=torch.Generator().manual_seed(3)) * 6.28
+        cos, sin = ang.cos().repeat_interleave(2, 1), ang.sin().repeat_interleave(2, 1)
+    dy = _r((B, L, H, D), 4)
+    xr = _leaf(x, dtype=torch.float32)
+    wr = None if w is None else _leaf(w)
+    yr = _rope_ref(xr, wr, cos, sin, per_head, 1e-6)
+    yr.backward(dy.float())
+    xc = _leaf(x, "cuda")
+    wc = None if w is None else _leaf(w, "cuda")
+    yc = Fn.qk_rmsnorm_rope(xc, wc, None if cos is None else cos.cuda(), None if sin is None else sin.cuda(),
+                            per_head=per_head, eps=1e-6)
+    yc.backward(dy.cuda())
+    assert R.max_rel_err(yc.float().cpu(), yr) < TOL
+    assert R.cosine(xc.grad.float().cpu(), xr.grad) > COS and R.max_rel_err(xc.grad.float().cpu(), xr.grad) < TOL
+    if w is not None:
+        assert R.cosine(wc.grad.cpu(), wr.grad) > COS and R.max_rel_err(wc.grad.cpu(), wr.grad) < TOL
+
+
+def test_qk_rmsnorm_rope_strided_qkv_view_and_golden():
+    import b200vt.functional as Fn
+    g = load_golden("hunyuan_norm_rope")
+    out = Fn.qk_rmsnorm_rope(g["xq"].cuda(), g["w"].cuda(), g["cos"].cuda(), g["sin"].cuda(), per_head=True, eps=g["eps"])
+    assert R.max_rel_err(out.float().cpu(), g["rope_q"]) < TOL
+    qkv = _r((1, 90, 3, 4, 128), 7).cuda()
+    q = qkv.unbind(2)[1]
+    w = torch.ones(128, device="cuda")
+    ref = R.hunyuan_rmsnorm(q.float().cpu(), torch.ones(128), 1e-6)
+    assert R.max_rel_err(Fn.qk_rmsnorm_rope(q, w, None, None).float().cpu(), ref) < TOL
+
+
+def test_wan_rope_golden():
+    import b200vt.functional as Fn
+    g = load_golden("wan_ops")
+    freqs = R.wan_freqs_table(128)
+    cos, sin = R.wan_rope_cos_sin(g["grid"][0].tolist(), freqs)
+    out = Fn.qk_rmsnorm_rope(g["q"][:1].cuda(), None, cos.cuda(), sin.cuda())
+    assert R.max_rel_err(out.float().cpu(), g["roped"][:1]) < TOL
+    y = Fn.qk_rmsnorm_rope(g["xr"].view(2, 60, 2, 128).cuda(), g["rms_w"].cuda(), None, None, per_head=False)
+    assert R.max_rel_err(y.float().cpu().view(2, 60, 256), g["rms_out"]) < TOL
+    y = Fn.ln_modulate(g["xr"].cuda(), eps=1e-6)
+    assert R.max_rel_err(y.float().cpu(), g["ln_out"]) < TOL
+
+
+@pytest.mark.parametrize("N,C,sp,dt,silu", [(4, 320, (40, 64), torch.bfloat16, True), (2, 640, (20, 32), torch.float32, True),
+                                             (3, 1280, (5, 8), torch.bfloat16, False), (2, 128, (3, 7), torch.float32, True),
+                                             (1, 320, (16, 9, 5), torch.bfloat16, True)])
+def test_groupnorm_silu_fwd_bwd(N, C, sp, dt, silu):
+    import b200vt.functional as Fn
+    x = (_r((N, C) + sp, 1, 2.0, 0.7)).to(dt)
+    gamma, beta = _r((C,), 2, 0.3, 1.0).float(), _r((C,), 3, 0.3).float()
+    dy = _r((N, C) + sp, 4).to(dt)
+    xr, gr, br = _leaf(x, dtype=torch.float32), _leaf(gamma), _leaf(beta)
+    yr = R.groupnorm_silu(xr, gr, br, 32, 1e-5, silu)
+    yr.backward(dy.float())
+    xc, gc, bc = _leaf(x, "cuda"), _leaf(gamma, "cuda"), _leaf(beta, "cuda")
+    yc = Fn.groupnorm_silu(xc, gc, bc, 32, 1e-5, silu)
+    yc.backward(dy.cuda())
+    tol = TOL if dt == torch.bfloat16 else 1e-4
+    assert R.max_rel_err(yc.float().cpu(), yr) < tol
+    assert R.cosine(xc.grad.float().cpu(), xr.grad) > COS and R.max_rel_err(xc.grad.float().cpu(), xr.grad) < tol * 2
+    assert R.max_rel_err(gc.grad.cpu(), gr.grad) < tol * 2 and R.max_rel_err(bc.grad.cpu(), br.grad) < tol * 2
+
+
+def test_groupnorm_golden():
+    import b200vt.functional as Fn
+    g = load_golden("lvdm_groupnorm")
+    y = Fn.groupnorm_silu(g["x"].float().cuda(), g["weight"].cuda(), g["bias"].cuda(), 32, g["eps"], True)
+    assert R.max_rel_err(y.cpu(), g["out_silu"]) < 1e-4
+    y = Fn.groupnorm_silu(g["x"].cuda(), g["weight"].cuda(), g["bias"].cuda(), 32, g["eps"], False)
+    assert R.max_rel_err(y.float().cpu(), g["out"]) < TOL

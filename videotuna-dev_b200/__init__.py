@@ -1,0 +1,12 @@
+"""b200vt — B200-native (sm_100a) attention hot path for VideoTuna-style video denoisers.
+
+Public surface (mirrors the reference callables):
+    b200vt.ops        torch.library ops over the C ABI (libb200vt.so)
+    b200vt.functional reference-signature functions: hunyuan `attention`, wan `flash_attention`,
+                      lvdm `CrossAttention.forward`, modulate/gate/norm helpers
+    b200vt.sp         Ulysses sequence parallelism (NCCL all-to-all)
+    b200vt.patch      patch_videotuna(): rebinds the reference's hooks to the functions above
+
+There is no CPU fallback and no alternative backend: calling an op without the CUDA library raises.
+"""
+__version__ = "0.1.0"

@@ -1,0 +1,207 @@
+"""Reference-signature functions over the b200vt ops (host-side mirror of the reference's Python plugin points).
+
+Each public function keeps the name, argument meaning and return layout of the reference callable it replaces, so the
+parity tests read like calls into VideoTuna. Anything the CUDA path does not implement raises `Unsupported`; the
+patch layer (patch.py) catches that and routes the call to the untouched reference function — never to a CPU kernel of
+our own.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import ops
+
+
+class Unsupported(NotImplementedError):
+    """The requested variant is outside the CUDA path; callers fall back to the reference implementation."""
+
+
+_HALF = (torch.bfloat16,)
+
+
+def _require(cond: bool, why: str):
+    if not cond:
+        raise Unsupported(why)
+
+
+def supported_qkv(q: Tensor, k: Tensor, v: Tensor) -> bool:
+    return (q.is_cuda and q.dtype in _HALF and k.dtype == q.dtype and v.dtype == q.dtype
+            and q.shape[-1] in (64, 128) and k.shape[-1] == q.shape[-1] and v.shape[-1] == q.shape[-1])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# generic (B, L, H, D) attention
+# ---------------------------------------------------------------------------------------------------------------------
+def attention_blhd(q: Tensor, k: Tensor, v: Tensor, softmax_scale: Optional[float] = None,
+                   k_lens: Optional[Tensor] = None, cu_seqlens_q: Optional[Tensor] = None,
+                   cu_seqlens_k: Optional[Tensor] = None, max_seqlen_q: Optional[int] = None,
+                   max_seqlen_k: Optional[int] = None, return_lse: bool = False):
+    """softmax(q k^T * scale) v for q (B,Lq,H,D), k/v (B,Lk,H,D) bf16 CUDA tensors -> (B,Lq,H,D).
+
+    k_lens (B,) int32: keys >= k_lens[b] are masked (fixed mode). cu_seqlens_*: packed varlen mode, B must be 1.
+    """
+    _require(supported_qkv(q, k, v), f"attention needs CUDA bf16 with head dim 64/128, got {q.dtype} {tuple(q.shape)}")
+    _require(q.shape[2] == k.shape[2] == v.shape[2], "grouped-query attention is not on this path")
+    scale = 1.0 / math.sqrt(q.shape[-1]) if softmax_scale is None else float(softmax_scale)
+    if cu_seqlens_q is not None:
+        cu_seqlens_q = cu_seqlens_q.to(device=q.device, dtype=torch.int32)
+        cu_seqlens_k = cu_seqlens_q if cu_seqlens_k is None else cu_seqlens_k.to(device=q.device, dtype=torch.int32)
+        mq = int(max_seqlen_q) if max_seqlen_q is not None else q.shape[1]
+        mk = int(max_seqlen_k) if max_seqlen_k is not None else k.shape[1]
+        o, lse = ops.attn_fwd(q, k, v, cu_seqlens_q, cu_seqlens_k, None, mq, mk, scale)
+    else:
+        if k_lens is not None:
+            k_lens = k_lens.to(device=q.device, dtype=torch.int32)
+        o, lse = ops.attn_fwd(q, k, v, None, None, k_lens, q.shape[1], k.shape[1], scale)
+    return (o, lse) if return_lse else o
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# HunyuanVideo: attention(q,k,v,mode,...)  (videotuna/models/hunyuan/hyvideo_t2v/modules/attenion.py:60-156)
+# ---------------------------------------------------------------------------------------------------------------------
+def hunyuan_attention(q, k, v, mode="flash", drop_rate=0, attn_mask=None, causal=False, cu_seqlens_q=None,
+                      cu_seqlens_kv=None, max_seqlen_q=None, max_seqlen_kv=None, batch_size=1):
+    """Same signature and return layout ([b, s, a*d]) as the reference `attention`.
+
+    mode="flash": packed two-segment varlen semantics of flash_attn_varlen_func via cu_seqlens (attenion.py:107-120).
+    mode="torch": dense attention; attn_mask / causal / dropout are not on the CUDA path (raise Unsupported).
+    mode="vanilla": never on the CUDA path (it applies dropout with train=True unconditionally, attenion.py:148).
+    """
+    _require(mode in ("flash", "torch"), f"mode {mode!r} stays on the reference path")
+    _require(not causal and (drop_rate == 0 or drop_rate == 0.0), "causal / dropout stay on the reference path")
+    b, s, a, d = q.shape
+    if mode == "torch":
+        _require(attn_mask is None, "attn_mask stays on the reference path")
+        out = attention_blhd(q, k, v)
+        return out.reshape(b, s, a * d)
+    # flash: q is [b, s, a, d] flattened to [(b s), a, d] by the reference's pre_attn_layout (attenion.py:22-25)
+    _require(cu_seqlens_q is not None and cu_seqlens_kv is not None, "mode='flash' needs cu_seqlens")
+    s1 = k.shape[1]
+    qp, kp, vp = q.reshape(1, b * s, a, d), k.reshape(1, b * s1, a, d), v.reshape(1, b * s1, a, d)
+    out = attention_blhd(qp, kp, vp, cu_seqlens_q=cu_seqlens_q, cu_seqlens_k=cu_seqlens_kv,
+                         max_seqlen_q=max_seqlen_q, max_seqlen_k=max_seqlen_kv)
+    return out.view(batch_size, max_seqlen_q, a, d).reshape(batch_size, max_seqlen_q, a * d)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Wan2.1: flash_attention(...)  (videotuna/models/wan/wan/modules/attention.py:24-130)
+# ---------------------------------------------------------------------------------------------------------------------
+def wan_flash_attention(q, k, v, q_lens=None, k_lens=None, dropout_p=0., softmax_scale=None, q_scale=None,
+                        causal=False, window_size=(-1, -1), deterministic=False, dtype=torch.bfloat16, version=None):
+    """Same signature as the reference. q [B,Lq,N,C], k/v [B,Lk,N,C]; non-half inputs are cast to `dtype`
+    (attention.py:59-83); the result comes back in q's original dtype (attention.py:57,130)."""
+    _require(dtype == torch.bfloat16, "only bfloat16 compute is on the CUDA path")
+    _require(not causal and tuple(window_size) == (-1, -1) and dropout_p == 0, "causal/window/dropout: reference path")
+    _require(q.is_cuda, "CPU tensors stay on the reference path")
+    out_dtype = q.dtype
+
+    def half(x):
+        return x if x.dtype == torch.bfloat16 else x.to(dtype)
+
+    qh, kh, vh = half(q), half(k), half(v)
+    _require(qh.shape[-1] in (64, 128), f"head dim {qh.shape[-1]} stays on the reference path")
+    scale = 1.0 / math.sqrt(qh.shape[-1]) if softmax_scale is None else float(softmax_scale)
+    if q_scale is not None:
+        scale = scale * float(q_scale)
+    out = attention_blhd(qh, kh, vh, softmax_scale=scale, k_lens=k_lens)
+    return out.type(out_dtype)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# lvdm: CrossAttention.forward  (videotuna/models/lvdm/modules/attention.py:101-170)
+# ---------------------------------------------------------------------------------------------------------------------
+def lvdm_cross_attention_forward(self, x, context=None, mask=None):
+    """Drop-in body for lvdm `CrossAttention.forward(self, x, context=None, mask=None)`.
+
+    Projections stay the module's own nn.Linear layers (state-dict keys and peft LoRA targets are untouched); the
+    einsum/softmax/einsum core (attention.py:126-149) runs in one CUDA kernel on the (B, N, H, D) view of the projected
+    tensors, so the reference's two `rearrange` copies disappear. Relative position and masks: temporal kernel only.
+    """
+    is_self_attn = context is None
+    h = self.heads
+    q = self.to_q(x)
+    context = x if context is None else context
+    k_ip = v_ip = None
+    if self.img_cross_attention and not is_self_attn:
+        context, context_img = context[:, : self.text_context_len, :], context[:, self.text_context_len:, :]
+        k, v = self.to_k(context), self.to_v(context)
+        k_ip, v_ip = self.to_k_ip(context_img), self.to_v_ip(context_img)
+    else:
+        if not is_self_attn:
+            context = context[:, : self.text_context_len, :]
+        k, v = self.to_k(context), self.to_v(context)
+    _require(q.is_cuda and q.dtype == torch.bfloat16, "fp32 / CPU activations stay on the reference path")
+    _require(self.dim_head in (64, 128), f"dim_head {self.dim_head} stays on the reference path")
+    b, n, _ = q.shape
+    d = self.dim_head
+    q4, k4, v4 = q.view(b, n, h, d), k.view(b, k.shape[1], h, d), v.view(b, v.shape[1], h, d)
+    if self.relative_position or mask is not None:
+        from .temporal import temporal_attention  # small-N kernel with rel-pos / causal support
+        out = temporal_attention(self, q4, k4, v4, mask)
+    else:
+        out = attention_blhd(q4, k4, v4, softmax_scale=self.scale)
+    out = out.reshape(b, n, h * d)
+    if k_ip is not None:
+        out_ip = attention_blhd(q4, k_ip.view(b, -1, h, d), v_ip.view(b, -1, h, d), softmax_scale=self.scale)
+        out_ip = out_ip.reshape(b, n, h * d)
+        if self.img_cross_attention_scale_learnable:
+            out = out + self.img_cross_attention_scale * out_ip * (torch.tanh(self.alpha) + 1)
+        else:
+            out = out + self.img_cross_attention_scale * out_ip
+    return self.to_out(out)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# memory-bound helpers
+# ---------------------------------------------------------------------------------------------------------------------
+def ln_modulate(x: Tensor, shift: Optional[Tensor] = None, scale: Optional[Tensor] = None,
+                weight: Optional[Tensor] = None, bias: Optional[Tensor] = None, eps: float = 1e-6) -> Tensor:
+    """modulate(LayerNorm(x), shift, scale) in one pass (hunyuan modulate_layers.py:31-49 after nn.LayerNorm;
+    wan model.py:294-296). x (B,L,C) bf16; shift/scale (B,C) or (B,1,C)."""
+    _require(x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 3 and x.shape[-1] % 8 == 0,
+             "ln_modulate needs a CUDA bf16 (B,L,C) tensor")
+    B, _, Cc = x.shape
+    sc = None if scale is None else scale.reshape(B, Cc)
+    sh = None if shift is None else shift.reshape(B, Cc)
+    y, _, _ = ops.ln_modulate_fwd(x, weight, bias, sc, sh, float(eps))
+    return y
+
+
+def layer_norm(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], eps: float) -> Tensor:
+    """nn.LayerNorm over the last dim for (.., C) bf16 tensors (lvdm BasicTransformerBlock norms, attention.py:262-264)."""
+    shp = x.shape
+    y = ln_modulate(x.reshape(1, -1, shp[-1]), None, None, weight, bias, eps)
+    return y.view(shp)
+
+
+def gate_residual(x: Tensor, branch: Tensor, gate: Optional[Tensor] = None) -> Tensor:
+    """x + apply_gate(branch, gate) (hunyuan modulate_layers.py:52-68, models.py:231; wan model.py:298)."""
+    _require(x.is_cuda and x.dtype == torch.bfloat16 and branch.dtype == torch.bfloat16 and x.dim() == 3,
+             "gate_residual needs CUDA bf16 (B,L,C) tensors")
+    B, _, Cc = x.shape
+    g = None if gate is None else gate.reshape(B, Cc)
+    return ops.gate_residual_fwd(x, branch, g)
+
+
+def qk_rmsnorm_rope(x: Tensor, weight: Optional[Tensor], cos: Optional[Tensor], sin: Optional[Tensor],
+                    per_head: bool = True, eps: float = 1e-6) -> Tensor:
+    """RMSNorm (per head, or over the whole token when per_head=False) followed by interleaved RoPE on the first
+    cos.shape[0] tokens. x (B,L,H,D) bf16 (strided views allowed); cos/sin (L_rope, D) fp32 (posemb_layers.py:140-171,
+    norm_layers.py:33-59; wan model.py:40-86)."""
+    _require(x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[-1] in (64, 128),
+             "qk_rmsnorm_rope needs a CUDA bf16 (B,L,H,D) tensor with D in {64,128}")
+    mode = 0 if weight is None else (1 if per_head else 2)
+    y, _ = ops.qk_rmsnorm_rope_fwd(x, weight, cos, sin, mode, float(eps))
+    return y
+
+
+def groupnorm_silu(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], groups: int, eps: float,
+                   silu: bool = False) -> Tensor:
+    """GroupNorm with fp32 statistics (+ SiLU) on (N,C,*) bf16/fp32 tensors (lvdm GroupNormSpecific, utils.py:192-203)."""
+    _require(x.is_cuda and x.dtype in (torch.bfloat16, torch.float32), "groupnorm needs a CUDA bf16/fp32 tensor")
+    y, _, _ = ops.groupnorm_silu_fwd(x, weight, bias, int(groups), float(eps), bool(silu))
+    return y

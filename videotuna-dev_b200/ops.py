@@ -1,0 +1,425 @@
+"""torch.library ops over the C ABI of libb200vt.so (include/b200vt.h).
+
+Each op is defined with a schema, a CUDA implementation that calls the shared library through ctypes on the current
+CUDA stream, a fake (meta) implementation for shape inference (torch.utils.checkpoint / tracing), and an autograd
+formula wired to the matching backward entry point. There is deliberately no CPU implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib
+
+_vp = C.c_void_p
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else _vp(t.data_ptr())
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None:
+        return None
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _check_bf16_cuda(name: str, t: Tensor):
+    if not t.is_cuda:
+        raise RuntimeError(f"b200vt: {name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != torch.bfloat16:
+        raise RuntimeError(f"b200vt: {name} must be bfloat16, got {t.dtype}")
+
+
+def _blhd(t: Tensor) -> Tensor:
+    """Return t (B,L,H,D) with unit head-dim stride and 16-byte aligned strides/base; copy only if it is not."""
+    ok = t.stride(3) == 1 and all(s % 8 == 0 for s in t.stride()[:3]) and t.data_ptr() % 16 == 0
+    return t if ok else t.contiguous()
+
+
+# =====================================================================================================================
+# attention
+# =====================================================================================================================
+@torch.library.custom_op("b200vt::attn_fwd", mutates_args=(), device_types="cuda")
+def attn_fwd(q: Tensor, k: Tensor, v: Tensor, cu_seqlens_q: Optional[Tensor], cu_seqlens_k: Optional[Tensor],
+             seqlens_k: Optional[Tensor], max_seqlen_q: int, max_seqlen_k: int,
+             softmax_scale: float) -> Tuple[Tensor, Tensor]:
+    """q (B,Lq,H,D), k/v (B,Lk,H,D) bf16 -> o (B,Lq,H,D) bf16 contiguous, lse (B,H,Lq) fp32."""
+    for n, t in (("q", q), ("k", k), ("v", v)):
+        _check_bf16_cuda(n, t)
+    q, k, v = _blhd(q), _blhd(k), _blhd(v)
+    B, Lq, H, D = q.shape
+    Lk = k.shape[1]
+    o = torch.empty((B, Lq, H, D), dtype=q.dtype, device=q.device)
+    lse = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device)
+    nseg = 0 if cu_seqlens_q is None else cu_seqlens_q.numel() - 1
+    with torch.cuda.device(q.device):
+        _lib.call("vt_attn_fwd", _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(lse), _lib.strides3(q), _lib.strides3(k),
+                  _lib.strides3(v), _lib.strides3(o), B, H, Lq, Lk, D, _ptr(cu_seqlens_q), _ptr(cu_seqlens_k), nseg,
+                  max_seqlen_q, max_seqlen_k, _ptr(seqlens_k), float(softmax_scale), _stream())
+    return o, lse
+
+
+@attn_fwd.register_fake
+def _(q, k, v, cu_seqlens_q, cu_seqlens_k, seqlens_k, max_seqlen_q, max_seqlen_k, softmax_scale):
+    B, Lq, H, D = q.shape
+    return q.new_empty((B, Lq, H, D)), q.new_empty((B, H, Lq), dtype=torch.float32)
+
+
+@torch.library.custom_op("b200vt::attn_bwd", mutates_args=(), device_types="cuda")
+def attn_bwd(dout: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tensor, cu_seqlens_q: Optional[Tensor],
+             cu_seqlens_k: Optional[Tensor], seqlens_k: Optional[Tensor], max_seqlen_q: int, max_seqlen_k: int,
+             softmax_scale: float) -> Tuple[Tensor, Tensor, Tensor]:
+    q, k, v, o, dout = _blhd(q), _blhd(k), _blhd(v), _blhd(o), _blhd(dout)
+    B, Lq, H, D = q.shape
+    Lk = k.shape[1]
+    dq = torch.empty((B, Lq, H, D), dtype=q.dtype, device=q.device)
+    dk = torch.empty((B, Lk, H, D), dtype=q.dtype, device=q.device)
+    dv = torch.empty((B, Lk, H, D), dtype=q.dtype, device=q.device)
+    nseg = 0 if cu_seqlens_q is None else cu_seqlens_q.numel() - 1
+    with torch.cuda.device(q.device):
+        nbytes = _lib.lib().vt_attn_bwd_workspace_bytes(B, H, Lq, D)
+        ws = torch.empty((nbytes,), dtype=torch.uint8, device=q.device)
+        _lib.call("vt_attn_bwd", _ptr(dout), _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(lse), _ptr(dq), _ptr(dk),
+                  _ptr(dv), _lib.strides3(dout), _lib.strides3(q), _lib.strides3(k), _lib.strides3(v),
+                  _lib.strides3(o), _lib.strides3(dq), _lib.strides3(dk), _lib.strides3(dv), B, H, Lq, Lk, D,
+                  _ptr(cu_seqlens_q), _ptr(cu_seqlens_k), nseg, max_seqlen_q, max_seqlen_k, _ptr(seqlens_k),
+                  float(softmax_scale), _ptr(ws), C.c_int64(nbytes), _stream())
+    return dq, dk, dv
+
+
+@attn_bwd.register_fake
+def _(dout, q, k, v, o, lse, cu_seqlens_q, cu_seqlens_k, seqlens_k, max_seqlen_q, max_seqlen_k, softmax_scale):
+    return torch.empty_like(q, memory_format=torch.contiguous_format), \
+        torch.empty_like(k, memory_format=torch.contiguous_format), \
+        torch.empty_like(v, memory_format=torch.contiguous_format)
+
+
+def _attn_setup(ctx, inputs, output):
+    q, k, v, cu_q, cu_k, sk, mq, mk, scale = inputs
+    o, lse = output
+    ctx.save_for_backward(q, k, v, o, lse, cu_q, cu_k, sk)
+    ctx.mq, ctx.mk, ctx.scale = mq, mk, scale
+
+
+def _attn_backward(ctx, do, dlse):
+    q, k, v, o, lse, cu_q, cu_k, sk = ctx.saved_tensors
+    dq, dk, dv = attn_bwd(do, q, k, v, o, lse, cu_q, cu_k, sk, ctx.mq, ctx.mk, ctx.scale)
+    return dq, dk, dv, None, None, None, None, None, None
+
+
+attn_fwd.register_autograd(_attn_backward, setup_context=_attn_setup)
+
+
+# =====================================================================================================================
+# LayerNorm + modulate
+# =====================================================================================================================
+@torch.library.custom_op("b200vt::ln_modulate_fwd", mutates_args=(), device_types="cuda")
+def ln_modulate_fwd(x: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor], scale: Optional[Tensor],
+                    shift: Optional[Tensor], eps: float) -> Tuple[Tensor, Tensor, Tensor]:
+    """x (B,L,C) bf16; gamma/beta (C); scale/shift (B,C). Returns y, mean (B*L), rstd (B*L)."""
+    _check_bf16_cuda("x", x)
+    x = x.contiguous()
+    B, L, Cc = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty((B * L,), dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    g, b, sc, sh = _f32(gamma), _f32(beta), _f32(scale), _f32(shift)
+    with torch.cuda.device(x.device):
+        _lib.call("vt_ln_modulate_fwd", _ptr(x), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(g), _ptr(b), _ptr(sc), _ptr(sh),
+                  B, L, Cc, float(eps), _stream())
+    return y, mean, rstd
+
+
+@ln_modulate_fwd.register_fake
+def _(x, gamma, beta, scale, shift, eps):
+    B, L, Cc = x.shape
+    return torch.empty_like(x, memory_format=torch.contiguous_format), x.new_empty((B * L,), dtype=torch.float32), \
+        x.new_empty((B * L,), dtype=torch.float32)
+
+
+@torch.library.custom_op("b200vt::ln_modulate_bwd", mutates_args=(), device_types="cuda")
+def ln_modulate_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Optional[Tensor],
+                    beta: Optional[Tensor], scale: Optional[Tensor], need_affine: bool,
+                    need_mod: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Returns dx and fp32 (dgamma, dbeta, dscale, dshift); unused ones are empty (0-element) tensors."""
+    dy, x = dy.contiguous(), x.contiguous()
+    B, L, Cc = x.shape
+    dx = torch.empty_like(x)
+    dev = x.device
+    dgamma = torch.zeros((Cc,), dtype=torch.float32, device=dev) if need_affine else x.new_empty((0,), dtype=torch.float32)
+    dbeta = torch.zeros_like(dgamma)
+    dscale = torch.zeros((B, Cc), dtype=torch.float32, device=dev) if need_mod else x.new_empty((0,), dtype=torch.float32)
+    dshift = torch.zeros_like(dscale)
+    g, b, sc = _f32(gamma), _f32(beta), _f32(scale)
+    with torch.cuda.device(dev):
+        _lib.call("vt_ln_modulate_bwd", _ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(g), _ptr(b), _ptr(sc),
+                  _ptr(dgamma) if need_affine else None, _ptr(dbeta) if need_affine else None,
+                  _ptr(dscale) if need_mod else None, _ptr(dshift) if need_mod else None, B, L, Cc, _stream())
+    return dx, dgamma, dbeta, dscale, dshift
+
+
+@ln_modulate_bwd.register_fake
+def _(dy, x, mean, rstd, gamma, beta, scale, need_affine, need_mod):
+    B, L, Cc = x.shape
+    e = x.new_empty((0,), dtype=torch.float32)
+    return (torch.empty_like(x, memory_format=torch.contiguous_format),
+            x.new_empty((Cc,), dtype=torch.float32) if need_affine else e,
+            x.new_empty((Cc,), dtype=torch.float32) if need_affine else e,
+            x.new_empty((B, Cc), dtype=torch.float32) if need_mod else e,
+            x.new_empty((B, Cc), dtype=torch.float32) if need_mod else e)
+
+
+def _lnm_setup(ctx, inputs, output):
+    x, gamma, beta, scale, shift, eps = inputs
+    y, mean, rstd = output
+    ctx.save_for_backward(x, mean, rstd, gamma, beta, scale, shift)
+
+
+def _lnm_backward(ctx, dy, dmean, drstd):
+    x, mean, rstd, gamma, beta, scale, shift = ctx.saved_tensors
+    need_affine = (gamma is not None and ctx.needs_input_grad[1]) or (beta is not None and ctx.needs_input_grad[2])
+    need_mod = (scale is not None and ctx.needs_input_grad[3]) or (shift is not None and ctx.needs_input_grad[4])
+    dx, dgamma, dbeta, dscale, dshift = ln_modulate_bwd(dy, x, mean, rstd, gamma, beta, scale, need_affine, need_mod)
+    out = [dx, None, None, None, None, None]
+    if gamma is not None and ctx.needs_input_grad[1]:
+        out[1] = dgamma.to(gamma.dtype)
+    if beta is not None and ctx.needs_input_grad[2]:
+        out[2] = dbeta.to(beta.dtype)
+    if scale is not None and ctx.needs_input_grad[3]:
+        out[3] = dscale.to(scale.dtype).view_as(scale)
+    if shift is not None and ctx.needs_input_grad[4]:
+        out[4] = dshift.to(shift.dtype).view_as(shift)
+    return tuple(out)
+
+
+ln_modulate_fwd.register_autograd(_lnm_backward, setup_context=_lnm_setup)
+
+
+# =====================================================================================================================
+# gated residual
+# =====================================================================================================================
+@torch.library.custom_op("b200vt::gate_residual_fwd", mutates_args=(), device_types="cuda")
+def gate_residual_fwd(x: Tensor, branch: Tensor, gate: Optional[Tensor]) -> Tensor:
+    """y = x + branch * gate[:, None, :];  x, branch (B,L,C) bf16, gate (B,C) or None."""
+    _check_bf16_cuda("x", x)
+    _check_bf16_cuda("branch", branch)
+    x, branch = x.contiguous(), branch.contiguous()
+    B, L, Cc = x.shape
+    y = torch.empty_like(x)
+    g = _f32(gate)
+    with torch.cuda.device(x.device):
+        _lib.call("vt_gate_residual_fwd", _ptr(x), _ptr(branch), _ptr(y), _ptr(g), B, L, Cc, _stream())
+    return y
+
+
+@gate_residual_fwd.register_fake
+def _(x, branch, gate):
+    return torch.empty_like(x, memory_format=torch.contiguous_format)
+
+
+@torch.library.custom_op("b200vt::gate_residual_bwd", mutates_args=(), device_types="cuda")
+def gate_residual_bwd(dy: Tensor, branch: Tensor, gate: Optional[Tensor], need_dgate: bool) -> Tuple[Tensor, Tensor]:
+    dy, branch = dy.contiguous(), branch.contiguous()
+    B, L, Cc = dy.shape
+    dbranch = torch.empty_like(dy)
+    dgate = torch.zeros((B, Cc), dtype=torch.float32, device=dy.device) if need_dgate else dy.new_empty((0,), dtype=torch.float32)
+    g = _f32(gate)
+    with torch.cuda.device(dy.device):
+        _lib.call("vt_gate_residual_bwd", _ptr(dy), _ptr(branch), _ptr(dbranch), _ptr(g),
+                  _ptr(dgate) if need_dgate else None, B, L, Cc, _stream())
+    return dbranch, dgate
+
+
+@gate_residual_bwd.register_fake
+def _(dy, branch, gate, need_dgate):
+    B, L, Cc = dy.shape
+    return torch.empty_like(dy, memory_format=torch.contiguous_format), \
+        dy.new_empty((B, Cc) if need_dgate else (0,), dtype=torch.float32)
+
+
+def _gr_setup(ctx, inputs, output):
+    x, branch, gate = inputs
+    ctx.save_for_backward(branch, gate)
+
+
+def _gr_backward(ctx, dy):
+    branch, gate = ctx.saved_tensors
+    need_dgate = gate is not None and ctx.needs_input_grad[2]
+    dbranch, dgate = gate_residual_bwd(dy, branch, gate, need_dgate)
+    return dy, dbranch, (dgate.to(gate.dtype).view_as(gate) if need_dgate else None)
+
+
+gate_residual_fwd.register_autograd(_gr_backward, setup_context=_gr_setup)
+
+
+# =====================================================================================================================
+# fused QK-RMSNorm + RoPE
+# =====================================================================================================================
+@torch.library.custom_op("b200vt::qk_rmsnorm_rope_fwd", mutates_args=(), device_types="cuda")
+def qk_rmsnorm_rope_fwd(x: Tensor, weight: Optional[Tensor], cos: Optional[Tensor], sin: Optional[Tensor],
+                        norm_mode: int, eps: float) -> Tuple[Tensor, Tensor]:
+    """x (B,L,H,D) bf16 (strided ok). norm_mode 0 none / 1 per-head (weight (D)) / 2 full-row (weight (H*D)).
+    cos/sin (L_rope, D) fp32. Returns y (B,L,H,D) contiguous and rstd."""
+    _check_bf16_cuda("x", x)
+    x = _blhd(x)
+    B, L, H, D = x.shape
+    y = torch.empty((B, L, H, D), dtype=x.dtype, device=x.device)
+    if norm_mode == 1:
+        rstd = torch.empty((B, L, H), dtype=torch.float32, device=x.device)
+    elif norm_mode == 2:
+        rstd = torch.empty((B, L), dtype=torch.float32, device=x.device)
+    else:
+        rstd = torch.empty((0,), dtype=torch.float32, device=x.device)
+    w, c, s = _f32(weight), _f32(cos), _f32(sin)
+    L_rope = 0 if c is None else min(c.shape[0], L)
+    with torch.cuda.device(x.device):
+        _lib.call("vt_qk_rmsnorm_rope_fwd", _ptr(x), _ptr(y), _ptr(rstd) if norm_mode else None, _ptr(w), _ptr(c),
+                  _ptr(s), _lib.strides3(x), _lib.strides3(y), B, L, H, D, L_rope, norm_mode, float(eps), _stream())
+    return y, rstd
+
+
+@qk_rmsnorm_rope_fwd.register_fake
+def _(x, weight, cos, sin, norm_mode, eps):
+    B, L, H, D = x.shape
+    shp = (B, L, H) if norm_mode == 1 else ((B, L) if norm_mode == 2 else (0,))
+    return x.new_empty((B, L, H, D)), x.new_empty(shp, dtype=torch.float32)
+
+
+@torch.library.custom_op("b200vt::qk_rmsnorm_rope_bwd", mutates_args=(), device_types="cuda")
+def qk_rmsnorm_rope_bwd(dy: Tensor, x: Tensor, rstd: Tensor, weight: Optional[Tensor], cos: Optional[Tensor],
+                        sin: Optional[Tensor], norm_mode: int, need_dw: bool) -> Tuple[Tensor, Tensor]:
+    dy, x = _blhd(dy), _blhd(x)
+    B, L, H, D = x.shape
+    dx = torch.empty((B, L, H, D), dtype=x.dtype, device=x.device)
+    nw = D if norm_mode == 1 else H * D
+    dw = torch.zeros((nw,), dtype=torch.float32, device=x.device) if need_dw else x.new_empty((0,), dtype=torch.float32)
+    w, c, s = _f32(weight), _f32(cos), _f32(sin)
+    L_rope = 0 if c is None else min(c.shape[0], L)
+    with torch.cuda.device(x.device):
+        _lib.call("vt_qk_rmsnorm_rope_bwd", _ptr(dy), _ptr(x), _ptr(rstd) if norm_mode else None, _ptr(dx),
+                  _ptr(dw) if need_dw else None, _ptr(w), _ptr(c), _ptr(s), _lib.strides3(dy), _lib.strides3(x),
+                  _lib.strides3(dx), B, L, H, D, L_rope, norm_mode, _stream())
+    return dx, dw
+
+
+@qk_rmsnorm_rope_bwd.register_fake
+def _(dy, x, rstd, weight, cos, sin, norm_mode, need_dw):
+    B, L, H, D = x.shape
+    nw = D if norm_mode == 1 else H * D
+    return x.new_empty((B, L, H, D)), x.new_empty((nw,) if need_dw else (0,), dtype=torch.float32)
+
+
+def _rr_setup(ctx, inputs, output):
+    x, weight, cos, sin, norm_mode, eps = inputs
+    y, rstd = output
+    ctx.save_for_backward(x, rstd, weight, cos, sin)
+    ctx.norm_mode = norm_mode
+
+
+def _rr_backward(ctx, dy, drstd):
+    x, rstd, weight, cos, sin = ctx.saved_tensors
+    need_dw = weight is not None and ctx.norm_mode != 0 and ctx.needs_input_grad[1]
+    dx, dw = qk_rmsnorm_rope_bwd(dy, x, rstd, weight, cos, sin, ctx.norm_mode, need_dw)
+    return dx, (dw.to(weight.dtype).view_as(weight) if need_dw else None), None, None, None, None
+
+
+qk_rmsnorm_rope_fwd.register_autograd(_rr_backward, setup_context=_rr_setup)
+
+
+# =====================================================================================================================
+# GroupNorm (+SiLU)
+# =====================================================================================================================
+def _gn_dtype(x: Tensor) -> int:
+    if x.dtype == torch.bfloat16:
+        return 0
+    if x.dtype == torch.float32:
+        return 1
+    raise RuntimeError(f"b200vt: groupnorm supports bf16/fp32, got {x.dtype}")
+
+
+@torch.library.custom_op("b200vt::groupnorm_silu_fwd", mutates_args=(), device_types="cuda")
+def groupnorm_silu_fwd(x: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor], groups: int, eps: float,
+                       silu: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    """x (N, C, *spatial) bf16/fp32 contiguous -> y, mean (N,G), rstd (N,G); statistics in fp32."""
+    if not x.is_cuda:
+        raise RuntimeError("b200vt: groupnorm input must be a CUDA tensor (there is no CPU path)")
+    x = x.contiguous()
+    N, Cc = x.shape[0], x.shape[1]
+    S = x.numel() // (N * Cc)
+    y = torch.empty_like(x)
+    mean = torch.empty((N, groups), dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    g, b = _f32(gamma), _f32(beta)
+    with torch.cuda.device(x.device):
+        _lib.call("vt_groupnorm_silu_fwd", _ptr(x), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(g), _ptr(b), N, Cc, S, groups,
+                  float(eps), int(silu), _gn_dtype(x), _stream())
+    return y, mean, rstd
+
+
+@groupnorm_silu_fwd.register_fake
+def _(x, gamma, beta, groups, eps, silu):
+    N = x.shape[0]
+    return torch.empty_like(x, memory_format=torch.contiguous_format), \
+        x.new_empty((N, groups), dtype=torch.float32), x.new_empty((N, groups), dtype=torch.float32)
+
+
+@torch.library.custom_op("b200vt::groupnorm_silu_bwd", mutates_args=(), device_types="cuda")
+def groupnorm_silu_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Optional[Tensor],
+                       beta: Optional[Tensor], groups: int, silu: bool) -> Tuple[Tensor, Tensor, Tensor]:
+    dy, x = dy.contiguous(), x.contiguous()
+    N, Cc = x.shape[0], x.shape[1]
+    S = x.numel() // (N * Cc)
+    dx = torch.empty_like(x)
+    dgamma = torch.zeros((Cc,), dtype=torch.float32, device=x.device)
+    dbeta = torch.zeros_like(dgamma)
+    g, b = _f32(gamma), _f32(beta)
+    dy = dy.to(x.dtype)
+    with torch.cuda.device(x.device):
+        _lib.call("vt_groupnorm_silu_bwd", _ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(g),
+                  _ptr(b), _ptr(dgamma), _ptr(dbeta), N, Cc, S, groups, int(silu), _gn_dtype(x), _stream())
+    return dx, dgamma, dbeta
+
+
+@groupnorm_silu_bwd.register_fake
+def _(dy, x, mean, rstd, gamma, beta, groups, silu):
+    Cc = x.shape[1]
+    return torch.empty_like(x, memory_format=torch.contiguous_format), x.new_empty((Cc,), dtype=torch.float32), \
+        x.new_empty((Cc,), dtype=torch.float32)
+
+
+def _gn_setup(ctx, inputs, output):
+    x, gamma, beta, groups, eps, silu = inputs
+    y, mean, rstd = output
+    ctx.save_for_backward(x, mean, rstd, gamma, beta)
+    ctx.groups, ctx.silu = groups, silu
+
+
+def _gn_backward(ctx, dy, dmean, drstd):
+    x, mean, rstd, gamma, beta = ctx.saved_tensors
+    dx, dgamma, dbeta = groupnorm_silu_bwd(dy, x, mean, rstd, gamma, beta, ctx.groups, ctx.silu)
+    return (dx, dgamma.to(gamma.dtype) if gamma is not None and ctx.needs_input_grad[1] else None,
+            dbeta.to(beta.dtype) if beta is not None and ctx.needs_input_grad[2] else None, None, None, None)
+
+
+groupnorm_silu_fwd.register_autograd(_gn_backward, setup_context=_gn_setup)
+
+
+# =====================================================================================================================
+# self-test hook
+# =====================================================================================================================
+def umma_probe(a: Tensor, b: Tensor, a_mode: int, b_mode: int, n: int = 128, a_desc=(16, 1024, 32),
+               b_desc=(16, 1024, 32)) -> Tensor:
+    """One 128 x n x 128 bf16 tile through TMA + tcgen05 (csrc/umma_probe.cu). a, b: (128,128) bf16 row-major."""
+    assert a.shape == (128, 128) and b.shape == (128, 128) and a.dtype == torch.bfloat16 and a.is_contiguous()
+    d = torch.zeros((128, n), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        _lib.call("vt_umma_probe", _ptr(a), _ptr(b.contiguous()), _ptr(d), a_mode, b_mode, n, *a_desc, *b_desc, _stream())
+    return d

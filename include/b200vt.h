@@ -58,6 +58,22 @@ int vt_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse
                 const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k, int num_segments, int max_seqlen_q,
                 int max_seqlen_k, const int32_t* seqlens_k, float softmax_scale, void* stream);
 
+/* Bytes of device workspace vt_attn_bwd needs (fp32 dQ accumulator + delta = rowsum(dO*O)). */
+int64_t vt_attn_bwd_workspace_bytes(int B, int H, int Lq, int D);
+
+/* Attention backward: given dO, recomputes P from (q,k,lse) and produces dq, dk, dv (bf16; layouts given by their own
+ * stride arrays). Replaces autograd through the reference torch attention path (same call sites as vt_attn_fwd).
+ * In varlen mode, rows of dk/dv/dq outside every segment are zero for dq and untouched for dk/dv; in fixed mode with
+ * seqlens_k, dk/dv rows of masked keys are written as zeros. `workspace` must hold vt_attn_bwd_workspace_bytes(...)
+ * bytes; it is overwritten. */
+int vt_attn_bwd(const void* dout, const void* q, const void* k, const void* v, const void* o, const float* lse,
+                void* dq, void* dk, void* dv, const int64_t* do_strides, const int64_t* q_strides,
+                const int64_t* k_strides, const int64_t* v_strides, const int64_t* o_strides,
+                const int64_t* dq_strides, const int64_t* dk_strides, const int64_t* dv_strides, int B, int H, int Lq,
+                int Lk, int D, const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k, int num_segments,
+                int max_seqlen_q, int max_seqlen_k, const int32_t* seqlens_k, float softmax_scale, void* workspace,
+                int64_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Fused QK-RMSNorm + 3-D RoPE (interleaved pairs) in one pass over q or k, in place of
  *   hunyuan RMSNorm (norm_layers.py:5-59) + apply_rotary_emb (posemb_layers.py:140-188)      -> norm_mode 1

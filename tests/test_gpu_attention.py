@@ -114,3 +114,88 @@ def test_linearity_in_v_full_size_property():
     kz = torch.zeros_like(k)
     om = _run(q, kz, v1).float().cpu()
     assert R.max_rel_err(om, v1.float().mean(dim=1, keepdim=True).expand_as(om)) < TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# backward
+# ---------------------------------------------------------------------------------------------------------------------
+def _grads_ref(q, k, v, do, mask=None, scale=None):
+    qr, kr, vr = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    out = R.sdpa_blhd(qr, kr, vr, mask, scale)
+    out.backward(do.float())
+    return out.detach(), qr.grad, kr.grad, vr.grad
+
+
+def _grads_cuda(q, k, v, do, **kw):
+    import b200vt.functional as Fn
+    qc, kc, vc = (t.cuda().clone().requires_grad_(True) for t in (q, k, v))
+    out = Fn.attention_blhd(qc, kc, vc, **kw)
+    out.backward(do.cuda())
+    torch.cuda.synchronize()
+    return out.detach(), qc.grad, kc.grad, vc.grad
+
+
+def _check_grads(got, ref, names=("out", "dq", "dk", "dv")):
+    for n, a, b in zip(names, got, ref):
+        a = a.float().cpu()
+        cos, err = R.cosine(a, b), R.max_rel_err(a, b)
+        assert cos > 0.999, (n, cos, err)
+        assert err < 3e-2, (n, cos, err)
+
+
+@pytest.mark.parametrize("B,Lq,Lk,H,D", [
+    (1, 128, 128, 1, 128), (1, 128, 128, 1, 64), (1, 256, 384, 2, 128), (2, 200, 333, 2, 128), (1, 1000, 77, 3, 64),
+    (2, 40, 40, 5, 64), (1, 640, 640, 2, 64), (1, 513, 1025, 1, 128), (1, 2560, 2560, 2, 64), (1, 1500, 1500, 2, 128),
+])
+def test_bwd_matches_oracle(B, Lq, Lk, H, D):
+    q, k, v = _rand((B, Lq, H, D), 21), _rand((B, Lk, H, D), 22), _rand((B, Lk, H, D), 23)
+    do = _rand((B, Lq, H, D), 24)
+    _check_grads(_grads_cuda(q, k, v, do), _grads_ref(q, k, v, do))
+
+
+def test_bwd_k_lens():
+    q, k, v = _rand((2, 200, 2, 128), 25), _rand((2, 300, 2, 128), 26), _rand((2, 300, 2, 128), 27)
+    do = _rand((2, 200, 2, 128), 28)
+    k_lens = torch.tensor([300, 131], dtype=torch.int32)
+    mask = (torch.arange(300)[None, :] < k_lens[:, None])[:, None, None, :]
+    got = _grads_cuda(q, k, v, do, k_lens=k_lens.cuda())
+    ref = _grads_ref(q, k, v, do, mask)
+    _check_grads(got, ref)
+    assert float(got[2][1, 131:].abs().max()) == 0.0 and float(got[3][1, 131:].abs().max()) == 0.0
+
+
+def test_bwd_varlen_two_segments():
+    g = load_golden("hunyuan_attention")
+    q, k, v = g["q"][:1], g["k"][:1], g["v"][:1]  # one sample: segments [0,140) and [140,150)
+    do = _rand(tuple(q.shape), 29)
+    cu = torch.tensor([0, 140, 150], dtype=torch.int32)
+    mask = R.varlen_block_mask(cu.tolist(), 150)[None, None]
+    got = _grads_cuda(q, k, v, do, cu_seqlens_q=cu.cuda(), cu_seqlens_k=cu.cuda(), max_seqlen_q=150, max_seqlen_k=150)
+    _check_grads(got, _grads_ref(q.float(), k.float(), v.float(), do, mask))
+
+
+def test_bwd_strided_fused_qkv_and_softmax_scale():
+    qkv = _rand((1, 300, 3, 2, 64), 30)
+    q, k, v = qkv.unbind(2)
+    do = _rand((1, 300, 2, 64), 31)
+    import b200vt.functional as Fn
+    qkv_c = qkv.cuda().clone().requires_grad_(True)
+    qc, kc, vc = qkv_c.unbind(2)
+    out = Fn.attention_blhd(qc, kc, vc, softmax_scale=0.2)
+    out.backward(do.cuda())
+    ref = _grads_ref(q, k, v, do, scale=0.2)
+    gq, gk, gv = qkv_c.grad.unbind(2)
+    _check_grads((out.detach(), gq, gk, gv), ref)
+
+
+def test_bwd_gradient_identities_long_sequence():
+    # size-independent properties at a long sequence: sum_j dS_ij = 0 => dq is orthogonal to nothing in general, but
+    # (1) dv = P^T dO implies sum over keys of dv equals sum over queries of dO (rows of P sum to 1);
+    # (2) the loss sum(o * do) is invariant to adding a constant vector c to all keys: dk must sum to ~0 along keys... per head dim weighted by q.
+    q, k, v = _rand((1, 8192, 1, 128), 32), _rand((1, 8192, 1, 128), 33), _rand((1, 8192, 1, 128), 34)
+    do = _rand((1, 8192, 1, 128), 35)
+    out, dq, dk, dv = _grads_cuda(q, k, v, do)
+    lhs, rhs = dv.float().sum(dim=1).cpu(), do.float().sum(dim=1)
+    assert R.max_rel_err(lhs, rhs) < 2e-2
+    # shifting every key by the same vector leaves softmax unchanged -> sum_j dk_j = 0 (up to bf16 rounding of dk)
+    assert float(dk.float().sum(dim=1).abs().max()) < 2e-2 * float(dk.float().abs().sum(dim=1).max())

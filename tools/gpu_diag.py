@@ -44,6 +44,28 @@ print("relerr %%.3e lse_abs_err %%.3e" %% (err, lerr))
 '''
 
 
+BWD = r'''
+import sys, math, torch
+sys.path.insert(0, %r)
+import b200vt.functional as Fn, b200vt._lib as L
+B,Lq,Lk,H,D = %d,%d,%d,%d,%d
+g = torch.Generator().manual_seed(3)
+mk = lambda *s: torch.randn(*s, generator=g).to(torch.bfloat16)
+q, k, v, do = mk(B,Lq,H,D), mk(B,Lk,H,D), mk(B,Lk,H,D), mk(B,Lq,H,D)
+qc, kc, vc = (t.cuda().requires_grad_(True) for t in (q,k,v))
+try:
+    o = Fn.attention_blhd(qc,kc,vc); o.backward(do.cuda()); torch.cuda.synchronize()
+except Exception as e:
+    print("EXC", repr(e)[:200], "watchdog", [hex(x) for x in L.watchdog()]); sys.exit(1)
+qr, kr, vr = (t.float().requires_grad_(True) for t in (q,k,v))
+s = torch.einsum("bihd,bjhd->bhij", qr, kr)/math.sqrt(D)
+ref = torch.einsum("bhij,bjhd->bihd", s.softmax(-1), vr); ref.backward(do.float())
+def e(a,b): a=a.float().cpu(); return float((a-b).abs().max()/b.abs().max())
+def c(a,b): a=a.float().cpu().flatten().double(); b=b.flatten().double(); return float(a@b/(a.norm()*b.norm()))
+print("dq err %%.2e cos %%.5f | dk err %%.2e cos %%.5f | dv err %%.2e cos %%.5f" %% (e(qc.grad,qr.grad), c(qc.grad,qr.grad), e(kc.grad,kr.grad), c(kc.grad,kr.grad), e(vc.grad,vr.grad), c(vc.grad,vr.grad)))
+'''
+
+
 def run(code):
     try:
         r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
@@ -64,6 +86,14 @@ def main():
         for cfg in [(1, 128, 128, 1, 128), (1, 128, 128, 1, 64), (1, 256, 256, 1, 128), (1, 256, 512, 2, 128), (2, 200, 333, 2, 128),
                     (1, 1000, 77, 3, 64), (1, 2560, 2560, 2, 64), (1, 4096, 4096, 2, 128)]:
             print(f"attn_fwd B,Lq,Lk,H,D={cfg}: {run(ATTN % ((ROOT,) + cfg))}", flush=True)
+    if what in ("bwd", "all"):
+        bwd()
+
+
+def bwd():
+    for cfg in [(1, 128, 128, 1, 128), (1, 128, 128, 1, 64), (1, 256, 256, 1, 128), (1, 256, 384, 2, 128), (2, 200, 333, 2, 128),
+                (1, 1000, 77, 3, 64), (1, 2560, 2560, 2, 64), (1, 2048, 2048, 2, 128)]:
+        print(f"attn_bwd B,Lq,Lk,H,D={cfg}: {run(BWD % ((ROOT,) + cfg))}", flush=True)
 
 
 if __name__ == "__main__":

@@ -1,5 +1,538 @@
-// placeholder until the backward kernel lands
+// attn_bwd_sm100.cu — flash-attention backward for sm_100a (dense, non-causal), 5 GEMMs per (Q tile, KV tile).
+//
+// Replaces autograd through the reference torch attention path (same call sites as attn_fwd_sm100.cu).
+//
+// One CTA owns one 128-key tile of one (problem, head): K and V stay in shared memory, dK and dV accumulate in TMEM
+// over a loop on 128-row query tiles; dQ is produced per (Q tile, KV tile) and added into an fp32 accumulator in
+// global memory with vector reductions (red.global.add.v4.f32).
+//
+// Transposed formulation (keys on TMEM lanes) so that P^T and dS^T are directly MMA A-operands:
+//   MMA1  S^T  = K  Q_i^T         SS   (A = K tile K-major, B = Q_i K-major)               -> TMEM S
+//   MMA2  dP^T = V  dO_i^T        SS                                                        -> TMEM dP
+//   SM1   P^T  = exp2(S^T * c - lse_i)  (compute warpgroups; bf16 P^T written back into the S columns)
+//   MMA3  dV  += P^T dO_i         TS   (A = P^T from TMEM, B = dO_i MN-major)
+//   SM2   dS^T = P^T o (dP^T - delta_i) -> bf16 -> shared memory tile [key][q] (128B-swizzled)
+//   MMA4  dK  += dS^T Q_i         SS   (A = dS^T K-major, B = Q_i MN-major)
+//   MMA5  dQ_i = dS  K            SS   (A = dS as MN-major view of the same tile, B = K MN-major) -> TMEM dQ
+//   DR    dQ_i: TMEM -> registers -> red.global.add into dq_acc (reduce warpgroup)
+// Warps: 0-7 compute (thread = key row x half of the q columns), 8-11 dQ reduce (thread = q row), 12 producer
+// (TMA + lse/delta staging), 13 MMA issuer, 14-15 idle (complete the 4th warpgroup for setmaxnreg).
+// TMEM columns: S [0,128) (P^T bf16 at [32,96)), dP [128,256), dV [256,256+D), dK [256+D,256+2D),
+//   dQ: D=128 aliases dP (dP is dead once dS is in shared memory); D=64 uses [384,448).
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
 #include "attn_common.h"
+#include "sm100_ptx.cuh"
+
 namespace vt {
-cudaError_t attn_bwd_set_debug_ptr(unsigned int*) { return cudaSuccess; }
+namespace {
+
+template <int D>
+struct BwdCfg {
+  static_assert(D == 64 || D == 128, "head dim must be 64 or 128");
+  static constexpr int KCH = D / 64;
+  static constexpr int CHUNK = 128 * 128;   // bytes of one [128 rows][64 bf16] swizzled box
+  static constexpr int TILE = CHUNK * KCH;  // 128 x D bf16
+  static constexpr int QS = 2;              // Q ring depth (dO is single-buffered)
+  static constexpr int OFF_K = 0;
+  static constexpr int OFF_V = OFF_K + TILE;
+  static constexpr int OFF_Q = OFF_V + TILE;
+  static constexpr int OFF_DO = OFF_Q + QS * TILE;
+  static constexpr int OFF_DS = OFF_DO + TILE;          // 128 x 128 bf16 = 2 boxes
+  static constexpr int OFF_STAT = OFF_DS + 2 * CHUNK;   // QS x {lse_log2[128], delta[128]} fp32
+  static constexpr int OFF_BAR = OFF_STAT + QS * 1024;
+  static constexpr int NBAR = 1 + 2 * QS + QS + 2 + 7;
+  static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+  static constexpr int BYTES = OFF_TMEM + 16 + 1024;
+  static constexpr int THREADS = 512;
+  static constexpr uint32_t T_S = 0, T_P = 32, T_DP = 128, T_DV = 256, T_DK = 256 + D;
+  static constexpr uint32_t T_DQ = (D == 128) ? 128 : 384;
+  static constexpr bool DQ_ALIASES_DP = (D == 128);
+};
+
+enum : uint32_t {
+  BT_KV_FULL = 0x200, BT_Q_FULL, BT_Q_EMPTY, BT_STAT_FULL, BT_DO_FULL, BT_DO_EMPTY, BT_S_FULL, BT_P_READY, BT_DP_FULL,
+  BT_DS_READY, BT_DQ_FULL, BT_DQ_DRAINED, BT_DKV_FULL, BT_ALIGN
+};
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
+
+template <int D>
+__global__ void __launch_bounds__(BwdCfg<D>::THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
+                float* __restrict__ dq_acc, const AttnBwdParams p, const int Lq_total) {
+  using C = BwdCfg<D>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  const int prob = blockIdx.z, h = blockIdx.y;
+  int q_base = 0, q_len = p.seq.Lq, bq = prob;
+  int k_base = 0, k_len = p.seq.Lk, bk = prob;
+  int k_rows_total = p.seq.Lk;  // rows that exist in the k/v tensors for this problem (fixed mode: padded length)
+  if (p.seq.cu_q != nullptr) {
+    q_base = p.seq.cu_q[prob];
+    q_len = p.seq.cu_q[prob + 1] - q_base;
+    bq = 0;
+  }
+  if (p.seq.cu_k != nullptr) {
+    k_base = p.seq.cu_k[prob];
+    k_len = p.seq.cu_k[prob + 1] - k_base;
+    k_rows_total = k_len;
+    bk = 0;
+  } else if (p.seq.seqlens_k != nullptr) {
+    k_len = min(max(p.seq.seqlens_k[prob], 0), p.seq.Lk);
+  }
+  const int kv0 = blockIdx.x * 128;
+  if (kv0 >= k_rows_total) return;
+  const int n_q = (q_len + 127) >> 7;
+  const int kv_valid = min(k_len - kv0, 128);  // may be <= 0: tile holds only masked (padding) keys
+
+  if (kv_valid <= 0 || n_q == 0) {  // nothing attends to these keys: dK = dV = 0
+    for (int r = threadIdx.x; r < 128; r += blockDim.x) {
+      if (kv0 + r < k_rows_total) {
+        __nv_bfloat16* dkp = p.dk + bk * p.dk_sb + static_cast<int64_t>(k_base + kv0 + r) * p.dk_sl + h * p.dk_sh;
+        __nv_bfloat16* dvp = p.dv + bk * p.dv_sb + static_cast<int64_t>(k_base + kv0 + r) * p.dv_sl + h * p.dv_sh;
+        for (int c = 0; c < D; c += 8) {
+          *reinterpret_cast<uint4*>(dkp + c) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(dvp + c) = make_uint4(0, 0, 0, 0);
+        }
+      }
+    }
+    return;
+  }
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* kv_full = bars;
+  uint64_t* q_full = kv_full + 1;
+  uint64_t* q_empty = q_full + C::QS;
+  uint64_t* stat_full = q_empty + C::QS;
+  uint64_t* do_full = stat_full + C::QS;
+  uint64_t* do_empty = do_full + 1;
+  uint64_t* s_full = do_empty + 1;
+  uint64_t* p_ready = s_full + 1;
+  uint64_t* dp_full = p_ready + 1;
+  uint64_t* ds_ready = dp_full + 1;
+  uint64_t* dq_full = ds_ready + 1;
+  uint64_t* dq_drained = dq_full + 1;
+  uint64_t* dkv_full = dq_drained + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM);
+
+  constexpr int PROD_WARP = 12, MMA_WARP = 13;
+
+  if (warp == PROD_WARP && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    tma_prefetch_desc(&tm_do);
+  }
+  if (warp == MMA_WARP && lane == 0) {
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < C::QS; ++i) {
+      mbar_init(q_full + i, 1);
+      mbar_init(q_empty + i, 1);
+      mbar_init(stat_full + i, 32);
+    }
+    mbar_init(do_full, 1);
+    mbar_init(do_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 256);
+    mbar_init(dp_full, 1);
+    mbar_init(ds_ready, 256);
+    mbar_init(dq_full, 1);
+    mbar_init(dq_drained, 128);
+    mbar_init(dkv_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp >= PROD_WARP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == PROD_WARP) {
+      // ================================ producer: TMA + lse/delta staging =========================
+      if (lane == 0) {
+        mbar_arrive_expect_tx(kv_full, 2 * C::TILE);
+#pragma unroll
+        for (int c = 0; c < C::KCH; ++c) {
+          tma_load_4d(smem + C::OFF_K + c * C::CHUNK, &tm_k, kv_full, c * 64, k_base + kv0, h, bk);
+          tma_load_4d(smem + C::OFF_V + c * C::CHUNK, &tm_v, kv_full, c * 64, k_base + kv0, h, bk);
+        }
+      }
+      const float* lse_row = p.lse + bq * p.lse_sb + h * p.lse_sh + q_base;
+      const float* dl_row = p.delta + bq * p.lse_sb + h * p.lse_sh + q_base;
+      for (int i = 0; i < n_q; ++i) {
+        const int s = i % C::QS;
+        mbar_wait(q_empty + s, ((i / C::QS) & 1) ^ 1, BT_Q_EMPTY);
+        if (lane == 0) {
+          mbar_arrive_expect_tx(q_full + s, C::TILE);
+#pragma unroll
+          for (int c = 0; c < C::KCH; ++c)
+            tma_load_4d(smem + C::OFF_Q + s * C::TILE + c * C::CHUNK, &tm_q, q_full + s, c * 64, q_base + i * 128, h, bq);
+        }
+        // lse (pre-multiplied by log2 e) and delta for the 128 rows of this Q tile; rows past q_len get lse = +inf
+        // so that P == 0 there.
+        float* st = reinterpret_cast<float*>(smem + C::OFF_STAT + s * 1024);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int row = r * 32 + lane;
+          const int qrow = i * 128 + row;
+          float l = CUDART_INF_F, d = 0.f;
+          if (qrow < q_len) {
+            l = lse_row[qrow] * 1.4426950408889634f;
+            d = dl_row[qrow];
+          }
+          st[row] = l;
+          st[128 + row] = d;
+        }
+        mbar_arrive(stat_full + s);
+        if (lane == 0) {
+          mbar_wait(do_empty, (i & 1) ^ 1, BT_DO_EMPTY);
+          mbar_arrive_expect_tx(do_full, C::TILE);
+#pragma unroll
+          for (int c = 0; c < C::KCH; ++c)
+            tma_load_4d(smem + C::OFF_DO + c * C::CHUNK, &tm_do, do_full, c * 64, q_base + i * 128, h, bq);
+        }
+        __syncwarp();
+      }
+    } else if (warp == MMA_WARP && lane == 0) {
+      // ================================ MMA issuer ===============================================
+      constexpr uint32_t IDESC_ST = umma_idesc_bf16(128, 128, 0, 0);  // S^T, dP^T: both operands K-major
+      constexpr uint32_t IDESC_KD = umma_idesc_bf16(128, D, 0, 1);    // dV, dK: A K-major (TMEM / smem), B MN-major
+      constexpr uint32_t IDESC_DQ = umma_idesc_bf16(128, D, 1, 1);    // dQ: A = dS MN-major, B = K MN-major
+      const uint32_t k_s = smem_u32(smem + C::OFF_K), v_s = smem_u32(smem + C::OFF_V);
+      const uint32_t q_s = smem_u32(smem + C::OFF_Q), do_s = smem_u32(smem + C::OFF_DO);
+      const uint32_t ds_s = smem_u32(smem + C::OFF_DS);
+
+      auto mma_kmajor_pair = [&](uint32_t d_tmem, uint32_t a_base, uint32_t b_base) {  // D = A B^T over the head dim
+#pragma unroll
+        for (int c = 0; c < C::KCH; ++c)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_ss(d_tmem, umma_desc_sw128(a_base + c * C::CHUNK + kk * 32, 16, 1024),
+                    umma_desc_sw128(b_base + c * C::CHUNK + kk * 32, 16, 1024), IDESC_ST, (c | kk) != 0);
+      };
+
+      mbar_wait(kv_full, 0, BT_KV_FULL);
+      mbar_wait(q_full + 0, 0, BT_Q_FULL);
+      tc_fence_after();
+      mma_kmajor_pair(tmem + C::T_S, k_s, q_s);
+      tc_commit(s_full);
+      mbar_wait(do_full, 0, BT_DO_FULL);
+      tc_fence_after();
+      mma_kmajor_pair(tmem + C::T_DP, v_s, do_s);
+      tc_commit(dp_full);
+
+      for (int i = 0; i < n_q; ++i) {
+        const int s = i % C::QS;
+        const bool has_next = i + 1 < n_q;
+        // ---- dV += P^T dO_i ----
+        mbar_wait(p_ready, i & 1, BT_P_READY);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)
+          umma_ts(tmem + C::T_DV, tmem + C::T_P + kk * 8, umma_desc_sw128(do_s + kk * 2048, C::CHUNK, 1024), IDESC_KD,
+                  (i > 0) || kk != 0);
+        tc_commit(do_empty);
+        // ---- S^T for the next Q tile ----
+        if (has_next) {
+          const int sn = (i + 1) % C::QS;
+          mbar_wait(q_full + sn, ((i + 1) / C::QS) & 1, BT_Q_FULL);
+          tc_fence_after();
+          mma_kmajor_pair(tmem + C::T_S, k_s, q_s + sn * C::TILE);
+          tc_commit(s_full);
+        }
+        // ---- dK += dS^T Q_i ; dQ_i = dS K ----
+        mbar_wait(ds_ready, i & 1, BT_DS_READY);
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // k = 16 query rows per step; dS^T tile is [key][q] in two 64-q boxes
+          umma_ss(tmem + C::T_DK, umma_desc_sw128(ds_s + (kk >> 2) * C::CHUNK + (kk & 3) * 32, 16, 1024),
+                  umma_desc_sw128(q_s + s * C::TILE + kk * 2048, C::CHUNK, 1024), IDESC_KD, (i > 0) || kk != 0);
+        tc_commit(q_empty + s);
+        if (!C::DQ_ALIASES_DP && i > 0) {
+          mbar_wait(dq_drained, (i - 1) & 1, BT_DQ_DRAINED);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // k = 16 keys per step
+          umma_ss(tmem + C::T_DQ, umma_desc_sw128(ds_s + kk * 2048, C::CHUNK, 1024),
+                  umma_desc_sw128(k_s + kk * 2048, C::CHUNK, 1024), IDESC_DQ, kk != 0);
+        tc_commit(dq_full);
+        // ---- dP^T for the next Q tile ----
+        if (has_next) {
+          if (C::DQ_ALIASES_DP) {
+            mbar_wait(dq_drained, i & 1, BT_DQ_DRAINED);
+            tc_fence_after();
+          }
+          mbar_wait(do_full, (i + 1) & 1, BT_DO_FULL);
+          tc_fence_after();
+          mma_kmajor_pair(tmem + C::T_DP, v_s, do_s);
+          tc_commit(dp_full);
+        }
+      }
+      tc_commit(dkv_full);
+    }
+  } else if (warp >= 8) {
+    // ================================ dQ reduce warpgroup ==========================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t dq_addr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + C::T_DQ;
+    for (int i = 0; i < n_q; ++i) {
+      mbar_wait(dq_full, i & 1, BT_DQ_FULL);
+      tc_fence_after();
+      const int qrow = i * 128 + row;
+      const bool valid = qrow < q_len;
+      float* dst = dq_acc + ((static_cast<int64_t>(bq) * Lq_total + q_base + qrow) * p.seq.H + h) * D;
+#pragma unroll
+      for (int c0 = 0; c0 < D; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(dq_addr + c0, r);
+        tc_wait_ld();
+        if (c0 + 32 == D) {  // every TMEM read of this tile is complete: the issuer may overwrite the columns
+          tc_fence_before();
+          mbar_arrive(dq_drained);
+        }
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 4)
+            red_add_v4(dst + c0 + c, __uint_as_float(r[c]), __uint_as_float(r[c + 1]), __uint_as_float(r[c + 2]),
+                       __uint_as_float(r[c + 3]));
+        }
+      }
+    }
+  } else {
+    // ================================ compute warpgroups ===========================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    const int half = warp >> 2;  // which 64 query columns
+    const int quarter = warp & 3;
+    const int krow = quarter * 32 + lane;  // key row of this thread
+    const bool key_valid = krow < kv_valid;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    const uint32_t s_addr = tmem + lane_addr + C::T_S + half * 64;
+    const uint32_t p_addr = tmem + lane_addr + C::T_P + half * 32;
+    const uint32_t dp_addr = tmem + lane_addr + C::T_DP + half * 64;
+    const float sl2 = p.scale_log2;
+    // this thread's 128-byte row inside the dS^T box of its column half (128B swizzle: 16-byte chunk c -> c ^ (row & 7))
+    uint8_t* ds_row = smem + C::OFF_DS + half * C::CHUNK + krow * 128;
+    const int sw = krow & 7;
+
+    for (int i = 0; i < n_q; ++i) {
+      const int s = i % C::QS;
+      const float* st = reinterpret_cast<const float*>(smem + C::OFF_STAT + s * 1024) + half * 64;
+      mbar_wait(stat_full + s, (i / C::QS) & 1, BT_STAT_FULL);
+      mbar_wait(s_full, i & 1, BT_S_FULL);
+      tc_fence_after();
+      float pr[64];
+      {
+        uint32_t su[64];
+        tmem_ld_x32(s_addr, su);
+        tmem_ld_x32(s_addr + 32, su + 32);
+        tc_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 64; c += 4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(st + c);
+          pr[c + 0] = ex2_approx(fmaf(__uint_as_float(su[c + 0]), sl2, -l4.x));
+          pr[c + 1] = ex2_approx(fmaf(__uint_as_float(su[c + 1]), sl2, -l4.y));
+          pr[c + 2] = ex2_approx(fmaf(__uint_as_float(su[c + 2]), sl2, -l4.z));
+          pr[c + 3] = ex2_approx(fmaf(__uint_as_float(su[c + 3]), sl2, -l4.w));
+        }
+      }
+      if (!key_valid) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) pr[c] = 0.f;
+      }
+      {
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) pk[c] = pack_bf16x2(pr[2 * c], pr[2 * c + 1]);
+        tmem_st_x32(p_addr, pk);
+      }
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(p_ready);
+
+      // ---- dS^T = P^T o (dP^T - delta) ----
+      mbar_wait(dp_full, i & 1, BT_DP_FULL);
+      tc_fence_after();
+      uint32_t dsp[32];
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t du[32];
+        tmem_ld_x32(dp_addr + c0, du);
+        tc_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          const float4 d4 = *reinterpret_cast<const float4*>(st + 128 + c0 + c);
+          const float a0 = pr[c0 + c + 0] * (__uint_as_float(du[c + 0]) - d4.x);
+          const float a1 = pr[c0 + c + 1] * (__uint_as_float(du[c + 1]) - d4.y);
+          const float a2 = pr[c0 + c + 2] * (__uint_as_float(du[c + 2]) - d4.z);
+          const float a3 = pr[c0 + c + 3] * (__uint_as_float(du[c + 3]) - d4.w);
+          dsp[(c0 + c) >> 1] = pack_bf16x2(a0, a1);
+          dsp[((c0 + c) >> 1) + 1] = pack_bf16x2(a2, a3);
+        }
+      }
+      // the dS tile of the previous iteration must have been consumed by MMA4/MMA5
+      if (i > 0) mbar_wait(dq_full, (i - 1) & 1, BT_DQ_FULL);
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch)
+        *reinterpret_cast<uint4*>(ds_row + ((ch ^ sw) << 4)) =
+            make_uint4(dsp[4 * ch], dsp[4 * ch + 1], dsp[4 * ch + 2], dsp[4 * ch + 3]);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(ds_ready);
+    }
+
+    // ---- epilogue: dV, dK (this warpgroup's half of the head dim) ---------------------------------
+    mbar_wait(dkv_full, 0, BT_DKV_FULL);
+    tc_fence_after();
+    constexpr int HC = D / 2;
+    const bool store_row = kv0 + krow < k_rows_total;
+    __nv_bfloat16* dvp = p.dv + bk * p.dv_sb + static_cast<int64_t>(k_base + kv0 + krow) * p.dv_sl + h * p.dv_sh + half * HC;
+    __nv_bfloat16* dkp = p.dk + bk * p.dk_sb + static_cast<int64_t>(k_base + kv0 + krow) * p.dk_sl + h * p.dk_sh + half * HC;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t addr = tmem + lane_addr + (which == 0 ? C::T_DV : C::T_DK) + half * HC;
+      const float mul = which == 0 ? 1.f : p.scale;
+      __nv_bfloat16* dst = which == 0 ? dvp : dkp;
+#pragma unroll
+      for (int c0 = 0; c0 < HC; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(addr + c0, r);
+        tc_wait_ld();
+        if (store_row) {
+#pragma unroll
+          for (int c = 0; c < 32; c += 8) {
+            uint4 w;
+            // rows of masked (padding) keys hold exact zeros because P == 0 there
+            w.x = pack_bf16x2(__uint_as_float(r[c + 0]) * mul, __uint_as_float(r[c + 1]) * mul);
+            w.y = pack_bf16x2(__uint_as_float(r[c + 2]) * mul, __uint_as_float(r[c + 3]) * mul);
+            w.z = pack_bf16x2(__uint_as_float(r[c + 4]) * mul, __uint_as_float(r[c + 5]) * mul);
+            w.w = pack_bf16x2(__uint_as_float(r[c + 6]) * mul, __uint_as_float(r[c + 7]) * mul);
+            *reinterpret_cast<uint4*>(dst + c0 + c) = w;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// delta[b,h,row] = sum_d dO[row,d] * O[row,d]   (one warp per (row, head); 4 B/elem of traffic)
+template <int D>
+__global__ void attn_bwd_delta_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ o,
+                                      float* __restrict__ delta, int64_t do_sb, int64_t do_sl, int64_t do_sh,
+                                      int64_t o_sb, int64_t o_sl, int64_t o_sh, int B, int L, int H) {
+  const int64_t gw = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t total = static_cast<int64_t>(B) * L * H;
+  if (gw >= total) return;
+  const int h = static_cast<int>(gw % H);
+  const int64_t bl = gw / H;
+  const int l = static_cast<int>(bl % L), b = static_cast<int>(bl / L);
+  constexpr int PER = D / 32;  // 2 or 4 elements per lane
+  const __nv_bfloat16* a = dout + b * do_sb + static_cast<int64_t>(l) * do_sl + h * do_sh + lane * PER;
+  const __nv_bfloat16* c = o + b * o_sb + static_cast<int64_t>(l) * o_sl + h * o_sh + lane * PER;
+  float acc = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; i += 2) {
+    const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + i));
+    const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(c + i));
+    acc += x.x * y.x + x.y * y.y;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if (lane == 0) delta[(static_cast<int64_t>(b) * H + h) * L + l] = acc;
+}
+
+// dq = bf16(dq_acc * scale)
+__global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, int64_t sb,
+                                           int64_t sl, int64_t sh, int B, int L, int H, int D, float scale) {
+  const int64_t idx = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 8;
+  const int64_t total = static_cast<int64_t>(B) * L * H * D;
+  if (idx >= total) return;
+  const int d = static_cast<int>(idx % D);
+  const int64_t r = idx / D;
+  const int h = static_cast<int>(r % H);
+  const int64_t bl = r / H;
+  const int l = static_cast<int>(bl % L), b = static_cast<int>(bl / L);
+  const float4 x = *reinterpret_cast<const float4*>(acc + idx);
+  const float4 y = *reinterpret_cast<const float4*>(acc + idx + 4);
+  uint4 w;
+  w.x = pack_bf16x2(x.x * scale, x.y * scale);
+  w.y = pack_bf16x2(x.z * scale, x.w * scale);
+  w.z = pack_bf16x2(y.x * scale, y.y * scale);
+  w.w = pack_bf16x2(y.z * scale, y.w * scale);
+  *reinterpret_cast<uint4*>(dq + b * sb + static_cast<int64_t>(l) * sl + h * sh + d) = w;
+}
+
+template <int D>
+cudaError_t launch_bwd_one(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
+                           const CUtensorMap& tm_do, float* dq_acc, const AttnBwdParams& p, int Lq_total,
+                           cudaStream_t stream) {
+  using C = BwdCfg<D>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((p.seq.Lk + 127) / 128, p.seq.H, p.seq.nprob);
+  attn_bwd_kernel<D><<<grid, C::THREADS, C::BYTES, stream>>>(tm_q, tm_k, tm_v, tm_do, dq_acc, p, Lq_total);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_attn_bwd(int D, const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
+                            const CUtensorMap& tm_do, float* dq_acc, const AttnBwdParams& p, int Lq_total,
+                            cudaStream_t stream) {
+  if (D == 128) return launch_bwd_one<128>(tm_q, tm_k, tm_v, tm_do, dq_acc, p, Lq_total, stream);
+  if (D == 64) return launch_bwd_one<64>(tm_q, tm_k, tm_v, tm_do, dq_acc, p, Lq_total, stream);
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_attn_bwd_delta(int D, const void* dout, const void* o, float* delta, const int64_t* do_strides,
+                                  const int64_t* o_strides, int B, int L, int H, cudaStream_t stream) {
+  const int64_t warps = static_cast<int64_t>(B) * L * H;
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((warps * 32 + threads - 1) / threads);
+  auto a = static_cast<const __nv_bfloat16*>(dout);
+  auto c = static_cast<const __nv_bfloat16*>(o);
+  if (D == 128)
+    attn_bwd_delta_kernel<128><<<blocks, threads, 0, stream>>>(a, c, delta, do_strides[0], do_strides[1], do_strides[2],
+                                                               o_strides[0], o_strides[1], o_strides[2], B, L, H);
+  else
+    attn_bwd_delta_kernel<64><<<blocks, threads, 0, stream>>>(a, c, delta, do_strides[0], do_strides[1], do_strides[2],
+                                                              o_strides[0], o_strides[1], o_strides[2], B, L, H);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_attn_bwd_dq_convert(const float* acc, void* dq, const int64_t* dq_strides, int B, int L, int H, int D,
+                                       float scale, cudaStream_t stream) {
+  const int64_t total = static_cast<int64_t>(B) * L * H * D;
+  const int threads = 256;
+  const unsigned blocks = static_cast<unsigned>((total / 8 + threads - 1) / threads);
+  attn_bwd_dq_convert_kernel<<<blocks, threads, 0, stream>>>(acc, static_cast<__nv_bfloat16*>(dq), dq_strides[0],
+                                                             dq_strides[1], dq_strides[2], B, L, H, D, scale);
+  return cudaGetLastError();
+}
+
+cudaError_t attn_bwd_set_debug_ptr(unsigned int* ptr) { return cudaMemcpyToSymbol(g_vt_dbg, &ptr, sizeof(ptr)); }
+
+}  // namespace vt

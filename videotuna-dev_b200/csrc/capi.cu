@@ -169,4 +169,71 @@ int vt_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse
   return 0;
 }
 
+static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+int64_t vt_attn_bwd_workspace_bytes(int B, int H, int Lq, int D) {
+  if (B <= 0 || H <= 0 || Lq <= 0 || D <= 0) return 0;
+  const int64_t rows = static_cast<int64_t>(B) * Lq * H;
+  return align_up(rows * D * 4, 256) + align_up(rows * 4, 256);
+}
+
+int vt_attn_bwd(const void* dout, const void* q, const void* k, const void* v, const void* o, const float* lse,
+                void* dq, void* dk, void* dv, const int64_t* do_strides, const int64_t* q_strides,
+                const int64_t* k_strides, const int64_t* v_strides, const int64_t* o_strides,
+                const int64_t* dq_strides, const int64_t* dk_strides, const int64_t* dv_strides, int B, int H, int Lq,
+                int Lk, int D, const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k, int num_segments,
+                int max_seqlen_q, int max_seqlen_k, const int32_t* seqlens_k, float softmax_scale, void* workspace,
+                int64_t workspace_bytes, void* stream) {
+  VT_REQUIRE(dout && q && k && v && o && lse && dq && dk && dv && workspace, VT_ERR_NULL, "vt_attn_bwd: NULL argument");
+  VT_REQUIRE(do_strides && q_strides && k_strides && v_strides && o_strides && dq_strides && dk_strides && dv_strides,
+             VT_ERR_NULL, "vt_attn_bwd: NULL stride array");
+  if (int rc = check_attn_common(B, H, Lq, Lk, D, num_segments, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k)) return rc;
+  if (int rc = ensure_init()) return rc;
+  VT_REQUIRE(workspace_bytes >= vt_attn_bwd_workspace_bytes(B, H, Lq, D), VT_ERR_SHAPE, "workspace too small");
+  VT_REQUIRE(aligned16(workspace) && aligned16(dq) && aligned16(dk) && aligned16(dv) && aligned16(o) && aligned16(dout),
+             VT_ERR_ALIGN, "buffers must be 16-byte aligned");
+  for (const int64_t* s : {dq_strides, dk_strides, dv_strides, o_strides, do_strides})
+    VT_REQUIRE(s[0] % 8 == 0 && s[1] % 8 == 0 && s[2] % 8 == 0, VT_ERR_ALIGN, "strides must be multiples of 8 elements");
+  auto st = static_cast<cudaStream_t>(stream);
+  const int64_t rows = static_cast<int64_t>(B) * Lq * H;
+  float* dq_acc = static_cast<float*>(workspace);
+  float* delta = reinterpret_cast<float*>(static_cast<char*>(workspace) + align_up(rows * D * 4, 256));
+
+  if (Lk == 0) {  // no keys at all: every gradient is zero
+    VT_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(rows) * D * 4, st));
+    VT_CHECK_CUDA(launch_attn_bwd_dq_convert(dq_acc, dq, dq_strides, B, Lq, H, D, 0.f, st));
+    return 0;
+  }
+  CUtensorMap tm_q, tm_k, tm_v, tm_do;
+  if (int rc = make_tmap_4d(&tm_q, q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, D, Lq, H, B, q_strides, 64, 128)) return rc;
+  if (int rc = make_tmap_4d(&tm_k, k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, D, Lk, H, B, k_strides, 64, 128)) return rc;
+  if (int rc = make_tmap_4d(&tm_v, v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, D, Lk, H, B, v_strides, 64, 128)) return rc;
+  if (int rc = make_tmap_4d(&tm_do, dout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, D, Lq, H, B, do_strides, 64, 128)) return rc;
+
+  VT_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(rows) * D * 4, st));
+  VT_CHECK_CUDA(launch_attn_bwd_delta(D, dout, o, delta, do_strides, o_strides, B, Lq, H, st));
+
+  AttnBwdParams p{};
+  p.seq.cu_q = num_segments > 0 ? cu_seqlens_q : nullptr;
+  p.seq.cu_k = num_segments > 0 ? cu_seqlens_k : nullptr;
+  p.seq.seqlens_k = num_segments > 0 ? nullptr : seqlens_k;
+  p.seq.Lq = num_segments > 0 ? max_seqlen_q : Lq;
+  p.seq.Lk = num_segments > 0 ? max_seqlen_k : Lk;
+  p.seq.H = H;
+  p.seq.nprob = num_segments > 0 ? num_segments : B;
+  p.lse = lse;
+  p.delta = delta;
+  p.lse_sb = static_cast<int64_t>(H) * Lq;
+  p.lse_sh = Lq;
+  p.dk = static_cast<__nv_bfloat16*>(dk);
+  p.dv = static_cast<__nv_bfloat16*>(dv);
+  p.dk_sb = dk_strides[0]; p.dk_sl = dk_strides[1]; p.dk_sh = dk_strides[2];
+  p.dv_sb = dv_strides[0]; p.dv_sl = dv_strides[1]; p.dv_sh = dv_strides[2];
+  p.scale = softmax_scale;
+  p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  VT_CHECK_CUDA(launch_attn_bwd(D, tm_q, tm_k, tm_v, tm_do, dq_acc, p, Lq, st));
+  VT_CHECK_CUDA(launch_attn_bwd_dq_convert(dq_acc, dq, dq_strides, B, Lq, H, D, softmax_scale, st));
+  return 0;
+}
+
 }  // extern "C"

@@ -13,7 +13,8 @@
 namespace vt {
 namespace {
 
-constexpr int RPI = 4;  // rows per iteration (independent 16-byte loads in flight per thread)
+// Kernels are templated on <MAXT, RPI>: MAXT bounds the CTA size (register budget = 64K / MAXT) and RPI is the number
+// of rows processed per iteration (independent 16-byte loads in flight per thread). Wide rows trade RPI for threads.
 
 struct alignas(16) Vec8 {
   uint4 u;
@@ -80,7 +81,8 @@ __device__ __forceinline__ void block_sum(float* v, float* red) {
 // ------------------------------------------------------------------------------------------------------------
 // LayerNorm + modulate
 // ------------------------------------------------------------------------------------------------------------
-__global__ void ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+template <int MAXT, int RPI>
+__global__ void __launch_bounds__(MAXT) ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                        float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                        const float* __restrict__ scale, const float* __restrict__ shift, int L, int C,
@@ -155,7 +157,8 @@ __global__ void ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv
 
 // dx = rstd * (gh - mean(gh) - xh * mean(gh * xh)),  gh = dy * (1+scale) * gamma,  xh = (x - mean) * rstd
 // dshift += dy; dscale += dy * (xh*gamma + beta); dbeta += dy*(1+scale); dgamma += dy*(1+scale)*xh
-__global__ void ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+template <int MAXT, int RPI>
+__global__ void __launch_bounds__(MAXT) ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                        const float* __restrict__ mean, const float* __restrict__ rstd,
                                        __nv_bfloat16* __restrict__ dx, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, const float* __restrict__ scale,
@@ -246,7 +249,8 @@ __global__ void ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ dy, con
 // ------------------------------------------------------------------------------------------------------------
 // gated residual
 // ------------------------------------------------------------------------------------------------------------
-__global__ void gate_residual_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ br,
+template <int MAXT, int RPI>
+__global__ void __launch_bounds__(MAXT) gate_residual_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ br,
                                          __nv_bfloat16* __restrict__ y, const float* __restrict__ gate, int L, int C) {
   const int b = blockIdx.y;
   const int col = threadIdx.x * 8;
@@ -278,7 +282,8 @@ __global__ void gate_residual_fwd_kernel(const __nv_bfloat16* __restrict__ x, co
   }
 }
 
-__global__ void gate_residual_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ br,
+template <int MAXT, int RPI>
+__global__ void __launch_bounds__(MAXT) gate_residual_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ br,
                                          __nv_bfloat16* __restrict__ dbr, const float* __restrict__ gate,
                                          float* __restrict__ dgate, int L, int C) {
   const int b = blockIdx.y;
@@ -325,8 +330,8 @@ __global__ void gate_residual_bwd_kernel(const __nv_bfloat16* __restrict__ dy, c
 //   y[2i]   = n[2i]*cos[2i]   - n[2i+1]*sin[2i]          (n = normalised x)
 //   y[2i+1] = n[2i+1]*cos[2i+1] + n[2i]*sin[2i+1]       tokens l >= L_rope are not rotated
 // ------------------------------------------------------------------------------------------------------------
-template <int NORM>
-__global__ void rmsnorm_rope_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+template <int NORM, int MAXT, int RPI>
+__global__ void __launch_bounds__(MAXT) rmsnorm_rope_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                         float* __restrict__ rstd_out, const float* __restrict__ w,
                                         const float* __restrict__ cosT, const float* __restrict__ sinT, int64_t x_sb,
                                         int64_t x_sl, int64_t x_sh, int64_t y_sb, int64_t y_sl, int64_t y_sh, int L,
@@ -404,8 +409,8 @@ __global__ void rmsnorm_rope_fwd_kernel(const __nv_bfloat16* __restrict__ x, __n
 
 // Backward: g = R^T dy (inverse rotation), then RMSNorm backward:
 //   xh = x*rstd; gw = g*w; dx = rstd * (gw - xh * mean(gw*xh)); dw += g*xh
-template <int NORM>
-__global__ void rmsnorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+template <int NORM, int MAXT, int RPI>
+__global__ void __launch_bounds__(MAXT) rmsnorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                         const float* __restrict__ rstd_in, __nv_bfloat16* __restrict__ dx,
                                         float* __restrict__ dw, const float* __restrict__ w,
                                         const float* __restrict__ cosT, const float* __restrict__ sinT, int64_t g_sb,
@@ -497,7 +502,16 @@ __global__ void rmsnorm_rope_bwd_kernel(const __nv_bfloat16* __restrict__ dy, co
   }
 }
 
-int row_launch_dims(int L, int C, int B, dim3* grid, dim3* block) {
+// CTA size = ceil(C/8) rounded to a warp; (MAXT, RPI) chosen so the register budget 64K/MAXT holds RPI rows in flight.
+struct RowCfg { int maxt, rpi; };
+inline RowCfg row_cfg(int C) {
+  const int threads = ((C / 8) + 31) / 32 * 32;
+  if (threads <= 256) return {256, 4};
+  if (threads <= 512) return {512, 4};
+  if (threads <= 768) return {768, 2};
+  return {1024, 1};
+}
+int row_launch_dims(int L, int C, int B, int RPI, dim3* grid, dim3* block) {
   VT_REQUIRE(C % 8 == 0 && C >= 8, VT_ERR_SHAPE, "row width %d must be a multiple of 8", C);
   const int threads = ((C / 8) + 31) / 32 * 32;
   VT_REQUIRE(threads <= 1024, VT_ERR_SHAPE, "row width %d exceeds 8192", C);
@@ -514,6 +528,19 @@ int row_launch_dims(int L, int C, int B, dim3* grid, dim3* block) {
   return 0;
 }
 
+// Expands KERNEL<..., MAXT, RPI><<<grid, block, 0, st>>>(ARGS) for the configuration row_cfg() selects.
+#define VT_ROW_DISPATCH(C_, B_, L_, ST_, KERNEL, ...)                                   \
+  do {                                                                                    \
+    const RowCfg cfg_ = row_cfg(C_);                                                      \
+    dim3 grid_, block_;                                                                   \
+    if (int rc_ = row_launch_dims(L_, C_, B_, cfg_.rpi, &grid_, &block_)) return rc_;     \
+    if (cfg_.maxt == 256) KERNEL(256, 4)<<<grid_, block_, 0, ST_>>>(__VA_ARGS__);        \
+    else if (cfg_.maxt == 512) KERNEL(512, 4)<<<grid_, block_, 0, ST_>>>(__VA_ARGS__);   \
+    else if (cfg_.maxt == 768) KERNEL(768, 2)<<<grid_, block_, 0, ST_>>>(__VA_ARGS__);   \
+    else KERNEL(1024, 1)<<<grid_, block_, 0, ST_>>>(__VA_ARGS__);                        \
+    VT_CHECK_CUDA(cudaGetLastError());                                                    \
+  } while (0)
+
 }  // namespace
 }  // namespace vt
 
@@ -526,11 +553,10 @@ int vt_ln_modulate_fwd(const void* x, void* y, float* mean, float* rstd, const f
                        const float* scale, const float* shift, int B, int L, int C, float eps, void* stream) {
   VT_REQUIRE(x && y, VT_ERR_NULL, "vt_ln_modulate_fwd: NULL argument");
   VT_REQUIRE(aligned16(x) && aligned16(y), VT_ERR_ALIGN, "x/y must be 16-byte aligned");
-  dim3 grid, block;
-  if (int rc = row_launch_dims(L, C, B, &grid, &block)) return rc;
-  ln_modulate_fwd_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+#define K_(M, R) ln_modulate_fwd_kernel<M, R>
+  VT_ROW_DISPATCH(C, B, L, static_cast<cudaStream_t>(stream), K_,
       static_cast<const bf16*>(x), static_cast<bf16*>(y), mean, rstd, gamma, beta, scale, shift, L, C, eps);
-  VT_CHECK_CUDA(cudaGetLastError());
+#undef K_
   return 0;
 }
 
@@ -539,12 +565,11 @@ int vt_ln_modulate_bwd(const void* dy, const void* x, const float* mean, const f
                        float* dscale, float* dshift, int B, int L, int C, void* stream) {
   VT_REQUIRE(dy && x && mean && rstd && dx, VT_ERR_NULL, "vt_ln_modulate_bwd: NULL argument");
   VT_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx), VT_ERR_ALIGN, "dy/x/dx must be 16-byte aligned");
-  dim3 grid, block;
-  if (int rc = row_launch_dims(L, C, B, &grid, &block)) return rc;
-  ln_modulate_bwd_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+#define K_(M, R) ln_modulate_bwd_kernel<M, R>
+  VT_ROW_DISPATCH(C, B, L, static_cast<cudaStream_t>(stream), K_,
       static_cast<const bf16*>(dy), static_cast<const bf16*>(x), mean, rstd, static_cast<bf16*>(dx), gamma, beta,
       scale, dgamma, dbeta, dscale, dshift, L, C);
-  VT_CHECK_CUDA(cudaGetLastError());
+#undef K_
   return 0;
 }
 
@@ -552,11 +577,10 @@ int vt_gate_residual_fwd(const void* x, const void* branch, void* y, const float
                          void* stream) {
   VT_REQUIRE(x && branch && y, VT_ERR_NULL, "vt_gate_residual_fwd: NULL argument");
   VT_REQUIRE(aligned16(x) && aligned16(branch) && aligned16(y), VT_ERR_ALIGN, "x/branch/y must be 16-byte aligned");
-  dim3 grid, block;
-  if (int rc = row_launch_dims(L, C, B, &grid, &block)) return rc;
-  gate_residual_fwd_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+#define K_(M, R) gate_residual_fwd_kernel<M, R>
+  VT_ROW_DISPATCH(C, B, L, static_cast<cudaStream_t>(stream), K_,
       static_cast<const bf16*>(x), static_cast<const bf16*>(branch), static_cast<bf16*>(y), gate, L, C);
-  VT_CHECK_CUDA(cudaGetLastError());
+#undef K_
   return 0;
 }
 
@@ -565,11 +589,10 @@ int vt_gate_residual_bwd(const void* dy, const void* branch, void* dbranch, cons
   VT_REQUIRE(dy && dbranch, VT_ERR_NULL, "vt_gate_residual_bwd: NULL argument");
   VT_REQUIRE(dgate == nullptr || branch != nullptr, VT_ERR_NULL, "dgate needs branch");
   VT_REQUIRE(aligned16(dy) && aligned16(dbranch) && aligned16(branch), VT_ERR_ALIGN, "buffers must be 16-byte aligned");
-  dim3 grid, block;
-  if (int rc = row_launch_dims(L, C, B, &grid, &block)) return rc;
-  gate_residual_bwd_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+#define K_(M, R) gate_residual_bwd_kernel<M, R>
+  VT_ROW_DISPATCH(C, B, L, static_cast<cudaStream_t>(stream), K_,
       static_cast<const bf16*>(dy), static_cast<const bf16*>(branch), static_cast<bf16*>(dbranch), gate, dgate, L, C);
-  VT_CHECK_CUDA(cudaGetLastError());
+#undef K_
   return 0;
 }
 
@@ -590,18 +613,19 @@ int vt_qk_rmsnorm_rope_fwd(const void* x, void* y, float* rstd_out, const float*
   VT_REQUIRE(norm_mode >= 0 && norm_mode <= 2, VT_ERR_SHAPE, "norm_mode %d", norm_mode);
   if (int rc = check_rope_args(x_strides, H, D, "x")) return rc;
   if (int rc = check_rope_args(y_strides, H, D, "y")) return rc;
-  dim3 grid, block;
-  if (int rc = row_launch_dims(L, H * D, B, &grid, &block)) return rc;
   auto st = static_cast<cudaStream_t>(stream);
-#define VT_LAUNCH_RR(NM)                                                                                              \
-  rmsnorm_rope_fwd_kernel<NM><<<grid, block, 0, st>>>(static_cast<const bf16*>(x), static_cast<bf16*>(y), rstd_out, w, \
-                                                      cos, sin, x_strides[0], x_strides[1], x_strides[2], y_strides[0], \
-                                                      y_strides[1], y_strides[2], L, H, D, L_rope, eps)
-  if (norm_mode == 0) VT_LAUNCH_RR(0);
-  else if (norm_mode == 1) VT_LAUNCH_RR(1);
-  else VT_LAUNCH_RR(2);
-#undef VT_LAUNCH_RR
-  VT_CHECK_CUDA(cudaGetLastError());
+#define VT_RR_ARGS static_cast<const bf16*>(x), static_cast<bf16*>(y), rstd_out, w, cos, sin, x_strides[0], x_strides[1], \
+                   x_strides[2], y_strides[0], y_strides[1], y_strides[2], L, H, D, L_rope, eps
+#define K0_(M, R) rmsnorm_rope_fwd_kernel<0, M, R>
+#define K1_(M, R) rmsnorm_rope_fwd_kernel<1, M, R>
+#define K2_(M, R) rmsnorm_rope_fwd_kernel<2, M, R>
+  if (norm_mode == 0) VT_ROW_DISPATCH(H * D, B, L, st, K0_, VT_RR_ARGS);
+  else if (norm_mode == 1) VT_ROW_DISPATCH(H * D, B, L, st, K1_, VT_RR_ARGS);
+  else VT_ROW_DISPATCH(H * D, B, L, st, K2_, VT_RR_ARGS);
+#undef K0_
+#undef K1_
+#undef K2_
+#undef VT_RR_ARGS
   return 0;
 }
 
@@ -618,19 +642,20 @@ int vt_qk_rmsnorm_rope_bwd(const void* dy, const void* x, const float* rstd, voi
   if (int rc = check_rope_args(dx_strides, H, D, "dx")) return rc;
   const int64_t zero3[3] = {0, 0, 0};
   const int64_t* xs = x_strides ? x_strides : zero3;
-  dim3 grid, block;
-  if (int rc = row_launch_dims(L, H * D, B, &grid, &block)) return rc;
   auto st = static_cast<cudaStream_t>(stream);
-#define VT_LAUNCH_RB(NM)                                                                                           \
-  rmsnorm_rope_bwd_kernel<NM><<<grid, block, 0, st>>>(                                                             \
-      static_cast<const bf16*>(dy), static_cast<const bf16*>(x), rstd, static_cast<bf16*>(dx), dw_accum, w, cos, sin, \
-      dy_strides[0], dy_strides[1], dy_strides[2], xs[0], xs[1], xs[2], dx_strides[0], dx_strides[1], dx_strides[2], L, \
-      H, D, L_rope)
-  if (norm_mode == 0) VT_LAUNCH_RB(0);
-  else if (norm_mode == 1) VT_LAUNCH_RB(1);
-  else VT_LAUNCH_RB(2);
-#undef VT_LAUNCH_RB
-  VT_CHECK_CUDA(cudaGetLastError());
+#define VT_RB_ARGS static_cast<const bf16*>(dy), static_cast<const bf16*>(x), rstd, static_cast<bf16*>(dx), dw_accum, w, cos, \
+                   sin, dy_strides[0], dy_strides[1], dy_strides[2], xs[0], xs[1], xs[2], dx_strides[0], dx_strides[1],        \
+                   dx_strides[2], L, H, D, L_rope
+#define K0_(M, R) rmsnorm_rope_bwd_kernel<0, M, R>
+#define K1_(M, R) rmsnorm_rope_bwd_kernel<1, M, R>
+#define K2_(M, R) rmsnorm_rope_bwd_kernel<2, M, R>
+  if (norm_mode == 0) VT_ROW_DISPATCH(H * D, B, L, st, K0_, VT_RB_ARGS);
+  else if (norm_mode == 1) VT_ROW_DISPATCH(H * D, B, L, st, K1_, VT_RB_ARGS);
+  else VT_ROW_DISPATCH(H * D, B, L, st, K2_, VT_RB_ARGS);
+#undef K0_
+#undef K1_
+#undef K2_
+#undef VT_RB_ARGS
   return 0;
 }
 

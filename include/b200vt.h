@@ -39,6 +39,18 @@ int vt_init(int device);
  * {call-site tag, blockIdx.x, blockIdx.y | blockIdx.z<<16, threadIdx.x}; all zero if none fired. */
 int vt_debug_watchdog(uint32_t out[4]);
 
+/* Optional per-kernel device timing (bench.py's roofline leg). While enabled, the attention entry points bracket each
+ * of their kernel launches with CUDA events recorded on the caller's stream. vt_profile_read() waits for the recorded
+ * events, adds their elapsed times into per-kernel totals and returns the totals accumulated since the last
+ * vt_profile_enable(1). Kernel ids: */
+#define VT_K_ATTN_FWD 0
+#define VT_K_ATTN_BWD 1        /* the 5-GEMM backward kernel */
+#define VT_K_ATTN_BWD_DELTA 2  /* rowsum(dO * O) */
+#define VT_K_ATTN_BWD_DQ 3     /* fp32 dQ accumulator -> bf16 */
+#define VT_K_COUNT 4
+int vt_profile_enable(int on);
+int vt_profile_read(int kernel_id, double* total_ms, int64_t* launches);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Dense non-causal attention forward:  O = softmax(scale * Q K^T) V,  LSE = logsumexp(scale * Q K^T) (natural log)
  * Replaces: lvdm CrossAttention.forward einsum/softmax/einsum   videotuna/models/lvdm/modules/attention.py:128-144

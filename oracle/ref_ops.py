@@ -86,6 +86,19 @@ def hunyuan_attention_torch(q: Tensor, k: Tensor, v: Tensor, attn_mask: Optional
     return sdpa_blhd(q, k, v, attn_mask).reshape(b, s, h * d)
 
 
+def hunyuan_attention_torch_fused(q: Tensor, k: Tensor, v: Tensor, attn_mask: Optional[Tensor] = None) -> Tensor:
+    """The same mode="torch" branch (attenion.py:97-106,151-156) written with the call the reference itself makes,
+    F.scaled_dot_product_attention, instead of the explicit softmax above. It never materialises the (S,S) score
+    matrix, so it is the form bench.py times on the host cores at the full 119 056-token sequence
+    (cpu_baseline / --impl reference). Checked against hunyuan_attention_torch in tests/test_oracle_golden.py."""
+    b, s, h, d = q.shape
+    if attn_mask is not None and attn_mask.dtype != torch.bool:
+        attn_mask = attn_mask.to(q.dtype)
+    x = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), attn_mask=attn_mask,
+                                       dropout_p=0.0, is_causal=False)
+    return x.transpose(1, 2).reshape(b, s, h * d)
+
+
 def hunyuan_cu_seqlens(text_mask: Tensor, img_len: int) -> Tensor:
     """get_cu_seqlens, attenion.py:34-57: [0, img+valid_0, img+max_0, (img+max)+img+valid_1, 2*(img+max), ...]."""
     batch_size = text_mask.shape[0]

@@ -19,6 +19,14 @@ def test_hunyuan_attention_torch_mode():
     assert R.max_rel_err(R.hunyuan_attention_torch(q, k, v, g["attn_mask"]), g["out_mask"]) < TOL
 
 
+def test_hunyuan_attention_torch_fused_form_matches_golden():
+    # the F.scaled_dot_product_attention form that bench.py times on the host cores
+    g = load_golden("hunyuan_attention")
+    q, k, v = f32(g["q"]), f32(g["k"]), f32(g["v"])
+    assert R.max_rel_err(R.hunyuan_attention_torch_fused(q, k, v), g["out_plain"]) < TOL
+    assert R.max_rel_err(R.hunyuan_attention_torch_fused(q, k, v, g["attn_mask"]), g["out_mask"]) < TOL
+
+
 def test_hunyuan_flash_semantics_equal_masked_torch_mode():
     g = load_golden("hunyuan_attention")
     q, k, v = f32(g["q"]), f32(g["k"]), f32(g["v"])

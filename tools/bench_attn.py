@@ -84,6 +84,13 @@ def main():
                 with sdpa_kernel([SDPBackend.CUDNN_ATTENTION]):
                     ms = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(qt, kt, vt), args.iters)
                 rec["cudnn_fwd_ms"], rec["cudnn_fwd_tflops"] = round(ms, 3), round(flops_f / ms / 1e9, 1)
+                if args.bwd:
+                    qg, kg, vg = (t.detach().clone().requires_grad_(True) for t in (qt, kt, vt))
+                    with sdpa_kernel([SDPBackend.CUDNN_ATTENTION]):
+                        og = torch.nn.functional.scaled_dot_product_attention(qg, kg, vg)
+                        dot = do.transpose(1, 2)
+                        ms = timeit(lambda: torch.autograd.grad(og, (qg, kg, vg), dot, retain_graph=True), args.iters)
+                    rec["cudnn_bwd_ms"], rec["cudnn_bwd_tflops"] = round(ms, 3), round(2.5 * flops_f / ms / 1e9, 1)
             except Exception as e:  # noqa: BLE001
                 rec["sdpa_error"] = repr(e)[:120]
         print(json.dumps(rec), flush=True)

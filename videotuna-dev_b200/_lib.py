@@ -20,6 +20,8 @@ _SIGS = {
     "vt_last_error": [C.c_char_p, C.c_size_t],
     "vt_init": [C.c_int],
     "vt_debug_watchdog": [C.POINTER(C.c_uint32)],
+    "vt_profile_enable": [C.c_int],
+    "vt_profile_read": [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
     "vt_attn_fwd": [vp, vp, vp, vp, vp, c_i64p, c_i64p, c_i64p, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                     vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_float, vp],
     "vt_attn_bwd_workspace_bytes": [C.c_int, C.c_int, C.c_int, C.c_int],
@@ -88,6 +90,20 @@ def watchdog() -> tuple[int, int, int, int]:
     arr = (C.c_uint32 * 4)()
     lib().vt_debug_watchdog(arr)
     return tuple(int(v) for v in arr)
+
+
+K_ATTN_FWD, K_ATTN_BWD, K_ATTN_BWD_DELTA, K_ATTN_BWD_DQ = 0, 1, 2, 3
+
+
+def profile_enable(on: bool) -> None:
+    call("vt_profile_enable", int(on))
+
+
+def profile_read(kernel_id: int) -> tuple[float, int]:
+    """(total device ms, launches) of one kernel id since profile_enable(True); waits for the recorded events."""
+    ms, n = C.c_double(0), C.c_int64(0)
+    call("vt_profile_read", kernel_id, C.byref(ms), C.byref(n))
+    return ms.value, n.value
 
 
 def call(name: str, *args):

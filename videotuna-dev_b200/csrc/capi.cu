@@ -1,6 +1,7 @@
 // capi.cu — library state, TMA tensor-map construction and the attention entry points of the C ABI.
 #include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "attn_common.h"
 #include "capi_util.h"
@@ -83,6 +84,53 @@ int make_tmap_4d(CUtensorMap* out, const void* ptr, CUtensorMapDataType dt, int 
 
 int lib_init() { return ensure_init(); }
 
+// ---- optional per-kernel event timing (vt_profile_*) ---------------------------------------------------------
+namespace {
+struct ProfSpan {
+  int id;
+  cudaEvent_t e0, e1;
+};
+struct Profiler {
+  std::mutex mu;
+  bool on = false;
+  std::vector<ProfSpan> pending;
+  std::vector<cudaEvent_t> pool;
+  double total_ms[VT_K_COUNT] = {0};
+  int64_t launches[VT_K_COUNT] = {0};
+  cudaEvent_t get() {
+    if (!pool.empty()) {
+      cudaEvent_t e = pool.back();
+      pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+Profiler g_prof;
+}  // namespace
+
+// RAII span: records an event before and after whatever is launched on `st` during its lifetime.
+struct ProfScope {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaStream_t st;
+  int id;
+  ProfScope(int kernel_id, cudaStream_t stream) : st(stream), id(kernel_id) {
+    std::lock_guard<std::mutex> lock(g_prof.mu);
+    if (!g_prof.on) return;
+    e0 = g_prof.get();
+    e1 = g_prof.get();
+    if (e0 != nullptr) cudaEventRecord(e0, st);
+  }
+  ~ProfScope() {
+    if (e0 == nullptr || e1 == nullptr) return;
+    cudaEventRecord(e1, st);
+    std::lock_guard<std::mutex> lock(g_prof.mu);
+    g_prof.pending.push_back({id, e0, e1});
+  }
+};
+
 }  // namespace vt
 
 using namespace vt;
@@ -105,6 +153,40 @@ int vt_last_error(char* buf, size_t n) {
 int vt_init(int device) {
   VT_CHECK_CUDA(cudaSetDevice(device));
   return ensure_init();
+}
+
+int vt_profile_enable(int on) {
+  std::lock_guard<std::mutex> lock(g_prof.mu);
+  for (auto& sp : g_prof.pending) {
+    g_prof.pool.push_back(sp.e0);
+    g_prof.pool.push_back(sp.e1);
+  }
+  g_prof.pending.clear();
+  for (int i = 0; i < VT_K_COUNT; ++i) {
+    g_prof.total_ms[i] = 0;
+    g_prof.launches[i] = 0;
+  }
+  g_prof.on = on != 0;
+  return 0;
+}
+
+int vt_profile_read(int kernel_id, double* total_ms, int64_t* launches) {
+  VT_REQUIRE(kernel_id >= 0 && kernel_id < VT_K_COUNT, VT_ERR_SHAPE, "kernel id %d out of range", kernel_id);
+  VT_REQUIRE(total_ms != nullptr && launches != nullptr, VT_ERR_NULL, "vt_profile_read: NULL output");
+  std::lock_guard<std::mutex> lock(g_prof.mu);
+  for (auto& sp : g_prof.pending) {
+    VT_CHECK_CUDA(cudaEventSynchronize(sp.e1));
+    float ms = 0.f;
+    VT_CHECK_CUDA(cudaEventElapsedTime(&ms, sp.e0, sp.e1));
+    g_prof.total_ms[sp.id] += ms;
+    g_prof.launches[sp.id] += 1;
+    g_prof.pool.push_back(sp.e0);
+    g_prof.pool.push_back(sp.e1);
+  }
+  g_prof.pending.clear();
+  *total_ms = g_prof.total_ms[kernel_id];
+  *launches = g_prof.launches[kernel_id];
+  return 0;
 }
 
 int vt_debug_watchdog(uint32_t out[4]) {
@@ -165,7 +247,10 @@ int vt_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse
   p.lse_sh = Lq;
   p.scale = softmax_scale;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  VT_CHECK_CUDA(launch_attn_fwd(D, tm_q, tm_k, tm_v, p, 0, static_cast<cudaStream_t>(stream)));
+  {
+    ProfScope span(VT_K_ATTN_FWD, static_cast<cudaStream_t>(stream));
+    VT_CHECK_CUDA(launch_attn_fwd(D, tm_q, tm_k, tm_v, p, 0, static_cast<cudaStream_t>(stream)));
+  }
   return 0;
 }
 
@@ -211,7 +296,10 @@ int vt_attn_bwd(const void* dout, const void* q, const void* k, const void* v, c
   if (int rc = make_tmap_4d(&tm_do, dout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, D, Lq, H, B, do_strides, 64, 128)) return rc;
 
   VT_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(rows) * D * 4, st));
-  VT_CHECK_CUDA(launch_attn_bwd_delta(D, dout, o, delta, do_strides, o_strides, B, Lq, H, st));
+  {
+    ProfScope span(VT_K_ATTN_BWD_DELTA, st);
+    VT_CHECK_CUDA(launch_attn_bwd_delta(D, dout, o, delta, do_strides, o_strides, B, Lq, H, st));
+  }
 
   AttnBwdParams p{};
   p.seq.cu_q = num_segments > 0 ? cu_seqlens_q : nullptr;
@@ -231,8 +319,14 @@ int vt_attn_bwd(const void* dout, const void* q, const void* k, const void* v, c
   p.dv_sb = dv_strides[0]; p.dv_sl = dv_strides[1]; p.dv_sh = dv_strides[2];
   p.scale = softmax_scale;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
-  VT_CHECK_CUDA(launch_attn_bwd(D, tm_q, tm_k, tm_v, tm_do, dq_acc, p, Lq, st));
-  VT_CHECK_CUDA(launch_attn_bwd_dq_convert(dq_acc, dq, dq_strides, B, Lq, H, D, softmax_scale, st));
+  {
+    ProfScope span(VT_K_ATTN_BWD, st);
+    VT_CHECK_CUDA(launch_attn_bwd(D, tm_q, tm_k, tm_v, tm_do, dq_acc, p, Lq, st));
+  }
+  {
+    ProfScope span(VT_K_ATTN_BWD_DQ, st);
+    VT_CHECK_CUDA(launch_attn_bwd_dq_convert(dq_acc, dq, dq_strides, B, Lq, H, D, softmax_scale, st));
+  }
   return 0;
 }
 

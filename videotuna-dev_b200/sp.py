@@ -1,0 +1,246 @@
+"""Ulysses sequence parallelism for the DiT attention path (one process per GPU, NCCL all-to-all over NVLink/NVSwitch).
+
+Replaces, for the hot path only, what the reference delegates to xfuser's `xFuserLongContextAttention` [ext, xfuser
+0.4.3.post2; not vendored, parity unpinned]:
+    hunyuan  parallel_attention(hybrid_seq_parallel_attn, ...)     videotuna/models/hunyuan/hyvideo_t2v/modules/attenion.py:159-212
+    hunyuan  parallelize_transformer (sets block.hybrid_seq_parallel_attn)  videotuna/flow/hunyuanvideo.py:114-178
+    wan      usp_attn_forward                                       videotuna/models/wan/wan/distributed/xdit_context_parallel.py:149-192
+and follows the autograd semantics of the reference's only in-tree Ulysses code (OpenSora `_AllToAll`,
+videotuna/models/opensora/acceleration/communications.py:23-58): the backward of an all-to-all is the all-to-all with
+scatter/gather dims swapped.
+
+Layout: activations live sequence-sharded (B, L/P, H, D). One all-to-all turns q, k, v into (B, L, H/P, D); the local
+kernel attends over the full sequence for H/P heads; one all-to-all returns (B, L/P, H, D). With B == 1 (every
+BASELINE config) the receive side of seq->head and the send side of head->seq are plain views, so each exchange costs
+exactly one pack copy. Replicated text tokens ("rear" joint strategy) are head-sliced locally and written behind the
+gathered image tokens in the same buffer, so no concatenation copy exists either.
+
+SP correctness is *defined* as equality with the single-GPU result on the same inputs.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+
+def _world(group) -> int:
+    return dist.get_world_size(group) if dist.is_initialized() else 1
+
+
+def _rank(group) -> int:
+    return dist.get_rank(group) if dist.is_initialized() else 0
+
+
+def _a2a(send: Tensor, group, out: Optional[Tensor] = None) -> Tensor:
+    """all_to_all_single over dim 0 (P equal chunks). `send` must be contiguous; `out` (optional) likewise."""
+    recv = torch.empty_like(send) if out is None else out
+    dist.all_to_all_single(recv, send, group=group)
+    return recv
+
+
+def _pack_seq_to_head(x: Tensor, P: int) -> Tensor:
+    """(B, Ls, H, D) -> send buffer (P, B, Ls, H/P, D): chunk p carries head group p of the local tokens."""
+    B, Ls, H, D = x.shape
+    return x.reshape(B, Ls, P, H // P, D).permute(2, 0, 1, 3, 4).contiguous()
+
+
+def _unpack_seq_to_head(recv: Tensor) -> Tensor:
+    """receive buffer (P, B, Ls, Hp, D), index 0 = source rank = sequence chunk -> (B, P*Ls, Hp, D)."""
+    P, B, Ls, Hp, D = recv.shape
+    if B == 1:
+        return recv.view(1, P * Ls, Hp, D)
+    return recv.permute(1, 0, 2, 3, 4).reshape(B, P * Ls, Hp, D)
+
+
+def _pack_head_to_seq(y: Tensor, P: int) -> Tensor:
+    """(B, L, Hp, D) -> send buffer (P, B, L/P, Hp, D): chunk p carries sequence chunk p of the local head group."""
+    B, L, Hp, D = y.shape
+    if B == 1 and y.is_contiguous():
+        return y.view(P, 1, L // P, Hp, D)
+    return y.reshape(B, P, L // P, Hp, D).permute(1, 0, 2, 3, 4).contiguous()
+
+
+def _unpack_head_to_seq(recv: Tensor) -> Tensor:
+    """receive buffer (P, B, Ls, Hp, D), index 0 = source rank = head group -> (B, Ls, P*Hp, D)."""
+    P, B, Ls, Hp, D = recv.shape
+    return recv.permute(1, 2, 0, 3, 4).reshape(B, Ls, P * Hp, D)
+
+
+class _SeqToHead(torch.autograd.Function):
+    """(B, L/P, H, D) sequence-sharded -> (B, L + T, H/P, D) head-sharded, with T optional rows left free at the rear
+    (filled by the caller with the head slice of replicated text tokens)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, group, rear: int):
+        P = _world(group)
+        ctx.group, ctx.P, ctx.rear = group, P, rear
+        B, Ls, H, D = x.shape
+        if H % P != 0:
+            raise ValueError(f"Ulysses needs num_heads % world_size == 0 (H={H}, P={P})")
+        Hp = H // P
+        send = _pack_seq_to_head(x, P)
+        if B == 1:
+            full = x.new_empty((1, P * Ls + rear, Hp, D))
+            _a2a(send, group, out=full[:, : P * Ls].view(P, 1, Ls, Hp, D))
+            return full
+        out = _unpack_seq_to_head(_a2a(send, group))
+        if rear:
+            out = torch.cat([out, out.new_empty((B, rear, Hp, D))], dim=1)
+        return out
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        P = ctx.P
+        L = g.shape[1] - ctx.rear
+        recv = _a2a(_pack_head_to_seq(g[:, :L], P), ctx.group)
+        return _unpack_head_to_seq(recv), None, None
+
+
+class _HeadToSeq(torch.autograd.Function):
+    """(B, L, H/P, D) head-sharded -> (B, L/P, H, D) sequence-sharded."""
+
+    @staticmethod
+    def forward(ctx, y: Tensor, group):
+        P = _world(group)
+        ctx.group, ctx.P = group, P
+        if y.shape[1] % P != 0:
+            raise ValueError(f"sequence length {y.shape[1]} is not divisible by the SP world size {P}")
+        recv = _a2a(_pack_head_to_seq(y, P), group)
+        return _unpack_head_to_seq(recv)
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        recv = _a2a(_pack_seq_to_head(g, ctx.P), ctx.group)
+        return _unpack_seq_to_head(recv), None
+
+
+class _GatherHeads(torch.autograd.Function):
+    """(B, T, H/P, D) per-rank head group of the replicated text rows -> (B, T, H, D) on every rank.
+    Adjoint: every rank's gradient for my head group is summed (reduce-scatter written as all-to-all + sum)."""
+
+    @staticmethod
+    def forward(ctx, t: Tensor, group):
+        P = _world(group)
+        ctx.group, ctx.P = group, P
+        parts = [torch.empty_like(t) for _ in range(P)]
+        dist.all_gather(parts, t.contiguous(), group=group)
+        return torch.cat(parts, dim=2)
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        P = ctx.P
+        B, T, H, D = g.shape
+        send = g.reshape(B, T, P, H // P, D).permute(2, 0, 1, 3, 4).contiguous()
+        recv = _a2a(send, ctx.group)
+        return recv.sum(dim=0), None
+
+
+def seq_to_head(x: Tensor, group=None, rear: int = 0) -> Tensor:
+    if _world(group) == 1:
+        return x if rear == 0 else torch.cat([x, x.new_empty((x.shape[0], rear, *x.shape[2:]))], dim=1)
+    return _SeqToHead.apply(x, group, rear)
+
+
+def head_to_seq(y: Tensor, group=None) -> Tensor:
+    if _world(group) == 1:
+        return y
+    return _HeadToSeq.apply(y, group)
+
+
+class _FillRear(torch.autograd.Function):
+    """Write `joint` (B, T, Hp, D) into the last T rows of `full` in place (no concatenation copy)."""
+
+    @staticmethod
+    def forward(ctx, full: Tensor, joint: Tensor):
+        T = joint.shape[1]
+        ctx.T = T
+        full[:, full.shape[1] - T:].copy_(joint)
+        ctx.mark_dirty(full)
+        return full
+
+    @staticmethod
+    def backward(ctx, g: Tensor):
+        T = ctx.T
+        L = g.shape[1] - T
+        return g, g[:, L:]
+
+
+def _default_attn(q: Tensor, k: Tensor, v: Tensor, softmax_scale: Optional[float]) -> Tensor:
+    from . import functional as Fn  # CUDA kernels; raises without the library — there is no CPU path
+    return Fn.attention_blhd(q, k, v, softmax_scale=softmax_scale)
+
+
+class UlyssesAttention:
+    """Drop-in for the object the reference stores in `block.hybrid_seq_parallel_attn` (flow/hunyuanvideo.py:154-157)
+    and calls as `xFuserLongContextAttention()(None, q, k, v, ...)`.
+
+    __call__(attn, query, key, value, *, dropout_p=0.0, softmax_scale=None, causal=False, window_size=(-1,-1),
+             joint_tensor_query=None, joint_tensor_key=None, joint_tensor_value=None, joint_strategy="none")
+    query/key/value: (B, L/P, H, D) local shard. joint_*: (B, T, H, D) replicated on every rank; with
+    joint_strategy="rear" they are attended jointly behind the image tokens. Returns (B, L/P [+ T], H, D).
+    """
+
+    def __init__(self, group=None, attn_fn: Optional[Callable] = None):
+        self.group = group
+        self.attn_fn = _default_attn if attn_fn is None else attn_fn
+
+    def __call__(self, attn, query: Tensor, key: Tensor, value: Tensor, *, dropout_p: float = 0.0,
+                 softmax_scale: Optional[float] = None, causal: bool = False, window_size=(-1, -1),
+                 joint_tensor_query: Optional[Tensor] = None, joint_tensor_key: Optional[Tensor] = None,
+                 joint_tensor_value: Optional[Tensor] = None, joint_strategy: str = "none") -> Tensor:
+        if causal or dropout_p != 0.0 or tuple(window_size) != (-1, -1):
+            raise NotImplementedError("causal / dropout / windowed attention are not on the sequence-parallel path")
+        has_joint = joint_tensor_query is not None
+        if has_joint and joint_strategy != "rear":
+            raise NotImplementedError(f"joint_strategy={joint_strategy!r}: only 'rear' is used by the reference")
+        P, r = _world(self.group), _rank(self.group)
+        H = query.shape[2]
+        if H % P != 0:
+            raise ValueError(f"Ulysses needs num_heads % world_size == 0 (H={H}, P={P})")
+        Hp = H // P
+        T = joint_tensor_query.shape[1] if has_joint else 0
+        q = seq_to_head(query, self.group, rear=T)
+        k = seq_to_head(key, self.group, rear=T)
+        v = seq_to_head(value, self.group, rear=T)
+        if T:
+            sl = slice(r * Hp, (r + 1) * Hp)
+            q = _FillRear.apply(q, joint_tensor_query[:, :, sl])
+            k = _FillRear.apply(k, joint_tensor_key[:, :, sl])
+            v = _FillRear.apply(v, joint_tensor_value[:, :, sl])
+        out = self.attn_fn(q, k, v, softmax_scale)
+        if not T:
+            return head_to_seq(out, self.group)
+        L = out.shape[1] - T
+        img = head_to_seq(out[:, :L], self.group)
+        txt = out[:, L:]
+        if P > 1:
+            txt = _GatherHeads.apply(txt, self.group)
+        return torch.cat([img, txt], dim=1)
+
+
+def ulysses_attention(q: Tensor, k: Tensor, v: Tensor, group=None, softmax_scale: Optional[float] = None,
+                      attn_fn: Optional[Callable] = None) -> Tensor:
+    """Plain Ulysses attention on sequence-sharded (B, L/P, H, D) tensors (Wan usp_attn_forward core)."""
+    return UlyssesAttention(group, attn_fn)(None, q, k, v, softmax_scale=softmax_scale)
+
+
+def shard_sequence(x: Tensor, dim: int = 1, group=None) -> Tensor:
+    """torch.chunk along `dim` and keep this rank's piece (wan usp_dit_forward, xdit_context_parallel.py:121-127)."""
+    P, r = _world(group), _rank(group)
+    if x.shape[dim] % P != 0:
+        raise ValueError(f"dim {dim} of size {x.shape[dim]} is not divisible by the SP world size {P}")
+    return x.chunk(P, dim=dim)[r]
+
+
+def gather_sequence(x: Tensor, dim: int = 1, group=None) -> Tensor:
+    """get_sp_group().all_gather(x, dim) at the end of the denoiser (xdit_context_parallel.py:142,
+    flow/hunyuanvideo.py:173). Forward only, like the reference (inference path)."""
+    P = _world(group)
+    if P == 1:
+        return x
+    parts = [torch.empty_like(x) for _ in range(P)]
+    dist.all_gather(parts, x.contiguous(), group=group)
+    return torch.cat(parts, dim=dim)

@@ -3,8 +3,9 @@
 // Replaces autograd through the reference torch attention path (same call sites as attn_fwd_sm100.cu).
 //
 // One CTA owns one 128-key tile of one (problem, head): K and V stay in shared memory, dK and dV accumulate in TMEM
-// over a loop on 128-row query tiles; dQ is produced per (Q tile, KV tile) and added into an fp32 accumulator in
-// global memory with vector reductions (red.global.add.v4.f32).
+// over a loop on 128-row query tiles; dQ is produced per (Q tile, KV tile), staged through shared memory in 32-column
+// fp32 chunks and added into an fp32 accumulator in global memory with TMA reductions
+// (cp.reduce.async.bulk.tensor .add): one bulk L2 reduction per 16 KB instead of 4096 per-thread red.global ops.
 //
 // Transposed formulation (keys on TMEM lanes) so that P^T and dS^T are directly MMA A-operands:
 //   MMA1  S^T  = K  Q_i^T         SS   (A = K tile K-major, B = Q_i K-major)               -> TMEM S
@@ -12,9 +13,9 @@
 //   SM1   P^T  = exp2(S^T * c - lse_i)  (compute warpgroups; bf16 P^T written back into the S columns)
 //   MMA3  dV  += P^T dO_i         TS   (A = P^T from TMEM, B = dO_i MN-major)
 //   SM2   dS^T = P^T o (dP^T - delta_i) -> bf16 -> shared memory tile [key][q] (128B-swizzled)
-//   MMA4  dK  += dS^T Q_i         SS   (A = dS^T K-major, B = Q_i MN-major)
-//   MMA5  dQ_i = dS  K            SS   (A = dS as MN-major view of the same tile, B = K MN-major) -> TMEM dQ
-//   DR    dQ_i: TMEM -> registers -> red.global.add into dq_acc (reduce warpgroup)
+//   MMA4  dQ_i = dS  K            SS   (A = dS as MN-major view of the same tile, B = K MN-major) -> TMEM dQ
+//   MMA5  dK  += dS^T Q_i         SS   (A = dS^T K-major, B = Q_i MN-major)   (runs while dQ_i is drained)
+//   DR    dQ_i: TMEM -> registers -> swizzled smem chunk -> TMA reduce-add into dq_acc (drain warpgroup)
 // Warps: 0-7 compute (thread = key row x half of the q columns), 8-11 dQ reduce (thread = q row), 12 producer
 // (TMA + lse/delta staging), 13 MMA issuer, 14-15 idle (complete the 4th warpgroup for setmaxnreg).
 // TMEM columns: S [0,128) (P^T bf16 at [32,96)), dP [128,256), dV [256,256+D), dK [256+D,256+2D),
@@ -40,11 +41,16 @@ struct BwdCfg {
   static constexpr int OFF_Q = OFF_V + TILE;
   static constexpr int OFF_DO = OFF_Q + QS * TILE;
   static constexpr int OFF_DS = OFF_DO + TILE;          // 128 x 128 bf16 = 2 boxes
-  static constexpr int OFF_STAT = OFF_DS + 2 * CHUNK;   // QS x {lse_log2[128], delta[128]} fp32
+  static constexpr int DQ_CHUNK = 128 * 128;            // bytes: 128 rows x 32 fp32 columns (one swizzled box)
+  static constexpr int OFF_DQS = OFF_DS + 2 * CHUNK;    // 2 staging buffers for the dQ TMA reduction
+  static constexpr int OFF_STAT = OFF_DQS + 2 * DQ_CHUNK;  // QS x {lse_log2[128], delta[128]} fp32
   static constexpr int OFF_BAR = OFF_STAT + QS * 1024;
-  static constexpr int NBAR = 1 + 2 * QS + QS + 2 + 7;
+  static constexpr int NBAR = 1 + 2 * QS + QS + 2 + 8;
   static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
-  static constexpr int BYTES = OFF_TMEM + 16 + 1024;
+  // The dynamic shared memory base is 1024-byte aligned (checked at kernel entry), so no alignment slack is spent:
+  // at D = 128 the layout uses 231 608 of the 232 448 bytes a CTA can have.
+  static constexpr int BYTES = OFF_TMEM + 16;
+  static_assert(BYTES <= 232448, "shared memory budget exceeded");
   static constexpr int THREADS = 512;
   static constexpr uint32_t T_S = 0, T_P = 32, T_DP = 128, T_DV = 256, T_DK = 256 + D;
   static constexpr uint32_t T_DQ = (D == 128) ? 128 : 384;
@@ -53,21 +59,18 @@ struct BwdCfg {
 
 enum : uint32_t {
   BT_KV_FULL = 0x200, BT_Q_FULL, BT_Q_EMPTY, BT_STAT_FULL, BT_DO_FULL, BT_DO_EMPTY, BT_S_FULL, BT_P_READY, BT_DP_FULL,
-  BT_DS_READY, BT_DQ_FULL, BT_DQ_DRAINED, BT_DKV_FULL, BT_ALIGN
+  BT_DS_READY, BT_DQ_FULL, BT_DQ_DRAINED, BT_DKV_FULL, BT_DS_FREE, BT_ALIGN
 };
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 template <int D>
 __global__ void __launch_bounds__(BwdCfg<D>::THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
-                float* __restrict__ dq_acc, const AttnBwdParams p, const int Lq_total) {
+                const __grid_constant__ CUtensorMap tm_dq, const AttnBwdParams p) {
   using C = BwdCfg<D>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) watchdog_trap(BT_ALIGN);  // swizzled tiles need a 1024-byte aligned base
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
 
@@ -121,6 +124,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* dq_full = ds_ready + 1;
   uint64_t* dq_drained = dq_full + 1;
   uint64_t* dkv_full = dq_drained + 1;
+  uint64_t* ds_free = dkv_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM);
 
   constexpr int PROD_WARP = 12, MMA_WARP = 13;
@@ -130,6 +134,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
     tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_dq);
   }
   if (warp == MMA_WARP && lane == 0) {
     mbar_init(kv_full, 1);
@@ -147,6 +152,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_init(dq_full, 1);
     mbar_init(dq_drained, 128);
     mbar_init(dkv_full, 1);
+    mbar_init(ds_free, 1);
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -159,7 +165,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t tmem = *tmem_slot;
 
   if (warp >= PROD_WARP) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     if (warp == PROD_WARP) {
       // ================================ producer: TMA + lse/delta staging =========================
       if (lane == 0) {
@@ -253,14 +259,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           mma_kmajor_pair(tmem + C::T_S, k_s, q_s + sn * C::TILE);
           tc_commit(s_full);
         }
-        // ---- dK += dS^T Q_i ; dQ_i = dS K ----
+        // ---- dQ_i = dS K (drained while the next MMA runs) ; dK += dS^T Q_i ----
         mbar_wait(ds_ready, i & 1, BT_DS_READY);
         tc_fence_after();
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)  // k = 16 query rows per step; dS^T tile is [key][q] in two 64-q boxes
-          umma_ss(tmem + C::T_DK, umma_desc_sw128(ds_s + (kk >> 2) * C::CHUNK + (kk & 3) * 32, 16, 1024),
-                  umma_desc_sw128(q_s + s * C::TILE + kk * 2048, C::CHUNK, 1024), IDESC_KD, (i > 0) || kk != 0);
-        tc_commit(q_empty + s);
         if (!C::DQ_ALIASES_DP && i > 0) {
           mbar_wait(dq_drained, (i - 1) & 1, BT_DQ_DRAINED);
           tc_fence_after();
@@ -270,6 +271,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           umma_ss(tmem + C::T_DQ, umma_desc_sw128(ds_s + kk * 2048, C::CHUNK, 1024),
                   umma_desc_sw128(k_s + kk * 2048, C::CHUNK, 1024), IDESC_DQ, kk != 0);
         tc_commit(dq_full);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // k = 16 query rows per step; dS^T tile is [key][q] in two 64-q boxes
+          umma_ss(tmem + C::T_DK, umma_desc_sw128(ds_s + (kk >> 2) * C::CHUNK + (kk & 3) * 32, 16, 1024),
+                  umma_desc_sw128(q_s + s * C::TILE + kk * 2048, C::CHUNK, 1024), IDESC_KD, (i > 0) || kk != 0);
+        tc_commit(q_empty + s);
+        tc_commit(ds_free);
         // ---- dP^T for the next Q tile ----
         if (has_next) {
           if (C::DQ_ALIASES_DP) {
@@ -285,34 +292,46 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_commit(dkv_full);
     }
   } else if (warp >= 8) {
-    // ================================ dQ reduce warpgroup ==========================================
+    // ================================ dQ drain warpgroup ===========================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
+    const bool leader = threadIdx.x == 256;
     const uint32_t dq_addr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + C::T_DQ;
+    uint8_t* stage = smem + C::OFF_DQS;
+    const int sw = row & 7;
+    constexpr int NCH = D / 32;
+    uint32_t g = 0;  // running chunk counter: staging buffer = g & 1
     for (int i = 0; i < n_q; ++i) {
       mbar_wait(dq_full, i & 1, BT_DQ_FULL);
       tc_fence_after();
-      const int qrow = i * 128 + row;
-      const bool valid = qrow < q_len;
-      float* dst = dq_acc + ((static_cast<int64_t>(bq) * Lq_total + q_base + qrow) * p.seq.H + h) * D;
 #pragma unroll
-      for (int c0 = 0; c0 < D; c0 += 32) {
+      for (int c = 0; c < NCH; ++c, ++g) {
         uint32_t r[32];
-        tmem_ld_x32(dq_addr + c0, r);
+        tmem_ld_x32(dq_addr + c * 32, r);
+        // the reduction issued two chunks ago has finished reading this staging buffer
+        if (leader) tma_wait_group_read<1>();
+        named_bar_sync(1, 128);
         tc_wait_ld();
-        if (c0 + 32 == D) {  // every TMEM read of this tile is complete: the issuer may overwrite the columns
+        if (c == NCH - 1) {  // every TMEM read of this tile is complete: the issuer may overwrite the columns
           tc_fence_before();
           mbar_arrive(dq_drained);
         }
-        if (valid) {
+        uint8_t* buf = stage + (g & 1) * C::DQ_CHUNK;
+        uint8_t* rowp = buf + row * 128;  // 128B swizzle: 16-byte chunk ch of row r lives at ch ^ (r & 7)
 #pragma unroll
-          for (int c = 0; c < 32; c += 4)
-            red_add_v4(dst + c0 + c, __uint_as_float(r[c]), __uint_as_float(r[c + 1]), __uint_as_float(r[c + 2]),
-                       __uint_as_float(r[c + 3]));
+        for (int ch = 0; ch < 8; ++ch)
+          *reinterpret_cast<uint4*>(rowp + ((ch ^ sw) << 4)) = make_uint4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
+        fence_proxy_async_smem();
+        named_bar_sync(2, 128);
+        if (leader) {
+          // rows past the end of the tensor are clipped by TMA; rows of another varlen segment receive exact zeros
+          tma_reduce_add_4d(&tm_dq, buf, c * 32, q_base + i * 128, h, bq);
+          tma_commit_group();
         }
       }
     }
+    if (leader) tma_wait_group<0>();
   } else {
     // ================================ compute warpgroups ===========================================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
@@ -385,7 +404,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
       // the dS tile of the previous iteration must have been consumed by MMA4/MMA5
-      if (i > 0) mbar_wait(dq_full, (i - 1) & 1, BT_DQ_FULL);
+      if (i > 0) mbar_wait(ds_free, (i - 1) & 1, BT_DS_FREE);
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch)
         *reinterpret_cast<uint4*>(ds_row + ((ch ^ sw) << 4)) =
@@ -483,7 +502,7 @@ __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_b
 
 template <int D>
 cudaError_t launch_bwd_one(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
-                           const CUtensorMap& tm_do, float* dq_acc, const AttnBwdParams& p, int Lq_total,
+                           const CUtensorMap& tm_do, const CUtensorMap& tm_dq, const AttnBwdParams& p,
                            cudaStream_t stream) {
   using C = BwdCfg<D>;
   static bool configured = false;
@@ -493,17 +512,17 @@ cudaError_t launch_bwd_one(const CUtensorMap& tm_q, const CUtensorMap& tm_k, con
     configured = true;
   }
   dim3 grid((p.seq.Lk + 127) / 128, p.seq.H, p.seq.nprob);
-  attn_bwd_kernel<D><<<grid, C::THREADS, C::BYTES, stream>>>(tm_q, tm_k, tm_v, tm_do, dq_acc, p, Lq_total);
+  attn_bwd_kernel<D><<<grid, C::THREADS, C::BYTES, stream>>>(tm_q, tm_k, tm_v, tm_do, tm_dq, p);
   return cudaGetLastError();
 }
 
 }  // namespace
 
 cudaError_t launch_attn_bwd(int D, const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
-                            const CUtensorMap& tm_do, float* dq_acc, const AttnBwdParams& p, int Lq_total,
+                            const CUtensorMap& tm_do, const CUtensorMap& tm_dq, const AttnBwdParams& p,
                             cudaStream_t stream) {
-  if (D == 128) return launch_bwd_one<128>(tm_q, tm_k, tm_v, tm_do, dq_acc, p, Lq_total, stream);
-  if (D == 64) return launch_bwd_one<64>(tm_q, tm_k, tm_v, tm_do, dq_acc, p, Lq_total, stream);
+  if (D == 128) return launch_bwd_one<128>(tm_q, tm_k, tm_v, tm_do, tm_dq, p, stream);
+  if (D == 64) return launch_bwd_one<64>(tm_q, tm_k, tm_v, tm_do, tm_dq, p, stream);
   return cudaErrorInvalidValue;
 }
 

@@ -289,7 +289,11 @@ int vt_attn_bwd(const void* dout, const void* q, const void* k, const void* v, c
     VT_CHECK_CUDA(launch_attn_bwd_dq_convert(dq_acc, dq, dq_strides, B, Lq, H, D, 0.f, st));
     return 0;
   }
-  CUtensorMap tm_q, tm_k, tm_v, tm_do;
+  CUtensorMap tm_q, tm_k, tm_v, tm_do, tm_dq;
+  {  // fp32 dQ accumulator (B, Lq, H, D) contiguous; reduced into through 128-row x 32-column swizzled boxes
+    const int64_t acc_strides[3] = {static_cast<int64_t>(Lq) * H * D, static_cast<int64_t>(H) * D, D};
+    if (int rc = make_tmap_4d(&tm_dq, dq_acc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, D, Lq, H, B, acc_strides, 32, 128)) return rc;
+  }
   if (int rc = make_tmap_4d(&tm_q, q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, D, Lq, H, B, q_strides, 64, 128)) return rc;
   if (int rc = make_tmap_4d(&tm_k, k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, D, Lk, H, B, k_strides, 64, 128)) return rc;
   if (int rc = make_tmap_4d(&tm_v, v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, D, Lk, H, B, v_strides, 64, 128)) return rc;
@@ -321,7 +325,7 @@ int vt_attn_bwd(const void* dout, const void* q, const void* k, const void* v, c
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   {
     ProfScope span(VT_K_ATTN_BWD, st);
-    VT_CHECK_CUDA(launch_attn_bwd(D, tm_q, tm_k, tm_v, tm_do, dq_acc, p, Lq, st));
+    VT_CHECK_CUDA(launch_attn_bwd(D, tm_q, tm_k, tm_v, tm_do, tm_dq, p, st));
   }
   {
     ProfScope span(VT_K_ATTN_BWD_DQ, st);

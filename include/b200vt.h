@@ -143,6 +143,11 @@ int vt_groupnorm_silu_bwd(const void* dy, const void* x, const float* mean, cons
 int vt_umma_probe(const void* a, const void* b, float* d, int a_mode, int b_mode, int n, uint32_t a_lbo, uint32_t a_sbo,
                   uint32_t a_kstep, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kstep, void* stream);
 
+/* Microbenchmark hook (tools/umma_rate.py): cycles for `iters` groups of eight 128 x n x 16 bf16 tcgen05.mma on `blocks`
+ * CTAs, per operand sourcing (see csrc/umma_rate.cu), with `noise_warps` warps streaming shared-memory stores.
+ * cycles_out: device int64[blocks]. Not part of the product path. */
+int vt_umma_rate(int mode, int n, int iters, int noise_warps, int blocks, long long* cycles_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

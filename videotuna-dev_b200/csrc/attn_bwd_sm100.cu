@@ -162,7 +162,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform: stays in a uniform register
 
   if (warp >= PROD_WARP) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
@@ -212,7 +212,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         __syncwarp();
       }
-    } else if (warp == MMA_WARP && lane == 0) {
+    } else if (warp == MMA_WARP && elect_one()) {
       // ================================ MMA issuer ===============================================
       constexpr uint32_t IDESC_ST = umma_idesc_bf16(128, 128, 0, 0);  // S^T, dP^T: both operands K-major
       constexpr uint32_t IDESC_KD = umma_idesc_bf16(128, D, 0, 1);    // dV, dK: A K-major (TMEM / smem), B MN-major

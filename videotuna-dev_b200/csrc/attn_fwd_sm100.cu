@@ -121,7 +121,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform: stays in a uniform register
 
   // NQ == 2: 384 threads x 168 regs at launch; the service warpgroup (warps 8..11) gives registers to the two
   // softmax warpgroups (setmaxnreg is warpgroup-wide, hence the idle warps 10,11 take the first branch too).
@@ -153,7 +153,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                       bk);
       }
     }
-    } else if (warp == MMA_WARP && lane == 0) {
+    } else if (warp == MMA_WARP && elect_one()) {
     // ================================ MMA issuer ==============================================
     {
       constexpr uint32_t IDESC_QK = umma_idesc_bf16(128, 128, 0, 0);  // A=Q K-major, B=K K-major

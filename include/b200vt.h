@@ -39,6 +39,10 @@ int vt_init(int device);
  * {call-site tag, blockIdx.x, blockIdx.y | blockIdx.z<<16, threadIdx.x}; all zero if none fired. */
 int vt_debug_watchdog(uint32_t out[4]);
 
+/* Debug: when device_buf is non-NULL, CTA (0,0,0) of the attention kernels stores clock64() timestamps of its first 64
+ * loop iterations into it (int64[4 roles][64 iterations][8 slots]; tools/trace_timeline.py decodes them). NULL = off. */
+int vt_debug_set_trace(long long* device_buf);
+
 /* Optional per-kernel device timing (bench.py's roofline leg). While enabled, the attention entry points bracket each
  * of their kernel launches with CUDA events recorded on the caller's stream. vt_profile_read() waits for the recorded
  * events, adds their elapsed times into per-kernel totals and returns the totals accumulated since the last
@@ -147,6 +151,10 @@ int vt_umma_probe(const void* a, const void* b, float* d, int a_mode, int b_mode
  * CTAs, per operand sourcing (see csrc/umma_rate.cu), with `noise_warps` warps streaming shared-memory stores.
  * cycles_out: device int64[blocks]. Not part of the product path. */
 int vt_umma_rate(int mode, int n, int iters, int noise_warps, int blocks, long long* cycles_out, void* stream);
+/* Same, for the fp32 TMA reduce-add path (16 KB boxes into acc, float[n_tiles*128][128]); depth = bulk groups in flight,
+ * spread = 0: all CTAs hit the same rows at once, 1: each CTA starts at its own tile. */
+int vt_tma_reduce_rate(float* acc, int n_tiles, int iters, int depth, int spread, int blocks, long long* cycles_out,
+                       void* stream);
 
 #ifdef __cplusplus
 }

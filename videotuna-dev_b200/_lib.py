@@ -20,6 +20,7 @@ _SIGS = {
     "vt_last_error": [C.c_char_p, C.c_size_t],
     "vt_init": [C.c_int],
     "vt_debug_watchdog": [C.POINTER(C.c_uint32)],
+    "vt_debug_set_trace": [vp],
     "vt_profile_enable": [C.c_int],
     "vt_profile_read": [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
     "vt_attn_fwd": [vp, vp, vp, vp, vp, c_i64p, c_i64p, c_i64p, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -44,6 +45,7 @@ _SIGS = {
     "vt_groupnorm_silu_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                               vp],
     "vt_umma_rate": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp],
+    "vt_tma_reduce_rate": [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp],
     "vt_umma_probe": [vp, vp, vp, C.c_int, C.c_int, C.c_int] + [C.c_uint32] * 6 + [vp],
 }
 _RESTYPE = {"vt_attn_bwd_workspace_bytes": C.c_int64}

@@ -165,7 +165,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform: stays in a uniform register
 
   if (warp >= PROD_WARP) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == PROD_WARP) {
       // ================================ producer: TMA + lse/delta staging =========================
       if (lane == 0) {
@@ -182,6 +182,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const int s = i % C::QS;
         mbar_wait(q_empty + s, ((i / C::QS) & 1) ^ 1, BT_Q_EMPTY);
         if (lane == 0) {
+          trace_mark(p.trace, 3, i, 0);
           mbar_arrive_expect_tx(q_full + s, C::TILE);
 #pragma unroll
           for (int c = 0; c < C::KCH; ++c)
@@ -205,6 +206,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         mbar_arrive(stat_full + s);
         if (lane == 0) {
           mbar_wait(do_empty, (i & 1) ^ 1, BT_DO_EMPTY);
+          trace_mark(p.trace, 3, i, 1);
           mbar_arrive_expect_tx(do_full, C::TILE);
 #pragma unroll
           for (int c = 0; c < C::KCH; ++c)
@@ -217,17 +219,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       constexpr uint32_t IDESC_ST = umma_idesc_bf16(128, 128, 0, 0);  // S^T, dP^T: both operands K-major
       constexpr uint32_t IDESC_KD = umma_idesc_bf16(128, D, 0, 1);    // dV, dK: A K-major (TMEM / smem), B MN-major
       constexpr uint32_t IDESC_DQ = umma_idesc_bf16(128, D, 1, 1);    // dQ: A = dS MN-major, B = K MN-major
-      const uint32_t k_s = smem_u32(smem + C::OFF_K), v_s = smem_u32(smem + C::OFF_V);
-      const uint32_t q_s = smem_u32(smem + C::OFF_Q), do_s = smem_u32(smem + C::OFF_DO);
-      const uint32_t ds_s = smem_u32(smem + C::OFF_DS);
+      // shared-memory addresses in 16-byte units (the descriptor's address field); all tile offsets are constants
+      const uint32_t sb16 = smem_u32(smem) >> 4;
+      const uint32_t k_s = sb16 + (C::OFF_K >> 4), v_s = sb16 + (C::OFF_V >> 4);
+      const uint32_t q_s = sb16 + (C::OFF_Q >> 4), do_s = sb16 + (C::OFF_DO >> 4);
+      const uint32_t ds_s = sb16 + (C::OFF_DS >> 4);
+      constexpr uint32_t CH16 = C::CHUNK >> 4, TILE16 = C::TILE >> 4;
 
       auto mma_kmajor_pair = [&](uint32_t d_tmem, uint32_t a_base, uint32_t b_base) {  // D = A B^T over the head dim
 #pragma unroll
         for (int c = 0; c < C::KCH; ++c)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_ss(d_tmem, umma_desc_sw128(a_base + c * C::CHUNK + kk * 32, 16, 1024),
-                    umma_desc_sw128(b_base + c * C::CHUNK + kk * 32, 16, 1024), IDESC_ST, (c | kk) != 0);
+            umma_ss(d_tmem, umma_desc_sw128_a16(a_base + c * CH16 + kk * 2, 16, 1024),
+                    umma_desc_sw128_a16(b_base + c * CH16 + kk * 2, 16, 1024), IDESC_ST, (c | kk) != 0);
       };
 
       mbar_wait(kv_full, 0, BT_KV_FULL);
@@ -244,11 +249,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const int s = i % C::QS;
         const bool has_next = i + 1 < n_q;
         // ---- dV += P^T dO_i ----
+        trace_mark(p.trace, 1, i, 0);
         mbar_wait(p_ready, i & 1, BT_P_READY);
         tc_fence_after();
+        trace_mark(p.trace, 1, i, 1);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_ts(tmem + C::T_DV, tmem + C::T_P + kk * 8, umma_desc_sw128(do_s + kk * 2048, C::CHUNK, 1024), IDESC_KD,
+          umma_ts(tmem + C::T_DV, tmem + C::T_P + kk * 8, umma_desc_sw128_a16(do_s + kk * 128, C::CHUNK, 1024), IDESC_KD,
                   (i > 0) || kk != 0);
         tc_commit(do_empty);
         // ---- S^T for the next Q tile ----
@@ -256,25 +263,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           const int sn = (i + 1) % C::QS;
           mbar_wait(q_full + sn, ((i + 1) / C::QS) & 1, BT_Q_FULL);
           tc_fence_after();
-          mma_kmajor_pair(tmem + C::T_S, k_s, q_s + sn * C::TILE);
+          trace_mark(p.trace, 1, i, 2);
+          mma_kmajor_pair(tmem + C::T_S, k_s, q_s + sn * TILE16);
           tc_commit(s_full);
         }
         // ---- dQ_i = dS K (drained while the next MMA runs) ; dK += dS^T Q_i ----
         mbar_wait(ds_ready, i & 1, BT_DS_READY);
         tc_fence_after();
+        trace_mark(p.trace, 1, i, 3);
         if (!C::DQ_ALIASES_DP && i > 0) {
           mbar_wait(dq_drained, (i - 1) & 1, BT_DQ_DRAINED);
           tc_fence_after();
         }
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)  // k = 16 keys per step
-          umma_ss(tmem + C::T_DQ, umma_desc_sw128(ds_s + kk * 2048, C::CHUNK, 1024),
-                  umma_desc_sw128(k_s + kk * 2048, C::CHUNK, 1024), IDESC_DQ, kk != 0);
+          umma_ss(tmem + C::T_DQ, umma_desc_sw128_a16(ds_s + kk * 128, C::CHUNK, 1024),
+                  umma_desc_sw128_a16(k_s + kk * 128, C::CHUNK, 1024), IDESC_DQ, kk != 0);
         tc_commit(dq_full);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)  // k = 16 query rows per step; dS^T tile is [key][q] in two 64-q boxes
-          umma_ss(tmem + C::T_DK, umma_desc_sw128(ds_s + (kk >> 2) * C::CHUNK + (kk & 3) * 32, 16, 1024),
-                  umma_desc_sw128(q_s + s * C::TILE + kk * 2048, C::CHUNK, 1024), IDESC_KD, (i > 0) || kk != 0);
+          umma_ss(tmem + C::T_DK, umma_desc_sw128_a16(ds_s + (kk >> 2) * CH16 + (kk & 3) * 2, 16, 1024),
+                  umma_desc_sw128_a16(q_s + s * TILE16 + kk * 128, C::CHUNK, 1024), IDESC_KD, (i > 0) || kk != 0);
         tc_commit(q_empty + s);
         tc_commit(ds_free);
         // ---- dP^T for the next Q tile ----
@@ -283,8 +292,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             mbar_wait(dq_drained, i & 1, BT_DQ_DRAINED);
             tc_fence_after();
           }
+          trace_mark(p.trace, 1, i, 4);
           mbar_wait(do_full, (i + 1) & 1, BT_DO_FULL);
           tc_fence_after();
+          trace_mark(p.trace, 1, i, 5);
           mma_kmajor_pair(tmem + C::T_DP, v_s, do_s);
           tc_commit(dp_full);
         }
@@ -293,7 +304,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     }
   } else if (warp >= 8) {
     // ================================ dQ drain warpgroup ===========================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    // The whole 128 x D fp32 tile is pulled into registers first, so the TMEM columns (which dP of the next iteration
+    // reuses at D = 128) are released ~100 cycles after the MMA completes; the registers are then fed to the TMA
+    // reduction through two 16 KB staging buffers at the engine's own pace (~640 cycles per box, measured).
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 144;");
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const bool leader = threadIdx.x == 256;
@@ -303,25 +317,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     constexpr int NCH = D / 32;
     uint32_t g = 0;  // running chunk counter: staging buffer = g & 1
     for (int i = 0; i < n_q; ++i) {
+      if (leader) trace_mark(p.trace, 2, i, 0);
       mbar_wait(dq_full, i & 1, BT_DQ_FULL);
       tc_fence_after();
+      if (leader) trace_mark(p.trace, 2, i, 1);
+      uint32_t r[D];
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) tmem_ld_x32(dq_addr + c * 32, r + c * 32);
+      tc_wait_ld();
+      tc_fence_before();
+      mbar_arrive(dq_drained);  // every TMEM read of this tile is complete: the issuer may overwrite the columns
+      if (leader) trace_mark(p.trace, 2, i, 2);
 #pragma unroll
       for (int c = 0; c < NCH; ++c, ++g) {
-        uint32_t r[32];
-        tmem_ld_x32(dq_addr + c * 32, r);
         // the reduction issued two chunks ago has finished reading this staging buffer
         if (leader) tma_wait_group_read<1>();
         named_bar_sync(1, 128);
-        tc_wait_ld();
-        if (c == NCH - 1) {  // every TMEM read of this tile is complete: the issuer may overwrite the columns
-          tc_fence_before();
-          mbar_arrive(dq_drained);
-        }
         uint8_t* buf = stage + (g & 1) * C::DQ_CHUNK;
         uint8_t* rowp = buf + row * 128;  // 128B swizzle: 16-byte chunk ch of row r lives at ch ^ (r & 7)
 #pragma unroll
         for (int ch = 0; ch < 8; ++ch)
-          *reinterpret_cast<uint4*>(rowp + ((ch ^ sw) << 4)) = make_uint4(r[4 * ch], r[4 * ch + 1], r[4 * ch + 2], r[4 * ch + 3]);
+          *reinterpret_cast<uint4*>(rowp + ((ch ^ sw) << 4)) =
+              make_uint4(r[c * 32 + 4 * ch], r[c * 32 + 4 * ch + 1], r[c * 32 + 4 * ch + 2], r[c * 32 + 4 * ch + 3]);
         fence_proxy_async_smem();
         named_bar_sync(2, 128);
         if (leader) {
@@ -330,11 +347,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           tma_commit_group();
         }
       }
+      if (leader) trace_mark(p.trace, 2, i, 3);
     }
     if (leader) tma_wait_group<0>();
   } else {
     // ================================ compute warpgroups ===========================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
     const int half = warp >> 2;  // which 64 query columns
     const int quarter = warp & 3;
     const int krow = quarter * 32 + lane;  // key row of this thread
@@ -351,9 +369,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     for (int i = 0; i < n_q; ++i) {
       const int s = i % C::QS;
       const float* st = reinterpret_cast<const float*>(smem + C::OFF_STAT + s * 1024) + half * 64;
+      const bool tr = threadIdx.x == 0;
+      if (tr) trace_mark(p.trace, 0, i, 0);
       mbar_wait(stat_full + s, (i / C::QS) & 1, BT_STAT_FULL);
       mbar_wait(s_full, i & 1, BT_S_FULL);
       tc_fence_after();
+      if (tr) trace_mark(p.trace, 0, i, 1);
       float pr[64];
       {
         uint32_t su[64];
@@ -382,10 +403,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(p_ready);
+      if (tr) trace_mark(p.trace, 0, i, 2);
 
       // ---- dS^T = P^T o (dP^T - delta) ----
       mbar_wait(dp_full, i & 1, BT_DP_FULL);
       tc_fence_after();
+      if (tr) trace_mark(p.trace, 0, i, 3);
       uint32_t dsp[32];
 #pragma unroll
       for (int c0 = 0; c0 < 64; c0 += 32) {
@@ -404,7 +427,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
       // the dS tile of the previous iteration must have been consumed by MMA4/MMA5
+      if (tr) trace_mark(p.trace, 0, i, 4);
       if (i > 0) mbar_wait(ds_free, (i - 1) & 1, BT_DS_FREE);
+      if (tr) trace_mark(p.trace, 0, i, 5);
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch)
         *reinterpret_cast<uint4*>(ds_row + ((ch ^ sw) << 4)) =
@@ -412,6 +437,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(ds_ready);
+      if (tr) trace_mark(p.trace, 0, i, 6);
     }
 
     // ---- epilogue: dV, dK (this warpgroup's half of the head dim) ---------------------------------

@@ -22,8 +22,13 @@ struct AttnSeq {
   int nprob;                 // batches (fixed) or segments (varlen)
 };
 
+// Optional timeline trace (debug): CTA (0,0,0) stores clock64() at protocol points of its first kTraceIters loop
+// iterations into trace[(role * kTraceIters + iter) * kTraceSlots + slot]. nullptr (the default) disables it.
+constexpr int kTraceIters = 64, kTraceSlots = 8, kTraceRoles = 4;
+
 struct AttnFwdParams {
   AttnSeq seq;
+  long long* trace;
   __nv_bfloat16* o;
   float* lse;                // (B, H, Lq_total) fp32, natural-log units
   int64_t o_sb, o_sl, o_sh;  // element strides of o
@@ -34,6 +39,7 @@ struct AttnFwdParams {
 
 struct AttnBwdParams {
   AttnSeq seq;
+  long long* trace;
   const float* lse;          // from forward
   const float* delta;        // rowsum(dO * O), same layout as lse
   int64_t lse_sb, lse_sh;
@@ -55,6 +61,7 @@ cudaError_t launch_attn_bwd_delta(int D, const void* dout, const void* o, float*
                                   const int64_t* o_strides, int B, int L, int H, cudaStream_t stream);
 cudaError_t launch_attn_bwd_dq_convert(const float* acc, void* dq, const int64_t* dq_strides, int B, int L, int H, int D,
                                        float scale, cudaStream_t stream);
+long long* debug_trace_ptr();  // capi.cu: device buffer set through vt_debug_set_trace, or nullptr
 cudaError_t attn_fwd_set_debug_ptr(unsigned int* p);
 cudaError_t attn_bwd_set_debug_ptr(unsigned int* p);
 

@@ -158,17 +158,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     {
       constexpr uint32_t IDESC_QK = umma_idesc_bf16(128, 128, 0, 0);  // A=Q K-major, B=K K-major
       constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, D, 0, 1);    // A=P (TMEM), B=V MN-major
-      const uint32_t q_smem = smem_u32(smem + C::OFF_Q);
-      const uint32_t k_smem = smem_u32(smem + C::OFF_K);
-      const uint32_t v_smem = smem_u32(smem + C::OFF_V);
+      // shared-memory addresses in 16-byte units (the descriptor's address field)
+      const uint32_t sb16 = smem_u32(smem) >> 4;
+      const uint32_t q_smem = sb16 + (C::OFF_Q >> 4), k_smem = sb16 + (C::OFF_K >> 4), v_smem = sb16 + (C::OFF_V >> 4);
+      constexpr uint32_t CH16 = C::CHUNK >> 4, TILE16 = C::TILE >> 4;
 
       auto issue_qk = [&](int t, int ks) {
 #pragma unroll
         for (int c = 0; c < C::KCH; ++c)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t a = umma_desc_sw128(q_smem + t * C::TILE + c * C::CHUNK + kk * 32, 16, 1024);
-            const uint64_t b = umma_desc_sw128(k_smem + ks * C::TILE + c * C::CHUNK + kk * 32, 16, 1024);
+            const uint64_t a = umma_desc_sw128_a16(q_smem + t * TILE16 + c * CH16 + kk * 2, 16, 1024);
+            const uint64_t b = umma_desc_sw128_a16(k_smem + ks * TILE16 + c * CH16 + kk * 2, 16, 1024);
             umma_ss(tmem_base + t * 128, a, b, IDESC_QK, (c | kk) != 0);
           }
       };
@@ -176,7 +177,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {  // 16 keys per MMA
           // V tile: [128 keys][64 d] x KCH boxes. MN-major B: LBO = next 64-d box, SBO = next 8 keys.
-          const uint64_t b = umma_desc_sw128(v_smem + vs * C::TILE + kk * 2048, C::CHUNK, 1024);
+          const uint64_t b = umma_desc_sw128_a16(v_smem + vs * TILE16 + kk * 128, C::CHUNK, 1024);
           umma_ts(tmem_base + NQ * 128 + t * D, tmem_base + t * 128 + kk * 8, b, IDESC_PV, acc || kk != 0);
         }
       };

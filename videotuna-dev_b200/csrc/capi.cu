@@ -84,6 +84,10 @@ int make_tmap_4d(CUtensorMap* out, const void* ptr, CUtensorMapDataType dt, int 
 
 int lib_init() { return ensure_init(); }
 
+static long long* g_trace = nullptr;
+long long* debug_trace_ptr() { return g_trace; }
+void debug_set_trace(long long* p) { g_trace = p; }
+
 // ---- optional per-kernel event timing (vt_profile_*) ---------------------------------------------------------
 namespace {
 struct ProfSpan {
@@ -189,6 +193,11 @@ int vt_profile_read(int kernel_id, double* total_ms, int64_t* launches) {
   return 0;
 }
 
+int vt_debug_set_trace(long long* device_buf) {
+  debug_set_trace(device_buf);
+  return 0;
+}
+
 int vt_debug_watchdog(uint32_t out[4]) {
   VT_REQUIRE(out != nullptr, VT_ERR_NULL, "out is NULL");
   for (int i = 0; i < 4; ++i) out[i] = g_state.dbg_host ? g_state.dbg_host[i] : 0u;
@@ -231,6 +240,7 @@ int vt_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse
   if (int rc = make_tmap_4d(&tm_v, v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, D, Lk_map, H, B, v_strides, 64, 128)) return rc;
 
   AttnFwdParams p{};
+  p.trace = debug_trace_ptr();
   p.seq.cu_q = num_segments > 0 ? cu_seqlens_q : nullptr;
   p.seq.cu_k = num_segments > 0 ? cu_seqlens_k : nullptr;
   p.seq.seqlens_k = num_segments > 0 ? nullptr : seqlens_k;
@@ -306,6 +316,7 @@ int vt_attn_bwd(const void* dout, const void* q, const void* k, const void* v, c
   }
 
   AttnBwdParams p{};
+  p.trace = debug_trace_ptr();
   p.seq.cu_q = num_segments > 0 ? cu_seqlens_q : nullptr;
   p.seq.cu_k = num_segments > 0 ? cu_seqlens_k : nullptr;
   p.seq.seqlens_k = num_segments > 0 ? nullptr : seqlens_k;

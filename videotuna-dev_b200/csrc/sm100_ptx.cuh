@@ -92,6 +92,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
   }
 }
 
+// ---- debug timeline (see attn_common.h) -----------------------------------------------------------------------
+__device__ __forceinline__ void trace_mark(long long* trace, int role, int iter, int slot) {
+  if (trace != nullptr && iter < 64 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0)
+    trace[(role * 64 + iter) * 8 + slot] = clock64();
+}
+
 // ---- named barriers (sub-CTA sync) --------------------------------------------------------------
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -171,6 +177,14 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t
   d |= 1ull << 46;
   d |= 2ull << 61;
   return d;
+}
+// Same descriptor from a pre-shifted address (smem byte address >> 4, below 2^14 for any CTA-window address): the
+// low word is `addr16 + constant`, one uniform add per MMA, so the issuing thread does not have to keep (or spill) a
+// table of precomputed descriptors.
+__device__ __forceinline__ uint64_t umma_desc_sw128_a16(uint32_t addr16, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  const uint32_t lo = addr16 | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+  const uint32_t hi = ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (2u << 29);
+  return (static_cast<uint64_t>(hi) << 32) | lo;
 }
 // Instruction descriptor for kind::f16 with bf16 inputs and fp32 accumulation.
 //   [4,6) D fmt (1=f32)  [7,10) A fmt (1=bf16)  [10,13) B fmt (1=bf16)

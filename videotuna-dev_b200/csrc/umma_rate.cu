@@ -10,8 +10,10 @@ namespace {
 
 // mode 0: SS, A K-major, B K-major   (S = Q K^T)          mode 1: TS, A in TMEM, B MN-major (O += P V)
 // mode 2: SS, A MN-major, B MN-major (dQ = dS K)          mode 3: SS, A K-major, B MN-major (dK += dS^T Q)
+template <int MODE, int N>
 __global__ void __launch_bounds__(256, 1)
-umma_rate_kernel(int mode, int n, int iters, int noise_warps, long long* cycles_out) {
+umma_rate_kernel(int iters, int noise_warps, int dep, long long* cycles_out) {
+  constexpr int mode = MODE, n = N;
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int CHUNK = 128 * 128;
   uint8_t* a_s = smem;
@@ -35,15 +37,16 @@ umma_rate_kernel(int mode, int n, int iters, int noise_warps, long long* cycles_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  if (threadIdx.x == 0) {
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  if (warp == 0 && elect_one()) {
     const uint32_t idesc = umma_idesc_bf16(128, n, mode == 2 ? 1 : 0, mode == 0 ? 0 : 1);
     const uint32_t a_addr = smem_u32(a_s), b_addr = smem_u32(b_s);
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
       for (int kk = 0; kk < 8; ++kk) {
-        const uint32_t d = tmem + (it & 1) * 128;
+        // dep == 1: all eight k-steps accumulate into one tile (as in the kernels); dep == 0: eight independent tiles
+        const uint32_t d = tmem + (dep ? (it & 1) * 128 : (kk & 1) * 128);
         if (mode == 0) {
           umma_ss(d, umma_desc_sw128(a_addr + (kk >> 2) * CHUNK + (kk & 3) * 32, 16, 1024),
                   umma_desc_sw128(b_addr + (kk >> 2) * CHUNK + (kk & 3) * 32, 16, 1024), idesc, kk != 0);
@@ -83,14 +86,77 @@ umma_rate_kernel(int mode, int n, int iters, int noise_warps, long long* cycles_
 
 using namespace vt;
 
+template <int MODE, int N>
+static cudaError_t launch_rate(int iters, int noise_warps, int dep, int blocks, long long* out, cudaStream_t st) {
+  const int bytes = 6 * 128 * 128 + 64;
+  cudaError_t e = cudaFuncSetAttribute(umma_rate_kernel<MODE, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  umma_rate_kernel<MODE, N><<<blocks, 256, bytes, st>>>(iters, noise_warps, dep, out);
+  return cudaGetLastError();
+}
+
 extern "C" int vt_umma_rate(int mode, int n, int iters, int noise_warps, int blocks, long long* cycles_out, void* stream) {
   VT_REQUIRE(cycles_out != nullptr, VT_ERR_NULL, "vt_umma_rate: NULL output");
-  VT_REQUIRE(mode >= 0 && mode <= 3 && n >= 16 && n <= 128 && n % 16 == 0 && iters > 0 && blocks > 0 && noise_warps >= 0 &&
+  // mode bit 4 (16) selects independent accumulators instead of one accumulate chain
+  const int dep = (mode & 16) ? 0 : 1;
+  mode &= 15;
+  VT_REQUIRE(mode >= 0 && mode <= 3 && (n == 64 || n == 128) && iters > 0 && blocks > 0 && noise_warps >= 0 &&
                  noise_warps <= 7, VT_ERR_SHAPE, "vt_umma_rate: bad argument");
   if (int rc = lib_init()) return rc;
-  const int bytes = 6 * 128 * 128 + 64;
-  VT_CHECK_CUDA(cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-  umma_rate_kernel<<<blocks, 256, bytes, static_cast<cudaStream_t>(stream)>>>(mode, n, iters, noise_warps, cycles_out);
+  auto st = static_cast<cudaStream_t>(stream);
+#define VT_RATE_CASE(M, NN) \
+  if (mode == M && n == NN) VT_CHECK_CUDA((launch_rate<M, NN>(iters, noise_warps, dep, blocks, cycles_out, st)))
+  VT_RATE_CASE(0, 128); VT_RATE_CASE(0, 64); VT_RATE_CASE(1, 128); VT_RATE_CASE(1, 64);
+  VT_RATE_CASE(2, 128); VT_RATE_CASE(2, 64); VT_RATE_CASE(3, 128); VT_RATE_CASE(3, 64);
+#undef VT_RATE_CASE
+  return 0;
+}
+
+// ---- TMA reduce-add (fp32) throughput: the dQ accumulation path of the backward kernel -----------------------------
+namespace vt {
+int make_tmap_4d(CUtensorMap* out, const void* ptr, CUtensorMapDataType dt, int elem_bytes, int64_t D, int64_t L,
+                 int64_t H, int64_t B, const int64_t* strides, int box_d, int box_rows);
+namespace {
+// Each CTA issues `iters` reductions of one 128-row x 32-column fp32 box (16 KB) with `depth` bulk groups in flight.
+// spread == 0: every CTA targets the same rows at the same time (what unstaggered backward CTAs do);
+// spread == 1: CTA b starts at row tile b and walks from there.
+__global__ void __launch_bounds__(128, 1)
+tma_reduce_rate_kernel(const __grid_constant__ CUtensorMap tm, int iters, int depth, int spread, int n_tiles,
+                       long long* cycles_out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  for (int i = threadIdx.x; i < 4 * 16384 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const int tile = (it / 4 + (spread ? blockIdx.x : 0)) % n_tiles;
+      tma_reduce_add_4d(&tm, smem + (it & 3) * 16384, (it & 3) * 32, tile * 128, 0, 0);
+      tma_commit_group();
+      if (depth == 1) tma_wait_group_read<0>();
+      else if (depth == 2) tma_wait_group_read<1>();
+      else if (depth == 3) tma_wait_group_read<2>();
+      else tma_wait_group_read<3>();
+    }
+    tma_wait_group<0>();
+    cycles_out[blockIdx.x] = clock64() - t0;
+  }
+}
+}  // namespace
+}  // namespace vt
+
+extern "C" int vt_tma_reduce_rate(float* acc, int n_tiles, int iters, int depth, int spread, int blocks,
+                                  long long* cycles_out, void* stream) {
+  VT_REQUIRE(acc != nullptr && cycles_out != nullptr, VT_ERR_NULL, "vt_tma_reduce_rate: NULL argument");
+  VT_REQUIRE(n_tiles > 0 && iters > 0 && depth >= 1 && depth <= 4 && blocks > 0, VT_ERR_SHAPE, "bad argument");
+  if (int rc = lib_init()) return rc;
+  CUtensorMap tm;
+  const int64_t st[3] = {static_cast<int64_t>(n_tiles) * 128 * 128, 128, 128};
+  if (int rc = make_tmap_4d(&tm, acc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 128, static_cast<int64_t>(n_tiles) * 128, 1, 1, st, 32, 128))
+    return rc;
+  VT_CHECK_CUDA(cudaFuncSetAttribute(tma_reduce_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 16384));
+  tma_reduce_rate_kernel<<<blocks, 128, 4 * 16384, static_cast<cudaStream_t>(stream)>>>(tm, iters, depth, spread, n_tiles,
+                                                                                       cycles_out);
   VT_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

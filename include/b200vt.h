@@ -156,6 +156,11 @@ int vt_umma_rate(int mode, int n, int iters, int noise_warps, int blocks, long l
 int vt_tma_reduce_rate(float* acc, int n_tiles, int iters, int depth, int spread, int blocks, long long* cycles_out,
                        void* stream);
 
+/* Same reduction stream with a second thread streaming 16 KB TMA loads (load_mode != 0) from src_bf16
+ * (bf16[n_tiles*128][128]); loads_out counts the boxes loaded meanwhile. */
+int vt_tma_mixed_rate(float* acc, const void* src_bf16, int n_tiles, int iters, int load_mode, int blocks,
+                      long long* cycles_out, long long* loads_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

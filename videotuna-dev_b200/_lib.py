@@ -46,6 +46,7 @@ _SIGS = {
                               vp],
     "vt_umma_rate": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp],
     "vt_tma_reduce_rate": [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp],
+    "vt_tma_mixed_rate": [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp],
     "vt_umma_probe": [vp, vp, vp, C.c_int, C.c_int, C.c_int] + [C.c_uint32] * 6 + [vp],
 }
 _RESTYPE = {"vt_attn_bwd_workspace_bytes": C.c_int64}

@@ -57,6 +57,12 @@ struct BwdCfg {
   static constexpr bool DQ_ALIASES_DP = (D == 128);
 };
 
+__device__ __forceinline__ void red_add_v4(float* addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(__uint_as_float(a)), "f"(__uint_as_float(b)),
+               "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
+               : "memory");
+}
+
 enum : uint32_t {
   BT_KV_FULL = 0x200, BT_Q_FULL, BT_Q_EMPTY, BT_STAT_FULL, BT_DO_FULL, BT_DO_EMPTY, BT_S_FULL, BT_P_READY, BT_DP_FULL,
   BT_DS_READY, BT_DQ_FULL, BT_DQ_DRAINED, BT_DKV_FULL, BT_DS_FREE, BT_ALIGN
@@ -67,7 +73,8 @@ template <int D>
 __global__ void __launch_bounds__(BwdCfg<D>::THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
-                const __grid_constant__ CUtensorMap tm_dq, const AttnBwdParams p) {
+                const __grid_constant__ CUtensorMap tm_dq, float* __restrict__ dq_acc, const int Lq_total,
+                const AttnBwdParams p) {
   using C = BwdCfg<D>;
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) watchdog_trap(BT_ALIGN);  // swizzled tiles need a 1024-byte aligned base
@@ -314,7 +321,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t dq_addr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + C::T_DQ;
     uint8_t* stage = smem + C::OFF_DQS;
     const int sw = row & 7;
+    // The TMA engine sustains ~25.6 B/clk of fp32 reduction per SM (measured, tools/tma_reduce_rate.py) and also
+    // carries the Q/dO loads, which makes it the busiest unit of this kernel. The last LSU_CH 32-column chunks of
+    // every tile therefore bypass it: the drain threads add them with red.global.add.v4.f32 straight from registers.
     constexpr int NCH = D / 32;
+    constexpr int LSU_CH = 0;  // measured: one LSU chunk makes the drain 25% slower (red.global stalls the issuing warps)
+    constexpr int TMA_CH = NCH - LSU_CH;
     uint32_t g = 0;  // running chunk counter: staging buffer = g & 1
     for (int i = 0; i < n_q; ++i) {
       if (leader) trace_mark(p.trace, 2, i, 0);
@@ -329,7 +341,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_arrive(dq_drained);  // every TMEM read of this tile is complete: the issuer may overwrite the columns
       if (leader) trace_mark(p.trace, 2, i, 2);
 #pragma unroll
-      for (int c = 0; c < NCH; ++c, ++g) {
+      for (int c = 0; c < TMA_CH; ++c, ++g) {
         // the reduction issued two chunks ago has finished reading this staging buffer
         if (leader) tma_wait_group_read<1>();
         named_bar_sync(1, 128);
@@ -345,6 +357,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           // rows past the end of the tensor are clipped by TMA; rows of another varlen segment receive exact zeros
           tma_reduce_add_4d(&tm_dq, buf, c * 32, q_base + i * 128, h, bq);
           tma_commit_group();
+        }
+      }
+      if (LSU_CH > 0) {
+        const int qrow = i * 128 + row;
+        if (qrow < q_len) {
+          float* dst = dq_acc + ((static_cast<int64_t>(bq) * Lq_total + q_base + qrow) * p.seq.H + h) * D + TMA_CH * 32;
+#pragma unroll
+          for (int c = 0; c < LSU_CH * 32; c += 4)
+            red_add_v4(dst + c, r[TMA_CH * 32 + c], r[TMA_CH * 32 + c + 1], r[TMA_CH * 32 + c + 2], r[TMA_CH * 32 + c + 3]);
         }
       }
       if (leader) trace_mark(p.trace, 2, i, 3);
@@ -528,8 +549,8 @@ __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_b
 
 template <int D>
 cudaError_t launch_bwd_one(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
-                           const CUtensorMap& tm_do, const CUtensorMap& tm_dq, const AttnBwdParams& p,
-                           cudaStream_t stream) {
+                           const CUtensorMap& tm_do, const CUtensorMap& tm_dq, float* dq_acc, int Lq_total,
+                           const AttnBwdParams& p, cudaStream_t stream) {
   using C = BwdCfg<D>;
   static bool configured = false;
   if (!configured) {
@@ -538,17 +559,17 @@ cudaError_t launch_bwd_one(const CUtensorMap& tm_q, const CUtensorMap& tm_k, con
     configured = true;
   }
   dim3 grid((p.seq.Lk + 127) / 128, p.seq.H, p.seq.nprob);
-  attn_bwd_kernel<D><<<grid, C::THREADS, C::BYTES, stream>>>(tm_q, tm_k, tm_v, tm_do, tm_dq, p);
+  attn_bwd_kernel<D><<<grid, C::THREADS, C::BYTES, stream>>>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p);
   return cudaGetLastError();
 }
 
 }  // namespace
 
 cudaError_t launch_attn_bwd(int D, const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
-                            const CUtensorMap& tm_do, const CUtensorMap& tm_dq, const AttnBwdParams& p,
-                            cudaStream_t stream) {
-  if (D == 128) return launch_bwd_one<128>(tm_q, tm_k, tm_v, tm_do, tm_dq, p, stream);
-  if (D == 64) return launch_bwd_one<64>(tm_q, tm_k, tm_v, tm_do, tm_dq, p, stream);
+                            const CUtensorMap& tm_do, const CUtensorMap& tm_dq, float* dq_acc, int Lq_total,
+                            const AttnBwdParams& p, cudaStream_t stream) {
+  if (D == 128) return launch_bwd_one<128>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream);
+  if (D == 64) return launch_bwd_one<64>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream);
   return cudaErrorInvalidValue;
 }
 

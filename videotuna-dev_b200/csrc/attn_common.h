@@ -55,8 +55,8 @@ struct AttnBwdParams {
 cudaError_t launch_attn_fwd(int D, const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
                             const AttnFwdParams& p, int q_tiles_hint, cudaStream_t stream);
 cudaError_t launch_attn_bwd(int D, const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
-                            const CUtensorMap& tm_do, const CUtensorMap& tm_dq, const AttnBwdParams& p,
-                            cudaStream_t stream);
+                            const CUtensorMap& tm_do, const CUtensorMap& tm_dq, float* dq_acc, int Lq_total,
+                            const AttnBwdParams& p, cudaStream_t stream);
 cudaError_t launch_attn_bwd_delta(int D, const void* dout, const void* o, float* delta, const int64_t* do_strides,
                                   const int64_t* o_strides, int B, int L, int H, cudaStream_t stream);
 cudaError_t launch_attn_bwd_dq_convert(const float* acc, void* dq, const int64_t* dq_strides, int B, int L, int H, int D,

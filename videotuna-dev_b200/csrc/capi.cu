@@ -336,7 +336,7 @@ int vt_attn_bwd(const void* dout, const void* q, const void* k, const void* v, c
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   {
     ProfScope span(VT_K_ATTN_BWD, st);
-    VT_CHECK_CUDA(launch_attn_bwd(D, tm_q, tm_k, tm_v, tm_do, tm_dq, p, st));
+    VT_CHECK_CUDA(launch_attn_bwd(D, tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq, p, st));
   }
   {
     ProfScope span(VT_K_ATTN_BWD_DQ, st);

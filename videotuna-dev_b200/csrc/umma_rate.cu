@@ -120,9 +120,55 @@ namespace {
 // Each CTA issues `iters` reductions of one 128-row x 32-column fp32 box (16 KB) with `depth` bulk groups in flight.
 // spread == 0: every CTA targets the same rows at the same time (what unstaggered backward CTAs do);
 // spread == 1: CTA b starts at row tile b and walks from there.
+// Concurrent TMA loads (what the backward producer does while the drain reduces): thread 32 streams 16 KB boxes of a
+// bf16 tensor into a second smem region, 4 in flight, until the reducing thread is done. load_mode 0: no loads.
 __global__ void __launch_bounds__(128, 1)
-tma_reduce_rate_kernel(const __grid_constant__ CUtensorMap tm, int iters, int depth, int spread, int n_tiles,
-                       long long* cycles_out) {
+tma_mixed_rate_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_ld, int iters,
+                      int n_tiles, int load_mode, long long* cycles_out, long long* loads_out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 8 * 16384);
+  volatile int* stop = reinterpret_cast<volatile int*>(bars + 4);
+  for (int i = threadIdx.x; i < 4 * 16384 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(bars + i, 1);
+    fence_mbar_init();
+    *stop = 0;
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const int tile = (it / 4 + blockIdx.x) % n_tiles;
+      tma_reduce_add_4d(&tm, smem + (it & 1) * 16384, (it & 3) * 32, tile * 128, 0, 0);
+      tma_commit_group();
+      tma_wait_group_read<1>();
+    }
+    tma_wait_group<0>();
+    cycles_out[blockIdx.x] = clock64() - t0;
+    *stop = 1;
+  } else if (threadIdx.x == 32 && load_mode != 0) {
+    long long n = 0;
+    int it = 0;
+    while (*stop == 0) {
+      const int s = it & 3;
+      if (it >= 4) mbar_wait(bars + s, ((it >> 2) - 1) & 1, 0x920);
+      mbar_arrive_expect_tx(bars + s, 16384);
+      tma_load_4d(smem + (4 + s) * 16384, &tm_ld, bars + s, (it & 1) * 64, ((it >> 1) % (n_tiles * 2)) * 64 % (n_tiles * 128 - 128), 0, 0);
+      ++it;
+      ++n;
+    }
+    for (int k = 0; k < 4 && k < it; ++k) {
+      const int j = it - 1 - k;
+      mbar_wait(bars + (j & 3), (j >> 2) & 1, 0x921);
+    }
+    loads_out[blockIdx.x] = n;
+  }
+}
+
+__global__ void __launch_bounds__(128, 1)
+tma_reduce_rate_kernel(const __grid_constant__ CUtensorMap tm, float* linear, int iters, int depth, int spread,
+                       int n_tiles, long long* cycles_out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   for (int i = threadIdx.x; i < 4 * 16384 / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   fence_proxy_async_smem();
@@ -131,7 +177,15 @@ tma_reduce_rate_kernel(const __grid_constant__ CUtensorMap tm, int iters, int de
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
       const int tile = (it / 4 + (spread ? blockIdx.x : 0)) % n_tiles;
-      tma_reduce_add_4d(&tm, smem + (it & 3) * 16384, (it & 3) * 32, tile * 128, 0, 0);
+      if (linear != nullptr) {
+        // 1-D bulk reduction of 16 KB of contiguous floats (no tensor map): rows of the accumulator are contiguous
+        float* dst = linear + (static_cast<size_t>(tile) * 4 + (it & 3)) * 4096;
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
+                     "r"(smem_u32(smem + (it & 3) * 16384)), "r"(16384)
+                     : "memory");
+      } else {
+        tma_reduce_add_4d(&tm, smem + (it & 3) * 16384, (it & 3) * 32, tile * 128, 0, 0);
+      }
       tma_commit_group();
       if (depth == 1) tma_wait_group_read<0>();
       else if (depth == 2) tma_wait_group_read<1>();
@@ -145,18 +199,40 @@ tma_reduce_rate_kernel(const __grid_constant__ CUtensorMap tm, int iters, int de
 }  // namespace
 }  // namespace vt
 
+extern "C" int vt_tma_mixed_rate(float* acc, const void* src_bf16, int n_tiles, int iters, int load_mode, int blocks,
+                                 long long* cycles_out, long long* loads_out, void* stream) {
+  VT_REQUIRE(acc && src_bf16 && cycles_out && loads_out, VT_ERR_NULL, "vt_tma_mixed_rate: NULL argument");
+  if (int rc = lib_init()) return rc;
+  CUtensorMap tm, tm_ld;
+  const int64_t st[3] = {static_cast<int64_t>(n_tiles) * 128 * 128, 128, 128};
+  if (int rc = make_tmap_4d(&tm, acc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 128, static_cast<int64_t>(n_tiles) * 128, 1, 1, st, 32, 128))
+    return rc;
+  if (int rc = make_tmap_4d(&tm_ld, src_bf16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, 128, static_cast<int64_t>(n_tiles) * 128, 1, 1, st, 64, 128))
+    return rc;
+  const int bytes = 8 * 16384 + 64;
+  VT_CHECK_CUDA(cudaFuncSetAttribute(tma_mixed_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  tma_mixed_rate_kernel<<<blocks, 128, bytes, static_cast<cudaStream_t>(stream)>>>(tm, tm_ld, iters, n_tiles, load_mode,
+                                                                                  cycles_out, loads_out);
+  VT_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int vt_tma_reduce_rate(float* acc, int n_tiles, int iters, int depth, int spread, int blocks,
                                   long long* cycles_out, void* stream) {
   VT_REQUIRE(acc != nullptr && cycles_out != nullptr, VT_ERR_NULL, "vt_tma_reduce_rate: NULL argument");
-  VT_REQUIRE(n_tiles > 0 && iters > 0 && depth >= 1 && depth <= 4 && blocks > 0, VT_ERR_SHAPE, "bad argument");
+  VT_REQUIRE(n_tiles > 0 && iters > 0 && ((depth >= 1 && depth <= 4) || (depth >= 17 && depth <= 20)) && blocks > 0,
+             VT_ERR_SHAPE, "bad argument");
   if (int rc = lib_init()) return rc;
   CUtensorMap tm;
   const int64_t st[3] = {static_cast<int64_t>(n_tiles) * 128 * 128, 128, 128};
   if (int rc = make_tmap_4d(&tm, acc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, 128, static_cast<int64_t>(n_tiles) * 128, 1, 1, st, 32, 128))
     return rc;
   VT_CHECK_CUDA(cudaFuncSetAttribute(tma_reduce_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 16384));
-  tma_reduce_rate_kernel<<<blocks, 128, 4 * 16384, static_cast<cudaStream_t>(stream)>>>(tm, iters, depth, spread, n_tiles,
-                                                                                       cycles_out);
+  // depth >= 16 selects the 1-D (non-tensor) bulk reduction with depth - 16 groups in flight
+  float* linear = depth >= 16 ? acc : nullptr;
+  if (depth >= 16) depth -= 16;
+  tma_reduce_rate_kernel<<<blocks, 128, 4 * 16384, static_cast<cudaStream_t>(stream)>>>(tm, linear, iters, depth, spread,
+                                                                                       n_tiles, cycles_out);
   VT_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

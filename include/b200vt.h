@@ -91,6 +91,22 @@ int vt_attn_bwd(const void* dout, const void* q, const void* k, const void* v, c
                 int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Micro-attention over very short sequences (N <= 32), one warp per (sequence, head) pair; HBM-bound.
+ * Replaces the attention core of lvdm TemporalTransformer blocks: CrossAttention.forward over t = 16 frames for
+ * b*h*w sequences (videotuna/models/lvdm/modules/attention.py:126-149 as called from :475-519).
+ * q, k, v, o: (B, N, H, D) bf16 with (b,n,h) element strides, D in {64,128}. mask: optional (N, N) fp32 shared by all
+ * pairs, > 0.5 = keep, others filled with -FLT_MAX before the softmax (attention.py:136-140). Backward recomputes the
+ * probabilities; dq, dk, dv are written as contiguous (B, N, H, D) bf16.
+ * ------------------------------------------------------------------------------------------------------------- */
+int vt_temporal_attn_fwd(const void* q, const void* k, const void* v, void* o, const float* mask,
+                         const int64_t* q_strides, const int64_t* k_strides, const int64_t* v_strides,
+                         const int64_t* o_strides, int B, int N, int H, int D, float softmax_scale, void* stream);
+int vt_temporal_attn_bwd(const void* dout, const void* q, const void* k, const void* v, void* dq, void* dk, void* dv,
+                         const float* mask, const int64_t* do_strides, const int64_t* q_strides,
+                         const int64_t* k_strides, const int64_t* v_strides, int B, int N, int H, int D,
+                         float softmax_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Fused QK-RMSNorm + 3-D RoPE (interleaved pairs) in one pass over q or k, in place of
  *   hunyuan RMSNorm (norm_layers.py:5-59) + apply_rotary_emb (posemb_layers.py:140-188)      -> norm_mode 1
  *   wan WanRMSNorm over dim = H*D (model.py:70-86) + rope_apply (model.py:40-67)              -> norm_mode 2

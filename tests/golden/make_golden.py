@@ -161,6 +161,28 @@ def golden_lvdm(gen):
                                 out=gn(xg).detach(), out_silu=torch.nn.functional.silu(gn(xg)).detach()))
 
 
+def golden_lvdm_temporal():
+    """Temporal self-attention as VideoCrafter2/DynamiCrafter configure it (no relative position): plain and with the
+    causal mask TemporalTransformer builds (attention.py:487-489). Own generator so earlier fixtures stay unchanged."""
+    from videotuna.models.lvdm.modules import attention as A
+    gen = torch.Generator().manual_seed(SEED + 7)
+    cases = {}
+    kw = dict(query_dim=128, context_dim=None, heads=2, dim_head=64, temporal_length=16)
+    m = round_params(A.CrossAttention(**kw))
+    xt = RN(40, 16, 128, generator=gen)
+    mask = torch.tril(torch.ones(1, 16, 16))
+    cases["temporal"] = dict(kw=kw, sd=sd(m), x=xt, context=None, mask=None, out=m(xt).detach())
+    cases["temporal_causal"] = dict(kw=kw, sd=sd(m), x=xt, context=None, mask=mask,
+                                    out=m(xt, mask=mask.expand(40, -1, -1)).detach())
+    xg = xt.clone().requires_grad_(True)
+    do = RN(40, 16, 128, generator=gen)
+    out = m(xg, mask=mask.expand(40, -1, -1))
+    out.backward(do)
+    cases["temporal_causal"].update(dout=do, dx=xg.grad.detach(),
+                                    dw_q=m.to_q.weight.grad.detach().clone(), dw_v=m.to_v.weight.grad.detach().clone())
+    save("lvdm_temporal_attention", cases)
+
+
 def golden_hunyuan(gen):
     M = importlib.import_module("videotuna.models.hunyuan.hyvideo_t2v.modules.models")
     att = importlib.import_module("videotuna.models.hunyuan.hyvideo_t2v.modules.attenion")
@@ -295,6 +317,7 @@ def main():
     golden_lvdm(gen)
     golden_hunyuan(gen)
     golden_wan(gen)
+    golden_lvdm_temporal()
 
 
 if __name__ == "__main__":

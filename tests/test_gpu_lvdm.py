@@ -1,0 +1,111 @@
+"""lvdm drop-in body and the temporal micro-attention kernel on the GPU, against fixtures recorded from the reference
+(tests/golden/lvdm_*.pt) and against the oracle. Tolerances: BASELINE.md §5."""
+import pytest
+import torch
+
+from conftest import load_golden
+from helpers import CrossAttentionShell
+from oracle import ref_ops as R
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+
+def _run_case(case):
+    import b200vt.functional as Fn
+    dev = torch.device("cuda")
+    m = CrossAttentionShell.from_fixture(case, dev)
+    x = case["x"].to(dev, torch.bfloat16)
+    ctx = None if case["context"] is None else case["context"].to(dev, torch.bfloat16)
+    mask = None if case["mask"] is None else case["mask"].to(dev).expand(x.shape[0], -1, -1)
+    return m, x, Fn.lvdm_cross_attention_forward(m, x, context=ctx, mask=mask)
+
+
+@pytest.mark.parametrize("name", ["self", "cross", "img_cross"])
+def test_cross_attention_forward_matches_reference_fixture(name):
+    case = load_golden("lvdm_cross_attention")[name]
+    _, _, out = _run_case(case)
+    assert R.max_rel_err(out.float().cpu(), case["out"].float()) < TOL
+
+
+@pytest.mark.parametrize("name", ["temporal", "temporal_causal"])
+def test_temporal_attention_module_matches_reference_fixture(name):
+    case = load_golden("lvdm_temporal_attention")[name]
+    _, _, out = _run_case(case)
+    assert R.max_rel_err(out.float().cpu(), case["out"].float()) < TOL
+
+
+def test_temporal_causal_backward_matches_reference_fixture():
+    import b200vt.functional as Fn
+    case = load_golden("lvdm_temporal_attention")["temporal_causal"]
+    dev = torch.device("cuda")
+    m = CrossAttentionShell.from_fixture(case, dev)
+    x = case["x"].to(dev, torch.bfloat16).requires_grad_(True)
+    mask = case["mask"].to(dev).expand(x.shape[0], -1, -1)
+    out = Fn.lvdm_cross_attention_forward(m, x, mask=mask)
+    out.backward(case["dout"].to(dev, torch.bfloat16))
+    assert R.cosine(x.grad.float().cpu(), case["dx"].float()) > 0.999
+    assert R.cosine(m.to_q.weight.grad.float().cpu(), case["dw_q"].float()) > 0.999
+    assert R.cosine(m.to_v.weight.grad.float().cpu(), case["dw_v"].float()) > 0.999
+
+
+def test_relative_position_stays_on_reference_path():
+    import b200vt.functional as Fn
+    case = load_golden("lvdm_cross_attention")["temporal_relpos"]
+    dev = torch.device("cuda")
+    m = CrossAttentionShell.from_fixture(case, dev)
+    with pytest.raises(Fn.Unsupported):
+        Fn.lvdm_cross_attention_forward(m, case["x"].to(dev, torch.bfloat16))
+
+
+def test_fp32_activations_stay_on_reference_path():
+    import b200vt.functional as Fn
+    case = load_golden("lvdm_cross_attention")["self"]
+    dev = torch.device("cuda")
+    m = CrossAttentionShell.from_fixture(case, dev, dtype=torch.float32)
+    with pytest.raises(Fn.Unsupported):
+        Fn.lvdm_cross_attention_forward(m, case["x"].to(dev, torch.float32))
+
+
+def _rand(shape, seed):
+    return torch.randn(shape, generator=torch.Generator().manual_seed(seed)).to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("B,N,H,D,masked", [(3, 16, 5, 64, False), (7, 16, 2, 64, True), (2, 1, 3, 64, False),
+                                             (5, 7, 2, 64, True), (4, 32, 2, 64, False), (3, 16, 2, 128, True),
+                                             (1000, 16, 5, 64, False)])
+def test_temporal_kernel_fwd_bwd_vs_oracle(B, N, H, D, masked):
+    import b200vt.functional as Fn
+    q, k, v, do = (_rand((B, N, H, D), s) for s in (1, 2, 3, 4))
+    mask = torch.tril(torch.ones(N, N)) if masked else None
+    scale = D ** -0.5
+    qr, kr, vr = (t.float().requires_grad_(True) for t in (q, k, v))
+
+    def heads_first(t):  # (B,N,H,D) -> (B*H, N, D)
+        return t.permute(0, 2, 1, 3).reshape(B * H, N, D)
+
+    ref = R.lvdm_attention_core(heads_first(qr), heads_first(kr), heads_first(vr), scale,
+                                mask=None if mask is None else mask[None])
+    ref = ref.view(B, H, N, D).permute(0, 2, 1, 3)
+    ref.backward(do.float())
+    qc, kc, vc = (t.cuda().requires_grad_(True) for t in (q, k, v))
+    out = Fn.temporal_attention(qc, kc, vc, softmax_scale=scale, mask=None if mask is None else mask.cuda())
+    out.backward(do.cuda())
+    assert R.max_rel_err(out.float().cpu(), ref.detach()) < TOL
+    for got, want in ((qc.grad, qr.grad), (kc.grad, kr.grad), (vc.grad, vr.grad)):
+        if float(want.abs().max()) < 1e-6:  # N == 1: softmax over one key is constant, dq = dk = 0 exactly
+            assert float(got.float().abs().max()) < 1e-3
+            continue
+        assert R.cosine(got.float().cpu(), want) > 0.999
+        assert R.max_rel_err(got.float().cpu(), want) < TOL
+
+
+def test_temporal_kernel_strided_views():
+    # q, k, v as views of one fused (B, N, 3, H, D) projection
+    import b200vt.functional as Fn
+    B, N, H, D = 9, 16, 4, 64
+    qkv = _rand((B, N, 3, H, D), 11).cuda()
+    q, k, v = qkv.unbind(2)
+    out = Fn.temporal_attention(q, k, v)
+    ref = R.sdpa_blhd(q.float().cpu(), k.float().cpu(), v.float().cpu())
+    assert R.max_rel_err(out.float().cpu(), ref) < TOL

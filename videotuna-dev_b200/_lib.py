@@ -29,9 +29,9 @@ _SIGS = {
     "vt_attn_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp] + [c_i64p] * 8 + [C.c_int] * 5 + [vp, vp, C.c_int, C.c_int,
                     C.c_int, vp, C.c_float, vp, C.c_int64, vp],
     "vt_temporal_attn_fwd": [vp, vp, vp, vp, vp, c_i64p, c_i64p, c_i64p, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int,
-                             vp, vp, C.c_int, C.c_float, vp],
-    "vt_temporal_attn_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp] + [c_i64p] * 7 + [C.c_int] * 4 +
-                            [vp, vp, C.c_int, C.c_float, vp],
+                             C.c_float, vp],
+    "vt_temporal_attn_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, c_i64p, c_i64p, c_i64p, c_i64p, C.c_int, C.c_int, C.c_int,
+                             C.c_int, C.c_float, vp],
     "vt_qk_rmsnorm_rope_fwd": [vp, vp, vp, vp, vp, vp, c_i64p, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                C.c_int, C.c_float, vp],
     "vt_qk_rmsnorm_rope_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, c_i64p, c_i64p, c_i64p, C.c_int, C.c_int, C.c_int,

@@ -1,0 +1,277 @@
+// temporal_attn.cu — micro-attention over very short sequences (N <= 32 tokens), forward and backward.
+//
+// Replaces the attention core of lvdm's TemporalTransformer blocks (videotuna/models/lvdm/modules/attention.py:475-519
+// reshapes (b, c, t, h, w) to (b*h*w, t, c); CrossAttention.forward :126-149 then runs softmax(q k^T * scale [mask]) v
+// over t = 16 frames for tens of thousands of (position, head) pairs). The work per pair is ~64 KFLOP against 8 KB of
+// q/k/v/o, so the kernel is HBM-bound: one warp owns one (sequence, head) pair, stages q, k, v (and dO) in shared
+// memory with coalesced 128-bit loads, does the N x N arithmetic in fp32 registers and writes each output row as one
+// coalesced store. No tensor cores: a 16 x 16 problem cannot fill a 128-row MMA tile, and the bytes dominate anyway.
+//
+// mask (optional): (N, N) fp32, > 0.5 = keep, shared by every pair — the causal temporal mask of attention.py:487-489;
+// masked scores are filled with -FLT_MAX before the softmax exactly like masked_fill(~mask, -finfo.max) (:136-140).
+#include <cfloat>
+#include <cuda_bf16.h>
+
+#include "capi_util.h"
+
+namespace vt {
+namespace {
+
+constexpr int kWarps = 4;       // (sequence, head) pairs in flight per CTA
+constexpr int kMaxN = 32;
+
+template <int D>
+struct TemporalSmem {
+  static constexpr int PITCH = D + 2;  // bf16 elements; +2 keeps row-per-lane reads conflict-free (pitch/2 odd)
+  __nv_bfloat16 q[kMaxN * PITCH];
+  __nv_bfloat16 k[kMaxN * PITCH];
+  __nv_bfloat16 v[kMaxN * PITCH];
+  __nv_bfloat16 g[kMaxN * PITCH];      // dO (backward only)
+  float p[kMaxN * (kMaxN + 1)];        // probabilities, [query][key]
+  float ds[kMaxN * (kMaxN + 1)];       // dS (backward only)
+};
+
+struct TemporalArgs {
+  const __nv_bfloat16 *q, *k, *v, *dout;
+  __nv_bfloat16 *o, *dq, *dk, *dv;
+  const float* mask;
+  int64_t q_s[3], k_s[3], v_s[3], o_s[3], g_s[3];  // (b, n, h) element strides; gradients are contiguous (B, N, H, D)
+  int B, N, H;
+  float scale;
+};
+
+// Stage one (N x D) bf16 matrix with row stride `sn` into padded shared memory; 128-bit global loads.
+template <int D>
+__device__ __forceinline__ void stage(__nv_bfloat16* dst, const __nv_bfloat16* src, int64_t sn, int N, int lane) {
+  constexpr int PITCH = TemporalSmem<D>::PITCH;
+  constexpr int VPR = D / 8;  // 16-byte vectors per row
+  for (int idx = lane; idx < N * VPR; idx += 32) {
+    const int r = idx / VPR, c = (idx % VPR) * 8;
+    const uint4 w = *reinterpret_cast<const uint4*>(src + r * sn + c);
+    uint32_t* d32 = reinterpret_cast<uint32_t*>(dst + r * PITCH + c);  // PITCH is even: 4-byte aligned
+    d32[0] = w.x; d32[1] = w.y; d32[2] = w.z; d32[3] = w.w;
+  }
+}
+
+__device__ __forceinline__ float warp_max(float x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+  return x;
+}
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+// Scores and probabilities for the staged q, k: lane j owns key j. Writes P[i][j] to sm.p.
+template <int D>
+__device__ __forceinline__ void softmax_rows(TemporalSmem<D>& sm, const TemporalArgs& a, int lane) {
+  constexpr int PITCH = TemporalSmem<D>::PITCH;
+  const int N = a.N;
+  const bool key_ok = lane < N;
+  const __nv_bfloat16* krow = sm.k + (key_ok ? lane : 0) * PITCH;
+  for (int i = 0; i < N; ++i) {
+    const __nv_bfloat16* qrow = sm.q + i * PITCH;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int d = 0; d < D; d += 2) {
+      const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(krow + d));
+      const float2 qq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qrow + d));
+      acc = fmaf(qq.x, kk.x, acc);
+      acc = fmaf(qq.y, kk.y, acc);
+    }
+    float s = acc * a.scale;
+    if (a.mask != nullptr && key_ok && !(a.mask[i * N + lane] > 0.5f)) s = -FLT_MAX;
+    if (!key_ok) s = -INFINITY;
+    const float m = warp_max(s);
+    const float e = key_ok ? __expf(s - m) : 0.f;
+    const float l = warp_sum(e);
+    if (key_ok) sm.p[i * (kMaxN + 1) + lane] = e / l;
+  }
+  __syncwarp();
+}
+
+// out[r][d] = sum_c coef(r, c) * mat[c][d] for the lane's D/32 consecutive dims; coef read as broadcast from smem.
+template <int D, bool TRANSPOSED>
+__device__ __forceinline__ void mix_rows(const float* coef, const __nv_bfloat16* mat, int N, int lane, int r,
+                                         float (&out)[D / 32]) {
+  constexpr int PITCH = TemporalSmem<D>::PITCH;
+  constexpr int PER = D / 32;
+#pragma unroll
+  for (int e = 0; e < PER; ++e) out[e] = 0.f;
+  for (int c = 0; c < N; ++c) {
+    const float w = TRANSPOSED ? coef[c * (kMaxN + 1) + r] : coef[r * (kMaxN + 1) + c];
+    const __nv_bfloat16* mrow = mat + c * PITCH + lane * PER;
+#pragma unroll
+    for (int e = 0; e < PER; e += 2) {
+      const float2 mm = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(mrow + e));
+      out[e] = fmaf(w, mm.x, out[e]);
+      out[e + 1] = fmaf(w, mm.y, out[e + 1]);
+    }
+  }
+}
+
+template <int D>
+__device__ __forceinline__ void store_row(__nv_bfloat16* dst, const float (&val)[D / 32], int lane, float mul) {
+  constexpr int PER = D / 32;
+  if constexpr (PER == 2) {
+    *reinterpret_cast<__nv_bfloat162*>(dst + lane * 2) = __floats2bfloat162_rn(val[0] * mul, val[1] * mul);
+  } else {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(val[0] * mul, val[1] * mul);
+    __nv_bfloat162 hi = __floats2bfloat162_rn(val[2] * mul, val[3] * mul);
+    uint2 w;
+    w.x = *reinterpret_cast<uint32_t*>(&lo);
+    w.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(dst + lane * 4) = w;
+  }
+}
+
+template <int D, bool BWD>
+__global__ void __launch_bounds__(kWarps * 32)
+temporal_attn_kernel(const TemporalArgs a) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  TemporalSmem<D>& sm = reinterpret_cast<TemporalSmem<D>*>(smem_raw)[warp];
+  const int64_t pairs = static_cast<int64_t>(a.B) * a.H;
+  const int N = a.N;
+  for (int64_t pair = static_cast<int64_t>(blockIdx.x) * kWarps + warp; pair < pairs;
+       pair += static_cast<int64_t>(gridDim.x) * kWarps) {
+    const int b = static_cast<int>(pair / a.H), h = static_cast<int>(pair % a.H);
+    stage<D>(sm.q, a.q + b * a.q_s[0] + h * a.q_s[2], a.q_s[1], N, lane);
+    stage<D>(sm.k, a.k + b * a.k_s[0] + h * a.k_s[2], a.k_s[1], N, lane);
+    stage<D>(sm.v, a.v + b * a.v_s[0] + h * a.v_s[2], a.v_s[1], N, lane);
+    if (BWD) stage<D>(sm.g, a.dout + b * a.g_s[0] + h * a.g_s[2], a.g_s[1], N, lane);
+    __syncwarp();
+    softmax_rows<D>(sm, a, lane);
+    if (!BWD) {
+      for (int i = 0; i < N; ++i) {
+        float o[D / 32];
+        mix_rows<D, false>(sm.p, sm.v, N, lane, i, o);
+        store_row<D>(a.o + b * a.o_s[0] + i * a.o_s[1] + h * a.o_s[2], o, lane, 1.f);
+      }
+    } else {
+      constexpr int PITCH = TemporalSmem<D>::PITCH;
+      // dP[i][j] = dO_i . v_j (lane j); delta_i = sum_j P dP; dS = P (dP - delta)
+      const bool key_ok = lane < N;
+      const __nv_bfloat16* vrow = sm.v + (key_ok ? lane : 0) * PITCH;
+      for (int i = 0; i < N; ++i) {
+        const __nv_bfloat16* grow = sm.g + i * PITCH;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int d = 0; d < D; d += 2) {
+          const float2 vv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vrow + d));
+          const float2 gg = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(grow + d));
+          acc = fmaf(gg.x, vv.x, acc);
+          acc = fmaf(gg.y, vv.y, acc);
+        }
+        const float pij = key_ok ? sm.p[i * (kMaxN + 1) + lane] : 0.f;
+        const float delta = warp_sum(pij * acc);
+        if (key_ok) sm.ds[i * (kMaxN + 1) + lane] = pij * (acc - delta);
+      }
+      __syncwarp();
+      const int64_t gbase = (static_cast<int64_t>(b) * N * a.H + h) * D;  // contiguous (B, N, H, D) gradients
+      const int64_t gn = static_cast<int64_t>(a.H) * D;
+      for (int r = 0; r < N; ++r) {
+        float t[D / 32];
+        mix_rows<D, true>(sm.p, sm.g, N, lane, r, t);    // dV_r = sum_i P[i][r] dO_i
+        store_row<D>(a.dv + gbase + r * gn, t, lane, 1.f);
+        mix_rows<D, true>(sm.ds, sm.q, N, lane, r, t);   // dK_r = scale * sum_i dS[i][r] q_i
+        store_row<D>(a.dk + gbase + r * gn, t, lane, a.scale);
+        mix_rows<D, false>(sm.ds, sm.k, N, lane, r, t);  // dQ_r = scale * sum_j dS[r][j] k_j
+        store_row<D>(a.dq + gbase + r * gn, t, lane, a.scale);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <int D, bool BWD>
+cudaError_t launch(const TemporalArgs& a, cudaStream_t st) {
+  const int bytes = kWarps * static_cast<int>(sizeof(TemporalSmem<D>));
+  cudaError_t e = cudaFuncSetAttribute(temporal_attn_kernel<D, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return e;
+  const int64_t pairs = static_cast<int64_t>(a.B) * a.H;
+  // persistent-style grid: a multiple of the 148 SMs, several CTAs per SM to cover the load latency
+  int64_t blocks = (pairs + kWarps - 1) / kWarps;
+  const int64_t cap = 148 * 8;
+  if (blocks > cap) blocks = cap;
+  temporal_attn_kernel<D, BWD><<<static_cast<unsigned>(blocks), kWarps * 32, bytes, st>>>(a);
+  return cudaGetLastError();
+}
+
+int check(const void* q, const void* k, const void* v, int B, int N, int H, int D, const int64_t* const* strides,
+          int nstr) {
+  VT_REQUIRE(q && k && v, VT_ERR_NULL, "temporal attention: NULL tensor");
+  VT_REQUIRE(D == 64 || D == 128, VT_ERR_DTYPE, "head dim %d unsupported (64 or 128)", D);
+  VT_REQUIRE(B > 0 && H > 0 && N > 0 && N <= kMaxN, VT_ERR_SHAPE, "temporal attention needs 0 < N <= %d (N=%d)", kMaxN, N);
+  for (int t = 0; t < nstr; ++t) {
+    VT_REQUIRE(strides[t] != nullptr, VT_ERR_NULL, "temporal attention: NULL stride array");
+    for (int i = 0; i < 3; ++i)
+      VT_REQUIRE(strides[t][i] % 8 == 0, VT_ERR_ALIGN, "strides must be multiples of 8 elements");
+  }
+  return 0;
+}
+
+void fill(TemporalArgs& a, const int64_t* qs, const int64_t* ks, const int64_t* vs) {
+  for (int i = 0; i < 3; ++i) {
+    a.q_s[i] = qs[i];
+    a.k_s[i] = ks[i];
+    a.v_s[i] = vs[i];
+  }
+}
+
+}  // namespace
+}  // namespace vt
+
+using namespace vt;
+
+extern "C" int vt_temporal_attn_fwd(const void* q, const void* k, const void* v, void* o, const float* mask,
+                                    const int64_t* q_strides, const int64_t* k_strides, const int64_t* v_strides,
+                                    const int64_t* o_strides, int B, int N, int H, int D, float softmax_scale,
+                                    void* stream) {
+  const int64_t* strides[4] = {q_strides, k_strides, v_strides, o_strides};
+  if (int rc = check(q, k, v, B, N, H, D, strides, 4)) return rc;
+  VT_REQUIRE(o != nullptr, VT_ERR_NULL, "o is NULL");
+  VT_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), VT_ERR_ALIGN, "tensors must be 16-byte aligned");
+  TemporalArgs a{};
+  a.q = static_cast<const __nv_bfloat16*>(q);
+  a.k = static_cast<const __nv_bfloat16*>(k);
+  a.v = static_cast<const __nv_bfloat16*>(v);
+  a.o = static_cast<__nv_bfloat16*>(o);
+  a.mask = mask;
+  fill(a, q_strides, k_strides, v_strides);
+  for (int i = 0; i < 3; ++i) a.o_s[i] = o_strides[i];
+  a.B = B; a.N = N; a.H = H;
+  a.scale = softmax_scale;
+  auto st = static_cast<cudaStream_t>(stream);
+  VT_CHECK_CUDA(D == 64 ? (launch<64, false>(a, st)) : (launch<128, false>(a, st)));
+  return 0;
+}
+
+extern "C" int vt_temporal_attn_bwd(const void* dout, const void* q, const void* k, const void* v, void* dq, void* dk,
+                                    void* dv, const float* mask, const int64_t* do_strides, const int64_t* q_strides,
+                                    const int64_t* k_strides, const int64_t* v_strides, int B, int N, int H, int D,
+                                    float softmax_scale, void* stream) {
+  const int64_t* strides[4] = {q_strides, k_strides, v_strides, do_strides};
+  if (int rc = check(q, k, v, B, N, H, D, strides, 4)) return rc;
+  VT_REQUIRE(dout && dq && dk && dv, VT_ERR_NULL, "temporal attention backward: NULL tensor");
+  VT_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(dout) && aligned16(dq) && aligned16(dk) && aligned16(dv),
+             VT_ERR_ALIGN, "tensors must be 16-byte aligned");
+  TemporalArgs a{};
+  a.q = static_cast<const __nv_bfloat16*>(q);
+  a.k = static_cast<const __nv_bfloat16*>(k);
+  a.v = static_cast<const __nv_bfloat16*>(v);
+  a.dout = static_cast<const __nv_bfloat16*>(dout);
+  a.dq = static_cast<__nv_bfloat16*>(dq);
+  a.dk = static_cast<__nv_bfloat16*>(dk);
+  a.dv = static_cast<__nv_bfloat16*>(dv);
+  a.mask = mask;
+  fill(a, q_strides, k_strides, v_strides);
+  for (int i = 0; i < 3; ++i) a.g_s[i] = do_strides[i];
+  a.B = B; a.N = N; a.H = H;
+  a.scale = softmax_scale;
+  auto st = static_cast<cudaStream_t>(stream);
+  VT_CHECK_CUDA(D == 64 ? (launch<64, true>(a, st)) : (launch<128, true>(a, st)));
+  return 0;
+}

@@ -119,7 +119,8 @@ def lvdm_cross_attention_forward(self, x, context=None, mask=None):
 
     Projections stay the module's own nn.Linear layers (state-dict keys and peft LoRA targets are untouched); the
     einsum/softmax/einsum core (attention.py:126-149) runs in one CUDA kernel on the (B, N, H, D) view of the projected
-    tensors, so the reference's two `rearrange` copies disappear. Relative position and masks: temporal kernel only.
+    tensors, so the reference's two `rearrange` copies disappear. Sequences of at most 32 tokens (the temporal
+    transformer's t = 16 frames) go to the one-warp-per-sequence kernel, which also takes the causal mask.
     """
     is_self_attn = context is None
     h = self.heads
@@ -139,9 +140,17 @@ def lvdm_cross_attention_forward(self, x, context=None, mask=None):
     b, n, _ = q.shape
     d = self.dim_head
     q4, k4, v4 = q.view(b, n, h, d), k.view(b, k.shape[1], h, d), v.view(b, v.shape[1], h, d)
-    if self.relative_position or mask is not None:
-        from .temporal import temporal_attention  # small-N kernel with rel-pos / causal support
-        out = temporal_attention(self, q4, k4, v4, mask)
+    _require(not self.relative_position, "relative-position attention (VideoCrafter1 configs) stays on the reference path")
+    small = n <= 32 and k4.shape[1] <= 32
+    if mask is not None:
+        # TemporalTransformer's causal mask: one (t, t) pattern repeated over the batch (attention.py:487-489)
+        _require(small, "masked attention is only on the CUDA path for the temporal (N <= 32) kernel")
+        m = mask if mask.dim() == 2 else mask[0]
+        if mask.dim() == 3 and mask.shape[0] > 1:
+            _require(bool((mask == mask[:1]).all()), "per-sample masks stay on the reference path")
+        out = ops.temporal_attn_fwd(q4, k4, v4, m, float(self.scale))
+    elif small:
+        out = ops.temporal_attn_fwd(q4, k4, v4, None, float(self.scale))
     else:
         out = attention_blhd(q4, k4, v4, softmax_scale=self.scale)
     out = out.reshape(b, n, h * d)
@@ -153,6 +162,16 @@ def lvdm_cross_attention_forward(self, x, context=None, mask=None):
         else:
             out = out + self.img_cross_attention_scale * out_ip
     return self.to_out(out)
+
+
+def temporal_attention(q: Tensor, k: Tensor, v: Tensor, softmax_scale: Optional[float] = None,
+                       mask: Optional[Tensor] = None) -> Tensor:
+    """softmax(q k^T * scale [mask]) v for (B, N, H, D) tensors with N <= 32: lvdm TemporalTransformer's attention
+    over frames (attention.py:475-519). mask: (N, N), > 0.5 = keep."""
+    _require(supported_qkv(q, k, v) and q.shape[1] <= 32 and k.shape[1] <= 32 and q.shape[1] == k.shape[1],
+             "temporal attention needs CUDA bf16 (B, N<=32, H, D in {64,128}) tensors")
+    scale = 1.0 / math.sqrt(q.shape[-1]) if softmax_scale is None else float(softmax_scale)
+    return ops.temporal_attn_fwd(q, k, v, mask, scale)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -119,6 +119,63 @@ attn_fwd.register_autograd(_attn_backward, setup_context=_attn_setup)
 
 
 # =====================================================================================================================
+# temporal micro-attention (N <= 32)
+# =====================================================================================================================
+@torch.library.custom_op("b200vt::temporal_attn_fwd", mutates_args=(), device_types="cuda")
+def temporal_attn_fwd(q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor], softmax_scale: float) -> Tensor:
+    """q, k, v (B, N, H, D) bf16 with N <= 32 -> o (B, N, H, D) contiguous. mask: (N, N) fp32, > 0.5 = keep."""
+    for n, t in (("q", q), ("k", k), ("v", v)):
+        _check_bf16_cuda(n, t)
+    q, k, v = _blhd(q), _blhd(k), _blhd(v)
+    B, N, H, D = q.shape
+    o = torch.empty((B, N, H, D), dtype=q.dtype, device=q.device)
+    m = _f32(mask)
+    with torch.cuda.device(q.device):
+        _lib.call("vt_temporal_attn_fwd", _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(m), _lib.strides3(q), _lib.strides3(k),
+                  _lib.strides3(v), _lib.strides3(o), B, N, H, D, float(softmax_scale), _stream())
+    return o
+
+
+@temporal_attn_fwd.register_fake
+def _(q, k, v, mask, softmax_scale):
+    return q.new_empty(q.shape)
+
+
+@torch.library.custom_op("b200vt::temporal_attn_bwd", mutates_args=(), device_types="cuda")
+def temporal_attn_bwd(dout: Tensor, q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor],
+                      softmax_scale: float) -> Tuple[Tensor, Tensor, Tensor]:
+    q, k, v, dout = _blhd(q), _blhd(k), _blhd(v), _blhd(dout)
+    B, N, H, D = q.shape
+    dq, dk, dv = (torch.empty((B, N, H, D), dtype=q.dtype, device=q.device) for _ in range(3))
+    m = _f32(mask)
+    with torch.cuda.device(q.device):
+        _lib.call("vt_temporal_attn_bwd", _ptr(dout), _ptr(q), _ptr(k), _ptr(v), _ptr(dq), _ptr(dk), _ptr(dv), _ptr(m),
+                  _lib.strides3(dout), _lib.strides3(q), _lib.strides3(k), _lib.strides3(v), B, N, H, D,
+                  float(softmax_scale), _stream())
+    return dq, dk, dv
+
+
+@temporal_attn_bwd.register_fake
+def _(dout, q, k, v, mask, softmax_scale):
+    return q.new_empty(q.shape), q.new_empty(k.shape), q.new_empty(v.shape)
+
+
+def _ta_setup(ctx, inputs, output):
+    q, k, v, mask, scale = inputs
+    ctx.save_for_backward(q, k, v, mask)
+    ctx.scale = scale
+
+
+def _ta_backward(ctx, do):
+    q, k, v, mask = ctx.saved_tensors
+    dq, dk, dv = temporal_attn_bwd(do, q, k, v, mask, ctx.scale)
+    return dq, dk, dv, None, None
+
+
+temporal_attn_fwd.register_autograd(_ta_backward, setup_context=_ta_setup)
+
+
+# =====================================================================================================================
 # LayerNorm + modulate
 # =====================================================================================================================
 @torch.library.custom_op("b200vt::ln_modulate_fwd", mutates_args=(), device_types="cuda")

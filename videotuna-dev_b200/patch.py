@@ -1,0 +1,173 @@
+"""patch_videotuna(): install the b200vt hot path underneath an importable VideoTuna tree.
+
+Nothing here re-implements VideoTuna: each hook is a place where the reference itself already swaps implementations
+(instance-level `self.forward = self.efficient_forward`, name imports of `attention` / `flash_attention`, the
+`hybrid_seq_parallel_attn` attribute). A patched callable first tries the CUDA path; `functional.Unsupported` (fp32 or
+CPU tensors, masks, dropout, causal, unsupported head dims ...) routes the call to the ORIGINAL reference callable,
+never to a CPU kernel of ours.
+
+    import b200vt
+    b200vt.patch.patch_videotuna()          # before building the model; idempotent
+    b200vt.patch.install_ulysses(dit)       # Hunyuan: every block's hybrid_seq_parallel_attn = UlyssesAttention()
+"""
+from __future__ import annotations
+
+import functools
+import importlib
+import types
+from typing import Callable, Dict, Optional
+
+import torch
+
+from . import functional as Fn
+from . import sp
+
+_ORIGINALS: Dict[str, Callable] = {}
+
+
+def _wrap(name: str, original: Callable, fast: Callable) -> Callable:
+    """fast(*a, **k) with fallback to the untouched reference callable on Unsupported."""
+    if getattr(original, "_b200vt_patched", False):
+        return original
+    _ORIGINALS[name] = original
+
+    @functools.wraps(original)
+    def patched(*args, **kwargs):
+        try:
+            return fast(*args, **kwargs)
+        except Fn.Unsupported:
+            return original(*args, **kwargs)
+
+    patched._b200vt_patched = True
+    patched._b200vt_original = original
+    return patched
+
+
+def _try_import(name: str):
+    try:
+        return importlib.import_module(name)
+    except Exception:  # noqa: BLE001  (a missing optional dependency of the reference must not break the others)
+        return None
+
+
+def patch_lvdm(module=None) -> bool:
+    """CrossAttention.forward (videotuna/models/lvdm/modules/attention.py:101-170) -> functional.lvdm_cross_attention_forward.
+    Installed on the class, so instances that switched themselves to `efficient_forward` (xformers, :98-99) keep it."""
+    mod = module or _try_import("videotuna.models.lvdm.modules.attention")
+    if mod is None:
+        return False
+    cls = mod.CrossAttention
+    cls.forward = _wrap("lvdm.CrossAttention.forward", cls.forward, Fn.lvdm_cross_attention_forward)
+    return True
+
+
+def patch_hunyuan(modules=None) -> int:
+    """Rebind the name `attention` that models.py / token_refiner.py imported from attenion.py
+    (hyvideo_t2v/modules/models.py:14, token_refiner.py:8; the i2v package is a byte-identical twin) to
+    functional.hunyuan_attention (same signature, attenion.py:60-156)."""
+    names = modules or [f"videotuna.models.hunyuan.{pkg}.modules.{m}" for pkg in ("hyvideo_t2v", "hyvideo_i2v")
+                        for m in ("models", "token_refiner", "attenion")]
+    n = 0
+    for name in names:
+        mod = name if isinstance(name, types.ModuleType) else _try_import(name)
+        if mod is None or not hasattr(mod, "attention"):
+            continue
+        mod.attention = _wrap(f"{mod.__name__}.attention", mod.attention, Fn.hunyuan_attention)
+        n += 1
+    return n
+
+
+def patch_wan(modules=None) -> int:
+    """Rebind `flash_attention` in wan/modules/model.py (imported at :10, called by WanSelfAttention :146 and the
+    cross-attention classes) and in wan/modules/attention.py (used by attention() :133-179)."""
+    names = modules or ["videotuna.models.wan.wan.modules.model", "videotuna.models.wan.wan.modules.attention"]
+    n = 0
+    for name in names:
+        mod = name if isinstance(name, types.ModuleType) else _try_import(name)
+        if mod is None or not hasattr(mod, "flash_attention"):
+            continue
+        mod.flash_attention = _wrap(f"{mod.__name__}.flash_attention", mod.flash_attention, Fn.wan_flash_attention)
+        n += 1
+    return n
+
+
+def patch_videotuna(lvdm: bool = True, hunyuan: bool = True, wan: bool = True) -> Dict[str, int]:
+    """Install every hook whose reference module imports in this environment; returns what was patched."""
+    done = {"lvdm": 0, "hunyuan": 0, "wan": 0}
+    if lvdm:
+        done["lvdm"] = int(patch_lvdm())
+    if hunyuan:
+        done["hunyuan"] = patch_hunyuan()
+    if wan:
+        done["wan"] = patch_wan()
+    return done
+
+
+def unpatch_videotuna() -> None:
+    """Restore every original callable (tests)."""
+    for name, original in list(_ORIGINALS.items()):
+        if name == "lvdm.CrossAttention.forward":
+            mod = _try_import("videotuna.models.lvdm.modules.attention")
+            if mod is not None:
+                mod.CrossAttention.forward = original
+        else:
+            modname, attr = name.rsplit(".", 1)
+            mod = _try_import(modname)
+            if mod is not None:
+                setattr(mod, attr, original)
+        _ORIGINALS.pop(name, None)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# sequence parallelism
+# ---------------------------------------------------------------------------------------------------------------------
+def install_ulysses(transformer: torch.nn.Module, group=None) -> int:
+    """What parallelize_transformer does with xfuser (videotuna/flow/hunyuanvideo.py:154-157): every double/single
+    stream block gets `hybrid_seq_parallel_attn`, here a b200vt.sp.UlyssesAttention with xfuser's call signature."""
+    attn = sp.UlyssesAttention(group)
+    n = 0
+    for name in ("double_blocks", "single_blocks"):
+        for block in getattr(transformer, name, []):
+            block.hybrid_seq_parallel_attn = attn
+            n += 1
+    return n
+
+
+def wan_sp_rope_tables(grid_size, freqs: torch.Tensor, s_local: int, group=None):
+    """cos/sin tables (s_local, D) for this rank's slice of the token sequence, equal to what the reference's
+    sequence-parallel rope_apply multiplies by (xdit_context_parallel.py:26-63): the (f*h*w, D/2) complex table is
+    padded with ones to s_local * P rows (pad_freqs :12-22) and rows [rank*s_local, (rank+1)*s_local) are taken."""
+    f, h, w = (int(v) for v in grid_size)
+    c = freqs.shape[1]
+    fs = freqs.split([c - 2 * (c // 3), c // 3, c // 3], dim=1)
+    fr = torch.cat([fs[0][:f].view(f, 1, 1, -1).expand(f, h, w, -1), fs[1][:h].view(1, h, 1, -1).expand(f, h, w, -1),
+                    fs[2][:w].view(1, 1, w, -1).expand(f, h, w, -1)], dim=-1).reshape(f * h * w, -1)
+    P, r = sp._world(group), sp._rank(group)
+    pad = s_local * P - fr.shape[0]
+    if pad > 0:
+        fr = torch.cat([fr, torch.ones(pad, c, dtype=fr.dtype, device=fr.device)], dim=0)
+    fr = fr[r * s_local:(r + 1) * s_local]
+    return (fr.real.float().repeat_interleave(2, dim=1).contiguous(),
+            fr.imag.float().repeat_interleave(2, dim=1).contiguous())
+
+
+def wan_usp_attn_forward(self, x, seq_lens, grid_sizes, freqs, dtype=torch.bfloat16, group=None):
+    """Replacement for usp_attn_forward (xdit_context_parallel.py:149-192), bound with types.MethodType onto
+    WanSelfAttention like the reference does (wan/text2video.py:261-271): q/k/v projections and the full-dim RMSNorm
+    stay the module's own layers; RoPE on this rank's token slice is fused with the bf16 cast; attention is Ulysses."""
+    b, s, n, d = *x.shape[:2], self.num_heads, self.head_dim
+    q = self.norm_q(self.q(x)).view(b, s, n, d)
+    k = self.norm_k(self.k(x)).view(b, s, n, d)
+    v = self.v(x).view(b, s, n, d)
+    if not (x.is_cuda and b == 1):
+        raise Fn.Unsupported("sequence-parallel Wan attention needs CUDA tensors and batch 1 (as the reference pipeline)")
+    cos, sin = wan_sp_rope_tables(grid_sizes[0].tolist(), freqs, s, group)
+    cos, sin = cos.to(x.device), sin.to(x.device)
+
+    def half(t):
+        return t if t.dtype == torch.bfloat16 else t.to(dtype)
+
+    q = Fn.qk_rmsnorm_rope(half(q), None, cos, sin)
+    k = Fn.qk_rmsnorm_rope(half(k), None, cos, sin)
+    out = sp.UlyssesAttention(group)(None, q, k, half(v), window_size=self.window_size)
+    return self.o(out.flatten(2).to(x.dtype))

@@ -16,10 +16,11 @@
 //   MMA4  dQ_i = dS  K            SS   (A = dS as MN-major view of the same tile, B = K MN-major) -> TMEM dQ
 //   MMA5  dK  += dS^T Q_i         SS   (A = dS^T K-major, B = Q_i MN-major)   (runs while dQ_i is drained)
 //   DR    dQ_i: TMEM -> registers -> swizzled smem chunk -> TMA reduce-add into dq_acc (drain warpgroup)
-// Warps: 0-7 compute (thread = key row x half of the q columns), 8-11 dQ reduce (thread = q row), 12 producer
-// (TMA + lse/delta staging), 13 MMA issuer, 14-15 idle (complete the 4th warpgroup for setmaxnreg).
+// Warps: 0-7 compute (thread = key row x half of the q columns), 8-11 dQ drain (thread = q row), 13 MMA issuer,
+// 12/14/15 loaders (K/V by TMA once; Q and dO tiles by cp.async; lse/delta staging).
 // TMEM columns: S [0,128) (P^T bf16 at [32,96)), dP [128,256), dV [256,256+D), dK [256+D,256+2D),
 //   dQ: D=128 aliases dP (dP is dead once dS is in shared memory); D=64 uses [384,448).
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <math_constants.h>
 
@@ -69,7 +70,39 @@ enum : uint32_t {
 };
 
 
+// 16-byte asynchronous copy global -> shared through the LSU (cp.async / LDGSTS); src_bytes == 0 zero-fills.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Copy rows [row0, row0 + 128) of a (rows_total, D) bf16 matrix with row stride `sl` into a 128B-swizzled tile
+// (KCH boxes of [128 rows][64 elements]; 16-byte unit u of row r lives at u ^ (r & 7)) — the layout TMA produces and
+// the UMMA descriptors expect. Rows at or past rows_total are zero-filled. `nthr` loader threads share the work.
 template <int D>
+__device__ __forceinline__ void lsu_load_tile(uint8_t* tile, const __nv_bfloat16* base, int64_t sl, int row0,
+                                              int rows_total, int lt, int nthr) {
+  constexpr int UPR = D / 8;  // 16-byte units per row
+  for (int u = lt; u < 128 * UPR; u += nthr) {
+    const int row = u / UPR, c16 = u % UPR;
+    const int grow = row0 + row;
+    const bool ok = grow < rows_total;
+    const __nv_bfloat16* src = base + (ok ? static_cast<int64_t>(grow) * sl + c16 * 8 : 0);
+    uint8_t* dst = tile + (c16 >> 3) * (128 * 128) + row * 128 + (((c16 & 7) ^ (row & 7)) << 4);
+    cp_async16(dst, src, ok ? 16u : 0u);
+  }
+}
+
+// LSU = false (default): Q and dO tiles arrive by TMA. LSU = true (experiment, VT_BWD_LSU_LOADS=1): they are loaded
+// with cp.async by three loader warps to leave the per-SM TMA engine to the dQ reduction (25.6 B/clk of fp32
+// reduce-add; a 16 KB reduction takes ~830 instead of 641 cycles when the engine also carries loads —
+// tools/tma_reduce_rate.py). Measured result: slower, see launch_attn_bwd.
+template <int D, bool LSU>
 __global__ void __launch_bounds__(BwdCfg<D>::THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
@@ -135,6 +168,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM);
 
   constexpr int PROD_WARP = 12, MMA_WARP = 13;
+  // LSU: warp 12 loads the Q ring (two stages of slack), warps 14-15 the single-buffered dO tile; each group runs its
+  // own loop so a blocking cp.async wait of one never delays the other.
+  constexpr int Q_LOADERS = LSU ? 32 : 1, DO_LOADERS = LSU ? 64 : 1;  // threads arriving on q_full / do_full
 
   if (warp == PROD_WARP && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -146,11 +182,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (warp == MMA_WARP && lane == 0) {
     mbar_init(kv_full, 1);
     for (int i = 0; i < C::QS; ++i) {
-      mbar_init(q_full + i, 1);
+      mbar_init(q_full + i, Q_LOADERS);
       mbar_init(q_empty + i, 1);
       mbar_init(stat_full + i, 32);
     }
-    mbar_init(do_full, 1);
+    mbar_init(do_full, DO_LOADERS);
     mbar_init(do_empty, 1);
     mbar_init(s_full, 1);
     mbar_init(p_ready, 256);
@@ -173,9 +209,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   if (warp >= PROD_WARP) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-    if (warp == PROD_WARP) {
-      // ================================ producer: TMA + lse/delta staging =========================
-      if (lane == 0) {
+    if (warp != MMA_WARP && (LSU || warp == PROD_WARP)) {
+      // ================================ producer: K/V by TMA, Q/dO tiles, lse/delta staging ========
+      const int lw = (warp == PROD_WARP) ? 0 : warp - 13;  // loader warps 12, 14, 15 -> 0, 1, 2
+      const int lt = lw * 32 + lane;
+      if (lt == 0) {
         mbar_arrive_expect_tx(kv_full, 2 * C::TILE);
 #pragma unroll
         for (int c = 0; c < C::KCH; ++c) {
@@ -185,41 +223,66 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       const float* lse_row = p.lse + bq * p.lse_sb + h * p.lse_sh + q_base;
       const float* dl_row = p.delta + bq * p.lse_sb + h * p.lse_sh + q_base;
-      for (int i = 0; i < n_q; ++i) {
-        const int s = i % C::QS;
-        mbar_wait(q_empty + s, ((i / C::QS) & 1) ^ 1, BT_Q_EMPTY);
-        if (lane == 0) {
-          trace_mark(p.trace, 3, i, 0);
-          mbar_arrive_expect_tx(q_full + s, C::TILE);
+      const __nv_bfloat16* q_g = p.q + bq * p.q_sb + h * p.q_sh;
+      const __nv_bfloat16* do_g = p.dout + bq * p.do_sb + h * p.do_sh;
+      if (!LSU || lw == 0) {
+        // ---- Q ring + lse/delta (warp 12) --------------------------------------------------------
+        for (int i = 0; i < n_q; ++i) {
+          const int s = i % C::QS;
+          mbar_wait(q_empty + s, ((i / C::QS) & 1) ^ 1, BT_Q_EMPTY);
+          if (lt == 0) trace_mark(p.trace, 3, i, 0);
+          if (LSU) {
+            lsu_load_tile<D>(smem + C::OFF_Q + s * C::TILE, q_g, p.q_sl, q_base + i * 128, Lq_total, lane, Q_LOADERS);
+            cp_async_commit();
+          } else if (lane == 0) {
+            mbar_arrive_expect_tx(q_full + s, C::TILE);
 #pragma unroll
-          for (int c = 0; c < C::KCH; ++c)
-            tma_load_4d(smem + C::OFF_Q + s * C::TILE + c * C::CHUNK, &tm_q, q_full + s, c * 64, q_base + i * 128, h, bq);
-        }
-        // lse (pre-multiplied by log2 e) and delta for the 128 rows of this Q tile; rows past q_len get lse = +inf
-        // so that P == 0 there.
-        float* st = reinterpret_cast<float*>(smem + C::OFF_STAT + s * 1024);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int row = r * 32 + lane;
-          const int qrow = i * 128 + row;
-          float l = CUDART_INF_F, d = 0.f;
-          if (qrow < q_len) {
-            l = lse_row[qrow] * 1.4426950408889634f;
-            d = dl_row[qrow];
+            for (int c = 0; c < C::KCH; ++c)
+              tma_load_4d(smem + C::OFF_Q + s * C::TILE + c * C::CHUNK, &tm_q, q_full + s, c * 64, q_base + i * 128, h, bq);
           }
-          st[row] = l;
-          st[128 + row] = d;
-        }
-        mbar_arrive(stat_full + s);
-        if (lane == 0) {
-          mbar_wait(do_empty, (i & 1) ^ 1, BT_DO_EMPTY);
-          trace_mark(p.trace, 3, i, 1);
-          mbar_arrive_expect_tx(do_full, C::TILE);
+          // lse (pre-multiplied by log2 e) and delta for the 128 rows of this Q tile; rows past q_len get lse = +inf
+          // so that P == 0 there.
+          float* st = reinterpret_cast<float*>(smem + C::OFF_STAT + s * 1024);
 #pragma unroll
-          for (int c = 0; c < C::KCH; ++c)
-            tma_load_4d(smem + C::OFF_DO + c * C::CHUNK, &tm_do, do_full, c * 64, q_base + i * 128, h, bq);
+          for (int r = 0; r < 4; ++r) {
+            const int row = r * 32 + lane;
+            const int qrow = i * 128 + row;
+            float l = CUDART_INF_F, d = 0.f;
+            if (qrow < q_len) {
+              l = lse_row[qrow] * 1.4426950408889634f;
+              d = dl_row[qrow];
+            }
+            st[row] = l;
+            st[128 + row] = d;
+          }
+          mbar_arrive(stat_full + s);
+          if (LSU) {
+            // writer-side completion: data landed (wait_group), visible to the async proxy the MMA reads through
+            cp_async_wait<0>();
+            fence_proxy_async_smem();
+            mbar_arrive(q_full + s);
+          } else if (lane == 0) {
+            mbar_wait(do_empty, (i & 1) ^ 1, BT_DO_EMPTY);
+            trace_mark(p.trace, 3, i, 1);
+            mbar_arrive_expect_tx(do_full, C::TILE);
+#pragma unroll
+            for (int c = 0; c < C::KCH; ++c)
+              tma_load_4d(smem + C::OFF_DO + c * C::CHUNK, &tm_do, do_full, c * 64, q_base + i * 128, h, bq);
+          }
+          __syncwarp();
         }
-        __syncwarp();
+      } else {
+        // ---- dO tile (warps 14, 15) --------------------------------------------------------------
+        const int dt = lt - 32;
+        for (int i = 0; i < n_q; ++i) {
+          mbar_wait(do_empty, (i & 1) ^ 1, BT_DO_EMPTY);
+          if (dt == 0) trace_mark(p.trace, 3, i, 1);
+          lsu_load_tile<D>(smem + C::OFF_DO, do_g, p.do_sl, q_base + i * 128, Lq_total, dt, DO_LOADERS);
+          cp_async_commit();
+          cp_async_wait<0>();
+          fence_proxy_async_smem();
+          mbar_arrive(do_full);
+        }
       }
     } else if (warp == MMA_WARP && elect_one()) {
       // ================================ MMA issuer ===============================================
@@ -547,19 +610,19 @@ __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_b
   *reinterpret_cast<uint4*>(dq + b * sb + static_cast<int64_t>(l) * sl + h * sh + d) = w;
 }
 
-template <int D>
+template <int D, bool LSU>
 cudaError_t launch_bwd_one(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
                            const CUtensorMap& tm_do, const CUtensorMap& tm_dq, float* dq_acc, int Lq_total,
                            const AttnBwdParams& p, cudaStream_t stream) {
   using C = BwdCfg<D>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<D, LSU>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   dim3 grid((p.seq.Lk + 127) / 128, p.seq.H, p.seq.nprob);
-  attn_bwd_kernel<D><<<grid, C::THREADS, C::BYTES, stream>>>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p);
+  attn_bwd_kernel<D, LSU><<<grid, C::THREADS, C::BYTES, stream>>>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p);
   return cudaGetLastError();
 }
 
@@ -568,8 +631,16 @@ cudaError_t launch_bwd_one(const CUtensorMap& tm_q, const CUtensorMap& tm_k, con
 cudaError_t launch_attn_bwd(int D, const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
                             const CUtensorMap& tm_do, const CUtensorMap& tm_dq, float* dq_acc, int Lq_total,
                             const AttnBwdParams& p, cudaStream_t stream) {
-  if (D == 128) return launch_bwd_one<128>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream);
-  if (D == 64) return launch_bwd_one<64>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream);
+  // Default: TMA loads. VT_BWD_LSU_LOADS=1 selects the cp.async producer for A/B measurements. Measured on K1 it is
+  // 40 % SLOWER (659 vs 1076 TFLOP/s): LSU writes into shared memory starve behind the UMMA operand fetch, which
+  // saturates the 128 B/clk shared-memory port, whereas TMA writes do not.
+  static const bool tma_loads = [] { const char* e = getenv("VT_BWD_LSU_LOADS"); return !(e != nullptr && e[0] == '1'); }();
+  if (D == 128)
+    return tma_loads ? launch_bwd_one<128, false>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream)
+                     : launch_bwd_one<128, true>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream);
+  if (D == 64)
+    return tma_loads ? launch_bwd_one<64, false>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream)
+                     : launch_bwd_one<64, true>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream);
   return cudaErrorInvalidValue;
 }
 

@@ -40,6 +40,10 @@ struct AttnFwdParams {
 struct AttnBwdParams {
   AttnSeq seq;
   long long* trace;
+  const __nv_bfloat16* q;     // for the cp.async (LSU) tile loads of the backward producer
+  const __nv_bfloat16* dout;
+  int64_t q_sb, q_sl, q_sh;
+  int64_t do_sb, do_sl, do_sh;
   const float* lse;          // from forward
   const float* delta;        // rowsum(dO * O), same layout as lse
   int64_t lse_sb, lse_sh;

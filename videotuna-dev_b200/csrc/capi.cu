@@ -324,6 +324,10 @@ int vt_attn_bwd(const void* dout, const void* q, const void* k, const void* v, c
   p.seq.Lk = num_segments > 0 ? max_seqlen_k : Lk;
   p.seq.H = H;
   p.seq.nprob = num_segments > 0 ? num_segments : B;
+  p.q = static_cast<const __nv_bfloat16*>(q);
+  p.dout = static_cast<const __nv_bfloat16*>(dout);
+  p.q_sb = q_strides[0]; p.q_sl = q_strides[1]; p.q_sh = q_strides[2];
+  p.do_sb = do_strides[0]; p.do_sl = do_strides[1]; p.do_sh = do_strides[2];
   p.lse = lse;
   p.delta = delta;
   p.lse_sb = static_cast<int64_t>(H) * Lq;

@@ -39,6 +39,12 @@ int vt_init(int device);
  * {call-site tag, blockIdx.x, blockIdx.y | blockIdx.z<<16, threadIdx.x}; all zero if none fired. */
 int vt_debug_watchdog(uint32_t out[4]);
 
+/* Strided host<->device copy on `stream` (cudaMemcpy2DAsync): `rows` rows of `width_bytes`, pitches in bytes. Used by
+ * the host-buffer attention entry point to move one head group of a pinned (B, L, H, D) tensor per DMA. The host
+ * buffer must be pinned for the copy to be asynchronous. to_device: 1 = host->device, 0 = device->host. */
+int vt_memcpy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t rows,
+                      int to_device, void* stream);
+
 /* Debug: when device_buf is non-NULL, CTA (0,0,0) of the attention kernels stores clock64() timestamps of its first 64
  * loop iterations into it (int64[4 roles][64 iterations][8 slots]; tools/trace_timeline.py decodes them). NULL = off. */
 int vt_debug_set_trace(long long* device_buf);

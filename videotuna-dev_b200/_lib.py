@@ -20,6 +20,7 @@ _SIGS = {
     "vt_last_error": [C.c_char_p, C.c_size_t],
     "vt_init": [C.c_int],
     "vt_debug_watchdog": [C.POINTER(C.c_uint32)],
+    "vt_memcpy2d_async": [vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.c_size_t, C.c_int, vp],
     "vt_debug_set_trace": [vp],
     "vt_profile_enable": [C.c_int],
     "vt_profile_read": [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)],

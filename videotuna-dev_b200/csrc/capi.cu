@@ -193,6 +193,16 @@ int vt_profile_read(int kernel_id, double* total_ms, int64_t* launches) {
   return 0;
 }
 
+int vt_memcpy2d_async(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width_bytes, size_t rows,
+                      int to_device, void* stream) {
+  VT_REQUIRE(dst != nullptr && src != nullptr, VT_ERR_NULL, "vt_memcpy2d_async: NULL pointer");
+  VT_REQUIRE(width_bytes <= dpitch && width_bytes <= spitch, VT_ERR_SHAPE, "vt_memcpy2d_async: width exceeds pitch");
+  VT_CHECK_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, rows,
+                                  to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                                  static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 int vt_debug_set_trace(long long* device_buf) {
   debug_set_trace(device_buf);
   return 0;

@@ -29,13 +29,15 @@ torch.cuda.synchronize()
 L.call("vt_debug_set_trace", None)
 t = buf.cpu().view(4, 64, 8)
 t0 = int(t[t > 0].min())
-names = {0: "compute", 1: "mma", 2: "drain", 3: "producer"}
+names = ({0: "compute", 1: "mma", 2: "drain", 3: "producer"} if which == "bwd" else
+         {0: "softmax0", 1: "mma", 2: "softmax1", 3: "-"})
 for it in range(20, 28):
     print(f"--- iteration {it}")
     for role in range(4):
         row = [int(x) - t0 if x > 0 else None for x in t[role, it]]
         if any(x is not None for x in row):
             print(f"  {names[role]:9s}", " ".join(f"{x:7d}" if x is not None else "      -" for x in row))
-per = [int(t[0, i + 1, 6] - t[0, i, 6]) for i in range(16, 40) if t[0, i + 1, 6] > 0 and t[0, i, 6] > 0]
+slot = 6 if which == "bwd" else 5
+per = [int(t[0, i + 1, slot] - t[0, i, slot]) for i in range(16, 40) if t[0, i + 1, slot] > 0 and t[0, i, slot] > 0]
 if per:
-    print("period (role 0 slot 6):", per)
+    print(f"period (role 0 slot {slot}):", per)

@@ -6,7 +6,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200vt.so")
+# B200VT_LIB selects another build of the same library (A/B kernel experiments); the default is the in-tree build.
+LIB_PATH = os.environ.get("B200VT_LIB") or os.path.join(_HERE, "libb200vt.so")
 
 _lib = None
 _lock = threading.Lock()

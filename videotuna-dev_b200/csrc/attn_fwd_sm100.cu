@@ -6,18 +6,25 @@
 //   wan flash_attention                  (videotuna/models/wan/wan/modules/attention.py:96-127)
 //
 // One CTA owns NQ (1 or 2) query tiles of 128 rows for one (problem, head) and streams 128-key tiles:
-//   warp 4*NQ     : TMA producer (Q once; K/V ring, 128B-swizzled boxes of 128 rows x 64 elems)
-//   warp 4*NQ + 1 : tcgen05.mma issuer (single thread).  S_t = Q_t K^T (SS), O_t += P_t V (A = P from TMEM)
-//   warps [0,4*NQ): softmax warpgroups, one thread per query row: tcgen05.ld S -> online softmax (exp2,
-//                   lazy rescale) -> bf16 P written back over S with tcgen05.st -> mbarrier to the issuer.
-// With NQ == 2 the two tiles ping-pong: while warpgroup 0 does softmax on S_0 the tensor core runs
-// P_1 V and Q_1 K^T, so MMA and MUFU work overlap.
+//   warp 8*NQ     : TMA producer (Q once; K/V ring, 128B-swizzled boxes of 128 rows x 64 elems)
+//   warp 8*NQ + 1 : tcgen05.mma issuer (single thread).  S_t = Q_t K^T (SS), O_t += P_t V (A = P from TMEM)
+//   warps [0,8*NQ): softmax, TWO threads per query row (two warpgroups per tile, each owning 64 of the 128 key
+//                   columns): tcgen05.ld S -> row max exchanged through shared memory -> online softmax (exp2 on packed
+//                   f32x2 math, part of it on the FMA pipe, lazy rescale) -> bf16 P written back over S -> mbarrier.
+//                   Halving the per-thread work halves the softmax latency, which — not MUFU or MMA throughput —
+//                   bounded the kernel: the per-tile chain softmax -> PV -> QK -> softmax was 1850 + 1024 + ~200 cycles.
+// With NQ == 2 the two tiles ping-pong: while one tile's warpgroups do softmax the tensor core runs the other tile's
+// P V and Q K^T, so MMA and MUFU work overlap.
 // TMEM columns: S_t at 128*t (P_t aliases its first 64 columns), O_t at 128*NQ + D*t.
 #include <cuda_bf16.h>
 #include <math_constants.h>
 
 #include "attn_common.h"
 #include "sm100_ptx.cuh"
+
+#ifndef VT_FWD_EMU
+#define VT_FWD_EMU 2
+#endif
 
 namespace vt {
 namespace {
@@ -29,17 +36,20 @@ struct FwdCfg {
   static constexpr int CHUNK = 128 * 128;          // bytes: 128 rows x 128 B (one swizzled box)
   static constexpr int TILE = CHUNK * KCH;         // bytes of a 128 x D bf16 tile
   static constexpr int KS = 2, VS = 2;             // K / V ring depth
+  static constexpr int EMU = VT_FWD_EMU;           // of every 8 exponential pairs, how many run on the FMA pipe
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + NQ * TILE;
   static constexpr int OFF_V = OFF_K + KS * TILE;
-  static constexpr int OFF_BAR = OFF_V + VS * TILE;
+  static constexpr int OFF_MX = OFF_V + VS * TILE;    // row-max / row-sum exchange: float [2 parity][NQ][2 halves][128]
+  static constexpr int OFF_BAR = OFF_MX + 2 * NQ * 2 * 128 * 4;
   static constexpr int NBAR = 1 + 2 * KS + 2 * VS + 3 * NQ;
   static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
   static constexpr int BYTES = OFF_TMEM + 16 + 1024;  // + alignment slack
   static constexpr int TMEM_USED = NQ * (128 + D);
   static constexpr int TMEM_COLS = TMEM_USED <= 256 ? 256 : 512;
-  // NQ == 2: three full warpgroups (warps 10,11 idle) so setmaxnreg can move registers to the softmax warps.
-  static constexpr int THREADS = NQ == 2 ? 384 : 192;
+  // 8 softmax warps per tile + producer + issuer. 576 threads (NQ == 2) launch with 112 registers each, which is what
+  // the softmax threads need, so no setmaxnreg re-balancing is involved.
+  static constexpr int THREADS = (NQ * 8 + 2) * 32;
 };
 
 enum : uint32_t {
@@ -100,7 +110,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* o_full = p_full + NQ;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM);
 
-  constexpr int PROD_WARP = NQ * 4, MMA_WARP = NQ * 4 + 1;
+  constexpr int PROD_WARP = NQ * 8, MMA_WARP = NQ * 8 + 1;
 
   if (warp == PROD_WARP && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -111,7 +121,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_init(q_full, 1);
     for (int i = 0; i < C::KS; ++i) { mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1); }
     for (int i = 0; i < C::VS; ++i) { mbar_init(v_full + i, 1); mbar_init(v_empty + i, 1); }
-    for (int i = 0; i < NQ; ++i) { mbar_init(s_full + i, 1); mbar_init(p_full + i, 128); mbar_init(o_full + i, 1); }
+    for (int i = 0; i < NQ; ++i) { mbar_init(s_full + i, 1); mbar_init(p_full + i, 256); mbar_init(o_full + i, 1); }
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -126,7 +136,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   // NQ == 2: 384 threads x 168 regs at launch; the service warpgroup (warps 8..11) gives registers to the two
   // softmax warpgroups (setmaxnreg is warpgroup-wide, hence the idle warps 10,11 take the first branch too).
   if (warp >= PROD_WARP) {
-    if constexpr (NQ == 2) asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     if (warp == PROD_WARP && lane == 0) {
     // ================================ TMA producer ============================================
     {
@@ -199,8 +208,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         const int ksn = (j + 1) % C::KS;
 #pragma unroll
         for (int t = 0; t < NQ; ++t) {
+          trace_mark(p.trace, 1, j, t * 3);
           mbar_wait(p_full + t, j & 1, TAG_P_FULL);
           tc_fence_after();
+          trace_mark(p.trace, 1, j, t * 3 + 1);
           issue_pv(t, vs, j > 0);
           if (t == NQ - 1) tc_commit(v_empty + vs);
           if (has_next) {
@@ -214,99 +225,131 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           } else {
             tc_commit(o_full + t);
           }
+          trace_mark(p.trace, 1, j, t * 3 + 2);
         }
       }
     }
     }
   } else {
     // ================================ softmax warpgroups ======================================
-    if constexpr (NQ == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
-    const int t = warp >> 2;
+    const int t = warp >> 3;         // query tile
+    const int hf = (warp >> 2) & 1;  // which 64 of the 128 key columns (and which half of the O columns)
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
-    const uint32_t s_addr = tmem_base + lane_addr + t * 128;
-    const uint32_t o_addr = tmem_base + lane_addr + NQ * 128 + t * D;
+    const uint32_t s_addr = tmem_base + lane_addr + t * 128 + hf * 64;   // this thread's 64 S columns
+    const uint32_t p_addr = tmem_base + lane_addr + t * 128 + hf * 32;   // its 32 packed-bf16 P columns
+    constexpr int OH = D / 2;                                            // O columns per thread
+    const uint32_t o_addr = tmem_base + lane_addr + NQ * 128 + t * D + hf * OH;
     const float sl2 = p.scale_log2;
+    float* mx = reinterpret_cast<float*>(smem + C::OFF_MX);  // [parity][t][half][row]
+    const uint32_t pair_bar = 1 + t;                         // named barrier of this tile's 256 threads
 
+    const bool tr = row == 0 && hf == 0;
+    const int trole = t == 0 ? 0 : 2;
     float m = -CUDART_INF_F, l = 0.f;
     for (int j = 0; j < n_kv; ++j) {
+      if (tr) trace_mark(p.trace, trole, j, 0);
       mbar_wait(s_full + t, j & 1, TAG_S_FULL);
       tc_fence_after();
-      uint32_t su[128];
+      if (tr) trace_mark(p.trace, trole, j, 1);
+      uint32_t su[64];
       tmem_ld_x32(s_addr + 0, su + 0);
       tmem_ld_x32(s_addr + 32, su + 32);
-      tmem_ld_x32(s_addr + 64, su + 64);
-      tmem_ld_x32(s_addr + 96, su + 96);
       tc_wait_ld();
       float* s = reinterpret_cast<float*>(su);
       if (j == n_kv - 1) {
-        const int valid = k_len - j * 128;
-        if (valid < 128) {
+        const int valid = k_len - j * 128 - hf * 64;
+        if (valid < 64) {
 #pragma unroll
-          for (int c = 0; c < 128; ++c)
+          for (int c = 0; c < 64; ++c)
             if (c >= valid) s[c] = -CUDART_INF_F;
         }
       }
       float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
 #pragma unroll
-      for (int c = 4; c < 128; c += 4) {
+      for (int c = 4; c < 64; c += 4) {
         mx0 = fmaxf(mx0, s[c]);
         mx1 = fmaxf(mx1, s[c + 1]);
         mx2 = fmaxf(mx2, s[c + 2]);
         mx3 = fmaxf(mx3, s[c + 3]);
       }
-      const float m_new = fmaxf(m, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)));
+      // exchange the half-row maxima. The barrier also orders every S read of this tile (tcgen05.wait::ld above)
+      // before any P write below: the partner's P columns overlay S columns this thread has just read.
+      float* slot = mx + (((j & 1) * NQ + t) * 2) * 128;
+      slot[hf * 128 + row] = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      named_bar_sync(pair_bar, 256);
+      const float m_new = fmaxf(m, fmaxf(slot[row], slot[128 + row]));
+      if (tr) trace_mark(p.trace, trole, j, 2);
       if (j == 0) {
         m = m_new;
       } else {
-        // Lazy rescale: keep the stale max while it is within 2^8 of the new one.
+        // Lazy rescale: keep the stale max while it is within 2^8 of the new one. Both threads of a row see the same
+        // m and m_new, so they take the same decision and each rescales its half of the O columns.
         const bool need = (m_new - m) * sl2 > 8.f;
         if (__any_sync(0xffffffffu, need)) {
           const float f = need ? ex2_approx((m - m_new) * sl2) : 1.f;
           if (need) m = m_new;
           l *= f;
-#pragma unroll
-          for (int c0 = 0; c0 < D; c0 += 32) {
-            uint32_t ou[32];
-            tmem_ld_x32(o_addr + c0, ou);
+          // rare path: 8 columns at a time keeps its register footprint (and with it the hot path's) small
+#pragma unroll 1
+          for (int c0 = 0; c0 < OH; c0 += 8) {
+            uint32_t ou[8];
+            tmem_ld_x8(o_addr + c0, ou);
             tc_wait_ld();
 #pragma unroll
-            for (int c = 0; c < 32; ++c) ou[c] = __float_as_uint(__uint_as_float(ou[c]) * f);
-            tmem_st_x32(o_addr + c0, ou);
+            for (int c = 0; c < 8; ++c) ou[c] = __float_as_uint(__uint_as_float(ou[c]) * f);
+            tmem_st_x8(o_addr + c0, ou);
           }
         }
       }
+      if (tr) trace_mark(p.trace, trole, j, 3);
+      // p = 2^(s * scale_log2 - m * scale_log2) on packed pairs: one FFMA2 for the argument, one FADD2 for the row sum.
+      // EMU of every 8 pairs take the FMA-pipe polynomial instead of MUFU.EX2 (see ex2_poly2).
       const float msc = m * sl2;
-      float l0 = 0.f, l1 = 0.f;
+      const float2 sc2 = make_float2(sl2, sl2), nm2 = make_float2(-msc, -msc);
+      float2 lacc = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = 0; c0 < 64; c0 += 32) {
         uint32_t pk[16];
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
-          const float p0 = ex2_approx(fmaf(s[c0 + c], sl2, -msc));
-          const float p1 = ex2_approx(fmaf(s[c0 + c + 1], sl2, -msc));
-          l0 += p0;
-          l1 += p1;
-          pk[c >> 1] = pack_bf16x2(p0, p1);
+          const float2 x = __ffma2_rn(make_float2(s[c0 + c], s[c0 + c + 1]), sc2, nm2);
+          float2 pv;
+          if ((((c0 + c) >> 1) & 7) < C::EMU) {
+            pv = ex2_poly2(x);
+          } else {
+            pv.x = ex2_approx(x.x);
+            pv.y = ex2_approx(x.y);
+          }
+          lacc = __fadd2_rn(lacc, pv);
+          pk[c >> 1] = pack_bf16x2(pv.x, pv.y);
         }
-        tmem_st_x16(s_addr + (c0 >> 1), pk);
+        tmem_st_x16(p_addr + (c0 >> 1), pk);
       }
-      l += l0 + l1;
+      l += lacc.x + lacc.y;
+      if (tr) trace_mark(p.trace, trole, j, 4);
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(p_full + t);
+      if (tr) trace_mark(p.trace, trole, j, 5);
     }
 
-    // ---- epilogue: O / l -> bf16 -> global; lse ------------------------------------------------
+    // ---- epilogue: total row sum, O / l -> bf16 -> global; lse ---------------------------------
+    {
+      float* slot = mx + (((n_kv & 1) * NQ + t) * 2) * 128;  // the parity the last iteration did not use
+      slot[hf * 128 + row] = l;
+      named_bar_sync(pair_bar, 256);
+      l = slot[row] + slot[128 + row];
+    }
     mbar_wait(o_full + t, 0, TAG_O_FULL);
     tc_fence_after();
     const float inv = 1.f / l;
     const int row_g = q0 + t * 128 + row;
     const bool valid_row = row_g < q_len;
-    __nv_bfloat16* optr = p.o + bq * p.o_sb + static_cast<int64_t>(q_base + row_g) * p.o_sl + h * p.o_sh;
+    __nv_bfloat16* optr = p.o + bq * p.o_sb + static_cast<int64_t>(q_base + row_g) * p.o_sl + h * p.o_sh + hf * OH;
 #pragma unroll
-    for (int c0 = 0; c0 < D; c0 += 32) {
+    for (int c0 = 0; c0 < OH; c0 += 32) {
       uint32_t ou[32];
       tmem_ld_x32(o_addr + c0, ou);
       tc_wait_ld();
@@ -322,7 +365,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
       }
     }
-    if (valid_row) p.lse[bq * p.lse_sb + h * p.lse_sh + q_base + row_g] = m * p.scale + __logf(l);
+    if (valid_row && hf == 0) p.lse[bq * p.lse_sb + h * p.lse_sh + q_base + row_g] = m * p.scale + __logf(l);
   }
 
   // ---- teardown ------------------------------------------------------------------------------------

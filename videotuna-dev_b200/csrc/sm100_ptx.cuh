@@ -269,6 +269,25 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x for a pair of values on the FMA pipe (no MUFU): Cody-Waite split x = n + f with n = round(x), f in [-0.5, 0.5],
+// a degree-3 minimax polynomial for 2^f (max relative error 7.5e-5, far below bf16's 3.9e-3) and n added into the
+// exponent field. Packed f32x2 arithmetic (FADD2 / FFMA2, sm_100): 6 packed ops + 2 clamps + 2 shift-adds per pair.
+// x is clamped at -125 (result ~2e-38), so -inf (masked keys) is safe. The softmax offloads a fraction of its
+// exponentials here because MUFU.EX2 (16/clk/SM) is as busy as the tensor pipe at head dim 128.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 r = __fadd2_rn(x, make_float2(12582912.f, 12582912.f));      // 1.5 * 2^23: integer part lands in the mantissa
+  const float2 n = __fadd2_rn(r, make_float2(-12582912.f, -12582912.f));
+  const float2 f = __ffma2_rn(n, make_float2(-1.f, -1.f), x);
+  float2 p = __ffma2_rn(f, make_float2(0.0551716648f, 0.0551716648f), make_float2(0.2426111251f, 0.2426111251f));
+  p = __ffma2_rn(p, f, make_float2(0.6932609677f, 0.6932609677f));
+  p = __ffma2_rn(p, f, make_float2(0.9999280572f, 0.9999280572f));
+  float2 y;
+  y.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(r.x) << 23));
+  y.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(r.y) << 23));
+  return y;
+}
 // pack two floats into bf16x2: low 16 bits = lo, high 16 bits = hi
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;

@@ -16,6 +16,7 @@
 // With NQ == 2 the two tiles ping-pong: while one tile's warpgroups do softmax the tensor core runs the other tile's
 // P V and Q K^T, so MMA and MUFU work overlap.
 // TMEM columns: S_t at 128*t (P_t aliases its first 64 columns), O_t at 128*NQ + D*t.
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <math_constants.h>
 
@@ -374,6 +375,326 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (warp == 0) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+// =====================================================================================================================
+// attn_fwd_db_kernel<D>: ONE 128-row query tile per CTA with S double-buffered in TMEM.
+//
+// In the ping-pong kernel above bf16 P overlays its own S tile, so S_t(j+1) = Q_t K(j+1)^T cannot be issued before
+// O_t += P_t(j) V(j) has consumed P: each tile runs the serial chain softmax -> PV -> QK -> softmax (measured
+// ~1850 + 1024 + ~200 cycles per 128 keys for 2 x 1024 cycles of MMA, i.e. 66 % tensor-active). Here TMEM holds
+// S[0] | S[1] | O (384 of 512 columns): QK(j+2) is issued right behind PV(j) into the buffer PV(j) frees, so S(j+1) is
+// always ready when softmax(j) ends and the softmax warps never wait for the tensor pipe; the kernel is bound by the
+// softmax throughput of one tile (two threads per row, packed f32x2 math, part of exp2 on the FMA pipe).
+// Warps 0-7 softmax (half = key columns [64*hf, 64*hf+64)), warp 8 TMA producer (K ring of 3, V ring of 2), warp 9
+// issuer. O is rescaled by the softmax threads only when the row max grew by > 2^8 (lazy), after waiting for PV(j-1).
+template <int D>
+struct FwdDbCfg {
+  static constexpr int KCH = D / 64;
+  static constexpr int CHUNK = 128 * 128;
+  static constexpr int TILE = CHUNK * KCH;
+  static constexpr int KS = 3, VS = 2;
+  static constexpr int EMU = VT_FWD_EMU;
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + TILE;
+  static constexpr int OFF_V = OFF_K + KS * TILE;
+  static constexpr int OFF_MX = OFF_V + VS * TILE;  // float [2 parity][2 halves][128]
+  static constexpr int OFF_BAR = OFF_MX + 2 * 2 * 128 * 4;
+  static constexpr int NBAR = 1 + 2 * KS + 2 * VS + 2 + 3;
+  static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+  static constexpr int BYTES = OFF_TMEM + 16;
+  static constexpr int THREADS = 10 * 32;
+  static constexpr uint32_t T_S = 0, T_O = 256;
+};
+
+enum : uint32_t { TAG_PV_DONE = 0x110, TAG_FWD_ALIGN };
+
+template <int D>
+__global__ void __launch_bounds__(FwdDbCfg<D>::THREADS, 1)
+attn_fwd_db_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                   const __grid_constant__ CUtensorMap tm_v, const AttnFwdParams p) {
+  using C = FwdDbCfg<D>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) watchdog_trap(TAG_FWD_ALIGN);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  const int prob = blockIdx.z, h = blockIdx.y;
+  int q_base = 0, q_len = p.seq.Lq, bq = prob;
+  int k_base = 0, k_len = p.seq.Lk, bk = prob;
+  if (p.seq.cu_q != nullptr) {
+    q_base = p.seq.cu_q[prob];
+    q_len = p.seq.cu_q[prob + 1] - q_base;
+    bq = 0;
+  }
+  if (p.seq.cu_k != nullptr) {
+    k_base = p.seq.cu_k[prob];
+    k_len = p.seq.cu_k[prob + 1] - k_base;
+    bk = 0;
+  } else if (p.seq.seqlens_k != nullptr) {
+    k_len = min(max(p.seq.seqlens_k[prob], 0), p.seq.Lk);
+  }
+  const int q0 = blockIdx.x * 128;
+  if (q0 >= q_len) return;  // CTA-uniform
+  const int n_kv = (k_len + 127) >> 7;
+
+  if (n_kv == 0) {  // no keys: softmax over the empty set -> zeros, lse = -inf (matches flash-attn)
+    for (int r = threadIdx.x; r < 128; r += blockDim.x) {
+      const int row = q0 + r;
+      if (row < q_len) {
+        __nv_bfloat16* optr = p.o + bq * p.o_sb + static_cast<int64_t>(q_base + row) * p.o_sl + h * p.o_sh;
+        for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(optr + c) = make_uint4(0, 0, 0, 0);
+        p.lse[bq * p.lse_sb + h * p.lse_sh + q_base + row] = -CUDART_INF_F;
+      }
+    }
+    return;
+  }
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = q_full + 1;
+  uint64_t* k_empty = k_full + C::KS;
+  uint64_t* v_full = k_empty + C::KS;
+  uint64_t* v_empty = v_full + C::VS;
+  uint64_t* s_full = v_empty + C::VS;  // [2]
+  uint64_t* p_full = s_full + 2;
+  uint64_t* pv_done = p_full + 1;
+  uint64_t* o_full = pv_done + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM);
+  constexpr int PROD_WARP = 8, MMA_WARP = 9;
+
+  if (warp == PROD_WARP && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+  }
+  if (warp == MMA_WARP && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < C::KS; ++i) { mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1); }
+    for (int i = 0; i < C::VS; ++i) { mbar_init(v_full + i, 1); mbar_init(v_empty + i, 1); }
+    mbar_init(s_full + 0, 1);
+    mbar_init(s_full + 1, 1);
+    mbar_init(p_full, 256);
+    mbar_init(pv_done, 1);
+    mbar_init(o_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == PROD_WARP) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, C::TILE);
+#pragma unroll
+      for (int c = 0; c < C::KCH; ++c)
+        tma_load_4d(smem + C::OFF_Q + c * C::CHUNK, &tm_q, q_full, c * 64, q_base + q0, h, bq);
+      for (int j = 0; j < n_kv; ++j) {
+        const int ks = j % C::KS, vs = j % C::VS;
+        mbar_wait(k_empty + ks, ((j / C::KS) & 1) ^ 1, TAG_K_EMPTY);
+        mbar_arrive_expect_tx(k_full + ks, C::TILE);
+#pragma unroll
+        for (int c = 0; c < C::KCH; ++c)
+          tma_load_4d(smem + C::OFF_K + ks * C::TILE + c * C::CHUNK, &tm_k, k_full + ks, c * 64, k_base + j * 128, h, bk);
+        mbar_wait(v_empty + vs, ((j / C::VS) & 1) ^ 1, TAG_V_EMPTY);
+        mbar_arrive_expect_tx(v_full + vs, C::TILE);
+#pragma unroll
+        for (int c = 0; c < C::KCH; ++c)
+          tma_load_4d(smem + C::OFF_V + vs * C::TILE + c * C::CHUNK, &tm_v, v_full + vs, c * 64, k_base + j * 128, h, bk);
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    if (elect_one()) {
+      constexpr uint32_t IDESC_QK = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, D, 0, 1);
+      const uint32_t sb16 = smem_u32(smem) >> 4;
+      const uint32_t q_smem = sb16 + (C::OFF_Q >> 4), k_smem = sb16 + (C::OFF_K >> 4), v_smem = sb16 + (C::OFF_V >> 4);
+      constexpr uint32_t CH16 = C::CHUNK >> 4, TILE16 = C::TILE >> 4;
+      auto issue_qk = [&](int jj) {  // S[jj & 1] = Q K(jj)^T
+        const int ks = jj % C::KS;
+        mbar_wait(k_full + ks, (jj / C::KS) & 1, TAG_K_FULL);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < C::KCH; ++c)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_ss(tmem_base + C::T_S + (jj & 1) * 128, umma_desc_sw128_a16(q_smem + c * CH16 + kk * 2, 16, 1024),
+                    umma_desc_sw128_a16(k_smem + ks * TILE16 + c * CH16 + kk * 2, 16, 1024), IDESC_QK, (c | kk) != 0);
+        tc_commit(s_full + (jj & 1));
+        tc_commit(k_empty + ks);
+      };
+      mbar_wait(q_full, 0, TAG_Q_FULL);
+      issue_qk(0);
+      if (n_kv > 1) issue_qk(1);
+      for (int j = 0; j < n_kv; ++j) {
+        const int vs = j % C::VS;
+        mbar_wait(v_full + vs, (j / C::VS) & 1, TAG_V_FULL);
+        trace_mark(p.trace, 1, j, 0);
+        mbar_wait(p_full, j & 1, TAG_P_FULL);
+        tc_fence_after();
+        trace_mark(p.trace, 1, j, 1);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // 16 keys per MMA; P(j) sits in the first 64 columns of S[j & 1]
+          umma_ts(tmem_base + C::T_O, tmem_base + C::T_S + (j & 1) * 128 + kk * 8,
+                  umma_desc_sw128_a16(v_smem + vs * TILE16 + kk * 128, C::CHUNK, 1024), IDESC_PV, (j > 0) || kk != 0);
+        tc_commit(v_empty + vs);
+        tc_commit(pv_done);
+        if (j + 2 < n_kv) issue_qk(j + 2);
+        if (j == n_kv - 1) tc_commit(o_full);
+        trace_mark(p.trace, 1, j, 2);
+      }
+    }
+  } else {
+    // ================================ softmax: two threads per query row ==========================
+    const int hf = warp >> 2;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    constexpr int OH = D / 2;
+    const uint32_t o_addr = tmem_base + lane_addr + C::T_O + hf * OH;
+    const float sl2 = p.scale_log2;
+    float* mx = reinterpret_cast<float*>(smem + C::OFF_MX);
+    const bool tr = row == 0 && hf == 0;
+    float m = -CUDART_INF_F, l = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t s_addr = tmem_base + lane_addr + C::T_S + (j & 1) * 128 + hf * 64;
+      const uint32_t p_addr = tmem_base + lane_addr + C::T_S + (j & 1) * 128 + hf * 32;
+      if (tr) trace_mark(p.trace, 0, j, 0);
+      mbar_wait(s_full + (j & 1), (j >> 1) & 1, TAG_S_FULL);
+      tc_fence_after();
+      if (tr) trace_mark(p.trace, 0, j, 1);
+      uint32_t su[64];
+      tmem_ld_x32(s_addr + 0, su + 0);
+      tmem_ld_x32(s_addr + 32, su + 32);
+      tc_wait_ld();
+      float* s = reinterpret_cast<float*>(su);
+      if (j == n_kv - 1) {
+        const int valid = k_len - j * 128 - hf * 64;
+        if (valid < 64) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c)
+            if (c >= valid) s[c] = -CUDART_INF_F;
+        }
+      }
+      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+      for (int c = 4; c < 64; c += 4) {
+        mx0 = fmaxf(mx0, s[c]);
+        mx1 = fmaxf(mx1, s[c + 1]);
+        mx2 = fmaxf(mx2, s[c + 2]);
+        mx3 = fmaxf(mx3, s[c + 3]);
+      }
+      // exchange the half-row maxima; the barrier also orders this tile's S reads before the partner's P writes
+      float* slot = mx + (j & 1) * 256;
+      slot[hf * 128 + row] = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      named_bar_sync(1, 256);
+      const float m_new = fmaxf(m, fmaxf(slot[row], slot[128 + row]));
+      if (tr) trace_mark(p.trace, 0, j, 2);
+      if (j == 0) {
+        m = m_new;
+      } else {
+        const bool need = (m_new - m) * sl2 > 8.f;  // lazy rescale, same decision in both threads of a row
+        if (__any_sync(0xffffffffu, need)) {
+          const float f = need ? ex2_approx((m - m_new) * sl2) : 1.f;
+          if (need) m = m_new;
+          l *= f;
+          mbar_wait(pv_done, (j - 1) & 1, TAG_PV_DONE);  // O += P(j-1) V(j-1) has landed
+          tc_fence_after();
+#pragma unroll 1
+          for (int c0 = 0; c0 < OH; c0 += 8) {
+            uint32_t ou[8];
+            tmem_ld_x8(o_addr + c0, ou);
+            tc_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 8; ++c) ou[c] = __float_as_uint(__uint_as_float(ou[c]) * f);
+            tmem_st_x8(o_addr + c0, ou);
+          }
+        }
+      }
+      if (tr) trace_mark(p.trace, 0, j, 3);
+      const float msc = m * sl2;
+      const float2 sc2 = make_float2(sl2, sl2), nm2 = make_float2(-msc, -msc);
+      float2 lacc = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float2 x = __ffma2_rn(make_float2(s[c0 + c], s[c0 + c + 1]), sc2, nm2);
+          float2 pv;
+          if ((((c0 + c) >> 1) & 7) < C::EMU) {
+            pv = ex2_poly2(x);
+          } else {
+            pv.x = ex2_approx(x.x);
+            pv.y = ex2_approx(x.y);
+          }
+          lacc = __fadd2_rn(lacc, pv);
+          pk[c >> 1] = pack_bf16x2(pv.x, pv.y);
+        }
+        tmem_st_x16(p_addr + (c0 >> 1), pk);
+      }
+      l += lacc.x + lacc.y;
+      if (tr) trace_mark(p.trace, 0, j, 4);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(p_full);
+      if (tr) trace_mark(p.trace, 0, j, 5);
+    }
+    {
+      float* slot = mx + (n_kv & 1) * 256;
+      slot[hf * 128 + row] = l;
+      named_bar_sync(1, 256);
+      l = slot[row] + slot[128 + row];
+    }
+    mbar_wait(o_full, 0, TAG_O_FULL);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const int row_g = q0 + row;
+    const bool valid_row = row_g < q_len;
+    __nv_bfloat16* optr = p.o + bq * p.o_sb + static_cast<int64_t>(q_base + row_g) * p.o_sl + h * p.o_sh + hf * OH;
+#pragma unroll
+    for (int c0 = 0; c0 < OH; c0 += 32) {
+      uint32_t ou[32];
+      tmem_ld_x32(o_addr + c0, ou);
+      tc_wait_ld();
+      if (valid_row) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(ou[c + 0]) * inv, __uint_as_float(ou[c + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(ou[c + 2]) * inv, __uint_as_float(ou[c + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(ou[c + 4]) * inv, __uint_as_float(ou[c + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(ou[c + 6]) * inv, __uint_as_float(ou[c + 7]) * inv);
+          *reinterpret_cast<uint4*>(optr + c0 + c) = w;
+        }
+      }
+    }
+    if (valid_row && hf == 0) p.lse[bq * p.lse_sb + h * p.lse_sh + q_base + row_g] = m * p.scale + __logf(l);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+template <int D>
+cudaError_t launch_db(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v, const AttnFwdParams& p,
+                      cudaStream_t stream) {
+  using C = FwdDbCfg<D>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_db_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((p.seq.Lq + 127) / 128, p.seq.H, p.seq.nprob);
+  attn_fwd_db_kernel<D><<<grid, C::THREADS, C::BYTES, stream>>>(tm_q, tm_k, tm_v, p);
+  return cudaGetLastError();
+}
+
 template <int D, int NQ>
 cudaError_t launch_one(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
                        const AttnFwdParams& p, cudaStream_t stream) {
@@ -393,6 +714,14 @@ cudaError_t launch_one(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const C
 
 cudaError_t launch_attn_fwd(int D, const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
                             const AttnFwdParams& p, int q_tiles_hint, cudaStream_t stream) {
+  // Default: the two-tile ping-pong kernel (K1: 1153 TFLOP/s). VT_FWD_KERNEL=db selects the one-tile kernel with S
+  // double-buffered in TMEM (K1: 1100 TFLOP/s; its softmax warps never wait for the tensor pipe, but with one tile
+  // per CTA nothing overlaps the exp phase, so it is MUFU-latency bound at ~1600 cycles per 128 keys).
+  static const bool use_db = [] { const char* e = getenv("VT_FWD_KERNEL"); return e != nullptr && e[0] == 'd'; }();
+  if (use_db && q_tiles_hint == 0) {
+    if (D == 128) return launch_db<128>(tm_q, tm_k, tm_v, p, stream);
+    if (D == 64) return launch_db<64>(tm_q, tm_k, tm_v, p, stream);
+  }
   // One query tile per CTA when the (max) query length fits a single 128-row tile; two otherwise.
   const bool single = (q_tiles_hint == 1) || (q_tiles_hint == 0 && p.seq.Lq <= 128);
   if (D == 128) return single ? launch_one<128, 1>(tm_q, tm_k, tm_v, p, stream) : launch_one<128, 2>(tm_q, tm_k, tm_v, p, stream);

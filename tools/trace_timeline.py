@@ -30,7 +30,7 @@ L.call("vt_debug_set_trace", None)
 t = buf.cpu().view(4, 64, 8)
 t0 = int(t[t > 0].min())
 names = ({0: "compute", 1: "mma", 2: "drain", 3: "producer"} if which == "bwd" else
-         {0: "softmax0", 1: "mma", 2: "softmax1", 3: "-"})
+         {0: "softmax0", 1: "mma", 2: "softmax1", 3: "mma-fine"})
 for it in range(20, 28):
     print(f"--- iteration {it}")
     for role in range(4):

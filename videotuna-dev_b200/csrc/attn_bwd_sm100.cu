@@ -36,17 +36,26 @@ struct BwdCfg {
   static constexpr int KCH = D / 64;
   static constexpr int CHUNK = 128 * 128;   // bytes of one [128 rows][64 bf16] swizzled box
   static constexpr int TILE = CHUNK * KCH;  // 128 x D bf16
-  static constexpr int QS = 2;              // Q ring depth (dO is single-buffered)
+  // Ring depths. D = 128 fills shared memory with Q x2 / dO x1. D = 64 has room for Q x3 / dO x2, which it needs: a Q
+  // slot is released by dK of iteration i - QS + 1 and its TMA load then queues behind that iteration's dQ reductions
+  // (~2000 cycles measured), so with two slots S^T of the next tile waited ~1400 cycles for Q in every iteration.
+  static constexpr int QS = (D == 64) ? 3 : 2;
+  static constexpr int DOS = (D == 64) ? 2 : 1;
+#ifdef VT_BWD_EMU
+  static constexpr int EMU = VT_BWD_EMU;    // of every 8 exponential pairs, how many run on the FMA pipe (ex2_poly2)
+#else
+  static constexpr int EMU = (D == 64) ? 3 : 2;
+#endif
   static constexpr int OFF_K = 0;
   static constexpr int OFF_V = OFF_K + TILE;
   static constexpr int OFF_Q = OFF_V + TILE;
   static constexpr int OFF_DO = OFF_Q + QS * TILE;
-  static constexpr int OFF_DS = OFF_DO + TILE;          // 128 x 128 bf16 = 2 boxes
+  static constexpr int OFF_DS = OFF_DO + DOS * TILE;    // 128 x 128 bf16 = 2 boxes
   static constexpr int DQ_CHUNK = 128 * 128;            // bytes: 128 rows x 32 fp32 columns (one swizzled box)
   static constexpr int OFF_DQS = OFF_DS + 2 * CHUNK;    // 2 staging buffers for the dQ TMA reduction
   static constexpr int OFF_STAT = OFF_DQS + 2 * DQ_CHUNK;  // QS x {lse_log2[128], delta[128]} fp32
   static constexpr int OFF_BAR = OFF_STAT + QS * 1024;
-  static constexpr int NBAR = 1 + 2 * QS + QS + 2 + 8;
+  static constexpr int NBAR = 1 + 2 * QS + QS + 2 * DOS + 8;
   static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
   // The dynamic shared memory base is 1024-byte aligned (checked at kernel entry), so no alignment slack is spent:
   // at D = 128 the layout uses 231 608 of the 232 448 bytes a CTA can have.
@@ -58,51 +67,16 @@ struct BwdCfg {
   static constexpr bool DQ_ALIASES_DP = (D == 128);
 };
 
-__device__ __forceinline__ void red_add_v4(float* addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(__uint_as_float(a)), "f"(__uint_as_float(b)),
-               "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
-               : "memory");
-}
-
 enum : uint32_t {
   BT_KV_FULL = 0x200, BT_Q_FULL, BT_Q_EMPTY, BT_STAT_FULL, BT_DO_FULL, BT_DO_EMPTY, BT_S_FULL, BT_P_READY, BT_DP_FULL,
   BT_DS_READY, BT_DQ_FULL, BT_DQ_DRAINED, BT_DKV_FULL, BT_DS_FREE, BT_ALIGN
 };
 
 
-// 16-byte asynchronous copy global -> shared through the LSU (cp.async / LDGSTS); src_bytes == 0 zero-fills.
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-// Copy rows [row0, row0 + 128) of a (rows_total, D) bf16 matrix with row stride `sl` into a 128B-swizzled tile
-// (KCH boxes of [128 rows][64 elements]; 16-byte unit u of row r lives at u ^ (r & 7)) — the layout TMA produces and
-// the UMMA descriptors expect. Rows at or past rows_total are zero-filled. `nthr` loader threads share the work.
+// Q and dO tiles arrive by TMA. A cp.async (LSU) producer was tried to leave the per-SM TMA engine to the dQ reduction
+// and measured 40 % slower on K1 (659 vs 1076 TFLOP/s): LSU writes into shared memory starve behind the UMMA operand
+// fetch, which saturates the 128 B/clk shared-memory port, whereas TMA writes do not (history: commit 782d835).
 template <int D>
-__device__ __forceinline__ void lsu_load_tile(uint8_t* tile, const __nv_bfloat16* base, int64_t sl, int row0,
-                                              int rows_total, int lt, int nthr) {
-  constexpr int UPR = D / 8;  // 16-byte units per row
-  for (int u = lt; u < 128 * UPR; u += nthr) {
-    const int row = u / UPR, c16 = u % UPR;
-    const int grow = row0 + row;
-    const bool ok = grow < rows_total;
-    const __nv_bfloat16* src = base + (ok ? static_cast<int64_t>(grow) * sl + c16 * 8 : 0);
-    uint8_t* dst = tile + (c16 >> 3) * (128 * 128) + row * 128 + (((c16 & 7) ^ (row & 7)) << 4);
-    cp_async16(dst, src, ok ? 16u : 0u);
-  }
-}
-
-// LSU = false (default): Q and dO tiles arrive by TMA. LSU = true (experiment, VT_BWD_LSU_LOADS=1): they are loaded
-// with cp.async by three loader warps to leave the per-SM TMA engine to the dQ reduction (25.6 B/clk of fp32
-// reduce-add; a 16 KB reduction takes ~830 instead of 641 cycles when the engine also carries loads —
-// tools/tma_reduce_rate.py). Measured result: slower, see launch_attn_bwd.
-template <int D, bool LSU>
 __global__ void __launch_bounds__(BwdCfg<D>::THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
@@ -156,8 +130,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* q_empty = q_full + C::QS;
   uint64_t* stat_full = q_empty + C::QS;
   uint64_t* do_full = stat_full + C::QS;
-  uint64_t* do_empty = do_full + 1;
-  uint64_t* s_full = do_empty + 1;
+  uint64_t* do_empty = do_full + C::DOS;
+  uint64_t* s_full = do_empty + C::DOS;
   uint64_t* p_ready = s_full + 1;
   uint64_t* dp_full = p_ready + 1;
   uint64_t* ds_ready = dp_full + 1;
@@ -168,9 +142,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM);
 
   constexpr int PROD_WARP = 12, MMA_WARP = 13;
-  // LSU: warp 12 loads the Q ring (two stages of slack), warps 14-15 the single-buffered dO tile; each group runs its
-  // own loop so a blocking cp.async wait of one never delays the other.
-  constexpr int Q_LOADERS = LSU ? 32 : 1, DO_LOADERS = LSU ? 64 : 1;  // threads arriving on q_full / do_full
 
   if (warp == PROD_WARP && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -182,12 +153,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   if (warp == MMA_WARP && lane == 0) {
     mbar_init(kv_full, 1);
     for (int i = 0; i < C::QS; ++i) {
-      mbar_init(q_full + i, Q_LOADERS);
+      mbar_init(q_full + i, 1);
       mbar_init(q_empty + i, 1);
       mbar_init(stat_full + i, 32);
     }
-    mbar_init(do_full, DO_LOADERS);
-    mbar_init(do_empty, 1);
+    for (int i = 0; i < C::DOS; ++i) {
+      mbar_init(do_full + i, 1);
+      mbar_init(do_empty + i, 1);
+    }
     mbar_init(s_full, 1);
     mbar_init(p_ready, 256);
     mbar_init(dp_full, 1);
@@ -209,11 +182,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
   if (warp >= PROD_WARP) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
-    if (warp != MMA_WARP && (LSU || warp == PROD_WARP)) {
-      // ================================ producer: K/V by TMA, Q/dO tiles, lse/delta staging ========
-      const int lw = (warp == PROD_WARP) ? 0 : warp - 13;  // loader warps 12, 14, 15 -> 0, 1, 2
-      const int lt = lw * 32 + lane;
-      if (lt == 0) {
+    if (warp == PROD_WARP) {
+      // ================================ producer: K/V once, Q / dO rings, lse / delta staging =======
+      if (lane == 0) {
         mbar_arrive_expect_tx(kv_full, 2 * C::TILE);
 #pragma unroll
         for (int c = 0; c < C::KCH; ++c) {
@@ -223,66 +194,41 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       }
       const float* lse_row = p.lse + bq * p.lse_sb + h * p.lse_sh + q_base;
       const float* dl_row = p.delta + bq * p.lse_sb + h * p.lse_sh + q_base;
-      const __nv_bfloat16* q_g = p.q + bq * p.q_sb + h * p.q_sh;
-      const __nv_bfloat16* do_g = p.dout + bq * p.do_sb + h * p.do_sh;
-      if (!LSU || lw == 0) {
-        // ---- Q ring + lse/delta (warp 12) --------------------------------------------------------
-        for (int i = 0; i < n_q; ++i) {
-          const int s = i % C::QS;
-          mbar_wait(q_empty + s, ((i / C::QS) & 1) ^ 1, BT_Q_EMPTY);
-          if (lt == 0) trace_mark(p.trace, 3, i, 0);
-          if (LSU) {
-            lsu_load_tile<D>(smem + C::OFF_Q + s * C::TILE, q_g, p.q_sl, q_base + i * 128, Lq_total, lane, Q_LOADERS);
-            cp_async_commit();
-          } else if (lane == 0) {
-            mbar_arrive_expect_tx(q_full + s, C::TILE);
+      for (int i = 0; i < n_q; ++i) {
+        const int s = i % C::QS, ds = i % C::DOS;
+        mbar_wait(q_empty + s, ((i / C::QS) & 1) ^ 1, BT_Q_EMPTY);
+        if (lane == 0) {
+          trace_mark(p.trace, 3, i, 0);
+          mbar_arrive_expect_tx(q_full + s, C::TILE);
 #pragma unroll
-            for (int c = 0; c < C::KCH; ++c)
-              tma_load_4d(smem + C::OFF_Q + s * C::TILE + c * C::CHUNK, &tm_q, q_full + s, c * 64, q_base + i * 128, h, bq);
-          }
-          // lse (pre-multiplied by log2 e) and delta for the 128 rows of this Q tile; rows past q_len get lse = +inf
-          // so that P == 0 there.
-          float* st = reinterpret_cast<float*>(smem + C::OFF_STAT + s * 1024);
-#pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const int row = r * 32 + lane;
-            const int qrow = i * 128 + row;
-            float l = CUDART_INF_F, d = 0.f;
-            if (qrow < q_len) {
-              l = lse_row[qrow] * 1.4426950408889634f;
-              d = dl_row[qrow];
-            }
-            st[row] = l;
-            st[128 + row] = d;
-          }
-          mbar_arrive(stat_full + s);
-          if (LSU) {
-            // writer-side completion: data landed (wait_group), visible to the async proxy the MMA reads through
-            cp_async_wait<0>();
-            fence_proxy_async_smem();
-            mbar_arrive(q_full + s);
-          } else if (lane == 0) {
-            mbar_wait(do_empty, (i & 1) ^ 1, BT_DO_EMPTY);
-            trace_mark(p.trace, 3, i, 1);
-            mbar_arrive_expect_tx(do_full, C::TILE);
-#pragma unroll
-            for (int c = 0; c < C::KCH; ++c)
-              tma_load_4d(smem + C::OFF_DO + c * C::CHUNK, &tm_do, do_full, c * 64, q_base + i * 128, h, bq);
-          }
-          __syncwarp();
+          for (int c = 0; c < C::KCH; ++c)
+            tma_load_4d(smem + C::OFF_Q + s * C::TILE + c * C::CHUNK, &tm_q, q_full + s, c * 64, q_base + i * 128, h, bq);
         }
-      } else {
-        // ---- dO tile (warps 14, 15) --------------------------------------------------------------
-        const int dt = lt - 32;
-        for (int i = 0; i < n_q; ++i) {
-          mbar_wait(do_empty, (i & 1) ^ 1, BT_DO_EMPTY);
-          if (dt == 0) trace_mark(p.trace, 3, i, 1);
-          lsu_load_tile<D>(smem + C::OFF_DO, do_g, p.do_sl, q_base + i * 128, Lq_total, dt, DO_LOADERS);
-          cp_async_commit();
-          cp_async_wait<0>();
-          fence_proxy_async_smem();
-          mbar_arrive(do_full);
+        // -lse * log2(e) and -delta for the 128 rows of this Q tile (negated so that the compute warps use them as
+        // FFMA2 / FADD2 addends); rows past q_len get -inf so that P == 0 there.
+        float* st = reinterpret_cast<float*>(smem + C::OFF_STAT + s * 1024);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int row = r * 32 + lane;
+          const int qrow = i * 128 + row;
+          float l = -CUDART_INF_F, d = 0.f;
+          if (qrow < q_len) {
+            l = lse_row[qrow] * -1.4426950408889634f;
+            d = -dl_row[qrow];
+          }
+          st[row] = l;
+          st[128 + row] = d;
         }
+        mbar_arrive(stat_full + s);
+        if (lane == 0) {
+          mbar_wait(do_empty + ds, ((i / C::DOS) & 1) ^ 1, BT_DO_EMPTY);
+          trace_mark(p.trace, 3, i, 1);
+          mbar_arrive_expect_tx(do_full + ds, C::TILE);
+#pragma unroll
+          for (int c = 0; c < C::KCH; ++c)
+            tma_load_4d(smem + C::OFF_DO + ds * C::TILE + c * C::CHUNK, &tm_do, do_full + ds, c * 64, q_base + i * 128, h, bq);
+        }
+        __syncwarp();
       }
     } else if (warp == MMA_WARP && elect_one()) {
       // ================================ MMA issuer ===============================================
@@ -310,13 +256,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_after();
       mma_kmajor_pair(tmem + C::T_S, k_s, q_s);
       tc_commit(s_full);
-      mbar_wait(do_full, 0, BT_DO_FULL);
+      mbar_wait(do_full + 0, 0, BT_DO_FULL);
       tc_fence_after();
       mma_kmajor_pair(tmem + C::T_DP, v_s, do_s);
       tc_commit(dp_full);
 
       for (int i = 0; i < n_q; ++i) {
-        const int s = i % C::QS;
+        const int s = i % C::QS, ds = i % C::DOS;
         const bool has_next = i + 1 < n_q;
         // ---- dV += P^T dO_i ----
         trace_mark(p.trace, 1, i, 0);
@@ -325,9 +271,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         trace_mark(p.trace, 1, i, 1);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)
-          umma_ts(tmem + C::T_DV, tmem + C::T_P + kk * 8, umma_desc_sw128_a16(do_s + kk * 128, C::CHUNK, 1024), IDESC_KD,
-                  (i > 0) || kk != 0);
-        tc_commit(do_empty);
+          umma_ts(tmem + C::T_DV, tmem + C::T_P + kk * 8,
+                  umma_desc_sw128_a16(do_s + ds * TILE16 + kk * 128, C::CHUNK, 1024), IDESC_KD, (i > 0) || kk != 0);
+        tc_commit(do_empty + ds);
         // ---- S^T for the next Q tile ----
         if (has_next) {
           const int sn = (i + 1) % C::QS;
@@ -363,10 +309,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             tc_fence_after();
           }
           trace_mark(p.trace, 1, i, 4);
-          mbar_wait(do_full, (i + 1) & 1, BT_DO_FULL);
+          const int dn = (i + 1) % C::DOS;
+          mbar_wait(do_full + dn, ((i + 1) / C::DOS) & 1, BT_DO_FULL);
           tc_fence_after();
           trace_mark(p.trace, 1, i, 5);
-          mma_kmajor_pair(tmem + C::T_DP, v_s, do_s);
+          mma_kmajor_pair(tmem + C::T_DP, v_s, do_s + dn * TILE16);
           tc_commit(dp_full);
         }
       }
@@ -384,12 +331,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     const uint32_t dq_addr = tmem + (static_cast<uint32_t>(quarter * 32) << 16) + C::T_DQ;
     uint8_t* stage = smem + C::OFF_DQS;
     const int sw = row & 7;
-    // The TMA engine sustains ~25.6 B/clk of fp32 reduction per SM (measured, tools/tma_reduce_rate.py) and also
-    // carries the Q/dO loads, which makes it the busiest unit of this kernel. The last LSU_CH 32-column chunks of
-    // every tile therefore bypass it: the drain threads add them with red.global.add.v4.f32 straight from registers.
+    // The TMA engine sustains ~25.6 B/clk of fp32 reduction per SM (measured, tools/tma_reduce_rate.py). Sending one of
+    // the chunks through the LSU instead (red.global.add.v4.f32 from registers) was measured 25 % slower.
     constexpr int NCH = D / 32;
-    constexpr int LSU_CH = 0;  // measured: one LSU chunk makes the drain 25% slower (red.global stalls the issuing warps)
-    constexpr int TMA_CH = NCH - LSU_CH;
     uint32_t g = 0;  // running chunk counter: staging buffer = g & 1
     for (int i = 0; i < n_q; ++i) {
       if (leader) trace_mark(p.trace, 2, i, 0);
@@ -404,7 +348,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       mbar_arrive(dq_drained);  // every TMEM read of this tile is complete: the issuer may overwrite the columns
       if (leader) trace_mark(p.trace, 2, i, 2);
 #pragma unroll
-      for (int c = 0; c < TMA_CH; ++c, ++g) {
+      for (int c = 0; c < NCH; ++c, ++g) {
         // the reduction issued two chunks ago has finished reading this staging buffer
         if (leader) tma_wait_group_read<1>();
         named_bar_sync(1, 128);
@@ -420,15 +364,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           // rows past the end of the tensor are clipped by TMA; rows of another varlen segment receive exact zeros
           tma_reduce_add_4d(&tm_dq, buf, c * 32, q_base + i * 128, h, bq);
           tma_commit_group();
-        }
-      }
-      if (LSU_CH > 0) {
-        const int qrow = i * 128 + row;
-        if (qrow < q_len) {
-          float* dst = dq_acc + ((static_cast<int64_t>(bq) * Lq_total + q_base + qrow) * p.seq.H + h) * D + TMA_CH * 32;
-#pragma unroll
-          for (int c = 0; c < LSU_CH * 32; c += 4)
-            red_add_v4(dst + c, r[TMA_CH * 32 + c], r[TMA_CH * 32 + c + 1], r[TMA_CH * 32 + c + 2], r[TMA_CH * 32 + c + 3]);
         }
       }
       if (leader) trace_mark(p.trace, 2, i, 3);
@@ -465,18 +400,40 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tmem_ld_x32(s_addr, su);
         tmem_ld_x32(s_addr + 32, su + 32);
         tc_wait_ld();
+        // P^T = 2^(S^T * scale_log2 - lse_log2) on packed pairs; EMU of every 8 pairs take the FMA-pipe polynomial
+        const float2 sc2 = make_float2(sl2, sl2);
 #pragma unroll
         for (int c = 0; c < 64; c += 4) {
-          const float4 l4 = *reinterpret_cast<const float4*>(st + c);
-          pr[c + 0] = ex2_approx(fmaf(__uint_as_float(su[c + 0]), sl2, -l4.x));
-          pr[c + 1] = ex2_approx(fmaf(__uint_as_float(su[c + 1]), sl2, -l4.y));
-          pr[c + 2] = ex2_approx(fmaf(__uint_as_float(su[c + 2]), sl2, -l4.z));
-          pr[c + 3] = ex2_approx(fmaf(__uint_as_float(su[c + 3]), sl2, -l4.w));
+          const float4 l4 = *reinterpret_cast<const float4*>(st + c);  // -lse * log2(e)
+#pragma unroll
+          for (int e = 0; e < 4; e += 2) {
+            const float2 nl = e == 0 ? make_float2(l4.x, l4.y) : make_float2(l4.z, l4.w);
+            const float2 x = __ffma2_rn(make_float2(__uint_as_float(su[c + e]), __uint_as_float(su[c + e + 1])), sc2, nl);
+            float2 pv;
+            if ((((c + e) >> 1) & 7) < C::EMU) {
+              pv = ex2_poly2(x);
+            } else {
+              pv.x = ex2_approx(x.x);
+              pv.y = ex2_approx(x.y);
+            }
+            pr[c + e] = pv.x;
+            pr[c + e + 1] = pv.y;
+          }
         }
       }
       if (!key_valid) {
 #pragma unroll
         for (int c = 0; c < 64; ++c) pr[c] = 0.f;
+      }
+      if (i == n_q - 1) {
+        // query rows past q_len (lse = -inf): MUFU gives an exact 0, the polynomial 2^-125 — force zeros so that rows
+        // of another varlen segment receive exact zeros in dQ
+        const int qv = q_len - i * 128 - half * 64;
+        if (qv < 64) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c)
+            if (c >= qv) pr[c] = 0.f;
+        }
       }
       {
         uint32_t pk[32];
@@ -501,13 +458,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         tc_wait_ld();
 #pragma unroll
         for (int c = 0; c < 32; c += 4) {
-          const float4 d4 = *reinterpret_cast<const float4*>(st + 128 + c0 + c);
-          const float a0 = pr[c0 + c + 0] * (__uint_as_float(du[c + 0]) - d4.x);
-          const float a1 = pr[c0 + c + 1] * (__uint_as_float(du[c + 1]) - d4.y);
-          const float a2 = pr[c0 + c + 2] * (__uint_as_float(du[c + 2]) - d4.z);
-          const float a3 = pr[c0 + c + 3] * (__uint_as_float(du[c + 3]) - d4.w);
-          dsp[(c0 + c) >> 1] = pack_bf16x2(a0, a1);
-          dsp[((c0 + c) >> 1) + 1] = pack_bf16x2(a2, a3);
+          const float4 d4 = *reinterpret_cast<const float4*>(st + 128 + c0 + c);  // -delta
+          const float2 a01 = __fmul2_rn(make_float2(pr[c0 + c + 0], pr[c0 + c + 1]),
+                                        __fadd2_rn(make_float2(__uint_as_float(du[c + 0]), __uint_as_float(du[c + 1])),
+                                                   make_float2(d4.x, d4.y)));
+          const float2 a23 = __fmul2_rn(make_float2(pr[c0 + c + 2], pr[c0 + c + 3]),
+                                        __fadd2_rn(make_float2(__uint_as_float(du[c + 2]), __uint_as_float(du[c + 3])),
+                                                   make_float2(d4.z, d4.w)));
+          dsp[(c0 + c) >> 1] = pack_bf16x2(a01.x, a01.y);
+          dsp[((c0 + c) >> 1) + 1] = pack_bf16x2(a23.x, a23.y);
         }
       }
       // the dS tile of the previous iteration must have been consumed by MMA4/MMA5
@@ -610,19 +569,19 @@ __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_b
   *reinterpret_cast<uint4*>(dq + b * sb + static_cast<int64_t>(l) * sl + h * sh + d) = w;
 }
 
-template <int D, bool LSU>
+template <int D>
 cudaError_t launch_bwd_one(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
                            const CUtensorMap& tm_do, const CUtensorMap& tm_dq, float* dq_acc, int Lq_total,
                            const AttnBwdParams& p, cudaStream_t stream) {
   using C = BwdCfg<D>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<D, LSU>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   dim3 grid((p.seq.Lk + 127) / 128, p.seq.H, p.seq.nprob);
-  attn_bwd_kernel<D, LSU><<<grid, C::THREADS, C::BYTES, stream>>>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p);
+  attn_bwd_kernel<D><<<grid, C::THREADS, C::BYTES, stream>>>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p);
   return cudaGetLastError();
 }
 
@@ -631,16 +590,8 @@ cudaError_t launch_bwd_one(const CUtensorMap& tm_q, const CUtensorMap& tm_k, con
 cudaError_t launch_attn_bwd(int D, const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
                             const CUtensorMap& tm_do, const CUtensorMap& tm_dq, float* dq_acc, int Lq_total,
                             const AttnBwdParams& p, cudaStream_t stream) {
-  // Default: TMA loads. VT_BWD_LSU_LOADS=1 selects the cp.async producer for A/B measurements. Measured on K1 it is
-  // 40 % SLOWER (659 vs 1076 TFLOP/s): LSU writes into shared memory starve behind the UMMA operand fetch, which
-  // saturates the 128 B/clk shared-memory port, whereas TMA writes do not.
-  static const bool tma_loads = [] { const char* e = getenv("VT_BWD_LSU_LOADS"); return !(e != nullptr && e[0] == '1'); }();
-  if (D == 128)
-    return tma_loads ? launch_bwd_one<128, false>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream)
-                     : launch_bwd_one<128, true>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream);
-  if (D == 64)
-    return tma_loads ? launch_bwd_one<64, false>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream)
-                     : launch_bwd_one<64, true>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream);
+  if (D == 128) return launch_bwd_one<128>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream);
+  if (D == 64) return launch_bwd_one<64>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream);
   return cudaErrorInvalidValue;
 }
 

@@ -680,6 +680,337 @@ attn_fwd_db_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
   if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
+// =====================================================================================================================
+// attn_fwd_rot_kernel<D = 64>: TWO 128-row query tiles per CTA sharing THREE rotating S buffers in TMEM.
+//
+// At head dim 64 a tile's MMAs (Q K^T 256 + P V 256 cycles per 128 keys) are much shorter than its softmax (~1500
+// cycles), so the ping-pong kernel's per-tile chain softmax -> PV -> QK -> softmax leaves the tensor pipe 34 % busy and
+// both tiles' softmax warps idle while they wait for their next S. Head dim 64 leaves TMEM room for a third S buffer
+// (3 x 128 + 2 x 64 = 512 columns): job n = 2 j + t (key tile j, query tile t) uses buffer n % 3, and Q K^T of job
+// n + 3 is issued right behind P V of job n into the buffer that P V frees. S of a tile's next key block is therefore
+// complete long before its softmax warps finish the current one: they never wait, and the kernel runs at the SM's
+// softmax throughput (MUFU + FMA-pipe exponentials of both tiles overlapped) instead of at the chain latency.
+// Warps 0-7 / 8-15: softmax of tile 0 / 1 (two threads per row), warp 16 TMA producer, warp 17 MMA issuer.
+template <int D>
+struct FwdRotCfg {
+  static_assert(D == 64, "three S buffers + two O tiles fit TMEM only at head dim 64");
+  static constexpr int CHUNK = 128 * 128;
+  static constexpr int TILE = CHUNK;  // 128 x 64 bf16
+  static constexpr int KS = 4, VS = 3;
+#ifdef VT_FWD_EMU64
+  static constexpr int EMU = VT_FWD_EMU64;
+#else
+  static constexpr int EMU = 3;
+#endif
+  static constexpr int OFF_Q = 0;
+  static constexpr int OFF_K = OFF_Q + 2 * TILE;
+  static constexpr int OFF_V = OFF_K + KS * TILE;
+  static constexpr int OFF_MX = OFF_V + VS * TILE;  // float [2 parity][2 tiles][2 halves][128]
+  static constexpr int OFF_BAR = OFF_MX + 2 * 2 * 2 * 128 * 4;
+  static constexpr int NBAR = 1 + 2 * KS + 2 * VS + 3 + 2 + 2 + 2;
+  static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
+  static constexpr int BYTES = OFF_TMEM + 16;
+  static constexpr int THREADS = 18 * 32;
+  static constexpr uint32_t T_S = 0, T_O = 384;
+};
+
+template <int D>
+__global__ void __launch_bounds__(FwdRotCfg<D>::THREADS, 1)
+attn_fwd_rot_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                    const __grid_constant__ CUtensorMap tm_v, const AttnFwdParams p) {
+  using C = FwdRotCfg<D>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) watchdog_trap(TAG_FWD_ALIGN);
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+
+  const int prob = blockIdx.z, h = blockIdx.y;
+  int q_base = 0, q_len = p.seq.Lq, bq = prob;
+  int k_base = 0, k_len = p.seq.Lk, bk = prob;
+  if (p.seq.cu_q != nullptr) {
+    q_base = p.seq.cu_q[prob];
+    q_len = p.seq.cu_q[prob + 1] - q_base;
+    bq = 0;
+  }
+  if (p.seq.cu_k != nullptr) {
+    k_base = p.seq.cu_k[prob];
+    k_len = p.seq.cu_k[prob + 1] - k_base;
+    bk = 0;
+  } else if (p.seq.seqlens_k != nullptr) {
+    k_len = min(max(p.seq.seqlens_k[prob], 0), p.seq.Lk);
+  }
+  const int q0 = blockIdx.x * 256;
+  if (q0 >= q_len) return;  // CTA-uniform
+  const int n_kv = (k_len + 127) >> 7;
+
+  if (n_kv == 0) {  // no keys: softmax over the empty set -> zeros, lse = -inf (matches flash-attn)
+    for (int r = threadIdx.x; r < 256; r += blockDim.x) {
+      const int row = q0 + r;
+      if (row < q_len) {
+        __nv_bfloat16* optr = p.o + bq * p.o_sb + static_cast<int64_t>(q_base + row) * p.o_sl + h * p.o_sh;
+        for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(optr + c) = make_uint4(0, 0, 0, 0);
+        p.lse[bq * p.lse_sb + h * p.lse_sh + q_base + row] = -CUDART_INF_F;
+      }
+    }
+    return;
+  }
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = q_full + 1;
+  uint64_t* k_empty = k_full + C::KS;
+  uint64_t* v_full = k_empty + C::KS;
+  uint64_t* v_empty = v_full + C::VS;
+  uint64_t* s_full = v_empty + C::VS;  // [3] one per S buffer
+  uint64_t* p_full = s_full + 3;       // [2] one per query tile
+  uint64_t* pv_done = p_full + 2;      // [2]
+  uint64_t* o_full = pv_done + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM);
+  constexpr int PROD_WARP = 16, MMA_WARP = 17;
+
+  if (warp == PROD_WARP && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+  }
+  if (warp == MMA_WARP && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < C::KS; ++i) { mbar_init(k_full + i, 1); mbar_init(k_empty + i, 1); }
+    for (int i = 0; i < C::VS; ++i) { mbar_init(v_full + i, 1); mbar_init(v_empty + i, 1); }
+    for (int i = 0; i < 3; ++i) mbar_init(s_full + i, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(p_full + i, 256); mbar_init(pv_done + i, 1); mbar_init(o_full + i, 1); }
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  const int njobs = 2 * n_kv;
+
+  if (warp == PROD_WARP) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * C::TILE);
+      tma_load_4d(smem + C::OFF_Q, &tm_q, q_full, 0, q_base + q0, h, bq);
+      tma_load_4d(smem + C::OFF_Q + C::TILE, &tm_q, q_full, 0, q_base + q0 + 128, h, bq);
+      for (int j = 0; j < n_kv; ++j) {
+        const int ks = j % C::KS, vs = j % C::VS;
+        mbar_wait(k_empty + ks, ((j / C::KS) & 1) ^ 1, TAG_K_EMPTY);
+        mbar_arrive_expect_tx(k_full + ks, C::TILE);
+        tma_load_4d(smem + C::OFF_K + ks * C::TILE, &tm_k, k_full + ks, 0, k_base + j * 128, h, bk);
+        mbar_wait(v_empty + vs, ((j / C::VS) & 1) ^ 1, TAG_V_EMPTY);
+        mbar_arrive_expect_tx(v_full + vs, C::TILE);
+        tma_load_4d(smem + C::OFF_V + vs * C::TILE, &tm_v, v_full + vs, 0, k_base + j * 128, h, bk);
+      }
+    }
+  } else if (warp == MMA_WARP) {
+    if (elect_one()) {
+      constexpr uint32_t IDESC_QK = umma_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, D, 0, 1);
+      const uint32_t sb16 = smem_u32(smem) >> 4;
+      const uint32_t q_smem = sb16 + (C::OFF_Q >> 4), k_smem = sb16 + (C::OFF_K >> 4), v_smem = sb16 + (C::OFF_V >> 4);
+      constexpr uint32_t TILE16 = C::TILE >> 4;
+      // job n = 2 j + t: S[buf] = Q_t K_j^T. `buf` is n % 3, carried as a counter by the caller.
+      auto issue_qk = [&](int n, int buf) {
+        const int t = n & 1, j = n >> 1, ks = j % C::KS;
+        if (t == 0) {
+          mbar_wait(k_full + ks, (j / C::KS) & 1, TAG_K_FULL);
+          tc_fence_after();
+        }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_ss(tmem_base + C::T_S + buf * 128, umma_desc_sw128_a16(q_smem + t * TILE16 + kk * 2, 16, 1024),
+                  umma_desc_sw128_a16(k_smem + ks * TILE16 + kk * 2, 16, 1024), IDESC_QK, kk != 0);
+        if (t == 1) trace_mark(p.trace, 3, j - 1, 2);
+        tc_commit(s_full + buf);
+        if (t == 1) tc_commit(k_empty + ks);
+        if (t == 1) trace_mark(p.trace, 3, j - 1, 3);
+      };
+      mbar_wait(q_full, 0, TAG_Q_FULL);
+      issue_qk(0, 0);
+      issue_qk(1, 1);
+      if (njobs > 2) issue_qk(2, 2);
+      int buf = 0;
+      for (int n = 0; n < njobs; ++n) {
+        const int t = n & 1, j = n >> 1, vs = j % C::VS;
+        if (t == 0) mbar_wait(v_full + vs, (j / C::VS) & 1, TAG_V_FULL);
+        trace_mark(p.trace, 1, j, t * 3);
+        mbar_wait(p_full + t, j & 1, TAG_P_FULL);
+        tc_fence_after();
+        trace_mark(p.trace, 1, j, t * 3 + 1);
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk)  // 16 keys per MMA; P sits in the first 64 columns of its S buffer
+          umma_ts(tmem_base + C::T_O + t * D, tmem_base + C::T_S + buf * 128 + kk * 8,
+                  umma_desc_sw128_a16(v_smem + vs * TILE16 + kk * 128, C::CHUNK, 1024), IDESC_PV, (j > 0) || kk != 0);
+        if (t == 0) trace_mark(p.trace, 3, j, 0);
+        tc_commit(pv_done + t);
+        if (t == 1) tc_commit(v_empty + vs);
+        if (t == 0) trace_mark(p.trace, 3, j, 1);
+        if (n + 3 < njobs) issue_qk(n + 3, buf);  // into the buffer this P V frees
+        if (j == n_kv - 1) tc_commit(o_full + t);
+        trace_mark(p.trace, 1, j, t * 3 + 2);
+        buf = (buf == 2) ? 0 : buf + 1;
+      }
+    }
+  } else {
+    // ================================ softmax: two threads per query row ==========================
+    const int t = warp >> 3;
+    const int hf = (warp >> 2) & 1;
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(quarter * 32) << 16;
+    constexpr int OH = D / 2;
+    const uint32_t o_addr = tmem_base + lane_addr + C::T_O + t * D + hf * OH;
+    const float sl2 = p.scale_log2;
+    float* mx = reinterpret_cast<float*>(smem + C::OFF_MX);
+    const uint32_t pair_bar = 1 + t;
+    const bool tr = row == 0 && hf == 0;
+    const int trole = t == 0 ? 0 : 2;
+    float m = -CUDART_INF_F, l = 0.f;
+    int buf = t;          // (2 j + t) % 3
+    uint32_t use = 0;     // (2 j + t) / 3
+    for (int j = 0; j < n_kv; ++j) {
+      const uint32_t s_addr = tmem_base + lane_addr + C::T_S + buf * 128 + hf * 64;
+      const uint32_t p_addr = tmem_base + lane_addr + C::T_S + buf * 128 + hf * 32;
+      if (tr) trace_mark(p.trace, trole, j, 0);
+      mbar_wait(s_full + buf, use & 1, TAG_S_FULL);
+      tc_fence_after();
+      if (tr) trace_mark(p.trace, trole, j, 1);
+      uint32_t su[64];
+      tmem_ld_x32(s_addr + 0, su + 0);
+      tmem_ld_x32(s_addr + 32, su + 32);
+      tc_wait_ld();
+      float* s = reinterpret_cast<float*>(su);
+      if (j == n_kv - 1) {
+        const int valid = k_len - j * 128 - hf * 64;
+        if (valid < 64) {
+#pragma unroll
+          for (int c = 0; c < 64; ++c)
+            if (c >= valid) s[c] = -CUDART_INF_F;
+        }
+      }
+      float mx0 = s[0], mx1 = s[1], mx2 = s[2], mx3 = s[3];
+#pragma unroll
+      for (int c = 4; c < 64; c += 4) {
+        mx0 = fmaxf(mx0, s[c]);
+        mx1 = fmaxf(mx1, s[c + 1]);
+        mx2 = fmaxf(mx2, s[c + 2]);
+        mx3 = fmaxf(mx3, s[c + 3]);
+      }
+      // exchange the half-row maxima; the barrier also orders this tile's S reads before the partner's P writes
+      float* slot = mx + (((j & 1) * 2 + t) * 2) * 128;
+      slot[hf * 128 + row] = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      named_bar_sync(pair_bar, 256);
+      const float m_new = fmaxf(m, fmaxf(slot[row], slot[128 + row]));
+      if (tr) trace_mark(p.trace, trole, j, 2);
+      if (j == 0) {
+        m = m_new;
+      } else {
+        const bool need = (m_new - m) * sl2 > 8.f;  // lazy rescale, same decision in both threads of a row
+        if (__any_sync(0xffffffffu, need)) {
+          const float f = need ? ex2_approx((m - m_new) * sl2) : 1.f;
+          if (need) m = m_new;
+          l *= f;
+          // S of this job was issued behind P V of job n - 3, not n - 2: wait for this tile's previous P V explicitly
+          mbar_wait(pv_done + t, (j - 1) & 1, TAG_PV_DONE);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c0 = 0; c0 < OH; c0 += 8) {
+            uint32_t ou[8];
+            tmem_ld_x8(o_addr + c0, ou);
+            tc_wait_ld();
+#pragma unroll
+            for (int c = 0; c < 8; ++c) ou[c] = __float_as_uint(__uint_as_float(ou[c]) * f);
+            tmem_st_x8(o_addr + c0, ou);
+          }
+        }
+      }
+      if (tr) trace_mark(p.trace, trole, j, 3);
+      const float msc = m * sl2;
+      const float2 sc2 = make_float2(sl2, sl2), nm2 = make_float2(-msc, -msc);
+      float2 lacc = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 32) {
+        uint32_t pk[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          const float2 x = __ffma2_rn(make_float2(s[c0 + c], s[c0 + c + 1]), sc2, nm2);
+          float2 pv;
+          if ((((c0 + c) >> 1) & 7) < C::EMU) {
+            pv = ex2_poly2(x);
+          } else {
+            pv.x = ex2_approx(x.x);
+            pv.y = ex2_approx(x.y);
+          }
+          lacc = __fadd2_rn(lacc, pv);
+          pk[c >> 1] = pack_bf16x2(pv.x, pv.y);
+        }
+        tmem_st_x16(p_addr + (c0 >> 1), pk);
+      }
+      l += lacc.x + lacc.y;
+      if (tr) trace_mark(p.trace, trole, j, 4);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(p_full + t);
+      if (tr) trace_mark(p.trace, trole, j, 5);
+      // next job of this tile: n + 2
+      buf += 2;
+      if (buf >= 3) { buf -= 3; ++use; }
+    }
+    {
+      float* slot = mx + (((n_kv & 1) * 2 + t) * 2) * 128;
+      slot[hf * 128 + row] = l;
+      named_bar_sync(pair_bar, 256);
+      l = slot[row] + slot[128 + row];
+    }
+    mbar_wait(o_full + t, 0, TAG_O_FULL);
+    tc_fence_after();
+    const float inv = 1.f / l;
+    const int row_g = q0 + t * 128 + row;
+    const bool valid_row = row_g < q_len;
+    __nv_bfloat16* optr = p.o + bq * p.o_sb + static_cast<int64_t>(q_base + row_g) * p.o_sl + h * p.o_sh + hf * OH;
+    {
+      uint32_t ou[OH];
+      tmem_ld_x32(o_addr, ou);
+      tc_wait_ld();
+      if (valid_row) {
+#pragma unroll
+        for (int c = 0; c < OH; c += 8) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(ou[c + 0]) * inv, __uint_as_float(ou[c + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(ou[c + 2]) * inv, __uint_as_float(ou[c + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(ou[c + 4]) * inv, __uint_as_float(ou[c + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(ou[c + 6]) * inv, __uint_as_float(ou[c + 7]) * inv);
+          *reinterpret_cast<uint4*>(optr + c) = w;
+        }
+      }
+    }
+    if (valid_row && hf == 0) p.lse[bq * p.lse_sb + h * p.lse_sh + q_base + row_g] = m * p.scale + __logf(l);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_base, 512);
+}
+
+template <int D>
+cudaError_t launch_rot(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v, const AttnFwdParams& p,
+                       cudaStream_t stream) {
+  using C = FwdRotCfg<D>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_rot_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::BYTES);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  dim3 grid((p.seq.Lq + 255) / 256, p.seq.H, p.seq.nprob);
+  attn_fwd_rot_kernel<D><<<grid, C::THREADS, C::BYTES, stream>>>(tm_q, tm_k, tm_v, p);
+  return cudaGetLastError();
+}
+
 template <int D>
 cudaError_t launch_db(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v, const AttnFwdParams& p,
                       cudaStream_t stream) {
@@ -725,7 +1056,12 @@ cudaError_t launch_attn_fwd(int D, const CUtensorMap& tm_q, const CUtensorMap& t
   // One query tile per CTA when the (max) query length fits a single 128-row tile; two otherwise.
   const bool single = (q_tiles_hint == 1) || (q_tiles_hint == 0 && p.seq.Lq <= 128);
   if (D == 128) return single ? launch_one<128, 1>(tm_q, tm_k, tm_v, p, stream) : launch_one<128, 2>(tm_q, tm_k, tm_v, p, stream);
-  if (D == 64) return single ? launch_one<64, 1>(tm_q, tm_k, tm_v, p, stream) : launch_one<64, 2>(tm_q, tm_k, tm_v, p, stream);
+  if (D == 64) {
+    // Head dim 64, two tiles: the rotating-S kernel (K3: see DESIGN.md §4.1). VT_FWD_KERNEL=pp keeps the ping-pong kernel.
+    static const bool use_pp = [] { const char* e = getenv("VT_FWD_KERNEL"); return e != nullptr && e[0] == 'p'; }();
+    if (single) return launch_one<64, 1>(tm_q, tm_k, tm_v, p, stream);
+    return use_pp ? launch_one<64, 2>(tm_q, tm_k, tm_v, p, stream) : launch_rot<64>(tm_q, tm_k, tm_v, p, stream);
+  }
   return cudaErrorInvalidValue;
 }
 

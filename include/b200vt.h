@@ -137,23 +137,28 @@ int vt_qk_rmsnorm_rope_bwd(const void* dy, const void* x, const float* rstd, voi
  * Replaces hunyuan  modulate(norm(x), shift, scale)   (modulate_layers.py:31-49 with nn.LayerNorm, models.py:161-164)
  *          wan      norm1(x).float() * (1 + e1) + e0  (wan/modules/model.py:294-296)
  *          lvdm     nn.LayerNorm(dim) (affine, no modulate: scale == shift == NULL)  (attention.py:299-310)
- * x,y: (B,L,C) bf16 contiguous rows; gamma/beta: (C) fp32 or NULL; scale/shift: (B,C) fp32 or NULL.
- * mean/rstd: (B*L) fp32 saved for backward.
+ * x: (B,L,C) contiguous rows, bf16 (x_dtype 0) or fp32 (x_dtype 1: Wan keeps its residual stream in fp32 and feeds the
+ * modulated activation to bf16 Linears, model.py:294-296); y: (B,L,C) bf16; gamma/beta: (C) fp32 or NULL;
+ * scale/shift: (B,C) fp32 or NULL. mean/rstd: (B*L) fp32 saved for backward.
  * ------------------------------------------------------------------------------------------------------------- */
 int vt_ln_modulate_fwd(const void* x, void* y, float* mean, float* rstd, const float* gamma, const float* beta,
-                       const float* scale, const float* shift, int B, int L, int C, float eps, void* stream);
-/* dx; and fp32 accumulators (atomically added, caller zeroes): dgamma,dbeta (C); dscale,dshift (B,C). Nullable. */
+                       const float* scale, const float* shift, int B, int L, int C, float eps, int x_dtype,
+                       void* stream);
+/* dy bf16 -> dx in x's dtype; and fp32 accumulators (atomically added, caller zeroes): dgamma,dbeta (C);
+ * dscale,dshift (B,C). Nullable. */
 int vt_ln_modulate_bwd(const void* dy, const void* x, const float* mean, const float* rstd, void* dx,
                        const float* gamma, const float* beta, const float* scale, float* dgamma, float* dbeta,
-                       float* dscale, float* dshift, int B, int L, int C, void* stream);
+                       float* dscale, float* dshift, int B, int L, int C, int x_dtype, void* stream);
 
 /* Gated residual: y = x + branch * gate[b]   (hunyuan apply_gate, modulate_layers.py:52-68 & models.py:231;
- * wan x + y * e2, model.py:298). x, branch, y: (B,L,C) bf16; gate: (B,C) fp32 or NULL (plain add). */
+ * wan x + y * e2, model.py:298). x, y: (B,L,C) bf16 (x_dtype 0) or fp32 (x_dtype 1, Wan's fp32 residual stream);
+ * branch: (B,L,C) bf16; gate: (B,C) fp32 or NULL (plain add). */
 int vt_gate_residual_fwd(const void* x, const void* branch, void* y, const float* gate, int B, int L, int C,
-                         void* stream);
-/* dbranch = dy * gate; dgate (B,C) fp32 accumulated atomically (caller zeroes); dx = dy is the caller's alias. */
+                         int x_dtype, void* stream);
+/* dbranch (bf16) = dy * gate, dy in x's dtype; dgate (B,C) fp32 accumulated atomically (caller zeroes); dx = dy is the
+ * caller's alias. */
 int vt_gate_residual_bwd(const void* dy, const void* branch, void* dbranch, const float* gate, float* dgate, int B,
-                         int L, int C, void* stream);
+                         int L, int C, int x_dtype, void* stream);
 
 /* GroupNorm(G) [+ SiLU] on NCHW-like tensors x: (N, C, S) bf16 or fp32 (S = product of spatial dims), fp32 statistics.
  * Replaces lvdm normalization()/GroupNormSpecific + nn.SiLU (lvdm/modules/utils.py:192-203, openaimodel3d.py:229-255)

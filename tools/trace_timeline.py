@@ -6,7 +6,11 @@ import sys
 
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+# the marks exist only in a -DVT_TRACE build: tools/build_variant.sh gpurun_tmp/lib_trace.so -DVT_TRACE
+if "B200VT_LIB" not in os.environ and os.path.exists(os.path.join(ROOT, "gpurun_tmp", "lib_trace.so")):
+    os.environ["B200VT_LIB"] = os.path.join(ROOT, "gpurun_tmp", "lib_trace.so")
 import b200vt._lib as L  # noqa: E402
 import b200vt.ops as ops  # noqa: E402
 

@@ -38,10 +38,10 @@ _SIGS = {
                                C.c_int, C.c_float, vp],
     "vt_qk_rmsnorm_rope_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, c_i64p, c_i64p, c_i64p, C.c_int, C.c_int, C.c_int,
                                C.c_int, C.c_int, C.c_int, vp],
-    "vt_ln_modulate_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, vp],
-    "vt_ln_modulate_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp],
-    "vt_gate_residual_fwd": [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp],
-    "vt_gate_residual_bwd": [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp],
+    "vt_ln_modulate_fwd": [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp],
+    "vt_ln_modulate_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
+    "vt_gate_residual_fwd": [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
+    "vt_gate_residual_bwd": [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "vt_groupnorm_silu_fwd": [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
                               vp],
     "vt_groupnorm_silu_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -696,11 +696,11 @@ struct FwdRotCfg {
   static_assert(D == 64, "three S buffers + two O tiles fit TMEM only at head dim 64");
   static constexpr int CHUNK = 128 * 128;
   static constexpr int TILE = CHUNK;  // 128 x 64 bf16
-  static constexpr int KS = 4, VS = 3;
+  static constexpr int KS = 3, VS = 3;  // ring depths = jobs-per-group / 2, so ring slots are compile-time in the issuer
 #ifdef VT_FWD_EMU64
   static constexpr int EMU = VT_FWD_EMU64;
 #else
-  static constexpr int EMU = 3;
+  static constexpr int EMU = 2;  // K3 fwd: 0/8 .., 1/8 908, 2/8 905, 3/8 886 TFLOP/s — flat: the loop is issue-bound, not MUFU-bound
 #endif
   static constexpr int OFF_Q = 0;
   static constexpr int OFF_K = OFF_Q + 2 * TILE;
@@ -813,46 +813,53 @@ attn_fwd_rot_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
       const uint32_t sb16 = smem_u32(smem) >> 4;
       const uint32_t q_smem = sb16 + (C::OFF_Q >> 4), k_smem = sb16 + (C::OFF_K >> 4), v_smem = sb16 + (C::OFF_V >> 4);
       constexpr uint32_t TILE16 = C::TILE >> 4;
-      // job n = 2 j + t: S[buf] = Q_t K_j^T. `buf` is n % 3, carried as a counter by the caller.
-      auto issue_qk = [&](int n, int buf) {
-        const int t = n & 1, j = n >> 1, ks = j % C::KS;
+      // Jobs n = 2 j + t run in groups of six (three key tiles x two query tiles): inside the unrolled group every
+      // S buffer (n % 3), ring slot (j % 3) and query tile is a compile-time constant and only the phase parities depend
+      // on the group index g. The issuer is one thread on a scheduler it shares with four busy softmax warps, so its
+      // instruction count per MMA is what limits the kernel at head dim 64.
+      // S[u % 3] = Q_t K_j^T for the job at position u (0..8: positions 6..8 are the next group's first jobs)
+      auto issue_qk = [&](int u, uint32_t g1) {
+        const int t = u & 1, jj = u >> 1, ks = jj % 3, buf = u % 3;
+        const uint32_t par = (jj >= 3 ? g1 ^ 1u : g1);  // (j / 3) & 1
         if (t == 0) {
-          mbar_wait(k_full + ks, (j / C::KS) & 1, TAG_K_FULL);
+          mbar_wait(k_full + ks, par, TAG_K_FULL);
           tc_fence_after();
         }
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk)
           umma_ss(tmem_base + C::T_S + buf * 128, umma_desc_sw128_a16(q_smem + t * TILE16 + kk * 2, 16, 1024),
                   umma_desc_sw128_a16(k_smem + ks * TILE16 + kk * 2, 16, 1024), IDESC_QK, kk != 0);
-        if (t == 1) trace_mark(p.trace, 3, j - 1, 2);
         tc_commit(s_full + buf);
         if (t == 1) tc_commit(k_empty + ks);
-        if (t == 1) trace_mark(p.trace, 3, j - 1, 3);
       };
       mbar_wait(q_full, 0, TAG_Q_FULL);
       issue_qk(0, 0);
-      issue_qk(1, 1);
-      if (njobs > 2) issue_qk(2, 2);
-      int buf = 0;
-      for (int n = 0; n < njobs; ++n) {
-        const int t = n & 1, j = n >> 1, vs = j % C::VS;
-        if (t == 0) mbar_wait(v_full + vs, (j / C::VS) & 1, TAG_V_FULL);
-        trace_mark(p.trace, 1, j, t * 3);
-        mbar_wait(p_full + t, j & 1, TAG_P_FULL);
-        tc_fence_after();
-        trace_mark(p.trace, 1, j, t * 3 + 1);
+      issue_qk(1, 0);
+      if (njobs > 2) issue_qk(2, 0);
+      for (int n0 = 0; n0 < njobs; n0 += 6) {
+        const uint32_t g1 = static_cast<uint32_t>(n0 / 6) & 1u;
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk)  // 16 keys per MMA; P sits in the first 64 columns of its S buffer
-          umma_ts(tmem_base + C::T_O + t * D, tmem_base + C::T_S + buf * 128 + kk * 8,
-                  umma_desc_sw128_a16(v_smem + vs * TILE16 + kk * 128, C::CHUNK, 1024), IDESC_PV, (j > 0) || kk != 0);
-        if (t == 0) trace_mark(p.trace, 3, j, 0);
-        tc_commit(pv_done + t);
-        if (t == 1) tc_commit(v_empty + vs);
-        if (t == 0) trace_mark(p.trace, 3, j, 1);
-        if (n + 3 < njobs) issue_qk(n + 3, buf);  // into the buffer this P V frees
-        if (j == n_kv - 1) tc_commit(o_full + t);
-        trace_mark(p.trace, 1, j, t * 3 + 2);
-        buf = (buf == 2) ? 0 : buf + 1;
+        for (int u = 0; u < 6; ++u) {
+          const int n = n0 + u;
+          if (n < njobs) {
+            const int t = u & 1, jj = u >> 1, buf = u % 3;
+            const uint32_t jpar = g1 ^ static_cast<uint32_t>(jj & 1);  // j & 1 with j = 3 g + jj
+            if (t == 0) mbar_wait(v_full + jj, g1, TAG_V_FULL);
+            trace_mark(p.trace, 1, n >> 1, t * 3);
+            mbar_wait(p_full + t, jpar, TAG_P_FULL);
+            tc_fence_after();
+            trace_mark(p.trace, 1, n >> 1, t * 3 + 1);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)  // 16 keys per MMA; P sits in the first 64 columns of its S buffer
+              umma_ts(tmem_base + C::T_O + t * D, tmem_base + C::T_S + buf * 128 + kk * 8,
+                      umma_desc_sw128_a16(v_smem + jj * TILE16 + kk * 128, C::CHUNK, 1024), IDESC_PV, (n > 1) || kk != 0);
+            tc_commit(pv_done + t);
+            if (t == 1) tc_commit(v_empty + jj);
+            if (n + 3 < njobs) issue_qk(u + 3, g1);  // into the buffer this P V frees
+            if (n + 2 >= njobs) tc_commit(o_full + t);
+            trace_mark(p.trace, 1, n >> 1, t * 3 + 2);
+          }
+        }
       }
     }
   } else {

@@ -53,6 +53,25 @@ __device__ __forceinline__ void load8f(const float* p, float* f) {
   f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
+// 8 consecutive elements of a row in either storage type (bf16: one 16-byte access; fp32: two).
+template <typename T> struct Raw8;
+template <> struct Raw8<__nv_bfloat16> { uint4 a; };
+template <> struct Raw8<float> { uint4 a, b; };
+__device__ __forceinline__ void zero8(Raw8<__nv_bfloat16>& r) { r.a = make_uint4(0, 0, 0, 0); }
+__device__ __forceinline__ void zero8(Raw8<float>& r) { r.a = r.b = make_uint4(0, 0, 0, 0); }
+__device__ __forceinline__ void ldg8(const __nv_bfloat16* p, Raw8<__nv_bfloat16>& r) { r.a = ldg_stream(p); }
+__device__ __forceinline__ void ldg8(const float* p, Raw8<float>& r) { r.a = ldg_stream(p); r.b = ldg_stream(p + 4); }
+__device__ __forceinline__ void unpack8(const Raw8<__nv_bfloat16>& r, float* f) { unpack8(r.a, f); }
+__device__ __forceinline__ void unpack8(const Raw8<float>& r, float* f) {
+  f[0] = __uint_as_float(r.a.x); f[1] = __uint_as_float(r.a.y); f[2] = __uint_as_float(r.a.z); f[3] = __uint_as_float(r.a.w);
+  f[4] = __uint_as_float(r.b.x); f[5] = __uint_as_float(r.b.y); f[6] = __uint_as_float(r.b.z); f[7] = __uint_as_float(r.b.w);
+}
+__device__ __forceinline__ void stg8(__nv_bfloat16* p, const float* f) { stg_stream(p, pack8(f)); }
+__device__ __forceinline__ void stg8(float* p, const float* f) {
+  stg_stream(p, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+  stg_stream(p + 4, make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
+}
+
 // Sum NV values per thread across the CTA. `red` holds NV * 32 floats. All threads get the totals.
 template <int NV>
 __device__ __forceinline__ void block_sum(float* v, float* red) {
@@ -81,8 +100,8 @@ __device__ __forceinline__ void block_sum(float* v, float* red) {
 // ------------------------------------------------------------------------------------------------------------
 // LayerNorm + modulate
 // ------------------------------------------------------------------------------------------------------------
-template <int MAXT, int RPI>
-__global__ void __launch_bounds__(MAXT) ln_modulate_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+template <typename XT, int MAXT, int RPI>
+__global__ void __launch_bounds__(MAXT) ln_modulate_fwd_kernel(const XT* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                        float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                        const float* __restrict__ scale, const float* __restrict__ shift, int L, int C,
@@ -106,11 +125,11 @@ __global__ void __launch_bounds__(MAXT) ln_modulate_fwd_kernel(const __nv_bfloat
   }
   const float invC = 1.f / C;
   for (int l0 = blockIdx.x * RPI; l0 < L; l0 += gridDim.x * RPI) {
-    uint4 raw[RPI];
+    Raw8<XT> raw[RPI];
 #pragma unroll
     for (int r = 0; r < RPI; ++r) {
-      raw[r] = make_uint4(0, 0, 0, 0);
-      if (active && l0 + r < L) raw[r] = ldg_stream(x + (static_cast<size_t>(b) * L + l0 + r) * C + col);
+      zero8(raw[r]);
+      if (active && l0 + r < L) ldg8(x + (static_cast<size_t>(b) * L + l0 + r) * C + col, raw[r]);
     }
     float s[RPI];
     float f[RPI][8];
@@ -157,10 +176,10 @@ __global__ void __launch_bounds__(MAXT) ln_modulate_fwd_kernel(const __nv_bfloat
 
 // dx = rstd * (gh - mean(gh) - xh * mean(gh * xh)),  gh = dy * (1+scale) * gamma,  xh = (x - mean) * rstd
 // dshift += dy; dscale += dy * (xh*gamma + beta); dbeta += dy*(1+scale); dgamma += dy*(1+scale)*xh
-template <int MAXT, int RPI>
-__global__ void __launch_bounds__(MAXT) ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+template <typename XT, int MAXT, int RPI>
+__global__ void __launch_bounds__(MAXT) ln_modulate_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const XT* __restrict__ x,
                                        const float* __restrict__ mean, const float* __restrict__ rstd,
-                                       __nv_bfloat16* __restrict__ dx, const float* __restrict__ gamma,
+                                       XT* __restrict__ dx, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, const float* __restrict__ scale,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        float* __restrict__ dscale, float* __restrict__ dshift, int L, int C) {
@@ -183,12 +202,13 @@ __global__ void __launch_bounds__(MAXT) ln_modulate_bwd_kernel(const __nv_bfloat
   float a_dgamma[8] = {0}, a_dbeta[8] = {0}, a_dscale[8] = {0}, a_dshift[8] = {0};
   const float invC = 1.f / C;
   for (int l0 = blockIdx.x * RPI; l0 < L; l0 += gridDim.x * RPI) {
-    uint4 rdy[RPI], rx[RPI];
+    uint4 rdy[RPI];
+    Raw8<XT> rx[RPI];
     float mu[RPI], rs[RPI];
 #pragma unroll
     for (int r = 0; r < RPI; ++r) {
       rdy[r] = make_uint4(0, 0, 0, 0);
-      rx[r] = make_uint4(0, 0, 0, 0);
+      zero8(rx[r]);
       mu[r] = 0.f;
       rs[r] = 0.f;
       if (l0 + r < L) {
@@ -197,7 +217,7 @@ __global__ void __launch_bounds__(MAXT) ln_modulate_bwd_kernel(const __nv_bfloat
         rs[r] = rstd[row];
         if (active) {
           rdy[r] = ldg_stream(dy + row * C + col);
-          rx[r] = ldg_stream(x + row * C + col);
+          ldg8(x + row * C + col, rx[r]);
         }
       }
     }
@@ -232,7 +252,7 @@ __global__ void __launch_bounds__(MAXT) ln_modulate_bwd_kernel(const __nv_bfloat
       float o[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = rs[r] * (gh[r][i] - m1 - xh[r][i] * m2);
-      stg_stream(dx + (static_cast<size_t>(b) * L + l0 + r) * C + col, pack8(o));
+      stg8(dx + (static_cast<size_t>(b) * L + l0 + r) * C + col, o);
     }
   }
   if (active) {
@@ -249,9 +269,9 @@ __global__ void __launch_bounds__(MAXT) ln_modulate_bwd_kernel(const __nv_bfloat
 // ------------------------------------------------------------------------------------------------------------
 // gated residual
 // ------------------------------------------------------------------------------------------------------------
-template <int MAXT, int RPI>
-__global__ void __launch_bounds__(MAXT) gate_residual_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ br,
-                                         __nv_bfloat16* __restrict__ y, const float* __restrict__ gate, int L, int C) {
+template <typename XT, int MAXT, int RPI>
+__global__ void __launch_bounds__(MAXT) gate_residual_fwd_kernel(const XT* __restrict__ x, const __nv_bfloat16* __restrict__ br,
+                                         XT* __restrict__ y, const float* __restrict__ gate, int L, int C) {
   const int b = blockIdx.y;
   const int col = threadIdx.x * 8;
   if (col >= C) return;
@@ -260,12 +280,13 @@ __global__ void __launch_bounds__(MAXT) gate_residual_fwd_kernel(const __nv_bflo
   for (int i = 0; i < 8; ++i) g[i] = 1.f;
   if (gate) load8f(gate + static_cast<size_t>(b) * C + col, g);
   for (int l0 = blockIdx.x * RPI; l0 < L; l0 += gridDim.x * RPI) {
-    uint4 rx[RPI], rb[RPI];
+    Raw8<XT> rx[RPI];
+    uint4 rb[RPI];
 #pragma unroll
     for (int r = 0; r < RPI; ++r) {
       if (l0 + r < L) {
         const size_t off = (static_cast<size_t>(b) * L + l0 + r) * C + col;
-        rx[r] = ldg_stream(x + off);
+        ldg8(x + off, rx[r]);
         rb[r] = ldg_stream(br + off);
       }
     }
@@ -277,13 +298,13 @@ __global__ void __launch_bounds__(MAXT) gate_residual_fwd_kernel(const __nv_bflo
       unpack8(rb[r], fb);
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = fmaf(fb[i], g[i], fx[i]);
-      stg_stream(y + (static_cast<size_t>(b) * L + l0 + r) * C + col, pack8(o));
+      stg8(y + (static_cast<size_t>(b) * L + l0 + r) * C + col, o);
     }
   }
 }
 
-template <int MAXT, int RPI>
-__global__ void __launch_bounds__(MAXT) gate_residual_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ br,
+template <typename XT, int MAXT, int RPI>
+__global__ void __launch_bounds__(MAXT) gate_residual_bwd_kernel(const XT* __restrict__ dy, const __nv_bfloat16* __restrict__ br,
                                          __nv_bfloat16* __restrict__ dbr, const float* __restrict__ gate,
                                          float* __restrict__ dgate, int L, int C) {
   const int b = blockIdx.y;
@@ -294,12 +315,13 @@ __global__ void __launch_bounds__(MAXT) gate_residual_bwd_kernel(const __nv_bflo
   for (int i = 0; i < 8; ++i) g[i] = 1.f;
   if (gate) load8f(gate + static_cast<size_t>(b) * C + col, g);
   for (int l0 = blockIdx.x * RPI; l0 < L; l0 += gridDim.x * RPI) {
-    uint4 rd[RPI], rb[RPI];
+    Raw8<XT> rd[RPI];
+    uint4 rb[RPI];
 #pragma unroll
     for (int r = 0; r < RPI; ++r) {
       if (l0 + r < L) {
         const size_t off = (static_cast<size_t>(b) * L + l0 + r) * C + col;
-        rd[r] = ldg_stream(dy + off);
+        ldg8(dy + off, rd[r]);
         if (dgate) rb[r] = ldg_stream(br + off);
       }
     }
@@ -550,49 +572,78 @@ using bf16 = __nv_bfloat16;
 extern "C" {
 
 int vt_ln_modulate_fwd(const void* x, void* y, float* mean, float* rstd, const float* gamma, const float* beta,
-                       const float* scale, const float* shift, int B, int L, int C, float eps, void* stream) {
+                       const float* scale, const float* shift, int B, int L, int C, float eps, int x_dtype, void* stream) {
   VT_REQUIRE(x && y, VT_ERR_NULL, "vt_ln_modulate_fwd: NULL argument");
   VT_REQUIRE(aligned16(x) && aligned16(y), VT_ERR_ALIGN, "x/y must be 16-byte aligned");
-#define K_(M, R) ln_modulate_fwd_kernel<M, R>
-  VT_ROW_DISPATCH(C, B, L, static_cast<cudaStream_t>(stream), K_,
-      static_cast<const bf16*>(x), static_cast<bf16*>(y), mean, rstd, gamma, beta, scale, shift, L, C, eps);
-#undef K_
+  VT_REQUIRE(x_dtype == 0 || x_dtype == 1, VT_ERR_DTYPE, "x_dtype %d (0 = bf16, 1 = fp32)", x_dtype);
+#define K16_(M, R) ln_modulate_fwd_kernel<bf16, M, R>
+#define K32_(M, R) ln_modulate_fwd_kernel<float, M, R>
+  if (x_dtype == 0)
+    VT_ROW_DISPATCH(C, B, L, static_cast<cudaStream_t>(stream), K16_,
+        static_cast<const bf16*>(x), static_cast<bf16*>(y), mean, rstd, gamma, beta, scale, shift, L, C, eps);
+  else
+    VT_ROW_DISPATCH(C, B, L, static_cast<cudaStream_t>(stream), K32_,
+        static_cast<const float*>(x), static_cast<bf16*>(y), mean, rstd, gamma, beta, scale, shift, L, C, eps);
+#undef K16_
+#undef K32_
   return 0;
 }
 
 int vt_ln_modulate_bwd(const void* dy, const void* x, const float* mean, const float* rstd, void* dx,
                        const float* gamma, const float* beta, const float* scale, float* dgamma, float* dbeta,
-                       float* dscale, float* dshift, int B, int L, int C, void* stream) {
+                       float* dscale, float* dshift, int B, int L, int C, int x_dtype, void* stream) {
   VT_REQUIRE(dy && x && mean && rstd && dx, VT_ERR_NULL, "vt_ln_modulate_bwd: NULL argument");
   VT_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx), VT_ERR_ALIGN, "dy/x/dx must be 16-byte aligned");
-#define K_(M, R) ln_modulate_bwd_kernel<M, R>
-  VT_ROW_DISPATCH(C, B, L, static_cast<cudaStream_t>(stream), K_,
-      static_cast<const bf16*>(dy), static_cast<const bf16*>(x), mean, rstd, static_cast<bf16*>(dx), gamma, beta,
-      scale, dgamma, dbeta, dscale, dshift, L, C);
-#undef K_
+  VT_REQUIRE(x_dtype == 0 || x_dtype == 1, VT_ERR_DTYPE, "x_dtype %d (0 = bf16, 1 = fp32)", x_dtype);
+#define K16_(M, R) ln_modulate_bwd_kernel<bf16, M, R>
+#define K32_(M, R) ln_modulate_bwd_kernel<float, M, R>
+  if (x_dtype == 0)
+    VT_ROW_DISPATCH(C, B, L, static_cast<cudaStream_t>(stream), K16_,
+        static_cast<const bf16*>(dy), static_cast<const bf16*>(x), mean, rstd, static_cast<bf16*>(dx), gamma, beta,
+        scale, dgamma, dbeta, dscale, dshift, L, C);
+  else
+    VT_ROW_DISPATCH(C, B, L, static_cast<cudaStream_t>(stream), K32_,
+        static_cast<const bf16*>(dy), static_cast<const float*>(x), mean, rstd, static_cast<float*>(dx), gamma, beta,
+        scale, dgamma, dbeta, dscale, dshift, L, C);
+#undef K16_
+#undef K32_
   return 0;
 }
 
 int vt_gate_residual_fwd(const void* x, const void* branch, void* y, const float* gate, int B, int L, int C,
-                         void* stream) {
+                         int x_dtype, void* stream) {
   VT_REQUIRE(x && branch && y, VT_ERR_NULL, "vt_gate_residual_fwd: NULL argument");
   VT_REQUIRE(aligned16(x) && aligned16(branch) && aligned16(y), VT_ERR_ALIGN, "x/branch/y must be 16-byte aligned");
-#define K_(M, R) gate_residual_fwd_kernel<M, R>
-  VT_ROW_DISPATCH(C, B, L, static_cast<cudaStream_t>(stream), K_,
-      static_cast<const bf16*>(x), static_cast<const bf16*>(branch), static_cast<bf16*>(y), gate, L, C);
-#undef K_
+  VT_REQUIRE(x_dtype == 0 || x_dtype == 1, VT_ERR_DTYPE, "x_dtype %d (0 = bf16, 1 = fp32)", x_dtype);
+#define K16_(M, R) gate_residual_fwd_kernel<bf16, M, R>
+#define K32_(M, R) gate_residual_fwd_kernel<float, M, R>
+  if (x_dtype == 0)
+    VT_ROW_DISPATCH(C, B, L, static_cast<cudaStream_t>(stream), K16_,
+        static_cast<const bf16*>(x), static_cast<const bf16*>(branch), static_cast<bf16*>(y), gate, L, C);
+  else
+    VT_ROW_DISPATCH(C, B, L, static_cast<cudaStream_t>(stream), K32_,
+        static_cast<const float*>(x), static_cast<const bf16*>(branch), static_cast<float*>(y), gate, L, C);
+#undef K16_
+#undef K32_
   return 0;
 }
 
 int vt_gate_residual_bwd(const void* dy, const void* branch, void* dbranch, const float* gate, float* dgate, int B,
-                         int L, int C, void* stream) {
+                         int L, int C, int x_dtype, void* stream) {
   VT_REQUIRE(dy && dbranch, VT_ERR_NULL, "vt_gate_residual_bwd: NULL argument");
   VT_REQUIRE(dgate == nullptr || branch != nullptr, VT_ERR_NULL, "dgate needs branch");
   VT_REQUIRE(aligned16(dy) && aligned16(dbranch) && aligned16(branch), VT_ERR_ALIGN, "buffers must be 16-byte aligned");
-#define K_(M, R) gate_residual_bwd_kernel<M, R>
-  VT_ROW_DISPATCH(C, B, L, static_cast<cudaStream_t>(stream), K_,
-      static_cast<const bf16*>(dy), static_cast<const bf16*>(branch), static_cast<bf16*>(dbranch), gate, dgate, L, C);
-#undef K_
+  VT_REQUIRE(x_dtype == 0 || x_dtype == 1, VT_ERR_DTYPE, "x_dtype %d (0 = bf16, 1 = fp32)", x_dtype);
+#define K16_(M, R) gate_residual_bwd_kernel<bf16, M, R>
+#define K32_(M, R) gate_residual_bwd_kernel<float, M, R>
+  if (x_dtype == 0)
+    VT_ROW_DISPATCH(C, B, L, static_cast<cudaStream_t>(stream), K16_,
+        static_cast<const bf16*>(dy), static_cast<const bf16*>(branch), static_cast<bf16*>(dbranch), gate, dgate, L, C);
+  else
+    VT_ROW_DISPATCH(C, B, L, static_cast<cudaStream_t>(stream), K32_,
+        static_cast<const float*>(dy), static_cast<const bf16*>(branch), static_cast<bf16*>(dbranch), gate, dgate, L, C);
+#undef K16_
+#undef K32_
   return 0;
 }
 

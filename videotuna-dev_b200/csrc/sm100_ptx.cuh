@@ -93,10 +93,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32
 }
 
 // ---- debug timeline (see attn_common.h) -----------------------------------------------------------------------
+// Compiled in only with -DVT_TRACE (tools/build_variant.sh): in the product build the marks vanish, so the single-thread
+// MMA issuer — which shares its scheduler with four busy softmax warps — carries no tracing instructions.
+#ifdef VT_TRACE
 __device__ __forceinline__ void trace_mark(long long* trace, int role, int iter, int slot) {
   if (trace != nullptr && iter < 64 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0)
     trace[(role * 64 + iter) * 8 + slot] = clock64();
 }
+#else
+__device__ __forceinline__ void trace_mark(long long*, int, int, int) {}
+#endif
 
 // ---- named barriers (sub-CTA sync) --------------------------------------------------------------
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {

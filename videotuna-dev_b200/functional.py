@@ -265,9 +265,10 @@ def temporal_attention(q: Tensor, k: Tensor, v: Tensor, softmax_scale: Optional[
 def ln_modulate(x: Tensor, shift: Optional[Tensor] = None, scale: Optional[Tensor] = None,
                 weight: Optional[Tensor] = None, bias: Optional[Tensor] = None, eps: float = 1e-6) -> Tensor:
     """modulate(LayerNorm(x), shift, scale) in one pass (hunyuan modulate_layers.py:31-49 after nn.LayerNorm;
-    wan model.py:294-296). x (B,L,C) bf16; shift/scale (B,C) or (B,1,C)."""
-    _require(x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 3 and x.shape[-1] % 8 == 0,
-             "ln_modulate needs a CUDA bf16 (B,L,C) tensor")
+    wan model.py:294-296). x (B,L,C) bf16 or fp32 (Wan's fp32 residual stream); the result is bf16, ready for the
+    following Linear; shift/scale (B,C) or (B,1,C)."""
+    _require(x.is_cuda and x.dtype in (torch.bfloat16, torch.float32) and x.dim() == 3 and x.shape[-1] % 8 == 0,
+             "ln_modulate needs a CUDA bf16 or fp32 (B,L,C) tensor")
     B, _, Cc = x.shape
     sc = None if scale is None else scale.reshape(B, Cc)
     sh = None if shift is None else shift.reshape(B, Cc)
@@ -284,8 +285,8 @@ def layer_norm(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], eps:
 
 def gate_residual(x: Tensor, branch: Tensor, gate: Optional[Tensor] = None) -> Tensor:
     """x + apply_gate(branch, gate) (hunyuan modulate_layers.py:52-68, models.py:231; wan model.py:298)."""
-    _require(x.is_cuda and x.dtype == torch.bfloat16 and branch.dtype == torch.bfloat16 and x.dim() == 3,
-             "gate_residual needs CUDA bf16 (B,L,C) tensors")
+    _require(x.is_cuda and x.dtype in (torch.bfloat16, torch.float32) and branch.dtype == torch.bfloat16
+             and x.dim() == 3, "gate_residual needs a CUDA bf16/fp32 (B,L,C) x and a bf16 branch")
     B, _, Cc = x.shape
     g = None if gate is None else gate.reshape(B, Cc)
     return ops.gate_residual_fwd(x, branch, g)

@@ -38,6 +38,17 @@ def _check_bf16_cuda(name: str, t: Tensor):
         raise RuntimeError(f"b200vt: {name} must be bfloat16, got {t.dtype}")
 
 
+def _xdtype(name: str, t: Tensor) -> int:
+    """x_dtype code of the row kernels: 0 = bf16, 1 = fp32 (Wan keeps its residual stream in fp32)."""
+    if not t.is_cuda:
+        raise RuntimeError(f"b200vt: {name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype == torch.bfloat16:
+        return 0
+    if t.dtype == torch.float32:
+        return 1
+    raise RuntimeError(f"b200vt: {name} must be bfloat16 or float32, got {t.dtype}")
+
+
 def _blhd(t: Tensor) -> Tensor:
     """Return t (B,L,H,D) with unit head-dim stride and 16-byte aligned strides/base; copy only if it is not."""
     ok = t.stride(3) == 1 and all(s % 8 == 0 for s in t.stride()[:3]) and t.data_ptr() % 16 == 0
@@ -181,24 +192,24 @@ temporal_attn_fwd.register_autograd(_ta_backward, setup_context=_ta_setup)
 @torch.library.custom_op("b200vt::ln_modulate_fwd", mutates_args=(), device_types="cuda")
 def ln_modulate_fwd(x: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor], scale: Optional[Tensor],
                     shift: Optional[Tensor], eps: float) -> Tuple[Tensor, Tensor, Tensor]:
-    """x (B,L,C) bf16; gamma/beta (C); scale/shift (B,C). Returns y, mean (B*L), rstd (B*L)."""
-    _check_bf16_cuda("x", x)
+    """x (B,L,C) bf16 or fp32; gamma/beta (C); scale/shift (B,C). Returns y (bf16), mean (B*L), rstd (B*L)."""
+    xd = _xdtype("x", x)
     x = x.contiguous()
     B, L, Cc = x.shape
-    y = torch.empty_like(x)
+    y = torch.empty((B, L, Cc), dtype=torch.bfloat16, device=x.device)
     mean = torch.empty((B * L,), dtype=torch.float32, device=x.device)
     rstd = torch.empty_like(mean)
     g, b, sc, sh = _f32(gamma), _f32(beta), _f32(scale), _f32(shift)
     with torch.cuda.device(x.device):
         _lib.call("vt_ln_modulate_fwd", _ptr(x), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(g), _ptr(b), _ptr(sc), _ptr(sh),
-                  B, L, Cc, float(eps), _stream())
+                  B, L, Cc, float(eps), xd, _stream())
     return y, mean, rstd
 
 
 @ln_modulate_fwd.register_fake
 def _(x, gamma, beta, scale, shift, eps):
     B, L, Cc = x.shape
-    return torch.empty_like(x, memory_format=torch.contiguous_format), x.new_empty((B * L,), dtype=torch.float32), \
+    return x.new_empty((B, L, Cc), dtype=torch.bfloat16), x.new_empty((B * L,), dtype=torch.float32), \
         x.new_empty((B * L,), dtype=torch.float32)
 
 
@@ -208,6 +219,9 @@ def ln_modulate_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Op
                     need_mod: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
     """Returns dx and fp32 (dgamma, dbeta, dscale, dshift); unused ones are empty (0-element) tensors."""
     dy, x = dy.contiguous(), x.contiguous()
+    if dy.dtype != torch.bfloat16:
+        dy = dy.to(torch.bfloat16)
+    xd = _xdtype("x", x)
     B, L, Cc = x.shape
     dx = torch.empty_like(x)
     dev = x.device
@@ -219,7 +233,7 @@ def ln_modulate_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Op
     with torch.cuda.device(dev):
         _lib.call("vt_ln_modulate_bwd", _ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(g), _ptr(b), _ptr(sc),
                   _ptr(dgamma) if need_affine else None, _ptr(dbeta) if need_affine else None,
-                  _ptr(dscale) if need_mod else None, _ptr(dshift) if need_mod else None, B, L, Cc, _stream())
+                  _ptr(dscale) if need_mod else None, _ptr(dshift) if need_mod else None, B, L, Cc, xd, _stream())
     return dx, dgamma, dbeta, dscale, dshift
 
 
@@ -265,15 +279,15 @@ ln_modulate_fwd.register_autograd(_lnm_backward, setup_context=_lnm_setup)
 # =====================================================================================================================
 @torch.library.custom_op("b200vt::gate_residual_fwd", mutates_args=(), device_types="cuda")
 def gate_residual_fwd(x: Tensor, branch: Tensor, gate: Optional[Tensor]) -> Tensor:
-    """y = x + branch * gate[:, None, :];  x, branch (B,L,C) bf16, gate (B,C) or None."""
-    _check_bf16_cuda("x", x)
+    """y = x + branch * gate[:, None, :];  x (B,L,C) bf16 or fp32 (y likewise), branch (B,L,C) bf16, gate (B,C) or None."""
+    xd = _xdtype("x", x)
     _check_bf16_cuda("branch", branch)
     x, branch = x.contiguous(), branch.contiguous()
     B, L, Cc = x.shape
     y = torch.empty_like(x)
     g = _f32(gate)
     with torch.cuda.device(x.device):
-        _lib.call("vt_gate_residual_fwd", _ptr(x), _ptr(branch), _ptr(y), _ptr(g), B, L, Cc, _stream())
+        _lib.call("vt_gate_residual_fwd", _ptr(x), _ptr(branch), _ptr(y), _ptr(g), B, L, Cc, xd, _stream())
     return y
 
 
@@ -285,20 +299,21 @@ def _(x, branch, gate):
 @torch.library.custom_op("b200vt::gate_residual_bwd", mutates_args=(), device_types="cuda")
 def gate_residual_bwd(dy: Tensor, branch: Tensor, gate: Optional[Tensor], need_dgate: bool) -> Tuple[Tensor, Tensor]:
     dy, branch = dy.contiguous(), branch.contiguous()
+    xd = _xdtype("dy", dy)
     B, L, Cc = dy.shape
-    dbranch = torch.empty_like(dy)
+    dbranch = torch.empty((B, L, Cc), dtype=torch.bfloat16, device=dy.device)
     dgate = torch.zeros((B, Cc), dtype=torch.float32, device=dy.device) if need_dgate else dy.new_empty((0,), dtype=torch.float32)
     g = _f32(gate)
     with torch.cuda.device(dy.device):
         _lib.call("vt_gate_residual_bwd", _ptr(dy), _ptr(branch), _ptr(dbranch), _ptr(g),
-                  _ptr(dgate) if need_dgate else None, B, L, Cc, _stream())
+                  _ptr(dgate) if need_dgate else None, B, L, Cc, xd, _stream())
     return dbranch, dgate
 
 
 @gate_residual_bwd.register_fake
 def _(dy, branch, gate, need_dgate):
     B, L, Cc = dy.shape
-    return torch.empty_like(dy, memory_format=torch.contiguous_format), \
+    return dy.new_empty((B, L, Cc), dtype=torch.bfloat16), \
         dy.new_empty((B, Cc) if need_dgate else (0,), dtype=torch.float32)
 
 

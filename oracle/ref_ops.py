@@ -298,6 +298,76 @@ def groupnorm_silu(x: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor], g
 # ---------------------------------------------------------------------------------------------------------------------
 # error metrics used by the parity tests (tensor-normalised error; gradient cosine)
 # ---------------------------------------------------------------------------------------------------------------------
+# ---------------------------------------------------------------------------------------------------------------------
+# diffusers 0.32.2 attention processors — PARITY UNPINNED (the wheel is neither vendored by the reference nor installed
+# here): restated from the published algorithm; anchored on the reference's call sites cogvideo_hf/cogvideo_pl.py:123,
+# 862-868 and hyvideo_t2v/hunyuanvideo.py:209, 946-955 and on the in-tree SAT description of the same model
+# (cogvideo_sat/dit_video_concat.py:263-427: text tokens first and un-rotated, interleaved rotate_half, per-head
+# LayerNorm of q and k).
+# ---------------------------------------------------------------------------------------------------------------------
+def diffusers_cogvideox_attention(hidden: Tensor, encoder_hidden: Tensor, wq: Tensor, wk: Tensor, wv: Tensor, bq, bk, bv,
+                                  wo: Tensor, bo, heads: int, ln_q=None, ln_k=None, rotary=None, eps: float = 1e-6):
+    """CogVideoXAttnProcessor2_0: x = [text; video]; q,k,v = Linear(x); per-head LayerNorm(q), LayerNorm(k); RoPE on the
+    video tokens; SDPA; to_out; split back into (video, text). ln_q/ln_k: (weight, bias) or None; rotary: (cos, sin)."""
+    T = encoder_hidden.shape[1]
+    x = torch.cat([encoder_hidden, hidden], dim=1)
+    B, S, _ = x.shape
+    q = F.linear(x, wq, bq).view(B, S, heads, -1)
+    k = F.linear(x, wk, bk).view(B, S, heads, -1)
+    v = F.linear(x, wv, bv).view(B, S, heads, -1)
+    D = q.shape[-1]
+    if ln_q is not None:
+        q = F.layer_norm(q, (D,), ln_q[0], ln_q[1], eps)
+    if ln_k is not None:
+        k = F.layer_norm(k, (D,), ln_k[0], ln_k[1], eps)
+    if rotary is not None:
+        q = torch.cat([q[:, :T], hunyuan_apply_rotary_emb(q[:, T:], *rotary)], dim=1)
+        k = torch.cat([k[:, :T], hunyuan_apply_rotary_emb(k[:, T:], *rotary)], dim=1)
+    o = sdpa_blhd(q, k, v).reshape(B, S, heads * D)
+    o = F.linear(o, wo, bo)
+    return o[:, T:], o[:, :T]
+
+
+def diffusers_hunyuan_attention(hidden: Tensor, encoder_hidden: Tensor, p: dict, heads: int, rotary=None,
+                                valid_len: Optional[Tensor] = None, eps: float = 1e-6):
+    """HunyuanVideoAttnProcessor2_0, double-stream form (p has add_q/add_k/add_v projections) or single-stream form
+    (hidden already is [video; text], encoder_hidden marks the text length). Per-head RMSNorm weights p["norm_q"] etc.;
+    RoPE on the video tokens; SDPA under the reference's square validity mask (i < valid) & (j < valid)
+    (hunyuanvideo.py builds it from the prompt mask); to_out / to_add_out when present."""
+    double = "add_q" in p
+    T = encoder_hidden.shape[1]
+    x = hidden if double else torch.cat([hidden, encoder_hidden], dim=1)
+    B, S1, _ = x.shape
+    n_img = S1 if double else S1 - T
+
+    def proj(name, t):
+        return F.linear(t, p[name][0], p[name][1]).view(t.shape[0], t.shape[1], heads, -1)
+
+    q, k, v = proj("q", x), proj("k", x), proj("v", x)
+    if "norm_q" in p:
+        q, k = hunyuan_rmsnorm(q, p["norm_q"], eps), hunyuan_rmsnorm(k, p["norm_k"], eps)
+    if rotary is not None:
+        q = torch.cat([hunyuan_apply_rotary_emb(q[:, :n_img], *rotary), q[:, n_img:]], dim=1)
+        k = torch.cat([hunyuan_apply_rotary_emb(k[:, :n_img], *rotary), k[:, n_img:]], dim=1)
+    if double:
+        eq, ek, ev = proj("add_q", encoder_hidden), proj("add_k", encoder_hidden), proj("add_v", encoder_hidden)
+        if "norm_added_q" in p:
+            eq, ek = hunyuan_rmsnorm(eq, p["norm_added_q"], eps), hunyuan_rmsnorm(ek, p["norm_added_k"], eps)
+        q, k, v = torch.cat([q, eq], 1), torch.cat([k, ek], 1), torch.cat([v, ev], 1)
+    S = q.shape[1]
+    mask = None
+    if valid_len is not None:
+        idx = torch.arange(S)
+        mask = (idx[None, None, :] < valid_len[:, None, None]).expand(B, S, S)[:, None]  # keys; padded rows are discarded
+    o = sdpa_blhd(q, k, v, attn_mask=mask).reshape(B, S, -1)
+    hs, ehs = o[:, :S - T], o[:, S - T:]
+    if "out" in p:
+        hs = F.linear(hs, p["out"][0], p["out"][1])
+    if "add_out" in p:
+        ehs = F.linear(ehs, p["add_out"][0], p["add_out"][1])
+    return hs, ehs
+
+
 def max_rel_err(y: Tensor, ref: Tensor) -> float:
     y, ref = y.double().cpu(), ref.double().cpu()
     return float((y - ref).abs().max() / ref.abs().max().clamp_min(1e-30))

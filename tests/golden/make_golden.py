@@ -309,6 +309,137 @@ def golden_wan(gen):
                            out=y.detach()))
 
 
+def golden_block_grads():
+    """Forward + backward of whole reference blocks (fp32, CPU) on the state dicts and inputs of the fixtures above, plus
+    a ResBlock: outputs, input gradients and a few parameter gradients for the block-level drop-ins (b200vt.blocks).
+    Own generator; reads hunyuan_blocks.pt / wan_block.pt / lvdm_transformers.pt, so run after the others."""
+    gen = torch.Generator().manual_seed(SEED + 11)
+    out = {}
+
+    def load(name):
+        return torch.load(os.path.join(OUT, name + ".pt"))
+
+    def f32(t):
+        return t.float() if t.is_floating_point() else t
+
+    def grads_of(mod, names):
+        # large weight gradients are stored in bf16 (they are compared by cosine similarity); small ones stay fp32
+        params = dict(mod.named_parameters())
+        return {n: (params[n].grad.detach().to(torch.bfloat16) if params[n].numel() > 16384 else params[n].grad.detach().clone())
+                for n in names}
+
+    with torch.enable_grad():
+        # ---- Hunyuan double / single stream blocks -----------------------------------------------------------
+        M = importlib.import_module("videotuna.models.hunyuan.hyvideo_t2v.modules.models")
+        g = load("hunyuan_blocks")
+        dbl = M.MMDoubleStreamBlock(g["hidden"], g["heads"], mlp_width_ratio=g["mlp_width_ratio"], qk_norm=True,
+                                    qk_norm_type="rms", qkv_bias=True)
+        dbl.load_state_dict({k: f32(v) for k, v in g["dbl_sd"].items()})
+        sgl = M.MMSingleStreamBlock(g["hidden"], g["heads"], mlp_width_ratio=g["mlp_width_ratio"], qk_norm=True,
+                                    qk_norm_type="rms")
+        sgl.load_state_dict({k: f32(v) for k, v in g["sgl_sd"].items()})
+        cu = g["cu_seqlens"]
+        segm = torch.zeros(150, dtype=torch.long)
+        segm[int(cu[1]):] = 1
+        bmask = (segm[:, None] == segm[None, :])[None, None]
+        orig = M.attention
+        M.attention = lambda q_, k_, v_, **kw: orig(q_, k_, v_, mode="torch", attn_mask=bmask)
+        try:
+            img, txt, vec = (f32(g[k]).clone().requires_grad_(True) for k in ("img", "txt", "vec"))
+            fc = (f32(g["cos"]), f32(g["sin"]))
+            io, to = dbl(img, txt, vec, cu_seqlens_q=cu, cu_seqlens_kv=cu, max_seqlen_q=150, max_seqlen_kv=150, freqs_cis=fc)
+            d_io, d_to = RN(*io.shape, generator=gen), RN(*to.shape, generator=gen)
+            torch.autograd.backward([io, to], [d_io, d_to])
+            out["hunyuan_double"] = dict(d_img_out=d_io, d_txt_out=d_to, d_img=img.grad.clone(), d_txt=txt.grad.clone(),
+                                         d_vec=vec.grad.clone(),
+                                         **grads_of(dbl, ["img_attn_qkv.weight", "img_attn_q_norm.weight",
+                                                          "txt_attn_k_norm.weight", "img_mod.linear.weight",
+                                                          "txt_attn_proj.bias"]))
+            x = torch.cat([f32(g["img"]), f32(g["txt"])], 1).clone().requires_grad_(True)
+            vec2 = f32(g["vec"]).clone().requires_grad_(True)
+            so = sgl(x, vec2, 30, cu_seqlens_q=cu, cu_seqlens_kv=cu, max_seqlen_q=150, max_seqlen_kv=150, freqs_cis=fc)
+            d_so = RN(*so.shape, generator=gen)
+            so.backward(d_so)
+            out["hunyuan_single"] = dict(d_out=d_so, d_x=x.grad.clone(), d_vec=vec2.grad.clone(),
+                                         **grads_of(sgl, ["linear1.weight", "q_norm.weight", "k_norm.weight",
+                                                          "modulation.linear.bias"]))
+        finally:
+            M.attention = orig
+
+        # ---- Wan attention block -----------------------------------------------------------------------------
+        pkg = types.ModuleType("wan_ref_modules")
+        pkg.__path__ = [os.path.join(REF, "videotuna/models/wan/wan/modules")]
+        sys.modules["wan_ref_modules"] = pkg
+        model = importlib.import_module("wan_ref_modules.model")
+
+        def sdpa_flash(q, k, v, q_lens=None, k_lens=None, dropout_p=0.0, softmax_scale=None, q_scale=None, causal=False,
+                       window_size=(-1, -1), deterministic=False, dtype=torch.bfloat16, version=None):
+            o = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2))
+            return o.transpose(1, 2).contiguous()
+
+        model.flash_attention = sdpa_flash
+        w = load("wan_block")
+        blk = model.WanAttentionBlock("t2v_cross_attn", w["dim"], w["ffn"], w["heads"], window_size=(-1, -1), qk_norm=True,
+                                      cross_attn_norm=True, eps=1e-6)
+        blk.load_state_dict({k: f32(v) for k, v in w["sd"].items()})
+        x = f32(w["x"]).clone().requires_grad_(True)
+        e = f32(w["e"]).clone().requires_grad_(True)
+        ctx = f32(w["context"]).clone().requires_grad_(True)
+        freqs_b = torch.cat([model.rope_params(1024, 128 - 4 * (128 // 6)), model.rope_params(1024, 2 * (128 // 6)),
+                             model.rope_params(1024, 2 * (128 // 6))], dim=1)
+        y = blk(x, e, torch.tensor([x.shape[1]]), w["grid"], freqs_b, ctx, None)
+        assert torch.allclose(y, f32(w["out"]), atol=1e-5)
+        d_y = RN(*y.shape, generator=gen)
+        y.backward(d_y)
+        out["wan_block"] = dict(d_out=d_y, d_x=x.grad.clone(), d_e=e.grad.clone(), d_context=ctx.grad.clone(),
+                                **grads_of(blk, ["modulation", "self_attn.norm_q.weight", "self_attn.q.weight",
+                                                 "cross_attn.norm_k.weight", "norm3.weight", "ffn.0.bias"]))
+
+        # ---- lvdm Spatial / Temporal transformer, ResBlock ---------------------------------------------------
+        from videotuna.models.lvdm.modules import attention as A
+        from videotuna.models.lvdm.modules.networks import openaimodel3d as O3
+        lv = load("lvdm_transformers")
+        st = A.SpatialTransformer(**lv["spatial"]["kw"])
+        st.load_state_dict({k: f32(v) for k, v in lv["spatial"]["sd"].items()})
+        xs = f32(lv["spatial"]["x"]).clone().requires_grad_(True)
+        cs = f32(lv["spatial"]["context"]).clone().requires_grad_(True)
+        ys = st(xs, cs)
+        d_ys = RN(*ys.shape, generator=gen)
+        ys.backward(d_ys)
+        out["lvdm_spatial"] = dict(d_out=d_ys, d_x=xs.grad.clone(), d_context=cs.grad.clone(),
+                                   **grads_of(st, ["norm.weight", "proj_in.weight", "transformer_blocks.0.norm2.weight",
+                                                   "transformer_blocks.0.attn2.to_k.weight"]))
+        tt = A.TemporalTransformer(**lv["temporal"]["kw"])
+        tt.load_state_dict({k: f32(v) for k, v in lv["temporal"]["sd"].items()})
+        xt = f32(lv["temporal"]["x"]).clone().requires_grad_(True)
+        yt = tt(xt)
+        d_yt = RN(*yt.shape, generator=gen)
+        yt.backward(d_yt)
+        out["lvdm_temporal"] = dict(d_out=d_yt, d_x=xt.grad.clone(),
+                                    **grads_of(tt, ["norm.bias", "transformer_blocks.0.norm1.weight",
+                                                    "transformer_blocks.0.attn1.to_q.weight"]))
+        rkw = dict(channels=64, emb_channels=96, dropout=0.0, out_channels=128, dims=2, use_checkpoint=False,
+                   use_temporal_conv=False)
+        rb = O3.ResBlock(**rkw)
+        dezero(rb, gen)
+        with torch.no_grad():
+            for n_, p_ in rb.named_parameters():
+                if n_ in ("in_layers.0.weight", "out_layers.0.weight"):
+                    p_.copy_(1 + 0.1 * RN(p_.shape, generator=gen))
+                if n_ in ("in_layers.0.bias", "out_layers.0.bias"):
+                    p_.copy_(0.1 * RN(p_.shape, generator=gen))
+        round_params(rb)
+        xr = r16(RN(2, 64, 6, 10, generator=gen) * 1.5 + 0.3).requires_grad_(True)
+        er = RN(2, 96, generator=gen).requires_grad_(True)
+        yr = rb(xr, er)
+        d_yr = RN(*yr.shape, generator=gen)
+        yr.backward(d_yr)
+        out["lvdm_resblock"] = dict(kw=rkw, sd=sd(rb), x=xr.detach().clone(), emb=er.detach().clone(), out=yr.detach(),
+                                    d_out=d_yr, d_x=xr.grad.clone(), d_emb=er.grad.clone(),
+                                    **grads_of(rb, ["in_layers.0.weight", "out_layers.0.bias", "in_layers.2.weight"]))
+    save("block_grads", out)
+
+
 def main():
     install_shims()
     torch.manual_seed(SEED)
@@ -318,6 +449,7 @@ def main():
     golden_hunyuan(gen)
     golden_wan(gen)
     golden_lvdm_temporal()
+    golden_block_grads()
 
 
 if __name__ == "__main__":

@@ -37,3 +37,239 @@ class CrossAttentionShell(nn.Module):
         sd = {k: v for k, v in case["sd"].items() if not k.startswith("relative_position")}
         m.load_state_dict({k: v.float() for k, v in sd.items()}, strict=True)
         return m.to(device=device, dtype=dtype)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Shells of the reference BLOCKS: same attribute and parameter names as the reference constructors create, with the
+# drop-in forwards of b200vt.blocks bound the way patch.patch_blocks() binds them onto the real classes.
+# ---------------------------------------------------------------------------------------------------------------------
+def _load(module, sd, device, dtype=torch.bfloat16):
+    module.load_state_dict({k: (v.float() if v.is_floating_point() else v) for k, v in sd.items()}, strict=True)
+    return module.to(device=device, dtype=dtype)
+
+
+class RMSNormShell(nn.Module):
+    """hunyuan norm_layers.RMSNorm / wan WanRMSNorm: .weight, .eps (the forward is never called by the drop-ins)."""
+
+    def __init__(self, dim, eps=1e-6):
+        super().__init__()
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(dim))
+
+
+class ModulateDiTShell(nn.Module):
+    def __init__(self, hidden, factor):
+        super().__init__()
+        self.act = nn.SiLU()
+        self.linear = nn.Linear(hidden, factor * hidden)
+
+    def forward(self, x):
+        return self.linear(self.act(x))
+
+
+class MLPShell(nn.Module):
+    def __init__(self, hidden, mlp_hidden):
+        super().__init__()
+        self.fc1 = nn.Linear(hidden, mlp_hidden)
+        self.act = nn.GELU(approximate="tanh")
+        self.fc2 = nn.Linear(mlp_hidden, hidden)
+
+    def forward(self, x):
+        return self.fc2(self.act(self.fc1(x)))
+
+
+class HunyuanDoubleShell(nn.Module):
+    """MMDoubleStreamBlock.__init__ (hyvideo_t2v/modules/models.py:28-128)."""
+
+    def __init__(self, hidden, heads, mlp_width_ratio):
+        super().__init__()
+        from b200vt import blocks
+        self.heads_num = heads
+        d = hidden // heads
+        for s in ("img", "txt"):
+            setattr(self, f"{s}_mod", ModulateDiTShell(hidden, 6))
+            setattr(self, f"{s}_norm1", nn.LayerNorm(hidden, elementwise_affine=False, eps=1e-6))
+            setattr(self, f"{s}_attn_qkv", nn.Linear(hidden, 3 * hidden))
+            setattr(self, f"{s}_attn_q_norm", RMSNormShell(d))
+            setattr(self, f"{s}_attn_k_norm", RMSNormShell(d))
+            setattr(self, f"{s}_attn_proj", nn.Linear(hidden, hidden))
+            setattr(self, f"{s}_norm2", nn.LayerNorm(hidden, elementwise_affine=False, eps=1e-6))
+            setattr(self, f"{s}_mlp", MLPShell(hidden, int(hidden * mlp_width_ratio)))
+        self.hybrid_seq_parallel_attn = None
+        self._fwd = blocks.hunyuan_double_block_forward
+
+    def forward(self, *a, **k):
+        return self._fwd(self, *a, **k)
+
+
+class HunyuanSingleShell(nn.Module):
+    """MMSingleStreamBlock.__init__ (models.py:262-318)."""
+
+    def __init__(self, hidden, heads, mlp_width_ratio):
+        super().__init__()
+        from b200vt import blocks
+        self.hidden_size, self.heads_num = hidden, heads
+        self.mlp_hidden_dim = int(hidden * mlp_width_ratio)
+        d = hidden // heads
+        self.scale = d ** -0.5
+        self.linear1 = nn.Linear(hidden, 3 * hidden + self.mlp_hidden_dim)
+        self.linear2 = nn.Linear(hidden + self.mlp_hidden_dim, hidden)
+        self.q_norm, self.k_norm = RMSNormShell(d), RMSNormShell(d)
+        self.pre_norm = nn.LayerNorm(hidden, elementwise_affine=False, eps=1e-6)
+        self.mlp_act = nn.GELU(approximate="tanh")
+        self.modulation = ModulateDiTShell(hidden, 3)
+        self.hybrid_seq_parallel_attn = None
+        self._fwd = blocks.hunyuan_single_block_forward
+
+    def forward(self, *a, **k):
+        return self._fwd(self, *a, **k)
+
+
+class WanAttnShell(nn.Module):
+    """WanSelfAttention / WanT2VCrossAttention.__init__ (wan/wan/modules/model.py:102-124)."""
+
+    def __init__(self, dim, heads, cross, eps=1e-6):
+        super().__init__()
+        from b200vt import blocks
+        self.dim, self.num_heads, self.head_dim = dim, heads, dim // heads
+        self.window_size, self.qk_norm, self.eps = (-1, -1), True, eps
+        self.q, self.k, self.v, self.o = (nn.Linear(dim, dim) for _ in range(4))
+        self.norm_q, self.norm_k = RMSNormShell(dim, eps), RMSNormShell(dim, eps)
+        self._fwd = blocks.wan_t2v_cross_attention_forward if cross else blocks.wan_self_attention_forward
+
+    def forward(self, *a, **k):
+        return self._fwd(self, *a, **k)
+
+
+class WanBlockShell(nn.Module):
+    """WanAttentionBlock.__init__ (model.py:230-272), t2v cross-attention, cross_attn_norm=True."""
+
+    def __init__(self, dim, ffn, heads, eps=1e-6):
+        super().__init__()
+        from b200vt import blocks
+        self.dim, self.ffn_dim, self.num_heads, self.eps = dim, ffn, heads, eps
+        self.norm1 = nn.LayerNorm(dim, eps, elementwise_affine=False)
+        self.self_attn = WanAttnShell(dim, heads, cross=False, eps=eps)
+        self.norm3 = nn.LayerNorm(dim, eps, elementwise_affine=True)
+        self.cross_attn = WanAttnShell(dim, heads, cross=True, eps=eps)
+        self.norm2 = nn.LayerNorm(dim, eps, elementwise_affine=False)
+        self.ffn = nn.Sequential(nn.Linear(dim, ffn), nn.GELU(approximate="tanh"), nn.Linear(ffn, dim))
+        self.modulation = nn.Parameter(torch.zeros(1, 6, dim))
+        self._fwd = blocks.wan_attention_block_forward
+
+    def forward(self, *a, **k):
+        return self._fwd(self, *a, **k)
+
+
+class GEGLUShell(nn.Module):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+    def forward(self, x):
+        x, gate = self.proj(x).chunk(2, dim=-1)
+        return x * torch.nn.functional.gelu(gate)
+
+
+class FeedForwardShell(nn.Module):
+    """lvdm FeedForward(dim, glu=True) (attention.py:222-242): net = [GEGLU, Dropout, Linear]."""
+
+    def __init__(self, dim, mult=4):
+        super().__init__()
+        self.net = nn.Sequential(GEGLUShell(dim, dim * mult), nn.Dropout(0.0), nn.Linear(dim * mult, dim))
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class BasicBlockShell(nn.Module):
+    """lvdm BasicTransformerBlock.__init__ (attention.py:245-281); forward reproduces the reference's argument plumbing
+    (:283-297, incl. dropping the context when a mask is given) without the checkpoint wrapper."""
+
+    def __init__(self, dim, n_heads, d_head, context_dim=None):
+        super().__init__()
+        from b200vt import blocks, functional
+        self.disable_self_attn = False
+        self.attn1 = CrossAttentionShell(dim, None, n_heads, d_head)
+        self.ff = FeedForwardShell(dim)
+        self.attn2 = CrossAttentionShell(dim, context_dim, n_heads, d_head)
+        for a in (self.attn1, self.attn2):
+            a.forward = functional.lvdm_cross_attention_forward.__get__(a)
+        self.norm1, self.norm2, self.norm3 = nn.LayerNorm(dim), nn.LayerNorm(dim), nn.LayerNorm(dim)
+        self.checkpoint = False
+        self._fwd = blocks.lvdm_basic_block_forward
+
+    def forward(self, x, context=None, mask=None):
+        if mask is not None:
+            return self._fwd(self, x, mask=mask)
+        return self._fwd(self, x, context) if context is not None else self._fwd(self, x)
+
+
+class SpatialTransformerShell(nn.Module):
+    """lvdm SpatialTransformer.__init__ (attention.py:323-374), use_linear=True."""
+
+    def __init__(self, in_channels, n_heads, d_head, depth=1, context_dim=None, use_linear=True, use_checkpoint=False):
+        super().__init__()
+        from b200vt import blocks
+        inner = n_heads * d_head
+        self.in_channels = in_channels
+        self.norm = nn.GroupNorm(32, in_channels, eps=1e-6, affine=True)
+        self.proj_in = nn.Linear(in_channels, inner)
+        self.transformer_blocks = nn.ModuleList(BasicBlockShell(inner, n_heads, d_head, context_dim) for _ in range(depth))
+        self.proj_out = nn.Linear(inner, in_channels)
+        self.use_linear = use_linear
+        self._fwd = blocks.lvdm_spatial_transformer_forward
+
+    def forward(self, *a, **k):
+        return self._fwd(self, *a, **k)
+
+
+class TemporalTransformerShell(nn.Module):
+    """lvdm TemporalTransformer.__init__ (attention.py:403-473), use_linear=True, only_self_att=True."""
+
+    def __init__(self, in_channels, n_heads, d_head, depth=1, use_linear=True, use_checkpoint=False, only_self_att=True,
+                 temporal_length=None, causal_attention=False):
+        super().__init__()
+        from b200vt import blocks
+        inner = n_heads * d_head
+        self.only_self_att, self.causal_attention, self.relative_position = only_self_att, causal_attention, False
+        self.in_channels = in_channels
+        self.norm = nn.GroupNorm(32, in_channels, eps=1e-6, affine=True)
+        self.proj_in = nn.Linear(in_channels, inner)
+        self.transformer_blocks = nn.ModuleList(BasicBlockShell(inner, n_heads, d_head, None) for _ in range(depth))
+        self.proj_out = nn.Linear(inner, in_channels)
+        self.use_linear = use_linear
+        if causal_attention:
+            self.mask = torch.tril(torch.ones([1, temporal_length, temporal_length]))
+        self._fwd = blocks.lvdm_temporal_transformer_forward
+
+    def forward(self, *a, **k):
+        return self._fwd(self, *a, **k)
+
+
+class ResBlockShell(nn.Module):
+    """lvdm ResBlock.__init__ (openaimodel3d.py:139-210), dims=2, no up/down-sampling, no temporal conv."""
+
+    def __init__(self, channels, emb_channels, dropout, out_channels=None, dims=2, use_checkpoint=False,
+                 use_temporal_conv=False):
+        super().__init__()
+        from b200vt import blocks
+        self.channels, self.emb_channels, self.out_channels = channels, emb_channels, out_channels or channels
+        self.use_checkpoint, self.use_scale_shift_norm, self.use_temporal_conv = use_checkpoint, False, use_temporal_conv
+        self.updown = False
+        self.in_layers = nn.Sequential(nn.GroupNorm(32, channels), nn.SiLU(),
+                                       nn.Conv2d(channels, self.out_channels, 3, padding=1))
+        self.h_upd = self.x_upd = nn.Identity()
+        self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_channels, self.out_channels))
+        self.out_layers = nn.Sequential(nn.GroupNorm(32, self.out_channels), nn.SiLU(), nn.Dropout(p=dropout),
+                                        nn.Conv2d(self.out_channels, self.out_channels, 3, padding=1))
+        self.skip_connection = (nn.Identity() if self.out_channels == channels
+                                else nn.Conv2d(channels, self.out_channels, 1))
+        self._fwd = blocks.lvdm_resblock_forward
+
+    def forward(self, x, emb, batch_size=None):
+        return self._fwd(self, x, emb, batch_size)
+
+
+def load_shell(module, sd, device, dtype=torch.bfloat16):
+    return _load(module, sd, device, dtype)

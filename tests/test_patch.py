@@ -69,3 +69,59 @@ def test_wan_sp_rope_tables_match_reference_slicing(monkeypatch):
         torch.testing.assert_close(sin[: hi - lo], full_sin[lo:hi])
         if hi - lo < 32:  # padding rows multiply by 1 + 0i (pad_freqs, xdit_context_parallel.py:12-22)
             assert torch.all(cos[hi - lo:] == 1) and torch.all(sin[hi - lo:] == 0)
+
+
+@needs_ref
+def test_block_hooks_install_fall_back_and_restore(shims):
+    """patch_blocks(): every block-level forward is replaced on the reference classes; on CPU fp32 tensors the fused
+    body raises Unsupported and the ORIGINAL forward runs, so results equal the unpatched reference bit for bit."""
+    import importlib
+    import b200vt.patch as P
+    from videotuna.models.lvdm.modules import attention as A
+    from videotuna.models.lvdm.modules.networks import openaimodel3d as O3
+    M = importlib.import_module("videotuna.models.hunyuan.hyvideo_t2v.modules.models")
+    torch.manual_seed(0)
+    st = A.SpatialTransformer(in_channels=64, n_heads=1, d_head=64, depth=1, context_dim=32, use_linear=True,
+                              use_checkpoint=False)
+    x, ctx = torch.randn(2, 64, 4, 4), torch.randn(2, 7, 32)
+    rb = O3.ResBlock(channels=32, emb_channels=16, dropout=0.0, out_channels=32, dims=2, use_checkpoint=False)
+    xr, er = torch.randn(2, 32, 4, 4), torch.randn(2, 16)
+    want_st, want_rb = st(x, ctx), rb(xr, er)
+    originals = (A.SpatialTransformer.forward, A.BasicTransformerBlock._forward, O3.ResBlock._forward,
+                 M.MMDoubleStreamBlock.forward)
+    done = P.patch_blocks(wan=False)
+    assert done["lvdm"] == 4 and done["hunyuan"] >= 3
+    assert all(getattr(f, "_b200vt_patched", False) for f in (A.SpatialTransformer.forward, A.TemporalTransformer.forward,
+                                                               A.BasicTransformerBlock._forward, O3.ResBlock._forward,
+                                                               M.MMDoubleStreamBlock.forward, M.MMSingleStreamBlock.forward,
+                                                               M.parallel_attention))
+    torch.testing.assert_close(st(x, ctx), want_st, rtol=0, atol=0)
+    torch.testing.assert_close(rb(xr, er), want_rb, rtol=0, atol=0)
+    P.unpatch_videotuna()
+    assert (A.SpatialTransformer.forward, A.BasicTransformerBlock._forward, O3.ResBlock._forward,
+            M.MMDoubleStreamBlock.forward) == originals
+
+
+def test_diffusers_processors_are_installed_by_duck_typing():
+    """set_diffusers_processors() keys on the stock processor's class name and the `set_processor` protocol only
+    (diffusers is not installed here); anything unsupported goes back to the stock processor."""
+    import b200vt.patch as P
+
+    class CogVideoXAttnProcessor2_0:  # stand-in for the stock processor
+        def __call__(self, attn, hidden_states, encoder_hidden_states, attention_mask=None, image_rotary_emb=None):
+            return "stock", None
+
+    class Attention(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.processor = CogVideoXAttnProcessor2_0()
+            self.heads = 2
+            self.to_q = self.to_k = self.to_v = torch.nn.Linear(128, 128)
+
+        def set_processor(self, p):
+            self.processor = p
+
+    model = torch.nn.Sequential(Attention(), Attention())
+    assert P.set_diffusers_processors(model) == 2
+    hs, ehs = torch.randn(1, 8, 128), torch.randn(1, 4, 128)
+    assert model[0].processor(model[0], hs, ehs)[0] == "stock"  # CPU fp32 -> Unsupported -> stock processor

@@ -1,0 +1,484 @@
+"""Block-level drop-in forwards: the reference's transformer blocks re-expressed over the b200vt kernels.
+
+`functional.py` replaces the attention *functions*; this module replaces the `forward` of the blocks that call them, so
+that the memory-bound chain around attention (LayerNorm + adaLN modulate, QK-RMSNorm + RoPE, gated residual,
+GroupNorm + SiLU) runs in the fused row kernels instead of the reference's elementwise passes. Every function takes
+the reference module as `self` and uses only its own parameters and sub-modules (state-dict keys, LoRA targets and
+checkpoints are untouched); `patch.patch_blocks()` installs them on the reference classes. Anything outside the CUDA
+path raises `functional.Unsupported`, which the patch layer turns into a call of the original forward.
+
+reference forward                                                          replaced by
+  hunyuan MMDoubleStreamBlock.forward   hyvideo_t2v/modules/models.py:132-252   hunyuan_double_block_forward
+  hunyuan MMSingleStreamBlock.forward   hyvideo_t2v/modules/models.py:326-393   hunyuan_single_block_forward
+  wan WanSelfAttention.forward          wan/wan/modules/model.py:127-156        wan_self_attention_forward
+  wan WanT2VCrossAttention.forward      wan/wan/modules/model.py:161-181        wan_t2v_cross_attention_forward
+  wan WanI2VCrossAttention.forward      wan/wan/modules/model.py:199-225        wan_i2v_cross_attention_forward
+  wan WanAttentionBlock.forward         wan/wan/modules/model.py:274-313        wan_attention_block_forward
+  lvdm BasicTransformerBlock._forward   lvdm/modules/attention.py:299-310       lvdm_basic_block_forward
+  lvdm SpatialTransformer.forward       lvdm/modules/attention.py:376-392       lvdm_spatial_transformer_forward
+  lvdm TemporalTransformer.forward      lvdm/modules/attention.py:475-519       lvdm_temporal_transformer_forward
+  lvdm ResBlock._forward                lvdm/modules/networks/openaimodel3d.py:229-255   lvdm_resblock_forward
+  diffusers CogVideoXAttnProcessor2_0   [ext, diffusers 0.32.2]                 CogVideoXAttnProcessor
+  diffusers HunyuanVideoAttnProcessor2_0 [ext, diffusers 0.32.2]                HunyuanVideoAttnProcessor
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+from torch import Tensor, nn
+
+from . import functional as Fn
+from .functional import Unsupported, _require
+
+_BF16 = torch.bfloat16
+
+
+def _is_identity(m) -> bool:
+    return isinstance(m, nn.Identity)
+
+
+def _rms_weight(norm) -> Tuple[Optional[Tensor], float]:
+    """(weight, eps) of a reference RMSNorm (hunyuan norm_layers.py:5-59, wan model.py:70-86); Identity -> (None, 0)."""
+    if _is_identity(norm):
+        return None, 0.0
+    _require(hasattr(norm, "weight") and hasattr(norm, "eps") and not isinstance(norm, nn.LayerNorm),
+             "only RMSNorm q/k normalisation is on the CUDA path")
+    return norm.weight, float(norm.eps)
+
+
+# =====================================================================================================================
+# HunyuanVideo
+# =====================================================================================================================
+def _hy_qk(x: Tensor, norm, cos: Optional[Tensor], sin: Optional[Tensor]) -> Tensor:
+    """RMSNorm over each head + RoPE on the first cos.shape[0] tokens of a (B, L, H, D) view of the fused QKV output."""
+    w, eps = _rms_weight(norm)
+    if w is None and cos is None:
+        return x
+    return Fn.qk_rmsnorm_rope(x, w, cos, sin, per_head=True, eps=eps if w is not None else 1e-6)
+
+
+def hunyuan_parallel_attention(hybrid_seq_parallel_attn, q, k, v, img_q_len, img_kv_len, cu_seqlens_q, cu_seqlens_kv):
+    """Same signature and result as the reference `parallel_attention` (attenion.py:159-212): sequence-parallel attention
+    of the image shard + replicated valid text ("rear" joint strategy) through `hybrid_seq_parallel_attn`, and a local
+    attention of the padding tail among itself, concatenated to (B, S, H*D). Like the reference it reads
+    cu_seqlens[1] on the host (one sync per call) and assumes batch 1."""
+    n_q, n_k = int(cu_seqlens_q[1]), int(cu_seqlens_kv[1])
+    attn1 = hybrid_seq_parallel_attn(
+        None, q[:, :img_q_len], k[:, :img_kv_len], v[:, :img_kv_len], dropout_p=0.0, causal=False,
+        joint_tensor_query=q[:, img_q_len:n_q], joint_tensor_key=k[:, img_kv_len:n_k],
+        joint_tensor_value=v[:, img_kv_len:n_k], joint_strategy="rear")
+    parts = [attn1]
+    if q.shape[1] > n_q:
+        parts.append(Fn.attention_blhd(q[:, n_q:], k[:, n_k:], v[:, n_k:]))
+    attn = torch.cat(parts, dim=1) if len(parts) > 1 else attn1
+    b, s, a, d = attn.shape
+    return attn.reshape(b, s, a * d)
+
+
+def _hy_attention(self, q, k, v, img_len, cu_seqlens_q, cu_seqlens_kv, max_seqlen_q, max_seqlen_kv, batch):
+    if not getattr(self, "hybrid_seq_parallel_attn", None):
+        return Fn.hunyuan_attention(q, k, v, cu_seqlens_q=cu_seqlens_q, cu_seqlens_kv=cu_seqlens_kv,
+                                    max_seqlen_q=max_seqlen_q, max_seqlen_kv=max_seqlen_kv, batch_size=batch)
+    return hunyuan_parallel_attention(self.hybrid_seq_parallel_attn, q, k, v, img_q_len=img_len, img_kv_len=img_len,
+                                      cu_seqlens_q=cu_seqlens_q, cu_seqlens_kv=cu_seqlens_kv)
+
+
+def hunyuan_double_block_forward(self, img: Tensor, txt: Tensor, vec: Tensor, cu_seqlens_q: Optional[Tensor] = None,
+                                 cu_seqlens_kv: Optional[Tensor] = None, max_seqlen_q: Optional[int] = None,
+                                 max_seqlen_kv: Optional[int] = None, freqs_cis: tuple = None):
+    """Drop-in body of MMDoubleStreamBlock.forward. Per stream: one LayerNorm+modulate pass, the module's own fused QKV
+    Linear, one RMSNorm+RoPE pass each over the q and k views of its output (no fp32 temporaries, no rotate_half
+    copies), joint varlen attention, and the two gated residuals as single passes."""
+    _require(img.is_cuda and img.dtype == _BF16 and txt.dtype == _BF16, "bf16 CUDA activations only")
+    _require(cu_seqlens_q is not None and cu_seqlens_kv is not None, "the block needs cu_seqlens (as the reference asserts)")
+    B, L, C = img.shape
+    T = txt.shape[1]
+    H = self.heads_num
+    D = C // H
+    _require(D in (64, 128), f"head dim {D} stays on the reference path")
+    assert cu_seqlens_q.shape[0] == 2 * B + 1, f"cu_seqlens_q.shape:{cu_seqlens_q.shape}, img.shape[0]:{B}"
+    cos, sin = freqs_cis if freqs_cis is not None else (None, None)
+
+    i_sh1, i_sc1, i_g1, i_sh2, i_sc2, i_g2 = self.img_mod(vec).chunk(6, dim=-1)
+    t_sh1, t_sc1, t_g1, t_sh2, t_sc2, t_g2 = self.txt_mod(vec).chunk(6, dim=-1)
+
+    img_qkv = self.img_attn_qkv(Fn.ln_modulate(img, shift=i_sh1, scale=i_sc1, eps=self.img_norm1.eps)).view(B, L, 3, H, D)
+    txt_qkv = self.txt_attn_qkv(Fn.ln_modulate(txt, shift=t_sh1, scale=t_sc1, eps=self.txt_norm1.eps)).view(B, T, 3, H, D)
+    img_q = _hy_qk(img_qkv[:, :, 0], self.img_attn_q_norm, cos, sin)
+    img_k = _hy_qk(img_qkv[:, :, 1], self.img_attn_k_norm, cos, sin)
+    txt_q = _hy_qk(txt_qkv[:, :, 0], self.txt_attn_q_norm, None, None)
+    txt_k = _hy_qk(txt_qkv[:, :, 1], self.txt_attn_k_norm, None, None)
+    q = torch.cat((img_q, txt_q), dim=1)
+    k = torch.cat((img_k, txt_k), dim=1)
+    v = torch.cat((img_qkv[:, :, 2], txt_qkv[:, :, 2]), dim=1)
+
+    attn = _hy_attention(self, q, k, v, L, cu_seqlens_q, cu_seqlens_kv, max_seqlen_q, max_seqlen_kv, B)
+    img_attn, txt_attn = attn[:, :L], attn[:, L:]
+
+    img = Fn.gate_residual(img, self.img_attn_proj(img_attn), i_g1)
+    img = Fn.gate_residual(img, self.img_mlp(Fn.ln_modulate(img, shift=i_sh2, scale=i_sc2, eps=self.img_norm2.eps)), i_g2)
+    txt = Fn.gate_residual(txt, self.txt_attn_proj(txt_attn), t_g1)
+    txt = Fn.gate_residual(txt, self.txt_mlp(Fn.ln_modulate(txt, shift=t_sh2, scale=t_sc2, eps=self.txt_norm2.eps)), t_g2)
+    return img, txt
+
+
+def hunyuan_single_block_forward(self, x: Tensor, vec: Tensor, txt_len: int, cu_seqlens_q: Optional[Tensor] = None,
+                                 cu_seqlens_kv: Optional[Tensor] = None, max_seqlen_q: Optional[int] = None,
+                                 max_seqlen_kv: Optional[int] = None, freqs_cis: Tuple[Tensor, Tensor] = None) -> Tensor:
+    """Drop-in body of MMSingleStreamBlock.forward: RoPE covers the first S - txt_len tokens only, which the fused kernel
+    expresses through the table length, so the reference's split / rotate / cat of q and k disappears."""
+    _require(x.is_cuda and x.dtype == _BF16, "bf16 CUDA activations only")
+    _require(cu_seqlens_q is not None and cu_seqlens_kv is not None, "the block needs cu_seqlens (as the reference asserts)")
+    B, S, C = x.shape
+    H = self.heads_num
+    D = C // H
+    _require(D in (64, 128), f"head dim {D} stays on the reference path")
+    assert cu_seqlens_q.shape[0] == 2 * B + 1, f"cu_seqlens_q.shape:{cu_seqlens_q.shape}, x.shape[0]:{B}"
+    cos = sin = None
+    if freqs_cis is not None:
+        cos, sin = freqs_cis
+        _require(cos.shape[0] == S - txt_len, "RoPE table must cover exactly the image tokens")
+
+    sh, sc, gate = self.modulation(vec).chunk(3, dim=-1)
+    lin = self.linear1(Fn.ln_modulate(x, shift=sh, scale=sc, eps=self.pre_norm.eps))
+    qkv = lin[..., : 3 * C].unflatten(-1, (3, H, D))
+    mlp = lin[..., 3 * C:]
+    q = _hy_qk(qkv[:, :, 0], self.q_norm, cos, sin)
+    k = _hy_qk(qkv[:, :, 1], self.k_norm, cos, sin)
+    v = qkv[:, :, 2]
+    attn = _hy_attention(self, q, k, v, S - txt_len, cu_seqlens_q, cu_seqlens_kv, max_seqlen_q, max_seqlen_kv, B)
+    out = self.linear2(torch.cat((attn, self.mlp_act(mlp)), 2))
+    return Fn.gate_residual(x, out, gate)
+
+
+# =====================================================================================================================
+# Wan2.1
+# =====================================================================================================================
+_WAN_ROPE_CACHE: dict = {}
+
+
+def wan_rope_tables(grid_size, freqs: Tensor, device) -> Tuple[Tensor, Tensor]:
+    """cos/sin tables (f*h*w, D) fp32 in the interleaved (repeat_interleave(2)) form the fused kernel takes, equal to the
+    per-token complex factors rope_apply multiplies by (model.py:40-67): the (1024, D/2) complex table is split into
+    [D/2 - 2(D/6), D/6, D/6] columns indexed by frame, row and column of the token."""
+    f, h, w = (int(v) for v in grid_size)
+    key = (f, h, w, freqs.data_ptr(), str(device))
+    hit = _WAN_ROPE_CACHE.get(key)
+    if hit is not None:
+        return hit
+    c = freqs.shape[1]
+    fs = freqs.split([c - 2 * (c // 3), c // 3, c // 3], dim=1)
+    fr = torch.cat([fs[0][:f].view(f, 1, 1, -1).expand(f, h, w, -1), fs[1][:h].view(1, h, 1, -1).expand(f, h, w, -1),
+                    fs[2][:w].view(1, 1, w, -1).expand(f, h, w, -1)], dim=-1).reshape(f * h * w, -1)
+    out = (fr.real.float().repeat_interleave(2, dim=1).contiguous().to(device),
+           fr.imag.float().repeat_interleave(2, dim=1).contiguous().to(device))
+    if len(_WAN_ROPE_CACHE) > 16:
+        _WAN_ROPE_CACHE.clear()
+    _WAN_ROPE_CACHE[key] = out
+    return out
+
+
+def _wan_half(t: Tensor) -> Tensor:
+    _require(t.dtype in (_BF16, torch.float32), "Wan projections must produce bf16 (autocast) or fp32 tensors")
+    return t if t.dtype == _BF16 else t.to(_BF16)
+
+
+def _wan_norm_rope(x4: Tensor, norm, grid_sizes, freqs) -> Tensor:
+    """WanRMSNorm over the whole token (dim = H*D) + RoPE, one pass. x4 (B, L, H, D) bf16."""
+    w, eps = _rms_weight(norm)
+    if grid_sizes is None:
+        return x4 if w is None else Fn.qk_rmsnorm_rope(x4, w, None, None, per_head=False, eps=eps)
+    grids = grid_sizes.tolist() if isinstance(grid_sizes, Tensor) else [list(g) for g in grid_sizes]
+    eps = eps if w is not None else 1e-6
+    if all(g == grids[0] for g in grids):
+        cos, sin = wan_rope_tables(grids[0], freqs, x4.device)
+        return Fn.qk_rmsnorm_rope(x4, w, cos, sin, per_head=False, eps=eps)
+    outs = []
+    for i, g in enumerate(grids):  # per-sample grids (the reference loops over samples too, model.py:47-64)
+        cos, sin = wan_rope_tables(g, freqs, x4.device)
+        outs.append(Fn.qk_rmsnorm_rope(x4[i:i + 1], w, cos, sin, per_head=False, eps=eps))
+    return torch.cat(outs, dim=0)
+
+
+def wan_self_attention_forward(self, x: Tensor, seq_lens: Tensor, grid_sizes: Tensor, freqs: Tensor) -> Tensor:
+    """Drop-in body of WanSelfAttention.forward: q/k/v/o stay the module's Linears; RMSNorm(dim) + RoPE is one bf16 pass
+    per tensor instead of an fp32 norm and a float64 complex multiply."""
+    _require(x.is_cuda, "CUDA activations only")
+    _require(tuple(self.window_size) == (-1, -1), "windowed attention stays on the reference path")
+    b, s, n, d = *x.shape[:2], self.num_heads, self.head_dim
+    _require(d in (64, 128), f"head dim {d} stays on the reference path")
+    q = _wan_norm_rope(_wan_half(self.q(x)).view(b, s, n, d), self.norm_q, grid_sizes, freqs)
+    k = _wan_norm_rope(_wan_half(self.k(x)).view(b, s, n, d), self.norm_k, grid_sizes, freqs)
+    v = _wan_half(self.v(x)).view(b, s, n, d)
+    out = Fn.wan_flash_attention(q, k, v, k_lens=seq_lens, window_size=self.window_size)
+    return self.o(out.flatten(2))
+
+
+def wan_t2v_cross_attention_forward(self, x: Tensor, context: Tensor, context_lens: Optional[Tensor]) -> Tensor:
+    """Drop-in body of WanT2VCrossAttention.forward."""
+    _require(x.is_cuda, "CUDA activations only")
+    b, n, d = x.size(0), self.num_heads, self.head_dim
+    _require(d in (64, 128), f"head dim {d} stays on the reference path")
+    q = _wan_norm_rope(_wan_half(self.q(x)).view(b, -1, n, d), self.norm_q, None, None)
+    k = _wan_norm_rope(_wan_half(self.k(context)).view(b, -1, n, d), self.norm_k, None, None)
+    v = _wan_half(self.v(context)).view(b, -1, n, d)
+    out = Fn.wan_flash_attention(q, k, v, k_lens=context_lens)
+    return self.o(out.flatten(2))
+
+
+def wan_i2v_cross_attention_forward(self, x: Tensor, context: Tensor, context_lens: Optional[Tensor]) -> Tensor:
+    """Drop-in body of WanI2VCrossAttention.forward: the first 257 context tokens are CLIP image tokens with their own
+    k/v projections; the two attention results are summed before the output projection."""
+    _require(x.is_cuda, "CUDA activations only")
+    context_img, context = context[:, :257], context[:, 257:]
+    b, n, d = x.size(0), self.num_heads, self.head_dim
+    _require(d in (64, 128), f"head dim {d} stays on the reference path")
+    q = _wan_norm_rope(_wan_half(self.q(x)).view(b, -1, n, d), self.norm_q, None, None)
+    k = _wan_norm_rope(_wan_half(self.k(context)).view(b, -1, n, d), self.norm_k, None, None)
+    v = _wan_half(self.v(context)).view(b, -1, n, d)
+    k_img = _wan_norm_rope(_wan_half(self.k_img(context_img)).view(b, -1, n, d), self.norm_k_img, None, None)
+    v_img = _wan_half(self.v_img(context_img)).view(b, -1, n, d)
+    img_x = Fn.wan_flash_attention(q, k_img, v_img, k_lens=None)
+    out = Fn.wan_flash_attention(q, k, v, k_lens=context_lens)
+    return self.o(out.flatten(2) + img_x.flatten(2))
+
+
+def _wan_ln(norm, x: Tensor) -> Tensor:
+    """WanLayerNorm (fp32 statistics, optional affine, model.py:89-99) or Identity -> bf16 for the following Linear."""
+    if _is_identity(norm):
+        return x
+    return Fn.ln_modulate(x, None, None, getattr(norm, "weight", None), getattr(norm, "bias", None), norm.eps)
+
+
+def wan_attention_block_forward(self, x: Tensor, e: Tensor, seq_lens, grid_sizes, freqs, context, context_lens) -> Tensor:
+    """Drop-in body of WanAttentionBlock.forward. The residual stream keeps the dtype it arrives in (fp32 in the
+    reference pipeline: `x + y * e[2]` promotes it); every LayerNorm+modulate reads it once and emits the bf16 tensor
+    the next Linear consumes, every gated residual is one read-modify-write pass."""
+    _require(x.is_cuda and x.dtype in (_BF16, torch.float32) and x.dim() == 3, "CUDA bf16/fp32 (B,L,C) activations only")
+    assert e.dtype == torch.float32
+    e6 = (self.modulation.float() + e).chunk(6, dim=1)  # six (B, 1, C) fp32 tensors
+
+    y = self.self_attn(Fn.ln_modulate(x, shift=e6[0], scale=e6[1], eps=self.norm1.eps), seq_lens, grid_sizes, freqs)
+    x = Fn.gate_residual(x, _wan_half(y), e6[2])
+    x = Fn.gate_residual(x, _wan_half(self.cross_attn(_wan_ln(self.norm3, x), context, context_lens)), None)
+    y = self.ffn(Fn.ln_modulate(x, shift=e6[3], scale=e6[4], eps=self.norm2.eps))
+    return Fn.gate_residual(x, _wan_half(y), e6[5])
+
+
+# =====================================================================================================================
+# lvdm (VideoCrafter / DynamiCrafter 3D-UNet)
+# =====================================================================================================================
+def _lvdm_ln(norm: nn.LayerNorm, x: Tensor) -> Tensor:
+    _require(x.is_cuda and x.dtype in (_BF16, torch.float32) and x.shape[-1] % 8 == 0, "CUDA bf16/fp32 activations only")
+    return Fn.layer_norm(x, norm.weight, norm.bias, norm.eps)
+
+
+def lvdm_basic_block_forward(self, x: Tensor, context: Optional[Tensor] = None, mask: Optional[Tensor] = None) -> Tensor:
+    """Drop-in body of BasicTransformerBlock._forward (the checkpoint wrapper in .forward stays the reference's):
+    the three affine LayerNorms run in the row kernel; attn1/attn2 are the module's CrossAttention (whose forward
+    patch_lvdm replaces); the GEGLU feed-forward stays cuBLAS."""
+    x = self.attn1(_lvdm_ln(self.norm1, x), context=context if self.disable_self_attn else None, mask=mask) + x
+    x = self.attn2(_lvdm_ln(self.norm2, x), context=context, mask=mask) + x
+    x = self.ff(_lvdm_ln(self.norm3, x)) + x
+    return x
+
+
+def _lvdm_gn(norm: nn.GroupNorm, x: Tensor, silu: bool = False) -> Tensor:
+    _require(x.is_cuda and x.dtype in (_BF16, torch.float32), "CUDA bf16/fp32 activations only")
+    _require(norm.affine, "GroupNorm without affine parameters stays on the reference path")
+    return Fn.groupnorm_silu(x, norm.weight, norm.bias, norm.num_groups, norm.eps, silu=silu)
+
+
+def lvdm_spatial_transformer_forward(self, x: Tensor, context: Optional[Tensor] = None) -> Tensor:
+    """Drop-in body of SpatialTransformer.forward: GroupNorm(32) with fp32 statistics in one kernel, then the
+    reference's own projections, blocks and layout changes."""
+    b, c, h, w = x.shape
+    x_in = x
+    x = _lvdm_gn(self.norm, x)
+    if not self.use_linear:
+        x = self.proj_in(x)
+    x = x.flatten(2).transpose(1, 2).contiguous()  # b c h w -> b (h w) c
+    if self.use_linear:
+        x = self.proj_in(x)
+    for block in self.transformer_blocks:
+        x = block(x, context=context)
+    if self.use_linear:
+        x = self.proj_out(x)
+    x = x.transpose(1, 2).reshape(b, -1, h, w).contiguous()  # b (h w) c -> b c h w
+    if not self.use_linear:
+        x = self.proj_out(x)
+    return x + x_in
+
+
+def lvdm_temporal_transformer_forward(self, x: Tensor, context: Optional[Tensor] = None) -> Tensor:
+    """Drop-in body of TemporalTransformer.forward for the configurations the reference trains (only_self_att, with or
+    without the causal mask); the per-sample cross-attention loop (:499-509) stays on the reference path."""
+    _require(self.only_self_att, "temporal cross-attention stays on the reference path")
+    b, c, t, h, w = x.shape
+    x_in = x
+    x = _lvdm_gn(self.norm, x)
+    if self.use_linear:
+        x = x.permute(0, 3, 4, 2, 1).reshape(b * h * w, t, c)  # b c t h w -> (b h w) t c   (one copy)
+        x = self.proj_in(x)
+    else:
+        x = x.permute(0, 3, 4, 1, 2).reshape(b * h * w, c, t)  # b c t h w -> (b h w) c t
+        x = self.proj_in(x).transpose(1, 2).contiguous()
+    mask = None
+    if self.causal_attention:
+        mask = self.mask.to(x.device).expand(b * h * w, -1, -1)
+    for block in self.transformer_blocks:
+        x = block(x, mask=mask)
+    if self.use_linear:
+        x = self.proj_out(x)
+        x = x.view(b, h, w, t, -1).permute(0, 4, 3, 1, 2).contiguous()  # (b h w) t c -> b c t h w
+    else:
+        x = self.proj_out(x.transpose(1, 2).contiguous())
+        x = x.view(b, h, w, -1, t).permute(0, 3, 4, 1, 2).contiguous()
+    return x + x_in
+
+
+def lvdm_resblock_forward(self, x: Tensor, emb: Tensor, batch_size: Optional[int] = None) -> Tensor:
+    """Drop-in body of ResBlock._forward: both GroupNormSpecific + SiLU pairs (fp32 statistics, utils.py:192-203) are one
+    kernel each; convolutions, up/down-sampling and the temporal conv block stay the module's own layers."""
+    _require(x.is_cuda and x.dtype in (_BF16, torch.float32), "CUDA bf16/fp32 activations only")
+    in_norm, in_conv = self.in_layers[0], self.in_layers[-1]
+    h = _lvdm_gn(in_norm, x, silu=True)
+    if self.updown:
+        h = self.h_upd(h)
+        x = self.x_upd(x)
+    h = in_conv(h)
+    emb_out = self.emb_layers(emb).type(h.dtype)
+    while len(emb_out.shape) < len(h.shape):
+        emb_out = emb_out[..., None]
+    out_norm, out_rest = self.out_layers[0], self.out_layers[2:]  # [norm, SiLU, Dropout, conv]
+    if self.use_scale_shift_norm:
+        scale, shift = torch.chunk(emb_out, 2, dim=1)
+        h = _lvdm_gn(out_norm, h) * (1 + scale) + shift
+        h = self.out_layers[1:](h)
+    else:
+        h = out_rest(_lvdm_gn(out_norm, h + emb_out, silu=True))
+    h = self.skip_connection(x) + h
+    if self.use_temporal_conv and batch_size:
+        bt, ch, hh, ww = h.shape
+        h = h.view(batch_size, bt // batch_size, ch, hh, ww).transpose(1, 2)  # (b t) c h w -> b c t h w
+        h = self.temopral_conv(h)
+        h = h.transpose(1, 2).reshape(bt, ch, hh, ww)
+    return h
+
+
+# =====================================================================================================================
+# diffusers attention processors (CogVideoX, diffusers-HunyuanVideo) — duck-typed, no diffusers import
+# =====================================================================================================================
+def _proc_qk_norm(norm, x4: Tensor) -> Tensor:
+    """diffusers `Attention.norm_q / norm_k` applied per head on (B, L, H, D): LayerNorm(D) for CogVideoX (qk_norm=
+    "layer_norm"), RMSNorm(D) for HunyuanVideo (qk_norm="rms_norm"); None -> unchanged."""
+    if norm is None:
+        return x4
+    if isinstance(norm, nn.LayerNorm):
+        B, L, H, D = x4.shape
+        return Fn.layer_norm(x4.reshape(B, L * H, D), norm.weight, norm.bias, norm.eps).view(B, L, H, D)
+    w, eps = _rms_weight(norm)
+    return Fn.qk_rmsnorm_rope(x4, w, None, None, per_head=True, eps=eps)
+
+
+def _proc_rope(x4: Tensor, image_rotary_emb, start: int, length: int) -> Tensor:
+    """diffusers apply_rotary_emb(use_real=True, unbind_dim=-1) — the same interleaved-pair rotation as hunyuan's —
+    on tokens [start, start + length) of (B, L, H, D)."""
+    if image_rotary_emb is None:
+        return x4
+    cos, sin = image_rotary_emb
+    if start == 0:
+        _require(cos.shape[0] == length, "rotary table must cover exactly the rotated tokens")
+        return Fn.qk_rmsnorm_rope(x4, None, cos, sin)
+    head, tail = x4[:, :start], x4[:, start:]
+    return torch.cat([head, Fn.qk_rmsnorm_rope(tail, None, cos, sin)], dim=1)
+
+
+class CogVideoXAttnProcessor:
+    """`attn.set_processor(CogVideoXAttnProcessor())` — protocol of diffusers 0.32.2 `CogVideoXAttnProcessor2_0`
+    (reference call sites: cogvideo_hf/cogvideo_pl.py:123, 862-868; semantics cross-checked against the in-tree SAT
+    description, cogvideo_sat/dit_video_concat.py:263-427): text tokens first, q/k/v Linears on the concatenation,
+    per-head LayerNorm on q and k, RoPE on the video tokens only, dense joint attention, output projection, split."""
+
+    def __call__(self, attn, hidden_states: Tensor, encoder_hidden_states: Tensor, attention_mask: Optional[Tensor] = None,
+                 image_rotary_emb=None) -> Tuple[Tensor, Tensor]:
+        _require(attention_mask is None, "attention masks stay on the stock processor")
+        text_len = encoder_hidden_states.size(1)
+        x = torch.cat([encoder_hidden_states, hidden_states], dim=1)
+        _require(x.is_cuda and x.dtype == _BF16, "bf16 CUDA activations only")
+        B, S, _ = x.shape
+        H = attn.heads
+        q, k, v = attn.to_q(x), attn.to_k(x), attn.to_v(x)
+        D = q.shape[-1] // H
+        _require(D in (64, 128), f"head dim {D} stays on the stock processor")
+        q = _proc_qk_norm(getattr(attn, "norm_q", None), q.view(B, S, H, D))
+        k = _proc_qk_norm(getattr(attn, "norm_k", None), k.view(B, S, H, D))
+        if image_rotary_emb is not None:
+            q = _proc_rope(q, image_rotary_emb, text_len, S - text_len)
+            if not getattr(attn, "is_cross_attention", False):
+                k = _proc_rope(k, image_rotary_emb, text_len, S - text_len)
+        out = Fn.attention_blhd(q, k, v.view(B, S, H, D)).reshape(B, S, H * D)
+        out = attn.to_out[1](attn.to_out[0](out))
+        return out[:, text_len:], out[:, :text_len]
+
+
+class HunyuanVideoAttnProcessor:
+    """Protocol of diffusers 0.32.2 `HunyuanVideoAttnProcessor2_0` (reference call site: hyvideo_t2v/hunyuanvideo.py:209,
+    946-955): video tokens first; double-stream blocks (attn.add_q_proj present) project the text stream separately,
+    single-stream blocks receive [video; text] already concatenated (encoder_hidden_states is only a length marker);
+    per-head RMSNorm on q/k, RoPE on the video tokens, joint attention. The only mask shape on the CUDA path is the
+    reference's key-padding mask (B, 1, 1|S, S) or (B, S), turned into per-sample key lengths."""
+
+    @staticmethod
+    def _key_lens(attention_mask: Optional[Tensor], B: int, S: int) -> Optional[Tensor]:
+        if attention_mask is None:
+            return None
+        m = attention_mask
+        _require(m.dtype == torch.bool, "only boolean key-padding masks are on the CUDA path")
+        if m.dim() == 4:
+            m = m[:, 0, 0]
+        _require(m.shape == (B, S), "unsupported mask shape")
+        lens = m.sum(dim=1).to(torch.int32)
+        # a key-padding mask must be a prefix of ones for key lengths to express it
+        _require(bool((m == (torch.arange(S, device=m.device)[None] < lens[:, None])).all()), "non-prefix mask")
+        return lens
+
+    def __call__(self, attn, hidden_states: Tensor, encoder_hidden_states: Optional[Tensor] = None,
+                 attention_mask: Optional[Tensor] = None, image_rotary_emb=None) -> Tuple[Tensor, Optional[Tensor]]:
+        double = getattr(attn, "add_q_proj", None) is not None
+        if not double and encoder_hidden_states is not None:
+            hidden_states = torch.cat([hidden_states, encoder_hidden_states], dim=1)
+        _require(hidden_states.is_cuda and hidden_states.dtype == _BF16, "bf16 CUDA activations only")
+        B, S1, _ = hidden_states.shape
+        H = attn.heads
+        T = encoder_hidden_states.shape[1] if encoder_hidden_states is not None else 0
+        n_img = S1 if double else S1 - T
+        q, k, v = attn.to_q(hidden_states), attn.to_k(hidden_states), attn.to_v(hidden_states)
+        D = q.shape[-1] // H
+        _require(D in (64, 128), f"head dim {D} stays on the stock processor")
+        q = _proc_qk_norm(getattr(attn, "norm_q", None), q.view(B, S1, H, D))
+        k = _proc_qk_norm(getattr(attn, "norm_k", None), k.view(B, S1, H, D))
+        v = v.view(B, S1, H, D)
+        if image_rotary_emb is not None:
+            cos, sin = image_rotary_emb
+            _require(cos.shape[0] == n_img, "rotary table must cover exactly the video tokens")
+            q = Fn.qk_rmsnorm_rope(q, None, cos, sin)
+            k = Fn.qk_rmsnorm_rope(k, None, cos, sin)
+        if double and encoder_hidden_states is not None:
+            eq = attn.add_q_proj(encoder_hidden_states).view(B, T, H, D)
+            ek = attn.add_k_proj(encoder_hidden_states).view(B, T, H, D)
+            ev = attn.add_v_proj(encoder_hidden_states).view(B, T, H, D)
+            eq = _proc_qk_norm(getattr(attn, "norm_added_q", None), eq)
+            ek = _proc_qk_norm(getattr(attn, "norm_added_k", None), ek)
+            q, k, v = torch.cat([q, eq], 1), torch.cat([k, ek], 1), torch.cat([v, ev], 1)
+        S = q.shape[1]
+        out = Fn.attention_blhd(q, k, v, k_lens=self._key_lens(attention_mask, B, S)).reshape(B, S, H * D)
+        if encoder_hidden_states is None:
+            return out, None
+        hs, ehs = out[:, :S - T], out[:, S - T:]
+        if getattr(attn, "to_out", None) is not None:
+            hs = attn.to_out[1](attn.to_out[0](hs))
+        if getattr(attn, "to_add_out", None) is not None:
+            ehs = attn.to_add_out(ehs)
+        return hs, ehs

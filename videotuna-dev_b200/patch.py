@@ -19,6 +19,7 @@ from typing import Callable, Dict, Optional
 
 import torch
 
+from . import blocks as Bk
 from . import functional as Fn
 from . import sp
 
@@ -91,8 +92,99 @@ def patch_wan(modules=None) -> int:
     return n
 
 
-def patch_videotuna(lvdm: bool = True, hunyuan: bool = True, wan: bool = True) -> Dict[str, int]:
-    """Install every hook whose reference module imports in this environment; returns what was patched."""
+def _patch_method(mod, cls_name: str, attr: str, fast: Callable) -> int:
+    cls = getattr(mod, cls_name, None)
+    if cls is None or not hasattr(cls, attr):
+        return 0
+    setattr(cls, attr, _wrap(f"{mod.__name__}.{cls_name}.{attr}", getattr(cls, attr), fast))
+    return 1
+
+
+def _t2v_signature_only(fast: Callable, n_positional: int, allowed: tuple) -> Callable:
+    """The i2v twins of the Hunyuan blocks take extra arguments (condition_type, token_replace_vec,
+    frist_frame_token_num; hyvideo_i2v/modules/models.py:136-297) for first-frame token replacement, which is not on the
+    CUDA path: calls that use them go to the original forward."""
+    def guarded(self, *args, **kwargs):
+        extra = [k for k in kwargs if k not in allowed and kwargs[k] is not None]
+        if len(args) > n_positional or extra:
+            raise Fn.Unsupported("token_replace (i2v first-frame modulation) stays on the reference path")
+        return fast(self, *args, **{k: v for k, v in kwargs.items() if k in allowed})
+    return guarded
+
+
+def patch_blocks(lvdm: bool = True, hunyuan: bool = True, wan: bool = True) -> Dict[str, int]:
+    """Replace the block-level forwards with the fused versions in b200vt.blocks.
+    Independent of patch_videotuna(): the fused blocks call b200vt's attention functions directly. Idempotent."""
+    done = {"lvdm": 0, "hunyuan": 0, "wan": 0}
+    if lvdm:
+        mod = _try_import("videotuna.models.lvdm.modules.attention")
+        if mod is not None:
+            done["lvdm"] += _patch_method(mod, "BasicTransformerBlock", "_forward", Bk.lvdm_basic_block_forward)
+            done["lvdm"] += _patch_method(mod, "SpatialTransformer", "forward", Bk.lvdm_spatial_transformer_forward)
+            done["lvdm"] += _patch_method(mod, "TemporalTransformer", "forward", Bk.lvdm_temporal_transformer_forward)
+        net = _try_import("videotuna.models.lvdm.modules.networks.openaimodel3d")
+        if net is not None:
+            done["lvdm"] += _patch_method(net, "ResBlock", "_forward", Bk.lvdm_resblock_forward)
+    if hunyuan:
+        dbl_kw = ("img", "txt", "vec", "cu_seqlens_q", "cu_seqlens_kv", "max_seqlen_q", "max_seqlen_kv", "freqs_cis")
+        sgl_kw = ("x", "vec", "txt_len", "cu_seqlens_q", "cu_seqlens_kv", "max_seqlen_q", "max_seqlen_kv", "freqs_cis")
+        for pkg in ("hyvideo_t2v", "hyvideo_i2v"):
+            mod = _try_import(f"videotuna.models.hunyuan.{pkg}.modules.models")
+            if mod is None:
+                continue
+            done["hunyuan"] += _patch_method(mod, "MMDoubleStreamBlock", "forward",
+                                             _t2v_signature_only(Bk.hunyuan_double_block_forward, 8, dbl_kw))
+            done["hunyuan"] += _patch_method(mod, "MMSingleStreamBlock", "forward",
+                                             _t2v_signature_only(Bk.hunyuan_single_block_forward, 8, sgl_kw))
+            if hasattr(mod, "parallel_attention"):
+                mod.parallel_attention = _wrap(f"{mod.__name__}.parallel_attention", mod.parallel_attention,
+                                               Bk.hunyuan_parallel_attention)
+                done["hunyuan"] += 1
+    if wan:
+        mod = _try_import("videotuna.models.wan.wan.modules.model")
+        if mod is not None:
+            done["wan"] += _patch_method(mod, "WanSelfAttention", "forward", Bk.wan_self_attention_forward)
+            done["wan"] += _patch_method(mod, "WanT2VCrossAttention", "forward", Bk.wan_t2v_cross_attention_forward)
+            done["wan"] += _patch_method(mod, "WanI2VCrossAttention", "forward", Bk.wan_i2v_cross_attention_forward)
+            done["wan"] += _patch_method(mod, "WanAttentionBlock", "forward", Bk.wan_attention_block_forward)
+    return done
+
+
+def set_diffusers_processors(transformer: torch.nn.Module) -> int:
+    """diffusers models (CogVideoXTransformer3DModel, HunyuanVideoTransformer3DModel; reference call sites
+    cogvideo_hf/cogvideo_pl.py:123 and hyvideo_t2v/hunyuanvideo.py:209): install the duck-typed processors on every
+    `Attention` module whose current processor is the stock CogVideoX / HunyuanVideo one. Returns how many were set."""
+    n = 0
+    for m in transformer.modules():
+        proc = getattr(m, "processor", None)
+        if proc is None or not hasattr(m, "set_processor"):
+            continue
+        name = type(proc).__name__
+        if name.startswith("CogVideoXAttnProcessor"):
+            m.set_processor(_FallbackProcessor(Bk.CogVideoXAttnProcessor(), proc))
+            n += 1
+        elif name.startswith("HunyuanVideoAttnProcessor"):
+            m.set_processor(_FallbackProcessor(Bk.HunyuanVideoAttnProcessor(), proc))
+            n += 1
+    return n
+
+
+class _FallbackProcessor:
+    """Try the CUDA processor; `Unsupported` (masks, fp32, CPU, ...) goes to the stock processor it replaced."""
+
+    def __init__(self, fast, original):
+        self.fast, self.original = fast, original
+
+    def __call__(self, attn, *args, **kwargs):
+        try:
+            return self.fast(attn, *args, **kwargs)
+        except Fn.Unsupported:
+            return self.original(attn, *args, **kwargs)
+
+
+def patch_videotuna(lvdm: bool = True, hunyuan: bool = True, wan: bool = True, blocks: bool = False) -> Dict[str, int]:
+    """Install every hook whose reference module imports in this environment; returns what was patched.
+    blocks=True additionally installs the fused block forwards (patch_blocks)."""
     done = {"lvdm": 0, "hunyuan": 0, "wan": 0}
     if lvdm:
         done["lvdm"] = int(patch_lvdm())
@@ -100,6 +192,9 @@ def patch_videotuna(lvdm: bool = True, hunyuan: bool = True, wan: bool = True) -
         done["hunyuan"] = patch_hunyuan()
     if wan:
         done["wan"] = patch_wan()
+    if blocks:
+        for k, v in patch_blocks(lvdm, hunyuan, wan).items():
+            done[k] += v
     return done
 
 
@@ -115,6 +210,11 @@ def unpatch_videotuna() -> None:
             mod = _try_import(modname)
             if mod is not None:
                 setattr(mod, attr, original)
+            else:  # "<module>.<Class>.<method>" (patch_blocks)
+                modname, cls_name = modname.rsplit(".", 1)
+                mod = _try_import(modname)
+                if mod is not None and hasattr(mod, cls_name):
+                    setattr(getattr(mod, cls_name), attr, original)
         _ORIGINALS.pop(name, None)
 
 

@@ -58,6 +58,8 @@ struct AttnBwdParams {
 // Host-side launchers implemented in the kernel translation units. Return cudaError_t of the launch.
 cudaError_t launch_attn_fwd(int D, const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
                             const AttnFwdParams& p, int q_tiles_hint, cudaStream_t stream);
+cudaError_t launch_attn_fwd_alt(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
+                                const AttnFwdParams& p, cudaStream_t stream);  // head dim 128 only
 cudaError_t launch_attn_bwd(int D, const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
                             const CUtensorMap& tm_do, const CUtensorMap& tm_dq, float* dq_acc, int Lq_total,
                             const AttnBwdParams& p, cudaStream_t stream);
@@ -67,6 +69,7 @@ cudaError_t launch_attn_bwd_dq_convert(const float* acc, void* dq, const int64_t
                                        float scale, cudaStream_t stream);
 long long* debug_trace_ptr();  // capi.cu: device buffer set through vt_debug_set_trace, or nullptr
 cudaError_t attn_fwd_set_debug_ptr(unsigned int* p);
+cudaError_t attn_fwd_alt_set_debug_ptr(unsigned int* p);
 cudaError_t attn_bwd_set_debug_ptr(unsigned int* p);
 
 }  // namespace vt

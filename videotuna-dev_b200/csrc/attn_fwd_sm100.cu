@@ -1062,7 +1062,13 @@ cudaError_t launch_attn_fwd(int D, const CUtensorMap& tm_q, const CUtensorMap& t
   }
   // One query tile per CTA when the (max) query length fits a single 128-row tile; two otherwise.
   const bool single = (q_tiles_hint == 1) || (q_tiles_hint == 0 && p.seq.Lq <= 128);
-  if (D == 128) return single ? launch_one<128, 1>(tm_q, tm_k, tm_v, p, stream) : launch_one<128, 2>(tm_q, tm_k, tm_v, p, stream);
+  if (D == 128) {
+    // Head dim 128: one tile per CTA, three rotating S buffers, two alternating softmax sets (attn_fwd_alt_sm100.cu).
+    // VT_FWD_KERNEL=pp keeps the two-tile ping-pong kernel for A/B measurements.
+    static const bool use_pp128 = [] { const char* e = getenv("VT_FWD_KERNEL"); return e != nullptr && e[0] == 'p'; }();
+    if (!use_pp128 && q_tiles_hint == 0) return launch_attn_fwd_alt(tm_q, tm_k, tm_v, p, stream);
+    return single ? launch_one<128, 1>(tm_q, tm_k, tm_v, p, stream) : launch_one<128, 2>(tm_q, tm_k, tm_v, p, stream);
+  }
   if (D == 64) {
     // Head dim 64, two tiles: the rotating-S kernel (K3: see DESIGN.md §4.1). VT_FWD_KERNEL=pp keeps the ping-pong kernel.
     static const bool use_pp = [] { const char* e = getenv("VT_FWD_KERNEL"); return e != nullptr && e[0] == 'p'; }();

@@ -48,6 +48,7 @@ int ensure_init() {
   VT_CHECK_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_state.dbg_dev), g_state.dbg_host, 0));
   VT_CHECK_CUDA(attn_fwd_set_debug_ptr(g_state.dbg_dev));
   VT_CHECK_CUDA(attn_bwd_set_debug_ptr(g_state.dbg_dev));
+  VT_CHECK_CUDA(attn_fwd_alt_set_debug_ptr(g_state.dbg_dev));
   g_state.ready = true;
   g_state.init_rc = 0;
   return 0;

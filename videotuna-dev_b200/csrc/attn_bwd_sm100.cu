@@ -41,6 +41,7 @@ struct BwdCfg {
   // (~2000 cycles measured), so with two slots S^T of the next tile waited ~1400 cycles for Q in every iteration.
   static constexpr int QS = (D == 64) ? 3 : 2;
   static constexpr int DOS = (D == 64) ? 2 : 1;
+  static constexpr bool TWO_ISSUERS = (D == 64);  // see the MMA issuer section of the kernel
 #ifdef VT_BWD_EMU
   static constexpr int EMU = VT_BWD_EMU;    // of every 8 exponential pairs, how many run on the FMA pipe (ex2_poly2)
 #else
@@ -55,7 +56,7 @@ struct BwdCfg {
   static constexpr int OFF_DQS = OFF_DS + 2 * CHUNK;    // 2 staging buffers for the dQ TMA reduction
   static constexpr int OFF_STAT = OFF_DQS + 2 * DQ_CHUNK;  // QS x {lse_log2[128], delta[128]} fp32
   static constexpr int OFF_BAR = OFF_STAT + QS * 1024;
-  static constexpr int NBAR = 1 + 2 * QS + QS + 2 * DOS + 8;
+  static constexpr int NBAR = 1 + 2 * QS + QS + 2 * DOS + 9;  // dkv_full[2], tok_s unused slot kept for layout
   static constexpr int OFF_TMEM = OFF_BAR + NBAR * 8;
   // The dynamic shared memory base is 1024-byte aligned (checked at kernel entry), so no alignment slack is spent:
   // at D = 128 the layout uses 231 608 of the 232 448 bytes a CTA can have.
@@ -69,7 +70,7 @@ struct BwdCfg {
 
 enum : uint32_t {
   BT_KV_FULL = 0x200, BT_Q_FULL, BT_Q_EMPTY, BT_STAT_FULL, BT_DO_FULL, BT_DO_EMPTY, BT_S_FULL, BT_P_READY, BT_DP_FULL,
-  BT_DS_READY, BT_DQ_FULL, BT_DQ_DRAINED, BT_DKV_FULL, BT_DS_FREE, BT_ALIGN
+  BT_DS_READY, BT_DQ_FULL, BT_DQ_DRAINED, BT_DKV_FULL, BT_DS_FREE, BT_ALIGN, BT_TOK_S
 };
 
 
@@ -138,10 +139,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   uint64_t* dq_full = ds_ready + 1;
   uint64_t* dq_drained = dq_full + 1;
   uint64_t* dkv_full = dq_drained + 1;
-  uint64_t* ds_free = dkv_full + 1;
+  uint64_t* ds_free = dkv_full + 2;    // dkv_full[0]: dK complete (issuer 0), dkv_full[1]: dV complete (issuer 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + C::OFF_TMEM);
 
-  constexpr int PROD_WARP = 12, MMA_WARP = 13;
+  constexpr int PROD_WARP = 12, MMA_WARP = 13, MMA_WARP1 = 14;
 
   if (warp == PROD_WARP && lane == 0) {
     tma_prefetch_desc(&tm_q);
@@ -168,6 +169,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_init(dq_full, 1);
     mbar_init(dq_drained, 128);
     mbar_init(dkv_full, 1);
+    mbar_init(dkv_full + 1, 1);
     mbar_init(ds_free, 1);
     fence_mbar_init();
   }
@@ -230,8 +232,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         }
         __syncwarp();
       }
-    } else if (warp == MMA_WARP && elect_one()) {
-      // ================================ MMA issuer ===============================================
+    } else if ((warp == MMA_WARP || warp == MMA_WARP1) && elect_one()) {
+      // ================================ MMA issuers ==============================================
+      // TWO issuer threads. A tcgen05.mma / commit sequence holds its issuing thread until the tensor pipe has nearly
+      // drained it, and every barrier poll plus the scalar code around it then runs with the pipe idle (a lone thread
+      // executes ~10 cycles per instruction next to four busy warps). With two threads one's polling overlaps the
+      // other's MMAs:
+      //   issuer 0 (warp 13): dQ = dS K and dK += dS^T Q          — wait for dS from the compute warps
+      //   issuer 1 (warp 14): dV += P^T dO, then S^T = K Q^T and dP^T = V dO^T of the NEXT Q tile
+      // S^T(i+1) overwrites the TMEM columns P^T(i) lives in, so it must enter the pipe behind dV(i): both are issued
+      // by the same thread, in program order (a hand-off flag between two threads does not order their MMAs: the arrive
+      // can overtake the issuing thread's own tcgen05.mma — measured as wrong dV). Cross-thread hazards are all covered
+      // by barriers that already exist: dP^T(i+1) overwrites dP^T(i) / dQ(i) only after dq_drained(i) (D = 128) or
+      // ds_ready(i) (D = 64); the Q tile is released by issuer 0 after dK(i), which S^T(i) precedes by data dependence.
       constexpr uint32_t IDESC_ST = umma_idesc_bf16(128, 128, 0, 0);  // S^T, dP^T: both operands K-major
       constexpr uint32_t IDESC_KD = umma_idesc_bf16(128, D, 0, 1);    // dV, dK: A K-major (TMEM / smem), B MN-major
       constexpr uint32_t IDESC_DQ = umma_idesc_bf16(128, D, 1, 1);    // dQ: A = dS MN-major, B = K MN-major
@@ -252,72 +265,142 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       };
 
       mbar_wait(kv_full, 0, BT_KV_FULL);
-      mbar_wait(q_full + 0, 0, BT_Q_FULL);
-      tc_fence_after();
-      mma_kmajor_pair(tmem + C::T_S, k_s, q_s);
-      tc_commit(s_full);
-      mbar_wait(do_full + 0, 0, BT_DO_FULL);
-      tc_fence_after();
-      mma_kmajor_pair(tmem + C::T_DP, v_s, do_s);
-      tc_commit(dp_full);
-
-      for (int i = 0; i < n_q; ++i) {
-        const int s = i % C::QS, ds = i % C::DOS;
-        const bool has_next = i + 1 < n_q;
-        // ---- dV += P^T dO_i ----
-        trace_mark(p.trace, 1, i, 0);
-        mbar_wait(p_ready, i & 1, BT_P_READY);
-        tc_fence_after();
-        trace_mark(p.trace, 1, i, 1);
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)
-          umma_ts(tmem + C::T_DV, tmem + C::T_P + kk * 8,
-                  umma_desc_sw128_a16(do_s + ds * TILE16 + kk * 128, C::CHUNK, 1024), IDESC_KD, (i > 0) || kk != 0);
-        tc_commit(do_empty + ds);
-        // ---- S^T for the next Q tile ----
-        if (has_next) {
-          const int sn = (i + 1) % C::QS;
-          mbar_wait(q_full + sn, ((i + 1) / C::QS) & 1, BT_Q_FULL);
+      if (!C::TWO_ISSUERS) {
+        // ---- one issuer (head dim 128: the kernel is bound by the dQ reduction, a second polling thread only costs power) ----
+        if (warp == MMA_WARP) {
+          mbar_wait(q_full + 0, 0, BT_Q_FULL);
           tc_fence_after();
-          trace_mark(p.trace, 1, i, 2);
-          mma_kmajor_pair(tmem + C::T_S, k_s, q_s + sn * TILE16);
+          mma_kmajor_pair(tmem + C::T_S, k_s, q_s);
           tc_commit(s_full);
-        }
-        // ---- dQ_i = dS K (drained while the next MMA runs) ; dK += dS^T Q_i ----
-        mbar_wait(ds_ready, i & 1, BT_DS_READY);
-        tc_fence_after();
-        trace_mark(p.trace, 1, i, 3);
-        if (!C::DQ_ALIASES_DP && i > 0) {
-          mbar_wait(dq_drained, (i - 1) & 1, BT_DQ_DRAINED);
+          mbar_wait(do_full + 0, 0, BT_DO_FULL);
           tc_fence_after();
-        }
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)  // k = 16 keys per step
-          umma_ss(tmem + C::T_DQ, umma_desc_sw128_a16(ds_s + kk * 128, C::CHUNK, 1024),
-                  umma_desc_sw128_a16(k_s + kk * 128, C::CHUNK, 1024), IDESC_DQ, kk != 0);
-        tc_commit(dq_full);
-#pragma unroll
-        for (int kk = 0; kk < 8; ++kk)  // k = 16 query rows per step; dS^T tile is [key][q] in two 64-q boxes
-          umma_ss(tmem + C::T_DK, umma_desc_sw128_a16(ds_s + (kk >> 2) * CH16 + (kk & 3) * 2, 16, 1024),
-                  umma_desc_sw128_a16(q_s + s * TILE16 + kk * 128, C::CHUNK, 1024), IDESC_KD, (i > 0) || kk != 0);
-        tc_commit(q_empty + s);
-        tc_commit(ds_free);
-        // ---- dP^T for the next Q tile ----
-        if (has_next) {
-          if (C::DQ_ALIASES_DP) {
-            mbar_wait(dq_drained, i & 1, BT_DQ_DRAINED);
-            tc_fence_after();
-          }
-          trace_mark(p.trace, 1, i, 4);
-          const int dn = (i + 1) % C::DOS;
-          mbar_wait(do_full + dn, ((i + 1) / C::DOS) & 1, BT_DO_FULL);
-          tc_fence_after();
-          trace_mark(p.trace, 1, i, 5);
-          mma_kmajor_pair(tmem + C::T_DP, v_s, do_s + dn * TILE16);
+          mma_kmajor_pair(tmem + C::T_DP, v_s, do_s);
           tc_commit(dp_full);
+
+          for (int i = 0; i < n_q; ++i) {
+            const int s = i % C::QS, ds = i % C::DOS;
+            const bool has_next = i + 1 < n_q;
+            // ---- dV += P^T dO_i ----
+            trace_mark(p.trace, 1, i, 0);
+            mbar_wait(p_ready, i & 1, BT_P_READY);
+            tc_fence_after();
+            trace_mark(p.trace, 1, i, 1);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)
+              umma_ts(tmem + C::T_DV, tmem + C::T_P + kk * 8,
+                      umma_desc_sw128_a16(do_s + ds * TILE16 + kk * 128, C::CHUNK, 1024), IDESC_KD, (i > 0) || kk != 0);
+            tc_commit(do_empty + ds);
+            // ---- S^T for the next Q tile ----
+            if (has_next) {
+              const int sn = (i + 1) % C::QS;
+              mbar_wait(q_full + sn, ((i + 1) / C::QS) & 1, BT_Q_FULL);
+              tc_fence_after();
+              trace_mark(p.trace, 1, i, 2);
+              mma_kmajor_pair(tmem + C::T_S, k_s, q_s + sn * TILE16);
+              tc_commit(s_full);
+            }
+            // ---- dQ_i = dS K (drained while the next MMA runs) ; dK += dS^T Q_i ----
+            mbar_wait(ds_ready, i & 1, BT_DS_READY);
+            tc_fence_after();
+            trace_mark(p.trace, 1, i, 3);
+            if (!C::DQ_ALIASES_DP && i > 0) {
+              mbar_wait(dq_drained, (i - 1) & 1, BT_DQ_DRAINED);
+              tc_fence_after();
+            }
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)  // k = 16 keys per step
+              umma_ss(tmem + C::T_DQ, umma_desc_sw128_a16(ds_s + kk * 128, C::CHUNK, 1024),
+                      umma_desc_sw128_a16(k_s + kk * 128, C::CHUNK, 1024), IDESC_DQ, kk != 0);
+            tc_commit(dq_full);
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk)  // k = 16 query rows per step; dS^T tile is [key][q] in two 64-q boxes
+              umma_ss(tmem + C::T_DK, umma_desc_sw128_a16(ds_s + (kk >> 2) * CH16 + (kk & 3) * 2, 16, 1024),
+                      umma_desc_sw128_a16(q_s + s * TILE16 + kk * 128, C::CHUNK, 1024), IDESC_KD, (i > 0) || kk != 0);
+            tc_commit(q_empty + s);
+            tc_commit(ds_free);
+            // ---- dP^T for the next Q tile ----
+            if (has_next) {
+              if (C::DQ_ALIASES_DP) {
+                mbar_wait(dq_drained, i & 1, BT_DQ_DRAINED);
+                tc_fence_after();
+              }
+              trace_mark(p.trace, 1, i, 4);
+              const int dn = (i + 1) % C::DOS;
+              mbar_wait(do_full + dn, ((i + 1) / C::DOS) & 1, BT_DO_FULL);
+              tc_fence_after();
+              trace_mark(p.trace, 1, i, 5);
+              mma_kmajor_pair(tmem + C::T_DP, v_s, do_s + dn * TILE16);
+              tc_commit(dp_full);
+            }
+          }
+          tc_commit(dkv_full);
+          tc_commit(dkv_full + 1);
         }
+      } else if (warp == MMA_WARP1) {
+        // prologue: S^T(0), dP^T(0)
+        mbar_wait(q_full + 0, 0, BT_Q_FULL);
+        tc_fence_after();
+        mma_kmajor_pair(tmem + C::T_S, k_s, q_s);
+        tc_commit(s_full);
+        mbar_wait(do_full + 0, 0, BT_DO_FULL);
+        tc_fence_after();
+        mma_kmajor_pair(tmem + C::T_DP, v_s, do_s);
+        tc_commit(dp_full);
+        for (int i = 0; i < n_q; ++i) {
+          const int ds = i % C::DOS;
+          const bool has_next = i + 1 < n_q;
+          // ---- dV += P^T dO_i ----
+          trace_mark(p.trace, 3, i, 2);
+          mbar_wait(p_ready, i & 1, BT_P_READY);
+          tc_fence_after();
+          trace_mark(p.trace, 3, i, 3);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)
+            umma_ts(tmem + C::T_DV, tmem + C::T_P + kk * 8,
+                    umma_desc_sw128_a16(do_s + ds * TILE16 + kk * 128, C::CHUNK, 1024), IDESC_KD, (i > 0) || kk != 0);
+          tc_commit(do_empty + ds);  // dP^T(i) was issued by this thread before dV(i): one commit covers both readers
+          if (has_next) {
+            // ---- S^T(i+1) = K Q_{i+1}^T ----
+            const int sn = (i + 1) % C::QS, dn = (i + 1) % C::DOS;
+            mbar_wait(q_full + sn, ((i + 1) / C::QS) & 1, BT_Q_FULL);
+            tc_fence_after();
+            mma_kmajor_pair(tmem + C::T_S, k_s, q_s + sn * TILE16);
+            tc_commit(s_full);
+            // ---- dP^T(i+1) = V dO_{i+1}^T ----
+            mbar_wait(do_full + dn, ((i + 1) / C::DOS) & 1, BT_DO_FULL);
+            if (C::DQ_ALIASES_DP) mbar_wait(dq_drained, i & 1, BT_DQ_DRAINED);  // dQ(i) has left these columns
+            else mbar_wait(ds_ready, i & 1, BT_DS_READY);                        // dP^T(i) has been read
+            tc_fence_after();
+            trace_mark(p.trace, 3, i, 4);
+            mma_kmajor_pair(tmem + C::T_DP, v_s, do_s + dn * TILE16);
+            tc_commit(dp_full);
+          }
+        }
+        tc_commit(dkv_full + 1);
+      } else {
+        for (int i = 0; i < n_q; ++i) {
+          const int s = i % C::QS;
+          // ---- dQ_i = dS K (drained while the next MMAs run) ; dK += dS^T Q_i ----
+          trace_mark(p.trace, 1, i, 0);
+          mbar_wait(ds_ready, i & 1, BT_DS_READY);
+          if (!C::DQ_ALIASES_DP && i > 0) mbar_wait(dq_drained, (i - 1) & 1, BT_DQ_DRAINED);
+          tc_fence_after();
+          trace_mark(p.trace, 1, i, 1);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)  // k = 16 keys per step
+            umma_ss(tmem + C::T_DQ, umma_desc_sw128_a16(ds_s + kk * 128, C::CHUNK, 1024),
+                    umma_desc_sw128_a16(k_s + kk * 128, C::CHUNK, 1024), IDESC_DQ, kk != 0);
+          tc_commit(dq_full);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)  // k = 16 query rows per step; dS^T tile is [key][q] in two 64-q boxes
+            umma_ss(tmem + C::T_DK, umma_desc_sw128_a16(ds_s + (kk >> 2) * CH16 + (kk & 3) * 2, 16, 1024),
+                    umma_desc_sw128_a16(q_s + s * TILE16 + kk * 128, C::CHUNK, 1024), IDESC_KD, (i > 0) || kk != 0);
+          tc_commit(q_empty + s);
+          tc_commit(ds_free);
+          trace_mark(p.trace, 1, i, 2);
+        }
+        tc_commit(dkv_full);
       }
-      tc_commit(dkv_full);
     }
   } else if (warp >= 8) {
     // ================================ dQ drain warpgroup ===========================================
@@ -485,6 +568,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 
     // ---- epilogue: dV, dK (this warpgroup's half of the head dim) ---------------------------------
     mbar_wait(dkv_full, 0, BT_DKV_FULL);
+    mbar_wait(dkv_full + 1, 0, BT_DKV_FULL);
     tc_fence_after();
     constexpr int HC = D / 2;
     const bool store_row = kv0 + krow < k_rows_total;

@@ -176,9 +176,12 @@ attn_fwd_alt_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     if (elect_one()) {
       // TWO issuer threads take alternate key blocks. A tcgen05.mma / commit sequence holds its issuing thread until
       // the tensor pipe has nearly drained it, and the scalar tail of the loop (barrier polls, counters, the back-edge:
-      // ~400 cycles measured, mostly instruction fetch of a lone warp) would then leave the pipe idle before the next
+      // ~400 cycles measured for a lone thread next to four busy warps) would then leave the pipe idle before the next
       // block. With two issuers one thread's tail overlaps the other's MMAs. P V of consecutive blocks must still
-      // enter the pipe in block order (pv_done counts one phase per block), which the tok[] hand-off enforces.
+      // execute in block order (pv_done counts one phase per block; P V of block 0 initialises O). A plain arrive does
+      // not order two threads' MMAs — it can overtake the arriving thread's own tcgen05.mma — so the hand-off is a
+      // tcgen05.commit: issuer i may queue P V of block j + 1 once P V of block j has completed. By then Q K^T of block
+      // j + 3 (queued behind P V(j) by the same thread, 512 cycles long) is executing, so the pipe does not drain.
       const int me = (warp == MMA_WARP) ? 0 : 1;
       constexpr uint32_t IDESC_QK = umma_idesc_bf16(128, 128, 0, 0);  // A = Q K-major, B = K K-major
       constexpr uint32_t IDESC_PV = umma_idesc_bf16(128, D, 0, 1);    // A = P (TMEM), B = V MN-major
@@ -216,14 +219,14 @@ attn_fwd_alt_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
         mbar_wait(v_full + buf, static_cast<uint32_t>(j / 3) & 1u, AT_V_FULL);
         trace_mark(p.trace, 1 + 2 * me, j, 0);
         mbar_wait(p_full + me, half & 1u, AT_P_FULL);
-        if (j > 0) mbar_wait(tok + me, (me == 1 ? half : half + 1u) & 1u, AT_TOK);  // P V of block j - 1 is queued
+        if (j > 0) mbar_wait(tok + me, (me == 1 ? half : half + 1u) & 1u, AT_TOK);  // P V of block j - 1 has completed
         tc_fence_after();
         trace_mark(p.trace, 1 + 2 * me, j, 1);
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk)  // 16 keys per MMA; V tile: [128 keys][64 d] x 2 boxes, MN-major B
           umma_ts(tmem_base + C::T_O, tmem_base + C::T_S + buf * 128 + kk * 8,
                   umma_desc_sw128_a16(v_smem + buf * TILE16 + kk * 128, C::CHUNK, 1024), IDESC_PV, (j > 0) || kk != 0);
-        mbar_arrive(tok + (me ^ 1));
+        tc_commit(tok + (me ^ 1));  // arrives when this P V has COMPLETED (see above)
         tc_commit(pv_done);
         tc_commit(v_empty + buf);
         trace_mark(p.trace, 1 + 2 * me, j, 2);

@@ -377,6 +377,9 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "B": 1, "L": SEQ, "img_tokens": IMG_TOKENS, "txt_tokens": TXT_TOKENS,
                    "H": HEADS, "D": HEAD_DIM, "flops_per_step": step_flops,
                    "parallelism": "single" if world == 1 else f"ulysses_sp{world}",
+                   **({} if world == 1 else {"exchange": (
+                       "q/k/v + gradients: NCCL all_to_all; forward O: peer stores from the attention epilogue "
+                       "(symmetric memory over NVLink)" if sp.fused_exchange_available(q, None) else "NCCL all_to_all")}),
                    "l2": "inputs (4 x 731 MB) exceed the 126 MB L2; no flush needed"},
         "clocks": clk,
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

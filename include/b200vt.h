@@ -80,6 +80,19 @@ int vt_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse
                 const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k, int num_segments, int max_seqlen_q,
                 int max_seqlen_k, const int32_t* seqlens_k, float softmax_scale, void* stream);
 
+/* vt_attn_fwd (fixed mode, B == 1, D == 128) with the Ulysses "head -> sequence" exchange fused into the epilogue:
+ * besides the local o / lse, query row l < n_peers * rows_per_peer of head h is also stored through NVLink to
+ *   (bf16*)peer_bases[l / rows_per_peer] + (l % rows_per_peer) * peer_strides[0] + h * peer_strides[1]
+ * peer_bases: HOST array of n_peers (<= 8) peer-mapped device pointers (symmetric memory; entry r is rank r's
+ * sequence-sharded output buffer, already offset to this rank's head slot). Rows past n_peers * rows_per_peer
+ * (replicated text tokens) stay local. Replaces xfuser's output all-to-all as called from hunyuan parallel_attention
+ * (attenion.py:169-180) and wan usp_attn_forward (xdit_context_parallel.py:179-186). The caller synchronises the ranks
+ * before the launch (destination buffers free) and after it (all stores visible). */
+int vt_attn_fwd_scatter(const void* q, const void* k, const void* v, void* o, float* lse, const int64_t* q_strides,
+                        const int64_t* k_strides, const int64_t* v_strides, const int64_t* o_strides, int H, int Lq, int Lk,
+                        int D, const int32_t* seqlens_k, float softmax_scale, void* const* peer_bases, int n_peers,
+                        int rows_per_peer, const int64_t* peer_strides, void* stream);
+
 /* Bytes of device workspace vt_attn_bwd needs (fp32 dQ accumulator + delta = rowsum(dO*O)). */
 int64_t vt_attn_bwd_workspace_bytes(int B, int H, int Lq, int D);
 

@@ -27,6 +27,8 @@ _SIGS = {
     "vt_profile_read": [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)],
     "vt_attn_fwd": [vp, vp, vp, vp, vp, c_i64p, c_i64p, c_i64p, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                     vp, vp, C.c_int, C.c_int, C.c_int, vp, C.c_float, vp],
+    "vt_attn_fwd_scatter": [vp, vp, vp, vp, vp, c_i64p, c_i64p, c_i64p, c_i64p, C.c_int, C.c_int, C.c_int, C.c_int, vp,
+                            C.c_float, C.POINTER(vp), C.c_int, C.c_int, c_i64p, vp],
     "vt_attn_bwd_workspace_bytes": [C.c_int, C.c_int, C.c_int, C.c_int],
     "vt_attn_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp] + [c_i64p] * 8 + [C.c_int] * 5 + [vp, vp, C.c_int, C.c_int,
                     C.c_int, vp, C.c_float, vp, C.c_int64, vp],

@@ -35,6 +35,13 @@ struct AttnFwdParams {
   int64_t lse_sb, lse_sh;    // element strides of lse (row stride 1)
   float scale;               // softmax scale
   float scale_log2;          // scale * log2(e)
+  // Optional fused "head -> sequence" exchange of Ulysses sequence parallelism (sc_n > 0, fixed mode, B == 1): besides
+  // the local o, query row l < sc_n * sc_rpr of head h is also stored to rank l / sc_rpr at
+  //   sc_base[l / sc_rpr] + (l % sc_rpr) * sc_sl + h * sc_sh
+  // through its peer-mapped pointer (NVLink), so the output all-to-all needs no separate kernel or pack copy.
+  __nv_bfloat16* sc_base[8];
+  int sc_n, sc_rpr;
+  int64_t sc_sl, sc_sh;
 };
 
 struct AttnBwdParams {

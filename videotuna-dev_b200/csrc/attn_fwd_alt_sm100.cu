@@ -381,6 +381,7 @@ attn_fwd_alt_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
     __nv_bfloat16* optr = p.o + bq * p.o_sb + static_cast<int64_t>(q_base + row_g) * p.o_sl + h * p.o_sh + part * 32;
     {
       uint32_t ou[32];
+      uint4 wv[4];
       tmem_ld_x32(tmem_base + lane_addr + C::T_O + part * 32, ou);
       tc_wait_ld();
       if (valid_row) {
@@ -392,6 +393,14 @@ attn_fwd_alt_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
           w.z = pack_bf16x2(__uint_as_float(ou[c + 4]) * inv, __uint_as_float(ou[c + 5]) * inv);
           w.w = pack_bf16x2(__uint_as_float(ou[c + 6]) * inv, __uint_as_float(ou[c + 7]) * inv);
           *reinterpret_cast<uint4*>(optr + c) = w;
+          wv[c >> 3] = w;
+        }
+        if (p.sc_n > 0 && row_g < p.sc_n * p.sc_rpr) {
+          // fused exchange: the same 64 bytes go to the rank that owns this query row (peer-mapped pointer)
+          const int dst = row_g / p.sc_rpr;
+          __nv_bfloat16* pptr = p.sc_base[dst] + static_cast<int64_t>(row_g - dst * p.sc_rpr) * p.sc_sl + h * p.sc_sh + part * 32;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) *reinterpret_cast<uint4*>(pptr + c * 8) = wv[c];
         }
       }
     }

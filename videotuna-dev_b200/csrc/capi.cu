@@ -231,10 +231,17 @@ static int check_attn_common(int B, int H, int Lq, int Lk, int D, int num_segmen
   return 0;
 }
 
-int vt_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const int64_t* q_strides,
-                const int64_t* k_strides, const int64_t* v_strides, const int64_t* o_strides, int B, int H, int Lq,
-                int Lk, int D, const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k, int num_segments,
-                int max_seqlen_q, int max_seqlen_k, const int32_t* seqlens_k, float softmax_scale, void* stream) {
+struct FwdScatter {
+  void* const* bases;
+  int n, rows_per_peer;
+  const int64_t* strides;  // (row, head) element strides at the destination
+};
+
+static int attn_fwd_impl(const void* q, const void* k, const void* v, void* o, float* lse, const int64_t* q_strides,
+                         const int64_t* k_strides, const int64_t* v_strides, const int64_t* o_strides, int B, int H, int Lq,
+                         int Lk, int D, const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k, int num_segments,
+                         int max_seqlen_q, int max_seqlen_k, const int32_t* seqlens_k, float softmax_scale,
+                         const FwdScatter* sc, void* stream) {
   VT_REQUIRE(q && k && v && o && lse && q_strides && k_strides && v_strides && o_strides, VT_ERR_NULL,
              "vt_attn_fwd: NULL argument");
   if (int rc = check_attn_common(B, H, Lq, Lk, D, num_segments, cu_seqlens_q, cu_seqlens_k, max_seqlen_q, max_seqlen_k)) return rc;
@@ -268,11 +275,43 @@ int vt_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse
   p.lse_sh = Lq;
   p.scale = softmax_scale;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  if (sc != nullptr) {
+    VT_REQUIRE(D == 128 && num_segments == 0 && B == 1, VT_ERR_UNSUPPORTED,
+               "the fused exchange epilogue needs head dim 128, fixed mode and batch 1");
+    VT_REQUIRE(sc->bases && sc->strides && sc->n >= 1 && sc->n <= 8 && sc->rows_per_peer >= 1 &&
+                   static_cast<int64_t>(sc->n) * sc->rows_per_peer <= Lq, VT_ERR_SHAPE, "bad peer layout");
+    VT_REQUIRE(sc->strides[0] % 8 == 0 && sc->strides[1] % 8 == 0, VT_ERR_ALIGN, "peer strides must be multiples of 8");
+    for (int i = 0; i < sc->n; ++i) {
+      VT_REQUIRE(sc->bases[i] != nullptr && aligned16(sc->bases[i]), VT_ERR_ALIGN, "peer base %d is NULL or misaligned", i);
+      p.sc_base[i] = static_cast<__nv_bfloat16*>(sc->bases[i]);
+    }
+    p.sc_n = sc->n;
+    p.sc_rpr = sc->rows_per_peer;
+    p.sc_sl = sc->strides[0];
+    p.sc_sh = sc->strides[1];
+  }
   {
     ProfScope span(VT_K_ATTN_FWD, static_cast<cudaStream_t>(stream));
     VT_CHECK_CUDA(launch_attn_fwd(D, tm_q, tm_k, tm_v, p, 0, static_cast<cudaStream_t>(stream)));
   }
   return 0;
+}
+
+int vt_attn_fwd(const void* q, const void* k, const void* v, void* o, float* lse, const int64_t* q_strides,
+                const int64_t* k_strides, const int64_t* v_strides, const int64_t* o_strides, int B, int H, int Lq,
+                int Lk, int D, const int32_t* cu_seqlens_q, const int32_t* cu_seqlens_k, int num_segments,
+                int max_seqlen_q, int max_seqlen_k, const int32_t* seqlens_k, float softmax_scale, void* stream) {
+  return attn_fwd_impl(q, k, v, o, lse, q_strides, k_strides, v_strides, o_strides, B, H, Lq, Lk, D, cu_seqlens_q,
+                       cu_seqlens_k, num_segments, max_seqlen_q, max_seqlen_k, seqlens_k, softmax_scale, nullptr, stream);
+}
+
+int vt_attn_fwd_scatter(const void* q, const void* k, const void* v, void* o, float* lse, const int64_t* q_strides,
+                        const int64_t* k_strides, const int64_t* v_strides, const int64_t* o_strides, int H, int Lq, int Lk,
+                        int D, const int32_t* seqlens_k, float softmax_scale, void* const* peer_bases, int n_peers,
+                        int rows_per_peer, const int64_t* peer_strides, void* stream) {
+  const FwdScatter sc{peer_bases, n_peers, rows_per_peer, peer_strides};
+  return attn_fwd_impl(q, k, v, o, lse, q_strides, k_strides, v_strides, o_strides, 1, H, Lq, Lk, D, nullptr, nullptr, 0,
+                       0, 0, seqlens_k, softmax_scale, &sc, stream);
 }
 
 static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }

@@ -7,7 +7,7 @@ formula wired to the matching backward entry point. There is deliberately no CPU
 from __future__ import annotations
 
 import ctypes as C
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 from torch import Tensor
@@ -111,6 +111,40 @@ def _(dout, q, k, v, o, lse, cu_seqlens_q, cu_seqlens_k, seqlens_k, max_seqlen_q
     return torch.empty_like(q, memory_format=torch.contiguous_format), \
         torch.empty_like(k, memory_format=torch.contiguous_format), \
         torch.empty_like(v, memory_format=torch.contiguous_format)
+
+
+@torch.library.custom_op("b200vt::attn_fwd_scatter", mutates_args=("peer_anchor",), device_types="cuda")
+def attn_fwd_scatter(q: Tensor, k: Tensor, v: Tensor, seqlens_k: Optional[Tensor], softmax_scale: float,
+                     peer_anchor: Tensor, peer_ptrs: Sequence[int], rows_per_peer: int, peer_stride_l: int,
+                     peer_stride_h: int) -> Tuple[Tensor, Tensor]:
+    """attn_fwd (B == 1, D == 128) with the Ulysses head -> sequence exchange fused into the epilogue: query row l of
+    local head h is also stored to rank l // rows_per_peer at peer_ptrs[rank] + (l % rows_per_peer) * peer_stride_l +
+    h * peer_stride_h (bf16 elements; peer_ptrs are peer-mapped addresses of every rank's symmetric output buffer,
+    already offset to this rank's head slot). peer_anchor is this rank's own buffer (declared mutated). The caller
+    synchronises the ranks before and after. Returns the local o (head layout, kept for backward) and lse."""
+    for n, t in (("q", q), ("k", k), ("v", v)):
+        _check_bf16_cuda(n, t)
+    q, k, v = _blhd(q), _blhd(k), _blhd(v)
+    B, Lq, H, D = q.shape
+    if B != 1:
+        raise RuntimeError("b200vt: the fused exchange epilogue needs batch 1")
+    Lk = k.shape[1]
+    o = torch.empty((B, Lq, H, D), dtype=q.dtype, device=q.device)
+    lse = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device)
+    n = len(peer_ptrs)
+    bases = (_vp * n)(*[_vp(int(a)) for a in peer_ptrs])
+    pst = (C.c_int64 * 2)(int(peer_stride_l), int(peer_stride_h))
+    with torch.cuda.device(q.device):
+        _lib.call("vt_attn_fwd_scatter", _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(lse), _lib.strides3(q),
+                  _lib.strides3(k), _lib.strides3(v), _lib.strides3(o), H, Lq, Lk, D, _ptr(seqlens_k),
+                  float(softmax_scale), bases, n, int(rows_per_peer), pst, _stream())
+    return o, lse
+
+
+@attn_fwd_scatter.register_fake
+def _(q, k, v, seqlens_k, softmax_scale, peer_anchor, peer_ptrs, rows_per_peer, peer_stride_l, peer_stride_h):
+    B, Lq, H, D = q.shape
+    return q.new_empty((B, Lq, H, D)), q.new_empty((B, H, Lq), dtype=torch.float32)
 
 
 def _attn_setup(ctx, inputs, output):

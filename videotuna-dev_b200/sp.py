@@ -19,6 +19,9 @@ SP correctness is *defined* as equality with the single-GPU result on the same i
 """
 from __future__ import annotations
 
+import importlib
+import math
+import os
 from typing import Callable, Optional
 
 import torch
@@ -168,6 +171,79 @@ class _FillRear(torch.autograd.Function):
         return g, g[:, L:]
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# fused exchange: the attention kernel's epilogue writes O straight into the destination ranks' buffers (NVLink peer
+# stores through symmetric memory), replacing the output all-to-all and its pack copy
+# ---------------------------------------------------------------------------------------------------------------------
+class _PeerBuffers:
+    """One symmetric (S_loc, H, D) bf16 output buffer per (group, shape), with every rank's peer-mapped address."""
+    _cache: dict = {}
+
+    def __init__(self, group, s_loc: int, H: int, D: int, device):
+        import torch.distributed._symmetric_memory as symm
+        pg = group if group is not None else dist.group.WORLD
+        self.buf = symm.empty((s_loc, H, D), dtype=torch.bfloat16, device=device)
+        self.handle = symm.rendezvous(self.buf, pg)
+        self.ptrs = [int(a) for a in self.handle.buffer_ptrs]
+
+    @classmethod
+    def get(cls, group, s_loc: int, H: int, D: int, device) -> "_PeerBuffers":
+        key = (id(group), s_loc, H, D, str(device))
+        if key not in cls._cache:
+            cls._cache[key] = cls(group, s_loc, H, D, device)
+        return cls._cache[key]
+
+
+class _FusedAttnExchange(torch.autograd.Function):
+    """out_seq (1, L/P, H, D) = head_to_seq(attention(q, k, v)) for head-sharded q, k, v (1, L [+ T], H/P, D), with the
+    exchange done by the kernel epilogue. Backward: the adjoint exchange of dO (NCCL all-to-all, `seq_to_head`) followed
+    by the ordinary backward kernel on the locally kept head-layout O. Rows past L (replicated text) come back as a
+    second, local tensor."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, group, scale, n_img):
+        from . import ops
+        P, r = _world(group), _rank(group)
+        _, Ltot, Hp, D = q.shape
+        s_loc = n_img // P
+        pb = _PeerBuffers.get(group, s_loc, Hp * P, D, q.device)
+        ptrs = [a + r * Hp * D * 2 for a in pb.ptrs]  # this rank's head slot inside every destination row
+        pb.handle.barrier(channel=0)                   # every rank has consumed the previous contents of its buffer
+        o, lse = ops.attn_fwd_scatter(q, k, v, None, float(scale), pb.buf, ptrs, s_loc, Hp * P * D, D)
+        pb.handle.barrier(channel=1)                   # all peers' stores into this rank's buffer are complete
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.group, ctx.scale, ctx.n_img = group, scale, n_img
+        return pb.buf.unsqueeze(0).clone(), o[:, n_img:]
+
+    @staticmethod
+    def backward(ctx, d_seq, d_txt):
+        from . import ops
+        q, k, v, o, lse = ctx.saved_tensors
+        P = _world(ctx.group)
+        d_head = _unpack_seq_to_head(_a2a(_pack_seq_to_head(d_seq.contiguous(), P), ctx.group))  # (1, L, H/P, D)
+        if o.shape[1] > ctx.n_img:
+            d_txt = d_txt if d_txt is not None else torch.zeros_like(o[:, ctx.n_img:])
+            d_head = torch.cat([d_head, d_txt], dim=1)
+        dq, dk, dv = ops.attn_bwd(d_head, q, k, v, o, lse, None, None, None, q.shape[1], k.shape[1], float(ctx.scale))
+        return dq, dk, dv, None, None, None
+
+
+def fused_exchange_available(q: Tensor, group) -> bool:
+    """The fused epilogue needs CUDA bf16, head dim 128, batch 1, P <= 8 and torch symmetric memory over NVLink."""
+    if not (q.is_cuda and q.dtype == torch.bfloat16 and q.shape[0] == 1 and q.shape[-1] == 128):
+        return False
+    if os.environ.get("B200VT_SP_FUSED", "1") == "0" or not dist.is_initialized():
+        return False
+    P = _world(group)
+    if P < 2 or P > 8:
+        return False
+    try:
+        importlib.import_module("torch.distributed._symmetric_memory")
+    except Exception:  # noqa: BLE001
+        return False
+    return dist.get_backend(group) == "nccl"
+
+
 def _default_attn(q: Tensor, k: Tensor, v: Tensor, softmax_scale: Optional[float]) -> Tensor:
     from . import functional as Fn  # CUDA kernels; raises without the library — there is no CPU path
     return Fn.attention_blhd(q, k, v, softmax_scale=softmax_scale)
@@ -210,6 +286,15 @@ class UlyssesAttention:
             q = _FillRear.apply(q, joint_tensor_query[:, :, sl])
             k = _FillRear.apply(k, joint_tensor_key[:, :, sl])
             v = _FillRear.apply(v, joint_tensor_value[:, :, sl])
+        if self.attn_fn is _default_attn and fused_exchange_available(q, self.group):
+            # attention with the output exchange fused into its epilogue (peer stores over NVLink)
+            scale = 1.0 / math.sqrt(q.shape[-1]) if softmax_scale is None else float(softmax_scale)
+            img, txt = _FusedAttnExchange.apply(q, k, v, self.group, scale, q.shape[1] - T)
+            if not T:
+                return img
+            if P > 1:
+                txt = _GatherHeads.apply(txt, self.group)
+            return torch.cat([img, txt], dim=1)
         out = self.attn_fn(q, k, v, softmax_scale)
         if not T:
             return head_to_seq(out, self.group)

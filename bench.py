@@ -201,6 +201,46 @@ def run_reference(args):
 # =====================================================================================================================
 # GPU legs
 # =====================================================================================================================
+OTHER_SHAPES = {  # (B, Lq, Lk, H, D)
+    "k2_wan14b_480x832x81_self": (1, 32760, 32760, 40, 128),
+    "k3_cogvideox2b_480x720x49": (1, 17776, 17776, 30, 64),
+    "k4_videocrafter2_spatial_self_level0_b2": (32, 2560, 2560, 5, 64),
+}
+
+
+def other_configs(torch, dev, iters: int = 5):
+    """Attention fwd+bwd TFLOP/s of the remaining configurations through the same ops (CUDA events, median of `iters`)."""
+    import math
+
+    import b200vt.ops as ops
+    out = {}
+    for name, (B, Lq, Lk, H, D) in OTHER_SHAPES.items():
+        g = torch.Generator(device=dev).manual_seed(SEED)
+        q, k, v, do = (torch.randn(B, n, H, D, device=dev, dtype=torch.bfloat16, generator=g) for n in (Lq, Lk, Lk, Lq))
+        scale = 1.0 / math.sqrt(D)
+
+        def step():
+            o, lse = ops.attn_fwd(q, k, v, None, None, None, Lq, Lk, scale)
+            ops.attn_bwd(do, q, k, v, o, lse, None, None, None, Lq, Lk, scale)
+
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sorted(ts)[len(ts) // 2]
+        out[name] = {"ms_fwd_bwd": round(ms, 3), "tflops": round(flops_fwd_bwd(Lq, Lk, H, D, B) / (ms * 1e-3) / 1e12, 1)}
+        del q, k, v, do
+        torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -362,6 +402,13 @@ def run_ours(args):
     }
     gpu_launches = int(sum(n for _, n in prof.values()))
 
+    # ---- the other BASELINE.json configurations, attention only (N = 1; context for the reader, not the headline) ----
+    others = None
+    if world == 1:
+        del host_attn, host_in, host_out
+        torch.cuda.empty_cache()
+        others = other_configs(torch, dev)
+
     # ---- CPU baseline (N = 1 only): oracle port of the reference's torch path on a bounded sample ----------------
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -388,6 +435,7 @@ def run_ours(args):
         "gpu_launches": gpu_launches,
         "roofline": roofline,
         "cpu_baseline": cpu,
+        **({"other_configs": others} if others else {}),
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -1,0 +1,141 @@
+"""Achieved HBM bandwidth of the memory-bound kernels around attention at the BASELINE shapes, next to
+the same arithmetic written with stock PyTorch ops on the same GPU (what the reference's block code launches).
+Algorithmic bytes per element are the ones DESIGN.md states; the roofline is the measured copy bandwidth in
+MEASURED_PEAKS.json. CUDA-event timing, 3 warm-ups, median of `--iters`; every tensor is far larger than the 126 MB L2.
+    python tools/bench_rowwise.py [--iters 10]"""
+import argparse
+import json
+import math
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import b200vt.functional as Fn  # noqa: E402
+import b200vt.ops as ops  # noqa: E402
+
+
+def timeit(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sorted(ts)[len(ts) // 2]
+
+
+def peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=10)
+    args = ap.parse_args()
+    dev = "cuda"
+    peak, src = peak_gbs()
+    g = torch.Generator(device=dev).manual_seed(20230211)
+
+    def rn(*shape, dtype=torch.bfloat16):
+        return torch.randn(*shape, device=dev, dtype=torch.float32, generator=g).to(dtype)
+
+    def report(name, shape, nbytes, ours_ms, torch_ms, note=""):
+        rec = {"kernel": name, "shape": list(shape), "algorithmic_MB": round(nbytes / 1e6, 1), "ours_ms": round(ours_ms, 4),
+               "ours_GBps": round(nbytes / ours_ms / 1e6, 1), "frac_of_hbm_peak": round(nbytes / ours_ms / 1e6 / peak, 3),
+               "torch_ops_ms": round(torch_ms, 4), "speedup_vs_torch_ops": round(torch_ms / ours_ms, 2),
+               "peak_GBps": peak, "peak_kind": src}
+        if note:
+            rec["note"] = note
+        print(json.dumps(rec), flush=True)
+
+    # ---- LayerNorm + modulate (Hunyuan K1 image stream; Wan C5 with the fp32 residual stream) -----------------------
+    for tag, (B, L, C), xdt in (("hunyuan_k1", (1, 119056, 3072), torch.bfloat16), ("wan_c5_fp32_stream", (1, 32760, 5120), torch.float32)):
+        x = rn(B, L, C, dtype=xdt).requires_grad_(True)
+        sc, sh = rn(B, C, dtype=torch.float32) * 0.1, rn(B, C, dtype=torch.float32) * 0.1
+        dy = rn(B, L, C)
+        esz = x.element_size()
+        y = Fn.ln_modulate(x, sh, sc, eps=1e-6)
+        f_ms = timeit(lambda: Fn.ln_modulate(x, sh, sc, eps=1e-6), args.iters)
+        b_ms = timeit(lambda: torch.autograd.grad(y, x, dy, retain_graph=True), args.iters)
+
+        def ref():
+            return (F.layer_norm(x.float(), (C,), eps=1e-6) * (1 + sc[:, None]) + sh[:, None]).to(torch.bfloat16)
+        yr = ref()
+        rf_ms = timeit(ref, args.iters)
+        rb_ms = timeit(lambda: torch.autograd.grad(yr, x, dy, retain_graph=True), args.iters)
+        n = B * L * C
+        report(f"ln_modulate_fwd[{tag}]", (B, L, C), n * (esz + 2), f_ms, rf_ms)
+        report(f"ln_modulate_bwd[{tag}]", (B, L, C), n * (2 + esz + esz), b_ms, rb_ms)
+        del x, y, yr, dy
+
+    # ---- gated residual -------------------------------------------------------------------------------------------
+    for tag, (B, L, C), xdt in (("hunyuan_k1", (1, 119056, 3072), torch.bfloat16), ("wan_c5_fp32_stream", (1, 32760, 5120), torch.float32)):
+        x, br, gate = rn(B, L, C, dtype=xdt), rn(B, L, C), rn(B, C, dtype=torch.float32)
+        f_ms = timeit(lambda: Fn.gate_residual(x, br, gate), args.iters)
+        rf_ms = timeit(lambda: x + br * gate[:, None].to(br.dtype if xdt == torch.bfloat16 else torch.float32), args.iters)
+        n = B * L * C
+        report(f"gate_residual_fwd[{tag}]", (B, L, C), n * (2 * x.element_size() + 2), f_ms, rf_ms)
+        del x, br
+
+    # ---- fused QK-RMSNorm + RoPE on the strided q view of a fused QKV projection (Hunyuan K1) -------------------------
+    B, L, H, D = 1, 118800, 24, 128
+    qkv = rn(B, L, 3, H, D)
+    w = (1 + 0.1 * rn(D, dtype=torch.float32))
+    ang = torch.rand(L, D // 2, device=dev, generator=g) * 6.28
+    cos, sin = ang.cos().repeat_interleave(2, dim=1).contiguous(), ang.sin().repeat_interleave(2, dim=1).contiguous()
+    q = qkv[:, :, 0]
+    f_ms = timeit(lambda: Fn.qk_rmsnorm_rope(q, w, cos, sin), args.iters)
+
+    def ref_rope():
+        xf = q.float()
+        n_ = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)).to(q.dtype) * w.to(q.dtype)
+        nf = n_.float()
+        xr, xi = nf.reshape(*nf.shape[:-1], -1, 2).unbind(-1)
+        rot = torch.stack([-xi, xr], dim=-1).flatten(3)
+        return (nf * cos.view(1, L, 1, D) + rot * sin.view(1, L, 1, D)).to(q.dtype)
+    rf_ms = timeit(ref_rope, max(3, args.iters // 3))
+    n = B * L * H * D
+    report("qk_rmsnorm_rope_fwd[hunyuan_k1, strided q of fused qkv]", (B, L, H, D), n * 4 + 2 * L * D * 4, f_ms, rf_ms,
+           note="reference = hunyuan RMSNorm (fp32 temporaries) + apply_rotary_emb (rotate_half stack/flatten) as torch ops")
+    del qkv, q
+
+    # ---- GroupNorm(32) + SiLU (VideoCrafter2 UNet level 0 and level 2, batch 2 x 16 frames) -----------------------------
+    for (N, C, Hh, Ww) in ((32, 320, 40, 64), (32, 1280, 10, 16)):
+        x = rn(N, C, Hh, Ww)
+        gw, gb = 1 + 0.1 * rn(C, dtype=torch.float32), 0.1 * rn(C, dtype=torch.float32)
+        f_ms = timeit(lambda: Fn.groupnorm_silu(x, gw, gb, 32, 1e-5, silu=True), args.iters)
+        rf_ms = timeit(lambda: F.silu(F.group_norm(x.float(), 32, gw, gb, 1e-5).to(x.dtype)), args.iters)
+        n = x.numel()
+        report("groupnorm_silu_fwd[vc2]", (N, C, Hh, Ww), n * 4, f_ms, rf_ms,
+               note="reference = GroupNormSpecific (x.float() -> group_norm -> type(x.dtype)) + SiLU")
+        del x
+
+    # ---- temporal micro-attention, N = 16 frames (VideoCrafter2 level 0: 2 x 40 x 64 positions, 5 heads) --------------
+    Bt, N, H, D = 5120, 16, 5, 64
+    q, k, v = rn(Bt, N, H, D), rn(Bt, N, H, D), rn(Bt, N, H, D)
+    sc = 1 / math.sqrt(D)
+    f_ms = timeit(lambda: ops.temporal_attn_fwd(q, k, v, None, sc), args.iters)
+    qt, kt, vt = (t.permute(0, 2, 1, 3).reshape(Bt * H, N, D) for t in (q, k, v))
+
+    def ref_t():  # lvdm einsum / softmax / einsum (attention.py:128-144)
+        s = torch.einsum("b i d, b j d -> b i j", qt, kt) * sc
+        return torch.einsum("b i j, b j d -> b i d", s.softmax(dim=-1), vt)
+    rf_ms = timeit(ref_t, args.iters)
+    report("temporal_attn_fwd[vc2 level 0]", (Bt, N, H, D), q.numel() * 2 * 4, f_ms, rf_ms)
+
+
+if __name__ == "__main__":
+    main()

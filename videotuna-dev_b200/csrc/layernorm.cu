@@ -1,0 +1,430 @@
+// layernorm.cu — LayerNorm (+affine) + adaLN modulate, forward and backward, for the row widths the denoisers use.
+//
+// Second-generation layout of the kernels in rowwise.cu (which stay as the fallback for other widths). The first layout
+// gave every thread 8 columns and every CTA (C/8 = 384..640 threads) RPI rows per iteration: 95-128 registers x 384
+// threads left ONE CTA per SM and 24 KB of loads in flight — 32 % of the measured HBM bandwidth on the HunyuanVideo K1
+// activation (2.1 of 6.45 TB/s). Here a small CTA (64 or 128 threads) owns one row at a time, every thread holds VPT
+// 16-byte vectors of it (columns (j * T + t) * 8: each j is one coalesced sweep), the next row's loads are issued before
+// the current row is reduced (double buffering), statistics take two cheap 4-warp block sums per row (mean, then the
+// centred second moment), and the per-column factors (gamma, beta, 1 + scale, shift) live pre-combined in shared memory:
+//   y = xhat * mul + add,   mul = gamma * (1 + scale),   add = beta * (1 + scale) + shift.
+// 6-8 CTAs per SM with two rows each in flight keep ~100 KB of loads outstanding per SM.
+// Replaces: hunyuan modulate(LayerNorm(x)) (modulate_layers.py:31-49, models.py:161-164), wan norm(x).float()*(1+e)+e
+// (wan/modules/model.py:294-296, fp32 residual stream), lvdm nn.LayerNorm (lvdm/modules/attention.py:299-310).
+#include <cuda_bf16.h>
+
+#include "capi_util.h"
+
+namespace vt {
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+__device__ __forceinline__ uint4 ldg16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg16(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+
+// 8 consecutive row elements in their storage type
+template <typename T> struct Vec8;
+template <> struct Vec8<bf16> { uint4 a; };
+template <> struct Vec8<float> { uint4 a, b; };
+__device__ __forceinline__ void load8(const bf16* p, Vec8<bf16>& r) { r.a = ldg16(p); }
+__device__ __forceinline__ void load8(const float* p, Vec8<float>& r) { r.a = ldg16(p); r.b = ldg16(p + 4); }
+__device__ __forceinline__ void zero8(Vec8<bf16>& r) { r.a = make_uint4(0, 0, 0, 0); }
+__device__ __forceinline__ void zero8(Vec8<float>& r) { r.a = r.b = make_uint4(0, 0, 0, 0); }
+__device__ __forceinline__ void unpack(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void unpack(const Vec8<bf16>& r, float* f) { unpack(r.a, f); }
+__device__ __forceinline__ void unpack(const Vec8<float>& r, float* f) {
+  f[0] = __uint_as_float(r.a.x); f[1] = __uint_as_float(r.a.y); f[2] = __uint_as_float(r.a.z); f[3] = __uint_as_float(r.a.w);
+  f[4] = __uint_as_float(r.b.x); f[5] = __uint_as_float(r.b.y); f[6] = __uint_as_float(r.b.z); f[7] = __uint_as_float(r.b.w);
+}
+__device__ __forceinline__ uint4 pack(const float* f) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return u;
+}
+__device__ __forceinline__ void store8(bf16* p, const float* f) { stg16(p, pack(f)); }
+__device__ __forceinline__ void store8(float* p, const float* f) {
+  stg16(p, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+  stg16(p + 4, make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
+}
+__device__ __forceinline__ void lds8(const float* p, float* f) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+template <int T, int NV>
+__device__ __forceinline__ void block_sum(float* v, float* red /* [2][T/32][NV] */, int parity) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(0xffffffffu, v[i], o);
+  constexpr int NW = T / 32;
+  if (NW == 1) return;
+  float* r = red + parity * NW * NV;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) r[warp * NV + i] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float t = r[i];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) t += r[w * NV + i];
+    v[i] = t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------------
+template <typename XT, int T, int VPT>
+__global__ void __launch_bounds__(T) ln_fwd_kernel(const XT* __restrict__ x, bf16* __restrict__ y, float* __restrict__ mean_out,
+                                                   float* __restrict__ rstd_out, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, const float* __restrict__ scale,
+                                                   const float* __restrict__ shift, int L, int C, float eps) {
+  extern __shared__ __align__(16) float sm[];  // mul[CP], add[CP], red[2 uses][2 parities][T/32]   (CP = T * VPT * 8 >= C)
+  constexpr int CP = T * VPT * 8;
+  float* mul = sm;
+  float* add = sm + CP;
+  float* red = sm + 2 * CP;
+  const int b = blockIdx.y, t = threadIdx.x;
+  for (int c = t; c < CP; c += T) {
+    float g = 1.f, be = 0.f, s1 = 1.f, sh = 0.f;
+    if (c < C) {
+      if (gamma) g = gamma[c];
+      if (beta) be = beta[c];
+      if (scale) s1 = 1.f + scale[static_cast<size_t>(b) * C + c];
+      if (shift) sh = shift[static_cast<size_t>(b) * C + c];
+    }
+    mul[c] = g * s1;
+    add[c] = be * s1 + sh;
+  }
+  __syncthreads();
+  bool act[VPT];
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) act[j] = (j * T + t) * 8 < C;
+  const size_t base = static_cast<size_t>(b) * L;
+  Vec8<XT> cur[VPT], nxt[VPT];
+  int l = blockIdx.x;
+  if (l < L) {
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      zero8(cur[j]);
+      if (act[j]) load8(x + (base + l) * C + (j * T + t) * 8, cur[j]);
+    }
+  }
+  int parity = 0;
+  for (; l < L; l += gridDim.x, parity ^= 1) {
+    const int ln = l + gridDim.x;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      zero8(nxt[j]);
+      if (ln < L && act[j]) load8(x + (base + ln) * C + (j * T + t) * 8, nxt[j]);
+    }
+    // two plain block sums (mean, then centred second moment): 2 x (5 shuffles + one 4-warp barrier) per row — cheaper
+    // than a single Chan merge of (n, mean, M2) triples, whose unequal-count form costs a division per butterfly stage
+    float f[VPT][8];
+    float s[1] = {0.f};
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      unpack(cur[j], f[j]);  // inactive vectors are zeros
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[0] += f[j][i];
+    }
+    block_sum<T, 1>(s, red, parity);
+    const float mean = s[0] / C;
+    float q[1] = {0.f};
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      if (act[j]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float d = f[j][i] - mean;
+          q[0] += d * d;
+        }
+      }
+    }
+    block_sum<T, 1>(q, red + 2 * (T / 32), parity);
+    const float rstd = rsqrtf(q[0] / C + eps);
+    if (t == 0) {
+      if (mean_out) mean_out[base + l] = mean;
+      if (rstd_out) rstd_out[base + l] = rstd;
+    }
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      if (!act[j]) continue;
+      const int col = (j * T + t) * 8;
+      float m8[8], a8[8], o[8];
+      lds8(mul + col, m8);
+      lds8(add + col, a8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf((f[j][i] - mean) * rstd, m8[i], a8[i]);
+      stg16(y + (base + l) * C + col, pack(o));
+    }
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) cur[j] = nxt[j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// backward.  xh = (x - mean) * rstd;  y = xh * mul + add  with  mul = gamma * s1, add = beta * s1 + shift, s1 = 1 + scale
+//   gh = dy * mul;  dx = rstd * (gh - mean_C(gh) - xh * mean_C(gh * xh))
+//   dshift += dy;  dscale += dy * (xh * gamma + beta);  dbeta += dy * s1;  dgamma += dy * s1 * xh
+// Column sums accumulate in registers over the CTA's rows (compile-time MODE keeps only the needed ones) and are
+// flushed with one atomicAdd per column per CTA.   MODE bit 0: dscale/dshift, bit 1: dgamma/dbeta.
+// ------------------------------------------------------------------------------------------------------------------
+template <typename XT, int T, int VPT, int MODE>
+__global__ void __launch_bounds__(T) ln_bwd_kernel(const bf16* __restrict__ dy, const XT* __restrict__ x,
+                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                   XT* __restrict__ dx, const float* __restrict__ gamma,
+                                                   const float* __restrict__ beta, const float* __restrict__ scale,
+                                                   float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                   float* __restrict__ dscale, float* __restrict__ dshift, int L, int C) {
+  extern __shared__ __align__(16) float sm[];  // mul[CP], (MODE & 1) gam[CP], bet[CP], (MODE & 2) s1[CP], red[2][T/32][2]
+  constexpr int CP = T * VPT * 8;
+  constexpr bool MOD = (MODE & 1) != 0, AFF = (MODE & 2) != 0;
+  float* mul = sm;
+  float* gam = mul + CP;                       // gamma          (MOD only)
+  float* bet = gam + (MOD ? CP : 0);           // beta           (MOD only)
+  float* s1v = bet + (MOD ? CP : 0);           // 1 + scale      (AFF only)
+  float* red = s1v + (AFF ? CP : 0);
+  const int b = blockIdx.y, t = threadIdx.x;
+  for (int c = t; c < CP; c += T) {
+    float g = 1.f, be = 0.f, s1 = 1.f;
+    if (c < C) {
+      if (gamma) g = gamma[c];
+      if (beta) be = beta[c];
+      if (scale) s1 = 1.f + scale[static_cast<size_t>(b) * C + c];
+    }
+    mul[c] = g * s1;
+    if constexpr (MOD) { gam[c] = g; bet[c] = be; }
+    if constexpr (AFF) s1v[c] = s1;
+  }
+  __syncthreads();
+  bool act[VPT];
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) act[j] = (j * T + t) * 8 < C;
+  float a_dshift[MOD ? VPT : 1][8], a_dscale[MOD ? VPT : 1][8], a_dbeta[AFF ? VPT : 1][8], a_dgamma[AFF ? VPT : 1][8];
+#pragma unroll
+  for (int j = 0; j < VPT; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if constexpr (MOD) { a_dshift[j][i] = 0.f; a_dscale[j][i] = 0.f; }
+      if constexpr (AFF) { a_dbeta[j][i] = 0.f; a_dgamma[j][i] = 0.f; }
+    }
+  const size_t base = static_cast<size_t>(b) * L;
+  const float invC = 1.f / C;
+  uint4 cdy[VPT], ndy[VPT];
+  Vec8<XT> cx[VPT], nx[VPT];
+  int l = blockIdx.x;
+  if (l < L) {
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      cdy[j] = make_uint4(0, 0, 0, 0);
+      zero8(cx[j]);
+      if (act[j]) {
+        cdy[j] = ldg16(dy + (base + l) * C + (j * T + t) * 8);
+        load8(x + (base + l) * C + (j * T + t) * 8, cx[j]);
+      }
+    }
+  }
+  int parity = 0;
+  for (; l < L; l += gridDim.x, parity ^= 1) {
+    const int ln = l + gridDim.x;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      ndy[j] = make_uint4(0, 0, 0, 0);
+      zero8(nx[j]);
+      if (ln < L && act[j]) {
+        ndy[j] = ldg16(dy + (base + ln) * C + (j * T + t) * 8);
+        load8(x + (base + ln) * C + (j * T + t) * 8, nx[j]);
+      }
+    }
+    const float mu = mean[base + l], rs = rstd[base + l];
+    float gh[VPT][8], xh[VPT][8];
+    float sums[2] = {0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      float fdy[8], fx[8], m8[8];
+      unpack(cdy[j], fdy);
+      unpack(cx[j], fx);
+      const int col = (j * T + t) * 8;
+      lds8(mul + col, m8);
+      float g8[8], b8[8], s8[8];
+      if constexpr (MOD) { lds8(gam + col, g8); lds8(bet + col, b8); }
+      if constexpr (AFF) lds8(s1v + col, s8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        xh[j][i] = act[j] ? (fx[i] - mu) * rs : 0.f;
+        gh[j][i] = fdy[i] * m8[i];
+        sums[0] += gh[j][i];
+        sums[1] += gh[j][i] * xh[j][i];
+        if constexpr (MOD) {
+          a_dshift[j][i] += fdy[i];
+          a_dscale[j][i] += fdy[i] * fmaf(xh[j][i], g8[i], b8[i]);
+        }
+        if constexpr (AFF) {
+          const float gm = fdy[i] * s8[i];
+          a_dbeta[j][i] += gm;
+          a_dgamma[j][i] += gm * xh[j][i];
+        }
+      }
+    }
+    block_sum<T, 2>(sums, red, parity);
+    const float m1 = sums[0] * invC, m2 = sums[1] * invC;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      if (!act[j]) continue;
+      float o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = rs * (gh[j][i] - m1 - xh[j][i] * m2);
+      store8(dx + (base + l) * C + (j * T + t) * 8, o);
+    }
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) { cdy[j] = ndy[j]; cx[j] = nx[j]; }
+  }
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) {
+    if (!act[j]) continue;
+    const int col = (j * T + t) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if constexpr (MOD) {
+        atomicAdd(dshift + static_cast<size_t>(b) * C + col + i, a_dshift[j][i]);
+        atomicAdd(dscale + static_cast<size_t>(b) * C + col + i, a_dscale[j][i]);
+      }
+      if constexpr (AFF) {
+        atomicAdd(dbeta + col + i, a_dbeta[j][i]);
+        atomicAdd(dgamma + col + i, a_dgamma[j][i]);
+      }
+    }
+  }
+}
+
+struct LnCfg { int T, VPT; };
+inline bool ln_cfg(int C, LnCfg* c) {
+  if (C % 8 != 0 || C < 8) return false;
+  if (C <= 512) { *c = {64, 1}; return true; }
+  if (C <= 1024) { *c = {128, 1}; return true; }
+  if (C <= 2048) { *c = {128, 2}; return true; }
+  if (C <= 3072) { *c = {128, 3}; return true; }
+  if (C > 4096 && C <= 5120) { *c = {128, 5}; return true; }
+  return false;  // other widths: the generic kernels in rowwise.cu
+}
+inline unsigned ln_grid_x(int L, int B, int ctas_per_sm) {
+  long long want = (148LL * ctas_per_sm + B - 1) / B;
+  if (want > L) want = L;
+  if (want < 1) want = 1;
+  return static_cast<unsigned>(want);
+}
+
+template <typename XT, int T, int VPT>
+int launch_fwd(const XT* x, bf16* y, float* mean, float* rstd, const float* gamma, const float* beta, const float* scale,
+               const float* shift, int B, int L, int C, float eps, cudaStream_t st) {
+  constexpr int CP = T * VPT * 8;
+  const int smem = (2 * CP + 4 * (T / 32)) * 4;
+  static bool configured = false;
+  if (!configured) {
+    VT_CHECK_CUDA(cudaFuncSetAttribute(ln_fwd_kernel<XT, T, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid(ln_grid_x(L, B, 8), B);
+  ln_fwd_kernel<XT, T, VPT><<<grid, T, smem, st>>>(x, y, mean, rstd, gamma, beta, scale, shift, L, C, eps);
+  VT_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename XT, int T, int VPT, int MODE>
+int launch_bwd(const bf16* dy, const XT* x, const float* mean, const float* rstd, XT* dx, const float* gamma,
+               const float* beta, const float* scale, float* dgamma, float* dbeta, float* dscale, float* dshift, int B, int L,
+               int C, cudaStream_t st) {
+  constexpr int CP = T * VPT * 8;
+  const int smem = (CP * (1 + ((MODE & 1) ? 2 : 0) + ((MODE & 2) ? 1 : 0)) + 2 * (T / 32) * 2) * 4;
+  static bool configured = false;
+  if (!configured) {
+    VT_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<XT, T, VPT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  dim3 grid(ln_grid_x(L, B, 4), B);
+  ln_bwd_kernel<XT, T, VPT, MODE><<<grid, T, smem, st>>>(dy, x, mean, rstd, dx, gamma, beta, scale, dgamma, dbeta, dscale,
+                                                        dshift, L, C);
+  VT_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename XT, int T, int VPT>
+int launch_bwd_mode(int mode, const bf16* dy, const XT* x, const float* mean, const float* rstd, XT* dx, const float* gamma,
+                    const float* beta, const float* scale, float* dgamma, float* dbeta, float* dscale, float* dshift, int B,
+                    int L, int C, cudaStream_t st) {
+  switch (mode) {
+    case 0: return launch_bwd<XT, T, VPT, 0>(dy, x, mean, rstd, dx, gamma, beta, scale, dgamma, dbeta, dscale, dshift, B, L, C, st);
+    case 1: return launch_bwd<XT, T, VPT, 1>(dy, x, mean, rstd, dx, gamma, beta, scale, dgamma, dbeta, dscale, dshift, B, L, C, st);
+    case 2: return launch_bwd<XT, T, VPT, 2>(dy, x, mean, rstd, dx, gamma, beta, scale, dgamma, dbeta, dscale, dshift, B, L, C, st);
+    default: return launch_bwd<XT, T, VPT, 3>(dy, x, mean, rstd, dx, gamma, beta, scale, dgamma, dbeta, dscale, dshift, B, L, C, st);
+  }
+}
+
+#define VT_LN_CFGS(X) X(64, 1) X(128, 1) X(128, 2) X(128, 3) X(128, 5)
+
+}  // namespace
+
+// Returns 1 when no specialised configuration exists for this width (caller falls back to rowwise.cu), 0 on success,
+// < 0 on error.
+int ln_fwd_fast(const void* x, void* y, float* mean, float* rstd, const float* gamma, const float* beta, const float* scale,
+                const float* shift, int B, int L, int C, float eps, int x_dtype, cudaStream_t st) {
+  LnCfg c;
+  if (!ln_cfg(C, &c) || B > 65535) return 1;
+#define X(T_, V_)                                                                                                        \
+  if (c.T == T_ && c.VPT == V_)                                                                                          \
+    return x_dtype == 0 ? launch_fwd<bf16, T_, V_>(static_cast<const bf16*>(x), static_cast<bf16*>(y), mean, rstd, gamma, beta, \
+                                                  scale, shift, B, L, C, eps, st)                                       \
+                        : launch_fwd<float, T_, V_>(static_cast<const float*>(x), static_cast<bf16*>(y), mean, rstd, gamma,    \
+                                                   beta, scale, shift, B, L, C, eps, st);
+  VT_LN_CFGS(X)
+#undef X
+  return 1;
+}
+
+int ln_bwd_fast(const void* dy, const void* x, const float* mean, const float* rstd, void* dx, const float* gamma,
+                const float* beta, const float* scale, float* dgamma, float* dbeta, float* dscale, float* dshift, int B, int L,
+                int C, int x_dtype, cudaStream_t st) {
+  LnCfg c;
+  if (!ln_cfg(C, &c) || B > 65535) return 1;
+  const bool mod = dscale != nullptr || dshift != nullptr, aff = dgamma != nullptr || dbeta != nullptr;
+  if ((mod && !(dscale && dshift)) || (aff && !(dgamma && dbeta))) return 1;  // half-requested pairs: generic kernel
+  const int mode = (mod ? 1 : 0) | (aff ? 2 : 0);
+#define X(T_, V_)                                                                                                        \
+  if (c.T == T_ && c.VPT == V_)                                                                                          \
+    return x_dtype == 0 ? launch_bwd_mode<bf16, T_, V_>(mode, static_cast<const bf16*>(dy), static_cast<const bf16*>(x), mean, \
+                                                       rstd, static_cast<bf16*>(dx), gamma, beta, scale, dgamma, dbeta, dscale, \
+                                                       dshift, B, L, C, st)                                              \
+                        : launch_bwd_mode<float, T_, V_>(mode, static_cast<const bf16*>(dy), static_cast<const float*>(x),     \
+                                                        mean, rstd, static_cast<float*>(dx), gamma, beta, scale, dgamma, dbeta, \
+                                                        dscale, dshift, B, L, C, st);
+  VT_LN_CFGS(X)
+#undef X
+  return 1;
+}
+
+}  // namespace vt

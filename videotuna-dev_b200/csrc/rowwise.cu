@@ -6,6 +6,7 @@
 //     with one atomicAdd per column per CTA,
 //   - row statistics use one shuffle+smem block reduction per group of RPI rows (RPI loads in flight per thread).
 // Algorithmic traffic: 4 B/elem forward (read x, write y), 6 B/elem backward (read dy, x; write dx).
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "capi_util.h"
@@ -566,6 +567,15 @@ int row_launch_dims(int L, int C, int B, int RPI, dim3* grid, dim3* block) {
 }  // namespace
 }  // namespace vt
 
+namespace vt {
+// layernorm.cu: specialised LayerNorm(+modulate) kernels for the common row widths; return 1 = "no configuration".
+int ln_fwd_fast(const void* x, void* y, float* mean, float* rstd, const float* gamma, const float* beta, const float* scale,
+                const float* shift, int B, int L, int C, float eps, int x_dtype, cudaStream_t st);
+int ln_bwd_fast(const void* dy, const void* x, const float* mean, const float* rstd, void* dx, const float* gamma,
+                const float* beta, const float* scale, float* dgamma, float* dbeta, float* dscale, float* dshift, int B, int L,
+                int C, int x_dtype, cudaStream_t st);
+}  // namespace vt
+
 using namespace vt;
 using bf16 = __nv_bfloat16;
 
@@ -576,6 +586,11 @@ int vt_ln_modulate_fwd(const void* x, void* y, float* mean, float* rstd, const f
   VT_REQUIRE(x && y, VT_ERR_NULL, "vt_ln_modulate_fwd: NULL argument");
   VT_REQUIRE(aligned16(x) && aligned16(y), VT_ERR_ALIGN, "x/y must be 16-byte aligned");
   VT_REQUIRE(x_dtype == 0 || x_dtype == 1, VT_ERR_DTYPE, "x_dtype %d (0 = bf16, 1 = fp32)", x_dtype);
+  VT_REQUIRE(B >= 1 && L >= 1 && C >= 8 && C % 8 == 0, VT_ERR_SHAPE, "bad B=%d L=%d C=%d", B, L, C);
+  if (getenv("VT_LN_GENERIC") == nullptr) {
+    const int rc = ln_fwd_fast(x, y, mean, rstd, gamma, beta, scale, shift, B, L, C, eps, x_dtype, static_cast<cudaStream_t>(stream));
+    if (rc <= 0) return rc;
+  }
 #define K16_(M, R) ln_modulate_fwd_kernel<bf16, M, R>
 #define K32_(M, R) ln_modulate_fwd_kernel<float, M, R>
   if (x_dtype == 0)
@@ -595,6 +610,12 @@ int vt_ln_modulate_bwd(const void* dy, const void* x, const float* mean, const f
   VT_REQUIRE(dy && x && mean && rstd && dx, VT_ERR_NULL, "vt_ln_modulate_bwd: NULL argument");
   VT_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(dx), VT_ERR_ALIGN, "dy/x/dx must be 16-byte aligned");
   VT_REQUIRE(x_dtype == 0 || x_dtype == 1, VT_ERR_DTYPE, "x_dtype %d (0 = bf16, 1 = fp32)", x_dtype);
+  VT_REQUIRE(B >= 1 && L >= 1 && C >= 8 && C % 8 == 0, VT_ERR_SHAPE, "bad B=%d L=%d C=%d", B, L, C);
+  if (getenv("VT_LN_GENERIC") == nullptr) {
+    const int rc = ln_bwd_fast(dy, x, mean, rstd, dx, gamma, beta, scale, dgamma, dbeta, dscale, dshift, B, L, C, x_dtype,
+                               static_cast<cudaStream_t>(stream));
+    if (rc <= 0) return rc;
+  }
 #define K16_(M, R) ln_modulate_bwd_kernel<bf16, M, R>
 #define K32_(M, R) ln_modulate_bwd_kernel<float, M, R>
   if (x_dtype == 0)

@@ -17,18 +17,34 @@
 namespace vt {
 namespace {
 
-constexpr int kWarps = 4;       // (sequence, head) pairs in flight per CTA
+constexpr int kWarps = 8;       // (sequence, head) pairs in flight per CTA (fewer when N = 32, D = 128 would not fit)
 constexpr int kMaxN = 32;
 
+// Per-warp shared memory, sized by the ACTUAL sequence length N (not the 32-token maximum): for N = 16, D = 64 that is
+// 7.4 KB (forward) / 10.6 KB (backward) instead of 25 KB, which is what bounds the number of resident warps — with the
+// fixed 32-row layout only 8 warps fitted per SM and the kernel ran at 7 % of the HBM roofline, slower than the three
+// torch kernels it replaces.
 template <int D>
 struct TemporalSmem {
   static constexpr int PITCH = D + 2;  // bf16 elements; +2 keeps row-per-lane reads conflict-free (pitch/2 odd)
-  __nv_bfloat16 q[kMaxN * PITCH];
-  __nv_bfloat16 k[kMaxN * PITCH];
-  __nv_bfloat16 v[kMaxN * PITCH];
-  __nv_bfloat16 g[kMaxN * PITCH];      // dO (backward only)
-  float p[kMaxN * (kMaxN + 1)];        // probabilities, [query][key]
-  float ds[kMaxN * (kMaxN + 1)];       // dS (backward only)
+  __nv_bfloat16 *q, *k, *v, *g;        // [N][PITCH]; g = dO (backward only)
+  float *p, *ds;                       // [N][N + 1] probabilities [query][key]; dS (backward only)
+  int pp;                              // row pitch of p / ds = N + 1
+  __host__ __device__ static int bytes(int N, bool bwd) {
+    const int mat = ((N * PITCH * 2 + 15) / 16) * 16, sq = ((N * (N + 1) * 4 + 15) / 16) * 16;
+    return (bwd ? 4 : 3) * mat + (bwd ? 2 : 1) * sq;
+  }
+  __device__ TemporalSmem(uint8_t* base, int N, bool bwd) {
+    const int mat = ((N * PITCH * 2 + 15) / 16) * 16, sq = ((N * (N + 1) * 4 + 15) / 16) * 16;
+    q = reinterpret_cast<__nv_bfloat16*>(base);
+    k = reinterpret_cast<__nv_bfloat16*>(base + mat);
+    v = reinterpret_cast<__nv_bfloat16*>(base + 2 * mat);
+    g = reinterpret_cast<__nv_bfloat16*>(base + 3 * mat);
+    uint8_t* f = base + (bwd ? 4 : 3) * mat;
+    p = reinterpret_cast<float*>(f);
+    ds = reinterpret_cast<float*>(f + sq);
+    pp = N + 1;
+  }
 };
 
 struct TemporalArgs {
@@ -64,44 +80,68 @@ __device__ __forceinline__ float warp_sum(float x) {
   return x;
 }
 
-// Scores and probabilities for the staged q, k: lane j owns key j. Writes P[i][j] to sm.p.
+__device__ __forceinline__ float group_max(float x, int width) {
+  for (int o = width >> 1; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+  return x;
+}
+__device__ __forceinline__ float group_sum(float x, int width) {
+  for (int o = width >> 1; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+  return x;
+}
+
+// Scores and probabilities for the staged q, k. N <= 16: the two half-warps take alternate query rows (lane % 16 owns
+// key lane % 16, its K row held in registers); N > 16: lane j owns key j. Writes P[i][j] to sm.p.
 template <int D>
 __device__ __forceinline__ void softmax_rows(TemporalSmem<D>& sm, const TemporalArgs& a, int lane) {
   constexpr int PITCH = TemporalSmem<D>::PITCH;
   const int N = a.N;
-  const bool key_ok = lane < N;
-  const __nv_bfloat16* krow = sm.k + (key_ok ? lane : 0) * PITCH;
-  for (int i = 0; i < N; ++i) {
-    const __nv_bfloat16* qrow = sm.q + i * PITCH;
-    float acc = 0.f;
-#pragma unroll 8
+  const bool split = N <= 16;
+  const int width = split ? 16 : 32;
+  const int key = split ? (lane & 15) : lane, half = split ? (lane >> 4) : 0, step = split ? 2 : 1;
+  const bool key_ok = key < N;
+  // D = 64: the lane's K row lives in registers (64 floats) for all query rows; D = 128 would need 128 and re-reads it
+  constexpr bool KREG = (D == 64);
+  const __nv_bfloat16* krow = sm.k + (key_ok ? key : 0) * PITCH;
+  float2 kreg[KREG ? D / 2 : 1];
+  if constexpr (KREG) {
+#pragma unroll
+    for (int d = 0; d < D; d += 2) kreg[d / 2] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(krow + d));
+  }
+  for (int i0 = 0; i0 < N; i0 += step) {
+    const int i = i0 + half;
+    const bool row_ok = i < N;
+    const __nv_bfloat16* qrow = sm.q + (row_ok ? i : 0) * PITCH;
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
     for (int d = 0; d < D; d += 2) {
-      const float2 kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(krow + d));
       const float2 qq = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(qrow + d));
-      acc = fmaf(qq.x, kk.x, acc);
-      acc = fmaf(qq.y, kk.y, acc);
+      float2 kk;
+      if constexpr (KREG) kk = kreg[d / 2];
+      else kk = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(krow + d));
+      acc0 = fmaf(qq.x, kk.x, acc0);
+      acc1 = fmaf(qq.y, kk.y, acc1);
     }
-    float s = acc * a.scale;
-    if (a.mask != nullptr && key_ok && !(a.mask[i * N + lane] > 0.5f)) s = -FLT_MAX;
+    float s = (acc0 + acc1) * a.scale;
+    if (a.mask != nullptr && key_ok && row_ok && !(a.mask[i * N + key] > 0.5f)) s = -FLT_MAX;
     if (!key_ok) s = -INFINITY;
-    const float m = warp_max(s);
+    const float m = group_max(s, width);
     const float e = key_ok ? __expf(s - m) : 0.f;
-    const float l = warp_sum(e);
-    if (key_ok) sm.p[i * (kMaxN + 1) + lane] = e / l;
+    const float l = group_sum(e, width);
+    if (key_ok && row_ok) sm.p[i * sm.pp + key] = e / l;
   }
   __syncwarp();
 }
 
 // out[r][d] = sum_c coef(r, c) * mat[c][d] for the lane's D/32 consecutive dims; coef read as broadcast from smem.
 template <int D, bool TRANSPOSED>
-__device__ __forceinline__ void mix_rows(const float* coef, const __nv_bfloat16* mat, int N, int lane, int r,
+__device__ __forceinline__ void mix_rows(const float* coef, int pp, const __nv_bfloat16* mat, int N, int lane, int r,
                                          float (&out)[D / 32]) {
   constexpr int PITCH = TemporalSmem<D>::PITCH;
   constexpr int PER = D / 32;
 #pragma unroll
   for (int e = 0; e < PER; ++e) out[e] = 0.f;
   for (int c = 0; c < N; ++c) {
-    const float w = TRANSPOSED ? coef[c * (kMaxN + 1) + r] : coef[r * (kMaxN + 1) + c];
+    const float w = TRANSPOSED ? coef[c * pp + r] : coef[r * pp + c];
     const __nv_bfloat16* mrow = mat + c * PITCH + lane * PER;
 #pragma unroll
     for (int e = 0; e < PER; e += 2) {
@@ -132,11 +172,12 @@ __global__ void __launch_bounds__(kWarps * 32)
 temporal_attn_kernel(const TemporalArgs a) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  TemporalSmem<D>& sm = reinterpret_cast<TemporalSmem<D>*>(smem_raw)[warp];
+  TemporalSmem<D> sm(smem_raw + warp * TemporalSmem<D>::bytes(a.N, BWD), a.N, BWD);
   const int64_t pairs = static_cast<int64_t>(a.B) * a.H;
   const int N = a.N;
-  for (int64_t pair = static_cast<int64_t>(blockIdx.x) * kWarps + warp; pair < pairs;
-       pair += static_cast<int64_t>(gridDim.x) * kWarps) {
+  const int nwarps = blockDim.x >> 5;
+  for (int64_t pair = static_cast<int64_t>(blockIdx.x) * nwarps + warp; pair < pairs;
+       pair += static_cast<int64_t>(gridDim.x) * nwarps) {
     const int b = static_cast<int>(pair / a.H), h = static_cast<int>(pair % a.H);
     stage<D>(sm.q, a.q + b * a.q_s[0] + h * a.q_s[2], a.q_s[1], N, lane);
     stage<D>(sm.k, a.k + b * a.k_s[0] + h * a.k_s[2], a.k_s[1], N, lane);
@@ -147,7 +188,7 @@ temporal_attn_kernel(const TemporalArgs a) {
     if (!BWD) {
       for (int i = 0; i < N; ++i) {
         float o[D / 32];
-        mix_rows<D, false>(sm.p, sm.v, N, lane, i, o);
+        mix_rows<D, false>(sm.p, sm.pp, sm.v, N, lane, i, o);
         store_row<D>(a.o + b * a.o_s[0] + i * a.o_s[1] + h * a.o_s[2], o, lane, 1.f);
       }
     } else {
@@ -165,20 +206,20 @@ temporal_attn_kernel(const TemporalArgs a) {
           acc = fmaf(gg.x, vv.x, acc);
           acc = fmaf(gg.y, vv.y, acc);
         }
-        const float pij = key_ok ? sm.p[i * (kMaxN + 1) + lane] : 0.f;
+        const float pij = key_ok ? sm.p[i * sm.pp + lane] : 0.f;
         const float delta = warp_sum(pij * acc);
-        if (key_ok) sm.ds[i * (kMaxN + 1) + lane] = pij * (acc - delta);
+        if (key_ok) sm.ds[i * sm.pp + lane] = pij * (acc - delta);
       }
       __syncwarp();
       const int64_t gbase = (static_cast<int64_t>(b) * N * a.H + h) * D;  // contiguous (B, N, H, D) gradients
       const int64_t gn = static_cast<int64_t>(a.H) * D;
       for (int r = 0; r < N; ++r) {
         float t[D / 32];
-        mix_rows<D, true>(sm.p, sm.g, N, lane, r, t);    // dV_r = sum_i P[i][r] dO_i
+        mix_rows<D, true>(sm.p, sm.pp, sm.g, N, lane, r, t);    // dV_r = sum_i P[i][r] dO_i
         store_row<D>(a.dv + gbase + r * gn, t, lane, 1.f);
-        mix_rows<D, true>(sm.ds, sm.q, N, lane, r, t);   // dK_r = scale * sum_i dS[i][r] q_i
+        mix_rows<D, true>(sm.ds, sm.pp, sm.q, N, lane, r, t);   // dK_r = scale * sum_i dS[i][r] q_i
         store_row<D>(a.dk + gbase + r * gn, t, lane, a.scale);
-        mix_rows<D, false>(sm.ds, sm.k, N, lane, r, t);  // dQ_r = scale * sum_j dS[r][j] k_j
+        mix_rows<D, false>(sm.ds, sm.pp, sm.k, N, lane, r, t);  // dQ_r = scale * sum_j dS[r][j] k_j
         store_row<D>(a.dq + gbase + r * gn, t, lane, a.scale);
       }
     }
@@ -188,15 +229,18 @@ temporal_attn_kernel(const TemporalArgs a) {
 
 template <int D, bool BWD>
 cudaError_t launch(const TemporalArgs& a, cudaStream_t st) {
-  const int bytes = kWarps * static_cast<int>(sizeof(TemporalSmem<D>));
+  const int per_warp = TemporalSmem<D>::bytes(a.N, BWD);
+  int warps = kWarps;
+  while (warps > 1 && warps * per_warp > 200 * 1024) warps >>= 1;
+  const int bytes = warps * per_warp;
   cudaError_t e = cudaFuncSetAttribute(temporal_attn_kernel<D, BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) return e;
   const int64_t pairs = static_cast<int64_t>(a.B) * a.H;
   // persistent-style grid: a multiple of the 148 SMs, several CTAs per SM to cover the load latency
-  int64_t blocks = (pairs + kWarps - 1) / kWarps;
-  const int64_t cap = 148 * 8;
+  int64_t blocks = (pairs + warps - 1) / warps;
+  const int64_t cap = 148 * 6;
   if (blocks > cap) blocks = cap;
-  temporal_attn_kernel<D, BWD><<<static_cast<unsigned>(blocks), kWarps * 32, bytes, st>>>(a);
+  temporal_attn_kernel<D, BWD><<<static_cast<unsigned>(blocks), warps * 32, bytes, st>>>(a);
   return cudaGetLastError();
 }
 

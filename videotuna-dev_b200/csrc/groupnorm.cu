@@ -6,6 +6,7 @@
 // reduces sum / sum of squares (Welford-free: shifted by the first element for stability); pass 2 re-reads it (an
 // L2 hit: slabs are 50-400 KB, far below the 126 MB L2), normalises, applies SiLU and writes. DRAM traffic is therefore
 // 4 B/elem (bf16) although the kernel is two-pass.
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "capi_util.h"
@@ -52,10 +53,10 @@ struct Io<__nv_bfloat16> {
   __device__ static void st1(__nv_bfloat16* p, float v) { *p = __float2bfloat16(v); }
 };
 
-template <int NV>
+template <int NV, int THREADS = GN_THREADS>
 __device__ __forceinline__ void cta_sum(float* v, float* red) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int NW = GN_THREADS / 32;
+  constexpr int NW = THREADS / 32;
 #pragma unroll
   for (int i = 0; i < NV; ++i)
 #pragma unroll
@@ -149,6 +150,83 @@ groupnorm_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, float* __restri
   }
 }
 
+// EXPERIMENT (off unless VT_GN_REG is set; measured SLOWER: 116 vs 79 us on the VC2 level-0 tensor, because ~100 registers x
+// 512 threads leave one CTA per SM while the two-pass kernel keeps four). Register-resident single pass for slabs of at most THREADS * NVEC vectors (every VideoCrafter2 level at its own
+// channel count: 6 400 .. 25 600 elements): the slab is read from HBM once, kept in registers across the statistics, and
+// written once — no L2 re-read and half the dependent latency of the two-pass kernel, which stays for larger slabs.
+template <typename T, int THREADS, int NVEC>
+__global__ void __launch_bounds__(THREADS)
+groupnorm_fwd_reg_kernel(const T* __restrict__ x, T* __restrict__ y, float* __restrict__ mean_out,
+                         float* __restrict__ rstd_out, const float* __restrict__ gamma, const float* __restrict__ beta,
+                         int C, int S, int G, float eps, int apply_silu) {
+  __shared__ float red[2 * (THREADS / 32)];
+  constexpr int VEC = Io<T>::VEC;
+  const int n = blockIdx.y, g = blockIdx.x;
+  const int cpg = C / G;
+  const size_t base = (static_cast<size_t>(n) * C + static_cast<size_t>(g) * cpg) * S;
+  const int count = cpg * S;
+  const T* xs = x + base;
+  T* ys = y + base;
+  const float shiftv = Io<T>::ld1(xs);
+  float f[NVEC][VEC];
+  float acc[2] = {0.f, 0.f};
+#pragma unroll
+  for (int j = 0; j < NVEC; ++j) {
+    const int i = (j * THREADS + threadIdx.x) * VEC;
+    if (i < count) {
+      Io<T>::load(xs + i, f[j]);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float d = f[j][k] - shiftv;
+        acc[0] += d;
+        acc[1] += d * d;
+      }
+    }
+  }
+  cta_sum<2, THREADS>(acc, red);
+  const float inv = 1.f / count;
+  const float md = acc[0] * inv;
+  const float var = fmaxf(acc[1] * inv - md * md, 0.f);
+  const float mean = md + shiftv;
+  const float rstd = rsqrtf(var + eps);
+  if (threadIdx.x == 0) {
+    if (mean_out) mean_out[n * G + g] = mean;
+    if (rstd_out) rstd_out[n * G + g] = rstd;
+  }
+#pragma unroll
+  for (int j = 0; j < NVEC; ++j) {
+    const int i = (j * THREADS + threadIdx.x) * VEC;
+    if (i < count) {
+      const int c = g * cpg + i / S;  // a vector never straddles channels because S % VEC == 0
+      const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+      const float a = rstd * ga, bsh = be - mean * a;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float z = fmaf(f[j][k], a, bsh);
+        f[j][k] = apply_silu ? silu_f(z) : z;
+      }
+      Io<T>::store(ys + i, f[j]);
+    }
+  }
+}
+
+template <typename T>
+bool launch_gn_fwd_reg(const T* x, T* y, float* mean, float* rstd, const float* gamma, const float* beta, int N, int C, int S,
+                       int G, float eps, int apply_silu, cudaStream_t st) {
+  constexpr int VEC = Io<T>::VEC;
+  const long long vectors = static_cast<long long>(C / G) * S / VEC;
+  dim3 grid(G, N);
+  if (vectors <= 128 * 8)
+    groupnorm_fwd_reg_kernel<T, 128, 8><<<grid, 128, 0, st>>>(x, y, mean, rstd, gamma, beta, C, S, G, eps, apply_silu);
+  else if (vectors <= 256 * 8)
+    groupnorm_fwd_reg_kernel<T, 256, 8><<<grid, 256, 0, st>>>(x, y, mean, rstd, gamma, beta, C, S, G, eps, apply_silu);
+  else if (vectors <= 512 * 8)
+    groupnorm_fwd_reg_kernel<T, 512, 8><<<grid, 512, 0, st>>>(x, y, mean, rstd, gamma, beta, C, S, G, eps, apply_silu);
+  else
+    return false;
+  return true;
+}
+
 // z = xh*gamma + beta; y = silu(z) or z; gz = dy * silu'(z); gh = gz * gamma
 // dx = rstd * (gh - mean_g(gh) - xh * mean_g(gh * xh)); dgamma[c] += sum gz*xh; dbeta[c] += sum gz
 template <typename T>
@@ -156,7 +234,7 @@ __global__ void __launch_bounds__(GN_THREADS)
 groupnorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean_in,
                      const float* __restrict__ rstd_in, T* __restrict__ dx, const float* __restrict__ gamma,
                      const float* __restrict__ beta, float* __restrict__ dgamma, float* __restrict__ dbeta, int C,
-                     int S, int G, int apply_silu) {
+                     int S, int G, int apply_silu, int vec_ok) {
   __shared__ float red[2 * (GN_THREADS / 32)];
   const int n = blockIdx.y, g = blockIdx.x;
   const int cpg = C / G;
@@ -170,12 +248,29 @@ groupnorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
     const T* xs = x + base + static_cast<size_t>(cc) * S;
     const T* ds = dy + base + static_cast<size_t>(cc) * S;
     float a[2] = {0.f, 0.f};
-    for (int i = threadIdx.x; i < S; i += GN_THREADS) {
-      const float xh = (Io<T>::ld1(xs + i) - mean) * rstd;
-      float gz = Io<T>::ld1(ds + i);
-      if (apply_silu) gz *= dsilu_f(xh * ga + be);
-      a[0] += gz;
-      a[1] += gz * xh;
+    if (vec_ok) {
+      constexpr int VEC = Io<T>::VEC;
+      for (int i = threadIdx.x * VEC; i < S; i += GN_THREADS * VEC) {
+        float fx[VEC], fg[VEC];
+        Io<T>::load(xs + i, fx);
+        Io<T>::load(ds + i, fg);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          const float xh = (fx[k] - mean) * rstd;
+          float gz = fg[k];
+          if (apply_silu) gz *= dsilu_f(xh * ga + be);
+          a[0] += gz;
+          a[1] += gz * xh;
+        }
+      }
+    } else {
+      for (int i = threadIdx.x; i < S; i += GN_THREADS) {
+        const float xh = (Io<T>::ld1(xs + i) - mean) * rstd;
+        float gz = Io<T>::ld1(ds + i);
+        if (apply_silu) gz *= dsilu_f(xh * ga + be);
+        a[0] += gz;
+        a[1] += gz * xh;
+      }
     }
     cta_sum<2>(a, red);
     if (threadIdx.x == 0) {
@@ -194,11 +289,28 @@ groupnorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
     const T* xs = x + base + static_cast<size_t>(cc) * S;
     const T* ds = dy + base + static_cast<size_t>(cc) * S;
     T* os = dx + base + static_cast<size_t>(cc) * S;
-    for (int i = threadIdx.x; i < S; i += GN_THREADS) {
-      const float xh = (Io<T>::ld1(xs + i) - mean) * rstd;
-      float gz = Io<T>::ld1(ds + i);
-      if (apply_silu) gz *= dsilu_f(xh * ga + be);
-      Io<T>::st1(os + i, rstd * (gz * ga - m1 - xh * m2));
+    if (vec_ok) {
+      constexpr int VEC = Io<T>::VEC;
+      for (int i = threadIdx.x * VEC; i < S; i += GN_THREADS * VEC) {
+        float fx[VEC], fg[VEC];
+        Io<T>::load(xs + i, fx);
+        Io<T>::load(ds + i, fg);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          const float xh = (fx[k] - mean) * rstd;
+          float gz = fg[k];
+          if (apply_silu) gz *= dsilu_f(xh * ga + be);
+          fx[k] = rstd * (gz * ga - m1 - xh * m2);
+        }
+        Io<T>::store(os + i, fx);
+      }
+    } else {
+      for (int i = threadIdx.x; i < S; i += GN_THREADS) {
+        const float xh = (Io<T>::ld1(xs + i) - mean) * rstd;
+        float gz = Io<T>::ld1(ds + i);
+        if (apply_silu) gz *= dsilu_f(xh * ga + be);
+        Io<T>::st1(os + i, rstd * (gz * ga - m1 - xh * m2));
+      }
     }
   }
 }
@@ -221,11 +333,21 @@ int vt_groupnorm_silu_fwd(const void* x, void* y, float* mean, float* rstd, cons
   dim3 grid(G, N);
   if (dtype == 0) {
     const int vec_ok = (S % 8 == 0) && aligned16(x) && aligned16(y);
+    if (vec_ok && getenv("VT_GN_REG") != nullptr && launch_gn_fwd_reg<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), mean,
+                                                   rstd, gamma, beta, N, C, S, G, eps, apply_silu, st)) {
+      VT_CHECK_CUDA(cudaGetLastError());
+      return 0;
+    }
     groupnorm_fwd_kernel<__nv_bfloat16><<<grid, GN_THREADS, 0, st>>>(
         static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), mean, rstd, gamma, beta, C, S, G, eps,
         apply_silu, vec_ok);
   } else {
     const int vec_ok = (S % 4 == 0) && aligned16(x) && aligned16(y);
+    if (vec_ok && getenv("VT_GN_REG") != nullptr && launch_gn_fwd_reg<float>(static_cast<const float*>(x), static_cast<float*>(y), mean, rstd, gamma, beta, N, C, S,
+                                           G, eps, apply_silu, st)) {
+      VT_CHECK_CUDA(cudaGetLastError());
+      return 0;
+    }
     groupnorm_fwd_kernel<float><<<grid, GN_THREADS, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(y), mean,
                                                              rstd, gamma, beta, C, S, G, eps, apply_silu, vec_ok);
   }
@@ -245,11 +367,13 @@ int vt_groupnorm_silu_bwd(const void* dy, const void* x, const float* mean, cons
   if (dtype == 0)
     groupnorm_bwd_kernel<__nv_bfloat16><<<grid, GN_THREADS, 0, st>>>(
         static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), mean, rstd,
-        static_cast<__nv_bfloat16*>(dx), gamma, beta, dgamma, dbeta, C, S, G, apply_silu);
+        static_cast<__nv_bfloat16*>(dx), gamma, beta, dgamma, dbeta, C, S, G, apply_silu,
+        (S % 8 == 0) && aligned16(x) && aligned16(dy) && aligned16(dx));
   else
     groupnorm_bwd_kernel<float><<<grid, GN_THREADS, 0, st>>>(static_cast<const float*>(dy), static_cast<const float*>(x),
                                                              mean, rstd, static_cast<float*>(dx), gamma, beta, dgamma,
-                                                             dbeta, C, S, G, apply_silu);
+                                                             dbeta, C, S, G, apply_silu,
+                                                             (S % 4 == 0) && aligned16(x) && aligned16(dy) && aligned16(dx));
   VT_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

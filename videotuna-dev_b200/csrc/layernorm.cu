@@ -428,3 +428,141 @@ int ln_bwd_fast(const void* dy, const void* x, const float* mean, const float* r
 }
 
 }  // namespace vt
+
+// =====================================================================================================================
+// Fused QK-RMSNorm + RoPE forward in the same layout (second generation of rmsnorm_rope_fwd_kernel in rowwise.cu, which
+// ran at 34 % of the HBM roofline on the K1 q tensor for the same occupancy reason). One 128-thread CTA per token; thread
+// t holds VPT vectors at columns (j * 128 + t) * 8, i.e. head j * (1024 / D) + t / (D / 8), always the same 8 head-dim
+// positions d0 = (t % (D / 8)) * 8 — so its cos / sin slice is loaded once per token and reused for all its heads, the
+// per-head sum of squares is a shuffle over D / 8 lanes, and the next token's loads are issued before this one is
+// normalised. NORM: 0 none, 1 per head (weight (D)), 2 whole token (weight (H * D), one 4-warp block sum).
+// =====================================================================================================================
+namespace vt {
+namespace {
+
+template <int NORM, int VPT, int D>
+__global__ void __launch_bounds__(128) rope_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, float* __restrict__ rstd_out,
+                                                       const float* __restrict__ w, const float* __restrict__ cosT,
+                                                       const float* __restrict__ sinT, int64_t x_sb, int64_t x_sl,
+                                                       int64_t x_sh, int64_t y_sb, int64_t y_sl, int64_t y_sh, int L, int H,
+                                                       int L_rope, float eps) {
+  constexpr int T = 128, LPH = D / 8, HPS = 1024 / D;  // lanes per head, heads per 128-thread sweep
+  __shared__ float red[2 * (T / 32)];
+  const int b = blockIdx.y, t = threadIdx.x;
+  const int d0 = (t % LPH) * 8, hsub = t / LPH;
+  const int C = H * D;
+  float wv[NORM == 2 ? VPT : 1][8];
+#pragma unroll
+  for (int j = 0; j < (NORM == 2 ? VPT : 1); ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wv[j][i] = 1.f;
+  if (w != nullptr) {
+    if (NORM == 1) lds8(w + d0, wv[0]);  // plain global loads through the same helper (16-byte aligned)
+    if (NORM == 2) {
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) lds8(w + (j * T + t) * 8, wv[NORM == 2 ? j : 0]);
+    }
+  }
+  Vec8<bf16> cur[VPT], nxt[VPT];
+  int l = blockIdx.x;
+  if (l < L) {
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) load8(x + b * x_sb + static_cast<int64_t>(l) * x_sl + (j * HPS + hsub) * x_sh + d0, cur[j]);
+  }
+  int parity = 0;
+  for (; l < L; l += gridDim.x, parity ^= 1) {
+    const int ln = l + gridDim.x;
+    if (ln < L) {
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) load8(x + b * x_sb + static_cast<int64_t>(ln) * x_sl + (j * HPS + hsub) * x_sh + d0, nxt[j]);
+    }
+    const bool rot = cosT != nullptr && l < L_rope;
+    float cs[8], sn[8];
+    if (rot) {
+      lds8(cosT + static_cast<size_t>(l) * D + d0, cs);
+      lds8(sinT + static_cast<size_t>(l) * D + d0, sn);
+    }
+    float f[VPT][8], ss[VPT];
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      unpack(cur[j], f[j]);
+      ss[j] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss[j] += f[j][i] * f[j][i];
+    }
+    float rstd[VPT];
+    if (NORM == 1) {
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+#pragma unroll
+        for (int o = LPH >> 1; o > 0; o >>= 1) ss[j] += __shfl_xor_sync(0xffffffffu, ss[j], o);
+        rstd[j] = rsqrtf(ss[j] / D + eps);
+        if (rstd_out != nullptr && (t % LPH) == 0)
+          rstd_out[(static_cast<size_t>(b) * L + l) * H + j * HPS + hsub] = rstd[j];
+      }
+    } else if (NORM == 2) {
+      float tot[1] = {0.f};
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) tot[0] += ss[j];
+      block_sum<T, 1>(tot, red, parity);
+      const float r = rsqrtf(tot[0] / C + eps);
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) rstd[j] = r;
+      if (rstd_out != nullptr && t == 0) rstd_out[static_cast<size_t>(b) * L + l] = r;
+    } else {
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) rstd[j] = 1.f;
+    }
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      float n[8], o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) n[i] = f[j][i] * rstd[j] * wv[NORM == 2 ? j : 0][i];
+      if (rot) {
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          o[i] = n[i] * cs[i] - n[i + 1] * sn[i];
+          o[i + 1] = n[i + 1] * cs[i + 1] + n[i] * sn[i + 1];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = n[i];
+      }
+      stg16(y + b * y_sb + static_cast<int64_t>(l) * y_sl + (j * HPS + hsub) * y_sh + d0, pack(o));
+    }
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) cur[j] = nxt[j];
+  }
+}
+
+template <int NORM, int VPT, int D>
+int launch_rope(const bf16* x, bf16* y, float* rstd, const float* w, const float* c, const float* s, const int64_t* xs,
+                const int64_t* ys, int B, int L, int H, int L_rope, float eps, cudaStream_t st) {
+  dim3 grid(ln_grid_x(L, B, 6), B);
+  rope_fwd_kernel<NORM, VPT, D><<<grid, 128, 0, st>>>(x, y, rstd, w, c, s, xs[0], xs[1], xs[2], ys[0], ys[1], ys[2], L, H,
+                                                       L_rope, eps);
+  VT_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// 1 = no specialised configuration (caller falls back to rowwise.cu)
+int rope_fwd_fast(const void* x, void* y, float* rstd, const float* w, const float* c, const float* s, const int64_t* xs,
+                  const int64_t* ys, int B, int L, int H, int D, int L_rope, int norm_mode, float eps, cudaStream_t st) {
+  const int C = H * D;
+  if (C % 1024 != 0 || B > 65535 || (D != 64 && D != 128)) return 1;
+  const int vpt = C / 1024;
+  const bf16* xp = static_cast<const bf16*>(x);
+  bf16* yp = static_cast<bf16*>(y);
+#define VT_ROPE(N_, V_)                                                                                                  \
+  if (norm_mode == N_ && vpt == V_)                                                                                     \
+    return D == 128 ? launch_rope<N_, V_, 128>(xp, yp, rstd, w, c, s, xs, ys, B, L, H, L_rope, eps, st)                 \
+                    : launch_rope<N_, V_, 64>(xp, yp, rstd, w, c, s, xs, ys, B, L, H, L_rope, eps, st);
+  VT_ROPE(0, 3) VT_ROPE(1, 3) VT_ROPE(2, 3) VT_ROPE(0, 5) VT_ROPE(1, 5) VT_ROPE(2, 5) VT_ROPE(0, 1) VT_ROPE(1, 1) VT_ROPE(2, 1)
+  VT_ROPE(0, 2) VT_ROPE(1, 2) VT_ROPE(2, 2)
+#undef VT_ROPE
+  return 1;
+}
+
+}  // namespace vt

@@ -574,6 +574,8 @@ int ln_fwd_fast(const void* x, void* y, float* mean, float* rstd, const float* g
 int ln_bwd_fast(const void* dy, const void* x, const float* mean, const float* rstd, void* dx, const float* gamma,
                 const float* beta, const float* scale, float* dgamma, float* dbeta, float* dscale, float* dshift, int B, int L,
                 int C, int x_dtype, cudaStream_t st);
+int rope_fwd_fast(const void* x, void* y, float* rstd, const float* w, const float* c, const float* s, const int64_t* xs,
+                  const int64_t* ys, int B, int L, int H, int D, int L_rope, int norm_mode, float eps, cudaStream_t st);
 }  // namespace vt
 
 using namespace vt;
@@ -686,6 +688,10 @@ int vt_qk_rmsnorm_rope_fwd(const void* x, void* y, float* rstd_out, const float*
   if (int rc = check_rope_args(x_strides, H, D, "x")) return rc;
   if (int rc = check_rope_args(y_strides, H, D, "y")) return rc;
   auto st = static_cast<cudaStream_t>(stream);
+  if (getenv("VT_LN_GENERIC") == nullptr) {
+    const int rc = rope_fwd_fast(x, y, rstd_out, w, cos, sin, x_strides, y_strides, B, L, H, D, L_rope, norm_mode, eps, st);
+    if (rc <= 0) return rc;
+  }
 #define VT_RR_ARGS static_cast<const bf16*>(x), static_cast<bf16*>(y), rstd_out, w, cos, sin, x_strides[0], x_strides[1], \
                    x_strides[2], y_strides[0], y_strides[1], y_strides[2], L, H, D, L_rope, eps
 #define K0_(M, R) rmsnorm_rope_fwd_kernel<0, M, R>

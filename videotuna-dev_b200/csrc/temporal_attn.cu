@@ -10,6 +10,7 @@
 // mask (optional): (N, N) fp32, > 0.5 = keep, shared by every pair — the causal temporal mask of attention.py:487-489;
 // masked scores are filled with -FLT_MAX before the softmax exactly like masked_fill(~mask, -finfo.max) (:136-140).
 #include <cfloat>
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "capi_util.h"
@@ -268,6 +269,12 @@ void fill(TemporalArgs& a, const int64_t* qs, const int64_t* ks, const int64_t* 
 }  // namespace
 }  // namespace vt
 
+namespace vt {
+cudaError_t temporal_attn_fwd_mma(const void* q, const void* k, const void* v, void* o, const float* mask,
+                                  const int64_t* qs, const int64_t* ks, const int64_t* vs, const int64_t* os, int B, int N,
+                                  int H, int D, float scale, cudaStream_t st);  // temporal_attn_mma.cu
+}
+
 using namespace vt;
 
 extern "C" int vt_temporal_attn_fwd(const void* q, const void* k, const void* v, void* o, const float* mask,
@@ -278,6 +285,11 @@ extern "C" int vt_temporal_attn_fwd(const void* q, const void* k, const void* v,
   if (int rc = check(q, k, v, B, N, H, D, strides, 4)) return rc;
   VT_REQUIRE(o != nullptr, VT_ERR_NULL, "o is NULL");
   VT_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), VT_ERR_ALIGN, "tensors must be 16-byte aligned");
+  if (getenv("VT_TEMPORAL_SIMT") == nullptr) {  // default: the tensor-core (mma.sync) forward
+    VT_CHECK_CUDA(temporal_attn_fwd_mma(q, k, v, o, mask, q_strides, k_strides, v_strides, o_strides, B, N, H, D,
+                                        softmax_scale, static_cast<cudaStream_t>(stream)));
+    return 0;
+  }
   TemporalArgs a{};
   a.q = static_cast<const __nv_bfloat16*>(q);
   a.k = static_cast<const __nv_bfloat16*>(k);

@@ -135,6 +135,14 @@ def main():
         return torch.einsum("b i j, b j d -> b i d", s.softmax(dim=-1), vt)
     rf_ms = timeit(ref_t, args.iters)
     report("temporal_attn_fwd[vc2 level 0]", (Bt, N, H, D), q.numel() * 2 * 4, f_ms, rf_ms)
+    do = rn(Bt, N, H, D)
+    b_ms = timeit(lambda: ops.temporal_attn_bwd(do, q, k, v, None, sc), args.iters)
+    qr, kr, vr = (t.detach().clone().requires_grad_(True) for t in (qt, kt, vt))
+    dot = do.permute(0, 2, 1, 3).reshape(Bt * H, N, D)
+    s_ = torch.einsum("b i d, b j d -> b i j", qr, kr) * sc
+    out_r = torch.einsum("b i j, b j d -> b i d", s_.softmax(dim=-1), vr)
+    rb_ms = timeit(lambda: torch.autograd.grad(out_r, (qr, kr, vr), dot, retain_graph=True), args.iters)
+    report("temporal_attn_bwd[vc2 level 0]", (Bt, N, H, D), q.numel() * 2 * 7, b_ms, rb_ms)
 
 
 if __name__ == "__main__":

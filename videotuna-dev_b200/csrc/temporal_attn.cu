@@ -273,6 +273,9 @@ namespace vt {
 cudaError_t temporal_attn_fwd_mma(const void* q, const void* k, const void* v, void* o, const float* mask,
                                   const int64_t* qs, const int64_t* ks, const int64_t* vs, const int64_t* os, int B, int N,
                                   int H, int D, float scale, cudaStream_t st);  // temporal_attn_mma.cu
+cudaError_t temporal_attn_bwd_mma(const void* dout, const void* q, const void* k, const void* v, void* dq, void* dk, void* dv,
+                                  const float* mask, const int64_t* gs, const int64_t* qs, const int64_t* ks, const int64_t* vs,
+                                  int B, int N, int H, int D, float scale, cudaStream_t st);
 }
 
 using namespace vt;
@@ -314,6 +317,11 @@ extern "C" int vt_temporal_attn_bwd(const void* dout, const void* q, const void*
   VT_REQUIRE(dout && dq && dk && dv, VT_ERR_NULL, "temporal attention backward: NULL tensor");
   VT_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(dout) && aligned16(dq) && aligned16(dk) && aligned16(dv),
              VT_ERR_ALIGN, "tensors must be 16-byte aligned");
+  if (getenv("VT_TEMPORAL_SIMT") == nullptr) {  // default: the tensor-core (mma.sync) backward
+    VT_CHECK_CUDA(temporal_attn_bwd_mma(dout, q, k, v, dq, dk, dv, mask, do_strides, q_strides, k_strides, v_strides, B, N, H,
+                                        D, softmax_scale, static_cast<cudaStream_t>(stream)));
+    return 0;
+  }
   TemporalArgs a{};
   a.q = static_cast<const __nv_bfloat16*>(q);
   a.k = static_cast<const __nv_bfloat16*>(k);

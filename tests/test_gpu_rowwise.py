@@ -144,7 +144,12 @@ def test_wan_rope_golden():
 
 @pytest.mark.parametrize("N,C,sp,dt,silu", [(4, 320, (40, 64), torch.bfloat16, True), (2, 640, (20, 32), torch.float32, True),
                                              (3, 1280, (5, 8), torch.bfloat16, False), (2, 128, (3, 7), torch.float32, True),
-                                             (1, 320, (16, 9, 5), torch.bfloat16, True)])
+                                             (1, 320, (16, 9, 5), torch.bfloat16, True),
+                                             # slabs split over a thread-block cluster (DSMEM reduction of the statistics):
+                                             (2, 64, (16, 40, 64), torch.bfloat16, True),    # 164 KB slab -> 16 CTAs
+                                             (2, 64, (8, 20, 32), torch.float32, True),      # fp32, 8 CTAs
+                                             (1, 96, (3, 25, 56), torch.bfloat16, False),    # ragged last chunk
+                                             (2, 960, (40, 64), torch.bfloat16, True)])      # 153 KB slab (skip concat)
 def test_groupnorm_silu_fwd_bwd(N, C, sp, dt, silu):
     import b200vt.functional as Fn
     x = (_r((N, C) + sp, 1, 2.0, 0.7)).to(dt)

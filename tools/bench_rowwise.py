@@ -1,7 +1,8 @@
 """Achieved HBM bandwidth of the memory-bound kernels around attention at the BASELINE shapes, next to
 the same arithmetic written with stock PyTorch ops on the same GPU (what the reference's block code launches).
 Algorithmic bytes per element are the ones DESIGN.md states; the roofline is the measured copy bandwidth in
-MEASURED_PEAKS.json. CUDA-event timing, 3 warm-ups, median of `--iters`; every tensor is far larger than the 126 MB L2.
+MEASURED_PEAKS.json. Device time per call from CUDA-graph replays (tools/_timing.py: no host launch path inside the timed
+region), 3 warm-ups, median of `--iters`; tensors are far larger than the 126 MB L2 or rotate over enough copies to be.
     python tools/bench_rowwise.py [--iters 10]"""
 import argparse
 import json
@@ -16,21 +17,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import b200vt.functional as Fn  # noqa: E402
 import b200vt.ops as ops  # noqa: E402
+from _timing import device_time_ms  # noqa: E402
 
 
 def timeit(fn, iters):
-    for _ in range(3):
-        fn()
-    torch.cuda.synchronize()
-    ts = []
-    for _ in range(iters):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        fn()
-        e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    return sorted(ts)[len(ts) // 2]
+    return device_time_ms(fn, iters)
 
 
 def peak_gbs():
@@ -56,7 +47,7 @@ def main():
         rec = {"kernel": name, "shape": list(shape), "algorithmic_MB": round(nbytes / 1e6, 1), "ours_ms": round(ours_ms, 4),
                "ours_GBps": round(nbytes / ours_ms / 1e6, 1), "frac_of_hbm_peak": round(nbytes / ours_ms / 1e6 / peak, 3),
                "torch_ops_ms": round(torch_ms, 4), "speedup_vs_torch_ops": round(torch_ms / ours_ms, 2),
-               "peak_GBps": peak, "peak_kind": src}
+               "peak_GBps": peak, "peak_kind": src, "timing": device_time_ms.last_mode}
         if note:
             rec["note"] = note
         print(json.dumps(rec), flush=True)
@@ -112,16 +103,36 @@ def main():
            note="reference = hunyuan RMSNorm (fp32 temporaries) + apply_rotary_emb (rotate_half stack/flatten) as torch ops")
     del qkv, q
 
-    # ---- GroupNorm(32) + SiLU (VideoCrafter2 UNet level 0 and level 2, batch 2 x 16 frames) -----------------------------
-    for (N, C, Hh, Ww) in ((32, 320, 40, 64), (32, 1280, 10, 16)):
-        x = rn(N, C, Hh, Ww)
+    # ---- GroupNorm(32) + SiLU (VideoCrafter2 UNet, batch 2 x 16 frames): ResBlock / SpatialTransformer 4-D inputs and the
+    # TemporalTransformer's 5-D input (N = 2 samples, slabs of (C/32) * t*h*w elements). These tensors are smaller than the
+    # 126 MB L2, so every call takes the next of enough distinct copies to cycle through >= 512 MB.
+    for shape in ((32, 320, 40, 64), (32, 960, 40, 64), (32, 1280, 10, 16), (2, 320, 16, 40, 64), (2, 1280, 16, 10, 16)):
+        C = shape[1]
+        nbuf = max(2, int(math.ceil(512e6 / (math.prod(shape) * 4))))
+        xs = [rn(*shape).requires_grad_(True) for _ in range(nbuf)]
+        dys = [rn(*shape) for _ in range(nbuf)]
         gw, gb = 1 + 0.1 * rn(C, dtype=torch.float32), 0.1 * rn(C, dtype=torch.float32)
-        f_ms = timeit(lambda: Fn.groupnorm_silu(x, gw, gb, 32, 1e-5, silu=True), args.iters)
-        rf_ms = timeit(lambda: F.silu(F.group_norm(x.float(), 32, gw, gb, 1e-5).to(x.dtype)), args.iters)
-        n = x.numel()
-        report("groupnorm_silu_fwd[vc2]", (N, C, Hh, Ww), n * 4, f_ms, rf_ms,
-               note="reference = GroupNormSpecific (x.float() -> group_norm -> type(x.dtype)) + SiLU")
-        del x
+        it = [0]
+
+        def nxt():
+            it[0] = (it[0] + 1) % nbuf
+            return it[0]
+        f_ms = timeit(lambda: Fn.groupnorm_silu(xs[nxt()], gw, gb, 32, 1e-5, silu=True), args.iters * 2)
+        rf_ms = timeit(lambda: F.silu(F.group_norm(xs[nxt()].float(), 32, gw, gb, 1e-5).to(torch.bfloat16)), args.iters * 2)
+        ys = [Fn.groupnorm_silu(x, gw, gb, 32, 1e-5, silu=True) for x in xs]
+        yrs = [F.silu(F.group_norm(x.float(), 32, gw, gb, 1e-5).to(torch.bfloat16)) for x in xs]
+
+        def bwd(outs):
+            i = nxt()
+            return torch.autograd.grad(outs[i], xs[i], dys[i], retain_graph=True)
+        b_ms = timeit(lambda: bwd(ys), args.iters * 2)
+        rb_ms = timeit(lambda: bwd(yrs), args.iters * 2)
+        n = math.prod(shape)
+        note = (f"reference = GroupNormSpecific (x.float() -> group_norm -> type(x.dtype)) + SiLU; {nbuf} rotating buffers "
+                "(tensor < L2)")
+        report("groupnorm_silu_fwd[vc2]", shape, n * 4, f_ms, rf_ms, note=note)
+        report("groupnorm_silu_bwd[vc2]", shape, n * 6, b_ms, rb_ms, note=note)
+        del xs, dys, ys, yrs
 
     # ---- temporal micro-attention, N = 16 frames (VideoCrafter2 level 0: 2 x 40 x 64 positions, 5 heads) --------------
     Bt, N, H, D = 5120, 16, 5, 64

@@ -1,20 +1,34 @@
-import sys, torch
-sys.path.insert(0, "/root/repo")
-import b200vt.functional as Fn, b200vt.ops as ops, math
+"""Launch each memory-bound kernel a few times at its BASELINE shape (for `ncu --set full -k regex:...` captures).
+    PROBE_ITERS=1 ncu --set full --clock-control none --import-source on -k regex:'ln_fwd|rmsnorm_rope_fwd|temporal_mma|groupnorm_fwd' \
+        -o gpurun_out/rowwise python tools/rowwise_probe.py"""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import b200vt.functional as Fn  # noqa: E402
+import b200vt.ops as ops  # noqa: E402
+
+N = int(os.environ.get("PROBE_ITERS", "3"))
 x = torch.randn(1, 119056, 3072, device="cuda", dtype=torch.bfloat16)
 sc = torch.randn(1, 3072, device="cuda") * 0.1
-for _ in range(3):
+for _ in range(N):
     y = Fn.ln_modulate(x, sc, sc, eps=1e-6)
 qkv = torch.randn(1, 118800, 3, 24, 128, device="cuda", dtype=torch.bfloat16)
-w = torch.ones(128, device="cuda"); cs = torch.rand(118800, 128, device="cuda")
-for _ in range(3):
+w = torch.ones(128, device="cuda")
+cs = torch.rand(118800, 128, device="cuda")
+for _ in range(N):
     z = Fn.qk_rmsnorm_rope(qkv[:, :, 0], w, cs, cs)
-q = torch.randn(5120, 16, 5, 64, device="cuda", dtype=torch.bfloat16)
-for _ in range(3):
-    o = ops.temporal_attn_fwd(q, q, q, None, 0.125)
-xg = torch.randn(32, 320, 40, 64, device="cuda", dtype=torch.bfloat16)
+q, k, v = (torch.randn(5120, 16, 5, 64, device="cuda", dtype=torch.bfloat16, requires_grad=True) for _ in range(3))
+for _ in range(N):
+    o = ops.temporal_attn_fwd(q, k, v, None, 0.125)
+    o.backward(torch.randn_like(o))
 gw = torch.ones(320, device="cuda")
-for _ in range(3):
-    g = Fn.groupnorm_silu(xg, gw, gw, 32, 1e-5, silu=True)
+for shape in ((32, 320, 40, 64), (2, 320, 16, 40, 64)):  # ResBlock / SpatialTransformer input; TemporalTransformer input
+    xg = torch.randn(*shape, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    for _ in range(N):
+        g = Fn.groupnorm_silu(xg, gw, gw, 32, 1e-5, silu=True)
+        g.backward(torch.randn_like(g))
 torch.cuda.synchronize()
 print("ok")

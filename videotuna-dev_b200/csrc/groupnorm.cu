@@ -6,10 +6,23 @@
 // reduces sum / sum of squares (Welford-free: shifted by the first element for stability); pass 2 re-reads it (an
 // L2 hit: slabs are 50-400 KB, far below the 126 MB L2), normalises, applies SiLU and writes. DRAM traffic is therefore
 // 4 B/elem (bf16) although the kernel is two-pass.
+//
+// Second generation (groupnorm_{fwd,bwd}_bulk_kernel, the default whenever the slab is 16-byte sliceable): the slab of
+// one (sample, group) is cut into CL equal chunks, one per CTA of a thread-block CLUSTER of CL CTAs (CL = 1..16). One
+// thread fetches the CTA's chunk into shared memory with four 1-D bulk asynchronous copies (cp.async.bulk + mbarrier
+// complete_tx), so the whole chunk is in flight at once with no registers tied up; the statistics are reduced over the
+// chunk as the sub-copies land, combined across the cluster through distributed shared memory, and the normalise +
+// SiLU pass reads the chunk back from shared memory: HBM sees every element exactly once in each direction. The cluster
+// dimension is what makes the TemporalTransformer's 5-D GroupNorm parallel: there the slab is (C/G) * t*h*w elements
+// (819 KB at VideoCrafter2 level 0) and only N*G = 64 slabs exist, i.e. 64 CTAs for 148 SMs in the first generation.
 #include <cstdlib>
+#include <cooperative_groups.h>
 #include <cuda_bf16.h>
 
 #include "capi_util.h"
+#include "sm100_ptx.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace vt {
 namespace {
@@ -315,6 +328,296 @@ groupnorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const fl
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// bulk-copy + cluster kernels
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int GB_THREADS = 256;
+constexpr int GB_NSUB = 4;
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// Sum `NV` per-CTA values over the CTAs of the cluster: every CTA publishes its partials in its own shared memory, the
+// cluster synchronises, and every CTA reads all peers' partials through DSMEM. The caller must keep its shared memory
+// alive until the peers have read it (cluster.sync() before exit).
+template <int NV>
+__device__ __forceinline__ void cluster_sum(float* v, float* partial, int CL) {
+  if (CL == 1) return;
+  cg::cluster_group cluster = cg::this_cluster();
+  if (threadIdx.x == 0)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) partial[i] = v[i];
+  cluster.sync();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = 0.f;
+  for (int r = 0; r < CL; ++r) {
+    const float* peer = cluster.map_shared_rank(partial, r);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] += peer[i];
+  }
+}
+
+// grid (CL, G, N), cluster (CL, 1, 1); `chunk` = elements per CTA (a multiple of the vector width), dynamic shared memory
+// = chunk * sizeof(T).
+template <typename T>
+__global__ void __launch_bounds__(GB_THREADS)
+groupnorm_fwd_bulk_kernel(const T* __restrict__ x, T* __restrict__ y, float* __restrict__ mean_out,
+                          float* __restrict__ rstd_out, const float* __restrict__ gamma, const float* __restrict__ beta,
+                          int C, int S, int G, float eps, int apply_silu, int chunk, int CL) {
+  extern __shared__ __align__(128) unsigned char gb_smem[];
+  T* buf = reinterpret_cast<T*>(gb_smem);
+  __shared__ __align__(8) uint64_t bars[GB_NSUB];
+  __shared__ float red[2 * (GB_THREADS / 32)];
+  __shared__ float partial[2];
+  constexpr int VEC = Io<T>::VEC;
+  const int rank = blockIdx.x, g = blockIdx.y, n = blockIdx.z, tid = threadIdx.x;
+  const int cpg = C / G;
+  const size_t base = (static_cast<size_t>(n) * C + static_cast<size_t>(g) * cpg) * S;
+  const int count = cpg * S;
+  const int start = rank * chunk;
+  const int len = max(0, min(chunk, count - start));
+  const int sub = ((chunk / VEC + GB_NSUB - 1) / GB_NSUB) * VEC;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < GB_NSUB; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < GB_NSUB; ++s) {
+      const int off = s * sub, l = min(sub, len - off);
+      if (l > 0) {
+        mbar_arrive_expect_tx(&bars[s], l * sizeof(T));
+        bulk_load_1d(buf + off, x + base + start + off, l * sizeof(T), &bars[s]);
+      }
+    }
+  }
+  const float shiftv = Io<T>::ld1(x + base);  // the same shift in every CTA of the cluster
+  float acc[2] = {0.f, 0.f};
+#pragma unroll 1
+  for (int s = 0; s < GB_NSUB; ++s) {
+    const int off = s * sub, l = min(sub, len - off);
+    if (l <= 0) break;
+    mbar_wait(&bars[s], 0, 0x6e01);
+    for (int i = off + tid * VEC; i < off + l; i += GB_THREADS * VEC) {
+      float f[VEC];
+      Io<T>::load(buf + i, f);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float d = f[k] - shiftv;
+        acc[0] += d;
+        acc[1] = fmaf(d, d, acc[1]);
+      }
+    }
+  }
+  cta_sum<2, GB_THREADS>(acc, red);
+  cluster_sum<2>(acc, partial, CL);
+  const float inv = 1.f / count;
+  const float md = acc[0] * inv;
+  const float var = fmaxf(acc[1] * inv - md * md, 0.f);
+  const float mean = md + shiftv;
+  const float rstd = rsqrtf(var + eps);
+  if (tid == 0 && rank == 0) {
+    if (mean_out) mean_out[n * G + g] = mean;
+    if (rstd_out) rstd_out[n * G + g] = rstd;
+  }
+  T* ys = y + base + start;
+  for (int i = tid * VEC; i < len; i += GB_THREADS * VEC) {
+    const int c = g * cpg + (start + i) / S;  // a vector never straddles channels because S % VEC == 0
+    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    const float a = rstd * ga, bsh = be - mean * a;
+    float f[VEC];
+    Io<T>::load(buf + i, f);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float z = fmaf(f[k], a, bsh);
+      f[k] = apply_silu ? silu_f(z) : z;
+    }
+    Io<T>::store(ys + i, f);
+  }
+  if (CL > 1) cg::this_cluster().sync();  // peers may still be reading `partial`
+}
+
+// Backward in the same layout: x and dy chunks both staged in shared memory (2 * chunk * sizeof(T)); per-channel
+// dgamma / dbeta partials go through shared-memory bins (one warp-reduced atomic per warp and vector sweep) and leave
+// the CTA as one global atomic per channel; the two group sums are combined across the cluster like the statistics.
+template <typename T>
+__global__ void __launch_bounds__(GB_THREADS)
+groupnorm_bwd_bulk_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean_in,
+                          const float* __restrict__ rstd_in, T* __restrict__ dx, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, float* __restrict__ dgamma, float* __restrict__ dbeta, int C,
+                          int S, int G, int apply_silu, int chunk, int CL) {
+  extern __shared__ __align__(128) unsigned char gb_smem[];
+  T* bx = reinterpret_cast<T*>(gb_smem);
+  T* bg = bx + chunk;
+  float* bins = reinterpret_cast<float*>(bg + chunk);  // [2][cpg]: sum gz, sum gz * xh per channel of this group
+  __shared__ __align__(8) uint64_t bars[GB_NSUB];
+  __shared__ float red[2 * (GB_THREADS / 32)];
+  __shared__ float partial[2];
+  constexpr int VEC = Io<T>::VEC;
+  const int rank = blockIdx.x, g = blockIdx.y, n = blockIdx.z, tid = threadIdx.x, lane = threadIdx.x & 31;
+  const int cpg = C / G;
+  const size_t base = (static_cast<size_t>(n) * C + static_cast<size_t>(g) * cpg) * S;
+  const int count = cpg * S;
+  const int start = rank * chunk;
+  const int len = max(0, min(chunk, count - start));
+  const int sub = ((chunk / VEC + GB_NSUB - 1) / GB_NSUB) * VEC;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < GB_NSUB; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < 2 * cpg; i += GB_THREADS) bins[i] = 0.f;
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < GB_NSUB; ++s) {
+      const int off = s * sub, l = min(sub, len - off);
+      if (l > 0) {
+        mbar_arrive_expect_tx(&bars[s], 2 * l * sizeof(T));
+        bulk_load_1d(bx + off, x + base + start + off, l * sizeof(T), &bars[s]);
+        bulk_load_1d(bg + off, dy + base + start + off, l * sizeof(T), &bars[s]);
+      }
+    }
+  }
+  const float mean = mean_in[n * G + g], rstd = rstd_in[n * G + g];
+  float tot[2] = {0.f, 0.f};
+#pragma unroll 1
+  for (int s = 0; s < GB_NSUB; ++s) {
+    const int off = s * sub, l = min(sub, len - off);
+    if (l <= 0) break;
+    mbar_wait(&bars[s], 0, 0x6e02);
+    // warp-uniform trip count so the shuffles below are convergent
+    for (int i0 = off + (tid - lane) * VEC; i0 < off + l; i0 += GB_THREADS * VEC) {
+      const int i = i0 + lane * VEC;
+      const bool ok = i < off + l;
+      const int cc = ok ? (start + i) / S : -1;
+      float a0 = 0.f, a1 = 0.f, ga = 0.f;
+      if (ok) {
+        const int c = g * cpg + cc;
+        ga = gamma ? gamma[c] : 1.f;
+        const float be = beta ? beta[c] : 0.f;
+        float fx[VEC], fg[VEC];
+        Io<T>::load(bx + i, fx);
+        Io<T>::load(bg + i, fg);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          const float xh = (fx[k] - mean) * rstd;
+          float gz = fg[k];
+          if (apply_silu) gz *= dsilu_f(fmaf(xh, ga, be));
+          a0 += gz;
+          a1 = fmaf(gz, xh, a1);
+        }
+      }
+      tot[0] = fmaf(a0, ga, tot[0]);
+      tot[1] = fmaf(a1, ga, tot[1]);
+      // per-channel bins: one atomic pair per warp when the warp's 32 vectors lie in one channel (the common case)
+      const int c_first = __shfl_sync(0xffffffffu, cc, 0);
+      if (__all_sync(0xffffffffu, cc == c_first)) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+          a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        }
+        if (lane == 0 && c_first >= 0) {
+          atomicAdd(bins + c_first, a0);
+          atomicAdd(bins + cpg + c_first, a1);
+        }
+      } else if (ok) {
+        atomicAdd(bins + cc, a0);
+        atomicAdd(bins + cpg + cc, a1);
+      }
+    }
+  }
+  cta_sum<2, GB_THREADS>(tot, red);  // (its barriers also order the bin atomics before the flush below)
+  for (int i = tid; i < cpg; i += GB_THREADS) {
+    if (dbeta) atomicAdd(dbeta + g * cpg + i, bins[i]);
+    if (dgamma) atomicAdd(dgamma + g * cpg + i, bins[cpg + i]);
+  }
+  cluster_sum<2>(tot, partial, CL);
+  const float inv = 1.f / count;
+  const float m1 = tot[0] * inv, m2 = tot[1] * inv;
+  T* os = dx + base + start;
+  for (int i = tid * VEC; i < len; i += GB_THREADS * VEC) {
+    const int c = g * cpg + (start + i) / S;
+    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    float fx[VEC], fg[VEC];
+    Io<T>::load(bx + i, fx);
+    Io<T>::load(bg + i, fg);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float xh = (fx[k] - mean) * rstd;
+      float gz = fg[k];
+      if (apply_silu) gz *= dsilu_f(fmaf(xh, ga, be));
+      fx[k] = rstd * (gz * ga - m1 - xh * m2);
+    }
+    Io<T>::store(os + i, fx);
+  }
+  if (CL > 1) cg::this_cluster().sync();
+}
+
+// Chunking policy. `streams` = staged tensors (1 forward, 2 backward). Prefer the smallest cluster whose chunk lets four
+// (forward) CTAs share an SM, but never fewer than ~4 CTAs per SM over the whole grid when the slab can still be split.
+constexpr size_t hard_smem() { return 112 * 1024; }
+struct BulkPlan {
+  int CL = 0, chunk = 0;
+  size_t smem = 0;
+};
+template <typename T>
+BulkPlan plan_bulk(int N, int C, int S, int G, int streams, const void* p0, const void* p1, const void* p2) {
+  BulkPlan plan;
+  constexpr int VEC = Io<T>::VEC;
+  const long long count = static_cast<long long>(C / G) * S;
+  if (getenv("VT_GN_TWOPASS") != nullptr) return plan;
+  if (S % VEC != 0 || !aligned16(p0) || !aligned16(p1) || (p2 != nullptr && !aligned16(p2))) return plan;
+  if (N > 65535 || G > 65535) return plan;
+  const long long vectors = count / VEC;
+  const size_t extra = streams == 2 ? 2 * static_cast<size_t>(C / G) * sizeof(float) : 0;
+  const size_t soft = 54 * 1024, hard = 110 * 1024;
+  for (int cl = 1; cl <= 16; cl *= 2) {
+    const long long chunk = (vectors + cl - 1) / cl * VEC;
+    const size_t bytes = static_cast<size_t>(chunk) * sizeof(T) * streams + extra;
+    const long long ctas = static_cast<long long>(N) * G * cl;
+    const bool enough_ctas = ctas >= 4 * 148 || chunk * static_cast<long long>(sizeof(T)) <= 8 * 1024;
+    if ((bytes <= soft && enough_ctas) || (cl == 16 && bytes <= hard)) {
+      plan.CL = cl;
+      plan.chunk = static_cast<int>(chunk);
+      plan.smem = bytes;
+      return plan;
+    }
+  }
+  return plan;
+}
+
+template <typename K, typename... Args>
+cudaError_t launch_cluster(K kernel, const BulkPlan& plan, int N, int G, cudaStream_t st, Args... args) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hard_smem()));
+  if (e != cudaSuccess) return e;
+  if (plan.CL > 8) {
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(plan.CL, G, N);
+  cfg.blockDim = dim3(GB_THREADS);
+  cfg.dynamicSmemBytes = plan.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = plan.CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 }  // namespace
 }  // namespace vt
 
@@ -330,6 +633,21 @@ int vt_groupnorm_silu_fwd(const void* x, void* y, float* mean, float* rstd, cons
   VT_REQUIRE(static_cast<long long>(C / G) * S < (1LL << 31), VT_ERR_SHAPE, "group too large");
   VT_REQUIRE(dtype == 0 || dtype == 1, VT_ERR_DTYPE, "dtype %d (0=bf16, 1=fp32)", dtype);
   auto st = static_cast<cudaStream_t>(stream);
+  if (dtype == 0) {
+    const BulkPlan plan = plan_bulk<__nv_bfloat16>(N, C, S, G, 1, x, y, nullptr);
+    if (plan.CL > 0 &&
+        launch_cluster(groupnorm_fwd_bulk_kernel<__nv_bfloat16>, plan, N, G, st, static_cast<const __nv_bfloat16*>(x),
+                       static_cast<__nv_bfloat16*>(y), mean, rstd, gamma, beta, C, S, G, eps, apply_silu, plan.chunk,
+                       plan.CL) == cudaSuccess)
+      return 0;
+  } else {
+    const BulkPlan plan = plan_bulk<float>(N, C, S, G, 1, x, y, nullptr);
+    if (plan.CL > 0 && launch_cluster(groupnorm_fwd_bulk_kernel<float>, plan, N, G, st, static_cast<const float*>(x),
+                                      static_cast<float*>(y), mean, rstd, gamma, beta, C, S, G, eps, apply_silu,
+                                      plan.chunk, plan.CL) == cudaSuccess)
+      return 0;
+  }
+  (void)cudaGetLastError();  // a refused cluster launch falls through to the two-pass kernel
   dim3 grid(G, N);
   if (dtype == 0) {
     const int vec_ok = (S % 8 == 0) && aligned16(x) && aligned16(y);
@@ -363,6 +681,22 @@ int vt_groupnorm_silu_bwd(const void* dy, const void* x, const float* mean, cons
   VT_REQUIRE(N <= 65535, VT_ERR_SHAPE, "N=%d exceeds grid.y", N);
   VT_REQUIRE(dtype == 0 || dtype == 1, VT_ERR_DTYPE, "dtype %d (0=bf16, 1=fp32)", dtype);
   auto st = static_cast<cudaStream_t>(stream);
+  if (dtype == 0) {
+    const BulkPlan plan = plan_bulk<__nv_bfloat16>(N, C, S, G, 2, x, dy, dx);
+    if (plan.CL > 0 &&
+        launch_cluster(groupnorm_bwd_bulk_kernel<__nv_bfloat16>, plan, N, G, st, static_cast<const __nv_bfloat16*>(dy),
+                       static_cast<const __nv_bfloat16*>(x), mean, rstd, static_cast<__nv_bfloat16*>(dx), gamma, beta,
+                       dgamma, dbeta, C, S, G, apply_silu, plan.chunk, plan.CL) == cudaSuccess)
+      return 0;
+  } else {
+    const BulkPlan plan = plan_bulk<float>(N, C, S, G, 2, x, dy, dx);
+    if (plan.CL > 0 &&
+        launch_cluster(groupnorm_bwd_bulk_kernel<float>, plan, N, G, st, static_cast<const float*>(dy),
+                       static_cast<const float*>(x), mean, rstd, static_cast<float*>(dx), gamma, beta, dgamma, dbeta, C, S,
+                       G, apply_silu, plan.chunk, plan.CL) == cudaSuccess)
+      return 0;
+  }
+  (void)cudaGetLastError();
   dim3 grid(G, N);
   if (dtype == 0)
     groupnorm_bwd_kernel<__nv_bfloat16><<<grid, GN_THREADS, 0, st>>>(

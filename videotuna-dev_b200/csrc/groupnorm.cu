@@ -89,9 +89,27 @@ __device__ __forceinline__ void cta_sum(float* v, float* red) {
 }
 
 __device__ __forceinline__ float silu_f(float z) { return z / (1.f + __expf(-z)); }
+// One MUFU op per element instead of two (ex2 + rcp): sigmoid(z) = 0.5 + 0.5 tanh(z / 2), tanh.approx.f32 (max relative
+// error 2^-11, below the 2^-9 rounding of a bf16 result — used by the bf16 instantiations only). At one element per lane
+// and clock the two-MUFU form costs 11.6 us on the VideoCrafter2 level-0 tensor, as much as its HBM time.
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <typename T> __device__ __forceinline__ float silu_t(float z) { return silu_f(z); }
+template <> __device__ __forceinline__ float silu_t<__nv_bfloat16>(float z) {
+  const float h = 0.5f * z;
+  return fmaf(h, tanh_approx(h), h);
+}
 __device__ __forceinline__ float dsilu_f(float z) {
   const float s = 1.f / (1.f + __expf(-z));
   return s * (1.f + z * (1.f - s));
+}
+template <typename T> __device__ __forceinline__ float dsilu_t(float z) { return dsilu_f(z); }
+template <> __device__ __forceinline__ float dsilu_t<__nv_bfloat16>(float z) {
+  const float s = fmaf(0.5f, tanh_approx(0.5f * z), 0.5f);
+  return s * fmaf(z, 1.f - s, 1.f);
 }
 
 // `vec_ok`: S is a multiple of the vector width and the base is 16-byte aligned -> vector path; else scalar path.
@@ -437,7 +455,7 @@ groupnorm_fwd_bulk_kernel(const T* __restrict__ x, T* __restrict__ y, float* __r
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       const float z = fmaf(f[k], a, bsh);
-      f[k] = apply_silu ? silu_f(z) : z;
+      f[k] = apply_silu ? silu_t<T>(z) : z;
     }
     Io<T>::store(ys + i, f);
   }
@@ -510,10 +528,12 @@ groupnorm_bwd_bulk_kernel(const T* __restrict__ dy, const T* __restrict__ x, con
         for (int k = 0; k < VEC; ++k) {
           const float xh = (fx[k] - mean) * rstd;
           float gz = fg[k];
-          if (apply_silu) gz *= dsilu_f(fmaf(xh, ga, be));
+          if (apply_silu) gz *= dsilu_t<T>(fmaf(xh, ga, be));
+          fg[k] = gz;
           a0 += gz;
           a1 = fmaf(gz, xh, a1);
         }
+        if (apply_silu) Io<T>::store(bg + i, fg);  // the second pass reads gz = dy * silu'(z) instead of recomputing it
       }
       tot[0] = fmaf(a0, ga, tot[0]);
       tot[1] = fmaf(a1, ga, tot[1]);
@@ -546,16 +566,15 @@ groupnorm_bwd_bulk_kernel(const T* __restrict__ dy, const T* __restrict__ x, con
   T* os = dx + base + start;
   for (int i = tid * VEC; i < len; i += GB_THREADS * VEC) {
     const int c = g * cpg + (start + i) / S;
-    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    const float ga = gamma ? gamma[c] : 1.f;
     float fx[VEC], fg[VEC];
     Io<T>::load(bx + i, fx);
     Io<T>::load(bg + i, fg);
+    const float rg = rstd * ga, rm1 = rstd * m1, rm2 = rstd * m2;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       const float xh = (fx[k] - mean) * rstd;
-      float gz = fg[k];
-      if (apply_silu) gz *= dsilu_f(fmaf(xh, ga, be));
-      fx[k] = rstd * (gz * ga - m1 - xh * m2);
+      fx[k] = fmaf(fg[k], rg, -fmaf(xh, rm2, rm1));  // fg holds gz (pass 1 rewrote it; cta_sum's barriers order those writes)
     }
     Io<T>::store(os + i, fx);
   }

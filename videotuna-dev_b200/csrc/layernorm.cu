@@ -11,6 +11,7 @@
 // 6-8 CTAs per SM with two rows each in flight keep ~100 KB of loads outstanding per SM.
 // Replaces: hunyuan modulate(LayerNorm(x)) (modulate_layers.py:31-49, models.py:161-164), wan norm(x).float()*(1+e)+e
 // (wan/modules/model.py:294-296, fp32 residual stream), lvdm nn.LayerNorm (lvdm/modules/attention.py:299-310).
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "capi_util.h"
@@ -187,6 +188,116 @@ __global__ void __launch_bounds__(T) ln_fwd_kernel(const XT* __restrict__ x, bf1
   }
 }
 
+// Two rows per iteration (bf16 rows: 2 x VPT vectors current + 2 x VPT prefetched per thread). ncu on the one-row kernel at
+// K1: shared-memory data pipe 67 % busy, 53 % of the stall samples on short-scoreboard (LDS) waits — every 16 bytes of x
+// cost 64 bytes of mul/add reads. Here each mul/add vector read serves two rows and each block-sum round (shuffles +
+// barrier) reduces two rows' values at once, halving both.
+template <typename XT, int T, int VPT>
+__global__ void __launch_bounds__(T, 5) ln_fwd2_kernel(const XT* __restrict__ x, bf16* __restrict__ y, float* __restrict__ mean_out,
+                                                    float* __restrict__ rstd_out, const float* __restrict__ gamma,
+                                                    const float* __restrict__ beta, const float* __restrict__ scale,
+                                                    const float* __restrict__ shift, int L, int C, float eps) {
+  extern __shared__ __align__(16) float sm[];  // mul[CP], add[CP], red[2 uses][2 parities][T/32][2 rows]
+  constexpr int CP = T * VPT * 8;
+  float* mul = sm;
+  float* add = sm + CP;
+  float* red = sm + 2 * CP;
+  const int b = blockIdx.y, t = threadIdx.x;
+  for (int c = t; c < CP; c += T) {
+    float g = 1.f, be = 0.f, s1 = 1.f, sh = 0.f;
+    if (c < C) {
+      if (gamma) g = gamma[c];
+      if (beta) be = beta[c];
+      if (scale) s1 = 1.f + scale[static_cast<size_t>(b) * C + c];
+      if (shift) sh = shift[static_cast<size_t>(b) * C + c];
+    }
+    mul[c] = g * s1;
+    add[c] = be * s1 + sh;
+  }
+  __syncthreads();
+  bool act[VPT];
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) act[j] = (j * T + t) * 8 < C;
+  const size_t base = static_cast<size_t>(b) * L;
+  Vec8<XT> cur[2][VPT], nxt[2][VPT];
+  int l = 2 * blockIdx.x;
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      zero8(cur[r][j]);
+      if (l + r < L && act[j]) load8(x + (base + l + r) * C + (j * T + t) * 8, cur[r][j]);
+    }
+  int parity = 0;
+  for (; l < L; l += 2 * gridDim.x, parity ^= 1) {
+    const int ln = l + 2 * gridDim.x;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+        zero8(nxt[r][j]);
+        if (ln + r < L && act[j]) load8(x + (base + ln + r) * C + (j * T + t) * 8, nxt[r][j]);
+      }
+    float s[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+        float f[8];
+        unpack(cur[r][j], f);  // inactive vectors and a missing second row are zeros
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s[r] += f[i];
+      }
+    block_sum<T, 2>(s, red, parity);
+    const float mean[2] = {s[0] / C, s[1] / C};
+    float q[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+        if (act[j]) {
+          float f[8];
+          unpack(cur[r][j], f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float d = f[i] - mean[r];
+            q[r] = fmaf(d, d, q[r]);
+          }
+        }
+      }
+    block_sum<T, 2>(q, red + 2 * 2 * (T / 32), parity);
+    const float rstd[2] = {rsqrtf(q[0] / C + eps), rsqrtf(q[1] / C + eps)};
+    const bool two = l + 1 < L;
+    if (t < 2 && (t == 0 || two)) {
+      if (mean_out) mean_out[base + l + t] = mean[t];
+      if (rstd_out) rstd_out[base + l + t] = rstd[t];
+    }
+    // xhat * mul + add = x * (rstd * mul) + (add - mean * rstd * mul)
+    const float nb[2] = {-mean[0] * rstd[0], -mean[1] * rstd[1]};
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      if (!act[j]) continue;
+      const int col = (j * T + t) * 8;
+      float m8[8], a8[8];
+      lds8(mul + col, m8);
+      lds8(add + col, a8);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        if (r == 1 && !two) break;
+        float f[8], o[8];
+        unpack(cur[r][j], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = fmaf(fmaf(f[i], rstd[r], nb[r]), m8[i], a8[i]);
+        stg16(y + (base + l + r) * C + col, pack(o));
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) cur[r][j] = nxt[r][j];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // backward.  xh = (x - mean) * rstd;  y = xh * mul + add  with  mul = gamma * s1, add = beta * s1 + shift, s1 = 1 + scale
 //   gh = dy * mul;  dx = rstd * (gh - mean_C(gh) - xh * mean_C(gh * xh))
@@ -343,14 +454,23 @@ template <typename XT, int T, int VPT>
 int launch_fwd(const XT* x, bf16* y, float* mean, float* rstd, const float* gamma, const float* beta, const float* scale,
                const float* shift, int B, int L, int C, float eps, cudaStream_t st) {
   constexpr int CP = T * VPT * 8;
-  const int smem = (2 * CP + 4 * (T / 32)) * 4;
+  // bf16 rows: two rows per iteration (ln_fwd2_kernel); fp32 rows (Wan residual stream) would need 4 x VPT x 8 data registers
+  // per thread for that and stay on the one-row kernel. VT_LN_ROWS=1 selects the one-row kernel for A/B measurements.
+  static const bool one_row = sizeof(XT) == 4 || (getenv("VT_LN_ROWS") != nullptr && atoi(getenv("VT_LN_ROWS")) == 1);
+  const int smem = (2 * CP + (one_row ? 4 : 8) * (T / 32)) * 4;
   static bool configured = false;
   if (!configured) {
     VT_CHECK_CUDA(cudaFuncSetAttribute(ln_fwd_kernel<XT, T, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    VT_CHECK_CUDA(cudaFuncSetAttribute(ln_fwd2_kernel<XT, T, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid(ln_grid_x(L, B, 8), B);
-  ln_fwd_kernel<XT, T, VPT><<<grid, T, smem, st>>>(x, y, mean, rstd, gamma, beta, scale, shift, L, C, eps);
+  if (one_row) {
+    dim3 grid(ln_grid_x(L, B, 8), B);
+    ln_fwd_kernel<XT, T, VPT><<<grid, T, smem, st>>>(x, y, mean, rstd, gamma, beta, scale, shift, L, C, eps);
+  } else {
+    dim3 grid(ln_grid_x((L + 1) / 2, B, 5), B);
+    ln_fwd2_kernel<XT, T, VPT><<<grid, T, smem, st>>>(x, y, mean, rstd, gamma, beta, scale, shift, L, C, eps);
+  }
   VT_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

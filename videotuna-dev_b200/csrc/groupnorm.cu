@@ -389,6 +389,7 @@ groupnorm_fwd_bulk_kernel(const T* __restrict__ x, T* __restrict__ y, float* __r
                           int C, int S, int G, float eps, int apply_silu, int chunk, int CL) {
   extern __shared__ __align__(128) unsigned char gb_smem[];
   T* buf = reinterpret_cast<T*>(gb_smem);
+  float* sgb = reinterpret_cast<float*>(buf + chunk);  // [2][cpg]: gamma, beta of this group's channels
   __shared__ __align__(8) uint64_t bars[GB_NSUB];
   __shared__ float red[2 * (GB_THREADS / 32)];
   __shared__ float partial[2];
@@ -404,6 +405,10 @@ groupnorm_fwd_bulk_kernel(const T* __restrict__ x, T* __restrict__ y, float* __r
 #pragma unroll
     for (int s = 0; s < GB_NSUB; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
+  }
+  for (int i = tid; i < cpg; i += GB_THREADS) {
+    sgb[i] = gamma ? gamma[g * cpg + i] : 1.f;
+    sgb[cpg + i] = beta ? beta[g * cpg + i] : 0.f;
   }
   __syncthreads();
   if (tid == 0) {
@@ -447,8 +452,8 @@ groupnorm_fwd_bulk_kernel(const T* __restrict__ x, T* __restrict__ y, float* __r
   }
   T* ys = y + base + start;
   for (int i = tid * VEC; i < len; i += GB_THREADS * VEC) {
-    const int c = g * cpg + (start + i) / S;  // a vector never straddles channels because S % VEC == 0
-    const float ga = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    const int cc = (start + i) / S;  // a vector never straddles channels because S % VEC == 0
+    const float ga = sgb[cc], be = sgb[cpg + cc];
     const float a = rstd * ga, bsh = be - mean * a;
     float f[VEC];
     Io<T>::load(buf + i, f);
@@ -472,15 +477,17 @@ groupnorm_bwd_bulk_kernel(const T* __restrict__ dy, const T* __restrict__ x, con
                           const float* __restrict__ beta, float* __restrict__ dgamma, float* __restrict__ dbeta, int C,
                           int S, int G, int apply_silu, int chunk, int CL) {
   extern __shared__ __align__(128) unsigned char gb_smem[];
+  const int cpg = C / G;
   T* bx = reinterpret_cast<T*>(gb_smem);
   T* bg = bx + chunk;
-  float* bins = reinterpret_cast<float*>(bg + chunk);  // [2][cpg]: sum gz, sum gz * xh per channel of this group
+  float* sgb = reinterpret_cast<float*>(bg + chunk);   // [2][cpg]: gamma, beta of this group's channels
+  float* bins = sgb + 2 * cpg;  // [warps][2][cpg]: sum gz, sum gz * xh per channel, one private copy per warp (no atomics)
   __shared__ __align__(8) uint64_t bars[GB_NSUB];
   __shared__ float red[2 * (GB_THREADS / 32)];
   __shared__ float partial[2];
   constexpr int VEC = Io<T>::VEC;
   const int rank = blockIdx.x, g = blockIdx.y, n = blockIdx.z, tid = threadIdx.x, lane = threadIdx.x & 31;
-  const int cpg = C / G;
+  constexpr int NW = GB_THREADS / 32;
   const size_t base = (static_cast<size_t>(n) * C + static_cast<size_t>(g) * cpg) * S;
   const int count = cpg * S;
   const int start = rank * chunk;
@@ -491,7 +498,12 @@ groupnorm_bwd_bulk_kernel(const T* __restrict__ dy, const T* __restrict__ x, con
     for (int s = 0; s < GB_NSUB; ++s) mbar_init(&bars[s], 1);
     fence_mbar_init();
   }
-  for (int i = tid; i < 2 * cpg; i += GB_THREADS) bins[i] = 0.f;
+  for (int i = tid; i < NW * 2 * cpg; i += GB_THREADS) bins[i] = 0.f;
+  for (int i = tid; i < cpg; i += GB_THREADS) {
+    sgb[i] = gamma ? gamma[g * cpg + i] : 1.f;
+    sgb[cpg + i] = beta ? beta[g * cpg + i] : 0.f;
+  }
+  float* wbins = bins + (tid >> 5) * 2 * cpg;
   __syncthreads();
   if (tid == 0) {
 #pragma unroll
@@ -518,9 +530,8 @@ groupnorm_bwd_bulk_kernel(const T* __restrict__ dy, const T* __restrict__ x, con
       const int cc = ok ? (start + i) / S : -1;
       float a0 = 0.f, a1 = 0.f, ga = 0.f;
       if (ok) {
-        const int c = g * cpg + cc;
-        ga = gamma ? gamma[c] : 1.f;
-        const float be = beta ? beta[c] : 0.f;
+        ga = sgb[cc];
+        const float be = sgb[cpg + cc];
         float fx[VEC], fg[VEC];
         Io<T>::load(bx + i, fx);
         Io<T>::load(bg + i, fg);
@@ -537,36 +548,44 @@ groupnorm_bwd_bulk_kernel(const T* __restrict__ dy, const T* __restrict__ x, con
       }
       tot[0] = fmaf(a0, ga, tot[0]);
       tot[1] = fmaf(a1, ga, tot[1]);
-      // per-channel bins: one atomic pair per warp when the warp's 32 vectors lie in one channel (the common case)
-      const int c_first = __shfl_sync(0xffffffffu, cc, 0);
-      if (__all_sync(0xffffffffu, cc == c_first)) {
+      // per-channel bins, private to the warp: for every distinct channel among the warp's 32 vectors (one in the common
+      // case, two across a channel boundary) the lanes of that channel are summed by shuffles and the leader adds the pair
+      // to the warp's own bin with plain loads / stores (shared-memory float atomics are CAS loops and, with eight warps on
+      // one address, were a quarter of the stall samples)
+      unsigned remaining = __ballot_sync(0xffffffffu, ok);
+      while (remaining != 0) {
+        const int leader = __ffs(remaining) - 1;
+        const int c = __shfl_sync(0xffffffffu, cc, leader);
+        const bool mine = ok && cc == c;
+        float v0 = mine ? a0 : 0.f, v1 = mine ? a1 : 0.f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-          a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-          a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+          v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+          v1 += __shfl_xor_sync(0xffffffffu, v1, o);
         }
-        if (lane == 0 && c_first >= 0) {
-          atomicAdd(bins + c_first, a0);
-          atomicAdd(bins + cpg + c_first, a1);
+        if (lane == leader) {
+          wbins[c] += v0;
+          wbins[cpg + c] += v1;
         }
-      } else if (ok) {
-        atomicAdd(bins + cc, a0);
-        atomicAdd(bins + cpg + cc, a1);
+        __syncwarp();  // the next leader may be another lane updating the same bin
+        remaining &= ~__ballot_sync(0xffffffffu, mine);
       }
     }
   }
-  cta_sum<2, GB_THREADS>(tot, red);  // (its barriers also order the bin atomics before the flush below)
-  for (int i = tid; i < cpg; i += GB_THREADS) {
-    if (dbeta) atomicAdd(dbeta + g * cpg + i, bins[i]);
-    if (dgamma) atomicAdd(dgamma + g * cpg + i, bins[cpg + i]);
+  cta_sum<2, GB_THREADS>(tot, red);  // (its barriers also order the bin updates before the flush below)
+  for (int i = tid; i < 2 * cpg; i += GB_THREADS) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) v += bins[w * 2 * cpg + i];
+    float* dst = i < cpg ? dbeta : dgamma;
+    if (dst) atomicAdd(dst + g * cpg + (i < cpg ? i : i - cpg), v);
   }
   cluster_sum<2>(tot, partial, CL);
   const float inv = 1.f / count;
   const float m1 = tot[0] * inv, m2 = tot[1] * inv;
   T* os = dx + base + start;
   for (int i = tid * VEC; i < len; i += GB_THREADS * VEC) {
-    const int c = g * cpg + (start + i) / S;
-    const float ga = gamma ? gamma[c] : 1.f;
+    const float ga = sgb[(start + i) / S];
     float fx[VEC], fg[VEC];
     Io<T>::load(bx + i, fx);
     Io<T>::load(bg + i, fg);
@@ -597,7 +616,7 @@ BulkPlan plan_bulk(int N, int C, int S, int G, int streams, const void* p0, cons
   if (S % VEC != 0 || !aligned16(p0) || !aligned16(p1) || (p2 != nullptr && !aligned16(p2))) return plan;
   if (N > 65535 || G > 65535) return plan;
   const long long vectors = count / VEC;
-  const size_t extra = streams == 2 ? 2 * static_cast<size_t>(C / G) * sizeof(float) : 0;
+  const size_t extra = (2 + (streams == 2 ? 2 * (GB_THREADS / 32) : 0)) * static_cast<size_t>(C / G) * sizeof(float);
   const size_t soft = 54 * 1024, hard = 110 * 1024;
   for (int cl = 1; cl <= 16; cl *= 2) {
     const long long chunk = (vectors + cl - 1) / cl * VEC;

@@ -561,7 +561,7 @@ namespace vt {
 namespace {
 
 template <int NORM, int VPT, int D>
-__global__ void __launch_bounds__(128) rope_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, float* __restrict__ rstd_out,
+__global__ void __launch_bounds__(128, (VPT <= 3 ? 5 : 3)) rope_fwd_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, float* __restrict__ rstd_out,
                                                        const float* __restrict__ w, const float* __restrict__ cosT,
                                                        const float* __restrict__ sinT, int64_t x_sb, int64_t x_sl,
                                                        int64_t x_sh, int64_t y_sb, int64_t y_sl, int64_t y_sh, int L, int H,
@@ -589,19 +589,25 @@ __global__ void __launch_bounds__(128) rope_fwd_kernel(const bf16* __restrict__ 
 #pragma unroll
     for (int j = 0; j < VPT; ++j) load8(x + b * x_sb + static_cast<int64_t>(l) * x_sl + (j * HPS + hsub) * x_sh + d0, cur[j]);
   }
+  // the token's cos / sin slice travels with its row: fetched one iteration ahead, like the row itself (fetched at the point
+  // of use it exposed a full L2 / HBM latency per token)
+  float cs[8], sn[8], csn[8], snn[8];
+  if (l < L && cosT != nullptr && l < L_rope) {
+    lds8(cosT + static_cast<size_t>(l) * D + d0, cs);
+    lds8(sinT + static_cast<size_t>(l) * D + d0, sn);
+  }
   int parity = 0;
   for (; l < L; l += gridDim.x, parity ^= 1) {
     const int ln = l + gridDim.x;
     if (ln < L) {
 #pragma unroll
       for (int j = 0; j < VPT; ++j) load8(x + b * x_sb + static_cast<int64_t>(ln) * x_sl + (j * HPS + hsub) * x_sh + d0, nxt[j]);
+      if (cosT != nullptr && ln < L_rope) {
+        lds8(cosT + static_cast<size_t>(ln) * D + d0, csn);
+        lds8(sinT + static_cast<size_t>(ln) * D + d0, snn);
+      }
     }
     const bool rot = cosT != nullptr && l < L_rope;
-    float cs[8], sn[8];
-    if (rot) {
-      lds8(cosT + static_cast<size_t>(l) * D + d0, cs);
-      lds8(sinT + static_cast<size_t>(l) * D + d0, sn);
-    }
     float f[VPT][8], ss[VPT];
 #pragma unroll
     for (int j = 0; j < VPT; ++j) {
@@ -652,6 +658,11 @@ __global__ void __launch_bounds__(128) rope_fwd_kernel(const bf16* __restrict__ 
     }
 #pragma unroll
     for (int j = 0; j < VPT; ++j) cur[j] = nxt[j];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      cs[i] = csn[i];
+      sn[i] = snn[i];
+    }
   }
 }
 

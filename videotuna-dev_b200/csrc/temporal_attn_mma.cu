@@ -33,8 +33,6 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -71,47 +69,33 @@ __global__ void __launch_bounds__(128) temporal_mma_fwd_kernel(const MmaArgs a) 
   constexpr int NTO = D / 8;      // 8-dim n-tiles of O
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // two stages per warp: the q/k/v tiles of the warp's NEXT pair are in flight (cp.async) while it computes the current one
-  constexpr int STAGE = 3 * R * PITCH;
-  bf16* sbase = reinterpret_cast<bf16*>(smem_raw) + warp * 2 * STAGE;
+  bf16* sq = reinterpret_cast<bf16*>(smem_raw) + warp * 3 * R * PITCH;
+  bf16* sk = sq + R * PITCH;
+  bf16* sv = sk + R * PITCH;
   const int N = a.N;
   const int g = lane >> 2, t = lane & 3;
   const int64_t pairs = static_cast<int64_t>(a.B) * a.H;
   // rows N..R-1 are never loaded: zero them once (their scores are masked, but 0 * garbage must not be NaN in P V)
-  for (int idx = lane; idx < 2 * 3 * (R - N) * (D / 8); idx += 32) {
-    const int tile = idx / ((R - N) * (D / 8)), rem = idx % ((R - N) * (D / 8));
-    const int r = N + rem / (D / 8), c = (rem % (D / 8)) * 8;
-    *reinterpret_cast<uint4*>(sbase + tile * R * PITCH + r * PITCH + c) = make_uint4(0, 0, 0, 0);
+  for (int idx = lane; idx < (R - N) * (D / 8); idx += 32) {
+    const int r = N + idx / (D / 8), c = (idx % (D / 8)) * 8;
+    *reinterpret_cast<uint4*>(sq + r * PITCH + c) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(sk + r * PITCH + c) = make_uint4(0, 0, 0, 0);
+    *reinterpret_cast<uint4*>(sv + r * PITCH + c) = make_uint4(0, 0, 0, 0);
   }
   const int nwarps = blockDim.x >> 5;
-  const int64_t stride = static_cast<int64_t>(gridDim.x) * nwarps;
-  auto issue = [&](int64_t pair, int stage) {
+  for (int64_t pair = static_cast<int64_t>(blockIdx.x) * nwarps + warp; pair < pairs;
+       pair += static_cast<int64_t>(gridDim.x) * nwarps) {
     const int b = static_cast<int>(pair / a.H), h = static_cast<int>(pair % a.H);
     const bf16* gq = a.q + b * a.q_s[0] + h * a.q_s[2];
     const bf16* gk = a.k + b * a.k_s[0] + h * a.k_s[2];
     const bf16* gv = a.v + b * a.v_s[0] + h * a.v_s[2];
-    bf16* dq = sbase + stage * STAGE;
     for (int idx = lane; idx < N * (D / 8); idx += 32) {
       const int r = idx / (D / 8), c = (idx % (D / 8)) * 8;
-      cp_async16(dq + r * PITCH + c, gq + r * a.q_s[1] + c);
-      cp_async16(dq + R * PITCH + r * PITCH + c, gk + r * a.k_s[1] + c);
-      cp_async16(dq + 2 * R * PITCH + r * PITCH + c, gv + r * a.v_s[1] + c);
+      cp_async16(sq + r * PITCH + c, gq + r * a.q_s[1] + c);
+      cp_async16(sk + r * PITCH + c, gk + r * a.k_s[1] + c);
+      cp_async16(sv + r * PITCH + c, gv + r * a.v_s[1] + c);
     }
-    cp_async_commit();
-  };
-  int64_t pair = static_cast<int64_t>(blockIdx.x) * nwarps + warp;
-  if (pair < pairs) issue(pair, 0);
-  for (int stage = 0; pair < pairs; pair += stride, stage ^= 1) {
-    const int b = static_cast<int>(pair / a.H), h = static_cast<int>(pair % a.H);
-    bf16* sq = sbase + stage * STAGE;
-    bf16* sk = sq + R * PITCH;
-    bf16* sv = sk + R * PITCH;
-    if (pair + stride < pairs) {
-      issue(pair + stride, stage ^ 1);  // the other stage was released by the __syncwarp closing the previous iteration
-      cp_async_wait_1();
-    } else {
-      cp_async_wait_all();
-    }
+    cp_async_wait_all();
     __syncwarp();
 
     // ---- S = Q K^T : acc[mt][nt][4], rows mt*16 + g (+8), keys nt*8 + 2t (+1) ----
@@ -225,14 +209,13 @@ __global__ void __launch_bounds__(128) temporal_mma_fwd_kernel(const MmaArgs a) 
       const int r = N + idx / (D / 8), c = (idx % (D / 8)) * 8;
       *reinterpret_cast<uint4*>(sq + r * PITCH + c) = make_uint4(0, 0, 0, 0);
     }
-    __syncwarp();  // this stage is refilled by the prefetch issued at the top of the next iteration
   }
 }
 
 template <int D, int MT>
 cudaError_t launch_mma(const MmaArgs& a, cudaStream_t st) {
   constexpr int WARPS = 4;
-  constexpr int bytes = WARPS * 2 * 3 * (16 * MT) * (D + 8) * 2;  // two stages per warp
+  constexpr int bytes = WARPS * 3 * (16 * MT) * (D + 8) * 2;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(temporal_mma_fwd_kernel<D, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);

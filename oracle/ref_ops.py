@@ -328,6 +328,35 @@ def diffusers_cogvideox_attention(hidden: Tensor, encoder_hidden: Tensor, wq: Te
     return o[:, T:], o[:, :T]
 
 
+def diffusers_cogvideox_norm_zero(hidden: Tensor, encoder: Tensor, temb: Tensor, lin_w: Tensor, lin_b, ln_w, ln_b, eps: float):
+    """CogVideoXLayerNormZero.forward (diffusers 0.32.2 models/normalization.py; PARITY UNPINNED as above):
+    shift, scale, gate, enc_shift, enc_scale, enc_gate = Linear(SiLU(temb)).chunk(6); both streams through the same
+    LayerNorm, then * (1 + scale) + shift; gates returned as (B, 1, C)."""
+    shift, scale, gate, e_shift, e_scale, e_gate = F.linear(F.silu(temb), lin_w, lin_b).chunk(6, dim=1)
+    C = hidden.shape[-1]
+    h = F.layer_norm(hidden, (C,), ln_w, ln_b, eps) * (1 + scale)[:, None, :] + shift[:, None, :]
+    e = F.layer_norm(encoder, (C,), ln_w, ln_b, eps) * (1 + e_scale)[:, None, :] + e_shift[:, None, :]
+    return h, e, gate[:, None, :], e_gate[:, None, :]
+
+
+def diffusers_cogvideox_block(hidden: Tensor, encoder: Tensor, temb: Tensor, p: dict, heads: int, rotary=None):
+    """CogVideoXBlock.forward (diffusers 0.32.2 models/transformers/cogvideox_transformer_3d.py; PARITY UNPINNED):
+    norm1 -> attention (diffusers_cogvideox_attention) -> gated residuals -> norm2 -> FeedForward(gelu-approximate) over
+    [text; video] -> gated residuals. p: norm1/norm2 = (lin_w, lin_b, ln_w, ln_b, eps); attn = kwargs of
+    diffusers_cogvideox_attention; ff = (w1, b1, w2, b2)."""
+    T = encoder.shape[1]
+    hn, en, g, eg = diffusers_cogvideox_norm_zero(hidden, encoder, temb, *p["norm1"])
+    ah, ae = diffusers_cogvideox_attention(hn, en, heads=heads, rotary=rotary, **p["attn"])
+    hidden = hidden + g * ah
+    encoder = encoder + eg * ae
+    hn, en, g, eg = diffusers_cogvideox_norm_zero(hidden, encoder, temb, *p["norm2"])
+    w1, b1, w2, b2 = p["ff"]
+    ff = F.linear(F.gelu(F.linear(torch.cat([en, hn], dim=1), w1, b1), approximate="tanh"), w2, b2)
+    hidden = hidden + g * ff[:, T:]
+    encoder = encoder + eg * ff[:, :T]
+    return hidden, encoder
+
+
 def diffusers_hunyuan_attention(hidden: Tensor, encoder_hidden: Tensor, p: dict, heads: int, rotary=None,
                                 valid_len: Optional[Tensor] = None, eps: float = 1e-6):
     """HunyuanVideoAttnProcessor2_0, double-stream form (p has add_q/add_k/add_v projections) or single-stream form

@@ -271,5 +271,77 @@ class ResBlockShell(nn.Module):
         return self._fwd(self, x, emb, batch_size)
 
 
+class DiffusersAttentionShell(nn.Module):
+    """diffusers 0.32.2 `Attention` as CogVideoXBlock builds it (query_dim=dim, heads, dim_head, qk_norm="layer_norm",
+    eps=1e-6, bias=True, out_bias=True): to_q/to_k/to_v, to_out = [Linear, Dropout], norm_q/norm_k = LayerNorm(dim_head),
+    .heads, .processor, set_processor(); forward hands over to the processor like the real module."""
+
+    def __init__(self, dim, heads, processor=None):
+        super().__init__()
+        self.heads = heads
+        d = dim // heads
+        self.to_q, self.to_k, self.to_v = nn.Linear(dim, dim), nn.Linear(dim, dim), nn.Linear(dim, dim)
+        self.to_out = nn.ModuleList([nn.Linear(dim, dim), nn.Dropout(0.0)])
+        self.norm_q, self.norm_k = nn.LayerNorm(d, eps=1e-6), nn.LayerNorm(d, eps=1e-6)
+        self.is_cross_attention = False
+        self.processor = processor
+
+    def set_processor(self, processor):
+        self.processor = processor
+
+    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **kw):
+        return self.processor(self, hidden_states, encoder_hidden_states=encoder_hidden_states,
+                              attention_mask=attention_mask, **kw)
+
+
+class CogLayerNormZeroShell(nn.Module):
+    """diffusers `CogVideoXLayerNormZero(conditioning_dim, embedding_dim, elementwise_affine=True, eps=1e-5, bias=True)`."""
+
+    def __init__(self, cond_dim, dim, eps=1e-5):
+        super().__init__()
+        self.silu = nn.SiLU()
+        self.linear = nn.Linear(cond_dim, 6 * dim)
+        self.norm = nn.LayerNorm(dim, eps=eps, elementwise_affine=True)
+
+
+class _GELUProj(nn.Module):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out)
+
+    def forward(self, x):
+        return torch.nn.functional.gelu(self.proj(x), approximate="tanh")
+
+
+class DiffusersFeedForwardShell(nn.Module):
+    """diffusers `FeedForward(dim, activation_fn="gelu-approximate")`: net = [GELU(proj), Dropout, Linear]."""
+
+    def __init__(self, dim, mult=4):
+        super().__init__()
+        self.net = nn.ModuleList([_GELUProj(dim, dim * mult), nn.Dropout(0.0), nn.Linear(dim * mult, dim)])
+
+    def forward(self, x):
+        for m in self.net:
+            x = m(x)
+        return x
+
+
+class CogVideoXBlockShell(nn.Module):
+    """diffusers 0.32.2 `CogVideoXBlock.__init__` (dim, num_attention_heads, attention_head_dim, time_embed_dim): norm1,
+    attn1, norm2, ff, with the drop-in forward bound as patch.set_diffusers_blocks() binds it."""
+
+    def __init__(self, dim, heads, time_embed_dim, processor=None):
+        super().__init__()
+        from b200vt import blocks
+        self.norm1 = CogLayerNormZeroShell(time_embed_dim, dim)
+        self.attn1 = DiffusersAttentionShell(dim, heads, processor if processor is not None else blocks.CogVideoXAttnProcessor())
+        self.norm2 = CogLayerNormZeroShell(time_embed_dim, dim)
+        self.ff = DiffusersFeedForwardShell(dim)
+        self._fwd = blocks.cogvideox_block_forward
+
+    def forward(self, *a, **k):
+        return self._fwd(self, *a, **k)
+
+
 def load_shell(module, sd, device, dtype=torch.bfloat16):
     return _load(module, sd, device, dtype)

@@ -125,3 +125,20 @@ def test_diffusers_processors_are_installed_by_duck_typing():
     assert P.set_diffusers_processors(model) == 2
     hs, ehs = torch.randn(1, 8, 128), torch.randn(1, 4, 128)
     assert model[0].processor(model[0], hs, ehs)[0] == "stock"  # CPU fp32 -> Unsupported -> stock processor
+
+
+def test_diffusers_cogvideox_blocks_are_bound_per_instance_with_fallback():
+    """set_diffusers_blocks() binds the drop-in forward on modules whose class is named CogVideoXBlock (diffusers is not
+    installed here) and only once; CPU / fp32 activations raise Unsupported inside it and reach the stock forward."""
+    import b200vt.patch as P
+
+    class CogVideoXBlock(torch.nn.Module):  # stand-in: only the name and a forward matter for the binding
+        def forward(self, hidden_states, encoder_hidden_states, temb, image_rotary_emb=None, attention_kwargs=None):
+            return "stock", hidden_states.shape
+
+    model = torch.nn.Sequential(CogVideoXBlock(), torch.nn.Linear(2, 2), CogVideoXBlock())
+    assert P.set_diffusers_blocks(model) == 2
+    assert P.set_diffusers_blocks(model) == 0  # idempotent
+    hs, ehs, temb = torch.randn(1, 8, 128), torch.randn(1, 4, 128), torch.randn(1, 16)
+    assert model[0](hs, ehs, temb)[0] == "stock"
+    assert model[2](hs, ehs, temb=temb)[0] == "stock"

@@ -2,7 +2,7 @@
 "End-to-end"): forward + backward of the transformer-block stack of a DiT backbone on synthetic tokens of the named
 shape, with random-init weights of the named architecture.
 
-    python tools/bench_denoiser.py --model hunyuan|wan [--arm ours|torch] [--double N --single M | --layers N]
+    python tools/bench_denoiser.py --model hunyuan|wan|cogvideox [--arm ours|torch] [--double N --single M | --layers N]
                                    [--steps K] [--warmup W] [--no-checkpoint]
     python -m torch.distributed.run --nproc-per-node P ... tools/bench_denoiser.py --model hunyuan   (Ulysses SP)
 
@@ -17,7 +17,8 @@ arms
 Both arms: bf16 weights, per-block activation checkpointing (use_reentrant=False, as lvdm/utils.py:122 and the i2v DiT
 switch hyvideo_i2v/modules/models.py:764-769 do), hunyuan = LoRA step (frozen base weights, rank-4 adapters on the
 attention projections, configs/007_hunyuanvideo/hunyuanvideo_t2v_diffuser_lora.yaml:56-61), wan = full fwd+bwd (weight
-gradients on). Patch embedding, text refiner and final layer (< 0.1 % of the FLOPs) are not part of the stack: the inputs
+gradients on), cogvideox = full fwd+bwd of diffusers-style CogVideoXBlocks (torch arm: the stock block math with
+F.scaled_dot_product_attention, as CogVideoXAttnProcessor2_0 calls it). Patch embedding, text refiner and final layer (< 0.1 % of the FLOPs) are not part of the stack: the inputs
 are the token streams the first block sees. One iteration = forward + backward of the stack; no optimizer step (rank-4
 adapters / out of the hot path). Timing: CUDA events around K iterations, barrier + synchronize on both sides, max over
 ranks. This is a tool next to bench.py (whose contract stays the attention metric), not a replacement for it."""
@@ -55,6 +56,9 @@ CONFIGS = {
                     rope_dims=(16, 56, 56), theta=256.0),
     # Wan2.1-T2V-14B 480x832x81 (C5): wan/configs/wan_t2v_14B.py:20-29
     "wan": dict(dim=5120, ffn=13824, heads=40, layers=40, grid=(21, 30, 52), txt=512),
+    # CogVideoX-2B 480x720x49 (C3): diffusers 0.32.2 CogVideoXTransformer3DModel config of THUDM/CogVideoX-2b [ext]
+    # (30 heads x 64, 30 layers, time_embed_dim 512, text 226 tokens, no rotary embedding in the 2B model)
+    "cogvideox": dict(dim=1920, heads=30, layers=30, time_embed_dim=512, grid=(13, 30, 45), txt=226),
 }
 
 
@@ -208,6 +212,35 @@ def wan_block_torch(m, x, e, seq_lens, grid_sizes, freqs, context, context_lens)
     return x + y * e[5]
 
 
+def cog_norm_zero_torch(norm, h, e, temb):  # diffusers CogVideoXLayerNormZero.forward [ext]
+    shift, scale, gate, e_shift, e_scale, e_gate = norm.linear(norm.silu(temb)).chunk(6, dim=1)
+    h = norm.norm(h) * (1 + scale)[:, None, :] + shift[:, None, :]
+    e = norm.norm(e) * (1 + e_scale)[:, None, :] + e_shift[:, None, :]
+    return h, e, gate[:, None, :], e_gate[:, None, :]
+
+
+def cog_attn_torch(attn, h, e):  # diffusers CogVideoXAttnProcessor2_0.__call__ [ext]: SDPA on (B, heads, S, d)
+    T = e.size(1)
+    x = torch.cat([e, h], dim=1)
+    B, S, _ = x.shape
+    q, k, v = (lin(x).view(B, S, attn.heads, -1).transpose(1, 2) for lin in (attn.to_q, attn.to_k, attn.to_v))
+    q, k = attn.norm_q(q), attn.norm_k(k)
+    o = F.scaled_dot_product_attention(q, k, v, dropout_p=0.0, is_causal=False)
+    o = attn.to_out[1](attn.to_out[0](o.transpose(1, 2).reshape(B, S, -1)))
+    return o[:, T:], o[:, :T]
+
+
+def cog_block_torch(m, h, e, temb):  # diffusers CogVideoXBlock.forward [ext]
+    T = e.size(1)
+    hn, en, g, eg = cog_norm_zero_torch(m.norm1, h, e, temb)
+    ah, ae = cog_attn_torch(m.attn1, hn, en)
+    h = h + g * ah
+    e = e + eg * ae
+    hn, en, g, eg = cog_norm_zero_torch(m.norm2, h, e, temb)
+    ff = m.ff(torch.cat([en, hn], dim=1))
+    return h + g * ff[:, T:], e + eg * ff[:, :T]
+
+
 # =====================================================================================================================
 # tables
 # =====================================================================================================================
@@ -255,6 +288,15 @@ def build_wan(cfg, n_layers, dev):
     for b in blocks:
         nn.init.normal_(b.modulation, std=0.02)  # zero-init in the reference; re-drawn (SURVEY §4 trap 1)
     return blocks
+
+
+def build_cogvideox(cfg, n_layers, dev):
+    torch.set_default_dtype(BF16)
+    try:
+        with torch.device(dev):
+            return [H.CogVideoXBlockShell(cfg["dim"], cfg["heads"], cfg["time_embed_dim"]) for _ in range(n_layers)]
+    finally:
+        torch.set_default_dtype(torch.float32)
 
 
 def main():
@@ -336,6 +378,32 @@ def main():
             for p in params:
                 p.grad = None
             return x.detach(), leaf.grad
+    elif args.model == "cogvideox":
+        assert world == 1, "CogVideoX-2B has 30 heads: data parallel only (SURVEY 8e); bench it at 1 GPU"
+        nl = cfg["layers"] if args.layers is None else args.layers
+        blocks = build_cogvideox(cfg, nl, dev)
+        C, heads = cfg["dim"], cfg["heads"]
+        g = torch.Generator(device=dev).manual_seed(SEED)
+        h0 = torch.randn(1, n_img, C, device=dev, dtype=BF16, generator=g)
+        t0 = torch.randn(1, n_txt, C, device=dev, dtype=BF16, generator=g)
+        temb = torch.randn(1, cfg["time_embed_dim"], device=dev, dtype=BF16, generator=g)
+        d_out = torch.randn(1, n_img, C, device=dev, dtype=BF16, generator=g) * 1e-2
+        params = [p for b in blocks for p in b.parameters()]
+        n_params = sum(p.numel() for p in params)
+        layers_desc = {"layers": nl}
+        attn_flops = 14.0 * heads * float(n_img + n_txt) ** 2 * (C // heads) * nl
+        attn_exec = attn_flops * (18.0 / 14.0 if ckpt else 1.0)
+
+        def iteration(ours=ours):
+            h = leaf = h0.detach().requires_grad_(True)
+            e = t0.detach().requires_grad_(True)
+            for b in blocks:
+                fn = b if ours else (lambda *a, _b=b: cog_block_torch(_b, *a))
+                h, e = run_block(fn, h, e, temb)
+            torch.autograd.backward([h, e], [d_out, torch.zeros_like(e)])
+            for p in params:
+                p.grad = None
+            return h.detach(), leaf.grad
     else:
         assert world == 1, "wan sequence parallel goes through patch.wan_usp_attn_forward; bench it at 1 GPU here"
         nl = cfg["layers"] if args.layers is None else args.layers
@@ -413,8 +481,9 @@ def main():
                        "block_params": n_params, "trainable_params": sum(p.numel() for p in params),
                        "activation_checkpointing": ckpt, "dtype": "bf16",
                        "parallelism": "single" if world == 1 else f"ulysses_sp{world}",
-                       "attention": ("b200vt tcgen05 kernels" if ours else "flash_attn_varlen_func (FA2, the reference's "
-                                     "mode=\"flash\")")},
+                       "attention": ("b200vt tcgen05 kernels" if ours else (
+                           "F.scaled_dot_product_attention (diffusers CogVideoXAttnProcessor2_0)" if args.model == "cogvideox"
+                           else "flash_attn_varlen_func (FA2, the reference's mode=\"flash\")"))},
             "attention_algorithmic_tflop_per_it": round(attn_flops / 1e12, 1),
             "attention_executed_tflop_per_it": round(attn_exec / 1e12, 1),
             "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1),

@@ -19,6 +19,7 @@ reference forward                                                          repla
   lvdm TemporalTransformer.forward      lvdm/modules/attention.py:475-519       lvdm_temporal_transformer_forward
   lvdm ResBlock._forward                lvdm/modules/networks/openaimodel3d.py:229-255   lvdm_resblock_forward
   diffusers CogVideoXAttnProcessor2_0   [ext, diffusers 0.32.2]                 CogVideoXAttnProcessor
+  diffusers CogVideoXBlock.forward      [ext, diffusers 0.32.2]                 cogvideox_block_forward
   diffusers HunyuanVideoAttnProcessor2_0 [ext, diffusers 0.32.2]                HunyuanVideoAttnProcessor
 """
 from __future__ import annotations
@@ -421,6 +422,38 @@ class CogVideoXAttnProcessor:
         out = Fn.attention_blhd(q, k, v.view(B, S, H, D)).reshape(B, S, H * D)
         out = attn.to_out[1](attn.to_out[0](out))
         return out[:, text_len:], out[:, :text_len]
+
+
+def _cog_norm_zero(norm, hidden: Tensor, encoder: Tensor, temb: Tensor):
+    """diffusers `CogVideoXLayerNormZero.forward`: six modulation vectors from Linear(SiLU(temb)); both streams go through
+    the same affine LayerNorm and their own (1 + scale) / shift; returns the two gates as (B, C)."""
+    shift, scale, gate, e_shift, e_scale, e_gate = norm.linear(norm.silu(temb)).chunk(6, dim=1)
+    ln = norm.norm
+    w, b = getattr(ln, "weight", None), getattr(ln, "bias", None)
+    return (Fn.ln_modulate(hidden, shift, scale, w, b, ln.eps), Fn.ln_modulate(encoder, e_shift, e_scale, w, b, ln.eps),
+            gate, e_gate)
+
+
+def cogvideox_block_forward(self, hidden_states: Tensor, encoder_hidden_states: Tensor, temb: Tensor,
+                            image_rotary_emb=None, attention_kwargs=None) -> Tuple[Tensor, Tensor]:
+    """Drop-in body of diffusers 0.32.2 `CogVideoXBlock.forward` (the denoiser block behind the reference's
+    cogvideo_hf/cogvideo_pl.py:862-868; parity unpinned): norm1 (LayerNormZero) -> attn1 (the module's own
+    `Attention`, i.e. whatever processor is installed — `CogVideoXAttnProcessor` after set_diffusers_processors) -> gated
+    residuals -> norm2 -> feed-forward over [text; video] -> gated residuals. The four LayerNorm + modulate passes and the
+    four gate-multiply-add passes run in the fused row kernels."""
+    _require(hidden_states.is_cuda and hidden_states.dtype == _BF16 and encoder_hidden_states.dtype == _BF16,
+             "bf16 CUDA activations only")
+    _require(not attention_kwargs, "attention_kwargs stay on the stock block")
+    T = encoder_hidden_states.size(1)
+    hn, en, gate, e_gate = _cog_norm_zero(self.norm1, hidden_states, encoder_hidden_states, temb)
+    ah, ae = self.attn1(hidden_states=hn, encoder_hidden_states=en, image_rotary_emb=image_rotary_emb)
+    hidden_states = Fn.gate_residual(hidden_states, ah, gate)
+    encoder_hidden_states = Fn.gate_residual(encoder_hidden_states, ae, e_gate)
+    hn, en, gate, e_gate = _cog_norm_zero(self.norm2, hidden_states, encoder_hidden_states, temb)
+    ff = self.ff(torch.cat([en, hn], dim=1))
+    hidden_states = Fn.gate_residual(hidden_states, ff[:, T:], gate)
+    encoder_hidden_states = Fn.gate_residual(encoder_hidden_states, ff[:, :T], e_gate)
+    return hidden_states, encoder_hidden_states
 
 
 class HunyuanVideoAttnProcessor:

@@ -169,6 +169,29 @@ def set_diffusers_processors(transformer: torch.nn.Module) -> int:
     return n
 
 
+def set_diffusers_blocks(transformer: torch.nn.Module) -> int:
+    """Bind `blocks.cogvideox_block_forward` on every `CogVideoXBlock` of a diffusers CogVideoXTransformer3DModel
+    (instance-level, like the reference's own `self.forward = self.efficient_forward` swap, lvdm attention.py:98-99);
+    `Unsupported` inputs go to the block's stock forward. Call set_diffusers_processors() as well for the attention."""
+    import types
+    n = 0
+    for m in transformer.modules():
+        if type(m).__name__ != "CogVideoXBlock" or getattr(m, "_b200vt_stock_forward", None) is not None:
+            continue
+        stock = m.forward
+
+        def forward(self, *args, _stock=stock, **kwargs):
+            try:
+                return Bk.cogvideox_block_forward(self, *args, **kwargs)
+            except Fn.Unsupported:
+                return _stock(*args, **kwargs)
+
+        m._b200vt_stock_forward = stock
+        m.forward = types.MethodType(forward, m)
+        n += 1
+    return n
+
+
 class _FallbackProcessor:
     """Try the CUDA processor; `Unsupported` (masks, fp32, CPU, ...) goes to the stock processor it replaced."""
 

@@ -77,12 +77,7 @@ enum : uint32_t {
 // Q and dO tiles arrive by TMA. A cp.async (LSU) producer was tried to leave the per-SM TMA engine to the dQ reduction
 // and measured 40 % slower on K1 (659 vs 1076 TFLOP/s): LSU writes into shared memory starve behind the UMMA operand
 // fetch, which saturates the 128 B/clk shared-memory port, whereas TMA writes do not (history: commit 782d835).
-// MC: launched as clusters of two CTAs (adjacent key tiles of one head). Both walk the same Q / dO tiles, so each CTA
-// fetches only HALF of every tile (one 64-column box) and TMA-multicasts it into both CTAs' shared memory: the per-SM TMA
-// engine, which is what bounds this kernel at D = 128 (64 KB of fp32 dQ reduce-adds + 64 KB of Q / dO loads per iteration),
-// carries 32 KB of loads instead of 64. A ring slot is refilled only when BOTH CTAs have released it: the issuers'
-// tcgen05.commit on q_empty / do_empty is multicast to both CTAs' barriers (count 2).
-template <int D, bool MC>
+template <int D>
 __global__ void __launch_bounds__(BwdCfg<D>::THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
@@ -130,16 +125,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     return;
   }
 
-  // multicast pair: only when the neighbouring key tile of the cluster also runs the main loop (it exits early when it
-  // lies past the sequence or holds only padding keys); both CTAs evaluate the same two conditions
-  bool mc = false;
-  if (MC) {
-    const int kvp = (blockIdx.x ^ 1) * 128;
-    mc = kvp < k_rows_total && min(k_len - kvp, 128) > 0;
-  }
-  const uint32_t cta_rank = blockIdx.x & 1;
-  (void)cta_rank;
-
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::OFF_BAR);
   uint64_t* kv_full = bars;
   uint64_t* q_full = kv_full + 1;
@@ -170,12 +155,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
     mbar_init(kv_full, 1);
     for (int i = 0; i < C::QS; ++i) {
       mbar_init(q_full + i, 1);
-      mbar_init(q_empty + i, mc ? 2 : 1);
+      mbar_init(q_empty + i, 1);
       mbar_init(stat_full + i, 32);
     }
     for (int i = 0; i < C::DOS; ++i) {
       mbar_init(do_full + i, 1);
-      mbar_init(do_empty + i, mc ? 2 : 1);
+      mbar_init(do_empty + i, 1);
     }
     mbar_init(s_full, 1);
     mbar_init(p_ready, 256);
@@ -195,7 +180,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (MC && mc) cluster_sync_all();  // the peer's barriers are initialised before anything of ours can reach them
   const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform: stays in a uniform register
 
   if (warp >= PROD_WARP) {
@@ -218,15 +202,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
         if (lane == 0) {
           trace_mark(p.trace, 3, i, 0);
           mbar_arrive_expect_tx(q_full + s, C::TILE);
-          if (MC && mc) {
-            static_assert(!MC || C::KCH == 2, "the multicast split is one 64-column box per CTA");
-            tma_load_4d_mc(smem + C::OFF_Q + s * C::TILE + cta_rank * C::CHUNK, &tm_q, q_full + s, cta_rank * 64,
-                           q_base + i * 128, h, bq, 0x3);
-          } else {
 #pragma unroll
-            for (int c = 0; c < C::KCH; ++c)
-              tma_load_4d(smem + C::OFF_Q + s * C::TILE + c * C::CHUNK, &tm_q, q_full + s, c * 64, q_base + i * 128, h, bq);
-          }
+          for (int c = 0; c < C::KCH; ++c)
+            tma_load_4d(smem + C::OFF_Q + s * C::TILE + c * C::CHUNK, &tm_q, q_full + s, c * 64, q_base + i * 128, h, bq);
         }
         // -lse * log2(e) and -delta for the 128 rows of this Q tile (negated so that the compute warps use them as
         // FFMA2 / FADD2 addends); rows past q_len get -inf so that P == 0 there.
@@ -248,14 +226,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           mbar_wait(do_empty + ds, ((i / C::DOS) & 1) ^ 1, BT_DO_EMPTY);
           trace_mark(p.trace, 3, i, 1);
           mbar_arrive_expect_tx(do_full + ds, C::TILE);
-          if (MC && mc) {
-            tma_load_4d_mc(smem + C::OFF_DO + ds * C::TILE + cta_rank * C::CHUNK, &tm_do, do_full + ds, cta_rank * 64,
-                           q_base + i * 128, h, bq, 0x3);
-          } else {
 #pragma unroll
-            for (int c = 0; c < C::KCH; ++c)
-              tma_load_4d(smem + C::OFF_DO + ds * C::TILE + c * C::CHUNK, &tm_do, do_full + ds, c * 64, q_base + i * 128, h, bq);
-          }
+          for (int c = 0; c < C::KCH; ++c)
+            tma_load_4d(smem + C::OFF_DO + ds * C::TILE + c * C::CHUNK, &tm_do, do_full + ds, c * 64, q_base + i * 128, h, bq);
         }
         __syncwarp();
       }
@@ -291,12 +264,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
                     umma_desc_sw128_a16(b_base + c * CH16 + kk * 2, 16, 1024), IDESC_ST, (c | kk) != 0);
       };
 
-      // ring-slot release: to this CTA's barrier, or to both CTAs' barriers of a multicast pair
-      auto release = [&](uint64_t* bar) {
-        if (MC && mc) tc_commit_mc(bar, 0x3);
-        else tc_commit(bar);
-      };
-
       mbar_wait(kv_full, 0, BT_KV_FULL);
       if (!C::TWO_ISSUERS) {
         // ---- one issuer (head dim 128: the kernel is bound by the dQ reduction, a second polling thread only costs power) ----
@@ -322,7 +289,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             for (int kk = 0; kk < 8; ++kk)
               umma_ts(tmem + C::T_DV, tmem + C::T_P + kk * 8,
                       umma_desc_sw128_a16(do_s + ds * TILE16 + kk * 128, C::CHUNK, 1024), IDESC_KD, (i > 0) || kk != 0);
-            release(do_empty + ds);
+            tc_commit(do_empty + ds);
             // ---- S^T for the next Q tile ----
             if (has_next) {
               const int sn = (i + 1) % C::QS;
@@ -349,7 +316,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
             for (int kk = 0; kk < 8; ++kk)  // k = 16 query rows per step; dS^T tile is [key][q] in two 64-q boxes
               umma_ss(tmem + C::T_DK, umma_desc_sw128_a16(ds_s + (kk >> 2) * CH16 + (kk & 3) * 2, 16, 1024),
                       umma_desc_sw128_a16(q_s + s * TILE16 + kk * 128, C::CHUNK, 1024), IDESC_KD, (i > 0) || kk != 0);
-            release(q_empty + s);
+            tc_commit(q_empty + s);
             tc_commit(ds_free);
             // ---- dP^T for the next Q tile ----
             if (has_next) {
@@ -391,7 +358,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           for (int kk = 0; kk < 8; ++kk)
             umma_ts(tmem + C::T_DV, tmem + C::T_P + kk * 8,
                     umma_desc_sw128_a16(do_s + ds * TILE16 + kk * 128, C::CHUNK, 1024), IDESC_KD, (i > 0) || kk != 0);
-          release(do_empty + ds);  // dP^T(i) was issued by this thread before dV(i): one commit covers both readers
+          tc_commit(do_empty + ds);  // dP^T(i) was issued by this thread before dV(i): one commit covers both readers
           if (has_next) {
             // ---- S^T(i+1) = K Q_{i+1}^T ----
             const int sn = (i + 1) % C::QS, dn = (i + 1) % C::DOS;
@@ -428,7 +395,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           for (int kk = 0; kk < 8; ++kk)  // k = 16 query rows per step; dS^T tile is [key][q] in two 64-q boxes
             umma_ss(tmem + C::T_DK, umma_desc_sw128_a16(ds_s + (kk >> 2) * CH16 + (kk & 3) * 2, 16, 1024),
                     umma_desc_sw128_a16(q_s + s * TILE16 + kk * 128, C::CHUNK, 1024), IDESC_KD, (i > 0) || kk != 0);
-          release(q_empty + s);
+          tc_commit(q_empty + s);
           tc_commit(ds_free);
           trace_mark(p.trace, 1, i, 2);
         }
@@ -636,7 +603,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
-  if (MC && mc) cluster_sync_all();  // the peer's last releases arrive on this CTA's barriers: stay until it is done too
 }
 
 // delta[b,h,row] = sum_d dO[row,d] * O[row,d]   (one warp per (row, head); 4 B/elem of traffic)
@@ -687,37 +653,20 @@ __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_b
   *reinterpret_cast<uint4*>(dq + b * sb + static_cast<int64_t>(l) * sl + h * sh + d) = w;
 }
 
-template <int D, bool MC>
+template <int D>
 cudaError_t launch_bwd_one(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
                            const CUtensorMap& tm_do, const CUtensorMap& tm_dq, float* dq_acc, int Lq_total,
                            const AttnBwdParams& p, cudaStream_t stream) {
   using C = BwdCfg<D>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<D, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  const unsigned tiles = (p.seq.Lk + 127) / 128;
-  if constexpr (!MC) {
-    dim3 grid(tiles, p.seq.H, p.seq.nprob);
-    attn_bwd_kernel<D, false><<<grid, C::THREADS, C::BYTES, stream>>>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p);
-    return cudaGetLastError();
-  } else {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((tiles + 1) & ~1u, p.seq.H, p.seq.nprob);  // an odd tail tile gets a partner that exits at once
-  cfg.blockDim = dim3(C::THREADS);
-  cfg.dynamicSmemBytes = C::BYTES;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, attn_bwd_kernel<D, true>, tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p);
-  }
+  dim3 grid((p.seq.Lk + 127) / 128, p.seq.H, p.seq.nprob);
+  attn_bwd_kernel<D><<<grid, C::THREADS, C::BYTES, stream>>>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p);
+  return cudaGetLastError();
 }
 
 }  // namespace
@@ -725,11 +674,8 @@ cudaError_t launch_bwd_one(const CUtensorMap& tm_q, const CUtensorMap& tm_k, con
 cudaError_t launch_attn_bwd(int D, const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
                             const CUtensorMap& tm_do, const CUtensorMap& tm_dq, float* dq_acc, int Lq_total,
                             const AttnBwdParams& p, cudaStream_t stream) {
-  // VT_BWD_MC=1: head dim 128 as multicast pairs (A/B switch; see the kernel's comment)
-  static const bool mc = getenv("VT_BWD_MC") != nullptr && atoi(getenv("VT_BWD_MC")) != 0;
-  if (D == 128 && mc) return launch_bwd_one<128, true>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream);
-  if (D == 128) return launch_bwd_one<128, false>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream);
-  if (D == 64) return launch_bwd_one<64, false>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream);
+  if (D == 128) return launch_bwd_one<128>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream);
+  if (D == 64) return launch_bwd_one<64>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream);
   return cudaErrorInvalidValue;
 }
 

@@ -122,15 +122,6 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* t
       "r"(c2), "r"(c3)
       : "memory");
 }
-// The same load delivered to the same shared-memory offset (and mbarrier offset) of every CTA in `cta_mask` of the cluster.
-__device__ __forceinline__ void tma_load_4d_mc(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2,
-                                               int c3, uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5, "
-      "%6}], [%2], %7;" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
-      : "memory");
-}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, const void* smem_src, int c0, int c1, int c2,
                                              int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
@@ -177,17 +168,6 @@ __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sy
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
-}
-
-// The arrival is delivered to the mbarrier at the same offset in every CTA of `cta_mask`.
-__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(cta_mask)
-               : "memory");
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ---- UMMA descriptors ------------------------------------------------------------------------------

@@ -174,3 +174,53 @@ def test_groupnorm_golden():
     assert R.max_rel_err(y.cpu(), g["out_silu"]) < 1e-4
     y = Fn.groupnorm_silu(g["x"].cuda(), g["weight"].cuda(), g["bias"].cuda(), 32, g["eps"], False)
     assert R.max_rel_err(y.float().cpu(), g["out"]) < TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# full BASELINE sizes, where the CPU oracle is too slow: the same arithmetic written with torch fp32 ops on the GPU
+# ---------------------------------------------------------------------------------------------------------------------
+def test_ln_modulate_full_k1_size_matches_torch_fp32():
+    """HunyuanVideo K1 activation (119 056 rows x 3072: the two-rows-per-iteration grid stride at full size): forward and input gradient against torch.layer_norm in fp32 on the GPU."""
+    import torch.nn.functional as F
+
+    import b200vt.functional as Fn
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B, L, C = 1, 119056, 3072
+    x = (torch.randn(B, L, C, device="cuda", generator=g) * 1.7 + 0.2).to(torch.bfloat16).requires_grad_(True)
+    sc = torch.randn(B, C, device="cuda", generator=g) * 0.3
+    sh = torch.randn(B, C, device="cuda", generator=g) * 0.3
+    dy = torch.randn(B, L, C, device="cuda", generator=g).to(torch.bfloat16)
+    y = Fn.ln_modulate(x, sh, sc, eps=1e-6)
+    (gx,) = torch.autograd.grad(y, x, dy)
+    xr = x.detach().float().requires_grad_(True)
+    yr = F.layer_norm(xr, (C,), eps=1e-6) * (1 + sc[:, None]) + sh[:, None]
+    (gr,) = torch.autograd.grad(yr, xr, dy.float())
+    assert float((y.float() - yr).abs().max() / yr.abs().max()) < TOL
+    assert float(torch.nn.functional.cosine_similarity(gx.float().flatten(), gr.flatten(), dim=0)) > COS
+    # every row was written (a skipped row would keep the allocator's stale bytes): per-row error, not only the global max
+    row_err = (y.float() - yr).abs().amax(dim=-1) / yr.abs().amax(dim=-1)
+    assert float(row_err.max()) < 4 * TOL
+
+
+@pytest.mark.parametrize("shape", [(32, 320, 40, 64), (32, 960, 40, 64), (2, 320, 16, 40, 64), (2, 1280, 16, 10, 16)])
+def test_groupnorm_silu_full_vc2_sizes_match_torch_fp32(shape):
+    """VideoCrafter2 ResBlock / SpatialTransformer (4-D) and TemporalTransformer (5-D) GroupNorm inputs at batch 2: the
+    bulk-copy kernels with 1-, 4- and 16-CTA clusters, forward + backward, against torch.group_norm + SiLU in fp32."""
+    import torch.nn.functional as F
+
+    import b200vt.functional as Fn
+    g = torch.Generator(device="cuda").manual_seed(6)
+    C = shape[1]
+    x = (torch.randn(*shape, device="cuda", generator=g) * 2.0 + 0.5).to(torch.bfloat16).requires_grad_(True)
+    w = (1 + 0.2 * torch.randn(C, device="cuda", generator=g)).requires_grad_(True)
+    b = (0.2 * torch.randn(C, device="cuda", generator=g)).requires_grad_(True)
+    dy = torch.randn(*shape, device="cuda", generator=g).to(torch.bfloat16)
+    y = Fn.groupnorm_silu(x, w, b, 32, 1e-5, silu=True)
+    gx, gw, gb = torch.autograd.grad(y, (x, w, b), dy)
+    xr = x.detach().float().requires_grad_(True)
+    wr, br = w.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    yr = F.silu(F.group_norm(xr, 32, wr, br, 1e-5))
+    gxr, gwr, gbr = torch.autograd.grad(yr, (xr, wr, br), dy.float())
+    assert float((y.float() - yr).abs().max() / yr.abs().max()) < TOL
+    assert float(F.cosine_similarity(gx.float().flatten(), gxr.flatten(), dim=0)) > COS
+    assert float((gw - gwr).abs().max() / gwr.abs().max()) < TOL and float((gb - gbr).abs().max() / gbr.abs().max()) < TOL

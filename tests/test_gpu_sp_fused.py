@@ -71,3 +71,68 @@ def test_ulysses_two_gpus_matches_single_gpu(fused, T):
         e = result[rank]
         assert e["out"] <= 2e-2, (rank, e)
         assert e["dq"] <= 2e-2 and e["dk"] <= 2e-2 and e["dv"] <= 2e-2, (rank, e)
+
+
+def _wan_worker(rank, world, port, result):
+    """Wan self-attention, sequence parallel (patch.wan_usp_attn_forward bound like wan/text2video.py:261-271 binds
+    usp_attn_forward) against the unsharded drop-in on the same weights: output slice, input gradient slice and the
+    rank-summed weight gradients."""
+    import types
+
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import b200vt.patch as P
+        from helpers import WanAttnShell
+        from oracle import ref_ops as R
+        dim, heads, grid = 1024, 8, (4, 8, 16)  # head dim 128; 512 tokens, 256 per rank
+        L = grid[0] * grid[1] * grid[2]
+        torch.manual_seed(7)
+        attn = WanAttnShell(dim, heads, cross=False)
+        with torch.no_grad():
+            for n_, p_ in attn.named_parameters():
+                p_.copy_(torch.randn_like(p_) * (0.03 if p_.dim() == 2 else 0.1) + (1.0 if "norm" in n_ else 0.0))
+        attn = attn.to("cuda", torch.bfloat16)
+        g = torch.Generator(device="cuda").manual_seed(99)
+        x = torch.randn(1, L, dim, device="cuda", dtype=torch.bfloat16, generator=g)
+        d_out = torch.randn(1, L, dim, device="cuda", dtype=torch.bfloat16, generator=g)
+        freqs = R.wan_freqs_table(dim // heads).cuda()
+        grid_sizes = torch.tensor([list(grid)])
+        seq_lens = torch.tensor([L], device="cuda")
+        xr = x.clone().requires_grad_(True)
+        ref = attn(xr, seq_lens, grid_sizes, freqs)  # single-GPU drop-in (blocks.wan_self_attention_forward)
+        ref.backward(d_out)
+        ref_wgrad = {n_: p_.grad.float().clone() for n_, p_ in attn.named_parameters()}
+        for p_ in attn.parameters():
+            p_.grad = None
+        S = L // world
+        sl = slice(rank * S, (rank + 1) * S)
+        xs = x[:, sl].clone().requires_grad_(True)
+        sp_forward = types.MethodType(P.wan_usp_attn_forward, attn)
+        out = sp_forward(xs, seq_lens, grid_sizes, freqs)
+        out.backward(d_out[:, sl])
+        errs = {"out": float((out.float() - ref[:, sl].float()).abs().max() / ref.float().abs().max()),
+                "dx": float((xs.grad.float() - xr.grad[:, sl].float()).abs().max() / xr.grad.float().abs().max())}
+        worst = 0.0
+        for n_, p_ in attn.named_parameters():
+            gsum = p_.grad.float().clone()
+            dist.all_reduce(gsum)
+            worst = max(worst, float((gsum - ref_wgrad[n_]).abs().max() / ref_wgrad[n_].abs().max().clamp_min(1e-20)))
+        errs["dw"] = worst
+        result[rank] = errs
+    finally:
+        dist.destroy_process_group()
+
+
+def test_wan_usp_attention_two_gpus_matches_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    result = mgr.dict()
+    mp.spawn(_wan_worker, args=(2, 29611, result), nprocs=2, join=True)
+    for rank in (0, 1):
+        e = result[rank]
+        assert e["out"] <= 2e-2 and e["dx"] <= 2e-2 and e["dw"] <= 3e-2, (rank, e)

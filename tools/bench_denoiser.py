@@ -405,18 +405,28 @@ def main():
                 p.grad = None
             return h.detach(), leaf.grad
     else:
-        assert world == 1, "wan sequence parallel goes through patch.wan_usp_attn_forward; bench it at 1 GPU here"
         nl = cfg["layers"] if args.layers is None else args.layers
         blocks = build_wan(cfg, nl, dev)
         C, heads = cfg["dim"], cfg["heads"]
-        g = torch.Generator(device=dev).manual_seed(SEED)
-        x0 = torch.randn(1, n_img, C, device=dev, dtype=torch.float32, generator=g)
-        e0 = torch.randn(1, 6, C, device=dev, dtype=torch.float32, generator=g) * 0.1
-        ctx = torch.randn(1, n_txt, C, device=dev, dtype=BF16, generator=g)
-        d_out = torch.randn(1, n_img, C, device=dev, dtype=torch.float32, generator=g) * 1e-2
+        assert heads % world == 0
+        g = torch.Generator(device=dev).manual_seed(SEED + rank)
+        x0 = torch.randn(1, n_loc, C, device=dev, dtype=torch.float32, generator=g)
+        d_out = torch.randn(1, n_loc, C, device=dev, dtype=torch.float32, generator=g) * 1e-2
+        g0 = torch.Generator(device=dev).manual_seed(SEED)
+        e0 = torch.randn(1, 6, C, device=dev, dtype=torch.float32, generator=g0) * 0.1
+        ctx = torch.randn(1, n_txt, C, device=dev, dtype=BF16, generator=g0)
         seq_lens = torch.tensor([n_img], dtype=torch.long, device=dev)
         grid_sizes = torch.tensor([[f, h, w]], dtype=torch.long)
         freqs = wan_freqs_table(C // heads, dev)
+        if world > 1:
+            # sequence parallel as the reference wires it (wan/text2video.py:261-271): every block's self-attention forward is
+            # rebound to the Ulysses version; tokens are sharded, the text context is replicated, and the weight gradients of
+            # the replicated parameters are summed over the ranks after the backward (one all-reduce per parameter)
+            import types
+
+            import b200vt.patch as P
+            for b in blocks:
+                b.self_attn._fwd = lambda self_, *a, **k: P.wan_usp_attn_forward(self_, *a, **k)
         params = [p for b in blocks for p in b.parameters()]
         n_params = sum(p.numel() for p in params)
         layers_desc = {"layers": nl}
@@ -430,6 +440,9 @@ def main():
                     fn = b if ours else (lambda *a, _b=b: wan_block_torch(_b, *a))
                     x = run_block(fn, x, e0, seq_lens, grid_sizes, freqs, ctx, None)
             x.backward(d_out)
+            if world > 1:
+                for p in params:
+                    dist.all_reduce(p.grad)
             for p in params:
                 p.grad = None
             return x.detach(), leaf.grad

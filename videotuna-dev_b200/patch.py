@@ -274,23 +274,41 @@ def wan_sp_rope_tables(grid_size, freqs: torch.Tensor, s_local: int, group=None)
             fr.imag.float().repeat_interleave(2, dim=1).contiguous())
 
 
+_WAN_SP_ROPE_CACHE: dict = {}
+
+
+def _wan_sp_rope_cached(grid, freqs: torch.Tensor, s_local: int, group, device):
+    key = (tuple(int(v) for v in grid), freqs.data_ptr(), s_local, id(group), sp._rank(group), str(device))
+    hit = _WAN_SP_ROPE_CACHE.get(key)
+    if hit is None:
+        cos, sin = wan_sp_rope_tables(grid, freqs, s_local, group)
+        hit = (cos.to(device), sin.to(device))
+        if len(_WAN_SP_ROPE_CACHE) > 16:
+            _WAN_SP_ROPE_CACHE.clear()
+        _WAN_SP_ROPE_CACHE[key] = hit
+    return hit
+
+
 def wan_usp_attn_forward(self, x, seq_lens, grid_sizes, freqs, dtype=torch.bfloat16, group=None):
     """Replacement for usp_attn_forward (xdit_context_parallel.py:149-192), bound with types.MethodType onto
-    WanSelfAttention like the reference does (wan/text2video.py:261-271): q/k/v projections and the full-dim RMSNorm
-    stay the module's own layers; RoPE on this rank's token slice is fused with the bf16 cast; attention is Ulysses."""
+    WanSelfAttention like the reference does (wan/text2video.py:261-271): the q/k/v/o projections stay the module's own
+    layers; the full-dim RMSNorm and the RoPE of this rank's token slice run as one bf16 pass per tensor (the same fused
+    kernel as the single-GPU block, with the per-rank table slice); attention is Ulysses."""
     b, s, n, d = *x.shape[:2], self.num_heads, self.head_dim
-    q = self.norm_q(self.q(x)).view(b, s, n, d)
-    k = self.norm_k(self.k(x)).view(b, s, n, d)
-    v = self.v(x).view(b, s, n, d)
     if not (x.is_cuda and b == 1):
         raise Fn.Unsupported("sequence-parallel Wan attention needs CUDA tensors and batch 1 (as the reference pipeline)")
-    cos, sin = wan_sp_rope_tables(grid_sizes[0].tolist(), freqs, s, group)
-    cos, sin = cos.to(x.device), sin.to(x.device)
+    grid = grid_sizes[0].tolist() if isinstance(grid_sizes, torch.Tensor) else list(grid_sizes[0])
+    cos, sin = _wan_sp_rope_cached(grid, freqs, s, group, x.device)
 
-    def half(t):
-        return t if t.dtype == torch.bfloat16 else t.to(dtype)
+    def proj(lin):
+        t = lin(x)
+        return (t if t.dtype == torch.bfloat16 else t.to(dtype)).view(b, s, n, d)
 
-    q = Fn.qk_rmsnorm_rope(half(q), None, cos, sin)
-    k = Fn.qk_rmsnorm_rope(half(k), None, cos, sin)
-    out = sp.UlyssesAttention(group)(None, q, k, half(v), window_size=self.window_size)
+    def norm_rope(t, norm):
+        w, eps = Bk._rms_weight(norm)
+        return Fn.qk_rmsnorm_rope(t, w, cos, sin, per_head=False, eps=eps if w is not None else 1e-6)
+
+    q = norm_rope(proj(self.q), self.norm_q)
+    k = norm_rope(proj(self.k), self.norm_k)
+    out = sp.UlyssesAttention(group)(None, q, k, proj(self.v), window_size=self.window_size)
     return self.o(out.flatten(2).to(x.dtype))

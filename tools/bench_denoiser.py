@@ -440,12 +440,21 @@ def main():
                     fn = b if ours else (lambda *a, _b=b: wan_block_torch(_b, *a))
                     x = run_block(fn, x, e0, seq_lens, grid_sizes, freqs, ctx, None)
             x.backward(d_out)
-            if world > 1:
-                for p in params:
-                    dist.all_reduce(p.grad)
+            for hnd in pending:
+                hnd.wait()
+            pending.clear()
             for p in params:
                 p.grad = None
             return x.detach(), leaf.grad
+
+        pending = []
+        if world > 1:
+            # DDP-style: a parameter's gradient is all-reduced as soon as it has been accumulated, so the NCCL reductions of
+            # block b overlap the backward of blocks b-1, b-2, ... (per-block checkpointing produces them block by block)
+            def _reduce_when_ready(prm):
+                pending.append(dist.all_reduce(prm.grad, async_op=True))
+            for p in params:
+                p.register_post_accumulate_grad_hook(_reduce_when_ready)
 
     if args.check:
         (y_a, g_a), (y_b, g_b) = iteration(True), iteration(False)

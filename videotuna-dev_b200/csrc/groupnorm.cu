@@ -612,12 +612,15 @@ BulkPlan plan_bulk(int N, int C, int S, int G, int streams, const void* p0, cons
   BulkPlan plan;
   constexpr int VEC = Io<T>::VEC;
   const long long count = static_cast<long long>(C / G) * S;
-  if (getenv("VT_GN_TWOPASS") != nullptr) return plan;
+  static const bool two_pass = getenv("VT_GN_TWOPASS") != nullptr;
+  if (two_pass) return plan;
   if (S % VEC != 0 || !aligned16(p0) || !aligned16(p1) || (p2 != nullptr && !aligned16(p2))) return plan;
   if (N > 65535 || G > 65535) return plan;
   const long long vectors = count / VEC;
   const size_t extra = (2 + (streams == 2 ? 2 * (GB_THREADS / 32) : 0)) * static_cast<size_t>(C / G) * sizeof(float);
-  const size_t soft = 54 * 1024, hard = 110 * 1024;
+  // soft: four CTAs per SM by shared memory (eight with VT_GN_SOFT_KB=27: an A/B knob); hard: two
+  static const size_t soft_kb = getenv("VT_GN_SOFT_KB") != nullptr ? static_cast<size_t>(atoi(getenv("VT_GN_SOFT_KB"))) : 54;
+  const size_t soft = soft_kb * 1024, hard = 110 * 1024;
   for (int cl = 1; cl <= 16; cl *= 2) {
     const long long chunk = (vectors + cl - 1) / cl * VEC;
     const size_t bytes = static_cast<size_t>(chunk) * sizeof(T) * streams + extra;

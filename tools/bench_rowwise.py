@@ -79,7 +79,15 @@ def main():
         rf_ms = timeit(lambda: x + br * gate[:, None].to(br.dtype if xdt == torch.bfloat16 else torch.float32), args.iters)
         n = B * L * C
         report(f"gate_residual_fwd[{tag}]", (B, L, C), n * (2 * x.element_size() + 2), f_ms, rf_ms)
-        del x, br
+        xg, bg, gg = x.detach().requires_grad_(True), br.detach().requires_grad_(True), gate.detach().requires_grad_(True)
+        yg = Fn.gate_residual(xg, bg, gg)
+        dyg = rn(B, L, C, dtype=xdt)
+        b_ms = timeit(lambda: torch.autograd.grad(yg, (xg, bg, gg), dyg, retain_graph=True), args.iters)
+        yr_ = xg + bg * gg[:, None].to(bg.dtype if xdt == torch.bfloat16 else torch.float32)
+        rb_ms = timeit(lambda: torch.autograd.grad(yr_, (xg, bg, gg), dyg, retain_graph=True), args.iters)
+        # dy read, branch read (for dgate), dbranch write; dx = dy is returned without a copy
+        report(f"gate_residual_bwd[{tag}]", (B, L, C), n * (x.element_size() + 2 + 2), b_ms, rb_ms)
+        del x, br, xg, bg, yg, dyg, yr_
 
     # ---- fused QK-RMSNorm + RoPE on the strided q view of a fused QKV projection (Hunyuan K1) -------------------------
     B, L, H, D = 1, 118800, 24, 128
@@ -101,7 +109,24 @@ def main():
     n = B * L * H * D
     report("qk_rmsnorm_rope_fwd[hunyuan_k1, strided q of fused qkv]", (B, L, H, D), n * 4 + 2 * L * D * 4, f_ms, rf_ms,
            note="reference = hunyuan RMSNorm (fp32 temporaries) + apply_rotary_emb (rotate_half stack/flatten) as torch ops")
-    del qkv, q
+    qg = qkv[:, :, 0].detach().requires_grad_(True)   # strided leaf: the backward reads x in place, like the block does
+    yq = Fn.qk_rmsnorm_rope(qg, w, cos, sin)
+    dyq = rn(B, L, H, D)
+    b_ms = timeit(lambda: torch.autograd.grad(yq, qg, dyq, retain_graph=True), args.iters)
+    qr = qkv[:, :, 0].detach().requires_grad_(True)
+
+    def ref_rope_g():
+        xf = qr.float()
+        n_ = (xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6)).to(qr.dtype) * w.to(qr.dtype)
+        nf = n_.float()
+        xr, xi = nf.reshape(*nf.shape[:-1], -1, 2).unbind(-1)
+        rot = torch.stack([-xi, xr], dim=-1).flatten(3)
+        return (nf * cos.view(1, L, 1, D) + rot * sin.view(1, L, 1, D)).to(qr.dtype)
+    yr_ = ref_rope_g()
+    rb_ms = timeit(lambda: torch.autograd.grad(yr_, qr, dyq, retain_graph=True), max(3, args.iters // 3))
+    report("qk_rmsnorm_rope_bwd[hunyuan_k1, strided q of fused qkv]", (B, L, H, D), n * 6 + 2 * L * D * 4 + B * L * H * 4,
+           b_ms, rb_ms)
+    del qkv, q, qg, yq, dyq, qr, yr_
 
     # ---- GroupNorm(32) + SiLU (VideoCrafter2 UNet, batch 2 x 16 frames): ResBlock / SpatialTransformer 4-D inputs and the
     # TemporalTransformer's 5-D input (N = 2 samples, slabs of (C/32) * t*h*w elements). These tensors are smaller than the

@@ -15,6 +15,7 @@
 #include <cuda_bf16.h>
 
 #include "capi_util.h"
+#include "sm100_ptx.cuh"
 
 namespace vt {
 namespace {
@@ -465,10 +466,14 @@ int launch_fwd(const XT* x, bf16* y, float* mean, float* rstd, const float* gamm
     configured = true;
   }
   if (one_row) {
-    dim3 grid(ln_grid_x(L, B, 8), B);
+    static const int want1 = getenv("VT_LN1_CTAS") != nullptr ? atoi(getenv("VT_LN1_CTAS")) : 8;
+    dim3 grid(ln_grid_x(L, B, want1), B);
     ln_fwd_kernel<XT, T, VPT><<<grid, T, smem, st>>>(x, y, mean, rstd, gamma, beta, scale, shift, L, C, eps);
   } else {
-    dim3 grid(ln_grid_x((L + 1) / 2, B, 5), B);
+    // CTAs per SM of grid (not of residency): the row -> CTA assignment is static, and many short-lived CTAs let the hardware
+    // scheduler even out SM-to-SM differences (measured at K1: 5 per SM 90 %, 32 per SM 97 % of the copy bandwidth)
+    static const int want = getenv("VT_LN_CTAS") != nullptr ? atoi(getenv("VT_LN_CTAS")) : 32;
+    dim3 grid(ln_grid_x((L + 1) / 2, B, want), B);
     ln_fwd2_kernel<XT, T, VPT><<<grid, T, smem, st>>>(x, y, mean, rstd, gamma, beta, scale, shift, L, C, eps);
   }
   VT_CHECK_CUDA(cudaGetLastError());
@@ -486,7 +491,8 @@ int launch_bwd(const bf16* dy, const XT* x, const float* mean, const float* rstd
     VT_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<XT, T, VPT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid(ln_grid_x(L, B, 4), B);
+  static const int wantb = getenv("VT_LNB_CTAS") != nullptr ? atoi(getenv("VT_LNB_CTAS")) : 4;
+  dim3 grid(ln_grid_x(L, B, wantb), B);
   ln_bwd_kernel<XT, T, VPT, MODE><<<grid, T, smem, st>>>(dy, x, mean, rstd, dx, gamma, beta, scale, dgamma, dbeta, dscale,
                                                         dshift, L, C);
   VT_CHECK_CUDA(cudaGetLastError());
@@ -666,12 +672,335 @@ __global__ void __launch_bounds__(128, (VPT <= 3 ? 5 : 3)) rope_fwd_kernel(const
   }
 }
 
+// Third generation of the same kernel: the token's row (contiguous H * D bf16 = 6 KB at K1) and its cos / sin slices arrive
+// in a shared-memory ring by 1-D BULK ASYNCHRONOUS COPIES (cp.async.bulk + mbarrier complete_tx) issued by one thread
+// STAGES - 1 tokens ahead. ncu on the register-prefetch kernel: 50 % of the stall samples are the first use of the
+// prefetched row (one token of look-ahead, 5 CTAs per SM by its 96 registers: ~30 KB in flight per SM). Here nothing in
+// flight holds a register, the look-ahead is two tokens with eight CTAs per SM, and the thread -> column mapping, the
+// statistics and the rotation are unchanged. Needs heads contiguous inside a token (x_sh == D) and 16-byte aligned rows.
+constexpr int ROPE_STAGES = 4;
+
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int NORM, int VPT, int D>
+__global__ void __launch_bounds__(128) rope_fwd_bulk_kernel(const bf16* __restrict__ x, bf16* __restrict__ y,
+                                                            float* __restrict__ rstd_out, const float* __restrict__ w,
+                                                            const float* __restrict__ cosT, const float* __restrict__ sinT,
+                                                            int64_t x_sb, int64_t x_sl, int64_t y_sb, int64_t y_sl,
+                                                            int64_t y_sh, int L, int H, int L_rope, float eps) {
+  constexpr int T = 128, LPH = D / 8, HPS = 1024 / D, S = ROPE_STAGES;
+  extern __shared__ __align__(128) uint8_t rb_smem[];  // S x { row[C] bf16, cos[D] fp32, sin[D] fp32 }
+  __shared__ __align__(8) uint64_t full[S];
+  __shared__ float red[2 * (T / 32)];
+  const int b = blockIdx.y, t = threadIdx.x;
+  const int d0 = (t % LPH) * 8, hsub = t / LPH;
+  const int C = H * D;
+  const int stage_bytes = C * 2 + 2 * D * 4;
+  float wv[NORM == 2 ? VPT : 1][8];
+#pragma unroll
+  for (int j = 0; j < (NORM == 2 ? VPT : 1); ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) wv[j][i] = 1.f;
+  if (w != nullptr) {
+    if (NORM == 1) lds8(w + d0, wv[0]);
+    if (NORM == 2) {
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) lds8(w + (j * T + t) * 8, wv[NORM == 2 ? j : 0]);
+    }
+  }
+  if (t == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int n_tok = blockIdx.x < static_cast<unsigned>(L) ? (L - 1 - blockIdx.x) / gridDim.x + 1 : 0;  // tokens of this CTA
+  auto issue = [&](int k) {  // thread 0 only: token k of this CTA into stage k % S
+    const int l = blockIdx.x + k * gridDim.x;
+    uint8_t* st = rb_smem + (k % S) * stage_bytes;
+    const bool rot = cosT != nullptr && l < L_rope;
+    mbar_arrive_expect_tx(&full[k % S], C * 2 + (rot ? 2 * D * 4 : 0));
+    bulk_g2s(st, x + b * x_sb + static_cast<int64_t>(l) * x_sl, C * 2, &full[k % S]);
+    if (rot) {
+      bulk_g2s(st + C * 2, cosT + static_cast<size_t>(l) * D, D * 4, &full[k % S]);
+      bulk_g2s(st + C * 2 + D * 4, sinT + static_cast<size_t>(l) * D, D * 4, &full[k % S]);
+    }
+  };
+  if (t == 0)
+    for (int k = 0; k < S - 1 && k < n_tok; ++k) issue(k);
+  for (int k = 0; k < n_tok; ++k) {
+    const int l = blockIdx.x + k * gridDim.x;
+    // every thread has finished reading stage (k - 1) % S (its values are in registers / stored): refill it
+    __syncthreads();
+    if (t == 0 && k + S - 1 < n_tok) issue(k + S - 1);
+    mbar_wait(&full[k % S], (k / S) & 1, 0x7e01);
+    const uint8_t* st = rb_smem + (k % S) * stage_bytes;
+    const bf16* row = reinterpret_cast<const bf16*>(st);
+    const bool rot = cosT != nullptr && l < L_rope;
+    float f[VPT][8], ss[VPT];
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      const uint4 u = *reinterpret_cast<const uint4*>(row + (j * T + t) * 8);
+      unpack(u, f[j]);
+      ss[j] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ss[j] = fmaf(f[j][i], f[j][i], ss[j]);
+    }
+    float cs[8], sn[8];
+    if (rot) {
+      lds8(reinterpret_cast<const float*>(st + C * 2) + d0, cs);
+      lds8(reinterpret_cast<const float*>(st + C * 2 + D * 4) + d0, sn);
+    }
+    float rstd[VPT];
+    if (NORM == 1) {
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+#pragma unroll
+        for (int o = LPH >> 1; o > 0; o >>= 1) ss[j] += __shfl_xor_sync(0xffffffffu, ss[j], o);
+        rstd[j] = rsqrtf(ss[j] / D + eps);
+        if (rstd_out != nullptr && (t % LPH) == 0)
+          rstd_out[(static_cast<size_t>(b) * L + l) * H + j * HPS + hsub] = rstd[j];
+      }
+    } else if (NORM == 2) {
+      float tot[1] = {0.f};
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) tot[0] += ss[j];
+      block_sum<T, 1>(tot, red, k & 1);
+      const float r = rsqrtf(tot[0] / C + eps);
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) rstd[j] = r;
+      if (rstd_out != nullptr && t == 0) rstd_out[static_cast<size_t>(b) * L + l] = r;
+    } else {
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) rstd[j] = 1.f;
+    }
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      float n[8], o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) n[i] = f[j][i] * rstd[j] * wv[NORM == 2 ? j : 0][i];
+      if (rot) {
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          o[i] = n[i] * cs[i] - n[i + 1] * sn[i];
+          o[i + 1] = n[i + 1] * cs[i + 1] + n[i] * sn[i + 1];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = n[i];
+      }
+      stg16(y + b * y_sb + static_cast<int64_t>(l) * y_sl + (j * HPS + hsub) * y_sh + d0, pack(o));
+    }
+  }
+}
+
+template <int NORM, int VPT, int D>
+int launch_rope_bulk(const bf16* x, bf16* y, float* rstd, const float* w, const float* c, const float* s, const int64_t* xs,
+                     const int64_t* ys, int B, int L, int H, int L_rope, float eps, cudaStream_t st) {
+  const int smem = ROPE_STAGES * (H * D * 2 + 2 * D * 4);
+  static bool configured = false;
+  if (!configured) {
+    VT_CHECK_CUDA(cudaFuncSetAttribute(rope_fwd_bulk_kernel<NORM, VPT, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       ROPE_STAGES * (5120 * 2 + 2 * 128 * 4)));
+    configured = true;
+  }
+  // Grid: many more CTAs than are resident (96 per SM, ~8 tokens each at K1). The token -> CTA assignment is static; with
+  // one wave of exactly-resident CTAs the kernel ran at 83 % of the copy bandwidth, with 8 / 24 / 96 per SM at 89 / 96 /
+  // 100 %: short-lived CTAs let the hardware scheduler even out SM-to-SM and DRAM-channel differences.
+  static const int want_f = getenv("VT_ROPE_CTAS_F") != nullptr ? atoi(getenv("VT_ROPE_CTAS_F")) : 96;
+  dim3 grid(ln_grid_x(L, B, want_f), B);
+  rope_fwd_bulk_kernel<NORM, VPT, D><<<grid, 128, smem, st>>>(x, y, rstd, w, c, s, xs[0], xs[1], ys[0], ys[1], ys[2], L, H,
+                                                               L_rope, eps);
+  VT_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int NORM, int VPT, int D>
 int launch_rope(const bf16* x, bf16* y, float* rstd, const float* w, const float* c, const float* s, const int64_t* xs,
                 const int64_t* ys, int B, int L, int H, int L_rope, float eps, cudaStream_t st) {
   dim3 grid(ln_grid_x(L, B, 6), B);
   rope_fwd_kernel<NORM, VPT, D><<<grid, 128, 0, st>>>(x, y, rstd, w, c, s, xs[0], xs[1], xs[2], ys[0], ys[1], ys[2], L, H,
                                                        L_rope, eps);
+  VT_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Backward of the fused RMSNorm + RoPE in the same bulk-copy ring layout (the generic kernel in rowwise.cu is the first
+// layout: one thread per 8 columns, C / 8 threads per CTA): per token the ring stage holds the dy row, the x row (norm
+// modes), the cos / sin slices and, for the per-head norm, the token's H saved rstd values.
+//   g = R^T dy (inverse rotation);  xh = x * rstd;  dx = rstd * (g w - xh * mean(g w xh));  dw += g xh
+template <int NORM, int VPT, int D>
+__global__ void __launch_bounds__(128) rope_bwd_bulk_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                            const float* __restrict__ rstd_in, bf16* __restrict__ dx,
+                                                            float* __restrict__ dw, const float* __restrict__ w,
+                                                            const float* __restrict__ cosT, const float* __restrict__ sinT,
+                                                            int64_t g_sb, int64_t g_sl, int64_t x_sb, int64_t x_sl,
+                                                            int64_t o_sb, int64_t o_sl, int64_t o_sh, int L, int H, int L_rope) {
+  constexpr int T = 128, LPH = D / 8, HPS = 1024 / D, S = ROPE_STAGES;
+  extern __shared__ __align__(128) uint8_t rb_smem[];  // S x { dy[C], x[C] bf16 (norm), cos[D], sin[D], rstd[H] fp32 (NORM 1) }
+  __shared__ __align__(8) uint64_t full[S];
+  __shared__ float red[2 * (T / 32)];
+  __shared__ float sdw[NORM == 1 ? D : 1];
+  const int b = blockIdx.y, t = threadIdx.x;
+  const int d0 = (t % LPH) * 8, hsub = t / LPH;
+  const int C = H * D;
+  const int off_x = C * 2, off_cs = off_x + (NORM != 0 ? C * 2 : 0), off_rs = off_cs + 2 * D * 4;
+  const int stage_bytes = off_rs + (NORM == 1 ? ((H * 4 + 15) & ~15) : 0);
+  float wv[NORM == 2 ? VPT : 1][8], acc[NORM == 2 ? VPT : 1][8];
+#pragma unroll
+  for (int j = 0; j < (NORM == 2 ? VPT : 1); ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      wv[j][i] = 1.f;
+      acc[j][i] = 0.f;
+    }
+  if (w != nullptr) {
+    if (NORM == 1) lds8(w + d0, wv[0]);
+    if (NORM == 2) {
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) lds8(w + (j * T + t) * 8, wv[NORM == 2 ? j : 0]);
+    }
+  }
+  if (t == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  if (NORM == 1)
+    for (int i = t; i < D; i += T) sdw[i] = 0.f;
+  __syncthreads();
+  const int n_tok = blockIdx.x < static_cast<unsigned>(L) ? (L - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  auto issue = [&](int k) {  // thread 0 only
+    const int l = blockIdx.x + k * gridDim.x;
+    uint8_t* st = rb_smem + (k % S) * stage_bytes;
+    const bool rot = cosT != nullptr && l < L_rope;
+    mbar_arrive_expect_tx(&full[k % S], C * 2 + (NORM != 0 ? C * 2 : 0) + (rot ? 2 * D * 4 : 0) + (NORM == 1 ? H * 4 : 0));
+    bulk_g2s(st, dy + b * g_sb + static_cast<int64_t>(l) * g_sl, C * 2, &full[k % S]);
+    if (NORM != 0) bulk_g2s(st + off_x, x + b * x_sb + static_cast<int64_t>(l) * x_sl, C * 2, &full[k % S]);
+    if (rot) {
+      bulk_g2s(st + off_cs, cosT + static_cast<size_t>(l) * D, D * 4, &full[k % S]);
+      bulk_g2s(st + off_cs + D * 4, sinT + static_cast<size_t>(l) * D, D * 4, &full[k % S]);
+    }
+    if (NORM == 1) bulk_g2s(st + off_rs, rstd_in + (static_cast<size_t>(b) * L + l) * H, H * 4, &full[k % S]);
+  };
+  if (t == 0)
+    for (int k = 0; k < S - 1 && k < n_tok; ++k) issue(k);
+  float rs_tok = 0.f;  // NORM 2: one rstd per token, fetched one token ahead
+  if (NORM == 2 && n_tok > 0) rs_tok = rstd_in[static_cast<size_t>(b) * L + blockIdx.x];
+  for (int k = 0; k < n_tok; ++k) {
+    const int l = blockIdx.x + k * gridDim.x;
+    __syncthreads();  // every thread is done with stage (k - 1) % S
+    if (t == 0 && k + S - 1 < n_tok) issue(k + S - 1);
+    float rs_next = 0.f;
+    if (NORM == 2 && k + 1 < n_tok) rs_next = rstd_in[static_cast<size_t>(b) * L + l + gridDim.x];
+    mbar_wait(&full[k % S], (k / S) & 1, 0x7e02);
+    const uint8_t* st = rb_smem + (k % S) * stage_bytes;
+    const bf16* grow = reinterpret_cast<const bf16*>(st);
+    const bf16* xrow = reinterpret_cast<const bf16*>(st + off_x);
+    const float* srs = reinterpret_cast<const float*>(st + off_rs);
+    const bool rot = cosT != nullptr && l < L_rope;
+    float cs[8], sn[8];
+    if (rot) {
+      lds8(reinterpret_cast<const float*>(st + off_cs) + d0, cs);
+      lds8(reinterpret_cast<const float*>(st + off_cs + D * 4) + d0, sn);
+    }
+    float g[VPT][8], xh[NORM == 2 ? VPT : 1][8], dot2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      float fd[8];
+      unpack(*reinterpret_cast<const uint4*>(grow + (j * T + t) * 8), fd);
+      if (rot) {
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          g[j][i] = fd[i] * cs[i] + fd[i + 1] * sn[i + 1];
+          g[j][i + 1] = fd[i + 1] * cs[i + 1] - fd[i] * sn[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[j][i] = fd[i];
+      }
+      bf16* dst = dx + b * o_sb + static_cast<int64_t>(l) * o_sl + (j * HPS + hsub) * o_sh + d0;
+      if (NORM == 0) {
+        stg16(dst, pack(g[j]));
+      } else if (NORM == 1) {
+        // the reduction is over one head = LPH adjacent lanes: finish this vector before the next
+        float fx[8], xv[8], o[8], dot = 0.f;
+        unpack(*reinterpret_cast<const uint4*>(xrow + (j * T + t) * 8), fx);
+        const float rs = srs[j * HPS + hsub];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xv[i] = fx[i] * rs;
+          dot = fmaf(g[j][i] * wv[0][i], xv[i], dot);
+          acc[0][i] = fmaf(g[j][i], xv[i], acc[0][i]);
+        }
+#pragma unroll
+        for (int o2 = LPH >> 1; o2 > 0; o2 >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o2);
+        const float m = dot / D;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = rs * (g[j][i] * wv[0][i] - xv[i] * m);
+        stg16(dst, pack(o));
+      } else {
+        float fx[8];
+        unpack(*reinterpret_cast<const uint4*>(xrow + (j * T + t) * 8), fx);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xh[NORM == 2 ? j : 0][i] = fx[i] * rs_tok;
+          dot2 = fmaf(g[j][i] * wv[NORM == 2 ? j : 0][i], xh[NORM == 2 ? j : 0][i], dot2);
+          acc[NORM == 2 ? j : 0][i] = fmaf(g[j][i], xh[NORM == 2 ? j : 0][i], acc[NORM == 2 ? j : 0][i]);
+        }
+      }
+    }
+    if (NORM == 2) {
+      float tot[1] = {dot2};
+      block_sum<T, 1>(tot, red, k & 1);
+      const float m = tot[0] / C;
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = rs_tok * (g[j][i] * wv[NORM == 2 ? j : 0][i] - xh[NORM == 2 ? j : 0][i] * m);
+        stg16(dx + b * o_sb + static_cast<int64_t>(l) * o_sl + (j * HPS + hsub) * o_sh + d0, pack(o));
+      }
+      rs_tok = rs_next;
+    }
+  }
+  if (dw != nullptr && NORM == 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&sdw[d0 + i], acc[0][i]);
+    __syncthreads();
+    for (int i = t; i < D; i += T) atomicAdd(dw + i, sdw[i]);
+  }
+  if (dw != nullptr && NORM == 2) {
+#pragma unroll
+    for (int j = 0; j < VPT; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(dw + (j * T + t) * 8 + i, acc[NORM == 2 ? j : 0][i]);
+  }
+}
+
+template <int NORM, int VPT, int D>
+int launch_rope_bwd_bulk(const bf16* dy, const bf16* x, const float* rstd, bf16* dx, float* dw, const float* w, const float* c,
+                         const float* s, const int64_t* gs, const int64_t* xs, const int64_t* os, int B, int L, int H,
+                         int L_rope, cudaStream_t st) {
+  const int C = H * D;
+  const int stage = C * 2 + (NORM != 0 ? C * 2 : 0) + 2 * D * 4 + (NORM == 1 ? ((H * 4 + 15) & ~15) : 0);
+  const int smem = ROPE_STAGES * stage;
+  static bool configured = false;
+  if (!configured) {
+    VT_CHECK_CUDA(cudaFuncSetAttribute(rope_bwd_bulk_kernel<NORM, VPT, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       ROPE_STAGES * (5120 * 4 + 2 * 128 * 4 + 512)));
+    configured = true;
+  }
+  // 48 CTAs per SM of grid (see launch_rope_bulk); the full-row norm flushes C weight-gradient atomics per CTA: fewer there
+  static const int want_b = getenv("VT_ROPE_CTAS_B") != nullptr ? atoi(getenv("VT_ROPE_CTAS_B")) : (NORM == 2 ? 8 : 48);
+  dim3 grid(ln_grid_x(L, B, want_b), B);
+  rope_bwd_bulk_kernel<NORM, VPT, D><<<grid, 128, smem, st>>>(dy, x, rstd, dx, dw, w, c, s, gs[0], gs[1], xs[0], xs[1], os[0],
+                                                               os[1], os[2], L, H, L_rope);
   VT_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -686,13 +1015,49 @@ int rope_fwd_fast(const void* x, void* y, float* rstd, const float* w, const flo
   const int vpt = C / 1024;
   const bf16* xp = static_cast<const bf16*>(x);
   bf16* yp = static_cast<bf16*>(y);
+  // rows that are contiguous and 16-byte aligned (heads packed inside a token, as every caller's views are) take the
+  // bulk-copy kernel; VT_ROPE_REG=1 keeps the register-prefetch kernel (A/B measurements)
+  static const bool reg_only = getenv("VT_ROPE_REG") != nullptr && atoi(getenv("VT_ROPE_REG")) != 0;
+  const bool bulk_ok = !reg_only && xs[2] == D && (xs[1] % 8) == 0 && (xs[0] % 8) == 0 && aligned16(x) &&
+                       (c == nullptr || (aligned16(c) && aligned16(s)));
 #define VT_ROPE(N_, V_)                                                                                                  \
-  if (norm_mode == N_ && vpt == V_)                                                                                     \
+  if (norm_mode == N_ && vpt == V_) {                                                                                   \
+    if (bulk_ok)                                                                                                        \
+      return D == 128 ? launch_rope_bulk<N_, V_, 128>(xp, yp, rstd, w, c, s, xs, ys, B, L, H, L_rope, eps, st)          \
+                      : launch_rope_bulk<N_, V_, 64>(xp, yp, rstd, w, c, s, xs, ys, B, L, H, L_rope, eps, st);          \
     return D == 128 ? launch_rope<N_, V_, 128>(xp, yp, rstd, w, c, s, xs, ys, B, L, H, L_rope, eps, st)                 \
-                    : launch_rope<N_, V_, 64>(xp, yp, rstd, w, c, s, xs, ys, B, L, H, L_rope, eps, st);
+                    : launch_rope<N_, V_, 64>(xp, yp, rstd, w, c, s, xs, ys, B, L, H, L_rope, eps, st);                 \
+  }
   VT_ROPE(0, 3) VT_ROPE(1, 3) VT_ROPE(2, 3) VT_ROPE(0, 5) VT_ROPE(1, 5) VT_ROPE(2, 5) VT_ROPE(0, 1) VT_ROPE(1, 1) VT_ROPE(2, 1)
   VT_ROPE(0, 2) VT_ROPE(1, 2) VT_ROPE(2, 2)
 #undef VT_ROPE
+  return 1;
+}
+
+// 1 = no specialised configuration (caller falls back to the generic kernel in rowwise.cu)
+int rope_bwd_fast(const void* dy, const void* x, const float* rstd, void* dx, float* dw, const float* w, const float* c,
+                  const float* s, const int64_t* gs, const int64_t* xs, const int64_t* os, int B, int L, int H, int D,
+                  int L_rope, int norm_mode, cudaStream_t st) {
+  const int C = H * D;
+  if (C % 1024 != 0 || B > 65535 || (D != 64 && D != 128)) return 1;
+  static const bool generic = getenv("VT_ROPE_REG") != nullptr && atoi(getenv("VT_ROPE_REG")) != 0;
+  if (generic) return 1;
+  // contiguous, 16-byte aligned token rows for dy and x; per-head rstd rows must be 16-byte multiples
+  if (gs[2] != D || (gs[1] % 8) != 0 || (gs[0] % 8) != 0 || !aligned16(dy)) return 1;
+  if (norm_mode != 0 && (xs[2] != D || (xs[1] % 8) != 0 || (xs[0] % 8) != 0 || !aligned16(x))) return 1;
+  if (norm_mode == 1 && ((H % 4) != 0 || !aligned16(rstd))) return 1;
+  if (c != nullptr && (!aligned16(c) || !aligned16(s))) return 1;
+  const int vpt = C / 1024;
+  const bf16* gp = static_cast<const bf16*>(dy);
+  const bf16* xp = static_cast<const bf16*>(x);
+  bf16* op = static_cast<bf16*>(dx);
+#define VT_ROPE_B(N_, V_)                                                                                                \
+  if (norm_mode == N_ && vpt == V_)                                                                                     \
+    return D == 128 ? launch_rope_bwd_bulk<N_, V_, 128>(gp, xp, rstd, op, dw, w, c, s, gs, xs, os, B, L, H, L_rope, st) \
+                    : launch_rope_bwd_bulk<N_, V_, 64>(gp, xp, rstd, op, dw, w, c, s, gs, xs, os, B, L, H, L_rope, st);
+  VT_ROPE_B(0, 3) VT_ROPE_B(1, 3) VT_ROPE_B(2, 3) VT_ROPE_B(0, 5) VT_ROPE_B(1, 5) VT_ROPE_B(2, 5) VT_ROPE_B(0, 1) VT_ROPE_B(1, 1)
+  VT_ROPE_B(2, 1) VT_ROPE_B(0, 2) VT_ROPE_B(1, 2) VT_ROPE_B(2, 2)
+#undef VT_ROPE_B
   return 1;
 }
 

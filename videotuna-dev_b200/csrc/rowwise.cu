@@ -574,6 +574,9 @@ int ln_fwd_fast(const void* x, void* y, float* mean, float* rstd, const float* g
 int ln_bwd_fast(const void* dy, const void* x, const float* mean, const float* rstd, void* dx, const float* gamma,
                 const float* beta, const float* scale, float* dgamma, float* dbeta, float* dscale, float* dshift, int B, int L,
                 int C, int x_dtype, cudaStream_t st);
+int rope_bwd_fast(const void* dy, const void* x, const float* rstd, void* dx, float* dw, const float* w, const float* c,
+                  const float* s, const int64_t* gs, const int64_t* xs, const int64_t* os, int B, int L, int H, int D,
+                  int L_rope, int norm_mode, cudaStream_t st);
 int rope_fwd_fast(const void* x, void* y, float* rstd, const float* w, const float* c, const float* s, const int64_t* xs,
                   const int64_t* ys, int B, int L, int H, int D, int L_rope, int norm_mode, float eps, cudaStream_t st);
 }  // namespace vt
@@ -721,6 +724,11 @@ int vt_qk_rmsnorm_rope_bwd(const void* dy, const void* x, const float* rstd, voi
   const int64_t zero3[3] = {0, 0, 0};
   const int64_t* xs = x_strides ? x_strides : zero3;
   auto st = static_cast<cudaStream_t>(stream);
+  if (getenv("VT_LN_GENERIC") == nullptr) {
+    const int rc = rope_bwd_fast(dy, x, rstd, dx, dw_accum, w, cos, sin, dy_strides, xs, dx_strides, B, L, H, D, L_rope,
+                                 norm_mode, st);
+    if (rc <= 0) return rc;
+  }
 #define VT_RB_ARGS static_cast<const bf16*>(dy), static_cast<const bf16*>(x), rstd, static_cast<bf16*>(dx), dw_accum, w, cos, \
                    sin, dy_strides[0], dy_strides[1], dy_strides[2], xs[0], xs[1], xs[2], dx_strides[0], dx_strides[1],        \
                    dx_strides[2], L, H, D, L_rope

@@ -10,6 +10,7 @@
 // Replaces the forward of lvdm CrossAttention.forward (videotuna/models/lvdm/modules/attention.py:126-149) as called by
 // TemporalTransformer over t = 16 frames (:475-519); mask semantics as temporal_attn.cu.
 #include <cfloat>
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "capi_util.h"
@@ -224,7 +225,8 @@ cudaError_t launch_mma(const MmaArgs& a, cudaStream_t st) {
   }
   const int64_t pairs = static_cast<int64_t>(a.B) * a.H;
   int64_t blocks = (pairs + WARPS - 1) / WARPS;
-  const int64_t cap = 148 * 8;
+  static const int64_t per_sm = getenv("VT_TEMPORAL_CTAS") != nullptr ? atoi(getenv("VT_TEMPORAL_CTAS")) : 8;
+  const int64_t cap = 148 * per_sm;
   if (blocks > cap) blocks = cap;
   temporal_mma_fwd_kernel<D, MT><<<static_cast<unsigned>(blocks), WARPS * 32, bytes, st>>>(a);
   return cudaGetLastError();
@@ -503,7 +505,8 @@ cudaError_t launch_mma_bwd(const MmaBwdArgs& a, cudaStream_t st) {
   }
   const int64_t pairs = static_cast<int64_t>(a.B) * a.H;
   int64_t blocks = (pairs + WARPS - 1) / WARPS;
-  const int64_t cap = 148 * 8;
+  static const int64_t per_sm = getenv("VT_TEMPORAL_CTAS") != nullptr ? atoi(getenv("VT_TEMPORAL_CTAS")) : 8;
+  const int64_t cap = 148 * per_sm;
   if (blocks > cap) blocks = cap;
   temporal_mma_bwd_kernel<D, MT><<<static_cast<unsigned>(blocks), WARPS * 32, bytes, st>>>(a);
   return cudaGetLastError();

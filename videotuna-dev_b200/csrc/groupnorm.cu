@@ -360,6 +360,26 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
                : "memory");
 }
 
+// Channel index of the vector a thread visits next, advanced without a division: a thread's vectors are `stride` elements
+// apart, so (channel, offset inside the channel) move by (stride / S, stride % S) with one carry.
+struct ChanIter {
+  int cc, rem, dq, dr, S;
+  __device__ __forceinline__ ChanIter(int pos, int stride, int S_) : S(S_) {
+    cc = pos / S_;
+    rem = pos - cc * S_;
+    dq = stride / S_;
+    dr = stride - dq * S_;
+  }
+  __device__ __forceinline__ void next() {
+    cc += dq;
+    rem += dr;
+    if (rem >= S) {
+      rem -= S;
+      ++cc;
+    }
+  }
+};
+
 // Sum `NV` per-CTA values over the CTAs of the cluster: every CTA publishes its partials in its own shared memory, the
 // cluster synchronises, and every CTA reads all peers' partials through DSMEM. The caller must keep its shared memory
 // alive until the peers have read it (cluster.sync() before exit).
@@ -400,7 +420,8 @@ groupnorm_fwd_bulk_kernel(const T* __restrict__ x, T* __restrict__ y, float* __r
   const int count = cpg * S;
   const int start = rank * chunk;
   const int len = max(0, min(chunk, count - start));
-  const int sub = ((chunk / VEC + GB_NSUB - 1) / GB_NSUB) * VEC;
+  // sub-copies of whole CTA sweeps (GB_THREADS vectors), so a thread's m-th vector is the same in every pass
+  const int sub = ((chunk / VEC + GB_NSUB * GB_THREADS - 1) / (GB_NSUB * GB_THREADS)) * (GB_THREADS * VEC);
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < GB_NSUB; ++s) mbar_init(&bars[s], 1);
@@ -451,18 +472,32 @@ groupnorm_fwd_bulk_kernel(const T* __restrict__ x, T* __restrict__ y, float* __r
     if (rstd_out) rstd_out[n * G + g] = rstd;
   }
   T* ys = y + base + start;
-  for (int i = tid * VEC; i < len; i += GB_THREADS * VEC) {
-    const int cc = (start + i) / S;  // a vector never straddles channels because S % VEC == 0
-    const float ga = sgb[cc], be = sgb[cpg + cc];
-    const float a = rstd * ga, bsh = be - mean * a;
-    float f[VEC];
-    Io<T>::load(buf + i, f);
+  ChanIter ch(start + tid * VEC, GB_THREADS * VEC, S);  // a vector never straddles channels because S % VEC == 0
+  if (apply_silu && sizeof(T) == 2) {
+    // silu(z) = h + h tanh(h), h = z / 2 = x * (rstd gamma / 2) + (beta - mean rstd gamma) / 2: 2 FMA + 1 MUFU per element
+    for (int i = tid * VEC; i < len; i += GB_THREADS * VEC, ch.next()) {
+      const float a = 0.5f * rstd * sgb[ch.cc], bsh = fmaf(-mean, a, 0.5f * sgb[cpg + ch.cc]);
+      float f[VEC];
+      Io<T>::load(buf + i, f);
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      const float z = fmaf(f[k], a, bsh);
-      f[k] = apply_silu ? silu_t<T>(z) : z;
+      for (int k = 0; k < VEC; ++k) {
+        const float h = fmaf(f[k], a, bsh);
+        f[k] = fmaf(h, tanh_approx(h), h);
+      }
+      Io<T>::store(ys + i, f);
     }
-    Io<T>::store(ys + i, f);
+  } else {
+    for (int i = tid * VEC; i < len; i += GB_THREADS * VEC, ch.next()) {
+      const float a = rstd * sgb[ch.cc], bsh = fmaf(-mean, a, sgb[cpg + ch.cc]);
+      float f[VEC];
+      Io<T>::load(buf + i, f);
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) {
+        const float z = fmaf(f[k], a, bsh);
+        f[k] = apply_silu ? silu_t<T>(z) : z;
+      }
+      Io<T>::store(ys + i, f);
+    }
   }
   if (CL > 1) cg::this_cluster().sync();  // peers may still be reading `partial`
 }
@@ -492,7 +527,8 @@ groupnorm_bwd_bulk_kernel(const T* __restrict__ dy, const T* __restrict__ x, con
   const int count = cpg * S;
   const int start = rank * chunk;
   const int len = max(0, min(chunk, count - start));
-  const int sub = ((chunk / VEC + GB_NSUB - 1) / GB_NSUB) * VEC;
+  // sub-copies of whole CTA sweeps (GB_THREADS vectors), so a thread's m-th vector is the same in every pass
+  const int sub = ((chunk / VEC + GB_NSUB * GB_THREADS - 1) / (GB_NSUB * GB_THREADS)) * (GB_THREADS * VEC);
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < GB_NSUB; ++s) mbar_init(&bars[s], 1);
@@ -517,59 +553,92 @@ groupnorm_bwd_bulk_kernel(const T* __restrict__ dy, const T* __restrict__ x, con
     }
   }
   const float mean = mean_in[n * G + g], rstd = rstd_in[n * G + g];
+  const float nmr = -mean * rstd;
   float tot[2] = {0.f, 0.f};
+  ChanIter ch(start + tid * VEC, GB_THREADS * VEC, S);
 #pragma unroll 1
   for (int s = 0; s < GB_NSUB; ++s) {
     const int off = s * sub, l = min(sub, len - off);
     if (l <= 0) break;
     mbar_wait(&bars[s], 0, 0x6e02);
-    // warp-uniform trip count so the shuffles below are convergent
-    for (int i0 = off + (tid - lane) * VEC; i0 < off + l; i0 += GB_THREADS * VEC) {
+    // `sub` is a whole number of CTA sweeps: the trip count is warp-uniform and the shuffles below are convergent
+    for (int i0 = off + (tid - lane) * VEC; i0 < off + l; i0 += GB_THREADS * VEC, ch.next()) {
       const int i = i0 + lane * VEC;
       const bool ok = i < off + l;
-      const int cc = ok ? (start + i) / S : -1;
-      float a0 = 0.f, a1 = 0.f, ga = 0.f;
+      const int cc = ok ? ch.cc : -1;
+      float a0 = 0.f, a1 = 0.f;
       if (ok) {
-        ga = sgb[cc];
-        const float be = sgb[cpg + cc];
+        const float ga = sgb[cc];
         float fx[VEC], fg[VEC];
         Io<T>::load(bx + i, fx);
         Io<T>::load(bg + i, fg);
+        if (apply_silu && sizeof(T) == 2) {
+          // silu'(z) = s (1 + z (1 - s)) with s = (1 + t) / 2, t = tanh(h), h = z / 2:  = (1/2 + t/2) (1 + h - h t)
+          const float ha = 0.5f * rstd * ga, hb = fmaf(mean, -ha, 0.5f * sgb[cpg + cc]);
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-          const float xh = (fx[k] - mean) * rstd;
-          float gz = fg[k];
-          if (apply_silu) gz *= dsilu_t<T>(fmaf(xh, ga, be));
-          fg[k] = gz;
-          a0 += gz;
-          a1 = fmaf(gz, xh, a1);
+          for (int k = 0; k < VEC; ++k) {
+            const float h = fmaf(fx[k], ha, hb);
+            const float t = tanh_approx(h);
+            const float u = fmaf(-h, t, h + 1.f);
+            const float gz = fg[k] * (fmaf(0.5f, t, 0.5f) * u);
+            const float xh = fmaf(fx[k], rstd, nmr);
+            fg[k] = gz;
+            a0 += gz;
+            a1 = fmaf(gz, xh, a1);
+          }
+          Io<T>::store(bg + i, fg);  // the second pass reads gz = dy * silu'(z) instead of recomputing it
+        } else {
+          const float be = sgb[cpg + cc];
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) {
+            const float xh = fmaf(fx[k], rstd, nmr);
+            float gz = fg[k];
+            if (apply_silu) gz *= dsilu_t<T>(fmaf(xh, ga, be));
+            fg[k] = gz;
+            a0 += gz;
+            a1 = fmaf(gz, xh, a1);
+          }
+          if (apply_silu) Io<T>::store(bg + i, fg);
         }
-        if (apply_silu) Io<T>::store(bg + i, fg);  // the second pass reads gz = dy * silu'(z) instead of recomputing it
+        tot[0] = fmaf(a0, ga, tot[0]);
+        tot[1] = fmaf(a1, ga, tot[1]);
       }
-      tot[0] = fmaf(a0, ga, tot[0]);
-      tot[1] = fmaf(a1, ga, tot[1]);
-      // per-channel bins, private to the warp: for every distinct channel among the warp's 32 vectors (one in the common
-      // case, two across a channel boundary) the lanes of that channel are summed by shuffles and the leader adds the pair
-      // to the warp's own bin with plain loads / stores (shared-memory float atomics are CAS loops and, with eight warps on
-      // one address, were a quarter of the stall samples)
-      unsigned remaining = __ballot_sync(0xffffffffu, ok);
-      while (remaining != 0) {
-        const int leader = __ffs(remaining) - 1;
-        const int c = __shfl_sync(0xffffffffu, cc, leader);
-        const bool mine = ok && cc == c;
-        float v0 = mine ? a0 : 0.f, v1 = mine ? a1 : 0.f;
+      // per-channel bins, private to the warp (shared-memory float atomics are CAS loops; with eight warps on one address
+      // they were a quarter of the stall samples). Fast path: the warp's 32 vectors lie in one channel — one shuffle
+      // reduction, the first lane adds the pair to the warp's bin with plain loads / stores. Across a channel boundary:
+      // one such round per distinct channel.
+      const int c0 = __shfl_sync(0xffffffffu, cc, 0);
+      if (__all_sync(0xffffffffu, cc == c0 || !ok)) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-          v0 += __shfl_xor_sync(0xffffffffu, v0, o);
-          v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+          a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+          a1 += __shfl_xor_sync(0xffffffffu, a1, o);
         }
-        if (lane == leader) {
-          wbins[c] += v0;
-          wbins[cpg + c] += v1;
+        if (lane == 0 && c0 >= 0) {
+          wbins[c0] += a0;
+          wbins[cpg + c0] += a1;
         }
-        __syncwarp();  // the next leader may be another lane updating the same bin
-        remaining &= ~__ballot_sync(0xffffffffu, mine);
+      } else {
+        unsigned remaining = __ballot_sync(0xffffffffu, ok);
+        while (remaining != 0) {
+          const int leader = __ffs(remaining) - 1;
+          const int c = __shfl_sync(0xffffffffu, cc, leader);
+          const bool mine = ok && cc == c;
+          float v0 = mine ? a0 : 0.f, v1 = mine ? a1 : 0.f;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+          }
+          if (lane == leader) {
+            wbins[c] += v0;
+            wbins[cpg + c] += v1;
+          }
+          __syncwarp();  // the next leader may be another lane updating the same bin
+          remaining &= ~__ballot_sync(0xffffffffu, mine);
+        }
       }
+      __syncwarp();
     }
   }
   cta_sum<2, GB_THREADS>(tot, red);  // (its barriers also order the bin updates before the flush below)
@@ -584,17 +653,16 @@ groupnorm_bwd_bulk_kernel(const T* __restrict__ dy, const T* __restrict__ x, con
   const float inv = 1.f / count;
   const float m1 = tot[0] * inv, m2 = tot[1] * inv;
   T* os = dx + base + start;
-  for (int i = tid * VEC; i < len; i += GB_THREADS * VEC) {
-    const float ga = sgb[(start + i) / S];
+  ChanIter ch2(start + tid * VEC, GB_THREADS * VEC, S);
+  const float rm1 = rstd * m1, rm2 = rstd * m2;
+  const float c2 = -rm2 * rstd, c0 = -fmaf(rm2, nmr, rm1);  // dx = gz * (rstd gamma) + x * c2 + c0
+  for (int i = tid * VEC; i < len; i += GB_THREADS * VEC, ch2.next()) {
+    const float rg = rstd * sgb[ch2.cc];
     float fx[VEC], fg[VEC];
     Io<T>::load(bx + i, fx);
-    Io<T>::load(bg + i, fg);
-    const float rg = rstd * ga, rm1 = rstd * m1, rm2 = rstd * m2;
+    Io<T>::load(bg + i, fg);  // gz (pass 1 rewrote it; cta_sum's barriers order those writes)
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      const float xh = (fx[k] - mean) * rstd;
-      fx[k] = fmaf(fg[k], rg, -fmaf(xh, rm2, rm1));  // fg holds gz (pass 1 rewrote it; cta_sum's barriers order those writes)
-    }
+    for (int k = 0; k < VEC; ++k) fx[k] = fmaf(fg[k], rg, fmaf(fx[k], c2, c0));
     Io<T>::store(os + i, fx);
   }
   if (CL > 1) cg::this_cluster().sync();

@@ -299,6 +299,103 @@ __global__ void __launch_bounds__(T, 5) ln_fwd2_kernel(const XT* __restrict__ x,
   }
 }
 
+// fp32 rows (Wan's residual stream, 20 KB per row): two rows in registers do not fit, and the one-row kernel sits at 72 %.
+// Here the rows arrive in a shared-memory ring by 1-D bulk asynchronous copies two rows ahead (like the RoPE kernels), so
+// no register is tied up by data in flight; 256 threads per CTA, the factor table (2 x C fp32) once per long-lived CTA.
+__device__ __forceinline__ void ln_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int T, int VPT>
+__global__ void __launch_bounds__(T) ln_fwd_ring_f32_kernel(const float* __restrict__ x, bf16* __restrict__ y,
+                                                            float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ scale, const float* __restrict__ shift,
+                                                            int L, int C, float eps) {
+  constexpr int S = 3;
+  extern __shared__ __align__(128) float ring[];  // S x row[C] | mul[C] | add[C]
+  __shared__ __align__(8) uint64_t full[S];
+  __shared__ float red[4 * (T / 32)];
+  float* mul = ring + S * C;
+  float* add = mul + C;
+  const int b = blockIdx.y, t = threadIdx.x;
+  for (int c = t; c < C; c += T) {
+    const float g = gamma ? gamma[c] : 1.f, be = beta ? beta[c] : 0.f;
+    const float s1 = scale ? 1.f + scale[static_cast<size_t>(b) * C + c] : 1.f;
+    const float sh = shift ? shift[static_cast<size_t>(b) * C + c] : 0.f;
+    mul[c] = g * s1;
+    add[c] = be * s1 + sh;
+  }
+  if (t == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  bool act[VPT];
+#pragma unroll
+  for (int j = 0; j < VPT; ++j) act[j] = (j * T + t) * 8 < C;
+  const size_t base = static_cast<size_t>(b) * L;
+  const int n_row = blockIdx.x < static_cast<unsigned>(L) ? (L - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  auto issue = [&](int k) {  // thread 0 only
+    const int l = blockIdx.x + k * gridDim.x;
+    mbar_arrive_expect_tx(&full[k % S], C * 4);
+    ln_bulk_g2s(ring + (k % S) * C, x + (base + l) * C, C * 4, &full[k % S]);
+  };
+  if (t == 0)
+    for (int k = 0; k < S - 1 && k < n_row; ++k) issue(k);
+  for (int k = 0; k < n_row; ++k) {
+    const int l = blockIdx.x + k * gridDim.x;
+    __syncthreads();  // every thread is done with stage (k - 1) % S
+    if (t == 0 && k + S - 1 < n_row) issue(k + S - 1);
+    mbar_wait(&full[k % S], (k / S) & 1, 0x7e03);
+    const float* row = ring + (k % S) * C;
+    float f[VPT][8];
+    float s[1] = {0.f};
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[j][i] = 0.f;
+      if (act[j]) lds8(row + (j * T + t) * 8, f[j]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[0] += f[j][i];
+    }
+    block_sum<T, 1>(s, red, k & 1);
+    const float mean = s[0] / C;
+    float q[1] = {0.f};
+#pragma unroll
+    for (int j = 0; j < VPT; ++j)
+      if (act[j]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float d = f[j][i] - mean;
+          q[0] = fmaf(d, d, q[0]);
+        }
+      }
+    block_sum<T, 1>(q, red + 2 * (T / 32), k & 1);
+    const float rstd = rsqrtf(q[0] / C + eps);
+    if (t == 0) {
+      if (mean_out) mean_out[base + l] = mean;
+      if (rstd_out) rstd_out[base + l] = rstd;
+    }
+    const float nb = -mean * rstd;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      if (!act[j]) continue;
+      const int col = (j * T + t) * 8;
+      float m8[8], a8[8], o[8];
+      lds8(mul + col, m8);
+      lds8(add + col, a8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(fmaf(f[j][i], rstd, nb), m8[i], a8[i]);
+      stg16(y + (base + l) * C + col, pack(o));
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // backward.  xh = (x - mean) * rstd;  y = xh * mul + add  with  mul = gamma * s1, add = beta * s1 + shift, s1 = 1 + scale
 //   gh = dy * mul;  dx = rstd * (gh - mean_C(gh) - xh * mean_C(gh * xh))
@@ -521,6 +618,24 @@ int ln_fwd_fast(const void* x, void* y, float* mean, float* rstd, const float* g
                 const float* shift, int B, int L, int C, float eps, int x_dtype, cudaStream_t st) {
   LnCfg c;
   if (!ln_cfg(C, &c) || B > 65535) return 1;
+  // fp32 rows wider than 4096 (Wan: 5120): bulk-copy ring kernel; VT_LN_RING=0 keeps the one-row register kernel (A/B)
+  static const bool ring_ok = !(getenv("VT_LN_RING") != nullptr && atoi(getenv("VT_LN_RING")) == 0);
+  if (ring_ok && x_dtype == 1 && C > 4096 && C <= 6144 && C % 8 == 0 && aligned16(x)) {
+    constexpr int T = 256, VPT = 3;
+    const int smem = (3 * C + 2 * C) * 4;
+    static bool configured = false;
+    if (!configured) {
+      VT_CHECK_CUDA(cudaFuncSetAttribute(ln_fwd_ring_f32_kernel<T, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         5 * 6144 * 4));
+      configured = true;
+    }
+    static const int want = getenv("VT_LNR_CTAS") != nullptr ? atoi(getenv("VT_LNR_CTAS")) : 2;
+    dim3 grid(ln_grid_x(L, B, want), B);
+    ln_fwd_ring_f32_kernel<T, VPT><<<grid, T, smem, st>>>(static_cast<const float*>(x), static_cast<bf16*>(y), mean, rstd, gamma,
+                                                         beta, scale, shift, L, C, eps);
+    VT_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
 #define X(T_, V_)                                                                                                        \
   if (c.T == T_ && c.VPT == V_)                                                                                          \
     return x_dtype == 0 ? launch_fwd<bf16, T_, V_>(static_cast<const bf16*>(x), static_cast<bf16*>(y), mean, rstd, gamma, beta, \

@@ -299,7 +299,8 @@ __global__ void __launch_bounds__(T, 5) ln_fwd2_kernel(const XT* __restrict__ x,
   }
 }
 
-// fp32 rows (Wan's residual stream, 20 KB per row): two rows in registers do not fit, and the one-row kernel sits at 72 %.
+// fp32 rows (Wan's residual stream, 20 KB per row): two rows in registers do not fit, and the one-row kernel sits at 72 %
+// (this one: 79 %; two 100 KB CTAs per SM, grid = one resident wave — 3 per SM of grid drops to 60 %).
 // Here the rows arrive in a shared-memory ring by 1-D bulk asynchronous copies two rows ahead (like the RoPE kernels), so
 // no register is tied up by data in flight; 256 threads per CTA, the factor table (2 x C fp32) once per long-lived CTA.
 __device__ __forceinline__ void ln_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -621,7 +622,7 @@ int ln_fwd_fast(const void* x, void* y, float* mean, float* rstd, const float* g
   // fp32 rows wider than 4096 (Wan: 5120): bulk-copy ring kernel; VT_LN_RING=0 keeps the one-row register kernel (A/B)
   static const bool ring_ok = !(getenv("VT_LN_RING") != nullptr && atoi(getenv("VT_LN_RING")) == 0);
   if (ring_ok && x_dtype == 1 && C > 4096 && C <= 6144 && C % 8 == 0 && aligned16(x)) {
-    constexpr int T = 256, VPT = 3;
+    constexpr int T = 256, VPT = 3;  // 512 x 2 measured slower (68 vs 79 %)
     const int smem = (3 * C + 2 * C) * 4;
     static bool configured = false;
     if (!configured) {

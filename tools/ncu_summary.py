@@ -35,6 +35,7 @@ def launches(path):
 KEYS = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "dram__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "gpc__cycles_elapsed.max", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_elapsed",
@@ -48,10 +49,20 @@ def full(rep):
     for r in rows[2:]:
         name = short(r[hdr.index("Kernel Name")])
         print(f"== {name}")
+        vals = {}
         for k in KEYS:
             if k in hdr:
                 i = hdr.index(k)
+                vals[k] = (r[i], units[i])
                 print(f"   {k} = {r[i]} {units[i]}")
+        try:  # achieved DRAM bandwidth of this launch (under ncu: cold caches, serialised — for the bytes, not the time)
+            to_b = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+            to_s = {"ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
+            nbytes = sum(float(vals[k][0].replace(",", "")) * to_b[vals[k][1]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+            secs = float(vals["gpu__time_duration.sum"][0].replace(",", "")) * to_s[vals["gpu__time_duration.sum"][1]]
+            print(f"   => DRAM read+write {nbytes / 1e6:.1f} MB in {secs * 1e6:.1f} us = {nbytes / secs / 1e9:.0f} GB/s")
+        except Exception:  # noqa: BLE001
+            pass
         src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + name.split("<")[0]],
                              capture_output=True, text=True).stdout
         with open("/tmp/_ncu_src.csv", "w") as fh:

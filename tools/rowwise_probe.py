@@ -13,13 +13,24 @@ import b200vt.ops as ops  # noqa: E402
 N = int(os.environ.get("PROBE_ITERS", "3"))
 x = torch.randn(1, 119056, 3072, device="cuda", dtype=torch.bfloat16)
 sc = torch.randn(1, 3072, device="cuda") * 0.1
+x.requires_grad_(True)
 for _ in range(N):
     y = Fn.ln_modulate(x, sc, sc, eps=1e-6)
+    y.backward(torch.randn_like(y))
+    x.grad = None
+xr = x.detach()
+for _ in range(N):
+    r = Fn.gate_residual(xr, y.detach(), sc)
+del y, r
 qkv = torch.randn(1, 118800, 3, 24, 128, device="cuda", dtype=torch.bfloat16)
 w = torch.ones(128, device="cuda")
 cs = torch.rand(118800, 128, device="cuda")
+qv = qkv[:, :, 0].detach().requires_grad_(True)
 for _ in range(N):
-    z = Fn.qk_rmsnorm_rope(qkv[:, :, 0], w, cs, cs)
+    z = Fn.qk_rmsnorm_rope(qv, w, cs, cs)
+    z.backward(torch.randn_like(z))
+    qv.grad = None
+del z
 q, k, v = (torch.randn(5120, 16, 5, 64, device="cuda", dtype=torch.bfloat16, requires_grad=True) for _ in range(3))
 for _ in range(N):
     o = ops.temporal_attn_fwd(q, k, v, None, 0.125)

@@ -92,7 +92,12 @@ def _rope_ref(x, w, cos, sin, per_head, eps):
 
 @pytest.mark.parametrize("B,L,H,D,per_head,use_w,Lr", [(1, 150, 3, 128, True, True, 120), (2, 70, 24, 128, True, True, 70),
                                                        (1, 61, 5, 128, False, True, 60), (2, 33, 2, 64, True, False, 33),
-                                                       (1, 40, 40, 128, False, True, 40), (1, 20, 2, 128, True, True, 0)])
+                                                       (1, 40, 40, 128, False, True, 40), (1, 20, 2, 128, True, True, 0),
+                                                       # widths that are multiples of 1024 take the bulk-copy ring kernels:
+                                                       (1, 90, 16, 64, True, True, 50),     # head dim 64, RoPE on a prefix
+                                                       (2, 45, 8, 128, True, False, 45),    # no norm weight -> rotation only
+                                                       (1, 700, 24, 128, True, True, 600),  # more tokens than ring stages
+                                                       (1, 333, 16, 128, False, True, 300)])  # full-row norm, 2048 wide
 def test_qk_rmsnorm_rope_fwd_bwd(B, L, H, D, per_head, use_w, Lr):
     import b200vt.functional as Fn
     x = _r((B, L, H, D), 1, 1.5)
@@ -224,3 +229,34 @@ def test_groupnorm_silu_full_vc2_sizes_match_torch_fp32(shape):
     assert float((y.float() - yr).abs().max() / yr.abs().max()) < TOL
     assert float(F.cosine_similarity(gx.float().flatten(), gxr.flatten(), dim=0)) > COS
     assert float((gw - gwr).abs().max() / gwr.abs().max()) < TOL and float((gb - gbr).abs().max() / gbr.abs().max()) < TOL
+
+
+def test_qk_rmsnorm_rope_full_k1_size_matches_torch_fp32():
+    """HunyuanVideo K1: the q view of the fused QKV projection (118 800 tokens x 24 heads x 128, row stride 3 x 3072), per-head
+    RMSNorm + RoPE, forward and backward through the bulk-copy ring kernels with their full-size grids (every CTA walks
+    several tokens through the ring), against the same arithmetic in torch fp32 on the GPU."""
+    import b200vt.functional as Fn
+    g = torch.Generator(device="cuda").manual_seed(8)
+    L, H, D = 118800, 24, 128
+    qkv = torch.randn(1, L, 3, H, D, device="cuda", generator=g).to(torch.bfloat16)
+    w = 1 + 0.1 * torch.randn(D, device="cuda", generator=g)
+    ang = torch.rand(L, D // 2, device="cuda", generator=g) * 6.28
+    cos, sin = ang.cos().repeat_interleave(2, dim=1).contiguous(), ang.sin().repeat_interleave(2, dim=1).contiguous()
+    dy = torch.randn(1, L, H, D, device="cuda", generator=g).to(torch.bfloat16)
+    q = qkv[:, :, 0].detach().requires_grad_(True)
+    wc = w.clone().requires_grad_(True)
+    y = Fn.qk_rmsnorm_rope(q, wc, cos, sin, per_head=True, eps=1e-6)
+    gq, gw = torch.autograd.grad(y, (q, wc), dy)
+    qr = qkv[:, :, 0].detach().float().requires_grad_(True)
+    wr = w.clone().requires_grad_(True)
+    n = qr * torch.rsqrt(qr.pow(2).mean(-1, keepdim=True) + 1e-6) * wr
+    a, b = n.reshape(1, L, H, D // 2, 2).unbind(-1)
+    rot = torch.stack([-b, a], dim=-1).flatten(3)
+    yr = n * cos.view(1, L, 1, D) + rot * sin.view(1, L, 1, D)
+    gqr, gwr = torch.autograd.grad(yr, (qr, wr), dy.float())
+    assert float((y.float() - yr).abs().max() / yr.abs().max()) < TOL
+    row_err = (y.float() - yr).abs().amax(dim=(2, 3)) / yr.abs().amax(dim=(2, 3))  # every token was written
+    assert float(row_err.max()) < 4 * TOL
+    assert float(torch.nn.functional.cosine_similarity(gq.float().flatten(), gqr.flatten(), dim=0)) > COS
+    assert float((gq.float() - gqr).abs().max() / gqr.abs().max()) < 2 * TOL
+    assert float((gw - gwr).abs().max() / gwr.abs().max()) < TOL

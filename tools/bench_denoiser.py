@@ -26,7 +26,6 @@ from __future__ import annotations
 
 import argparse
 import json
-import math
 import os
 import sys
 import time
@@ -422,8 +421,6 @@ def main():
             # sequence parallel as the reference wires it (wan/text2video.py:261-271): every block's self-attention forward is
             # rebound to the Ulysses version; tokens are sharded, the text context is replicated, and the weight gradients of
             # the replicated parameters are summed over the ranks after the backward (one all-reduce per parameter)
-            import types
-
             import b200vt.patch as P
             for b in blocks:
                 b.self_attn._fwd = lambda self_, *a, **k: P.wan_usp_attn_forward(self_, *a, **k)

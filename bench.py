@@ -259,6 +259,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # rank 0 must print exactly one line: NCCL_DEBUG=VERSION makes NCCL write its banner to stdout
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
         if HEADS % world or IMG_TOKENS % world:
             raise SystemExit(f"world size {world} must divide {HEADS} heads and {IMG_TOKENS} image tokens")

@@ -77,7 +77,9 @@ enum : uint32_t {
 // Q and dO tiles arrive by TMA. A cp.async (LSU) producer was tried to leave the per-SM TMA engine to the dQ reduction
 // and measured 40 % slower on K1 (659 vs 1076 TFLOP/s): LSU writes into shared memory starve behind the UMMA operand
 // fetch, which saturates the 128 B/clk shared-memory port, whereas TMA writes do not (history: commit 782d835).
-template <int D>
+// DIRECT: single key tile per (sample, head) — the dQ tile is written straight to dq (AttnBwdParams::dq_direct). A compile-
+// time variant: as a run-time branch in the drain loop it cost the general kernel 2 % at K1 (same-box A/B).
+template <int D, bool DIRECT>
 __global__ void __launch_bounds__(BwdCfg<D>::THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_do,
@@ -120,6 +122,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
           *reinterpret_cast<uint4*>(dkp + c) = make_uint4(0, 0, 0, 0);
           *reinterpret_cast<uint4*>(dvp + c) = make_uint4(0, 0, 0, 0);
         }
+      }
+    }
+    if (DIRECT) {  // no valid key for this (sample, head): its dQ rows are zero and nobody else writes them
+      for (int r = threadIdx.x; r < q_len; r += blockDim.x) {
+        __nv_bfloat16* dqp = p.dq_direct + bq * p.dq_sb + static_cast<int64_t>(q_base + r) * p.dq_sl + h * p.dq_sh;
+        for (int c = 0; c < D; c += 8) *reinterpret_cast<uint4*>(dqp + c) = make_uint4(0, 0, 0, 0);
       }
     }
     return;
@@ -430,6 +438,22 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
       tc_fence_before();
       mbar_arrive(dq_drained);  // every TMEM read of this tile is complete: the issuer may overwrite the columns
       if (leader) trace_mark(p.trace, 2, i, 2);
+      if (DIRECT) {  // single key tile: this tile IS dQ (see AttnBwdParams::dq_direct)
+        const int qrow = i * 128 + row;
+        if (qrow < q_len) {
+          __nv_bfloat16* dqp = p.dq_direct + bq * p.dq_sb + static_cast<int64_t>(q_base + qrow) * p.dq_sl + h * p.dq_sh;
+#pragma unroll
+          for (int c = 0; c < D; c += 8) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(r[c + 0]) * p.scale, __uint_as_float(r[c + 1]) * p.scale);
+            w.y = pack_bf16x2(__uint_as_float(r[c + 2]) * p.scale, __uint_as_float(r[c + 3]) * p.scale);
+            w.z = pack_bf16x2(__uint_as_float(r[c + 4]) * p.scale, __uint_as_float(r[c + 5]) * p.scale);
+            w.w = pack_bf16x2(__uint_as_float(r[c + 6]) * p.scale, __uint_as_float(r[c + 7]) * p.scale);
+            *reinterpret_cast<uint4*>(dqp + c) = w;
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int c = 0; c < NCH; ++c, ++g) {
         // the reduction issued two chunks ago has finished reading this staging buffer
@@ -653,19 +677,19 @@ __global__ void attn_bwd_dq_convert_kernel(const float* __restrict__ acc, __nv_b
   *reinterpret_cast<uint4*>(dq + b * sb + static_cast<int64_t>(l) * sl + h * sh + d) = w;
 }
 
-template <int D>
+template <int D, bool DIRECT>
 cudaError_t launch_bwd_one(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
                            const CUtensorMap& tm_do, const CUtensorMap& tm_dq, float* dq_acc, int Lq_total,
                            const AttnBwdParams& p, cudaStream_t stream) {
   using C = BwdCfg<D>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<D, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::BYTES);
     if (e != cudaSuccess) return e;
     configured = true;
   }
   dim3 grid((p.seq.Lk + 127) / 128, p.seq.H, p.seq.nprob);
-  attn_bwd_kernel<D><<<grid, C::THREADS, C::BYTES, stream>>>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p);
+  attn_bwd_kernel<D, DIRECT><<<grid, C::THREADS, C::BYTES, stream>>>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p);
   return cudaGetLastError();
 }
 
@@ -674,8 +698,11 @@ cudaError_t launch_bwd_one(const CUtensorMap& tm_q, const CUtensorMap& tm_k, con
 cudaError_t launch_attn_bwd(int D, const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
                             const CUtensorMap& tm_do, const CUtensorMap& tm_dq, float* dq_acc, int Lq_total,
                             const AttnBwdParams& p, cudaStream_t stream) {
-  if (D == 128) return launch_bwd_one<128>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream);
-  if (D == 64) return launch_bwd_one<64>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream);
+  const bool direct = p.dq_direct != nullptr;
+  if (D == 128 && direct) return launch_bwd_one<128, true>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream);
+  if (D == 128) return launch_bwd_one<128, false>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream);
+  if (D == 64 && direct) return launch_bwd_one<64, true>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream);
+  if (D == 64) return launch_bwd_one<64, false>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p, stream);
   return cudaErrorInvalidValue;
 }
 

@@ -60,6 +60,11 @@ struct AttnBwdParams {
   int64_t dv_sb, dv_sl, dv_sh;
   float scale;
   float scale_log2;
+  // Single key tile (fixed mode, Lk <= 128: lvdm cross-attention on 77 text tokens, the 40-token level): a CTA's dQ tile is
+  // the whole gradient, so the drain warps write it straight to dq as scaled bf16 — no fp32 accumulator memset, no TMA
+  // reduce-add, no convert pass. NULL = accumulate (the general path).
+  __nv_bfloat16* dq_direct;
+  int64_t dq_sb, dq_sl, dq_sh;
 };
 
 // Host-side launchers implemented in the kernel translation units. Return cudaError_t of the launch.

@@ -359,7 +359,9 @@ int vt_attn_bwd(const void* dout, const void* q, const void* k, const void* v, c
   if (int rc = make_tmap_4d(&tm_v, v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, D, Lk, H, B, v_strides, 64, 128)) return rc;
   if (int rc = make_tmap_4d(&tm_do, dout, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, D, Lq, H, B, do_strides, 64, 128)) return rc;
 
-  VT_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(rows) * D * 4, st));
+  // one key tile per (sample, head) in fixed mode: dQ is written directly by the kernel (AttnBwdParams::dq_direct)
+  const bool dq_direct = num_segments <= 0 && Lk <= 128;
+  if (!dq_direct) VT_CHECK_CUDA(cudaMemsetAsync(dq_acc, 0, static_cast<size_t>(rows) * D * 4, st));
   {
     ProfScope span(VT_K_ATTN_BWD_DELTA, st);
     VT_CHECK_CUDA(launch_attn_bwd_delta(D, dout, o, delta, do_strides, o_strides, B, Lq, H, st));
@@ -388,11 +390,13 @@ int vt_attn_bwd(const void* dout, const void* q, const void* k, const void* v, c
   p.dv_sb = dv_strides[0]; p.dv_sl = dv_strides[1]; p.dv_sh = dv_strides[2];
   p.scale = softmax_scale;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  p.dq_direct = dq_direct ? static_cast<__nv_bfloat16*>(dq) : nullptr;
+  p.dq_sb = dq_strides[0]; p.dq_sl = dq_strides[1]; p.dq_sh = dq_strides[2];
   {
     ProfScope span(VT_K_ATTN_BWD, st);
     VT_CHECK_CUDA(launch_attn_bwd(D, tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq, p, st));
   }
-  {
+  if (!dq_direct) {
     ProfScope span(VT_K_ATTN_BWD_DQ, st);
     VT_CHECK_CUDA(launch_attn_bwd_dq_convert(dq_acc, dq, dq_strides, B, Lq, H, D, softmax_scale, st));
   }

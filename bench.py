@@ -259,10 +259,23 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # rank 0 must print exactly one line: NCCL_DEBUG=VERSION makes NCCL write its banner to stdout
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=dev)
+        # rank 0 must print exactly one line, but NCCL printf()s its "NCCL version ..." banner to stdout when the first
+        # communicator is created: send file descriptor 1 to stderr for that moment (and flush C stdio before restoring it)
+        import ctypes
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            try:
+                ctypes.CDLL(None).fflush(None)
+            except Exception:  # noqa: BLE001
+                pass
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
         if HEADS % world or IMG_TOKENS % world:
             raise SystemExit(f"world size {world} must divide {HEADS} heads and {IMG_TOKENS} image tokens")
     L.call("vt_init", local)

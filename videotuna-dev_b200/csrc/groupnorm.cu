@@ -16,6 +16,8 @@
 // dimension is what makes the TemporalTransformer's 5-D GroupNorm parallel: there the slab is (C/G) * t*h*w elements
 // (819 KB at VideoCrafter2 level 0) and only N*G = 64 slabs exist, i.e. 64 CTAs for 148 SMs in the first generation.
 #include <cstdlib>
+#include <mutex>
+#include <set>
 #include <cooperative_groups.h>
 #include <cuda_bf16.h>
 
@@ -706,11 +708,18 @@ BulkPlan plan_bulk(int N, int C, int S, int G, int streams, const void* p0, cons
 
 template <typename K, typename... Args>
 cudaError_t launch_cluster(K kernel, const BulkPlan& plan, int N, int G, cudaStream_t st, Args... args) {
-  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hard_smem()));
-  if (e != cudaSuccess) return e;
-  if (plan.CL > 8) {
-    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-    if (e != cudaSuccess) return e;
+  // function attributes once per kernel (keyed by its address: several instantiations share this template)
+  static std::mutex mu;
+  static std::set<const void*> configured;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (configured.find(reinterpret_cast<const void*>(kernel)) == configured.end()) {
+      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hard_smem()));
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+      if (e != cudaSuccess) return e;
+      configured.insert(reinterpret_cast<const void*>(kernel));
+    }
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(plan.CL, G, N);

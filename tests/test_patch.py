@@ -42,6 +42,32 @@ def test_lvdm_hook_falls_back_to_reference_on_cpu(shims):
 
 
 @needs_ref
+def test_lvdm_xformers_switch_is_covered(shims):
+    """The reference's spatial CrossAttention binds `self.forward = self.efficient_forward` when xformers is importable
+    (attention.py:98-99). Instances built after patch_lvdm() must bind the replacement; instances built before it are
+    fixed by rebind_lvdm_instances(); either way CPU fp32 inputs end in a reference body."""
+    import b200vt.patch as P
+    from videotuna.models.lvdm.modules import attention as A
+    original_eff = A.CrossAttention.efficient_forward
+    torch.manual_seed(0)
+    early = A.CrossAttention(query_dim=128, context_dim=None, heads=2, dim_head=64)
+    early.forward = early.efficient_forward  # what __init__ does with xformers installed
+    assert P.patch_lvdm()
+    assert A.CrossAttention.efficient_forward._b200vt_original is original_eff
+    late = A.CrossAttention(query_dim=128, context_dim=None, heads=2, dim_head=64)
+    late.forward = late.efficient_forward  # binds the patched class attribute
+    assert getattr(late.forward.__func__, "_b200vt_patched", False)
+    assert not getattr(early.forward.__func__, "_b200vt_patched", False)
+    holder = torch.nn.Sequential(early)
+    assert P.rebind_lvdm_instances(holder) == 1 and "forward" not in vars(early)
+    x = torch.randn(2, 30, 128)
+    want = A.CrossAttention.forward._b200vt_original(early, x)
+    torch.testing.assert_close(early(x), want)  # class-level patched forward -> Unsupported on CPU -> reference forward
+    P.unpatch_videotuna()
+    assert A.CrossAttention.efficient_forward is original_eff
+
+
+@needs_ref
 def test_hunyuan_and_wan_hooks_install_and_fall_back(shims):
     import importlib
     import b200vt.patch as P

@@ -51,15 +51,32 @@ def _try_import(name: str):
         return None
 
 
-def patch_lvdm(module=None) -> bool:
-    """CrossAttention.forward (videotuna/models/lvdm/modules/attention.py:101-170) -> functional.lvdm_cross_attention_forward.
-    Installed on the class, so instances that switched themselves to `efficient_forward` (xformers, :98-99) keep it."""
+def patch_lvdm(module=None, xformers_too: bool = True) -> bool:
+    """CrossAttention.forward (videotuna/models/lvdm/modules/attention.py:101-170) -> functional.lvdm_cross_attention_forward,
+    installed on the class. With xformers present the reference's spatial instances switch themselves to
+    `efficient_forward` at construction (`self.forward = self.efficient_forward`, :98-99): xformers_too=True also replaces
+    the class's `efficient_forward` (same signature; `Unsupported` inputs reach the original xformers body), so instances
+    built AFTER the patch bind ours; for models built before it call rebind_lvdm_instances(model)."""
     mod = module or _try_import("videotuna.models.lvdm.modules.attention")
     if mod is None:
         return False
     cls = mod.CrossAttention
     cls.forward = _wrap("lvdm.CrossAttention.forward", cls.forward, Fn.lvdm_cross_attention_forward)
+    if xformers_too and hasattr(cls, "efficient_forward"):
+        cls.efficient_forward = _wrap("lvdm.CrossAttention.efficient_forward", cls.efficient_forward,
+                                      Fn.lvdm_cross_attention_forward)
     return True
+
+
+def rebind_lvdm_instances(model: torch.nn.Module) -> int:
+    """Drop the instance-level `forward` that reference CrossAttention modules built before patch_lvdm() set on themselves
+    (the xformers switch, attention.py:98-99), so that the patched class attribute applies. Returns how many were reset."""
+    n = 0
+    for m in model.modules():
+        if type(m).__name__ == "CrossAttention" and "forward" in vars(m):
+            del vars(m)["forward"]
+            n += 1
+    return n
 
 
 def patch_hunyuan(modules=None) -> int:
@@ -224,10 +241,10 @@ def patch_videotuna(lvdm: bool = True, hunyuan: bool = True, wan: bool = True, b
 def unpatch_videotuna() -> None:
     """Restore every original callable (tests)."""
     for name, original in list(_ORIGINALS.items()):
-        if name == "lvdm.CrossAttention.forward":
+        if name in ("lvdm.CrossAttention.forward", "lvdm.CrossAttention.efficient_forward"):
             mod = _try_import("videotuna.models.lvdm.modules.attention")
             if mod is not None:
-                mod.CrossAttention.forward = original
+                setattr(mod.CrossAttention, name.rsplit(".", 1)[1], original)
         else:
             modname, attr = name.rsplit(".", 1)
             mod = _try_import(modname)

@@ -29,7 +29,22 @@ struct LibState {
 };
 LibState g_state;
 
+// The tensor-map encoder is a DRIVER entry point and needs a context current on the calling thread. PyTorch's autograd
+// worker threads select their device lazily (no cudaSetDevice until a runtime call needs it), so a backward entry point
+// reached without the dispatcher's device guard — the eager path of ops.py — can arrive with no context bound
+// (CUDA_ERROR_INVALID_CONTEXT from cuTensorMapEncodeTiled). One runtime call per thread binds the primary context of the
+// thread's current device.
+int bind_context_once() {
+  thread_local bool bound = false;
+  if (!bound) {
+    VT_CHECK_CUDA(cudaFree(nullptr));
+    bound = true;
+  }
+  return 0;
+}
+
 int ensure_init() {
+  if (int rc = bind_context_once()) return rc;
   std::lock_guard<std::mutex> lock(g_state.mu);
   if (g_state.ready) return g_state.init_rc;
   int dev = 0;

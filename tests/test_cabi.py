@@ -57,3 +57,28 @@ def test_no_cpu_fallback():
     q = torch.zeros(1, 128, 1, 128, dtype=torch.bfloat16)
     with pytest.raises((RuntimeError, NotImplementedError)):
         ops.attn_fwd(q, q, q, None, None, None, 128, 128, 0.1)
+
+
+def test_eager_fast_path_keeps_registered_ops_for_tracing():
+    """ops.* are thin callables (eager fast path, ops._make_eager) over the registered torch.library ops: under a dispatch
+    mode (here FakeTensorMode, as torch.compile / make_fx use) they must route through the registered op and its fake
+    kernel; on CPU tensors either path must raise (there is no CPU implementation)."""
+    import pytest
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+
+    import b200vt.ops as ops
+    assert callable(ops.attn_fwd) and hasattr(torch.ops.b200vt, "attn_fwd")
+    assert getattr(ops.attn_fwd, "op", ops.attn_fwd) is not None
+    assert ops._eager_ok((torch.randn(2), None, 3))
+    with FakeTensorMode():
+        x = torch.empty(2, 5, 64, dtype=torch.bfloat16, device="cuda")
+        sc = torch.empty(2, 64, dtype=torch.float32, device="cuda")
+        assert not ops._eager_ok((x,))
+        y, mean, rstd = ops.ln_modulate_fwd(x, None, None, sc, sc, 1e-6)
+        assert tuple(y.shape) == (2, 5, 64) and y.dtype == torch.bfloat16 and tuple(mean.shape) == (10,)
+        q = torch.empty(1, 40, 2, 64, dtype=torch.bfloat16, device="cuda")
+        o, lse = ops.attn_fwd(q, q, q, None, None, None, 40, 40, 0.125)
+        assert tuple(o.shape) == (1, 40, 2, 64) and tuple(lse.shape) == (1, 2, 40) and lse.dtype == torch.float32
+    with pytest.raises(RuntimeError):
+        ops.groupnorm_silu_fwd(torch.randn(2, 32, 4), None, None, 32, 1e-5, True)

@@ -182,6 +182,13 @@ int vt_groupnorm_silu_bwd(const void* dy, const void* x, const float* mean, cons
                           const float* gamma, const float* beta, float* dgamma, float* dbeta, int N, int C, int S, int G,
                           int apply_silu, int dtype, void* stream);
 
+#ifdef VT_EXPERIMENTS
+/* ---------------------------------------------------------------------------------------------------------------
+ * Not part of the product library: the hooks below exist only in builds made with -DVT_EXPERIMENTS
+ * (tools/build_variant.sh <out.so> -DVT_EXPERIMENTS; point the Python side at it with B200VT_LIB=<out.so>), together
+ * with the earlier kernel variants those builds keep selectable for A/B measurements (VT_FWD_KERNEL=pp|db,
+ * VT_TEMPORAL_SIMT=1, VT_GN_REG=1).
+ * ------------------------------------------------------------------------------------------------------------- */
 /* Self-test hook used by tests/: one 128x128x128 bf16 GEMM tile through TMA + tcgen05 with selectable operand
  * sources (see csrc/umma_probe.cu). Not part of the product path. */
 int vt_umma_probe(const void* a, const void* b, float* d, int a_mode, int b_mode, int n, uint32_t a_lbo, uint32_t a_sbo,
@@ -200,6 +207,8 @@ int vt_tma_reduce_rate(float* acc, int n_tiles, int iters, int depth, int spread
  * (bf16[n_tiles*128][128]); loads_out counts the boxes loaded meanwhile. */
 int vt_tma_mixed_rate(float* acc, const void* src_bf16, int n_tiles, int iters, int load_mode, int blocks,
                       long long* cycles_out, long long* loads_out, void* stream);
+
+#endif /* VT_EXPERIMENTS */
 
 #ifdef __cplusplus
 }

@@ -79,6 +79,54 @@ def sdpa_blhd(q: Tensor, k: Tensor, v: Tensor, attn_mask: Optional[Tensor] = Non
     return torch.einsum("bhij,bjhd->bihd", p, v)
 
 
+def attention_fwd_bwd_chunked(q: Tensor, k: Tensor, v: Tensor, do: Tensor, scale: Optional[float] = None,
+                              segments: Optional[Sequence[int]] = None, k_len: Optional[int] = None,
+                              chunk: int = 2048) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """sdpa_blhd + its analytic backward for ONE (sample, head): q, do (Lq, D), k, v (Lk, D) fp32 -> (o, lse, dq, dk, dv),
+    evaluated in chunks of `chunk` query rows so that the (Lq, Lk) score matrix never exists at once. This is the same
+    arithmetic as the reference's torch path (lvdm attention.py:128-144, hunyuan attenion.py:101-106 + autograd:
+    P = softmax(S), O = P V, dV = P^T dO, dP = dO V^T, dS = P o (dP - rowsum(dO o O)), dQ = dS K s, dK = dS^T Q s); it
+    exists so that the BASELINE.json sizes (119 056 tokens: a 57 GB score matrix per head) can be compared on the GPU
+    box in fp32 (tests/test_gpu_attention_fullsize.py). Runs on whatever device the inputs live on; pinned to
+    sdpa_blhd + autograd on CPU by tests/test_oracle_golden.py.
+    segments: packed varlen boundaries (cu_seqlens of attenion.py:34-57) — row i attends key j iff same segment, rows /
+    keys outside every segment give zeros; k_len: keys >= k_len are masked (wan attention.py:62-71)."""
+    Lq, D = q.shape
+    Lk = k.shape[0]
+    scale = 1.0 / math.sqrt(D) if scale is None else scale
+    dev = q.device
+    seg_q = seg_k = None
+    if segments is not None:
+        cu = [int(c) for c in segments]
+        seg_q = torch.full((Lq,), -1, dtype=torch.long, device=dev)
+        seg_k = torch.full((Lk,), -2, dtype=torch.long, device=dev)
+        for s_ in range(len(cu) - 1):
+            seg_q[cu[s_]:cu[s_ + 1]] = s_
+            seg_k[cu[s_]:cu[s_ + 1]] = s_
+    o = torch.zeros_like(q)
+    lse = torch.full((Lq,), float("-inf"), dtype=q.dtype, device=dev)
+    dq, dk, dv = torch.zeros_like(q), torch.zeros_like(k), torch.zeros_like(v)
+    for r0 in range(0, Lq, chunk):
+        r1 = min(Lq, r0 + chunk)
+        s = (q[r0:r1] @ k.T) * scale
+        if seg_q is not None:
+            s = s.masked_fill(seg_q[r0:r1, None] != seg_k[None, :], float("-inf"))
+        if k_len is not None:
+            s[:, k_len:] = float("-inf")
+        l = torch.logsumexp(s, dim=-1)
+        p = torch.exp(s - l.masked_fill(torch.isinf(l), 0.0)[:, None])  # fully masked rows: exp(-inf) = 0
+        lse[r0:r1] = l
+        oc = p @ v
+        o[r0:r1] = oc
+        doc = do[r0:r1]
+        dv += p.T @ doc
+        dp = doc @ v.T
+        ds = p * (dp - (doc * oc).sum(dim=-1, keepdim=True))
+        dq[r0:r1] = (ds @ k) * scale
+        dk += (ds.T @ q[r0:r1]) * scale
+    return o, lse, dq, dk, dv
+
+
 def hunyuan_attention_torch(q: Tensor, k: Tensor, v: Tensor, attn_mask: Optional[Tensor] = None) -> Tensor:
     """hunyuan/hyvideo_t2v/modules/attenion.py:101-106,151-156 (mode="torch"): q,k,v (B,S,H,D) -> (B,S,H*D).
     pre: transpose(1,2); SDPA(attn_mask); post: transpose back; reshape(b, s, -1)."""

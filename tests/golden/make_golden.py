@@ -1,7 +1,8 @@
 """Generate tests/golden/*.pt by running the UNMODIFIED reference code (/root/reference) on seeded CPU inputs.
 
-Run in the development container only (`python tests/golden/make_golden.py`); the GPU box has no /root/reference and
-only reads the committed fixtures. Import shims cover wheels that are absent here: colorama,
+Run in the development container only (`python tests/golden/make_golden.py`; `--check` regenerates everything in
+memory and diffs it bit for bit against the committed fixtures); the GPU box has no /root/reference and only reads the
+committed fixtures. Import shims cover wheels that are absent here: colorama,
 omegaconf, diffusers — none of them takes part in the arithmetic being recorded.
 """
 from __future__ import annotations
@@ -45,6 +46,8 @@ def install_shims():
     sys.modules.setdefault("diffusers.models", difm)
     sys.modules.setdefault("diffusers.models.modeling_utils", difmu)
     sys.modules.setdefault("diffusers.configuration_utils", difc)
+    # hyvideo_i2v/utils/helpers.py:11 imports deepspeed at module level; nothing on the block path uses it
+    sys.modules.setdefault("deepspeed", types.ModuleType("deepspeed"))
 
 
 def dezero(module: torch.nn.Module, gen: torch.Generator):
@@ -68,9 +71,40 @@ def _compact(obj):
     return obj
 
 
+CHECK = False      # --check: compare with the committed fixtures instead of writing them
+MISMATCHES = []
+
+
+def _diff(a, b, path, out):
+    if isinstance(a, torch.Tensor):
+        if not (isinstance(b, torch.Tensor) and a.dtype == b.dtype and a.shape == b.shape and torch.equal(a, b)):
+            out.append(path)
+    elif isinstance(a, dict):
+        if not isinstance(b, dict) or set(a) != set(b):
+            out.append(path + " (keys)")
+        else:
+            for k in a:
+                _diff(a[k], b[k], f"{path}.{k}", out)
+    elif isinstance(a, (list, tuple)):
+        if not isinstance(b, (list, tuple)) or len(a) != len(b):
+            out.append(path + " (len)")
+        else:
+            for i, (x, y) in enumerate(zip(a, b)):
+                _diff(x, y, f"{path}[{i}]", out)
+    elif a != b:
+        out.append(path)
+
+
 def save(name, obj):
     path = os.path.join(OUT, name + ".pt")
-    torch.save(_compact(obj), path)
+    obj = _compact(obj)
+    if CHECK:
+        bad = []
+        _diff(obj, torch.load(path, map_location="cpu"), name, bad)
+        MISMATCHES.extend(bad)
+        print(f"{name}: {'bit-identical' if not bad else 'DIFFERS at ' + ', '.join(bad[:6])}")
+        return
+    torch.save(obj, path)
     print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
 
 
@@ -100,7 +134,15 @@ def sd(module):
             for k, v in module.state_dict().items()}
 
 
-def golden_lvdm(gen):
+def _seeded(offset: int) -> torch.Generator:
+    """Module constructors draw their initial weights from the GLOBAL generator: every fixture function re-seeds it and
+    owns a private generator for its inputs, so each fixture regenerates bit-identically whatever ran before it."""
+    torch.manual_seed(SEED + offset)
+    return torch.Generator().manual_seed(SEED + offset)
+
+
+def golden_lvdm():
+    gen = _seeded(0)
     from videotuna.models.lvdm.modules import attention as A
     assert not A.XFORMERS_IS_AVAILBLE
     cases = {}
@@ -165,7 +207,7 @@ def golden_lvdm_temporal():
     """Temporal self-attention as VideoCrafter2/DynamiCrafter configure it (no relative position): plain and with the
     causal mask TemporalTransformer builds (attention.py:487-489). Own generator so earlier fixtures stay unchanged."""
     from videotuna.models.lvdm.modules import attention as A
-    gen = torch.Generator().manual_seed(SEED + 7)
+    gen = _seeded(7)
     cases = {}
     kw = dict(query_dim=128, context_dim=None, heads=2, dim_head=64, temporal_length=16)
     m = round_params(A.CrossAttention(**kw))
@@ -176,14 +218,16 @@ def golden_lvdm_temporal():
                                     out=m(xt, mask=mask.expand(40, -1, -1)).detach())
     xg = xt.clone().requires_grad_(True)
     do = RN(40, 16, 128, generator=gen)
-    out = m(xg, mask=mask.expand(40, -1, -1))
-    out.backward(do)
+    with torch.enable_grad():
+        out = m(xg, mask=mask.expand(40, -1, -1))
+        out.backward(do)
     cases["temporal_causal"].update(dout=do, dx=xg.grad.detach(),
                                     dw_q=m.to_q.weight.grad.detach().clone(), dw_v=m.to_v.weight.grad.detach().clone())
     save("lvdm_temporal_attention", cases)
 
 
-def golden_hunyuan(gen):
+def golden_hunyuan():
+    gen = _seeded(1)
     M = importlib.import_module("videotuna.models.hunyuan.hyvideo_t2v.modules.models")
     att = importlib.import_module("videotuna.models.hunyuan.hyvideo_t2v.modules.attenion")
     pos = importlib.import_module("videotuna.models.hunyuan.hyvideo_t2v.modules.posemb_layers")
@@ -256,7 +300,8 @@ def golden_hunyuan(gen):
                                 txt_out=txt_o.detach(), single_out=sgl_o.detach()))
 
 
-def golden_wan(gen):
+def golden_wan():
+    gen = _seeded(2)
     pkg = types.ModuleType("wan_ref_modules")
     pkg.__path__ = [os.path.join(REF, "videotuna/models/wan/wan/modules")]
     sys.modules["wan_ref_modules"] = pkg
@@ -313,7 +358,7 @@ def golden_block_grads():
     """Forward + backward of whole reference blocks (fp32, CPU) on the state dicts and inputs of the fixtures above, plus
     a ResBlock: outputs, input gradients and a few parameter gradients for the block-level drop-ins (b200vt.blocks).
     Own generator; reads hunyuan_blocks.pt / wan_block.pt / lvdm_transformers.pt, so run after the others."""
-    gen = torch.Generator().manual_seed(SEED + 11)
+    gen = _seeded(11)
     out = {}
 
     def load(name):
@@ -440,16 +485,172 @@ def golden_block_grads():
     save("block_grads", out)
 
 
+def golden_hunyuan_i2v():
+    """The i2v twins of the Hunyuan blocks (hyvideo_i2v/modules/models.py:136-297, 371-462) called the way
+    HYVideoDiffusionTransformer.forward calls them — 11 positional arguments (:749-761, 776-788) — once as T2V
+    (condition_type None) and once with the "token_replace" first-frame modulation (modulate_layers.py:37-96), forward and
+    backward."""
+    gen = _seeded(21)
+    M = importlib.import_module("videotuna.models.hunyuan.hyvideo_i2v.modules.models")
+    pos = importlib.import_module("videotuna.models.hunyuan.hyvideo_i2v.modules.posemb_layers")
+    hidden, heads, ff = 128, 2, 40  # head dim 64; 40 = one latent frame of the (3, 4, 10) token grid
+    dbl = M.MMDoubleStreamBlock(hidden, heads, mlp_width_ratio=1.0, qk_norm=True, qk_norm_type="rms", qkv_bias=True)
+    sgl = M.MMSingleStreamBlock(hidden, heads, mlp_width_ratio=1.0, qk_norm=True, qk_norm_type="rms")
+    dezero(dbl, gen)
+    dezero(sgl, gen)
+    with torch.no_grad():
+        for mm in (dbl, sgl):
+            for n_, p_ in mm.named_parameters():
+                if n_.endswith("norm.weight"):
+                    p_.copy_(1 + 0.1 * RN(p_.shape, generator=gen))
+    round_params(dbl)
+    round_params(sgl)
+    cos, sin = pos.get_nd_rotary_pos_embed([8, 28, 28], (3, 4, 10), theta=256, use_real=True, theta_rescale_factor=1)
+    cu = torch.tensor([0, 140, 150], dtype=torch.int32)
+    segm = torch.zeros(150, dtype=torch.long)
+    segm[140:] = 1
+    bmask = (segm[:, None] == segm[None, :])[None, None]
+    orig = M.attention
+    M.attention = lambda q_, k_, v_, **kw: orig(q_, k_, v_, mode="torch", attn_mask=bmask)
+    out = dict(hidden=hidden, heads=heads, mlp_width_ratio=1.0, dbl_sd=sd(dbl), sgl_sd=sd(sgl), cu_seqlens=cu, cos=cos,
+               sin=sin, first_frame_tokens=ff)
+    pnames_d = ["img_attn_qkv.weight", "img_mod.linear.bias", "img_attn_k_norm.weight"]
+    pnames_s = ["linear1.bias", "modulation.linear.bias", "linear2.weight"]
+    try:
+        with torch.enable_grad():
+            base = dict(img=RN(1, 120, hidden, generator=gen), txt=RN(1, 30, hidden, generator=gen),
+                        vec=RN(1, hidden, generator=gen), trv=RN(1, hidden, generator=gen))
+            d_io, d_to = RN(1, 120, hidden, generator=gen), RN(1, 30, hidden, generator=gen)
+            d_so = RN(1, 150, hidden, generator=gen)
+            out.update(base, d_img_out=d_io, d_txt_out=d_to, d_single_out=d_so)
+            for tag, cond in (("t2v", None), ("tr", "token_replace")):
+                img, txt, vec, trv = (base[k].clone().requires_grad_(True) for k in ("img", "txt", "vec", "trv"))
+                dbl.zero_grad()
+                io, to = dbl(img, txt, vec, cu, cu, 150, 150, (cos, sin), cond, trv if cond else None, ff if cond else None)
+                torch.autograd.backward([io, to], [d_io, d_to])
+                rec = dict(img_out=io.detach(), txt_out=to.detach(), d_img=img.grad.clone(), d_txt=txt.grad.clone(),
+                           d_vec=vec.grad.clone(),
+                           **{n: dict(dbl.named_parameters())[n].grad.detach().to(torch.bfloat16) for n in pnames_d})
+                if cond:
+                    rec["d_trv"] = trv.grad.clone()
+                out["double_" + tag] = rec
+                x = torch.cat([base["img"], base["txt"]], 1).clone().requires_grad_(True)
+                vec2, trv2 = base["vec"].clone().requires_grad_(True), base["trv"].clone().requires_grad_(True)
+                sgl.zero_grad()
+                so = sgl(x, vec2, 30, cu, cu, 150, 150, (cos, sin), cond, trv2 if cond else None, ff if cond else None)
+                so.backward(d_so)
+                rec = dict(out=so.detach(), d_x=x.grad.clone(), d_vec=vec2.grad.clone(),
+                           **{n: dict(sgl.named_parameters())[n].grad.detach().to(torch.bfloat16) for n in pnames_s})
+                if cond:
+                    rec["d_trv"] = trv2.grad.clone()
+                out["single_" + tag] = rec
+    finally:
+        M.attention = orig
+    save("hunyuan_i2v_blocks", out)
+
+
+def golden_wan_i2v_cross():
+    """WanI2VCrossAttention (wan/modules/model.py:184-225): 257 CLIP image tokens + text tokens, forward and backward."""
+    gen = _seeded(22)
+    pkg = types.ModuleType("wan_ref_modules")
+    pkg.__path__ = [os.path.join(REF, "videotuna/models/wan/wan/modules")]
+    sys.modules["wan_ref_modules"] = pkg
+    model = importlib.import_module("wan_ref_modules.model")
+
+    def sdpa_flash(q, k, v, q_lens=None, k_lens=None, dropout_p=0.0, softmax_scale=None, q_scale=None, causal=False,
+                   window_size=(-1, -1), deterministic=False, dtype=torch.bfloat16, version=None):
+        mask = None
+        if k_lens is not None:  # flash_attention packs the first k_lens[b] keys of every sample (attention.py:62-71)
+            mask = (torch.arange(k.shape[1])[None, :] < k_lens[:, None])[:, None, None, :]
+        o = torch.nn.functional.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2),
+                                                             attn_mask=mask)
+        return o.transpose(1, 2).contiguous()
+
+    model.flash_attention = sdpa_flash
+    dim, heads = 256, 2
+    m = model.WanI2VCrossAttention(dim, heads, qk_norm=True, eps=1e-6)
+    with torch.no_grad():
+        for n_, p_ in m.named_parameters():
+            if n_.startswith("norm") and n_.endswith("weight"):
+                p_.copy_(1 + 0.1 * RN(p_.shape, generator=gen))
+    round_params(m)
+    x = RN(2, 60, dim, generator=gen).requires_grad_(True)
+    ctx = RN(2, 257 + 24, dim, generator=gen).requires_grad_(True)
+    lens = torch.tensor([24, 17])
+    d_y = RN(2, 60, dim, generator=gen)
+    with torch.enable_grad():
+        y = m(x, ctx, lens)
+        y.backward(d_y)
+    params = dict(m.named_parameters())
+    save("wan_i2v_cross", dict(dim=dim, heads=heads, sd=sd(m), x=x.detach().clone(), context=ctx.detach().clone(),
+                               context_lens=lens, out=y.detach(), d_out=d_y, d_x=x.grad.clone(),
+                               d_context=ctx.grad.clone(),
+                               **{n: params[n].grad.detach().clone() for n in ("norm_k_img.weight", "norm_q.weight")},
+                               **{n: params[n].grad.detach().to(torch.bfloat16) for n in ("k_img.weight", "v.weight")}))
+
+
+def golden_lvdm_extra():
+    """TemporalConvBlock (openaimodel3d.py:258-310: four GroupNorm(32) + SiLU + Conv3d stages) forward + backward, and the
+    VideoCrafter1 relative-position temporal attention (attention.py:19-42, 129-133, 145-148) forward + backward."""
+    gen = _seeded(23)
+    from videotuna.models.lvdm.modules import attention as A
+    from videotuna.models.lvdm.modules.networks import openaimodel3d as O3
+    tc = O3.TemporalConvBlock(64, out_channels=64, dropout=0.0)
+    dezero(tc, gen)
+    with torch.no_grad():
+        for n_, p_ in tc.named_parameters():
+            if n_.endswith(".0.weight"):
+                p_.copy_(1 + 0.1 * RN(p_.shape, generator=gen))
+            if n_.endswith(".0.bias"):
+                p_.copy_(0.1 * RN(p_.shape, generator=gen))
+    round_params(tc)
+    x = r16(RN(2, 64, 8, 5, 6, generator=gen) * 1.5 + 0.3).requires_grad_(True)
+    d_y = RN(2, 64, 8, 5, 6, generator=gen)
+    with torch.enable_grad():
+        y = tc(x)
+        y.backward(d_y)
+    params = dict(tc.named_parameters())
+    out = dict(tconv=dict(channels=64, sd=sd(tc), x=x.detach().clone(), out=y.detach(), d_out=d_y, d_x=x.grad.clone(),
+                          **{n: params[n].grad.detach().clone() for n in ("conv1.0.weight", "conv3.0.bias", "conv2.3.bias")}))
+
+    kw = dict(query_dim=128, context_dim=None, heads=2, dim_head=64, relative_position=True, temporal_length=16)
+    m = A.CrossAttention(**kw)
+    round_params(m)
+    xt = RN(12, 16, 128, generator=gen)
+    mask = torch.tril(torch.ones(1, 16, 16))
+    d_o = RN(12, 16, 128, generator=gen)
+    rel = {}
+    with torch.enable_grad():
+        for tag, mk in (("plain", None), ("causal", mask.expand(12, -1, -1))):
+            xg = xt.clone().requires_grad_(True)
+            m.zero_grad()
+            o = m(xg, mask=mk)
+            o.backward(d_o)
+            p_ = dict(m.named_parameters())
+            rel[tag] = dict(out=o.detach(), d_x=xg.grad.clone(),
+                            d_rel_k=p_["relative_position_k.embeddings_table"].grad.detach().clone(),
+                            d_rel_v=p_["relative_position_v.embeddings_table"].grad.detach().clone(),
+                            d_to_q=p_["to_q.weight"].grad.detach().clone())
+    out["relpos"] = dict(kw=kw, sd=sd(m), x=xt, mask=mask, d_out=d_o, **rel)
+    save("lvdm_extra", out)
+
+
 def main():
+    global CHECK
+    CHECK = "--check" in sys.argv
     install_shims()
-    torch.manual_seed(SEED)
-    gen = torch.Generator().manual_seed(SEED)
     torch.set_grad_enabled(False)
-    golden_lvdm(gen)
-    golden_hunyuan(gen)
-    golden_wan(gen)
+    golden_lvdm()
+    golden_hunyuan()
+    golden_wan()
     golden_lvdm_temporal()
     golden_block_grads()
+    golden_hunyuan_i2v()
+    golden_wan_i2v_cross()
+    golden_lvdm_extra()
+    if CHECK:
+        print("check:", "all fixtures regenerate bit-identically" if not MISMATCHES else f"{len(MISMATCHES)} mismatches")
+        raise SystemExit(1 if MISMATCHES else 0)
 
 
 if __name__ == "__main__":

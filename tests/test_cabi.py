@@ -6,8 +6,11 @@ import re
 from conftest import ROOT
 
 
-def declared_symbols():
+def declared_symbols(experiments: bool = False):
+    """Entry points the header declares for the product build (or, experiments=True, only inside #ifdef VT_EXPERIMENTS)."""
     text = open(os.path.join(ROOT, "include", "b200vt.h")).read()
+    exp = re.search(r"#ifdef VT_EXPERIMENTS(.*?)#endif /\* VT_EXPERIMENTS \*/", text, flags=re.S)
+    text = exp.group(1) if experiments else text.replace(exp.group(0), "")
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(?:int|int64_t)\s+(vt_[a-z0-9_]+)\s*\(", text)))
 
@@ -22,6 +25,17 @@ def test_library_exports_every_declared_symbol():
     lib = L.lib()
     missing = [s for s in declared_symbols() if not hasattr(lib, s)]
     assert not missing, f"declared in b200vt.h but not exported: {missing}"
+
+
+def test_product_library_exports_no_experiment_hooks():
+    """Microbenchmark / probe hooks and the earlier kernel variants live behind -DVT_EXPERIMENTS (tools/build_variant.sh);
+    the in-tree product library must not carry them."""
+    import b200vt._lib as L
+    if os.environ.get("B200VT_LIB"):
+        return  # an A/B build was selected on purpose
+    exp = declared_symbols(experiments=True)
+    assert set(exp) == set(L._EXPERIMENT_SIGS) and len(exp) == 4
+    assert not [s for s in exp if hasattr(L.lib(), s)] and not L.has_experiments()
 
 
 def test_binding_table_matches_header():

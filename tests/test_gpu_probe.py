@@ -21,7 +21,10 @@ def _expected(a, b, a_mode, b_mode, n):
 @pytest.mark.parametrize("a_mode,b_mode,n", [(0, 0, 128), (0, 0, 64), (0, 1, 128), (0, 1, 64), (2, 1, 128), (2, 1, 64),
                                              (2, 0, 128), (1, 1, 128), (1, 0, 128)])
 def test_umma_probe(a_mode, b_mode, n):
+    import b200vt._lib as L
     import b200vt.ops as ops
+    if not L.has_experiments():
+        pytest.skip("vt_umma_probe exists only in -DVT_EXPERIMENTS builds (tools/build_variant.sh + B200VT_LIB)")
     a, b = _mk(a_mode * 10 + b_mode)
     kmaj = (16, 1024, 32)          # K-major SW128: LBO ignored, SBO = 8 rows * 128 B, 32 B per 16-element k-step
     mnmaj = (16384, 1024, 2048)    # MN-major SW128: LBO = next 64-wide box, SBO = next 8 k-rows, 16 k-rows per step

@@ -113,3 +113,28 @@ def test_lvdm_cross_attention_all_variants():
     for name, case in cases.items():
         err = R.max_rel_err(_lvdm_cross_attention(case), case["out"])
         assert err < 5e-5, (name, err)
+
+
+def test_chunked_attention_reference_equals_explicit_softmax_and_autograd():
+    # oracle.attention_fwd_bwd_chunked (used at the BASELINE sizes on the GPU box) against sdpa_blhd + autograd, with
+    # the two-segment varlen mask of the golden fixture, a key-length mask, ragged chunking, and rows outside every segment
+    g = load_golden("hunyuan_attention")
+    q, k, v = (f32(g[n])[0, :, 1].contiguous() for n in ("q", "k", "v"))  # one sample, one head: (150, D)
+    gen = torch.Generator().manual_seed(5)
+    do = torch.randn(q.shape, generator=gen)
+    for segments, k_len in (([0, 140, 150], None), (None, 131), (None, None), ([0, 100, 120], None)):
+        n = 150 if segments is None else segments[-1]  # rows / keys past the last segment take no part
+        qr, kr, vr = (t[:n].clone().requires_grad_(True) for t in (q, k, v))
+        mask = None
+        if segments is not None:
+            mask = R.varlen_block_mask(segments, n)[None, None]
+        if k_len is not None:
+            mask = (torch.arange(n) < k_len)[None, None, None, :]
+        out = R.sdpa_blhd(qr[None, :, None], kr[None, :, None], vr[None, :, None], mask)[0, :, 0]
+        out.backward(do[:n])
+        o, lse, dq, dk, dv = R.attention_fwd_bwd_chunked(q, k, v, do, segments=segments, k_len=k_len, chunk=64)
+        assert R.max_rel_err(o[:n], out.detach()) < TOL
+        for got, want in ((dq, qr.grad), (dk, kr.grad), (dv, vr.grad)):
+            assert R.max_rel_err(got[:n], want) < TOL
+            assert n == 150 or float(got[n:].abs().max()) == 0.0
+        assert n == 150 or float(o[n:].abs().max()) == 0.0

@@ -128,6 +128,54 @@ def test_block_hooks_install_fall_back_and_restore(shims):
             M.MMDoubleStreamBlock.forward) == originals
 
 
+@needs_ref
+def test_hunyuan_i2v_blocks_enter_the_fast_path_with_11_positionals(shims, monkeypatch):
+    """HunyuanVideoFlow drives T2V and I2V through the i2v DiT, whose forward passes condition_type, token_replace_vec and
+    frist_frame_token_num positionally to every block (hyvideo_i2v/modules/models.py:749-761, 776-788). The patched
+    forwards must reach the drop-in bodies with that call (round 1 rejected it before the body ran); on CPU tensors the
+    body then raises Unsupported and the original forward produces the reference result."""
+    import importlib
+    import b200vt.blocks as Bk
+    import b200vt.functional as Fn
+    import b200vt.patch as P
+    M = importlib.import_module("videotuna.models.hunyuan.hyvideo_i2v.modules.models")
+    entered = []
+
+    def spy(name, real):
+        def f(self, *a, **k):
+            entered.append((name, len(a), a[8] if len(a) > 8 else None))
+            return real(self, *a, **k)
+        return f
+
+    monkeypatch.setattr(Bk, "hunyuan_double_block_forward", spy("double", Bk.hunyuan_double_block_forward))
+    monkeypatch.setattr(Bk, "hunyuan_single_block_forward", spy("single", Bk.hunyuan_single_block_forward))
+    torch.manual_seed(0)
+    dbl = M.MMDoubleStreamBlock(128, 2, mlp_width_ratio=1.0, qk_norm=True, qk_norm_type="rms", qkv_bias=True)
+    sgl = M.MMSingleStreamBlock(128, 2, mlp_width_ratio=1.0, qk_norm=True, qk_norm_type="rms")
+    img, txt, vec, trv = torch.randn(1, 40, 128), torch.randn(1, 8, 128), torch.randn(1, 128), torch.randn(1, 128)
+    cu = torch.tensor([0, 48, 48], dtype=torch.int32)
+    orig_attn = M.attention
+    M.attention = lambda q_, k_, v_, **kw: orig_attn(q_, k_, v_, mode="torch")
+    try:
+        want = {c: (dbl(img, txt, vec, cu, cu, 48, 48, None, c, trv, 10),
+                    sgl(torch.cat([img, txt], 1), vec, 8, cu, cu, 48, 48, None, c, trv, 10))
+                for c in (None, "token_replace")}
+        assert P.patch_blocks(lvdm=False, wan=False)["hunyuan"] >= 4
+        for c in (None, "token_replace"):
+            entered.clear()
+            got_d = dbl(img, txt, vec, cu, cu, 48, 48, None, c, trv, 10)
+            got_s = sgl(torch.cat([img, txt], 1), vec, 8, cu, cu, 48, 48, None, c, trv, 10)
+            assert entered == [("double", 11, c), ("single", 11, c)]
+            torch.testing.assert_close(got_d, want[c][0], rtol=0, atol=0)  # CPU -> Unsupported -> reference forward
+            torch.testing.assert_close(got_s, want[c][1], rtol=0, atol=0)
+        # the drop-in refuses what it cannot do BEFORE touching anything: token_replace without its vector
+        with pytest.raises(Fn.Unsupported):
+            Bk._token_replace("token_replace", None, 10)
+        assert Bk._token_replace(None, trv, 10) == 0 and Bk._token_replace("token_replace", trv, 10) == 10
+    finally:
+        M.attention = orig_attn
+
+
 def test_diffusers_processors_are_installed_by_duck_typing():
     """set_diffusers_processors() keys on the stock processor's class name and the `set_processor` protocol only
     (diffusers is not installed here); anything unsupported goes back to the stock processor."""

@@ -48,6 +48,9 @@ _SIGS = {
                               vp],
     "vt_groupnorm_silu_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                               vp],
+}
+# Present only in -DVT_EXPERIMENTS builds of the library (tools/build_variant.sh + B200VT_LIB); see include/b200vt.h.
+_EXPERIMENT_SIGS = {
     "vt_umma_rate": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp],
     "vt_tma_reduce_rate": [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp],
     "vt_tma_mixed_rate": [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp],
@@ -77,7 +80,7 @@ def lib() -> C.CDLL:
                 f"{LIB_PATH} is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(needs nvcc with sm_100a support). b200vt has no CPU or PyTorch fallback.")
         handle = C.CDLL(LIB_PATH)
-        for name, argtypes in _SIGS.items():
+        for name, argtypes in {**_SIGS, **_EXPERIMENT_SIGS}.items():
             try:
                 fn = getattr(handle, name)
             except AttributeError:
@@ -128,6 +131,11 @@ def call(name: str, *args):
 
 def exported_symbols() -> list[str]:
     return [n for n in _SIGS if hasattr(lib(), n)]
+
+
+def has_experiments() -> bool:
+    """True when the loaded library was built with -DVT_EXPERIMENTS (microbenchmark hooks, earlier kernel variants)."""
+    return hasattr(lib(), "vt_umma_probe")
 
 
 def strides3(t, dims=(0, 1, 2)):

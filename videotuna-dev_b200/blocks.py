@@ -39,6 +39,17 @@ def _is_identity(m) -> bool:
     return isinstance(m, nn.Identity)
 
 
+def _bf16_consumer(*linears) -> None:
+    """The row kernels emit bf16 for the Linear that follows. That is what the reference computes under bf16 autocast or
+    with bf16 weights; an fp32 model run WITHOUT autocast (plain fp32 inference) must stay on the reference path — handing
+    its fp32 Linear a bf16 tensor raises a dtype error instead of falling back."""
+    if torch.is_autocast_enabled():
+        return
+    for lin in linears:
+        w = getattr(lin, "weight", None)
+        _require(w is None or w.dtype == _BF16, "fp32 weights without autocast stay on the reference path")
+
+
 def _rms_weight(norm) -> Tuple[Optional[Tensor], float]:
     """(weight, eps) of a reference RMSNorm (hunyuan norm_layers.py:5-59, wan model.py:70-86); Identity -> (None, 0)."""
     if _is_identity(norm):
@@ -85,12 +96,40 @@ def _hy_attention(self, q, k, v, img_len, cu_seqlens_q, cu_seqlens_kv, max_seqle
                                       cu_seqlens_q=cu_seqlens_q, cu_seqlens_kv=cu_seqlens_kv)
 
 
+def _token_replace(condition_type, token_replace_vec, frist_frame_token_num) -> int:
+    """Number of leading image rows modulated with the token_replace vectors (hyvideo_i2v/modules/models.py:150-152:
+    only condition_type == "token_replace" switches the i2v twins away from the t2v arithmetic)."""
+    if condition_type != "token_replace":
+        return 0
+    _require(token_replace_vec is not None and frist_frame_token_num is not None and int(frist_frame_token_num) > 0,
+             "token_replace needs token_replace_vec and a positive frist_frame_token_num")
+    return int(frist_frame_token_num)
+
+
+def _linear2_split(linear2: nn.Module, attn: Tensor, mlp_act: Tensor) -> Tensor:
+    """linear2(cat(attn, mlp_act)) (models.py:390) without the concatenation: the weight is applied as two column
+    blocks. Anything but a plain nn.Linear (e.g. a LoRA wrapper around linear2) keeps the module call."""
+    if type(linear2) is not nn.Linear:
+        return linear2(torch.cat((attn, mlp_act), 2))
+    c = attn.shape[-1]
+    w = linear2.weight
+    out = torch.nn.functional.linear(attn, w[:, :c], linear2.bias)
+    B, S, _ = out.shape
+    return torch.addmm(out.view(B * S, -1), mlp_act.reshape(B * S, -1), w[:, c:].t()).view(B, S, -1)
+
+
 def hunyuan_double_block_forward(self, img: Tensor, txt: Tensor, vec: Tensor, cu_seqlens_q: Optional[Tensor] = None,
                                  cu_seqlens_kv: Optional[Tensor] = None, max_seqlen_q: Optional[int] = None,
-                                 max_seqlen_kv: Optional[int] = None, freqs_cis: tuple = None):
-    """Drop-in body of MMDoubleStreamBlock.forward. Per stream: one LayerNorm+modulate pass, the module's own fused QKV
-    Linear, one RMSNorm+RoPE pass each over the q and k views of its output (no fp32 temporaries, no rotate_half
-    copies), joint varlen attention, and the two gated residuals as single passes."""
+                                 max_seqlen_kv: Optional[int] = None, freqs_cis: tuple = None,
+                                 condition_type: Optional[str] = None, token_replace_vec: Optional[Tensor] = None,
+                                 frist_frame_token_num: Optional[int] = None):
+    """Drop-in body of MMDoubleStreamBlock.forward — the t2v signature (hyvideo_t2v/modules/models.py:132-143) and the
+    i2v twin's, which the new-style flow uses for T2V and I2V alike and always calls with 11 positionals
+    (hyvideo_i2v/modules/models.py:136-149, 749-761). Per stream: one LayerNorm+modulate pass, the module's own fused QKV
+    Linear, per-head RMSNorm (+RoPE) of q and k written directly into the joint [img; txt] tensors (no fp32 temporaries,
+    no rotate_half copies, no torch.cat), joint varlen attention, and the two gated residuals as single passes.
+    condition_type == "token_replace": the first frist_frame_token_num image rows take the modulation vectors computed
+    from token_replace_vec (modulate_layers.py:37-96 of the i2v package)."""
     _require(img.is_cuda and img.dtype == _BF16 and txt.dtype == _BF16, "bf16 CUDA activations only")
     _require(cu_seqlens_q is not None and cu_seqlens_kv is not None, "the block needs cu_seqlens (as the reference asserts)")
     B, L, C = img.shape
@@ -100,25 +139,28 @@ def hunyuan_double_block_forward(self, img: Tensor, txt: Tensor, vec: Tensor, cu
     _require(D in (64, 128), f"head dim {D} stays on the reference path")
     assert cu_seqlens_q.shape[0] == 2 * B + 1, f"cu_seqlens_q.shape:{cu_seqlens_q.shape}, img.shape[0]:{B}"
     cos, sin = freqs_cis if freqs_cis is not None else (None, None)
+    ff = _token_replace(condition_type, token_replace_vec, frist_frame_token_num)
+    _bf16_consumer(self.img_attn_qkv, self.txt_attn_qkv)
 
     i_sh1, i_sc1, i_g1, i_sh2, i_sc2, i_g2 = self.img_mod(vec).chunk(6, dim=-1)
     t_sh1, t_sc1, t_g1, t_sh2, t_sc2, t_g2 = self.txt_mod(vec).chunk(6, dim=-1)
+    r_sh1 = r_sc1 = r_g1 = r_sh2 = r_sc2 = r_g2 = None
+    if ff:
+        r_sh1, r_sc1, r_g1, r_sh2, r_sc2, r_g2 = self.img_mod(token_replace_vec).chunk(6, dim=-1)
 
-    img_qkv = self.img_attn_qkv(Fn.ln_modulate(img, shift=i_sh1, scale=i_sc1, eps=self.img_norm1.eps)).view(B, L, 3, H, D)
+    img_qkv = self.img_attn_qkv(Fn.ln_modulate(img, i_sh1, i_sc1, eps=self.img_norm1.eps, tr_shift=r_sh1, tr_scale=r_sc1,
+                                               first_frame_tokens=ff)).view(B, L, 3, H, D)
     txt_qkv = self.txt_attn_qkv(Fn.ln_modulate(txt, shift=t_sh1, scale=t_sc1, eps=self.txt_norm1.eps)).view(B, T, 3, H, D)
-    img_q = _hy_qk(img_qkv[:, :, 0], self.img_attn_q_norm, cos, sin)
-    img_k = _hy_qk(img_qkv[:, :, 1], self.img_attn_k_norm, cos, sin)
-    txt_q = _hy_qk(txt_qkv[:, :, 0], self.txt_attn_q_norm, None, None)
-    txt_k = _hy_qk(txt_qkv[:, :, 1], self.txt_attn_k_norm, None, None)
-    q = torch.cat((img_q, txt_q), dim=1)
-    k = torch.cat((img_k, txt_k), dim=1)
-    v = torch.cat((img_qkv[:, :, 2], txt_qkv[:, :, 2]), dim=1)
+    q, k, v = Fn.hunyuan_joint_qkv(img_qkv, txt_qkv, self.img_attn_q_norm, self.img_attn_k_norm, self.txt_attn_q_norm,
+                                   self.txt_attn_k_norm, cos, sin)
 
     attn = _hy_attention(self, q, k, v, L, cu_seqlens_q, cu_seqlens_kv, max_seqlen_q, max_seqlen_kv, B)
     img_attn, txt_attn = attn[:, :L], attn[:, L:]
 
-    img = Fn.gate_residual(img, self.img_attn_proj(img_attn), i_g1)
-    img = Fn.gate_residual(img, self.img_mlp(Fn.ln_modulate(img, shift=i_sh2, scale=i_sc2, eps=self.img_norm2.eps)), i_g2)
+    img = Fn.gate_residual(img, self.img_attn_proj(img_attn), i_g1, tr_gate=r_g1, first_frame_tokens=ff)
+    img = Fn.gate_residual(img, self.img_mlp(Fn.ln_modulate(img, i_sh2, i_sc2, eps=self.img_norm2.eps, tr_shift=r_sh2,
+                                                            tr_scale=r_sc2, first_frame_tokens=ff)),
+                           i_g2, tr_gate=r_g2, first_frame_tokens=ff)
     txt = Fn.gate_residual(txt, self.txt_attn_proj(txt_attn), t_g1)
     txt = Fn.gate_residual(txt, self.txt_mlp(Fn.ln_modulate(txt, shift=t_sh2, scale=t_sc2, eps=self.txt_norm2.eps)), t_g2)
     return img, txt
@@ -126,9 +168,13 @@ def hunyuan_double_block_forward(self, img: Tensor, txt: Tensor, vec: Tensor, cu
 
 def hunyuan_single_block_forward(self, x: Tensor, vec: Tensor, txt_len: int, cu_seqlens_q: Optional[Tensor] = None,
                                  cu_seqlens_kv: Optional[Tensor] = None, max_seqlen_q: Optional[int] = None,
-                                 max_seqlen_kv: Optional[int] = None, freqs_cis: Tuple[Tensor, Tensor] = None) -> Tensor:
-    """Drop-in body of MMSingleStreamBlock.forward: RoPE covers the first S - txt_len tokens only, which the fused kernel
-    expresses through the table length, so the reference's split / rotate / cat of q and k disappears."""
+                                 max_seqlen_kv: Optional[int] = None, freqs_cis: Tuple[Tensor, Tensor] = None,
+                                 condition_type: Optional[str] = None, token_replace_vec: Optional[Tensor] = None,
+                                 frist_frame_token_num: Optional[int] = None) -> Tensor:
+    """Drop-in body of MMSingleStreamBlock.forward (t2v models.py:326-393; i2v twin :371-462 with its three extra
+    arguments): RoPE covers the first S - txt_len tokens only, which the fused kernel expresses through the table length,
+    so the reference's split / rotate / cat of q and k disappears; linear2 runs on its two operands without the
+    concatenation."""
     _require(x.is_cuda and x.dtype == _BF16, "bf16 CUDA activations only")
     _require(cu_seqlens_q is not None and cu_seqlens_kv is not None, "the block needs cu_seqlens (as the reference asserts)")
     B, S, C = x.shape
@@ -137,20 +183,26 @@ def hunyuan_single_block_forward(self, x: Tensor, vec: Tensor, txt_len: int, cu_
     _require(D in (64, 128), f"head dim {D} stays on the reference path")
     assert cu_seqlens_q.shape[0] == 2 * B + 1, f"cu_seqlens_q.shape:{cu_seqlens_q.shape}, x.shape[0]:{B}"
     cos = sin = None
-    if freqs_cis is not None:
+    if freqs_cis is not None and freqs_cis[0] is not None:
         cos, sin = freqs_cis
         _require(cos.shape[0] == S - txt_len, "RoPE table must cover exactly the image tokens")
+    ff = _token_replace(condition_type, token_replace_vec, frist_frame_token_num)
+    _bf16_consumer(self.linear1)
 
     sh, sc, gate = self.modulation(vec).chunk(3, dim=-1)
-    lin = self.linear1(Fn.ln_modulate(x, shift=sh, scale=sc, eps=self.pre_norm.eps))
+    r_sh = r_sc = r_gate = None
+    if ff:
+        r_sh, r_sc, r_gate = self.modulation(token_replace_vec).chunk(3, dim=-1)
+    lin = self.linear1(Fn.ln_modulate(x, sh, sc, eps=self.pre_norm.eps, tr_shift=r_sh, tr_scale=r_sc,
+                                      first_frame_tokens=ff))
     qkv = lin[..., : 3 * C].unflatten(-1, (3, H, D))
     mlp = lin[..., 3 * C:]
     q = _hy_qk(qkv[:, :, 0], self.q_norm, cos, sin)
     k = _hy_qk(qkv[:, :, 1], self.k_norm, cos, sin)
     v = qkv[:, :, 2]
     attn = _hy_attention(self, q, k, v, S - txt_len, cu_seqlens_q, cu_seqlens_kv, max_seqlen_q, max_seqlen_kv, B)
-    out = self.linear2(torch.cat((attn, self.mlp_act(mlp)), 2))
-    return Fn.gate_residual(x, out, gate)
+    out = _linear2_split(self.linear2, attn, self.mlp_act(mlp))
+    return Fn.gate_residual(x, out, gate, tr_gate=r_gate, first_frame_tokens=ff)
 
 
 # =====================================================================================================================
@@ -258,6 +310,7 @@ def wan_attention_block_forward(self, x: Tensor, e: Tensor, seq_lens, grid_sizes
     the next Linear consumes, every gated residual is one read-modify-write pass."""
     _require(x.is_cuda and x.dtype in (_BF16, torch.float32) and x.dim() == 3, "CUDA bf16/fp32 (B,L,C) activations only")
     assert e.dtype == torch.float32
+    _bf16_consumer(self.self_attn.q, self.ffn[0])
     e6 = (self.modulation.float() + e).chunk(6, dim=1)  # six (B, 1, C) fp32 tensors
 
     y = self.self_attn(Fn.ln_modulate(x, shift=e6[0], scale=e6[1], eps=self.norm1.eps), seq_lens, grid_sizes, freqs)
@@ -272,6 +325,8 @@ def wan_attention_block_forward(self, x: Tensor, e: Tensor, seq_lens, grid_sizes
 # =====================================================================================================================
 def _lvdm_ln(norm: nn.LayerNorm, x: Tensor) -> Tensor:
     _require(x.is_cuda and x.dtype in (_BF16, torch.float32) and x.shape[-1] % 8 == 0, "CUDA bf16/fp32 activations only")
+    _require(x.dtype == _BF16 or torch.is_autocast_enabled() or norm.weight.dtype == _BF16,
+             "fp32 activations with fp32 weights and no autocast stay on the reference path")
     return Fn.layer_norm(x, norm.weight, norm.bias, norm.eps)
 
 
@@ -456,6 +511,9 @@ def cogvideox_block_forward(self, hidden_states: Tensor, encoder_hidden_states: 
     return hidden_states, encoder_hidden_states
 
 
+_KEY_LENS_CACHE: dict = {}
+
+
 class HunyuanVideoAttnProcessor:
     """Protocol of diffusers 0.32.2 `HunyuanVideoAttnProcessor2_0` (reference call site: hyvideo_t2v/hunyuanvideo.py:209,
     946-955): video tokens first; double-stream blocks (attn.add_q_proj present) project the text stream separately,
@@ -472,10 +530,19 @@ class HunyuanVideoAttnProcessor:
         if m.dim() == 4:
             m = m[:, 0, 0]
         _require(m.shape == (B, S), "unsupported mask shape")
-        lens = m.sum(dim=1).to(torch.int32)
-        # a key-padding mask must be a prefix of ones for key lengths to express it
-        _require(bool((m == (torch.arange(S, device=m.device)[None] < lens[:, None])).all()), "non-prefix mask")
-        return lens
+        # The denoiser passes the SAME mask tensor to every block of every step: validate it (one host sync) and turn it
+        # into key lengths once per tensor, not once per attention call.
+        key = (m.data_ptr(), tuple(m.shape), m._version, str(m.device))
+        hit = _KEY_LENS_CACHE.get(key)
+        if hit is None:
+            lens = m.sum(dim=1).to(torch.int32)
+            # a key-padding mask must be a prefix of ones for key lengths to express it
+            ok = bool((m == (torch.arange(S, device=m.device)[None] < lens[:, None])).all())
+            if len(_KEY_LENS_CACHE) > 64:
+                _KEY_LENS_CACHE.clear()
+            hit = _KEY_LENS_CACHE[key] = (lens if ok else None, m)  # keep m alive: the key holds its address
+        _require(hit[0] is not None, "non-prefix mask")
+        return hit[0]
 
     def __call__(self, attn, hidden_states: Tensor, encoder_hidden_states: Optional[Tensor] = None,
                  attention_mask: Optional[Tensor] = None, image_rotary_emb=None) -> Tuple[Tensor, Optional[Tensor]]:

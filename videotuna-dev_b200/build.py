@@ -40,6 +40,8 @@ def _digest() -> str:
     h = hashlib.sha256()
     for root in (CSRC, os.path.join(os.path.dirname(HERE), "include")):
         for f in sorted(os.listdir(root)):
+            if not os.path.isfile(os.path.join(root, f)):
+                continue
             with open(os.path.join(root, f), "rb") as fh:
                 h.update(f.encode())
                 h.update(fh.read())

@@ -25,6 +25,7 @@
 #include <math_constants.h>
 
 #include "attn_common.h"
+#include "capi_util.h"
 #include "sm100_ptx.cuh"
 
 namespace vt {
@@ -682,11 +683,10 @@ cudaError_t launch_bwd_one(const CUtensorMap& tm_q, const CUtensorMap& tm_k, con
                            const CUtensorMap& tm_do, const CUtensorMap& tm_dq, float* dq_acc, int Lq_total,
                            const AttnBwdParams& p, cudaStream_t stream) {
   using C = BwdCfg<D>;
-  static bool configured = false;
-  if (!configured) {
+  static char cfg_site;  // per call site; the attribute is per DEVICE (first_on_device)
+  if (first_on_device(&cfg_site)) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<D, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::BYTES);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   dim3 grid((p.seq.Lk + 127) / 128, p.seq.H, p.seq.nprob);
   attn_bwd_kernel<D, DIRECT><<<grid, C::THREADS, C::BYTES, stream>>>(tm_q, tm_k, tm_v, tm_do, tm_dq, dq_acc, Lq_total, p);

@@ -26,6 +26,7 @@
 #include <math_constants.h>
 
 #include "attn_common.h"
+#include "capi_util.h"
 #include "sm100_ptx.cuh"
 
 // Of every 8 exponential pairs, how many run on the FMA pipe (ex2_poly2). With both softmax sets busy the loop is
@@ -417,11 +418,10 @@ attn_fwd_alt_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
 cudaError_t launch_attn_fwd_alt(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
                                 const AttnFwdParams& p, cudaStream_t stream) {
   using C = AltCfg;
-  static bool configured = false;  // benign race: attribute set is idempotent
-  if (!configured) {
+  static char cfg_site;  // per call site; the attribute is per DEVICE (first_on_device)
+  if (first_on_device(&cfg_site)) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_alt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::BYTES);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   dim3 grid((p.seq.Lq + 127) / 128, p.seq.H, p.seq.nprob);
   attn_fwd_alt_kernel<<<grid, C::THREADS, C::BYTES, stream>>>(tm_q, tm_k, tm_v, p);

@@ -21,6 +21,7 @@
 #include <math_constants.h>
 
 #include "attn_common.h"
+#include "capi_util.h"
 #include "sm100_ptx.cuh"
 
 #ifndef VT_FWD_EMU
@@ -386,6 +387,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant_
 // softmax throughput of one tile (two threads per row, packed f32x2 math, part of exp2 on the FMA pipe).
 // Warps 0-7 softmax (half = key columns [64*hf, 64*hf+64)), warp 8 TMA producer (K ring of 3, V ring of 2), warp 9
 // issuer. O is rescaled by the softmax threads only when the row max grew by > 2^8 (lazy), after waiting for PV(j-1).
+enum : uint32_t { TAG_PV_DONE = 0x110, TAG_FWD_ALIGN };
+
+#ifdef VT_EXPERIMENTS  // one-tile kernel with S double-buffered in TMEM: an earlier variant kept for A/B builds
 template <int D>
 struct FwdDbCfg {
   static constexpr int KCH = D / 64;
@@ -405,7 +409,6 @@ struct FwdDbCfg {
   static constexpr uint32_t T_S = 0, T_O = 256;
 };
 
-enum : uint32_t { TAG_PV_DONE = 0x110, TAG_FWD_ALIGN };
 
 template <int D>
 __global__ void __launch_bounds__(FwdDbCfg<D>::THREADS, 1)
@@ -691,6 +694,8 @@ attn_fwd_db_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_consta
 // complete long before its softmax warps finish the current one: they never wait, and the kernel runs at the SM's
 // softmax throughput (MUFU + FMA-pipe exponentials of both tiles overlapped) instead of at the chain latency.
 // Warps 0-7 / 8-15: softmax of tile 0 / 1 (two threads per row), warp 16 TMA producer, warp 17 MMA issuer.
+#endif  // VT_EXPERIMENTS
+
 template <int D>
 struct FwdRotCfg {
   static_assert(D == 64, "three S buffers + two O tiles fit TMEM only at head dim 64");
@@ -1007,41 +1012,41 @@ template <int D>
 cudaError_t launch_rot(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v, const AttnFwdParams& p,
                        cudaStream_t stream) {
   using C = FwdRotCfg<D>;
-  static bool configured = false;
-  if (!configured) {
+  static char cfg_site;  // per call site; the attribute is per DEVICE (first_on_device)
+  if (first_on_device(&cfg_site)) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_rot_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::BYTES);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   dim3 grid((p.seq.Lq + 255) / 256, p.seq.H, p.seq.nprob);
   attn_fwd_rot_kernel<D><<<grid, C::THREADS, C::BYTES, stream>>>(tm_q, tm_k, tm_v, p);
   return cudaGetLastError();
 }
 
+#ifdef VT_EXPERIMENTS
 template <int D>
 cudaError_t launch_db(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v, const AttnFwdParams& p,
                       cudaStream_t stream) {
   using C = FwdDbCfg<D>;
-  static bool configured = false;
-  if (!configured) {
+  static char cfg_site;  // per call site; the attribute is per DEVICE (first_on_device)
+  if (first_on_device(&cfg_site)) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_db_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::BYTES);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   dim3 grid((p.seq.Lq + 127) / 128, p.seq.H, p.seq.nprob);
   attn_fwd_db_kernel<D><<<grid, C::THREADS, C::BYTES, stream>>>(tm_q, tm_k, tm_v, p);
   return cudaGetLastError();
 }
 
+#endif  // VT_EXPERIMENTS
+
 template <int D, int NQ>
 cudaError_t launch_one(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
                        const AttnFwdParams& p, cudaStream_t stream) {
   using C = FwdCfg<D, NQ>;
-  static bool configured = false;  // benign race: attribute set is idempotent
-  if (!configured) {
+  static char cfg_site;  // per call site; the attribute is per DEVICE (first_on_device)
+  if (first_on_device(&cfg_site)) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<D, NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::BYTES);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   dim3 grid((p.seq.Lq + NQ * 128 - 1) / (NQ * 128), p.seq.H, p.seq.nprob);
   attn_fwd_kernel<D, NQ><<<grid, C::THREADS, C::BYTES, stream>>>(tm_q, tm_k, tm_v, p);
@@ -1052,28 +1057,32 @@ cudaError_t launch_one(const CUtensorMap& tm_q, const CUtensorMap& tm_k, const C
 
 cudaError_t launch_attn_fwd(int D, const CUtensorMap& tm_q, const CUtensorMap& tm_k, const CUtensorMap& tm_v,
                             const AttnFwdParams& p, int q_tiles_hint, cudaStream_t stream) {
-  // Default: the two-tile ping-pong kernel (K1: 1153 TFLOP/s). VT_FWD_KERNEL=db selects the one-tile kernel with S
-  // double-buffered in TMEM (K1: 1100 TFLOP/s; its softmax warps never wait for the tensor pipe, but with one tile
-  // per CTA nothing overlaps the exp phase, so it is MUFU-latency bound at ~1600 cycles per 128 keys).
-  static const bool use_db = [] { const char* e = getenv("VT_FWD_KERNEL"); return e != nullptr && e[0] == 'd'; }();
-  if (use_db && q_tiles_hint == 0) {
-    if (D == 128) return launch_db<128>(tm_q, tm_k, tm_v, p, stream);
-    if (D == 64) return launch_db<64>(tm_q, tm_k, tm_v, p, stream);
+#ifdef VT_EXPERIMENTS
+  // A/B builds only (tools/build_variant.sh -DVT_EXPERIMENTS): VT_FWD_KERNEL=db selects the one-tile kernel with S
+  // double-buffered in TMEM, VT_FWD_KERNEL=pp the two-tile ping-pong kernel. Neither has the fused exchange epilogue, so
+  // a scatter launch (p.sc_n > 0) never takes them.
+  static const char fwd_sel = [] { const char* e = getenv("VT_FWD_KERNEL"); return e != nullptr ? e[0] : '\0'; }();
+  if (p.sc_n == 0) {
+    const bool single_x = (q_tiles_hint == 1) || (q_tiles_hint == 0 && p.seq.Lq <= 128);
+    if (fwd_sel == 'd' && q_tiles_hint == 0) {
+      if (D == 128) return launch_db<128>(tm_q, tm_k, tm_v, p, stream);
+      if (D == 64) return launch_db<64>(tm_q, tm_k, tm_v, p, stream);
+    }
+    if (D == 128 && (fwd_sel == 'p' || q_tiles_hint != 0))
+      return single_x ? launch_one<128, 1>(tm_q, tm_k, tm_v, p, stream) : launch_one<128, 2>(tm_q, tm_k, tm_v, p, stream);
+    if (D == 64 && fwd_sel == 'p' && !single_x) return launch_one<64, 2>(tm_q, tm_k, tm_v, p, stream);
   }
-  // One query tile per CTA when the (max) query length fits a single 128-row tile; two otherwise.
-  const bool single = (q_tiles_hint == 1) || (q_tiles_hint == 0 && p.seq.Lq <= 128);
-  if (D == 128) {
-    // Head dim 128: one tile per CTA, three rotating S buffers, two alternating softmax sets (attn_fwd_alt_sm100.cu).
-    // VT_FWD_KERNEL=pp keeps the two-tile ping-pong kernel for A/B measurements.
-    static const bool use_pp128 = [] { const char* e = getenv("VT_FWD_KERNEL"); return e != nullptr && e[0] == 'p'; }();
-    if (!use_pp128 && q_tiles_hint == 0) return launch_attn_fwd_alt(tm_q, tm_k, tm_v, p, stream);
-    return single ? launch_one<128, 1>(tm_q, tm_k, tm_v, p, stream) : launch_one<128, 2>(tm_q, tm_k, tm_v, p, stream);
-  }
+#endif
+  (void)q_tiles_hint;
+  // Head dim 128: one tile per CTA, three rotating S buffers, two alternating softmax sets (attn_fwd_alt_sm100.cu) — the
+  // only kernel with the fused Ulysses exchange epilogue.
+  if (D == 128) return launch_attn_fwd_alt(tm_q, tm_k, tm_v, p, stream);
   if (D == 64) {
-    // Head dim 64, two tiles: the rotating-S kernel (K3: see DESIGN.md §4.1). VT_FWD_KERNEL=pp keeps the ping-pong kernel.
-    static const bool use_pp = [] { const char* e = getenv("VT_FWD_KERNEL"); return e != nullptr && e[0] == 'p'; }();
-    if (single) return launch_one<64, 1>(tm_q, tm_k, tm_v, p, stream);
-    return use_pp ? launch_one<64, 2>(tm_q, tm_k, tm_v, p, stream) : launch_rot<64>(tm_q, tm_k, tm_v, p, stream);
+    if (p.sc_n > 0) return cudaErrorNotSupported;  // capi.cu rejects this earlier (VT_ERR_UNSUPPORTED)
+    // One query tile per CTA when the (max) query length fits a single 128-row tile; otherwise two tiles sharing three
+    // rotating S buffers (K3: see DESIGN.md §4.1).
+    if (p.seq.Lq <= 128) return launch_one<64, 1>(tm_q, tm_k, tm_v, p, stream);
+    return launch_rot<64>(tm_q, tm_k, tm_v, p, stream);
   }
   return cudaErrorInvalidValue;
 }

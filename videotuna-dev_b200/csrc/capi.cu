@@ -35,38 +35,49 @@ LibState g_state;
 // (CUDA_ERROR_INVALID_CONTEXT from cuTensorMapEncodeTiled). One runtime call per thread binds the primary context of the
 // thread's current device.
 int bind_context_once() {
-  thread_local bool bound = false;
-  if (!bound) {
+  thread_local int bound_dev = -1;  // the device whose primary context this thread last bound
+  int dev = 0;
+  VT_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev != bound_dev) {
     VT_CHECK_CUDA(cudaFree(nullptr));
-    bound = true;
+    bound_dev = dev;
   }
+  return 0;
+}
+
+// Per-device part of the initialisation: the compute-capability check and the watchdog pointer, which lives in a
+// __device__ symbol of every attention translation unit (one copy per device).
+int ensure_device_init() {
+  static char site;
+  if (!first_on_device(&site)) return 0;
+  int dev = 0;
+  VT_CHECK_CUDA(cudaGetDevice(&dev));
+  int major = 0, minor = 0;
+  VT_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  VT_CHECK_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (major != 10) return fail(VT_ERR_UNSUPPORTED, "device %d is sm_%d%d; libb200vt needs sm_100", dev, major, minor);
+  VT_CHECK_CUDA(attn_fwd_set_debug_ptr(g_state.dbg_dev));
+  VT_CHECK_CUDA(attn_bwd_set_debug_ptr(g_state.dbg_dev));
+  VT_CHECK_CUDA(attn_fwd_alt_set_debug_ptr(g_state.dbg_dev));
   return 0;
 }
 
 int ensure_init() {
   if (int rc = bind_context_once()) return rc;
   std::lock_guard<std::mutex> lock(g_state.mu);
-  if (g_state.ready) return g_state.init_rc;
-  int dev = 0;
-  VT_CHECK_CUDA(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  VT_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
-  if (prop.major != 10) return fail(VT_ERR_UNSUPPORTED, "device %d is sm_%d%d; libb200vt needs sm_100", dev, prop.major, prop.minor);
+  if (g_state.ready) return g_state.init_rc != 0 ? g_state.init_rc : ensure_device_init();
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   VT_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   if (qres != cudaDriverEntryPointSuccess || fn == nullptr)
     return fail(VT_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled not available from the driver");
   g_state.encode = reinterpret_cast<EncodeTiledFn>(fn);
-  VT_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_state.dbg_host), 64, cudaHostAllocMapped));
+  VT_CHECK_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_state.dbg_host), 64, cudaHostAllocMapped | cudaHostAllocPortable));
   std::memset(g_state.dbg_host, 0, 64);
   VT_CHECK_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_state.dbg_dev), g_state.dbg_host, 0));
-  VT_CHECK_CUDA(attn_fwd_set_debug_ptr(g_state.dbg_dev));
-  VT_CHECK_CUDA(attn_bwd_set_debug_ptr(g_state.dbg_dev));
-  VT_CHECK_CUDA(attn_fwd_alt_set_debug_ptr(g_state.dbg_dev));
   g_state.ready = true;
   g_state.init_rc = 0;
-  return 0;
+  return ensure_device_init();
 }
 
 }  // namespace

@@ -4,6 +4,9 @@
 #include <cstdint>
 #include <cstdio>
 #include <cuda_runtime.h>
+#include <mutex>
+#include <set>
+#include <utility>
 
 #include "../../include/b200vt.h"
 
@@ -35,6 +38,18 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
   do {                                                  \
     if (!(cond)) return ::vt::fail(code, __VA_ARGS__);  \
   } while (0)
+
+// True the first time `site` is seen on the calling thread's current device. Function attributes
+// (cudaFuncAttributeMaxDynamicSharedMemorySize, cluster opt-in) and __device__ symbols are PER DEVICE: a process that
+// drives several GPUs must configure every kernel once on each of them.
+inline bool first_on_device(const void* site) {
+  static std::mutex mu;
+  static std::set<std::pair<const void*, int>> seen;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  return seen.insert({site, dev}).second;
+}
 
 inline unsigned cdiv(long long a, long long b) { return static_cast<unsigned>((a + b - 1) / b); }
 

@@ -183,6 +183,7 @@ groupnorm_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, float* __restri
   }
 }
 
+#ifdef VT_EXPERIMENTS
 // EXPERIMENT (off unless VT_GN_REG is set; measured SLOWER: 116 vs 79 us on the VC2 level-0 tensor, because ~100 registers x
 // 512 threads leave one CTA per SM while the two-pass kernel keeps four). Register-resident single pass for slabs of at most THREADS * NVEC vectors (every VideoCrafter2 level at its own
 // channel count: 6 400 .. 25 600 elements): the slab is read from HBM once, kept in registers across the statistics, and
@@ -259,6 +260,7 @@ bool launch_gn_fwd_reg(const T* x, T* y, float* mean, float* rstd, const float* 
     return false;
   return true;
 }
+#endif  // VT_EXPERIMENTS
 
 // z = xh*gamma + beta; y = silu(z) or z; gz = dy * silu'(z); gh = gz * gamma
 // dx = rstd * (gh - mean_g(gh) - xh * mean_g(gh * xh)); dgamma[c] += sum gz*xh; dbeta[c] += sum gz
@@ -709,17 +711,11 @@ BulkPlan plan_bulk(int N, int C, int S, int G, int streams, const void* p0, cons
 template <typename K, typename... Args>
 cudaError_t launch_cluster(K kernel, const BulkPlan& plan, int N, int G, cudaStream_t st, Args... args) {
   // function attributes once per kernel (keyed by its address: several instantiations share this template)
-  static std::mutex mu;
-  static std::set<const void*> configured;
-  {
-    std::lock_guard<std::mutex> lock(mu);
-    if (configured.find(reinterpret_cast<const void*>(kernel)) == configured.end()) {
-      cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hard_smem()));
-      if (e != cudaSuccess) return e;
-      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-      if (e != cudaSuccess) return e;
-      configured.insert(reinterpret_cast<const void*>(kernel));
-    }
+  if (first_on_device(reinterpret_cast<const void*>(kernel))) {  // function attributes are per device
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(hard_smem()));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(plan.CL, G, N);
@@ -769,21 +765,25 @@ int vt_groupnorm_silu_fwd(const void* x, void* y, float* mean, float* rstd, cons
   dim3 grid(G, N);
   if (dtype == 0) {
     const int vec_ok = (S % 8 == 0) && aligned16(x) && aligned16(y);
+#ifdef VT_EXPERIMENTS
     if (vec_ok && getenv("VT_GN_REG") != nullptr && launch_gn_fwd_reg<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), mean,
                                                    rstd, gamma, beta, N, C, S, G, eps, apply_silu, st)) {
       VT_CHECK_CUDA(cudaGetLastError());
       return 0;
     }
+#endif
     groupnorm_fwd_kernel<__nv_bfloat16><<<grid, GN_THREADS, 0, st>>>(
         static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), mean, rstd, gamma, beta, C, S, G, eps,
         apply_silu, vec_ok);
   } else {
     const int vec_ok = (S % 4 == 0) && aligned16(x) && aligned16(y);
+#ifdef VT_EXPERIMENTS
     if (vec_ok && getenv("VT_GN_REG") != nullptr && launch_gn_fwd_reg<float>(static_cast<const float*>(x), static_cast<float*>(y), mean, rstd, gamma, beta, N, C, S,
                                            G, eps, apply_silu, st)) {
       VT_CHECK_CUDA(cudaGetLastError());
       return 0;
     }
+#endif
     groupnorm_fwd_kernel<float><<<grid, GN_THREADS, 0, st>>>(static_cast<const float*>(x), static_cast<float*>(y), mean,
                                                              rstd, gamma, beta, C, S, G, eps, apply_silu, vec_ok);
   }

@@ -557,11 +557,10 @@ int launch_fwd(const XT* x, bf16* y, float* mean, float* rstd, const float* gamm
   // per thread for that and stay on the one-row kernel. VT_LN_ROWS=1 selects the one-row kernel for A/B measurements.
   static const bool one_row = sizeof(XT) == 4 || (getenv("VT_LN_ROWS") != nullptr && atoi(getenv("VT_LN_ROWS")) == 1);
   const int smem = (2 * CP + (one_row ? 4 : 8) * (T / 32)) * 4;
-  static bool configured = false;
-  if (!configured) {
+  static char cfg_site;  // per call site; the attribute is per DEVICE (first_on_device)
+  if (first_on_device(&cfg_site)) {
     VT_CHECK_CUDA(cudaFuncSetAttribute(ln_fwd_kernel<XT, T, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     VT_CHECK_CUDA(cudaFuncSetAttribute(ln_fwd2_kernel<XT, T, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   if (one_row) {
     static const int want1 = getenv("VT_LN1_CTAS") != nullptr ? atoi(getenv("VT_LN1_CTAS")) : 8;
@@ -584,10 +583,9 @@ int launch_bwd(const bf16* dy, const XT* x, const float* mean, const float* rstd
                int C, cudaStream_t st) {
   constexpr int CP = T * VPT * 8;
   const int smem = (CP * (1 + ((MODE & 1) ? 2 : 0) + ((MODE & 2) ? 1 : 0)) + 2 * (T / 32) * 2) * 4;
-  static bool configured = false;
-  if (!configured) {
+  static char cfg_site;  // per call site; the attribute is per DEVICE (first_on_device)
+  if (first_on_device(&cfg_site)) {
     VT_CHECK_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<XT, T, VPT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
   }
   // grid CTAs per SM (each flushes its column sums with atomics at the end): measured best 64 for bf16 rows (K1: 89 -> 93.5 %
   // of the copy bandwidth) and 4 for the fp32 rows of the Wan stream (98.7 %; 64 there: 87 %)
@@ -626,11 +624,10 @@ int ln_fwd_fast(const void* x, void* y, float* mean, float* rstd, const float* g
   if (ring_ok && x_dtype == 1 && C > 4096 && C <= 6144 && C % 8 == 0 && aligned16(x)) {
     constexpr int T = 256, VPT = 3;  // 512 x 2 measured slower (68 vs 79 %)
     const int smem = (3 * C + 2 * C) * 4;
-    static bool configured = false;
-    if (!configured) {
+    static char cfg_site;  // per call site; the attribute is per DEVICE (first_on_device)
+    if (first_on_device(&cfg_site)) {
       VT_CHECK_CUDA(cudaFuncSetAttribute(ln_fwd_ring_f32_kernel<T, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          5 * 6144 * 4));
-      configured = true;
     }
     static const int want = getenv("VT_LNR_CTAS") != nullptr ? atoi(getenv("VT_LNR_CTAS")) : 2;
     dim3 grid(ln_grid_x(L, B, want), B);
@@ -921,11 +918,10 @@ template <int NORM, int VPT, int D>
 int launch_rope_bulk(const bf16* x, bf16* y, float* rstd, const float* w, const float* c, const float* s, const int64_t* xs,
                      const int64_t* ys, int B, int L, int H, int L_rope, float eps, cudaStream_t st) {
   const int smem = ROPE_STAGES * (H * D * 2 + 2 * D * 4);
-  static bool configured = false;
-  if (!configured) {
+  static char cfg_site;  // per call site; the attribute is per DEVICE (first_on_device)
+  if (first_on_device(&cfg_site)) {
     VT_CHECK_CUDA(cudaFuncSetAttribute(rope_fwd_bulk_kernel<NORM, VPT, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        ROPE_STAGES * (5120 * 2 + 2 * 128 * 4)));
-    configured = true;
   }
   // Grid: many more CTAs than are resident (96 per SM, ~8 tokens each at K1). The token -> CTA assignment is static; with
   // one wave of exactly-resident CTAs the kernel ran at 83 % of the copy bandwidth, with 8 / 24 / 96 per SM at 89 / 96 /
@@ -1108,11 +1104,10 @@ int launch_rope_bwd_bulk(const bf16* dy, const bf16* x, const float* rstd, bf16*
   const int C = H * D;
   const int stage = C * 2 + (NORM != 0 ? C * 2 : 0) + 2 * D * 4 + (NORM == 1 ? ((H * 4 + 15) & ~15) : 0);
   const int smem = ROPE_STAGES * stage;
-  static bool configured = false;
-  if (!configured) {
+  static char cfg_site;  // per call site; the attribute is per DEVICE (first_on_device)
+  if (first_on_device(&cfg_site)) {
     VT_CHECK_CUDA(cudaFuncSetAttribute(rope_bwd_bulk_kernel<NORM, VPT, D>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        ROPE_STAGES * (5120 * 4 + 2 * 128 * 4 + 512)));
-    configured = true;
   }
   // 48 CTAs per SM of grid (see launch_rope_bulk); the full-row norm flushes C weight-gradient atomics per CTA: fewer there
   static const int want_b = getenv("VT_ROPE_CTAS_B") != nullptr ? atoi(getenv("VT_ROPE_CTAS_B")) : (NORM == 2 ? 8 : 48);

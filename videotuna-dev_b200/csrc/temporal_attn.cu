@@ -18,8 +18,10 @@
 namespace vt {
 namespace {
 
-constexpr int kWarps = 8;       // (sequence, head) pairs in flight per CTA (fewer when N = 32, D = 128 would not fit)
 constexpr int kMaxN = 32;
+
+#ifdef VT_EXPERIMENTS  // first-generation SIMT kernel (VT_TEMPORAL_SIMT=1 in A/B builds); the product path is temporal_attn_mma.cu
+constexpr int kWarps = 8;       // (sequence, head) pairs in flight per CTA (fewer when N = 32, D = 128 would not fit)
 
 // Per-warp shared memory, sized by the ACTUAL sequence length N (not the 32-token maximum): for N = 16, D = 64 that is
 // 7.4 KB (forward) / 10.6 KB (backward) instead of 25 KB, which is what bounds the number of resident warps — with the
@@ -245,6 +247,8 @@ cudaError_t launch(const TemporalArgs& a, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+#endif  // VT_EXPERIMENTS
+
 int check(const void* q, const void* k, const void* v, int B, int N, int H, int D, const int64_t* const* strides,
           int nstr) {
   VT_REQUIRE(q && k && v, VT_ERR_NULL, "temporal attention: NULL tensor");
@@ -258,6 +262,7 @@ int check(const void* q, const void* k, const void* v, int B, int N, int H, int 
   return 0;
 }
 
+#ifdef VT_EXPERIMENTS
 void fill(TemporalArgs& a, const int64_t* qs, const int64_t* ks, const int64_t* vs) {
   for (int i = 0; i < 3; ++i) {
     a.q_s[i] = qs[i];
@@ -265,6 +270,7 @@ void fill(TemporalArgs& a, const int64_t* qs, const int64_t* ks, const int64_t* 
     a.v_s[i] = vs[i];
   }
 }
+#endif
 
 }  // namespace
 }  // namespace vt
@@ -288,11 +294,15 @@ extern "C" int vt_temporal_attn_fwd(const void* q, const void* k, const void* v,
   if (int rc = check(q, k, v, B, N, H, D, strides, 4)) return rc;
   VT_REQUIRE(o != nullptr, VT_ERR_NULL, "o is NULL");
   VT_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(o), VT_ERR_ALIGN, "tensors must be 16-byte aligned");
-  if (getenv("VT_TEMPORAL_SIMT") == nullptr) {  // default: the tensor-core (mma.sync) forward
+#ifdef VT_EXPERIMENTS
+  if (getenv("VT_TEMPORAL_SIMT") == nullptr)
+#endif
+  {  // the tensor-core (mma.sync) forward
     VT_CHECK_CUDA(temporal_attn_fwd_mma(q, k, v, o, mask, q_strides, k_strides, v_strides, o_strides, B, N, H, D,
                                         softmax_scale, static_cast<cudaStream_t>(stream)));
     return 0;
   }
+#ifdef VT_EXPERIMENTS
   TemporalArgs a{};
   a.q = static_cast<const __nv_bfloat16*>(q);
   a.k = static_cast<const __nv_bfloat16*>(k);
@@ -306,6 +316,7 @@ extern "C" int vt_temporal_attn_fwd(const void* q, const void* k, const void* v,
   auto st = static_cast<cudaStream_t>(stream);
   VT_CHECK_CUDA(D == 64 ? (launch<64, false>(a, st)) : (launch<128, false>(a, st)));
   return 0;
+#endif
 }
 
 extern "C" int vt_temporal_attn_bwd(const void* dout, const void* q, const void* k, const void* v, void* dq, void* dk,
@@ -317,11 +328,15 @@ extern "C" int vt_temporal_attn_bwd(const void* dout, const void* q, const void*
   VT_REQUIRE(dout && dq && dk && dv, VT_ERR_NULL, "temporal attention backward: NULL tensor");
   VT_REQUIRE(aligned16(q) && aligned16(k) && aligned16(v) && aligned16(dout) && aligned16(dq) && aligned16(dk) && aligned16(dv),
              VT_ERR_ALIGN, "tensors must be 16-byte aligned");
-  if (getenv("VT_TEMPORAL_SIMT") == nullptr) {  // default: the tensor-core (mma.sync) backward
+#ifdef VT_EXPERIMENTS
+  if (getenv("VT_TEMPORAL_SIMT") == nullptr)
+#endif
+  {  // the tensor-core (mma.sync) backward
     VT_CHECK_CUDA(temporal_attn_bwd_mma(dout, q, k, v, dq, dk, dv, mask, do_strides, q_strides, k_strides, v_strides, B, N, H,
                                         D, softmax_scale, static_cast<cudaStream_t>(stream)));
     return 0;
   }
+#ifdef VT_EXPERIMENTS
   TemporalArgs a{};
   a.q = static_cast<const __nv_bfloat16*>(q);
   a.k = static_cast<const __nv_bfloat16*>(k);
@@ -338,4 +353,5 @@ extern "C" int vt_temporal_attn_bwd(const void* dout, const void* q, const void*
   auto st = static_cast<cudaStream_t>(stream);
   VT_CHECK_CUDA(D == 64 ? (launch<64, true>(a, st)) : (launch<128, true>(a, st)));
   return 0;
+#endif
 }

@@ -217,11 +217,10 @@ template <int D, int MT>
 cudaError_t launch_mma(const MmaArgs& a, cudaStream_t st) {
   constexpr int WARPS = 4;
   constexpr int bytes = WARPS * 3 * (16 * MT) * (D + 8) * 2;
-  static bool configured = false;
-  if (!configured) {
+  static char cfg_site;  // per call site; the attribute is per DEVICE (first_on_device)
+  if (first_on_device(&cfg_site)) {
     cudaError_t e = cudaFuncSetAttribute(temporal_mma_fwd_kernel<D, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const int64_t pairs = static_cast<int64_t>(a.B) * a.H;
   int64_t blocks = (pairs + WARPS - 1) / WARPS;
@@ -497,11 +496,10 @@ cudaError_t launch_mma_bwd(const MmaBwdArgs& a, cudaStream_t st) {
   constexpr int WARPS = 4;
   constexpr int R = 16 * MT;
   constexpr int bytes = WARPS * (4 * R * (D + 8) + 2 * R * (R + 8)) * 2;
-  static bool configured = false;
-  if (!configured) {
+  static char cfg_site;  // per call site; the attribute is per DEVICE (first_on_device)
+  if (first_on_device(&cfg_site)) {
     cudaError_t e = cudaFuncSetAttribute(temporal_mma_bwd_kernel<D, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
-    configured = true;
   }
   const int64_t pairs = static_cast<int64_t>(a.B) * a.H;
   int64_t blocks = (pairs + WARPS - 1) / WARPS;

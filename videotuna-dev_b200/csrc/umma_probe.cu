@@ -1,3 +1,5 @@
+// Built only with -DVT_EXPERIMENTS (tools/build_variant.sh): not part of the product library.
+#ifdef VT_EXPERIMENTS
 // umma_probe.cu — single-tile self-test of the TMA + tcgen05 building blocks the attention kernels rely on.
 // D[128 x n] = A[128 x 128] * B, bf16 in / fp32 out, with selectable operand sources:
 //   a_mode 0: A (M x K, K contiguous) from smem, K-major       (Q, K, V, dO as "row" operands)
@@ -147,3 +149,5 @@ extern "C" int vt_umma_probe(const void* a, const void* b, float* d, int a_mode,
   VT_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+#endif  // VT_EXPERIMENTS

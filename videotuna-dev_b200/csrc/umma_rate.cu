@@ -1,3 +1,5 @@
+// Built only with -DVT_EXPERIMENTS (tools/build_variant.sh): not part of the product library.
+#ifdef VT_EXPERIMENTS
 // umma_rate.cu — tcgen05.mma issue-rate microbenchmark (tools/umma_rate.py). Measures cycles per 128 x N x 16 bf16 MMA
 // for the operand sourcings the attention kernels use, optionally with other warps streaming shared-memory stores, so
 // the kernels' MMA-floor arithmetic in DESIGN.md rests on measured numbers. Test infrastructure only.
@@ -236,3 +238,5 @@ extern "C" int vt_tma_reduce_rate(float* acc, int n_tiles, int iters, int depth,
   VT_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
+
+#endif  // VT_EXPERIMENTS

@@ -226,7 +226,7 @@ def lvdm_cross_attention_forward(self, x, context=None, mask=None):
     d = self.dim_head
     q4, k4, v4 = q.view(b, n, h, d), k.view(b, k.shape[1], h, d), v.view(b, v.shape[1], h, d)
     _require(not self.relative_position, "relative-position attention (VideoCrafter1 configs) stays on the reference path")
-    small = n <= 32 and k4.shape[1] <= 32
+    small = n <= 32 and k4.shape[1] == n  # the one-warp kernel takes a single N for q, k and v
     if mask is not None:
         # TemporalTransformer's causal mask: one (t, t) pattern repeated over the batch (attention.py:487-489)
         _require(small, "masked attention is only on the CUDA path for the temporal (N <= 32) kernel")
@@ -263,15 +263,25 @@ def temporal_attention(q: Tensor, k: Tensor, v: Tensor, softmax_scale: Optional[
 # memory-bound helpers
 # ---------------------------------------------------------------------------------------------------------------------
 def ln_modulate(x: Tensor, shift: Optional[Tensor] = None, scale: Optional[Tensor] = None,
-                weight: Optional[Tensor] = None, bias: Optional[Tensor] = None, eps: float = 1e-6) -> Tensor:
+                weight: Optional[Tensor] = None, bias: Optional[Tensor] = None, eps: float = 1e-6,
+                tr_shift: Optional[Tensor] = None, tr_scale: Optional[Tensor] = None,
+                first_frame_tokens: int = 0) -> Tensor:
     """modulate(LayerNorm(x), shift, scale) in one pass (hunyuan modulate_layers.py:31-49 after nn.LayerNorm;
     wan model.py:294-296). x (B,L,C) bf16 or fp32 (Wan's fp32 residual stream); the result is bf16, ready for the
-    following Linear; shift/scale (B,C) or (B,1,C)."""
+    following Linear; shift/scale (B,C) or (B,1,C).
+    first_frame_tokens > 0: the i2v "token_replace" form (hyvideo_i2v/modules/modulate_layers.py:37-63) — rows
+    [0, first_frame_tokens) of every sample take tr_shift / tr_scale, the rest shift / scale."""
     _require(x.is_cuda and x.dtype in (torch.bfloat16, torch.float32) and x.dim() == 3 and x.shape[-1] % 8 == 0,
              "ln_modulate needs a CUDA bf16 or fp32 (B,L,C) tensor")
     B, _, Cc = x.shape
     sc = None if scale is None else scale.reshape(B, Cc)
     sh = None if shift is None else shift.reshape(B, Cc)
+    if first_frame_tokens > 0:
+        _require(tr_shift is not None and tr_scale is not None and sc is not None and sh is not None,
+                 "token_replace modulation needs both vector sets")
+        y, _, _ = ops.ln_modulate_fwd(x, weight, bias, sc, sh, float(eps), tr_scale.reshape(B, Cc),
+                                      tr_shift.reshape(B, Cc), int(first_frame_tokens))
+        return y
     y, _, _ = ops.ln_modulate_fwd(x, weight, bias, sc, sh, float(eps))
     return y
 
@@ -283,12 +293,18 @@ def layer_norm(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], eps:
     return y.view(shp)
 
 
-def gate_residual(x: Tensor, branch: Tensor, gate: Optional[Tensor] = None) -> Tensor:
-    """x + apply_gate(branch, gate) (hunyuan modulate_layers.py:52-68, models.py:231; wan model.py:298)."""
+def gate_residual(x: Tensor, branch: Tensor, gate: Optional[Tensor] = None, tr_gate: Optional[Tensor] = None,
+                  first_frame_tokens: int = 0) -> Tensor:
+    """x + apply_gate(branch, gate) (hunyuan modulate_layers.py:52-68, models.py:231; wan model.py:298).
+    first_frame_tokens > 0: i2v "token_replace" (hyvideo_i2v/modules/modulate_layers.py:66-96) — rows
+    [0, first_frame_tokens) of every sample are gated by tr_gate."""
     _require(x.is_cuda and x.dtype in (torch.bfloat16, torch.float32) and branch.dtype == torch.bfloat16
              and x.dim() == 3, "gate_residual needs a CUDA bf16/fp32 (B,L,C) x and a bf16 branch")
     B, _, Cc = x.shape
     g = None if gate is None else gate.reshape(B, Cc)
+    if first_frame_tokens > 0 and g is not None:
+        _require(tr_gate is not None, "token_replace gating needs tr_gate")
+        return ops.gate_residual_fwd(x, branch, g, tr_gate.reshape(B, Cc), int(first_frame_tokens))
     return ops.gate_residual_fwd(x, branch, g)
 
 
@@ -302,6 +318,29 @@ def qk_rmsnorm_rope(x: Tensor, weight: Optional[Tensor], cos: Optional[Tensor], 
     mode = 0 if weight is None else (1 if per_head else 2)
     y, _ = ops.qk_rmsnorm_rope_fwd(x, weight, cos, sin, mode, float(eps))
     return y
+
+
+def hunyuan_joint_qkv(img_qkv: Tensor, txt_qkv: Tensor, img_q_norm, img_k_norm, txt_q_norm, txt_k_norm,
+                      cos: Optional[Tensor], sin: Optional[Tensor]) -> Tuple[Tensor, Tensor, Tensor]:
+    """MMDoubleStreamBlock's q/k/v preparation (hyvideo_t2v/modules/models.py:166-194) in one op: img_qkv (B,L,3,H,D) and
+    txt_qkv (B,T,3,H,D) -> joint q, k, v (B, L+T, H, D) with the per-head RMSNorm of both streams (norm_layers.py:33-59)
+    and the RoPE of the image rows (posemb_layers.py:140-188) applied on the way; replaces the three torch.cat.
+    *_norm: the block's RMSNorm modules or nn.Identity (qk_norm=False)."""
+    _require(img_qkv.is_cuda and img_qkv.dtype == torch.bfloat16 and txt_qkv.dtype == torch.bfloat16
+             and img_qkv.shape[-1] in (64, 128), "joint q/k/v needs CUDA bf16 tensors with head dim 64/128")
+    ws, eps = [], None
+    for n in (img_q_norm, img_k_norm, txt_q_norm, txt_k_norm):
+        if isinstance(n, torch.nn.Identity):
+            ws.append(None)
+            continue
+        _require(hasattr(n, "weight") and hasattr(n, "eps") and not isinstance(n, torch.nn.LayerNorm),
+                 "only RMSNorm q/k normalisation is on the CUDA path")
+        _require(eps is None or float(n.eps) == eps, "q/k norms with different eps stay on the reference path")
+        eps = float(n.eps)
+        ws.append(n.weight)
+    _require((ws[0] is None) == (ws[1] is None) and (ws[2] is None) == (ws[3] is None), "q and k norms must match")
+    q, k, v, _, _ = ops.joint_qkv_fwd(img_qkv, txt_qkv, ws[0], ws[1], ws[2], ws[3], cos, sin, 1e-6 if eps is None else eps)
+    return q, k, v
 
 
 def groupnorm_silu(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], groups: int, eps: float,

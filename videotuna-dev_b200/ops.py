@@ -68,8 +68,12 @@ def attn_fwd(q: Tensor, k: Tensor, v: Tensor, cu_seqlens_q: Optional[Tensor], cu
     q, k, v = _blhd(q), _blhd(k), _blhd(v)
     B, Lq, H, D = q.shape
     Lk = k.shape[1]
-    o = torch.empty((B, Lq, H, D), dtype=q.dtype, device=q.device)
-    lse = torch.empty((B, H, Lq), dtype=torch.float32, device=q.device)
+    # varlen: rows outside every [cu_seqlens[s], cu_seqlens[s+1]) segment are never touched by the kernel — they must
+    # read as zeros (output) / -inf (lse), not as whatever the allocator handed out
+    alloc = torch.empty if cu_seqlens_q is None else torch.zeros
+    o = alloc((B, Lq, H, D), dtype=q.dtype, device=q.device)
+    lse = (torch.empty((B, H, Lq), dtype=torch.float32, device=q.device) if cu_seqlens_q is None
+           else torch.full((B, H, Lq), float("-inf"), dtype=torch.float32, device=q.device))
     nseg = 0 if cu_seqlens_q is None else cu_seqlens_q.numel() - 1
     with torch.cuda.device(q.device):
         _lib.call("vt_attn_fwd", _ptr(q), _ptr(k), _ptr(v), _ptr(o), _ptr(lse), _lib.strides3(q), _lib.strides3(k),
@@ -92,8 +96,9 @@ def attn_bwd(dout: Tensor, q: Tensor, k: Tensor, v: Tensor, o: Tensor, lse: Tens
     B, Lq, H, D = q.shape
     Lk = k.shape[1]
     dq = torch.empty((B, Lq, H, D), dtype=q.dtype, device=q.device)
-    dk = torch.empty((B, Lk, H, D), dtype=q.dtype, device=q.device)
-    dv = torch.empty((B, Lk, H, D), dtype=q.dtype, device=q.device)
+    alloc = torch.empty if cu_seqlens_q is None else torch.zeros  # varlen: key rows outside every segment stay zero
+    dk = alloc((B, Lk, H, D), dtype=q.dtype, device=q.device)
+    dv = alloc((B, Lk, H, D), dtype=q.dtype, device=q.device)
     nseg = 0 if cu_seqlens_q is None else cu_seqlens_q.numel() - 1
     with torch.cuda.device(q.device):
         nbytes = _lib.lib().vt_attn_bwd_workspace_bytes(B, H, Lq, D)
@@ -166,11 +171,22 @@ attn_fwd.register_autograd(_attn_backward, setup_context=_attn_setup)
 # =====================================================================================================================
 # temporal micro-attention (N <= 32)
 # =====================================================================================================================
+def _check_temporal_shapes(q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor], dout: Optional[Tensor] = None):
+    """The one-warp kernel's ABI carries ONE sequence length for q, k and v (include/b200vt.h): anything else would read
+    past k / v or ignore keys, so it is refused here rather than inside the library."""
+    if not (q.dim() == 4 and q.shape == k.shape == v.shape and (dout is None or dout.shape == q.shape)):
+        raise RuntimeError(f"b200vt: temporal attention needs q, k, v (and dO) of one shape (B, N, H, D); got "
+                           f"{tuple(q.shape)}, {tuple(k.shape)}, {tuple(v.shape)}")
+    if mask is not None and tuple(mask.shape) != (q.shape[1], q.shape[1]):
+        raise RuntimeError(f"b200vt: temporal attention mask must be (N, N) = ({q.shape[1]}, {q.shape[1]}), got {tuple(mask.shape)}")
+
+
 @torch.library.custom_op("b200vt::temporal_attn_fwd", mutates_args=(), device_types="cuda")
 def temporal_attn_fwd(q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor], softmax_scale: float) -> Tensor:
     """q, k, v (B, N, H, D) bf16 with N <= 32 -> o (B, N, H, D) contiguous. mask: (N, N) fp32, > 0.5 = keep."""
     for n, t in (("q", q), ("k", k), ("v", v)):
         _check_bf16_cuda(n, t)
+    _check_temporal_shapes(q, k, v, mask)
     q, k, v = _blhd(q), _blhd(k), _blhd(v)
     B, N, H, D = q.shape
     o = torch.empty((B, N, H, D), dtype=q.dtype, device=q.device)
@@ -189,6 +205,7 @@ def _(q, k, v, mask, softmax_scale):
 @torch.library.custom_op("b200vt::temporal_attn_bwd", mutates_args=(), device_types="cuda")
 def temporal_attn_bwd(dout: Tensor, q: Tensor, k: Tensor, v: Tensor, mask: Optional[Tensor],
                       softmax_scale: float) -> Tuple[Tensor, Tensor, Tensor]:
+    _check_temporal_shapes(q, k, v, mask, dout)
     q, k, v, dout = _blhd(q), _blhd(k), _blhd(v), _blhd(dout)
     B, N, H, D = q.shape
     dq, dk, dv = (torch.empty((B, N, H, D), dtype=q.dtype, device=q.device) for _ in range(3))
@@ -223,10 +240,28 @@ temporal_attn_fwd.register_autograd(_ta_backward, setup_context=_ta_setup)
 # =====================================================================================================================
 # LayerNorm + modulate
 # =====================================================================================================================
+def _off(t: Optional[Tensor], elems: int):
+    """Raw pointer `elems` elements into t (None stays NULL)."""
+    return None if t is None else _vp(t.data_ptr() + elems * t.element_size())
+
+
+def _row_segments(B: int, L: int, split: int):
+    """Row ranges of the i2v "token_replace" modulation (hyvideo_i2v/modules/modulate_layers.py:37-63,66-96): rows
+    [0, split) of every sample take the second vector set, rows [split, L) the first. Yields (b, r0, n, which)."""
+    split = max(0, min(int(split), L))
+    for b in range(B):
+        if split > 0:
+            yield b, 0, split, 1
+        if split < L:
+            yield b, split, L - split, 0
+
+
 @torch.library.custom_op("b200vt::ln_modulate_fwd", mutates_args=(), device_types="cuda")
 def ln_modulate_fwd(x: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor], scale: Optional[Tensor],
-                    shift: Optional[Tensor], eps: float) -> Tuple[Tensor, Tensor, Tensor]:
-    """x (B,L,C) bf16 or fp32; gamma/beta (C); scale/shift (B,C). Returns y (bf16), mean (B*L), rstd (B*L)."""
+                    shift: Optional[Tensor], eps: float, scale2: Optional[Tensor] = None,
+                    shift2: Optional[Tensor] = None, split: int = 0) -> Tuple[Tensor, Tensor, Tensor]:
+    """x (B,L,C) bf16 or fp32; gamma/beta (C); scale/shift (B,C). Returns y (bf16), mean (B*L), rstd (B*L).
+    split > 0 (i2v token_replace): rows [0, split) of every sample are modulated with scale2/shift2 instead."""
     xd = _xdtype("x", x)
     x = x.contiguous()
     B, L, Cc = x.shape
@@ -235,13 +270,21 @@ def ln_modulate_fwd(x: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor], 
     rstd = torch.empty_like(mean)
     g, b, sc, sh = _f32(gamma), _f32(beta), _f32(scale), _f32(shift)
     with torch.cuda.device(x.device):
-        _lib.call("vt_ln_modulate_fwd", _ptr(x), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(g), _ptr(b), _ptr(sc), _ptr(sh),
-                  B, L, Cc, float(eps), xd, _stream())
+        if split <= 0:
+            _lib.call("vt_ln_modulate_fwd", _ptr(x), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(g), _ptr(b), _ptr(sc), _ptr(sh),
+                      B, L, Cc, float(eps), xd, _stream())
+        else:
+            sc2, sh2 = _f32(scale2), _f32(shift2)
+            for bi, r0, n, which in _row_segments(B, L, split):
+                row = bi * L + r0
+                s_, h_ = (sc2, sh2) if which else (sc, sh)
+                _lib.call("vt_ln_modulate_fwd", _off(x, row * Cc), _off(y, row * Cc), _off(mean, row), _off(rstd, row),
+                          _ptr(g), _ptr(b), _off(s_, bi * Cc), _off(h_, bi * Cc), 1, n, Cc, float(eps), xd, _stream())
     return y, mean, rstd
 
 
 @ln_modulate_fwd.register_fake
-def _(x, gamma, beta, scale, shift, eps):
+def _(x, gamma, beta, scale, shift, eps, scale2=None, shift2=None, split=0):
     B, L, Cc = x.shape
     return x.new_empty((B, L, Cc), dtype=torch.bfloat16), x.new_empty((B * L,), dtype=torch.float32), \
         x.new_empty((B * L,), dtype=torch.float32)
@@ -249,9 +292,10 @@ def _(x, gamma, beta, scale, shift, eps):
 
 @torch.library.custom_op("b200vt::ln_modulate_bwd", mutates_args=(), device_types="cuda")
 def ln_modulate_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Optional[Tensor],
-                    beta: Optional[Tensor], scale: Optional[Tensor], need_affine: bool,
-                    need_mod: bool) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
-    """Returns dx and fp32 (dgamma, dbeta, dscale, dshift); unused ones are empty (0-element) tensors."""
+                    beta: Optional[Tensor], scale: Optional[Tensor], need_affine: bool, need_mod: bool,
+                    scale2: Optional[Tensor] = None, split: int = 0
+                    ) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """Returns dx and fp32 (dgamma, dbeta, dscale, dshift, dscale2, dshift2); unused ones are empty (0-element)."""
     dy, x = dy.contiguous(), x.contiguous()
     if dy.dtype != torch.bfloat16:
         dy = dy.to(torch.bfloat16)
@@ -259,50 +303,76 @@ def ln_modulate_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Op
     B, L, Cc = x.shape
     dx = torch.empty_like(x)
     dev = x.device
-    dgamma = torch.zeros((Cc,), dtype=torch.float32, device=dev) if need_affine else x.new_empty((0,), dtype=torch.float32)
+    empty = x.new_empty((0,), dtype=torch.float32)
+    dgamma = torch.zeros((Cc,), dtype=torch.float32, device=dev) if need_affine else empty
     dbeta = torch.zeros_like(dgamma)
-    dscale = torch.zeros((B, Cc), dtype=torch.float32, device=dev) if need_mod else x.new_empty((0,), dtype=torch.float32)
+    dscale = torch.zeros((B, Cc), dtype=torch.float32, device=dev) if need_mod else empty
     dshift = torch.zeros_like(dscale)
+    dscale2 = torch.zeros_like(dscale) if split > 0 else empty
+    dshift2 = torch.zeros_like(dscale2)
     g, b, sc = _f32(gamma), _f32(beta), _f32(scale)
     with torch.cuda.device(dev):
-        _lib.call("vt_ln_modulate_bwd", _ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(g), _ptr(b), _ptr(sc),
-                  _ptr(dgamma) if need_affine else None, _ptr(dbeta) if need_affine else None,
-                  _ptr(dscale) if need_mod else None, _ptr(dshift) if need_mod else None, B, L, Cc, xd, _stream())
-    return dx, dgamma, dbeta, dscale, dshift
+        if split <= 0:
+            _lib.call("vt_ln_modulate_bwd", _ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(g), _ptr(b), _ptr(sc),
+                      _ptr(dgamma) if need_affine else None, _ptr(dbeta) if need_affine else None,
+                      _ptr(dscale) if need_mod else None, _ptr(dshift) if need_mod else None, B, L, Cc, xd, _stream())
+        else:
+            sc2 = _f32(scale2)
+            for bi, r0, n, which in _row_segments(B, L, split):
+                row = bi * L + r0
+                s_, ds_, dh_ = (sc2, dscale2, dshift2) if which else (sc, dscale, dshift)
+                _lib.call("vt_ln_modulate_bwd", _off(dy, row * Cc), _off(x, row * Cc), _off(mean, row), _off(rstd, row),
+                          _off(dx, row * Cc), _ptr(g), _ptr(b), _off(s_, bi * Cc),
+                          _ptr(dgamma) if need_affine else None, _ptr(dbeta) if need_affine else None,
+                          _off(ds_, bi * Cc) if need_mod else None, _off(dh_, bi * Cc) if need_mod else None,
+                          1, n, Cc, xd, _stream())
+    return dx, dgamma, dbeta, dscale, dshift, dscale2, dshift2
 
 
 @ln_modulate_bwd.register_fake
-def _(dy, x, mean, rstd, gamma, beta, scale, need_affine, need_mod):
+def _(dy, x, mean, rstd, gamma, beta, scale, need_affine, need_mod, scale2=None, split=0):
     B, L, Cc = x.shape
     e = x.new_empty((0,), dtype=torch.float32)
+    mod = x.new_empty((B, Cc), dtype=torch.float32) if need_mod else e
+    mod2 = x.new_empty((B, Cc), dtype=torch.float32) if (need_mod and split > 0) else e
     return (torch.empty_like(x, memory_format=torch.contiguous_format),
             x.new_empty((Cc,), dtype=torch.float32) if need_affine else e,
             x.new_empty((Cc,), dtype=torch.float32) if need_affine else e,
-            x.new_empty((B, Cc), dtype=torch.float32) if need_mod else e,
-            x.new_empty((B, Cc), dtype=torch.float32) if need_mod else e)
+            mod, torch.empty_like(mod), mod2, torch.empty_like(mod2))
 
 
 def _lnm_setup(ctx, inputs, output):
-    x, gamma, beta, scale, shift, eps = inputs
+    x, gamma, beta, scale, shift, eps = inputs[:6]
+    scale2, shift2, split = (tuple(inputs[6:]) + (None, None, 0))[:3]
     y, mean, rstd = output
-    ctx.save_for_backward(x, mean, rstd, gamma, beta, scale, shift)
+    ctx.save_for_backward(x, mean, rstd, gamma, beta, scale, shift, scale2, shift2)
+    ctx.split = int(split)
+    ctx.n_inputs = len(inputs)
 
 
 def _lnm_backward(ctx, dy, dmean, drstd):
-    x, mean, rstd, gamma, beta, scale, shift = ctx.saved_tensors
-    need_affine = (gamma is not None and ctx.needs_input_grad[1]) or (beta is not None and ctx.needs_input_grad[2])
-    need_mod = (scale is not None and ctx.needs_input_grad[3]) or (shift is not None and ctx.needs_input_grad[4])
-    dx, dgamma, dbeta, dscale, dshift = ln_modulate_bwd(dy, x, mean, rstd, gamma, beta, scale, need_affine, need_mod)
-    out = [dx, None, None, None, None, None]
-    if gamma is not None and ctx.needs_input_grad[1]:
+    x, mean, rstd, gamma, beta, scale, shift, scale2, shift2 = ctx.saved_tensors
+    nig = tuple(ctx.needs_input_grad) + (False,) * 9
+    need_affine = (gamma is not None and nig[1]) or (beta is not None and nig[2])
+    need_mod = ((scale is not None and nig[3]) or (shift is not None and nig[4])
+                or (scale2 is not None and nig[6]) or (shift2 is not None and nig[7]))
+    dx, dgamma, dbeta, dscale, dshift, dscale2, dshift2 = ln_modulate_bwd(
+        dy, x, mean, rstd, gamma, beta, scale, need_affine, need_mod, scale2, ctx.split)
+    out = [dx] + [None] * 8
+    if gamma is not None and nig[1]:
         out[1] = dgamma.to(gamma.dtype)
-    if beta is not None and ctx.needs_input_grad[2]:
+    if beta is not None and nig[2]:
         out[2] = dbeta.to(beta.dtype)
-    if scale is not None and ctx.needs_input_grad[3]:
+    if scale is not None and nig[3]:
         out[3] = dscale.to(scale.dtype).view_as(scale)
-    if shift is not None and ctx.needs_input_grad[4]:
+    if shift is not None and nig[4]:
         out[4] = dshift.to(shift.dtype).view_as(shift)
-    return tuple(out)
+    if ctx.split > 0:
+        if scale2 is not None and nig[6]:
+            out[6] = dscale2.to(scale2.dtype).view_as(scale2)
+        if shift2 is not None and nig[7]:
+            out[7] = dshift2.to(shift2.dtype).view_as(shift2)
+    return tuple(out[:ctx.n_inputs])
 
 
 ln_modulate_fwd.register_autograd(_lnm_backward, setup_context=_lnm_setup)
@@ -312,8 +382,10 @@ ln_modulate_fwd.register_autograd(_lnm_backward, setup_context=_lnm_setup)
 # gated residual
 # =====================================================================================================================
 @torch.library.custom_op("b200vt::gate_residual_fwd", mutates_args=(), device_types="cuda")
-def gate_residual_fwd(x: Tensor, branch: Tensor, gate: Optional[Tensor]) -> Tensor:
-    """y = x + branch * gate[:, None, :];  x (B,L,C) bf16 or fp32 (y likewise), branch (B,L,C) bf16, gate (B,C) or None."""
+def gate_residual_fwd(x: Tensor, branch: Tensor, gate: Optional[Tensor], gate2: Optional[Tensor] = None,
+                      split: int = 0) -> Tensor:
+    """y = x + branch * gate[:, None, :];  x (B,L,C) bf16 or fp32 (y likewise), branch (B,L,C) bf16, gate (B,C) or None.
+    split > 0 (i2v token_replace, modulate_layers.py:66-96): rows [0, split) of every sample use gate2."""
     xd = _xdtype("x", x)
     _check_bf16_cuda("branch", branch)
     x, branch = x.contiguous(), branch.contiguous()
@@ -321,46 +393,74 @@ def gate_residual_fwd(x: Tensor, branch: Tensor, gate: Optional[Tensor]) -> Tens
     y = torch.empty_like(x)
     g = _f32(gate)
     with torch.cuda.device(x.device):
-        _lib.call("vt_gate_residual_fwd", _ptr(x), _ptr(branch), _ptr(y), _ptr(g), B, L, Cc, xd, _stream())
+        if split <= 0:
+            _lib.call("vt_gate_residual_fwd", _ptr(x), _ptr(branch), _ptr(y), _ptr(g), B, L, Cc, xd, _stream())
+        else:
+            g2 = _f32(gate2)
+            for bi, r0, n, which in _row_segments(B, L, split):
+                e = (bi * L + r0) * Cc
+                _lib.call("vt_gate_residual_fwd", _off(x, e), _off(branch, e), _off(y, e),
+                          _off(g2 if which else g, bi * Cc), 1, n, Cc, xd, _stream())
     return y
 
 
 @gate_residual_fwd.register_fake
-def _(x, branch, gate):
+def _(x, branch, gate, gate2=None, split=0):
     return torch.empty_like(x, memory_format=torch.contiguous_format)
 
 
 @torch.library.custom_op("b200vt::gate_residual_bwd", mutates_args=(), device_types="cuda")
-def gate_residual_bwd(dy: Tensor, branch: Tensor, gate: Optional[Tensor], need_dgate: bool) -> Tuple[Tensor, Tensor]:
+def gate_residual_bwd(dy: Tensor, branch: Tensor, gate: Optional[Tensor], need_dgate: bool,
+                      gate2: Optional[Tensor] = None, split: int = 0) -> Tuple[Tensor, Tensor, Tensor]:
     dy, branch = dy.contiguous(), branch.contiguous()
     xd = _xdtype("dy", dy)
     B, L, Cc = dy.shape
     dbranch = torch.empty((B, L, Cc), dtype=torch.bfloat16, device=dy.device)
-    dgate = torch.zeros((B, Cc), dtype=torch.float32, device=dy.device) if need_dgate else dy.new_empty((0,), dtype=torch.float32)
+    empty = dy.new_empty((0,), dtype=torch.float32)
+    dgate = torch.zeros((B, Cc), dtype=torch.float32, device=dy.device) if need_dgate else empty
+    dgate2 = torch.zeros_like(dgate) if split > 0 else empty
     g = _f32(gate)
     with torch.cuda.device(dy.device):
-        _lib.call("vt_gate_residual_bwd", _ptr(dy), _ptr(branch), _ptr(dbranch), _ptr(g),
-                  _ptr(dgate) if need_dgate else None, B, L, Cc, xd, _stream())
-    return dbranch, dgate
+        if split <= 0:
+            _lib.call("vt_gate_residual_bwd", _ptr(dy), _ptr(branch), _ptr(dbranch), _ptr(g),
+                      _ptr(dgate) if need_dgate else None, B, L, Cc, xd, _stream())
+        else:
+            g2 = _f32(gate2)
+            for bi, r0, n, which in _row_segments(B, L, split):
+                e = (bi * L + r0) * Cc
+                _lib.call("vt_gate_residual_bwd", _off(dy, e), _off(branch, e), _off(dbranch, e),
+                          _off(g2 if which else g, bi * Cc),
+                          _off(dgate2 if which else dgate, bi * Cc) if need_dgate else None, 1, n, Cc, xd, _stream())
+    return dbranch, dgate, dgate2
 
 
 @gate_residual_bwd.register_fake
-def _(dy, branch, gate, need_dgate):
+def _(dy, branch, gate, need_dgate, gate2=None, split=0):
     B, L, Cc = dy.shape
     return dy.new_empty((B, L, Cc), dtype=torch.bfloat16), \
-        dy.new_empty((B, Cc) if need_dgate else (0,), dtype=torch.float32)
+        dy.new_empty((B, Cc) if need_dgate else (0,), dtype=torch.float32), \
+        dy.new_empty((B, Cc) if (need_dgate and split > 0) else (0,), dtype=torch.float32)
 
 
 def _gr_setup(ctx, inputs, output):
-    x, branch, gate = inputs
-    ctx.save_for_backward(branch, gate)
+    x, branch, gate = inputs[:3]
+    gate2, split = (tuple(inputs[3:]) + (None, 0))[:2]
+    ctx.save_for_backward(branch, gate, gate2)
+    ctx.split = int(split)
+    ctx.n_inputs = len(inputs)
 
 
 def _gr_backward(ctx, dy):
-    branch, gate = ctx.saved_tensors
-    need_dgate = gate is not None and ctx.needs_input_grad[2]
-    dbranch, dgate = gate_residual_bwd(dy, branch, gate, need_dgate)
-    return dy, dbranch, (dgate.to(gate.dtype).view_as(gate) if need_dgate else None)
+    branch, gate, gate2 = ctx.saved_tensors
+    nig = tuple(ctx.needs_input_grad) + (False,) * 5
+    need_dgate = (gate is not None and nig[2]) or (gate2 is not None and nig[3])
+    dbranch, dgate, dgate2 = gate_residual_bwd(dy, branch, gate, need_dgate, gate2, ctx.split)
+    out = [dy, dbranch, None, None, None]
+    if gate is not None and nig[2]:
+        out[2] = dgate.to(gate.dtype).view_as(gate)
+    if ctx.split > 0 and gate2 is not None and nig[3]:
+        out[3] = dgate2.to(gate2.dtype).view_as(gate2)
+    return tuple(out[:ctx.n_inputs])
 
 
 gate_residual_fwd.register_autograd(_gr_backward, setup_context=_gr_setup)
@@ -438,6 +538,120 @@ def _rr_backward(ctx, dy, drstd):
 
 
 qk_rmsnorm_rope_fwd.register_autograd(_rr_backward, setup_context=_rr_setup)
+
+
+# =====================================================================================================================
+# HunyuanVideo double-stream block: [img ; txt] q, k, v straight from the two fused QKV projections
+# =====================================================================================================================
+def _rr_call_fwd(x4: Tensor, y4: Tensor, rstd: Optional[Tensor], w, cos, sin, eps: float):
+    """vt_qk_rmsnorm_rope_fwd on (B,L,H,D) views x4 -> y4 (any (b,l,h) strides); per-head norm when w is given."""
+    B, L, H, D = x4.shape
+    mode = 0 if w is None else 1
+    L_rope = 0 if cos is None else min(cos.shape[0], L)
+    _lib.call("vt_qk_rmsnorm_rope_fwd", _ptr(x4), _ptr(y4), _ptr(rstd) if mode else None, _ptr(w), _ptr(cos), _ptr(sin),
+              _lib.strides3(x4), _lib.strides3(y4), B, L, H, D, L_rope, mode, float(eps), _stream())
+
+
+def _rr_call_bwd(dy4: Tensor, x4: Tensor, rstd: Optional[Tensor], dx4: Tensor, dw: Optional[Tensor], w, cos, sin):
+    B, L, H, D = x4.shape
+    mode = 0 if w is None else 1
+    L_rope = 0 if cos is None else min(cos.shape[0], L)
+    _lib.call("vt_qk_rmsnorm_rope_bwd", _ptr(dy4), _ptr(x4), _ptr(rstd) if mode else None, _ptr(dx4), _ptr(dw), _ptr(w),
+              _ptr(cos), _ptr(sin), _lib.strides3(dy4), _lib.strides3(x4), _lib.strides3(dx4), B, L, H, D, L_rope, mode,
+              _stream())
+
+
+@torch.library.custom_op("b200vt::joint_qkv_fwd", mutates_args=(), device_types="cuda")
+def joint_qkv_fwd(img_qkv: Tensor, txt_qkv: Tensor, wq_img: Optional[Tensor], wk_img: Optional[Tensor],
+                  wq_txt: Optional[Tensor], wk_txt: Optional[Tensor], cos: Optional[Tensor], sin: Optional[Tensor],
+                  eps: float) -> Tuple[Tensor, Tensor, Tensor, Tensor, Tensor]:
+    """img_qkv (B,L,3,H,D), txt_qkv (B,T,3,H,D) bf16 — the outputs of MMDoubleStreamBlock's img_attn_qkv / txt_attn_qkv
+    (hyvideo_t2v/modules/models.py:165-189). Returns q, k, v (B, L+T, H, D) with the per-head RMSNorm (+ RoPE on the
+    image rows) of q and k written straight into their rows of the joint tensors — the reference's three torch.cat
+    (:192-194) never happen — and the saved rstd of both streams, (2,B,L,H) / (2,B,T,H) fp32."""
+    _check_bf16_cuda("img_qkv", img_qkv)
+    _check_bf16_cuda("txt_qkv", txt_qkv)
+    img_qkv, txt_qkv = img_qkv.contiguous(), txt_qkv.contiguous()
+    B, L, _, H, D = img_qkv.shape
+    T = txt_qkv.shape[1]
+    dev = img_qkv.device
+    q, k, v = (torch.empty((B, L + T, H, D), dtype=torch.bfloat16, device=dev) for _ in range(3))
+    rstd_i = torch.empty((2, B, L, H), dtype=torch.float32, device=dev)
+    rstd_t = torch.empty((2, B, T, H), dtype=torch.float32, device=dev)
+    c, s_ = _f32(cos), _f32(sin)
+    with torch.cuda.device(dev):
+        for which, (dst, wi, wt) in enumerate(((q, wq_img, wq_txt), (k, wk_img, wk_txt))):
+            _rr_call_fwd(img_qkv[:, :, which], dst[:, :L], rstd_i[which], _f32(wi), c, s_, eps)
+            if wt is None:
+                dst[:, L:].copy_(txt_qkv[:, :, which])
+            else:
+                _rr_call_fwd(txt_qkv[:, :, which], dst[:, L:], rstd_t[which], _f32(wt), None, None, eps)
+        v[:, :L].copy_(img_qkv[:, :, 2])
+        v[:, L:].copy_(txt_qkv[:, :, 2])
+    return q, k, v, rstd_i, rstd_t
+
+
+@joint_qkv_fwd.register_fake
+def _(img_qkv, txt_qkv, wq_img, wk_img, wq_txt, wk_txt, cos, sin, eps):
+    B, L, _, H, D = img_qkv.shape
+    T = txt_qkv.shape[1]
+    mk = lambda: img_qkv.new_empty((B, L + T, H, D))  # noqa: E731
+    return mk(), mk(), mk(), img_qkv.new_empty((2, B, L, H), dtype=torch.float32), \
+        img_qkv.new_empty((2, B, T, H), dtype=torch.float32)
+
+
+@torch.library.custom_op("b200vt::joint_qkv_bwd", mutates_args=(), device_types="cuda")
+def joint_qkv_bwd(dq: Tensor, dk: Tensor, dv: Tensor, img_qkv: Tensor, txt_qkv: Tensor, rstd_i: Tensor, rstd_t: Tensor,
+                  wq_img: Optional[Tensor], wk_img: Optional[Tensor], wq_txt: Optional[Tensor], wk_txt: Optional[Tensor],
+                  cos: Optional[Tensor], sin: Optional[Tensor]) -> Tuple[Tensor, Tensor, Tensor]:
+    """Gradients of joint_qkv_fwd written straight into (B,L,3,H,D) / (B,T,3,H,D) buffers (no select/cat backward
+    zero-fills); dw (4, D) fp32 = d(wq_img, wk_img, wq_txt, wk_txt)."""
+    img_qkv, txt_qkv = img_qkv.contiguous(), txt_qkv.contiguous()
+    dq, dk, dv = _blhd(dq), _blhd(dk), _blhd(dv)
+    B, L, _, H, D = img_qkv.shape
+    dev = img_qkv.device
+    d_img, d_txt = torch.empty_like(img_qkv), torch.empty_like(txt_qkv)
+    dw = torch.zeros((4, D), dtype=torch.float32, device=dev)
+    c, s_ = _f32(cos), _f32(sin)
+    with torch.cuda.device(dev):
+        for which, (g, wi, wt) in enumerate(((dq, wq_img, wq_txt), (dk, wk_img, wk_txt))):
+            _rr_call_bwd(g[:, :L], img_qkv[:, :, which], rstd_i[which], d_img[:, :, which],
+                         dw[which] if wi is not None else None, _f32(wi), c, s_)
+            if wt is None:
+                d_txt[:, :, which].copy_(g[:, L:])
+            else:
+                _rr_call_bwd(g[:, L:], txt_qkv[:, :, which], rstd_t[which], d_txt[:, :, which], dw[2 + which], _f32(wt),
+                             None, None)
+        d_img[:, :, 2].copy_(dv[:, :L])
+        d_txt[:, :, 2].copy_(dv[:, L:])
+    return d_img, d_txt, dw
+
+
+@joint_qkv_bwd.register_fake
+def _(dq, dk, dv, img_qkv, txt_qkv, rstd_i, rstd_t, wq_img, wk_img, wq_txt, wk_txt, cos, sin):
+    return (torch.empty_like(img_qkv, memory_format=torch.contiguous_format),
+            torch.empty_like(txt_qkv, memory_format=torch.contiguous_format),
+            img_qkv.new_empty((4, img_qkv.shape[-1]), dtype=torch.float32))
+
+
+def _jq_setup(ctx, inputs, output):
+    img_qkv, txt_qkv, wq_i, wk_i, wq_t, wk_t, cos, sin, eps = inputs
+    q, k, v, rstd_i, rstd_t = output
+    ctx.save_for_backward(img_qkv, txt_qkv, rstd_i, rstd_t, wq_i, wk_i, wq_t, wk_t, cos, sin)
+
+
+def _jq_backward(ctx, dq, dk, dv, d_ri, d_rt):
+    img_qkv, txt_qkv, rstd_i, rstd_t, wq_i, wk_i, wq_t, wk_t, cos, sin = ctx.saved_tensors
+    zeros = lambda: torch.zeros((img_qkv.shape[0], img_qkv.shape[1] + txt_qkv.shape[1], *img_qkv.shape[3:]),  # noqa: E731
+                                dtype=img_qkv.dtype, device=img_qkv.device)
+    dq, dk, dv = (zeros() if g is None else g for g in (dq, dk, dv))
+    d_img, d_txt, dw = joint_qkv_bwd(dq, dk, dv, img_qkv, txt_qkv, rstd_i, rstd_t, wq_i, wk_i, wq_t, wk_t, cos, sin)
+    ws = [None if w is None or not ctx.needs_input_grad[2 + i] else dw[i].to(w.dtype).view_as(w)
+          for i, w in enumerate((wq_i, wk_i, wq_t, wk_t))]
+    return (d_img, d_txt, *ws, None, None, None)
+
+
+joint_qkv_fwd.register_autograd(_jq_backward, setup_context=_jq_setup)
 
 
 # =====================================================================================================================
@@ -598,6 +812,6 @@ _default_fast = "1" if int(_os.environ.get("WORLD_SIZE", "1") or "1") <= 1 else 
 if _os.environ.get("B200VT_EAGER_FAST", _default_fast) != "0":
     for _name in ("attn_fwd", "attn_bwd", "attn_fwd_scatter", "temporal_attn_fwd", "temporal_attn_bwd", "ln_modulate_fwd",
                   "ln_modulate_bwd", "gate_residual_fwd", "gate_residual_bwd", "qk_rmsnorm_rope_fwd", "qk_rmsnorm_rope_bwd",
-                  "groupnorm_silu_fwd", "groupnorm_silu_bwd"):
+                  "groupnorm_silu_fwd", "groupnorm_silu_bwd", "joint_qkv_fwd", "joint_qkv_bwd"):
         if _name in globals():
             globals()[_name] = _make_eager(globals()[_name])

@@ -117,18 +117,6 @@ def _patch_method(mod, cls_name: str, attr: str, fast: Callable) -> int:
     return 1
 
 
-def _t2v_signature_only(fast: Callable, n_positional: int, allowed: tuple) -> Callable:
-    """The i2v twins of the Hunyuan blocks take extra arguments (condition_type, token_replace_vec,
-    frist_frame_token_num; hyvideo_i2v/modules/models.py:136-297) for first-frame token replacement, which is not on the
-    CUDA path: calls that use them go to the original forward."""
-    def guarded(self, *args, **kwargs):
-        extra = [k for k in kwargs if k not in allowed and kwargs[k] is not None]
-        if len(args) > n_positional or extra:
-            raise Fn.Unsupported("token_replace (i2v first-frame modulation) stays on the reference path")
-        return fast(self, *args, **{k: v for k, v in kwargs.items() if k in allowed})
-    return guarded
-
-
 def patch_blocks(lvdm: bool = True, hunyuan: bool = True, wan: bool = True) -> Dict[str, int]:
     """Replace the block-level forwards with the fused versions in b200vt.blocks.
     Independent of patch_videotuna(): the fused blocks call b200vt's attention functions directly. Idempotent."""
@@ -143,16 +131,15 @@ def patch_blocks(lvdm: bool = True, hunyuan: bool = True, wan: bool = True) -> D
         if net is not None:
             done["lvdm"] += _patch_method(net, "ResBlock", "_forward", Bk.lvdm_resblock_forward)
     if hunyuan:
-        dbl_kw = ("img", "txt", "vec", "cu_seqlens_q", "cu_seqlens_kv", "max_seqlen_q", "max_seqlen_kv", "freqs_cis")
-        sgl_kw = ("x", "vec", "txt_len", "cu_seqlens_q", "cu_seqlens_kv", "max_seqlen_q", "max_seqlen_kv", "freqs_cis")
+        # The drop-ins take the i2v twins' full signature (condition_type, token_replace_vec, frist_frame_token_num:
+        # hyvideo_i2v/modules/models.py:136-149, 371-384) — HunyuanVideoFlow drives T2V and I2V through the i2v DiT, which
+        # always passes all 11 arguments positionally (:749-761, 776-788).
         for pkg in ("hyvideo_t2v", "hyvideo_i2v"):
             mod = _try_import(f"videotuna.models.hunyuan.{pkg}.modules.models")
             if mod is None:
                 continue
-            done["hunyuan"] += _patch_method(mod, "MMDoubleStreamBlock", "forward",
-                                             _t2v_signature_only(Bk.hunyuan_double_block_forward, 8, dbl_kw))
-            done["hunyuan"] += _patch_method(mod, "MMSingleStreamBlock", "forward",
-                                             _t2v_signature_only(Bk.hunyuan_single_block_forward, 8, sgl_kw))
+            done["hunyuan"] += _patch_method(mod, "MMDoubleStreamBlock", "forward", Bk.hunyuan_double_block_forward)
+            done["hunyuan"] += _patch_method(mod, "MMSingleStreamBlock", "forward", Bk.hunyuan_single_block_forward)
             if hasattr(mod, "parallel_attention"):
                 mod.parallel_attention = _wrap(f"{mod.__name__}.parallel_attention", mod.parallel_attention,
                                                Bk.hunyuan_parallel_attention)

@@ -30,6 +30,7 @@ import torch
 from torch import Tensor, nn
 
 from . import functional as Fn
+from . import sp as _sp
 from .functional import Unsupported, _require
 
 _BF16 = torch.bfloat16
@@ -82,7 +83,13 @@ def hunyuan_parallel_attention(hybrid_seq_parallel_attn, q, k, v, img_q_len, img
         joint_tensor_value=v[:, img_kv_len:n_k], joint_strategy="rear")
     parts = [attn1]
     if q.shape[1] > n_q:
-        parts.append(Fn.attention_blhd(q[:, n_q:], k[:, n_k:], v[:, n_k:]))
+        # the padding tail attends among itself, locally (the reference calls flash-attn directly, attenion.py:182-197);
+        # an injected attention core (CPU tests of the exchange logic) serves the tail as well
+        core = getattr(hybrid_seq_parallel_attn, "attn_fn", None)
+        if core is None or core is _sp._default_attn:
+            parts.append(Fn.attention_blhd(q[:, n_q:], k[:, n_k:], v[:, n_k:]))
+        else:
+            parts.append(core(q[:, n_q:], k[:, n_k:], v[:, n_k:], None))
     attn = torch.cat(parts, dim=1) if len(parts) > 1 else attn1
     b, s, a, d = attn.shape
     return attn.reshape(b, s, a * d)

@@ -8,7 +8,8 @@ never to a CPU kernel of ours.
 
     import b200vt
     b200vt.patch.patch_videotuna()          # before building the model; idempotent
-    b200vt.patch.install_ulysses(dit)       # Hunyuan: every block's hybrid_seq_parallel_attn = UlyssesAttention()
+    b200vt.patch.patch_sp()                 # sequence parallelism without xfuser: the reference flows enter SP unmodified
+    b200vt.patch.install_ulysses(dit)       # or by hand: every block's hybrid_seq_parallel_attn = UlyssesAttention()
 """
 from __future__ import annotations
 
@@ -22,6 +23,7 @@ import torch
 from . import blocks as Bk
 from . import functional as Fn
 from . import sp
+from . import xfuser_shim
 
 _ORIGINALS: Dict[str, Callable] = {}
 
@@ -316,3 +318,99 @@ def wan_usp_attn_forward(self, x, seq_lens, grid_sizes, freqs, dtype=torch.bfloa
     k = norm_rope(proj(self.k), self.norm_k)
     out = sp.UlyssesAttention(group)(None, q, k, proj(self.v), window_size=self.window_size)
     return self.o(out.flatten(2).to(x.dtype))
+
+
+def wan_usp_dit_forward(self, x, t, context, seq_len, clip_fea=None, y=None, group=None):
+    """xfuser-free replacement for usp_dit_forward (xdit_context_parallel.py:66-146), bound onto a WanModel with
+    types.MethodType like the reference does (wan/text2video.py:270). The reference's wrapper restates WanModel.forward
+    (wan/modules/model.py:482-574) with two changes — `torch.chunk(x, P, dim=1)[rank]` on the padded token sequence before
+    the first block (:121-127) and `get_sp_group().all_gather(x, dim=1)` after the head (:142). Here the model's OWN class
+    forward runs and those two steps are attached where they belong: a pre-hook on the first block keeps this rank's token
+    chunk, a hook on the head gathers the chunks. Patch embedding, time / text / CLIP embeddings and unpatchify are
+    therefore exactly the model's, whatever its version."""
+    if sp._world(group) == 1:
+        return type(self).forward(self, x, t, context, seq_len, clip_fea=clip_fea, y=y)
+
+    def keep_my_chunk(_module, args, kwargs):
+        return (sp.shard_sequence(args[0], dim=1, group=group), *args[1:]), kwargs
+
+    def gather_chunks(_module, _args, out):
+        return sp.gather_sequence(out, dim=1, group=group)
+
+    hooks = [self.blocks[0].register_forward_pre_hook(keep_my_chunk, with_kwargs=True),
+             self.head.register_forward_hook(gather_chunks)]
+    try:
+        return type(self).forward(self, x, t, context, seq_len, clip_fea=clip_fea, y=y)
+    finally:
+        for h in hooks:
+            h.remove()
+
+
+def hunyuan_parallelize_transformer(pipe, group=None, attn_fn: Optional[Callable] = None):
+    """xfuser-free replacement for parallelize_transformer (flow/hunyuanvideo.py:114-178; twin in
+    hyvideo_t2v/inference.py:48-110): wraps `pipe.transformer.forward` so that every rank denoises one slab of the latent.
+    The latent (B, C, T, H, W) is cut along the patch rows when H/2 divides by the SP size, else along the patch columns;
+    the RoPE tables, laid out as (T, H/2, W/2) tokens, are cut the same way; every double / single stream block gets the
+    Ulysses attention object; the output slabs are gathered back along the cut axis. attn_fn: attention core for
+    sp.UlyssesAttention (default: the CUDA kernels; the CPU tests of the exchange logic inject the oracle)."""
+    transformer = pipe.transformer
+    inner = transformer.forward
+    attn = sp.UlyssesAttention(group, attn_fn)
+
+    @functools.wraps(type(transformer).forward)
+    def forward(self, x, t, text_states=None, text_mask=None, text_states_2=None, freqs_cos=None, freqs_sin=None,
+                guidance=None, return_dict=True):
+        P, r = sp._world(group), sp._rank(group)
+        axis = next((a for a in (-2, -1) if (x.shape[a] // 2) % P == 0), None)  # 2 x 2 spatial patches
+        if axis is None:
+            raise ValueError(f"Cannot split video sequence into ulysses_degree x ring_degree ({P}) parts evenly")
+        frames, rows, cols = x.shape[2], x.shape[3] // 2, x.shape[4] // 2
+
+        def my_slab(table):
+            if table is None:
+                return None
+            grid = table.reshape(frames, rows, cols, table.shape[-1])
+            return grid.chunk(P, dim=axis - 1)[r].reshape(-1, table.shape[-1])
+
+        for block in list(self.double_blocks) + list(self.single_blocks):
+            block.hybrid_seq_parallel_attn = attn
+        out = inner(x.chunk(P, dim=axis)[r], t, text_states, text_mask, text_states_2, my_slab(freqs_cos),
+                    my_slab(freqs_sin), guidance, return_dict)
+        if isinstance(out, dict):
+            out["x"] = sp.gather_sequence(out["x"], dim=axis, group=group)
+            return out
+        return (sp.gather_sequence(out[0], dim=axis, group=group), *out[1:])
+
+    transformer.forward = types.MethodType(forward, transformer)
+    return transformer
+
+
+def patch_sp(group=None) -> Dict[str, int]:
+    """Make the reference's sequence-parallel entry points work without xfuser and on the b200vt kernels:
+      * registers the xfuser stand-in (xfuser_shim.install(); no-op when the real package is importable), so that
+        `from xfuser.core.distributed import ...` in xdit_context_parallel.py:3-7, flow/hunyuanvideo.py:31-46 and
+        wan/text2video.py:262 resolves and `xFuserLongContextAttention()` is a b200vt.sp.UlyssesAttention;
+      * rebinds `usp_attn_forward` / `usp_dit_forward` in wan/distributed/xdit_context_parallel.py (text2video.py:264-270
+        imports them from there at bind time) to wan_usp_attn_forward / wan_usp_dit_forward;
+      * rebinds `parallelize_transformer` in flow/hunyuanvideo.py and hyvideo_t2v/inference.py.
+    Unsupported inputs fall back to the reference callables, which then run on the stand-in. Returns what was installed."""
+    done = {"xfuser_shim": int(xfuser_shim.install()), "wan": 0, "hunyuan": 0}
+
+    def _with_group(fast):
+        if group is None:
+            return fast
+        return functools.wraps(fast)(lambda *a, **k: fast(*a, **{**k, "group": group}))
+
+    mod = _try_import("videotuna.models.wan.wan.distributed.xdit_context_parallel")
+    if mod is not None:
+        mod.usp_attn_forward = _wrap(f"{mod.__name__}.usp_attn_forward", mod.usp_attn_forward,
+                                     _with_group(wan_usp_attn_forward))
+        mod.usp_dit_forward = _wrap(f"{mod.__name__}.usp_dit_forward", mod.usp_dit_forward, _with_group(wan_usp_dit_forward))
+        done["wan"] = 2
+    for name in ("videotuna.flow.hunyuanvideo", "videotuna.models.hunyuan.hyvideo_t2v.inference"):
+        mod = _try_import(name)
+        if mod is not None and hasattr(mod, "parallelize_transformer"):
+            mod.parallelize_transformer = _wrap(f"{name}.parallelize_transformer", mod.parallelize_transformer,
+                                                _with_group(hunyuan_parallelize_transformer))
+            done["hunyuan"] += 1
+    return done

@@ -16,6 +16,15 @@ parallel_attention(hybrid_seq_parallel_attn, ...) at :215) on synthetic q, k, v,
 N > 1 (launched by torchrun, one rank per GPU): Ulysses sequence parallelism — image tokens sharded over ranks, text
 tokens replicated ("rear" joint strategy), NCCL all-to-all before and after the local kernel; strong scaling.
 --impl reference: the reference's own CPU attention path timed on the host cores (rank 0 only).
+Further keys on the same line (each measured in this process, with its own clocks record; --no-extras skips them):
+    sp_parity          N > 1: one sequence-parallel step compared, for 2 heads, with the unsharded kernels run on the
+                       gathered tensors (outputs and all gradients; must be <= 2e-2)
+    library_baselines  N = 1: cuDNN SDPA (what the reference's mode="torch" reaches on torch 2.11) and flash-attn 2
+                       (mode="flash") forward / backward on K1 and K4, next to the b200vt kernels, same inputs
+    denoiser_it_s      the metric's second half: forward + backward of DiT block stacks through tools/bench_denoiser.py
+                       (HunyuanVideo 2 double + 4 single blocks = 1/10 of the stack, Wan2.1-14B 8 of 40 blocks, both
+                       Ulysses at N GPUs; CogVideoX-2B all 30 blocks at N = 1)
+    rowwise            N = 1: achieved GB/s and fraction of the measured copy bandwidth of the memory-bound kernels
 """
 from __future__ import annotations
 
@@ -124,11 +133,37 @@ class ClockSampler:
 # =====================================================================================================================
 # CPU legs (oracle port of the reference's torch path) — the only place bench.py executes oracle/
 # =====================================================================================================================
+REFERENCE_TREE = "/root/reference"
+_CPU_ATTENTION = {}
+
+
+def cpu_attention_fn():
+    """(callable, kind): the reference's own `attention(q, k, v, mode="torch")` (hyvideo_t2v/modules/attenion.py:60-156)
+    imported from the reference tree when it is present (development container; kind "reference"), else the oracle's
+    restatement of the same call (the GPU box has no /root/reference; kind "port")."""
+    if not _CPU_ATTENTION:
+        fn, kind = None, "port"
+        if os.path.isdir(os.path.join(REFERENCE_TREE, "videotuna")):
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+                import importlib
+                import make_golden
+                make_golden.install_shims()  # import shims for absent wheels (no arithmetic)
+                att = importlib.import_module("videotuna.models.hunyuan.hyvideo_t2v.modules.attenion")
+                fn, kind = (lambda q, k, v: att.attention(q, k, v, mode="torch")), "reference"
+            except Exception:  # noqa: BLE001
+                fn = None
+        if fn is None:
+            from oracle import ref_ops as R
+            fn, kind = R.hunyuan_attention_torch_fused, "port"
+        _CPU_ATTENTION.update(fn=fn, kind=kind)
+    return _CPU_ATTENTION["fn"], _CPU_ATTENTION["kind"]
+
+
 def _cpu_sample_step(q, k, v, do):
     """One fwd+bwd of the reference's mode="torch" attention on host tensors (B, Lq|Lk, H, D)."""
     import torch
-    from oracle import ref_ops as R
-    out = R.hunyuan_attention_torch_fused(q, k, v)
+    out = cpu_attention_fn()[0](q, k, v)
     torch.autograd.grad(out, (q, k, v), do)
 
 
@@ -190,7 +225,7 @@ def run_reference(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "B": 1, "L": SEQ, "H": HEADS, "D": HEAD_DIM,
                    "note": "each step is a bounded sample of the workload; TFLOP/s is size-independent"},
-        "cpu_baseline": {"value": round(tflops, 4), "unit": UNIT, "cores": host_threads(), "kind": "port",
+        "cpu_baseline": {"value": round(tflops, 4), "unit": UNIT, "cores": host_threads(), "kind": cpu_attention_fn()[1],
                          "sample": sample_text(lq, lk, heads)},
         "e2e": {"value": round(tflops, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -249,6 +284,177 @@ def other_configs(torch, dev, iters: int = 5):
         del q, k, v, do
         torch.cuda.empty_cache()
     return out
+
+
+def _ev_time(torch, fn, iters: int, warmup: int = 1) -> float:
+    """Device ms per call of fn: CUDA events around `iters` back-to-back calls after `warmup` untimed ones."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def library_baselines(torch, dev):
+    """cuDNN SDPA (F.scaled_dot_product_attention with the cuDNN backend: what the reference's mode="torch" / diffusers
+    processors reach on torch 2.11) and flash-attn 2 (the reference's mode="flash", attenion.py:108-123) forward and
+    backward on K1 and K4, next to the b200vt kernels: same process, same seeded inputs, device time from CUDA events."""
+    import math
+
+    import torch.nn.functional as F
+
+    import b200vt.ops as ops
+    shapes = {"k1_hunyuan": (1, SEQ, SEQ, HEADS, HEAD_DIM, 2), "k4_videocrafter2_spatial_self_level0_b2": (32, 2560, 2560, 5, 64, 10)}
+    out = {}
+    for name, (B, Lq, Lk, H, D, iters) in shapes.items():
+        g = torch.Generator(device=dev).manual_seed(SEED)
+        q, k, v, do = (torch.randn(B, n, H, D, device=dev, dtype=torch.bfloat16, generator=g) for n in (Lq, Lk, Lk, Lq))
+        scale = 1.0 / math.sqrt(D)
+        ff, fb = flops_fwd(Lq, Lk, H, D, B), 2.5 * flops_fwd(Lq, Lk, H, D, B)
+        rec = {}
+
+        def tf(flops, ms):
+            return round(flops / (ms * 1e-3) / 1e12, 1)
+
+        # ---- b200vt ----
+        o, lse = ops.attn_fwd(q, k, v, None, None, None, Lq, Lk, scale)
+        f_ms = _ev_time(torch, lambda: ops.attn_fwd(q, k, v, None, None, None, Lq, Lk, scale), iters)
+        b_ms = _ev_time(torch, lambda: ops.attn_bwd(do, q, k, v, o, lse, None, None, None, Lq, Lk, scale), iters)
+        rec["b200vt"] = {"fwd_ms": round(f_ms, 3), "bwd_ms": round(b_ms, 3), "fwd_tflops": tf(ff, f_ms), "bwd_tflops": tf(fb, b_ms),
+                         "fwd_bwd_tflops": tf(ff + fb, f_ms + b_ms)}
+        del o, lse
+        # ---- library kernels through autograd (forward timed alone; backward = retained-graph grad) ----
+        ql, kl, vl = (t.detach().requires_grad_(True) for t in (q, k, v))
+
+        def lib_arm(label, fwd):
+            try:
+                y = fwd()
+                f_ms = _ev_time(torch, fwd, iters)
+                b_ms = _ev_time(torch, lambda: torch.autograd.grad(y, (ql, kl, vl), do, retain_graph=True), iters)
+                rec[label] = {"fwd_ms": round(f_ms, 3), "bwd_ms": round(b_ms, 3), "fwd_tflops": tf(ff, f_ms),
+                              "bwd_tflops": tf(fb, b_ms), "fwd_bwd_tflops": tf(ff + fb, f_ms + b_ms)}
+                del y
+            except Exception as e:  # noqa: BLE001  (a library that refuses the shape is a result, not a bench failure)
+                rec[label] = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+            torch.cuda.empty_cache()
+
+        def cudnn_fwd():
+            from torch.nn.attention import SDPBackend, sdpa_kernel
+            with sdpa_kernel(SDPBackend.CUDNN_ATTENTION):
+                return F.scaled_dot_product_attention(ql.transpose(1, 2), kl.transpose(1, 2), vl.transpose(1, 2)).transpose(1, 2)
+
+        def fa2_fwd():
+            from flash_attn import flash_attn_func
+            return flash_attn_func(ql, kl, vl)
+
+        lib_arm("cudnn_sdpa", cudnn_fwd)
+        lib_arm("flash_attn_2", fa2_fwd)
+        rec["shape_BLqLkHD"] = [B, Lq, Lk, H, D]
+        out[name] = rec
+        del q, k, v, do, ql, kl, vl
+        torch.cuda.empty_cache()
+    try:
+        import flash_attn
+        out["versions"] = {"flash_attn": flash_attn.__version__, "cudnn": torch.backends.cudnn.version(), "torch": torch.__version__}
+    except Exception:  # noqa: BLE001
+        pass
+    return out
+
+
+def denoiser_it_s(world: int):
+    """Forward + backward of DiT block stacks (tools/bench_denoiser.py code path, `ours` arm: the reference blocks'
+    constructors with the b200vt drop-in forwards, per-block activation checkpointing, >= 3 warm-ups)."""
+    import types
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_denoiser as BD
+    runs = [("hunyuanvideo_720x1280x129f_lora", dict(model="hunyuan", double=2, single=4, layers=None), 10.0,
+             "2 of 20 double + 4 of 40 single blocks = exactly 1/10 of the block stack at the full 119 056 tokens"),
+            ("wan2.1_t2v_14b_480x832x81f", dict(model="wan", double=None, single=None, layers=8), 5.0,
+             "8 of 40 blocks at the full 32 760 tokens"),
+            ("cogvideox_2b_480x720x49f", dict(model="cogvideox", double=None, single=None, layers=None), 1.0,
+             "all 30 blocks")]
+    out = {}
+    for name, kw, scale, note in runs:
+        if kw["model"] == "cogvideox" and world > 1:
+            continue  # 30 heads: data parallel only (SURVEY 8e)
+        a = types.SimpleNamespace(arm="ours", steps=2, warmup=3, no_checkpoint=False, tokens_scale=1.0, check=False, **kw)
+        import gc
+
+        import torch
+        try:
+            line = BD.run(a, manage_dist=False, emit=False)
+        except Exception as e:  # noqa: BLE001
+            line = {"error": f"{type(e).__name__}: {str(e)[:200]}"} if int(os.environ.get("RANK", "0")) == 0 else None
+        gc.collect()
+        torch.cuda.empty_cache()
+        if line is None:
+            continue
+        if "error" in line:
+            out[name] = line
+            continue
+        out[name] = {"s_per_it_measured": line["s_per_it"], "blocks_measured": note,
+                     "s_per_it_full_stack": round(line["s_per_it"] * scale, 3),
+                     "it_per_s_full_stack": round(1.0 / (line["s_per_it"] * scale), 5),
+                     "full_stack_scaling": f"x{scale:g} (identical blocks; embeddings / final layer < 0.1 % of the FLOPs are not in the stack)",
+                     "steps": line["steps"], "warmup": line["warmup"], "parallelism": line["config"]["parallelism"],
+                     "attention_share_of_step": line.get("attention_share_of_step"),
+                     "attention_tflops_in_step": line.get("attention_tflops_in_step"), "peak_mem_GB": line["peak_mem_GB"]}
+    return out
+
+
+def rowwise_summary():
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench_rowwise as BR
+    recs = BR.run(iters=5, with_torch=False, emit=False)
+    return [{"kernel": r["kernel"], "shape": r["shape"], "GBps": r["ours_GBps"], "frac_of_hbm_peak": r["frac_of_hbm_peak"],
+             "ms": r["ours_ms"]} for r in recs] + [{"peak_GBps": recs[0]["peak_GBps"], "peak_kind": recs[0]["peak_kind"],
+                                                    "timing": recs[0]["timing"]}]
+
+
+def sp_parity_check(torch, dist, dev, world, S_loc, leaves, do, step_device, nh: int = 2):
+    """One sequence-parallel step against the UNSHARDED kernels on the gathered tensors, for heads [0, nh) (owned by rank
+    0 under Ulysses): outputs, dq/dk/dv of this rank's image rows and the text-row gradients. Every rank takes part in the
+    gathers; rank 0 computes the comparison. Returns {"max_rel_err": ..., ...} on rank 0, None elsewhere."""
+    import math
+
+    import b200vt.ops as ops
+    q, k, v, tq, tk, tv = leaves
+    out, grads = step_device()
+
+    def gather_rows(t):
+        loc = t[:, :, :nh].detach().contiguous()
+        parts = [torch.empty_like(loc) for _ in range(world)]
+        dist.all_gather(parts, loc)
+        return torch.cat(parts, dim=1)
+
+    full = [torch.cat([gather_rows(a), b[:, :, :nh].detach()], dim=1).contiguous() for a, b in ((q, tq), (k, tk), (v, tv))]
+    do_txt = do[:, S_loc:, :nh].float().contiguous()  # the text rows' output is replicated: their upstream gradients add up
+    dist.all_reduce(do_txt)
+    do_full = torch.cat([gather_rows(do[:, :S_loc]), do_txt.to(torch.bfloat16)], dim=1).contiguous()
+    if dist.get_rank() != 0:
+        return None
+    L = full[0].shape[1]
+    scale = 1.0 / math.sqrt(HEAD_DIM)
+    o_ref, lse = ops.attn_fwd(*full, None, None, None, L, L, scale)
+    dq_r, dk_r, dv_r = ops.attn_bwd(do_full, *full, o_ref, lse, None, None, None, L, L, scale)
+    n_img = L - TXT_TOKENS
+
+    def rel(a, b):
+        return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30))
+
+    errs = {"out_img": rel(out[:, :S_loc, :nh], o_ref[:, :S_loc]), "out_txt": rel(out[:, S_loc:, :nh], o_ref[:, n_img:]),
+            "dq": rel(grads[0][:, :, :nh], dq_r[:, :S_loc]), "dk": rel(grads[1][:, :, :nh], dk_r[:, :S_loc]),
+            "dv": rel(grads[2][:, :, :nh], dv_r[:, :S_loc]), "dq_txt": rel(grads[3][:, :, :nh], dq_r[:, n_img:]),
+            "dk_txt": rel(grads[4][:, :, :nh], dk_r[:, n_img:]), "dv_txt": rel(grads[5][:, :, :nh], dv_r[:, n_img:])}
+    worst = max(errs.values())
+    return {"max_rel_err": round(worst, 6), "tolerance": 2e-2, "ok": bool(worst <= 2e-2), "heads_checked": nh,
+            "per_tensor": {n_: round(e, 6) for n_, e in errs.items()},
+            "against": "unsharded b200vt attn_fwd / attn_bwd on the gathered (1, 119056, 2, 128) tensors, rank 0"}
 
 
 def run_ours(args):
@@ -322,6 +528,7 @@ def run_ours(args):
             return out, torch.autograd.grad(out, (q, k, v, tq, tk, tv), do)
 
     step_flops = flops_fwd_bwd(SEQ, SEQ)  # whole job, all ranks
+    fused_exchange = world > 1 and sp.fused_exchange_available(q, None)
 
     def sync_all():
         torch.cuda.synchronize()
@@ -360,6 +567,11 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = step_flops / (ms_per_step * 1e-3) / 1e12
 
+    # ---- N > 1: the sequence-parallel step against the unsharded kernels (2 heads), in the driver's own run -------
+    sp_parity = None
+    if world > 1 and not args.no_extras:
+        sp_parity = sp_parity_check(torch, dist, dev, world, S_loc, leaves, do, step_device)
+
     # ---- end to end with host buffers ----------------------------------------------------------------------------
     # N = 1: the library's host-buffer entry point (functional.HostAttention): pinned (B, L, H, D) tensors in, pinned
     # results out, head groups pipelined over copy-in / compute / copy-out streams. N > 1: each rank copies its
@@ -375,25 +587,50 @@ def run_ours(args):
         def step_e2e():
             host_attn(*host_in, *host_out)
     else:
-        host_in = [t.detach().to("cpu").pin_memory() for t in (*leaves, do)]
-        host_out = None
+        # every rank's shard lives in pinned host memory; sp.HostUlyssesAttention pipelines head groups: copy-in of group
+        # g+1 || all-to-all + attention + backward of group g || copy-out of group g-1
+        host_in = [t.detach().to("cpu").pin_memory() for t in (*leaves, do)]  # q, k, v, tq, tk, tv, dO
+        host_out = [torch.empty(t.shape, dtype=torch.bfloat16).pin_memory() for t in (do, q, k, v, tq, tk, tv)]
+        del q, k, v, tq, tk, tv, do, leaves
+        torch.cuda.empty_cache()
+        n_groups = max(g_ for g_ in (6, 4, 3, 2, 1) if HEADS % g_ == 0 and (HEADS // g_) % world == 0)
+        host_attn = sp.HostUlyssesAttention(S_loc, TXT_TOKENS, HEADS, HEAD_DIM, head_groups=n_groups)
+        hq, hk, hv, htq, htk, htv, hdo = host_in
 
         def step_e2e():
-            nonlocal host_out
-            dev_in = [h.to(dev, non_blocking=True) for h in host_in]
-            ins = [t.requires_grad_(True) for t in dev_in[:-1]]
-            out, grads = step_device(*ins, dev_in[-1])
-            results = (out, *grads)
-            if host_out is None:
-                host_out = [torch.empty(t.shape, dtype=t.dtype, device="cpu").pin_memory() for t in results]
-            for h, t in zip(host_out, results):
-                h.copy_(t, non_blocking=True)
+            host_attn(hq, hk, hv, hdo, host_out[0], host_out[1], host_out[2], host_out[3], htq, htk, htv,
+                      host_out[4], host_out[5], host_out[6])
 
     step_e2e()  # allocates buffers; untimed
     e2e_ms = timed(step_e2e, e2e_steps) / e2e_steps
     h2d = sum(h.numel() * h.element_size() for h in host_in)
     d2h = sum(h.numel() * h.element_size() for h in host_out)
     e2e_value = step_flops / (e2e_ms * 1e-3) / 1e12
+
+    del host_attn, host_in, host_out
+    import gc
+    gc.collect()
+    torch.cuda.empty_cache()
+
+    # ---- the metric's second half and the claims around the headline, measured in this run (all ranks take part) -----
+    extras, extras_clk = {}, None
+    if not args.no_extras:
+        xclocks = ClockSampler(local)
+        if rank == 0:
+            xclocks.start()
+        try:
+            extras["denoiser_it_s"] = denoiser_it_s(world)
+        except Exception as e:  # noqa: BLE001  (the headline line must still be printed)
+            extras["denoiser_it_s"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        if world == 1:
+            for key, fn in (("library_baselines", lambda: library_baselines(torch, dev)), ("rowwise", rowwise_summary)):
+                try:
+                    extras[key] = fn()
+                except Exception as e:  # noqa: BLE001
+                    extras[key] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+                gc.collect()
+                torch.cuda.empty_cache()
+        extras_clk = xclocks.stop() if rank == 0 else None
 
     if rank != 0:
         if world > 1:
@@ -416,11 +653,14 @@ def run_ours(args):
     if os.path.exists(tpath):
         with open(tpath) as fh:
             traffic = json.load(fh).get(f"{dom}@k1_h{heads_loc}")
+    traffic_source = ("profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of "
+                      "this kernel at this shape (a profiler counter: cannot be measured inside the timed run)"
+                      if traffic is not None else "no ncu capture committed for this head count")
     roofline = {
         "bound": "tensor", "kernel": f"{dom}_kernel<128>", "achieved": round(achieved, 1),
         "peak": peaks["sustained"], "unit": UNIT, "frac": round(achieved / peaks["sustained"], 4),
         "peak_kind": "sustained bf16 cuBLAS, " + peaks["source"], "frac_of_burst": round(achieved / peaks["burst"], 4),
-        "traffic": traffic,
+        "traffic": traffic, "traffic_source": traffic_source,
         "kernels": {n: {"avg_ms": round(kk["avg_ms"], 3), "launches_per_step": kk["launches_per_step"],
                         **({"tflops": round(fl[n] / (kk["avg_ms"] * 1e-3) / 1e12, 1)} if n in fl else {})}
                     for n, kk in kern.items()},
@@ -431,8 +671,6 @@ def run_ours(args):
     # ---- the other BASELINE.json configurations, attention only (N = 1; context for the reader, not the headline) ----
     others = None
     if world == 1:
-        del host_attn, host_in, host_out
-        torch.cuda.empty_cache()
         others = other_configs(torch, dev)
 
     # ---- CPU baseline (N = 1 only): oracle port of the reference's torch path on a bounded sample ----------------
@@ -440,7 +678,7 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         lq, lk, heads, _ = cpu_size_sample(target_s=12.0)
         tf, dt = cpu_time_sample(lq, lk, heads, steps=1, warmup=0)
-        cpu = {"value": round(tf, 4), "unit": UNIT, "cores": host_threads(), "kind": "port",
+        cpu = {"value": round(tf, 4), "unit": UNIT, "cores": host_threads(), "kind": cpu_attention_fn()[1],
                "sample": sample_text(lq, lk, heads) + f"; {dt:.1f} s"}
 
     line = {
@@ -452,16 +690,20 @@ def run_ours(args):
                    "parallelism": "single" if world == 1 else f"ulysses_sp{world}",
                    **({} if world == 1 else {"exchange": (
                        "q/k/v + gradients: NCCL all_to_all; forward O: peer stores from the attention epilogue "
-                       "(symmetric memory over NVLink)" if sp.fused_exchange_available(q, None) else "NCCL all_to_all")}),
+                       "(symmetric memory over NVLink)" if fused_exchange else "NCCL all_to_all")}),
                    "l2": "inputs (4 x 731 MB) exceed the 126 MB L2; no flush needed"},
         "clocks": clk,
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps,
-                "api": "functional.HostAttention (head-group pipeline)" if world == 1 else "sp.UlyssesAttention + copies"},
+                "api": ("functional.HostAttention (head-group pipeline)" if world == 1
+                        else "sp.HostUlyssesAttention (head-group pipeline: copy-in || all-to-all + attention + backward || copy-out)")},
         "gpu_launches": gpu_launches,
         "roofline": roofline,
         "cpu_baseline": cpu,
         **({"other_configs": others} if others else {}),
+        **({"sp_parity": sp_parity} if sp_parity is not None else {}),
+        **extras,
+        **({"extras_clocks": extras_clk} if extras_clk is not None else {}),
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -477,6 +719,8 @@ def main():
     ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the ~15 s host-core leg (profiling runs)")
     ap.add_argument("--head-groups", type=int, default=4, help="pipeline depth of the host-buffer (e2e) entry point")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip sp_parity / library_baselines / denoiser_it_s / rowwise (profiling runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print(f"note: --warmup {args.warmup} is below the 3 the timing rules ask for", file=sys.stderr)

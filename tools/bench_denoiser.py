@@ -298,7 +298,7 @@ def build_cogvideox(cfg, n_layers, dev):
         torch.set_default_dtype(torch.float32)
 
 
-def main():
+def parse(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--model", choices=tuple(CONFIGS), default="hunyuan")
     ap.add_argument("--arm", choices=("ours", "torch"), default="ours")
@@ -311,14 +311,19 @@ def main():
     ap.add_argument("--tokens-scale", type=float, default=1.0, help="debug: shrink the latent frame count")
     ap.add_argument("--check", action="store_true", help="run one forward+backward of BOTH arms on the same weights and "
                     "print the relative difference of the outputs and input gradients, then exit")
-    args = ap.parse_args()
+    return ap.parse_args(argv)
 
+
+def run(args, manage_dist: bool = True, emit: bool = True):
+    """One measurement; returns the result line (rank 0) or None. manage_dist=False: the caller (bench.py) owns the process
+    group and the CUDA device; emit=False: do not print."""
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        if manage_dist:
+            dist.init_process_group("nccl", device_id=dev)
         assert args.arm == "ours", "the torch arm is single-GPU"
     L.call("vt_init", local)
     torch.manual_seed(SEED)
@@ -461,10 +466,12 @@ def main():
 
         def cos_sim(a, b):
             return float(F.cosine_similarity(a.float().flatten(), b.float().flatten(), dim=0))
-        print(json.dumps({"tool": "bench_denoiser --check", "model": args.model, **layers_desc, "img_tokens": n_img,
-                          "out_max_rel_diff_ours_vs_torch": round(rel(y_a, y_b), 5),
-                          "input_grad_cosine_ours_vs_torch": round(cos_sim(g_a, g_b), 6)}), flush=True)
-        return
+        chk = {"tool": "bench_denoiser --check", "model": args.model, **layers_desc, "img_tokens": n_img,
+               "out_max_rel_diff_ours_vs_torch": round(rel(y_a, y_b), 5),
+               "input_grad_cosine_ours_vs_torch": round(cos_sim(g_a, g_b), 6)}
+        if emit:
+            print(json.dumps(chk), flush=True)
+        return chk
 
     def sync_all():
         torch.cuda.synchronize()
@@ -492,6 +499,7 @@ def main():
     attn_launches = sum(L.profile_read(k)[1] for k in (L.K_ATTN_FWD, L.K_ATTN_BWD))
     L.profile_enable(False)
     s_per_it = float(ms.item()) / 1e3 / args.steps
+    line = None
     if rank == 0:
         line = {
             "tool": "bench_denoiser", "model": args.model, "arm": args.arm, "n_gpus": world,
@@ -513,10 +521,17 @@ def main():
             line["attention_share_of_step"] = round(attn_ms / 1e3 / args.steps / s_per_it, 4)
             line["attention_launches_per_it"] = attn_launches / args.steps
             line["attention_tflops_in_step"] = round(attn_exec / world / (attn_ms / 1e3 / args.steps) / 1e12, 1)
-        print(json.dumps(line), flush=True)
+        if emit:
+            print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        if manage_dist:
+            dist.destroy_process_group()
+    return line
+
+
+def main():
+    run(parse())
 
 
 if __name__ == "__main__":

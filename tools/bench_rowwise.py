@@ -35,7 +35,17 @@ def peak_gbs():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--no-torch", action="store_true", help="skip the stock-PyTorch comparison columns")
     args = ap.parse_args()
+    run(args.iters, with_torch=not args.no_torch, emit=True)
+
+
+def run(iters: int = 10, with_torch: bool = True, emit: bool = True):
+    """Returns the list of records (also printed when emit). with_torch=False skips the stock-PyTorch comparison arm
+    (bench.py's `rowwise` key: our kernels only)."""
+    import types
+    args = types.SimpleNamespace(iters=iters)
+    records = []
     dev = "cuda"
     peak, src = peak_gbs()
     g = torch.Generator(device=dev).manual_seed(20230211)
@@ -50,7 +60,14 @@ def main():
                "peak_GBps": peak, "peak_kind": src, "timing": device_time_ms.last_mode}
         if note:
             rec["note"] = note
-        print(json.dumps(rec), flush=True)
+        if not with_torch:
+            rec.pop("torch_ops_ms"), rec.pop("speedup_vs_torch_ops")
+        records.append(rec)
+        if emit:
+            print(json.dumps(rec), flush=True)
+
+    def timeit_ref(fn, iters):
+        return timeit(fn, iters) if with_torch else float("nan")
 
     # ---- LayerNorm + modulate (Hunyuan K1 image stream; Wan C5 with the fp32 residual stream) -----------------------
     for tag, (B, L, C), xdt in (("hunyuan_k1", (1, 119056, 3072), torch.bfloat16), ("wan_c5_fp32_stream", (1, 32760, 5120), torch.float32)):
@@ -64,9 +81,9 @@ def main():
 
         def ref():
             return (F.layer_norm(x.float(), (C,), eps=1e-6) * (1 + sc[:, None]) + sh[:, None]).to(torch.bfloat16)
-        yr = ref()
-        rf_ms = timeit(ref, args.iters)
-        rb_ms = timeit(lambda: torch.autograd.grad(yr, x, dy, retain_graph=True), args.iters)
+        yr = ref() if with_torch else None
+        rf_ms = timeit_ref(ref, args.iters)
+        rb_ms = timeit_ref(lambda: torch.autograd.grad(yr, x, dy, retain_graph=True), args.iters)
         n = B * L * C
         report(f"ln_modulate_fwd[{tag}]", (B, L, C), n * (esz + 2), f_ms, rf_ms)
         report(f"ln_modulate_bwd[{tag}]", (B, L, C), n * (2 + esz + esz), b_ms, rb_ms)
@@ -76,15 +93,15 @@ def main():
     for tag, (B, L, C), xdt in (("hunyuan_k1", (1, 119056, 3072), torch.bfloat16), ("wan_c5_fp32_stream", (1, 32760, 5120), torch.float32)):
         x, br, gate = rn(B, L, C, dtype=xdt), rn(B, L, C), rn(B, C, dtype=torch.float32)
         f_ms = timeit(lambda: Fn.gate_residual(x, br, gate), args.iters)
-        rf_ms = timeit(lambda: x + br * gate[:, None].to(br.dtype if xdt == torch.bfloat16 else torch.float32), args.iters)
+        rf_ms = timeit_ref(lambda: x + br * gate[:, None].to(br.dtype if xdt == torch.bfloat16 else torch.float32), args.iters)
         n = B * L * C
         report(f"gate_residual_fwd[{tag}]", (B, L, C), n * (2 * x.element_size() + 2), f_ms, rf_ms)
         xg, bg, gg = x.detach().requires_grad_(True), br.detach().requires_grad_(True), gate.detach().requires_grad_(True)
         yg = Fn.gate_residual(xg, bg, gg)
         dyg = rn(B, L, C, dtype=xdt)
         b_ms = timeit(lambda: torch.autograd.grad(yg, (xg, bg, gg), dyg, retain_graph=True), args.iters)
-        yr_ = xg + bg * gg[:, None].to(bg.dtype if xdt == torch.bfloat16 else torch.float32)
-        rb_ms = timeit(lambda: torch.autograd.grad(yr_, (xg, bg, gg), dyg, retain_graph=True), args.iters)
+        yr_ = (xg + bg * gg[:, None].to(bg.dtype if xdt == torch.bfloat16 else torch.float32)) if with_torch else None
+        rb_ms = timeit_ref(lambda: torch.autograd.grad(yr_, (xg, bg, gg), dyg, retain_graph=True), args.iters)
         # dy read, branch read (for dgate), dbranch write; dx = dy is returned without a copy
         report(f"gate_residual_bwd[{tag}]", (B, L, C), n * (x.element_size() + 2 + 2), b_ms, rb_ms)
         del x, br, xg, bg, yg, dyg, yr_
@@ -105,7 +122,7 @@ def main():
         xr, xi = nf.reshape(*nf.shape[:-1], -1, 2).unbind(-1)
         rot = torch.stack([-xi, xr], dim=-1).flatten(3)
         return (nf * cos.view(1, L, 1, D) + rot * sin.view(1, L, 1, D)).to(q.dtype)
-    rf_ms = timeit(ref_rope, max(3, args.iters // 3))
+    rf_ms = timeit_ref(ref_rope, max(3, args.iters // 3))
     n = B * L * H * D
     report("qk_rmsnorm_rope_fwd[hunyuan_k1, strided q of fused qkv]", (B, L, H, D), n * 4 + 2 * L * D * 4, f_ms, rf_ms,
            note="reference = hunyuan RMSNorm (fp32 temporaries) + apply_rotary_emb (rotate_half stack/flatten) as torch ops")
@@ -122,8 +139,8 @@ def main():
         xr, xi = nf.reshape(*nf.shape[:-1], -1, 2).unbind(-1)
         rot = torch.stack([-xi, xr], dim=-1).flatten(3)
         return (nf * cos.view(1, L, 1, D) + rot * sin.view(1, L, 1, D)).to(qr.dtype)
-    yr_ = ref_rope_g()
-    rb_ms = timeit(lambda: torch.autograd.grad(yr_, qr, dyq, retain_graph=True), max(3, args.iters // 3))
+    yr_ = ref_rope_g() if with_torch else None
+    rb_ms = timeit_ref(lambda: torch.autograd.grad(yr_, qr, dyq, retain_graph=True), max(3, args.iters // 3))
     report("qk_rmsnorm_rope_bwd[hunyuan_k1, strided q of fused qkv]", (B, L, H, D), n * 6 + 2 * L * D * 4 + B * L * H * 4,
            b_ms, rb_ms)
     del qkv, q, qg, yq, dyq, qr, yr_
@@ -143,15 +160,15 @@ def main():
             it[0] = (it[0] + 1) % nbuf
             return it[0]
         f_ms = timeit(lambda: Fn.groupnorm_silu(xs[nxt()], gw, gb, 32, 1e-5, silu=True), args.iters * 2)
-        rf_ms = timeit(lambda: F.silu(F.group_norm(xs[nxt()].float(), 32, gw, gb, 1e-5).to(torch.bfloat16)), args.iters * 2)
+        rf_ms = timeit_ref(lambda: F.silu(F.group_norm(xs[nxt()].float(), 32, gw, gb, 1e-5).to(torch.bfloat16)), args.iters * 2)
         ys = [Fn.groupnorm_silu(x, gw, gb, 32, 1e-5, silu=True) for x in xs]
-        yrs = [F.silu(F.group_norm(x.float(), 32, gw, gb, 1e-5).to(torch.bfloat16)) for x in xs]
+        yrs = [F.silu(F.group_norm(x.float(), 32, gw, gb, 1e-5).to(torch.bfloat16)) for x in xs] if with_torch else None
 
         def bwd(outs):
             i = nxt()
             return torch.autograd.grad(outs[i], xs[i], dys[i], retain_graph=True)
         b_ms = timeit(lambda: bwd(ys), args.iters * 2)
-        rb_ms = timeit(lambda: bwd(yrs), args.iters * 2)
+        rb_ms = timeit_ref(lambda: bwd(yrs), args.iters * 2)
         n = math.prod(shape)
         note = (f"reference = GroupNormSpecific (x.float() -> group_norm -> type(x.dtype)) + SiLU; {nbuf} rotating buffers "
                 "(tensor < L2)")
@@ -169,7 +186,7 @@ def main():
     def ref_t():  # lvdm einsum / softmax / einsum (attention.py:128-144)
         s = torch.einsum("b i d, b j d -> b i j", qt, kt) * sc
         return torch.einsum("b i j, b j d -> b i d", s.softmax(dim=-1), vt)
-    rf_ms = timeit(ref_t, args.iters)
+    rf_ms = timeit_ref(ref_t, args.iters)
     report("temporal_attn_fwd[vc2 level 0]", (Bt, N, H, D), q.numel() * 2 * 4, f_ms, rf_ms)
     do = rn(Bt, N, H, D)
     b_ms = timeit(lambda: ops.temporal_attn_bwd(do, q, k, v, None, sc), args.iters)
@@ -177,8 +194,9 @@ def main():
     dot = do.permute(0, 2, 1, 3).reshape(Bt * H, N, D)
     s_ = torch.einsum("b i d, b j d -> b i j", qr, kr) * sc
     out_r = torch.einsum("b i j, b j d -> b i d", s_.softmax(dim=-1), vr)
-    rb_ms = timeit(lambda: torch.autograd.grad(out_r, (qr, kr, vr), dot, retain_graph=True), args.iters)
+    rb_ms = timeit_ref(lambda: torch.autograd.grad(out_r, (qr, kr, vr), dot, retain_graph=True), args.iters)
     report("temporal_attn_bwd[vc2 level 0]", (Bt, N, H, D), q.numel() * 2 * 7, b_ms, rb_ms)
+    return records
 
 
 if __name__ == "__main__":

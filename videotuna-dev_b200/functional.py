@@ -63,6 +63,22 @@ def attention_blhd(q: Tensor, k: Tensor, v: Tensor, softmax_scale: Optional[floa
 # ---------------------------------------------------------------------------------------------------------------------
 # host-buffer entry point: attention fwd+bwd on pinned host tensors, pipelined over head groups
 # ---------------------------------------------------------------------------------------------------------------------
+def copy_head_group(dev_t: Tensor, host_t: Tensor, h0: int, to_device: bool, stream) -> None:
+    """One strided DMA per sample between heads [h0, h0 + hg) of a pinned host (B, L, H, D) bf16 tensor and a contiguous
+    device (B, L, hg, D) tensor, enqueued on `stream` (cudaMemcpy2DAsync: L rows of hg*D elements, host pitch H*D)."""
+    from . import _lib
+    B, L, hg, D = dev_t.shape
+    es = dev_t.element_size()
+    for b in range(B):
+        hptr = host_t.data_ptr() + (b * host_t.stride(0) + h0 * host_t.stride(2)) * es
+        dptr = dev_t.data_ptr() + b * dev_t.stride(0) * es
+        hpitch, dpitch, width = host_t.stride(1) * es, hg * D * es, hg * D * es
+        if to_device:
+            _lib.call("vt_memcpy2d_async", _lib.vp(dptr), dpitch, _lib.vp(hptr), hpitch, width, L, 1, _lib.vp(stream.cuda_stream))
+        else:
+            _lib.call("vt_memcpy2d_async", _lib.vp(hptr), hpitch, _lib.vp(dptr), dpitch, width, L, 0, _lib.vp(stream.cuda_stream))
+
+
 class HostAttention:
     """softmax(q k^T * scale) v forward + backward for q, k, v, dO that live in PINNED HOST memory as (B, L, H, D)
     bf16 — the activation-offload case of long-sequence DiT finetuning (one HunyuanVideo layer's q, k, v at 119 056

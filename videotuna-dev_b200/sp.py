@@ -306,6 +306,92 @@ class UlyssesAttention:
         return torch.cat([img, txt], dim=1)
 
 
+class HostUlyssesAttention:
+    """Sequence-parallel joint attention forward + backward for activations that live in PINNED HOST memory (the
+    activation-offload case of long-sequence DiT finetuning, one rank's shard per process): the multi-GPU counterpart of
+    functional.HostAttention. Heads are independent, so the H heads are cut into groups of `hg` (a multiple of the SP
+    world size) and pipelined on three streams: group g+1's q, k, v, dO shards are copied in (strided DMA out of the
+    (1, L/P, H, D) host layout) while group g runs all-to-all -> attention -> all-to-all -> backward, and group g-1's
+    out, dq, dk, dv are copied out. The replicated text tensors (a few MB) travel once per call.
+    Same arithmetic as UlyssesAttention + autograd on device tensors (bench.py sp_parity / tests)."""
+
+    def __init__(self, s_loc: int, T: int, H: int, D: int, head_groups: int, group=None, device=None):
+        P = _world(group)
+        if H % head_groups != 0 or (H // head_groups) % P != 0:
+            raise ValueError(f"head_groups={head_groups} must divide H={H} into groups that are multiples of the SP size {P}")
+        self.s_loc, self.T, self.H, self.D, self.G, self.hg = s_loc, T, H, D, head_groups, H // head_groups
+        self.group = group
+        self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.attn = UlyssesAttention(group)
+
+        def buf(rows):
+            return torch.empty((1, rows, self.hg, D), dtype=torch.bfloat16, device=self.dev)
+
+        self.inp = [[buf(s_loc), buf(s_loc), buf(s_loc), buf(s_loc + T)] for _ in range(2)]
+        self.txt = [torch.empty((1, T, H, D), dtype=torch.bfloat16, device=self.dev) for _ in range(3)] if T else None
+        self.s_in, self.s_out = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]
+        self.ev_free = [torch.cuda.Event() for _ in range(2)]
+        self.ev_done = [torch.cuda.Event() for _ in range(2)]
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]
+        self.outp = [None, None]
+
+    def __call__(self, q: Tensor, k: Tensor, v: Tensor, dout: Tensor, out: Tensor, dq: Tensor, dk: Tensor, dv: Tensor,
+                 tq: Optional[Tensor] = None, tk: Optional[Tensor] = None, tv: Optional[Tensor] = None,
+                 dtq: Optional[Tensor] = None, dtk: Optional[Tensor] = None, dtv: Optional[Tensor] = None):
+        """q, k, v, dq, dk, dv: pinned host (1, L/P, H, D); dout, out: (1, L/P + T, H, D); tq/tk/tv and their gradient
+        buffers: (1, T, H, D) (replicated text, "rear"). A rank's text gradients cover its own head slices only (zeros
+        elsewhere), as with UlyssesAttention. Everything is ENQUEUED; synchronise the current stream before reading."""
+        from .functional import copy_head_group
+        cur = torch.cuda.current_stream(self.dev)
+        self.s_in.wait_stream(cur)
+        self.s_out.wait_stream(cur)
+        T = self.T
+        if T:
+            with torch.cuda.stream(self.s_in):
+                for d_t, h_t in zip(self.txt, (tq, tk, tv)):
+                    d_t.copy_(h_t, non_blocking=True)
+            t_grads = [torch.zeros_like(t) for t in self.txt]
+        for g in range(self.G):
+            slot, h0 = g & 1, g * self.hg
+            with torch.cuda.stream(self.s_in):
+                if g >= 2:
+                    self.s_in.wait_event(self.ev_free[slot])
+                for d_t, h_t in zip(self.inp[slot], (q, k, v, dout)):
+                    copy_head_group(d_t, h_t, h0, True, self.s_in)
+                self.ev_in[slot].record(self.s_in)
+            cur.wait_event(self.ev_in[slot])
+            if g >= 2:
+                cur.wait_event(self.ev_out[slot])
+            qd, kd, vd, dod = self.inp[slot]
+            leaves = [t.detach().requires_grad_(True) for t in (qd, kd, vd)]
+            kw = {}
+            if T:
+                tl = [t[:, :, h0:h0 + self.hg].detach().requires_grad_(True) for t in self.txt]
+                kw = dict(joint_tensor_query=tl[0], joint_tensor_key=tl[1], joint_tensor_value=tl[2], joint_strategy="rear")
+                leaves += tl
+            o = self.attn(None, *leaves[:3], **kw)
+            grads = torch.autograd.grad(o, leaves, dod)
+            if T:
+                for acc, gr in zip(t_grads, grads[3:]):
+                    acc[:, :, h0:h0 + self.hg].copy_(gr)
+            self.outp[slot] = (o.detach(), *grads[:3])
+            self.ev_free[slot].record(cur)
+            self.ev_done[slot].record(cur)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_done[slot])
+                for d_t, h_t in zip(self.outp[slot], (out, dq, dk, dv)):
+                    d_t.record_stream(self.s_out)
+                    copy_head_group(d_t, h_t, h0, False, self.s_out)
+                self.ev_out[slot].record(self.s_out)
+        if T:
+            for acc, h_t in zip(t_grads, (dtq, dtk, dtv)):
+                if h_t is not None:
+                    h_t.copy_(acc, non_blocking=True)
+        cur.wait_stream(self.s_out)
+        return out, dq, dk, dv
+
+
 def ulysses_attention(q: Tensor, k: Tensor, v: Tensor, group=None, softmax_scale: Optional[float] = None,
                       attn_fn: Optional[Callable] = None) -> Tensor:
     """Plain Ulysses attention on sequence-sharded (B, L/P, H, D) tensors (Wan usp_attn_forward core)."""

@@ -271,6 +271,24 @@ class ResBlockShell(nn.Module):
         return self._fwd(self, x, emb, batch_size)
 
 
+class TemporalConvBlockShell(nn.Module):
+    """lvdm TemporalConvBlock.__init__ (openaimodel3d.py:263-301), spatial_aware=False."""
+
+    def __init__(self, channels, dropout=0.0):
+        super().__init__()
+        from b200vt import blocks
+
+        def stage(with_dropout):
+            layers = [nn.GroupNorm(32, channels), nn.SiLU()] + ([nn.Dropout(dropout)] if with_dropout else [])
+            return nn.Sequential(*layers, nn.Conv3d(channels, channels, (3, 1, 1), padding=(1, 0, 0)))
+
+        self.conv1, self.conv2, self.conv3, self.conv4 = stage(False), stage(True), stage(True), stage(True)
+        self._fwd = blocks.lvdm_temporal_conv_block_forward
+
+    def forward(self, x):
+        return self._fwd(self, x)
+
+
 class DiffusersAttentionShell(nn.Module):
     """diffusers 0.32.2 `Attention` as CogVideoXBlock builds it (query_dim=dim, heads, dim_head, qk_norm="layer_norm",
     eps=1e-6, bias=True, out_bias=True): to_q/to_k/to_v, to_out = [Linear, Dropout], norm_q/norm_k = LayerNorm(dim_head),

@@ -260,3 +260,50 @@ def test_qk_rmsnorm_rope_full_k1_size_matches_torch_fp32():
     assert float(torch.nn.functional.cosine_similarity(gq.float().flatten(), gqr.flatten(), dim=0)) > COS
     assert float((gq.float() - gqr).abs().max() / gqr.abs().max()) < 2 * TOL
     assert float((gw - gwr).abs().max() / gwr.abs().max()) < TOL
+
+
+def test_registered_op_route_matches_eager_fast_path():
+    """Under a multi-rank launch (and under tracing / dispatch modes) the ops run through torch.library's registered
+    custom ops instead of the eager autograd.Function path (ops._make_eager): same results, and the registered route's
+    stricter rules hold (no output may alias another output or an input) — forward and backward."""
+    import b200vt.ops as ops
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(9)
+    B, L, C = 2, 70, 256
+    x = torch.randn(B, L, C, device=dev, generator=g).bfloat16()
+    br = torch.randn(B, L, C, device=dev, generator=g).bfloat16()
+    vecs = [torch.randn(B, C, device=dev, generator=g) * 0.1 for _ in range(6)]
+    dy = torch.randn(B, L, C, device=dev, generator=g).bfloat16()
+
+    def run(reg, split):
+        ln = ops.ln_modulate_fwd.op if reg else ops.ln_modulate_fwd
+        gr = ops.gate_residual_fwd.op if reg else ops.gate_residual_fwd
+        leaves = [t.clone().requires_grad_(True) for t in (x, br, *vecs)]
+        xx, bb, sc, sh, sc2, sh2, gt, gt2 = leaves
+        if split:
+            y = ln(xx, None, None, sc, sh, 1e-6, sc2, sh2, split)[0]
+            z = gr(y, bb, gt, gt2, split)
+        else:
+            y = ln(xx, None, None, sc, sh, 1e-6)[0]
+            z = gr(y, bb, gt)
+        grads = torch.autograd.grad(z, [t for t in leaves if split or t is not sc2 and t is not sh2 and t is not gt2], dy)
+        return [z.detach(), *grads]
+
+    for split in (0, 25):
+        a, b = run(True, split), run(False, split)
+        for u, v in zip(a, b):
+            assert float((u.float() - v.float()).abs().max()) <= 1e-2 * float(v.float().abs().max()) + 1e-6
+    # joint q/k/v op through the registered route
+    H, D, T = 2, 64, 10
+    iq = torch.randn(1, L, 3, H, D, device=dev, generator=g).bfloat16().requires_grad_(True)
+    tq = torch.randn(1, T, 3, H, D, device=dev, generator=g).bfloat16().requires_grad_(True)
+    w = [(1 + 0.1 * torch.randn(D, device=dev, generator=g)).requires_grad_(True) for _ in range(4)]
+    cs, sn = torch.randn(L, D, device=dev, generator=g).cos(), torch.randn(L, D, device=dev, generator=g).sin()
+    outs = {}
+    for reg in (True, False):
+        f = ops.joint_qkv_fwd.op if reg else ops.joint_qkv_fwd
+        q, k, v, _, _ = f(iq, tq, *w, cs, sn, 1e-6)
+        gs = torch.autograd.grad([q, k, v], [iq, tq, *w], [torch.ones_like(q), torch.ones_like(k), torch.ones_like(v)])
+        outs[reg] = [q.detach(), k.detach(), v.detach(), *gs]
+    for u, v in zip(outs[True], outs[False]):
+        assert float((u.float() - v.float()).abs().max()) <= 1e-3 * float(v.float().abs().max()) + 1e-6

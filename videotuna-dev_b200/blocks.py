@@ -18,6 +18,7 @@ reference forward                                                          repla
   lvdm SpatialTransformer.forward       lvdm/modules/attention.py:376-392       lvdm_spatial_transformer_forward
   lvdm TemporalTransformer.forward      lvdm/modules/attention.py:475-519       lvdm_temporal_transformer_forward
   lvdm ResBlock._forward                lvdm/modules/networks/openaimodel3d.py:229-255   lvdm_resblock_forward
+  lvdm TemporalConvBlock.forward        lvdm/modules/networks/openaimodel3d.py:303-310   lvdm_temporal_conv_block_forward
   diffusers CogVideoXAttnProcessor2_0   [ext, diffusers 0.32.2]                 CogVideoXAttnProcessor
   diffusers CogVideoXBlock.forward      [ext, diffusers 0.32.2]                 cogvideox_block_forward
   diffusers HunyuanVideoAttnProcessor2_0 [ext, diffusers 0.32.2]                HunyuanVideoAttnProcessor
@@ -428,6 +429,19 @@ def lvdm_resblock_forward(self, x: Tensor, emb: Tensor, batch_size: Optional[int
         h = self.temopral_conv(h)
         h = h.transpose(1, 2).reshape(bt, ch, hh, ww)
     return h
+
+
+def lvdm_temporal_conv_block_forward(self, x: Tensor) -> Tensor:
+    """Drop-in body of TemporalConvBlock.forward (openaimodel3d.py:258-310, one per ResBlock with use_temporal_conv: 22 in
+    the VideoCrafter2 UNet): four stages of GroupNorm(32) -> SiLU -> [Dropout] -> Conv3d on (b, c, t, h, w) plus the
+    identity. Each GroupNorm + SiLU pair is one pass of the 5-D cluster kernel; the (3,1,1) convolutions stay cuDNN."""
+    _require(x.is_cuda and x.dtype in (_BF16, torch.float32) and x.dim() == 5, "CUDA bf16/fp32 (b, c, t, h, w) activations only")
+    h = x
+    for stage in (self.conv1, self.conv2, self.conv3, self.conv4):
+        norm, act = stage[0], stage[1]
+        _require(isinstance(norm, nn.GroupNorm) and isinstance(act, nn.SiLU), "unexpected TemporalConvBlock layout")
+        h = stage[2:](_lvdm_gn(norm, h, silu=True))
+    return h + x
 
 
 # =====================================================================================================================

@@ -560,6 +560,118 @@ groupnorm_bwd_bulk_kernel(const T* __restrict__ dy, const T* __restrict__ x, con
   const float nmr = -mean * rstd;
   float tot[2] = {0.f, 0.f};
   ChanIter ch(start + tid * VEC, GB_THREADS * VEC, S);
+  if constexpr (sizeof(T) == 2) {
+    if (apply_silu) {
+      // ---- bf16 + SiLU fast path: packed f32x2 arithmetic and DEFERRED bin updates ----------------------------------
+      // The first version spent 54 executed instructions per element (issue slots 70 % busy, profiles/r1_s22): scalar FMAs
+      // and a ten-shuffle warp reduction per 8-element vector. Here every arithmetic step handles two elements
+      // (fma.rn.f32x2), and while a warp's 32 vectors stay inside one channel — the common case: a channel is S elements
+      // long — the per-thread sums simply keep accumulating; the warp reduction and the bin update happen once per channel
+      // change instead of once per vector.
+      int cur_c = -1;
+      float2 A0 = make_float2(0.f, 0.f), A1 = make_float2(0.f, 0.f);
+      auto flush = [&]() {
+        if (cur_c >= 0) {
+          float v0 = A0.x + A0.y, v1 = A1.x + A1.y;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+            v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+          }
+          if (lane == 0) {
+            const float ga = sgb[cur_c];
+            wbins[cur_c] += v0;
+            wbins[cpg + cur_c] += v1;
+            tot[0] = fmaf(v0, ga, tot[0]);
+            tot[1] = fmaf(v1, ga, tot[1]);
+          }
+          __syncwarp();
+        }
+        A0 = make_float2(0.f, 0.f);
+        A1 = make_float2(0.f, 0.f);
+      };
+      const float2 one2 = make_float2(1.f, 1.f), mone2 = make_float2(-1.f, -1.f), half2 = make_float2(0.5f, 0.5f);
+      const float2 rstd2 = make_float2(rstd, rstd), nmr2 = make_float2(nmr, nmr);
+#pragma unroll 1
+      for (int s = 0; s < GB_NSUB; ++s) {
+        const int off = s * sub, l = min(sub, len - off);
+        if (l <= 0) break;
+        mbar_wait(&bars[s], 0, 0x6e02);
+        for (int i0 = off + (tid - lane) * VEC; i0 < off + l; i0 += GB_THREADS * VEC, ch.next()) {
+          const int i = i0 + lane * VEC;
+          const bool ok = i < off + l;
+          const int cc = ok ? ch.cc : -1;
+          const int c0 = __shfl_sync(0xffffffffu, cc, 0);
+          const bool uniform = __all_sync(0xffffffffu, cc == c0 || !ok);
+          if (uniform && c0 != cur_c) {
+            flush();
+            cur_c = c0;
+          }
+          float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
+          if (ok) {
+            const float ga = sgb[cc];
+            // silu'(z) = s (1 + z (1 - s)) with s = (1 + t) / 2, t = tanh(h), h = z / 2:  = (1/2 + t/2) (1 + h (1 - t))
+            const float ha = 0.5f * rstd * ga, hb = fmaf(mean, -ha, 0.5f * sgb[cpg + cc]);
+            const float2 ha2 = make_float2(ha, ha), hb2 = make_float2(hb, hb);
+            const uint4 ux = *reinterpret_cast<const uint4*>(bx + i);
+            uint4 ug = *reinterpret_cast<const uint4*>(bg + i);
+            const __nv_bfloat162* hx = reinterpret_cast<const __nv_bfloat162*>(&ux);
+            __nv_bfloat162* hg = reinterpret_cast<__nv_bfloat162*>(&ug);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 x2 = __bfloat1622float2(hx[k]);
+              const float2 g2 = __bfloat1622float2(hg[k]);
+              const float2 h = __ffma2_rn(x2, ha2, hb2);
+              const float2 t = make_float2(tanh_approx(h.x), tanh_approx(h.y));
+              const float2 u = __ffma2_rn(h, __ffma2_rn(t, mone2, one2), one2);   // 1 + h (1 - t)
+              const float2 sg = __ffma2_rn(t, half2, half2);                       // sigmoid(z)
+              const float2 gz = __fmul2_rn(g2, __fmul2_rn(sg, u));
+              const float2 xh = __ffma2_rn(x2, rstd2, nmr2);
+              a0 = __fadd2_rn(a0, gz);
+              a1 = __ffma2_rn(gz, xh, a1);
+              hg[k] = __floats2bfloat162_rn(gz.x, gz.y);
+            }
+            *reinterpret_cast<uint4*>(bg + i) = ug;  // the second pass reads gz = dy * silu'(z) instead of recomputing it
+          }
+          if (uniform) {
+            A0 = __fadd2_rn(A0, a0);
+            A1 = __fadd2_rn(A1, a1);
+          } else {
+            // a channel boundary runs through this warp's 256 elements: settle what is pending, then one reduction round
+            // per distinct channel
+            flush();
+            cur_c = -1;
+            float s0 = a0.x + a0.y, s1 = a1.x + a1.y;
+            if (ok) {
+              const float ga = sgb[cc];
+              tot[0] = fmaf(s0, ga, tot[0]);
+              tot[1] = fmaf(s1, ga, tot[1]);
+            }
+            unsigned remaining = __ballot_sync(0xffffffffu, ok);
+            while (remaining != 0) {
+              const int leader = __ffs(remaining) - 1;
+              const int c = __shfl_sync(0xffffffffu, cc, leader);
+              const bool mine = ok && cc == c;
+              float v0 = mine ? s0 : 0.f, v1 = mine ? s1 : 0.f;
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+                v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+              }
+              if (lane == leader) {
+                wbins[c] += v0;
+                wbins[cpg + c] += v1;
+              }
+              __syncwarp();
+              remaining &= ~__ballot_sync(0xffffffffu, mine);
+            }
+          }
+        }
+      }
+      flush();
+    }
+  }
+  if (!(sizeof(T) == 2 && apply_silu)) {
 #pragma unroll 1
   for (int s = 0; s < GB_NSUB; ++s) {
     const int off = s * sub, l = min(sub, len - off);
@@ -645,6 +757,7 @@ groupnorm_bwd_bulk_kernel(const T* __restrict__ dy, const T* __restrict__ x, con
       __syncwarp();
     }
   }
+  }
   cta_sum<2, GB_THREADS>(tot, red);  // (its barriers also order the bin updates before the flush below)
   for (int i = tid; i < 2 * cpg; i += GB_THREADS) {
     float v = 0.f;
@@ -662,12 +775,28 @@ groupnorm_bwd_bulk_kernel(const T* __restrict__ dy, const T* __restrict__ x, con
   const float c2 = -rm2 * rstd, c0 = -fmaf(rm2, nmr, rm1);  // dx = gz * (rstd gamma) + x * c2 + c0
   for (int i = tid * VEC; i < len; i += GB_THREADS * VEC, ch2.next()) {
     const float rg = rstd * sgb[ch2.cc];
-    float fx[VEC], fg[VEC];
-    Io<T>::load(bx + i, fx);
-    Io<T>::load(bg + i, fg);  // gz (pass 1 rewrote it; cta_sum's barriers order those writes)
+    if constexpr (sizeof(T) == 2) {  // packed f32x2: two elements per instruction
+      const uint4 ux = *reinterpret_cast<const uint4*>(bx + i);
+      const uint4 ug = *reinterpret_cast<const uint4*>(bg + i);  // gz (pass 1 rewrote it; cta_sum's barriers order those writes)
+      const __nv_bfloat162* hx = reinterpret_cast<const __nv_bfloat162*>(&ux);
+      const __nv_bfloat162* hg = reinterpret_cast<const __nv_bfloat162*>(&ug);
+      const float2 rg2 = make_float2(rg, rg), c22 = make_float2(c2, c2), c02 = make_float2(c0, c0);
+      uint4 uo;
+      __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&uo);
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) fx[k] = fmaf(fg[k], rg, fmaf(fx[k], c2, c0));
-    Io<T>::store(os + i, fx);
+      for (int k = 0; k < 4; ++k) {
+        const float2 r = __ffma2_rn(__bfloat1622float2(hg[k]), rg2, __ffma2_rn(__bfloat1622float2(hx[k]), c22, c02));
+        ho[k] = __floats2bfloat162_rn(r.x, r.y);
+      }
+      *reinterpret_cast<uint4*>(os + i) = uo;
+    } else {
+      float fx[VEC], fg[VEC];
+      Io<T>::load(bx + i, fx);
+      Io<T>::load(bg + i, fg);  // gz (pass 1 rewrote it; cta_sum's barriers order those writes)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) fx[k] = fmaf(fg[k], rg, fmaf(fx[k], c2, c0));
+      Io<T>::store(os + i, fx);
+    }
   }
   if (CL > 1) cg::this_cluster().sync();
 }

@@ -303,12 +303,14 @@ def ln_modulate_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Op
     B, L, Cc = x.shape
     dx = torch.empty_like(x)
     dev = x.device
-    empty = x.new_empty((0,), dtype=torch.float32)
-    dgamma = torch.zeros((Cc,), dtype=torch.float32, device=dev) if need_affine else empty
+    def empty():  # a fresh tensor each time: outputs of a registered op may not alias one another
+        return x.new_empty((0,), dtype=torch.float32)
+
+    dgamma = torch.zeros((Cc,), dtype=torch.float32, device=dev) if need_affine else empty()
     dbeta = torch.zeros_like(dgamma)
-    dscale = torch.zeros((B, Cc), dtype=torch.float32, device=dev) if need_mod else empty
+    dscale = torch.zeros((B, Cc), dtype=torch.float32, device=dev) if need_mod else empty()
     dshift = torch.zeros_like(dscale)
-    dscale2 = torch.zeros_like(dscale) if split > 0 else empty
+    dscale2 = torch.zeros_like(dscale) if split > 0 else empty()
     dshift2 = torch.zeros_like(dscale2)
     g, b, sc = _f32(gamma), _f32(beta), _f32(scale)
     with torch.cuda.device(dev):
@@ -332,13 +334,13 @@ def ln_modulate_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Op
 @ln_modulate_bwd.register_fake
 def _(dy, x, mean, rstd, gamma, beta, scale, need_affine, need_mod, scale2=None, split=0):
     B, L, Cc = x.shape
-    e = x.new_empty((0,), dtype=torch.float32)
-    mod = x.new_empty((B, Cc), dtype=torch.float32) if need_mod else e
-    mod2 = x.new_empty((B, Cc), dtype=torch.float32) if (need_mod and split > 0) else e
-    return (torch.empty_like(x, memory_format=torch.contiguous_format),
-            x.new_empty((Cc,), dtype=torch.float32) if need_affine else e,
-            x.new_empty((Cc,), dtype=torch.float32) if need_affine else e,
-            mod, torch.empty_like(mod), mod2, torch.empty_like(mod2))
+
+    def f32(*shape):
+        return x.new_empty(shape, dtype=torch.float32)
+
+    aff, mod, mod2 = ((Cc,) if need_affine else (0,)), ((B, Cc) if need_mod else (0,)), ((B, Cc) if split > 0 else (0,))
+    return (torch.empty_like(x, memory_format=torch.contiguous_format), f32(*aff), f32(*aff), f32(*mod), f32(*mod),
+            f32(*mod2), f32(*mod2))
 
 
 def _lnm_setup(ctx, inputs, output):
@@ -416,9 +418,9 @@ def gate_residual_bwd(dy: Tensor, branch: Tensor, gate: Optional[Tensor], need_d
     xd = _xdtype("dy", dy)
     B, L, Cc = dy.shape
     dbranch = torch.empty((B, L, Cc), dtype=torch.bfloat16, device=dy.device)
-    empty = dy.new_empty((0,), dtype=torch.float32)
-    dgate = torch.zeros((B, Cc), dtype=torch.float32, device=dy.device) if need_dgate else empty
-    dgate2 = torch.zeros_like(dgate) if split > 0 else empty
+    dgate = (torch.zeros((B, Cc), dtype=torch.float32, device=dy.device) if need_dgate
+             else dy.new_empty((0,), dtype=torch.float32))
+    dgate2 = torch.zeros_like(dgate) if split > 0 else dy.new_empty((0,), dtype=torch.float32)
     g = _f32(gate)
     with torch.cuda.device(dy.device):
         if split <= 0:

@@ -132,6 +132,7 @@ def patch_blocks(lvdm: bool = True, hunyuan: bool = True, wan: bool = True) -> D
         net = _try_import("videotuna.models.lvdm.modules.networks.openaimodel3d")
         if net is not None:
             done["lvdm"] += _patch_method(net, "ResBlock", "_forward", Bk.lvdm_resblock_forward)
+            done["lvdm"] += _patch_method(net, "TemporalConvBlock", "forward", Bk.lvdm_temporal_conv_block_forward)
     if hunyuan:
         # The drop-ins take the i2v twins' full signature (condition_type, token_replace_vec, frist_frame_token_num:
         # hyvideo_i2v/modules/models.py:136-149, 371-384) — HunyuanVideoFlow drives T2V and I2V through the i2v DiT, which

@@ -367,8 +367,9 @@ def library_baselines(torch, dev):
 
 
 def denoiser_it_s(world: int):
-    """Forward + backward of DiT block stacks (tools/bench_denoiser.py code path, `ours` arm: the reference blocks'
-    constructors with the b200vt drop-in forwards, per-block activation checkpointing, >= 3 warm-ups)."""
+    """Finetuning iterations (forward + backward + AdamW step) of DiT block stacks (tools/bench_denoiser.py code path,
+    `ours` arm: the reference blocks' constructors with the b200vt drop-in forwards, per-block activation checkpointing,
+    3 warm-ups, 2 timed iterations)."""
     import types
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import bench_denoiser as BD
@@ -382,7 +383,8 @@ def denoiser_it_s(world: int):
     for name, kw, scale, note in runs:
         if kw["model"] == "cogvideox" and world > 1:
             continue  # 30 heads: data parallel only
-        a = types.SimpleNamespace(arm="ours", steps=2, warmup=3, no_checkpoint=False, tokens_scale=1.0, check=False, **kw)
+        a = types.SimpleNamespace(arm="ours", steps=2, warmup=3, no_checkpoint=False, tokens_scale=1.0, check=False,
+                                  optimizer="adamw", **kw)
         import gc
 
         import torch
@@ -402,6 +404,7 @@ def denoiser_it_s(world: int):
                      "it_per_s_full_stack": round(1.0 / (line["s_per_it"] * scale), 5),
                      "full_stack_scaling": f"x{scale:g} (identical blocks; embeddings / final layer < 0.1 % of the FLOPs are not in the stack)",
                      "steps": line["steps"], "warmup": line["warmup"], "parallelism": line["config"]["parallelism"],
+                     "iteration": "forward + backward + fused AdamW step on the trainable parameters, per-block activation checkpointing",
                      "attention_share_of_step": line.get("attention_share_of_step"),
                      "attention_tflops_in_step": line.get("attention_tflops_in_step"), "peak_mem_GB": line["peak_mem_GB"]}
     return out

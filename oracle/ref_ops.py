@@ -446,10 +446,10 @@ def diffusers_hunyuan_attention(hidden: Tensor, encoder_hidden: Tensor, p: dict,
 
 
 def max_rel_err(y: Tensor, ref: Tensor) -> float:
-    y, ref = y.double().cpu(), ref.double().cpu()
+    y, ref = y.detach().double().cpu(), ref.detach().double().cpu()
     return float((y - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
 
 
 def cosine(a: Tensor, b: Tensor) -> float:
-    a, b = a.double().cpu().flatten(), b.double().cpu().flatten()
+    a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
     return float(torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-30))

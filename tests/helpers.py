@@ -30,13 +30,30 @@ class CrossAttentionShell(nn.Module):
             if img_cross_attention_scale_learnable:
                 self.register_parameter("alpha", nn.Parameter(torch.tensor(0.0)))
         self.relative_position = relative_position
+        if relative_position:
+            self.relative_position_k = RelativePositionShell(dim_head, temporal_length)
+            self.relative_position_v = RelativePositionShell(dim_head, temporal_length)
 
     @classmethod
     def from_fixture(cls, case, device, dtype=torch.bfloat16):
         m = cls(**case["kw"])
-        sd = {k: v for k, v in case["sd"].items() if not k.startswith("relative_position")}
-        m.load_state_dict({k: v.float() for k, v in sd.items()}, strict=True)
+        m.load_state_dict({k: v.float() for k, v in case["sd"].items()}, strict=True)
         return m.to(device=device, dtype=dtype)
+
+
+class RelativePositionShell(nn.Module):
+    """lvdm RelativePosition (attention.py:19-42): a (2 * max + 1, D) table gathered at clamp(k - q, -max, max) + max."""
+
+    def __init__(self, num_units, max_relative_position):
+        super().__init__()
+        self.num_units, self.max_relative_position = num_units, max_relative_position
+        self.embeddings_table = nn.Parameter(torch.zeros(max_relative_position * 2 + 1, num_units))
+
+    def forward(self, length_q, length_k):
+        dev = self.embeddings_table.device
+        dist = torch.arange(length_k, device=dev)[None, :] - torch.arange(length_q, device=dev)[:, None]
+        idx = dist.clamp(-self.max_relative_position, self.max_relative_position) + self.max_relative_position
+        return self.embeddings_table[idx.long()]
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -49,13 +49,30 @@ def test_temporal_causal_backward_matches_reference_fixture():
     assert R.cosine(m.to_v.weight.grad.float().cpu(), case["dw_v"].float()) > 0.999
 
 
-def test_relative_position_stays_on_reference_path():
+@pytest.mark.parametrize("name", ["temporal_relpos", "temporal_relpos_causal"])
+def test_relative_position_attention_forward_matches_reference_fixture(name):
+    """VideoCrafter1's relative-position temporal attention (attention.py:19-42, 129-133, 145-148) on the CUDA path."""
+    case = load_golden("lvdm_cross_attention")[name]
+    _, _, out = _run_case(case)
+    assert R.max_rel_err(out.float().cpu(), case["out"].float()) < TOL
+
+
+@pytest.mark.parametrize("tag", ["plain", "causal"])
+def test_relative_position_attention_backward_matches_reference_fixture(tag):
     import b200vt.functional as Fn
-    case = load_golden("lvdm_cross_attention")["temporal_relpos"]
+    g = load_golden("lvdm_extra")["relpos"]
     dev = torch.device("cuda")
-    m = CrossAttentionShell.from_fixture(case, dev)
-    with pytest.raises(Fn.Unsupported):
-        Fn.lvdm_cross_attention_forward(m, case["x"].to(dev, torch.bfloat16))
+    m = CrossAttentionShell.from_fixture(g, dev)
+    x = g["x"].to(dev, torch.bfloat16).requires_grad_(True)
+    mask = g["mask"].to(dev).expand(x.shape[0], -1, -1) if tag == "causal" else None
+    out = Fn.lvdm_cross_attention_forward(m, x, mask=mask)
+    r = g[tag]
+    assert R.max_rel_err(out.float().cpu(), r["out"].float()) < TOL
+    out.backward(g["d_out"].to(dev, torch.bfloat16))
+    assert R.cosine(x.grad.float().cpu(), r["d_x"].float()) > 0.999
+    assert R.cosine(m.to_q.weight.grad.float().cpu(), r["d_to_q"].float()) > 0.999
+    assert R.cosine(m.relative_position_k.embeddings_table.grad.float().cpu(), r["d_rel_k"].float()) > 0.995
+    assert R.cosine(m.relative_position_v.embeddings_table.grad.float().cpu(), r["d_rel_v"].float()) > 0.995
 
 
 def test_fp32_activations_stay_on_reference_path():

@@ -308,6 +308,9 @@ def parse(argv=None):
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--no-checkpoint", action="store_true")
+    ap.add_argument("--optimizer", choices=("none", "adamw"), default="none",
+                    help="adamw: one fused AdamW step on the trainable parameters (LoRA adapters for hunyuan, every block "
+                    "weight for wan / cogvideox) inside the timed iteration, lr 1e-5 as the reference configs")
     ap.add_argument("--tokens-scale", type=float, default=1.0, help="debug: shrink the latent frame count")
     ap.add_argument("--check", action="store_true", help="run one forward+backward of BOTH arms on the same weights and "
                     "print the relative difference of the outputs and input gradients, then exit")
@@ -338,6 +341,17 @@ def run(args, manage_dist: bool = True, emit: bool = True):
 
     def run_block(fn, *a):
         return checkpoint(fn, *a, use_reentrant=False) if ckpt else fn(*a)
+
+    opt_state = {}
+
+    def finish_step(params):
+        """End of an iteration: the optimizer step of a finetuning iteration (--optimizer adamw), then drop the gradients."""
+        if getattr(args, "optimizer", "none") == "adamw":
+            if "opt" not in opt_state:
+                opt_state["opt"] = torch.optim.AdamW([p for p in params if p.requires_grad], lr=1e-5, fused=True)
+            opt_state["opt"].step()
+        for p in params:
+            p.grad = None
 
     if args.model == "hunyuan":
         nd = cfg["double"] if args.double is None else args.double
@@ -379,8 +393,7 @@ def run(args, manage_dist: bool = True, emit: bool = True):
                 fn = b if ours else (lambda *a, _b=b: hy_single_torch(_b, *a))
                 x = run_block(fn, x, vec, n_txt, cu, cu, S, S, (cos, sin))
             x.backward(d_out)
-            for p in params:
-                p.grad = None
+            finish_step(params)
             return x.detach(), leaf.grad
     elif args.model == "cogvideox":
         assert world == 1, "CogVideoX-2B has 30 heads: data parallel only (SURVEY 8e); bench it at 1 GPU"
@@ -405,8 +418,7 @@ def run(args, manage_dist: bool = True, emit: bool = True):
                 fn = b if ours else (lambda *a, _b=b: cog_block_torch(_b, *a))
                 h, e = run_block(fn, h, e, temb)
             torch.autograd.backward([h, e], [d_out, torch.zeros_like(e)])
-            for p in params:
-                p.grad = None
+            finish_step(params)
             return h.detach(), leaf.grad
     else:
         nl = cfg["layers"] if args.layers is None else args.layers
@@ -445,8 +457,7 @@ def run(args, manage_dist: bool = True, emit: bool = True):
             for hnd in pending:
                 hnd.wait()
             pending.clear()
-            for p in params:
-                p.grad = None
+            finish_step(params)
             return x.detach(), leaf.grad
 
         pending = []
@@ -506,7 +517,7 @@ def run(args, manage_dist: bool = True, emit: bool = True):
             "it_per_s": round(1.0 / s_per_it, 5), "s_per_it": round(s_per_it, 4), "steps": args.steps, "warmup": args.warmup,
             "config": {**layers_desc, "img_tokens": n_img, "txt_tokens": n_txt, "hidden": C, "heads": heads,
                        "block_params": n_params, "trainable_params": sum(p.numel() for p in params),
-                       "activation_checkpointing": ckpt, "dtype": "bf16",
+                       "activation_checkpointing": ckpt, "dtype": "bf16", "optimizer": getattr(args, "optimizer", "none"),
                        "parallelism": "single" if world == 1 else f"ulysses_sp{world}",
                        "attention": ("b200vt tcgen05 kernels" if ours else (
                            "F.scaled_dot_product_attention (diffusers CogVideoXAttnProcessor2_0)" if args.model == "cogvideox"

@@ -241,8 +241,17 @@ def lvdm_cross_attention_forward(self, x, context=None, mask=None):
     b, n, _ = q.shape
     d = self.dim_head
     q4, k4, v4 = q.view(b, n, h, d), k.view(b, k.shape[1], h, d), v.view(b, v.shape[1], h, d)
-    _require(not self.relative_position, "relative-position attention (VideoCrafter1 configs) stays on the reference path")
     small = n <= 32 and k4.shape[1] == n  # the one-warp kernel takes a single N for q, k and v
+    if self.relative_position:
+        _require(small and d + n <= 128 and k_ip is None,
+                 "relative-position attention is on the CUDA path for temporal self-attention with dim_head + frames <= 128")
+        m2 = None
+        if mask is not None:
+            m2 = mask if mask.dim() == 2 else mask[0]
+            if mask.dim() == 3 and mask.shape[0] > 1:
+                _require(bool((mask == mask[:1]).all()), "per-sample masks stay on the reference path")
+        out = _relative_position_attention(self, q4, k4, v4, m2).reshape(b, n, h * d)
+        return self.to_out(out)
     if mask is not None:
         # TemporalTransformer's causal mask: one (t, t) pattern repeated over the batch (attention.py:487-489)
         _require(small, "masked attention is only on the CUDA path for the temporal (N <= 32) kernel")
@@ -263,6 +272,28 @@ def lvdm_cross_attention_forward(self, x, context=None, mask=None):
         else:
             out = out + self.img_cross_attention_scale * out_ip
     return self.to_out(out)
+
+
+def _relative_position_attention(self, q4: Tensor, k4: Tensor, v4: Tensor, mask: Optional[Tensor]) -> Tensor:
+    """lvdm CrossAttention with relative_position=True (VideoCrafter1, attention.py:19-42, 129-133, 145-148):
+        S_ij = scale * (q_i . k_j + q_i . k2_ij),   O_i = sum_j P_ij (v_j + v2_ij),   k2_ij = table_k[j - i + max], v2 likewise.
+    Both extra terms ride on the one-warp temporal kernel at head dim 128 through an AUGMENTED head: with e_j the one-hot
+    of key position j,
+        q'_i = [q_i ; m_i ; 0],  m_i[j] = q_i . k2_ij        k'_j = [k_j ; e_j ; 0]   =>  q'_i . k'_j = q_i . k_j + q_i . k2_ij
+        v'_j = [v_j ; e_j ; 0]                               =>  O'_i = [ sum_j P_ij v_j ; P_i. ; 0 ]
+    so the kernel's extra output columns ARE the attention probabilities, from which sum_j P_ij v2_ij is a small einsum.
+    Autograd flows through the same kernel backward (the e_j columns are constants). q4, k4, v4: (B, N, H, D), D + N <= 128."""
+    b, n, h, d = q4.shape
+    k2 = self.relative_position_k(n, n).to(q4.dtype)   # (N, N, D); the module call keeps the table's gradient
+    v2 = self.relative_position_v(n, n).to(q4.dtype)
+    m = torch.einsum("bthd,tsd->bths", q4, k2)         # (B, N, H, N)
+    eye = torch.eye(n, device=q4.device, dtype=q4.dtype).view(1, n, 1, n).expand(b, n, h, n)
+    pad = q4.new_zeros((b, n, h, 128 - d - n))
+    q_aug = torch.cat([q4, m, pad], dim=-1)
+    k_aug = torch.cat([k4, eye, pad], dim=-1)
+    v_aug = torch.cat([v4, eye, pad], dim=-1)
+    o_aug = ops.temporal_attn_fwd(q_aug, k_aug, v_aug, mask, float(self.scale))
+    return o_aug[..., :d] + torch.einsum("bths,tsd->bthd", o_aug[..., d:d + n], v2)
 
 
 def temporal_attention(q: Tensor, k: Tensor, v: Tensor, softmax_scale: Optional[float] = None,

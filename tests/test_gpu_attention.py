@@ -208,9 +208,10 @@ def test_host_buffer_entry_point_matches_device_path():
     q, k, v, do = (_rand((B, L, H, D), s).pin_memory() for s in (21, 22, 23, 24))
     outs = [torch.empty((B, L, H, D), dtype=torch.bfloat16).pin_memory() for _ in range(4)]
     ha = Fn.HostAttention(B, L, H, D, head_groups=2)
-    for _ in range(2):  # second call reuses the device buffers
+    for _ in range(3):  # consecutive calls reuse the device buffers and pipeline into one another
         ha(q, k, v, do, *outs)
-        torch.cuda.synchronize()
+    ha.synchronize()
+    torch.cuda.synchronize()
     qd, kd, vd = (t.cuda().requires_grad_(True) for t in (q, k, v))
     ref = Fn.attention_blhd(qd, kd, vd)
     gq, gk, gv = torch.autograd.grad(ref, (qd, kd, vd), do.cuda())
@@ -218,3 +219,30 @@ def test_host_buffer_entry_point_matches_device_path():
         # same kernels on the same values; dq is accumulated with fp32 atomics whose order is not fixed
         err = R.max_rel_err(got.float(), want.detach().float().cpu())
         assert err < (1e-2 if name == "dq" else 1e-6), (name, err)
+
+
+def test_host_ulysses_entry_point_single_rank_pipelines_across_calls():
+    """sp.HostUlyssesAttention at SP world size 1 (no process group): pinned host shards in, pinned results out, head groups
+    and CONSECUTIVE CALLS pipelined; equals joint attention of [img; txt] + autograd on device tensors."""
+    import b200vt.functional as Fn
+    import b200vt.sp as sp
+    S, T, H, D = 300, 20, 4, 128
+    q, k, v = (_rand((1, S, H, D), s).pin_memory() for s in (41, 42, 43))
+    tq, tk, tv = (_rand((1, T, H, D), s).pin_memory() for s in (44, 45, 46))
+    do = _rand((1, S + T, H, D), 47).pin_memory()
+    outs = [[torch.empty(shape, dtype=torch.bfloat16).pin_memory() for shape in
+             ((1, S + T, H, D), (1, S, H, D), (1, S, H, D), (1, S, H, D), (1, T, H, D), (1, T, H, D), (1, T, H, D))]
+            for _ in range(3)]
+    ha = sp.HostUlyssesAttention(S, T, H, D, head_groups=2)
+    for o in outs:  # three calls back to back, no synchronisation in between
+        ha(q, k, v, do, o[0], o[1], o[2], o[3], tq, tk, tv, o[4], o[5], o[6])
+    ha.synchronize()
+    torch.cuda.synchronize()
+    leaves = [t.cuda().requires_grad_(True) for t in (q, k, v, tq, tk, tv)]
+    ref = Fn.attention_blhd(*(torch.cat([leaves[i], leaves[i + 3]], 1) for i in range(3)))
+    grads = torch.autograd.grad(ref, leaves, do.cuda())
+    want = (ref, *grads)
+    for o in outs:
+        for name, got, w in zip(("out", "dq", "dk", "dv", "dtq", "dtk", "dtv"), o, want):
+            err = R.max_rel_err(got.float(), w.detach().float().cpu())
+            assert err < (1e-2 if name in ("dq", "dtq") else 1e-6), (name, err)

@@ -85,8 +85,9 @@ class HostAttention:
     tokens is 2.2 GB). Heads are independent, so the work is cut into head groups and pipelined on three streams:
     group g+1 is copied in (strided cudaMemcpy2DAsync straight out of the (B, L, H, D) layout) while group g runs the
     forward and backward kernels and group g-1's o, dq, dk, dv are copied out; PCIe is full duplex, so apart from the
-    first copy-in and the last copy-out the transfers hide behind the kernels. Device buffers are allocated once and
-    reused across calls. Same arithmetic as attention_blhd + autograd (tests/test_gpu_attention.py)."""
+    first copy-in of the first call and the last copy-out of the last the transfers hide behind the kernels (consecutive
+    calls pipeline into one another). Input device buffers are allocated once and reused across calls. Same arithmetic as
+    attention_blhd + autograd (tests/test_gpu_attention.py)."""
 
     def __init__(self, B: int, L: int, H: int, D: int, head_groups: int = 4, device=None):
         _require(H % head_groups == 0, f"head_groups={head_groups} must divide H={H}")
@@ -99,65 +100,55 @@ class HostAttention:
         def buf():
             return torch.empty(shape, dtype=torch.bfloat16, device=self.dev)
 
-        # two sets of inputs (q, k, v, dO) and outputs (o, dq, dk, dv): copy of the next / previous group overlaps
+        # two sets of inputs (q, k, v, dO): the copy-in of the next group overlaps the kernels of the current one; outputs
+        # are fresh allocations kept alive for the copy-out stream (record_stream)
         self.inp = [[buf() for _ in range(4)] for _ in range(2)]
         self.s_in, self.s_out = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
         self.ev_in = [torch.cuda.Event() for _ in range(2)]      # inputs of slot landed
         self.ev_free = [torch.cuda.Event() for _ in range(2)]    # compute finished reading slot's inputs
         self.ev_done = [torch.cuda.Event() for _ in range(2)]    # outputs of slot computed
-        self.ev_out = [torch.cuda.Event() for _ in range(2)]     # outputs of slot copied out
-        self.outp = [None, None]
+        self.n_groups_done = 0   # running counter: slots alternate ACROSS calls (see __call__)
 
-    def _copy(self, dev_t: Tensor, host_t: Tensor, g: int, to_device: bool, stream):
-        from . import _lib
-        B, L, H, D, hg = self.B, self.L, self.H, self.D, self.hg
-        for b in range(B):
-            hptr = host_t.data_ptr() + (b * host_t.stride(0) + g * hg * host_t.stride(2)) * 2
-            dptr = dev_t.data_ptr() + b * dev_t.stride(0) * 2
-            hpitch, dpitch, width = host_t.stride(1) * 2, hg * D * 2, hg * D * 2
-            if to_device:
-                _lib.call("vt_memcpy2d_async", _lib.vp(dptr), dpitch, _lib.vp(hptr), hpitch, width, L, 1,
-                          _lib.vp(stream.cuda_stream))
-            else:
-                _lib.call("vt_memcpy2d_async", _lib.vp(hptr), hpitch, _lib.vp(dptr), dpitch, width, L, 0,
-                          _lib.vp(stream.cuda_stream))
+    def synchronize(self) -> None:
+        """Wait until every copy-out enqueued so far has landed in the host buffers."""
+        self.s_out.synchronize()
 
     def __call__(self, q: Tensor, k: Tensor, v: Tensor, dout: Tensor, out: Tensor, dq: Tensor, dk: Tensor, dv: Tensor,
                  softmax_scale: Optional[float] = None):
         """All eight tensors: pinned host (B, L, H, D) bf16 with unit D stride and H stride D. Returns when everything
-        has been ENQUEUED; synchronise the current stream (the last copy-out is joined into it) before reading."""
+        has been ENQUEUED. Consecutive calls pipeline into one another — the next call's first copy-in runs under this
+        call's last kernels, this call's last copy-out under the next call's first — so inputs must stay untouched, and
+        outputs are valid, only after synchronize() (or a device synchronize)."""
         for t in (q, k, v, dout, out, dq, dk, dv):
             _require(not t.is_cuda and t.is_pinned() and t.dtype == torch.bfloat16 and tuple(t.shape) ==
                      (self.B, self.L, self.H, self.D) and t.stride(3) == 1 and t.stride(2) == self.D,
                      "HostAttention needs pinned host (B, L, H, D) bf16 tensors with contiguous heads")
         scale = 1.0 / math.sqrt(self.D) if softmax_scale is None else float(softmax_scale)
         cur = torch.cuda.current_stream(self.dev)
-        self.s_in.wait_stream(cur)
-        self.s_out.wait_stream(cur)
+        if self.n_groups_done == 0:
+            self.s_in.wait_stream(cur)
+            self.s_out.wait_stream(cur)
         for g in range(self.G):
-            slot = g & 1
+            n = self.n_groups_done
+            slot, h0 = n & 1, g * self.hg
             with torch.cuda.stream(self.s_in):
-                if g >= 2:
-                    self.s_in.wait_event(self.ev_free[slot])  # compute of group g-2 is done with these buffers
+                if n >= 2:
+                    self.s_in.wait_event(self.ev_free[slot])  # the compute that last used these buffers is done
                 for dev_t, host_t in zip(self.inp[slot], (q, k, v, dout)):
-                    self._copy(dev_t, host_t, g, True, self.s_in)
+                    copy_head_group(dev_t, host_t, h0, True, self.s_in)
                 self.ev_in[slot].record(self.s_in)
             cur.wait_event(self.ev_in[slot])
-            if g >= 2:
-                cur.wait_event(self.ev_out[slot])  # previous outputs of this slot have left the device
             qd, kd, vd, dod = self.inp[slot]
             o, lse = ops.attn_fwd(qd, kd, vd, None, None, None, self.L, self.L, scale)
             gq, gk, gv = ops.attn_bwd(dod, qd, kd, vd, o, lse, None, None, None, self.L, self.L, scale)
-            self.outp[slot] = (o, gq, gk, gv)
             self.ev_free[slot].record(cur)
             self.ev_done[slot].record(cur)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_done[slot])
-                for dev_t, host_t in zip(self.outp[slot], (out, dq, dk, dv)):
-                    dev_t.record_stream(self.s_out)
-                    self._copy(dev_t, host_t, g, False, self.s_out)
-                self.ev_out[slot].record(self.s_out)
-        cur.wait_stream(self.s_out)
+                for dev_t, host_t in zip((o, gq, gk, gv), (out, dq, dk, dv)):
+                    dev_t.record_stream(self.s_out)  # returned to the allocator only after the copy-out has run
+                    copy_head_group(dev_t, host_t, h0, False, self.s_out)
+            self.n_groups_done += 1
         return out, dq, dk, dv
 
 

@@ -328,46 +328,63 @@ class HostUlyssesAttention:
             return torch.empty((1, rows, self.hg, D), dtype=torch.bfloat16, device=self.dev)
 
         self.inp = [[buf(s_loc), buf(s_loc), buf(s_loc), buf(s_loc + T)] for _ in range(2)]
-        self.txt = [torch.empty((1, T, H, D), dtype=torch.bfloat16, device=self.dev) for _ in range(3)] if T else None
+        self.txt = [[torch.empty((1, T, H, D), dtype=torch.bfloat16, device=self.dev) for _ in range(3)] for _ in range(2)] if T else None
         self.s_in, self.s_out = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
-        self.ev_in = [torch.cuda.Event() for _ in range(2)]
-        self.ev_free = [torch.cuda.Event() for _ in range(2)]
-        self.ev_done = [torch.cuda.Event() for _ in range(2)]
-        self.ev_out = [torch.cuda.Event() for _ in range(2)]
+        self.ev_in = [torch.cuda.Event() for _ in range(2)]      # inputs of slot landed
+        self.ev_free = [torch.cuda.Event() for _ in range(2)]    # compute finished reading the slot's inputs
+        self.ev_done = [torch.cuda.Event() for _ in range(2)]    # outputs of slot computed
+        self.ev_out = [torch.cuda.Event() for _ in range(2)]     # outputs of slot copied out
+        self.ev_txt_in = [torch.cuda.Event() for _ in range(2)]
+        self.ev_txt_free = [torch.cuda.Event() for _ in range(2)]
         self.outp = [None, None]
+        self.n_groups_done = 0   # running counters: slots alternate ACROSS calls, so that the copy-in of the next call's
+        self.n_calls = 0         # first group overlaps the compute of this call's last group
+
+    def synchronize(self) -> None:
+        """Wait until every copy-out enqueued so far has landed in the host buffers."""
+        self.s_out.synchronize()
 
     def __call__(self, q: Tensor, k: Tensor, v: Tensor, dout: Tensor, out: Tensor, dq: Tensor, dk: Tensor, dv: Tensor,
                  tq: Optional[Tensor] = None, tk: Optional[Tensor] = None, tv: Optional[Tensor] = None,
                  dtq: Optional[Tensor] = None, dtk: Optional[Tensor] = None, dtv: Optional[Tensor] = None):
         """q, k, v, dq, dk, dv: pinned host (1, L/P, H, D); dout, out: (1, L/P + T, H, D); tq/tk/tv and their gradient
         buffers: (1, T, H, D) (replicated text, "rear"). A rank's text gradients cover its own head slices only (zeros
-        elsewhere), as with UlyssesAttention. Everything is ENQUEUED; synchronise the current stream before reading."""
+        elsewhere), as with UlyssesAttention. Everything is ENQUEUED and consecutive calls pipeline into one another (the
+        next call's copy-in runs under this call's kernels, this call's last copy-out under the next call's): the input
+        buffers must stay untouched, and the outputs are valid, only after synchronize() (or a device synchronize)."""
         from .functional import copy_head_group
         cur = torch.cuda.current_stream(self.dev)
-        self.s_in.wait_stream(cur)
-        self.s_out.wait_stream(cur)
         T = self.T
+        first = self.n_calls == 0
+        if first:  # nothing in flight yet: order the side streams behind whatever produced the host buffers' device peers
+            self.s_in.wait_stream(cur)
+            self.s_out.wait_stream(cur)
+        tslot = self.n_calls & 1
         if T:
             with torch.cuda.stream(self.s_in):
-                for d_t, h_t in zip(self.txt, (tq, tk, tv)):
+                if self.n_calls >= 2:
+                    self.s_in.wait_event(self.ev_txt_free[tslot])
+                for d_t, h_t in zip(self.txt[tslot], (tq, tk, tv)):
                     d_t.copy_(h_t, non_blocking=True)
-            t_grads = [torch.zeros_like(t) for t in self.txt]
+                self.ev_txt_in[tslot].record(self.s_in)
+            t_grads = [torch.zeros_like(t) for t in self.txt[tslot]]
         for g in range(self.G):
-            slot, h0 = g & 1, g * self.hg
+            n = self.n_groups_done
+            slot, h0 = n & 1, g * self.hg
             with torch.cuda.stream(self.s_in):
-                if g >= 2:
-                    self.s_in.wait_event(self.ev_free[slot])
+                if n >= 2:
+                    self.s_in.wait_event(self.ev_free[slot])  # the compute that last used this slot's inputs is done
                 for d_t, h_t in zip(self.inp[slot], (q, k, v, dout)):
                     copy_head_group(d_t, h_t, h0, True, self.s_in)
                 self.ev_in[slot].record(self.s_in)
             cur.wait_event(self.ev_in[slot])
-            if g >= 2:
-                cur.wait_event(self.ev_out[slot])
+            if g == 0 and T:
+                cur.wait_event(self.ev_txt_in[tslot])
             qd, kd, vd, dod = self.inp[slot]
             leaves = [t.detach().requires_grad_(True) for t in (qd, kd, vd)]
             kw = {}
             if T:
-                tl = [t[:, :, h0:h0 + self.hg].detach().requires_grad_(True) for t in self.txt]
+                tl = [t[:, :, h0:h0 + self.hg].detach().requires_grad_(True) for t in self.txt[tslot]]
                 kw = dict(joint_tensor_query=tl[0], joint_tensor_key=tl[1], joint_tensor_value=tl[2], joint_strategy="rear")
                 leaves += tl
             o = self.attn(None, *leaves[:3], **kw)
@@ -375,20 +392,26 @@ class HostUlyssesAttention:
             if T:
                 for acc, gr in zip(t_grads, grads[3:]):
                     acc[:, :, h0:h0 + self.hg].copy_(gr)
-            self.outp[slot] = (o.detach(), *grads[:3])
             self.ev_free[slot].record(cur)
             self.ev_done[slot].record(cur)
+            results = (o.detach(), *grads[:3])
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_done[slot])
-                for d_t, h_t in zip(self.outp[slot], (out, dq, dk, dv)):
-                    d_t.record_stream(self.s_out)
+                for d_t, h_t in zip(results, (out, dq, dk, dv)):
+                    d_t.record_stream(self.s_out)  # freed by the caching allocator only after the copy-out has run
                     copy_head_group(d_t, h_t, h0, False, self.s_out)
-                self.ev_out[slot].record(self.s_out)
+            self.n_groups_done += 1
         if T:
-            for acc, h_t in zip(t_grads, (dtq, dtk, dtv)):
-                if h_t is not None:
-                    h_t.copy_(acc, non_blocking=True)
-        cur.wait_stream(self.s_out)
+            self.ev_txt_free[tslot].record(cur)
+            done = torch.cuda.Event()
+            done.record(cur)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(done)
+                for acc, h_t in zip(t_grads, (dtq, dtk, dtv)):
+                    if h_t is not None:
+                        acc.record_stream(self.s_out)
+                        h_t.copy_(acc, non_blocking=True)
+        self.n_calls += 1
         return out, dq, dk, dv
 
 

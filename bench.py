@@ -407,6 +407,29 @@ def denoiser_it_s(world: int):
                      "iteration": "forward + backward + fused AdamW step on the trainable parameters, per-block activation checkpointing",
                      "attention_share_of_step": line.get("attention_share_of_step"),
                      "attention_tflops_in_step": line.get("attention_tflops_in_step"), "peak_mem_GB": line["peak_mem_GB"]}
+    if world == 1:
+        # BASELINE config 2: the whole VideoCrafter2 3D-UNet LoRA step (tools/bench_vc2_unet.py), ours and the reference's
+        # op sequence on the same weights (data parallel model: measured at 1 GPU)
+        import types as _t
+
+        import torch
+        import bench_vc2_unet as VU
+        rec = {}
+        for arm in ("ours", "torch"):
+            try:
+                r = VU.run(_t.SimpleNamespace(arm=arm, steps=5, warmup=3, no_checkpoint=False, check=False), emit=False)
+                rec[arm] = {"s_per_it": r["s_per_it"], "it_per_s": r["it_per_s"], "peak_mem_GB": r["peak_mem_GB"]}
+            except Exception as e:  # noqa: BLE001
+                rec[arm] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+        if "s_per_it" in rec.get("ours", {}) and "s_per_it" in rec.get("torch", {}):
+            rec["speedup_vs_reference_op_sequence"] = round(rec["torch"]["s_per_it"] / rec["ours"]["s_per_it"], 3)
+        rec["iteration"] = ("whole UNet (1.4 B parameters): forward on 2 x 4 x 16 x 40 x 64 latents + 77 x 1024 context, MSE loss, "
+                            "backward, fused AdamW on rank-4 LoRA adapters; bf16 autocast, per-block activation checkpointing "
+                            "(use_checkpoint: true); `torch` = the reference's op sequence on the same modules and weights")
+        out["videocrafter2_320x512x16f_lora_b2"] = rec
     return out
 
 

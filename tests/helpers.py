@@ -217,6 +217,13 @@ class BasicBlockShell(nn.Module):
         self._fwd = blocks.lvdm_basic_block_forward
 
     def forward(self, x, context=None, mask=None):
+        if self.checkpoint and torch.is_grad_enabled():  # the reference checkpoints here (attention.py:283-297, utils.py:112-125)
+            from torch.utils.checkpoint import checkpoint
+            if mask is not None:
+                return checkpoint(lambda t: self._fwd(self, t, mask=mask), x, use_reentrant=False)
+            if context is not None:
+                return checkpoint(lambda t, c: self._fwd(self, t, c), x, context, use_reentrant=False)
+            return checkpoint(lambda t: self._fwd(self, t), x, use_reentrant=False)
         if mask is not None:
             return self._fwd(self, x, mask=mask)
         return self._fwd(self, x, context) if context is not None else self._fwd(self, x)
@@ -242,7 +249,8 @@ class SpatialTransformerShell(nn.Module):
 
 
 class TemporalTransformerShell(nn.Module):
-    """lvdm TemporalTransformer.__init__ (attention.py:403-473), use_linear=True, only_self_att=True."""
+    """lvdm TemporalTransformer.__init__ (attention.py:403-473), only_self_att=True; use_linear=False gives the Conv1d
+    projections the UNet's init_attn is built with (openaimodel3d.py:418-432 passes no use_linear)."""
 
     def __init__(self, in_channels, n_heads, d_head, depth=1, use_linear=True, use_checkpoint=False, only_self_att=True,
                  temporal_length=None, causal_attention=False):
@@ -252,9 +260,9 @@ class TemporalTransformerShell(nn.Module):
         self.only_self_att, self.causal_attention, self.relative_position = only_self_att, causal_attention, False
         self.in_channels = in_channels
         self.norm = nn.GroupNorm(32, in_channels, eps=1e-6, affine=True)
-        self.proj_in = nn.Linear(in_channels, inner)
+        self.proj_in = nn.Linear(in_channels, inner) if use_linear else nn.Conv1d(in_channels, inner, 1)
         self.transformer_blocks = nn.ModuleList(BasicBlockShell(inner, n_heads, d_head, None) for _ in range(depth))
-        self.proj_out = nn.Linear(inner, in_channels)
+        self.proj_out = nn.Linear(inner, in_channels) if use_linear else nn.Conv1d(inner, in_channels, 1)
         self.use_linear = use_linear
         if causal_attention:
             self.mask = torch.tril(torch.ones([1, temporal_length, temporal_length]))
@@ -265,7 +273,8 @@ class TemporalTransformerShell(nn.Module):
 
 
 class ResBlockShell(nn.Module):
-    """lvdm ResBlock.__init__ (openaimodel3d.py:139-210), dims=2, no up/down-sampling, no temporal conv."""
+    """lvdm ResBlock.__init__ (openaimodel3d.py:139-210), dims=2, no up/down-sampling; use_temporal_conv adds the
+    TemporalConvBlock under the reference's attribute name (`temopral_conv`, :205-210, dropout 0.1)."""
 
     def __init__(self, channels, emb_channels, dropout, out_channels=None, dims=2, use_checkpoint=False,
                  use_temporal_conv=False):
@@ -282,6 +291,8 @@ class ResBlockShell(nn.Module):
                                         nn.Conv2d(self.out_channels, self.out_channels, 3, padding=1))
         self.skip_connection = (nn.Identity() if self.out_channels == channels
                                 else nn.Conv2d(channels, self.out_channels, 1))
+        if use_temporal_conv:
+            self.temopral_conv = TemporalConvBlockShell(self.out_channels, dropout=0.1)
         self._fwd = blocks.lvdm_resblock_forward
 
     def forward(self, x, emb, batch_size=None):

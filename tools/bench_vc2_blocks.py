@@ -109,12 +109,17 @@ def temporal_torch(m, x):  # attention.py:475-519 (use_linear, only_self_att)
     b, c, t, h, w = x.shape
     x_in = x
     x = m.norm(x)
-    x = x.permute(0, 3, 4, 1, 2).reshape(b * h * w, c, t).transpose(1, 2).contiguous()  # (b h w) t c
-    x = m.proj_in(x)
+    x = x.permute(0, 3, 4, 1, 2).reshape(b * h * w, c, t)  # (b h w) c t
+    if m.use_linear:
+        x = m.proj_in(x.transpose(1, 2).contiguous())
+    else:  # Conv1d projections (the UNet's init_attn, openaimodel3d.py:418-432)
+        x = m.proj_in(x).transpose(1, 2).contiguous()
     for blk in m.transformer_blocks:
         x = basic_torch(blk, x)
-    x = m.proj_out(x)
-    x = x.view(b, h, w, t, c).permute(0, 4, 3, 1, 2).contiguous()
+    if m.use_linear:
+        x = m.proj_out(x).view(b, h, w, t, c).permute(0, 4, 3, 1, 2).contiguous()
+    else:
+        x = m.proj_out(x.transpose(1, 2).contiguous()).view(b, h, w, c, t).permute(0, 3, 4, 1, 2).contiguous()
     return x + x_in
 
 
@@ -165,7 +170,8 @@ def main():
             # the UNet's first temporal transformer (init_attn): 8 heads x 64 on the 320-channel input, openaimodel3d.py:418-432
             C, _, h, w = LEVELS[0][:4]
             xt0 = rn(BATCH, C, FRAMES, h, w)
-            work.append(("temporal", H.TemporalTransformerShell(C, 8, 64, depth=1, temporal_length=FRAMES), (xt0,), rn(*xt0.shape)))
+            work.append(("temporal", H.TemporalTransformerShell(C, 8, 64, depth=1, use_linear=False, temporal_length=FRAMES),
+                         (xt0,), rn(*xt0.shape)))
     finally:
         torch.set_default_dtype(torch.float32)
     for _, m, _, _ in work:

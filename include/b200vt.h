@@ -182,6 +182,19 @@ int vt_groupnorm_silu_bwd(const void* dy, const void* x, const float* mean, cons
                           const float* gamma, const float* beta, float* dgamma, float* dbeta, int N, int C, int S, int G,
                           int apply_silu, int dtype, void* stream);
 
+/* The same GroupNorm(G) [+ SiLU] for CHANNELS-LAST activations: x, y, dy, dx are (N, S, C) in memory (torch.channels_last /
+ * channels_last_3d views of (N, C, *spatial) tensors), the layout the tensor-core convolutions run in and in which lvdm's
+ * `b c h w -> b (h w) c` (attention.py:381) is a free view. Same reference callables as vt_groupnorm_silu_fwd/bwd.
+ * C % 8 == 0 (bf16; C <= 4096) or C % 4 == 0 (fp32; C <= 2048). workspace: vt_groupnorm_nhwc_workspace_bytes(N, G) bytes,
+ * overwritten. dgamma / dbeta accumulate atomically (caller zeroes; nullable). */
+int64_t vt_groupnorm_nhwc_workspace_bytes(int N, int G);
+int vt_groupnorm_silu_nhwc_fwd(const void* x, void* y, float* mean, float* rstd, const float* gamma, const float* beta,
+                               void* workspace, int N, int C, int S, int G, float eps, int apply_silu, int dtype,
+                               void* stream);
+int vt_groupnorm_silu_nhwc_bwd(const void* dy, const void* x, const float* mean, const float* rstd, void* dx,
+                               const float* gamma, const float* beta, float* dgamma, float* dbeta, void* workspace, int N,
+                               int C, int S, int G, int apply_silu, int dtype, void* stream);
+
 #ifdef VT_EXPERIMENTS
 /* ---------------------------------------------------------------------------------------------------------------
  * Not part of the product library: the hooks below exist only in builds made with -DVT_EXPERIMENTS

@@ -307,3 +307,39 @@ def test_registered_op_route_matches_eager_fast_path():
         outs[reg] = [q.detach(), k.detach(), v.detach(), *gs]
     for u, v in zip(outs[True], outs[False]):
         assert float((u.float() - v.float()).abs().max()) <= 1e-3 * float(v.float().abs().max()) + 1e-6
+
+
+@pytest.mark.parametrize("shape", [(4, 320, 12, 16), (3, 960, 5, 8), (2, 2560, 4, 4), (2, 64, 3, 5, 7), (2, 320, 16, 6, 8)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("silu", [True, False])
+def test_groupnorm_channels_last_matches_fp32_reference_and_nchw_kernel(shape, dtype, silu):
+    """Channels-last GroupNorm(+SiLU) kernels (csrc/groupnorm_nhwc.cu; torch.channels_last / channels_last_3d inputs)
+    against torch's group_norm in fp32 and against the NCHW kernels, forward and backward; the output keeps the layout."""
+    import torch.nn.functional as F
+    import b200vt.functional as Fn
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(31)
+    C = shape[1]
+    fmt = torch.channels_last if len(shape) == 4 else torch.channels_last_3d
+    x = (torch.randn(*shape, device=dev, generator=g) * 1.5 + 0.3).to(dtype)
+    gw, gb = 1 + 0.1 * torch.randn(C, device=dev, generator=g), 0.1 * torch.randn(C, device=dev, generator=g)
+    dy = torch.randn(*shape, device=dev, generator=g).to(dtype)
+    x_cl = x.contiguous(memory_format=fmt).requires_grad_(True)
+    wl, bl = gw.clone().requires_grad_(True), gb.clone().requires_grad_(True)
+    y = Fn.groupnorm_silu(x_cl, wl, bl, 32, 1e-5, silu=silu)
+    native = C <= (4096 if dtype == torch.bfloat16 else 2048)  # wider rows take the NCHW kernels (one layout copy)
+    assert y.shape == x.shape and (y.is_contiguous(memory_format=fmt) or not native)
+    y.backward(dy.contiguous(memory_format=fmt))
+    assert x_cl.grad.is_contiguous(memory_format=fmt) or not native
+    xr, wr, br = x.detach().float().clone().requires_grad_(True), gw.clone().requires_grad_(True), gb.clone().requires_grad_(True)
+    ref = F.group_norm(xr, 32, wr, br, 1e-5)
+    ref = F.silu(ref) if silu else ref
+    ref.backward(dy.float())
+    tol = 2e-2 if dtype == torch.bfloat16 else 2e-3
+    rel = lambda a, b: float((a.float() - b.float()).abs().max() / b.float().abs().max())  # noqa: E731
+    assert rel(y, ref) <= tol and rel(x_cl.grad, xr.grad) <= tol
+    assert rel(wl.grad, wr.grad) <= tol and rel(bl.grad, br.grad) <= tol
+    xn = x.detach().clone().requires_grad_(True)  # NCHW kernels on the same values
+    yn = Fn.groupnorm_silu(xn, gw, gb, 32, 1e-5, silu=silu)
+    yn.backward(dy)
+    assert rel(y, yn) <= tol and rel(x_cl.grad, xn.grad) <= tol

@@ -242,6 +242,9 @@ def run(args, emit=True):
     net = build(dev)
     add_lora_qkv(net)
     net.train()
+    if args.arm == "ours" and not getattr(args, "nchw", False):
+        import b200vt.patch as P
+        P.lvdm_channels_last(net)  # channels-last activation flow of the drop-ins (the reference arm stays NCHW, as it is)
     params = [p for p in net.parameters() if p.requires_grad]
     g = torch.Generator(device=dev).manual_seed(20230211)
     B, T = 2, 16
@@ -250,16 +253,20 @@ def run(args, emit=True):
     ctx = torch.randn(B, 77, 1024, device=dev, generator=g)
     tt = torch.randint(0, 1000, (B,), device=dev, generator=g)
     ckpt = not args.no_checkpoint
-    opt = torch.optim.AdamW(params, lr=6e-6, fused=True)
+    use_graph = bool(getattr(args, "graph", False))
+    if use_graph:
+        ckpt = False  # whole-step CUDA graph: no activation checkpointing (its RNG-state save is a host operation)
+    opt = torch.optim.AdamW(params, lr=6e-6, fused=True, capturable=use_graph)
 
-    def step(ours):
+    def step(ours, zero=True):
         x = (0.7 * x0 + 0.7 * noise).requires_grad_(False)
         with torch.autocast("cuda", dtype=BF16):
             pred = net(x, tt, ctx, 24, ours=ours, ckpt=ckpt)
             loss = F.mse_loss(pred.float(), noise)
         loss.backward()
         opt.step()
-        opt.zero_grad(set_to_none=True)
+        if zero:
+            opt.zero_grad(set_to_none=True)
         return loss
 
     if args.check:
@@ -284,22 +291,46 @@ def run(args, emit=True):
         return line
 
     ours = args.arm == "ours"
-    for _ in range(args.warmup):
-        step(ours)
+    graph = None
+    if use_graph:
+        # The whole training step — forward, loss, backward, fused AdamW — captured ONCE into a CUDA graph and replayed:
+        # the ~10 000 eager launches of a step (the B200 finishes most of them faster than the host can issue the next) become
+        # one graph launch. Static inputs, graph-safe philox for the dropout masks, capturable optimizer.
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(3, args.warmup)):
+                step(ours)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_loss = step(ours, zero=False)
+        for _ in range(2):
+            graph.replay()
+    else:
+        for _ in range(args.warmup):
+            step(ours)
     torch.cuda.synchronize()
     torch.cuda.reset_peak_memory_stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        loss = step(ours)
+        if graph is not None:
+            graph.replay()
+            loss = static_loss
+        else:
+            loss = step(ours)
     e1.record()
     torch.cuda.synchronize()
     s_per_it = e0.elapsed_time(e1) / 1e3 / args.steps
     line = {"tool": "bench_vc2_unet", "arm": args.arm, "s_per_it": round(s_per_it, 4), "it_per_s": round(1.0 / s_per_it, 3),
-            "steps": args.steps, "warmup": args.warmup, "loss": round(float(loss), 4),
+            "steps": args.steps, "warmup": args.warmup, "loss": round(float(loss.detach()), 4),
             "config": {"batch": B, "frames": T, "latent": [4, T, 40, 64], "context": [77, 1024], "dtype": "bf16 autocast",
                        "unet_params": sum(p.numel() for p in net.parameters()), "trainable_params": sum(p.numel() for p in params),
-                       "lora": "rank 4 on to_q/to_k/to_v", "activation_checkpointing": ckpt, "optimizer": "AdamW (fused)"},
+                       "lora": "rank 4 on to_q/to_k/to_v", "activation_checkpointing": ckpt, "optimizer": "AdamW (fused)",
+                       "launch": "one CUDA graph per step" if use_graph else "eager",
+                       "activation_layout": ("channels_last" if args.arm == "ours" and not getattr(args, "nchw", False) else "nchw")},
             "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1)}
     if emit:
         print(json.dumps(line), flush=True)
@@ -313,6 +344,10 @@ def parse(argv=None):
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--no-checkpoint", action="store_true")
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--nchw", action="store_true", help="ours arm without the channels-last activation flow")
+    ap.add_argument("--graph", action="store_true",
+                    help="capture the whole step (forward, loss, backward, AdamW) into one CUDA graph and replay it (implies "
+                    "--no-checkpoint)")
     return ap.parse_args(argv)
 
 

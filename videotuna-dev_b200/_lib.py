@@ -48,6 +48,11 @@ _SIGS = {
                               vp],
     "vt_groupnorm_silu_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                               vp],
+    "vt_groupnorm_nhwc_workspace_bytes": [C.c_int, C.c_int],
+    "vt_groupnorm_silu_nhwc_fwd": [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
+                                   C.c_int, vp],
+    "vt_groupnorm_silu_nhwc_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, vp],
 }
 # Present only in -DVT_EXPERIMENTS builds of the library (tools/build_variant.sh + B200VT_LIB); see include/b200vt.h.
 _EXPERIMENT_SIGS = {
@@ -56,7 +61,7 @@ _EXPERIMENT_SIGS = {
     "vt_tma_mixed_rate": [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp, vp],
     "vt_umma_probe": [vp, vp, vp, C.c_int, C.c_int, C.c_int] + [C.c_uint32] * 6 + [vp],
 }
-_RESTYPE = {"vt_attn_bwd_workspace_bytes": C.c_int64}
+_RESTYPE = {"vt_attn_bwd_workspace_bytes": C.c_int64, "vt_groupnorm_nhwc_workspace_bytes": C.c_int64}
 
 
 class B200VTError(RuntimeError):

@@ -354,12 +354,33 @@ def _lvdm_gn(norm: nn.GroupNorm, x: Tensor, silu: bool = False) -> Tensor:
     return Fn.groupnorm_silu(x, norm.weight, norm.bias, norm.num_groups, norm.eps, silu=silu)
 
 
+def _is_cl(x: Tensor) -> bool:
+    """Channels-last activation: (N, C, *spatial) whose memory is (N, *spatial, C) (torch.channels_last / channels_last_3d)."""
+    from .ops import _channels_last
+    return x.dim() >= 4 and _channels_last(x)
+
+
+def _cl_weights(conv) -> bool:
+    """The module opted into the channels-last flow: its convolution weight was converted once by
+    patch.lvdm_channels_last(model) (otherwise cuDNN would re-lay the filter on every call)."""
+    w = getattr(conv, "weight", None)
+    return w is not None and w.dim() >= 4 and not w.is_contiguous() and w.stride(1) == 1
+
+
 def lvdm_spatial_transformer_forward(self, x: Tensor, context: Optional[Tensor] = None) -> Tensor:
     """Drop-in body of SpatialTransformer.forward: GroupNorm(32) with fp32 statistics in one kernel, then the
-    reference's own projections, blocks and layout changes."""
+    reference's own projections and blocks. With a channels-last activation (the layout the UNet's convolutions run in
+    after patch.lvdm_channels_last) both layout changes of the reference — `b c h w -> b (h w) c` before proj_in and its
+    inverse after proj_out (attention.py:381, 389) — are views: GroupNorm reads and writes (b, h*w, c) memory directly."""
     b, c, h, w = x.shape
     x_in = x
     x = _lvdm_gn(self.norm, x)
+    if self.use_linear and _is_cl(x):
+        x = self.proj_in(x.permute(0, 2, 3, 1).reshape(b, h * w, c))  # free view of the channels-last tensor
+        for block in self.transformer_blocks:
+            x = block(x, context=context)
+        x = self.proj_out(x)
+        return x.view(b, h, w, -1).permute(0, 3, 1, 2) + x_in       # a channels-last (b, c, h, w) view: no copy
     if not self.use_linear:
         x = self.proj_in(x)
     x = x.flatten(2).transpose(1, 2).contiguous()  # b c h w -> b (h w) c
@@ -377,10 +398,13 @@ def lvdm_spatial_transformer_forward(self, x: Tensor, context: Optional[Tensor] 
 
 def lvdm_temporal_transformer_forward(self, x: Tensor, context: Optional[Tensor] = None) -> Tensor:
     """Drop-in body of TemporalTransformer.forward for the configurations the reference trains (only_self_att, with or
-    without the causal mask); the per-sample cross-attention loop (:499-509) stays on the reference path."""
+    without the causal mask); the per-sample cross-attention loop (:499-509) stays on the reference path. A channels-last
+    (channels_last_3d) input keeps its layout: GroupNorm runs on (b, t*h*w, c) memory and the result of the block is
+    written back in that layout, so the surrounding `(b f) c h w <-> b c f h w` rearranges stay views."""
     _require(self.only_self_att, "temporal cross-attention stays on the reference path")
     b, c, t, h, w = x.shape
     x_in = x
+    cl = _is_cl(x)
     x = _lvdm_gn(self.norm, x)
     if self.use_linear:
         x = x.permute(0, 3, 4, 2, 1).reshape(b * h * w, t, c)  # b c t h w -> (b h w) t c   (one copy)
@@ -393,12 +417,13 @@ def lvdm_temporal_transformer_forward(self, x: Tensor, context: Optional[Tensor]
         mask = self.mask.to(x.device).expand(b * h * w, -1, -1)
     for block in self.transformer_blocks:
         x = block(x, mask=mask)
+    fmt = torch.channels_last_3d if cl else torch.contiguous_format
     if self.use_linear:
         x = self.proj_out(x)
-        x = x.view(b, h, w, t, -1).permute(0, 4, 3, 1, 2).contiguous()  # (b h w) t c -> b c t h w
+        x = x.view(b, h, w, t, -1).permute(0, 4, 3, 1, 2).contiguous(memory_format=fmt)  # (b h w) t c -> b c t h w
     else:
         x = self.proj_out(x.transpose(1, 2).contiguous())
-        x = x.view(b, h, w, -1, t).permute(0, 3, 4, 1, 2).contiguous()
+        x = x.view(b, h, w, -1, t).permute(0, 3, 4, 1, 2).contiguous(memory_format=fmt)
     return x + x_in
 
 
@@ -407,6 +432,8 @@ def lvdm_resblock_forward(self, x: Tensor, emb: Tensor, batch_size: Optional[int
     kernel each; convolutions, up/down-sampling and the temporal conv block stay the module's own layers."""
     _require(x.is_cuda and x.dtype in (_BF16, torch.float32), "CUDA bf16/fp32 activations only")
     in_norm, in_conv = self.in_layers[0], self.in_layers[-1]
+    if x.dim() == 4 and _cl_weights(in_conv) and not _is_cl(x):
+        x = x.contiguous(memory_format=torch.channels_last)  # enter the channels-last flow (patch.lvdm_channels_last)
     h = _lvdm_gn(in_norm, x, silu=True)
     if self.updown:
         h = self.h_upd(h)

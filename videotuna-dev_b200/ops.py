@@ -667,54 +667,92 @@ def _gn_dtype(x: Tensor) -> int:
     raise RuntimeError(f"b200vt: groupnorm supports bf16/fp32, got {x.dtype}")
 
 
+def _channels_last(x: Tensor) -> bool:
+    """(N, C, *spatial) tensor whose memory is (N, *spatial, C) — torch.channels_last / channels_last_3d — and not also
+    plain contiguous (degenerate sizes). Strides are compared directly (this runs on every GroupNorm call)."""
+    nd = x.dim()
+    if nd < 3:
+        return False
+    st, sh = x.stride(), x.shape
+    if st[1] != 1 or sh[1] == 1:
+        return False
+    want = sh[1]
+    for d in range(nd - 1, 1, -1):
+        if st[d] != want and sh[d] != 1:
+            return False
+        want *= sh[d]
+    return (st[0] == want or sh[0] == 1) and want != sh[1]  # want == C only when every spatial size is 1
+
+
+def _to_channels_last(t: Tensor) -> Tensor:
+    return t if _channels_last(t) else t.movedim(1, -1).contiguous().movedim(-1, 1)
+
+
 @torch.library.custom_op("b200vt::groupnorm_silu_fwd", mutates_args=(), device_types="cuda")
 def groupnorm_silu_fwd(x: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor], groups: int, eps: float,
                        silu: bool) -> Tuple[Tensor, Tensor, Tensor]:
-    """x (N, C, *spatial) bf16/fp32 contiguous -> y, mean (N,G), rstd (N,G); statistics in fp32."""
+    """x (N, C, *spatial) bf16/fp32 -> y, mean (N,G), rstd (N,G); statistics in fp32. A channels-last x (torch.channels_last
+    / channels_last_3d) runs the channels-last kernels and y keeps that layout; anything else is made NCHW-contiguous."""
     if not x.is_cuda:
         raise RuntimeError("b200vt: groupnorm input must be a CUDA tensor (there is no CPU path)")
-    x = x.contiguous()
     N, Cc = x.shape[0], x.shape[1]
     S = x.numel() // (N * Cc)
-    y = torch.empty_like(x)
+    nhwc = _channels_last(x) and Cc % (8 if x.dtype == torch.bfloat16 else 4) == 0 and Cc <= (4096 if x.dtype == torch.bfloat16 else 2048)
+    if not nhwc:
+        x = x.contiguous()
+    y = torch.empty_like(x)  # preserves x's (dense) layout
     mean = torch.empty((N, groups), dtype=torch.float32, device=x.device)
     rstd = torch.empty_like(mean)
     g, b = _f32(gamma), _f32(beta)
     with torch.cuda.device(x.device):
-        _lib.call("vt_groupnorm_silu_fwd", _ptr(x), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(g), _ptr(b), N, Cc, S, groups,
-                  float(eps), int(silu), _gn_dtype(x), _stream())
+        if nhwc:
+            ws = torch.empty((_lib.lib().vt_groupnorm_nhwc_workspace_bytes(N, groups),), dtype=torch.uint8, device=x.device)
+            _lib.call("vt_groupnorm_silu_nhwc_fwd", _ptr(x), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(g), _ptr(b), _ptr(ws), N, Cc,
+                      S, groups, float(eps), int(silu), _gn_dtype(x), _stream())
+        else:
+            _lib.call("vt_groupnorm_silu_fwd", _ptr(x), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(g), _ptr(b), N, Cc, S, groups,
+                      float(eps), int(silu), _gn_dtype(x), _stream())
     return y, mean, rstd
 
 
 @groupnorm_silu_fwd.register_fake
 def _(x, gamma, beta, groups, eps, silu):
     N = x.shape[0]
-    return torch.empty_like(x, memory_format=torch.contiguous_format), \
-        x.new_empty((N, groups), dtype=torch.float32), x.new_empty((N, groups), dtype=torch.float32)
+    y = torch.empty_like(x) if _channels_last(x) else torch.empty_like(x, memory_format=torch.contiguous_format)
+    return y, x.new_empty((N, groups), dtype=torch.float32), x.new_empty((N, groups), dtype=torch.float32)
 
 
 @torch.library.custom_op("b200vt::groupnorm_silu_bwd", mutates_args=(), device_types="cuda")
 def groupnorm_silu_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Optional[Tensor],
                        beta: Optional[Tensor], groups: int, silu: bool) -> Tuple[Tensor, Tensor, Tensor]:
-    dy, x = dy.contiguous(), x.contiguous()
     N, Cc = x.shape[0], x.shape[1]
     S = x.numel() // (N * Cc)
+    nhwc = _channels_last(x) and Cc % (8 if x.dtype == torch.bfloat16 else 4) == 0 and Cc <= (4096 if x.dtype == torch.bfloat16 else 2048)
+    dy = dy.to(x.dtype)
+    if nhwc:
+        dy = _to_channels_last(dy)
+    else:
+        dy, x = dy.contiguous(), x.contiguous()
     dx = torch.empty_like(x)
     dgamma = torch.zeros((Cc,), dtype=torch.float32, device=x.device)
     dbeta = torch.zeros_like(dgamma)
     g, b = _f32(gamma), _f32(beta)
-    dy = dy.to(x.dtype)
     with torch.cuda.device(x.device):
-        _lib.call("vt_groupnorm_silu_bwd", _ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(g),
-                  _ptr(b), _ptr(dgamma), _ptr(dbeta), N, Cc, S, groups, int(silu), _gn_dtype(x), _stream())
+        if nhwc:
+            ws = torch.empty((_lib.lib().vt_groupnorm_nhwc_workspace_bytes(N, groups),), dtype=torch.uint8, device=x.device)
+            _lib.call("vt_groupnorm_silu_nhwc_bwd", _ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(g), _ptr(b),
+                      _ptr(dgamma), _ptr(dbeta), _ptr(ws), N, Cc, S, groups, int(silu), _gn_dtype(x), _stream())
+        else:
+            _lib.call("vt_groupnorm_silu_bwd", _ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(g),
+                      _ptr(b), _ptr(dgamma), _ptr(dbeta), N, Cc, S, groups, int(silu), _gn_dtype(x), _stream())
     return dx, dgamma, dbeta
 
 
 @groupnorm_silu_bwd.register_fake
 def _(dy, x, mean, rstd, gamma, beta, groups, silu):
     Cc = x.shape[1]
-    return torch.empty_like(x, memory_format=torch.contiguous_format), x.new_empty((Cc,), dtype=torch.float32), \
-        x.new_empty((Cc,), dtype=torch.float32)
+    dx = torch.empty_like(x) if _channels_last(x) else torch.empty_like(x, memory_format=torch.contiguous_format)
+    return dx, x.new_empty((Cc,), dtype=torch.float32), x.new_empty((Cc,), dtype=torch.float32)
 
 
 def _gn_setup(ctx, inputs, output):

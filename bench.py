@@ -415,20 +415,27 @@ def denoiser_it_s(world: int):
         import torch
         import bench_vc2_unet as VU
         rec = {}
-        for arm in ("ours", "torch"):
+        for key, arm, graph in (("ours", "ours", False), ("torch", "torch", False), ("ours_cuda_graph", "ours", True)):
             try:
-                r = VU.run(_t.SimpleNamespace(arm=arm, steps=5, warmup=3, no_checkpoint=False, check=False), emit=False)
-                rec[arm] = {"s_per_it": r["s_per_it"], "it_per_s": r["it_per_s"], "peak_mem_GB": r["peak_mem_GB"]}
+                r = VU.run(_t.SimpleNamespace(arm=arm, steps=5, warmup=3, no_checkpoint=False, check=False, nchw=False,
+                                              graph=graph), emit=False)
+                rec[key] = {"s_per_it": r["s_per_it"], "it_per_s": r["it_per_s"], "peak_mem_GB": r["peak_mem_GB"],
+                            "launch": r["config"]["launch"], "activation_checkpointing": r["config"]["activation_checkpointing"],
+                            "activation_layout": r["config"]["activation_layout"]}
             except Exception as e:  # noqa: BLE001
-                rec[arm] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+                rec[key] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
             import gc
             gc.collect()
             torch.cuda.empty_cache()
         if "s_per_it" in rec.get("ours", {}) and "s_per_it" in rec.get("torch", {}):
             rec["speedup_vs_reference_op_sequence"] = round(rec["torch"]["s_per_it"] / rec["ours"]["s_per_it"], 3)
+        if "s_per_it" in rec.get("ours_cuda_graph", {}) and "s_per_it" in rec.get("torch", {}):
+            rec["speedup_cuda_graph_vs_reference_op_sequence"] = round(rec["torch"]["s_per_it"] / rec["ours_cuda_graph"]["s_per_it"], 3)
         rec["iteration"] = ("whole UNet (1.4 B parameters): forward on 2 x 4 x 16 x 40 x 64 latents + 77 x 1024 context, MSE loss, "
-                            "backward, fused AdamW on rank-4 LoRA adapters; bf16 autocast, per-block activation checkpointing "
-                            "(use_checkpoint: true); `torch` = the reference's op sequence on the same modules and weights")
+                            "backward, fused AdamW on rank-4 LoRA adapters; bf16 autocast. `ours` / `torch`: the reference's "
+                            "configuration (eager launches, per-block activation checkpointing, use_checkpoint: true), `torch` = "
+                            "the reference's op sequence on the same modules and weights; `ours_cuda_graph`: the whole step "
+                            "captured once into a CUDA graph, no checkpointing (fits easily in 180 GB)")
         out["videocrafter2_320x512x16f_lora_b2"] = rec
     return out
 

@@ -195,6 +195,12 @@ int vt_groupnorm_silu_nhwc_bwd(const void* dy, const void* x, const float* mean,
                                const float* gamma, const float* beta, float* dgamma, float* dbeta, void* workspace, int N,
                                int C, int S, int G, int apply_silu, int dtype, void* stream);
 
+/* Gated GELU of lvdm's feed-forward in one pass: y[m, f] = xin[m, f] * gelu(xin[m, F + f]) (exact erf GELU), xin (M, 2F),
+ * y (M, F) bf16 contiguous, F % 8 == 0. Replaces GEGLU.forward after its Linear (lvdm/modules/attention.py:522-529).
+ * Backward: dxin (M, 2F) = [dy * gelu(gate) | dy * x * gelu'(gate)]. */
+int vt_geglu_fwd(const void* xin, void* y, int64_t M, int F, void* stream);
+int vt_geglu_bwd(const void* dy, const void* xin, void* dxin, int64_t M, int F, void* stream);
+
 #ifdef VT_EXPERIMENTS
 /* ---------------------------------------------------------------------------------------------------------------
  * Not part of the product library: the hooks below exist only in builds made with -DVT_EXPERIMENTS

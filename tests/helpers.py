@@ -179,13 +179,20 @@ class WanBlockShell(nn.Module):
 
 
 class GEGLUShell(nn.Module):
+    """lvdm GEGLU (attention.py:522-529) with the drop-in forward patch_blocks() installs (functional.lvdm_geglu_forward);
+    inputs outside the CUDA path take the reference arithmetic, as the patch layer's fallback does."""
+
     def __init__(self, dim_in, dim_out):
         super().__init__()
         self.proj = nn.Linear(dim_in, dim_out * 2)
 
     def forward(self, x):
-        x, gate = self.proj(x).chunk(2, dim=-1)
-        return x * torch.nn.functional.gelu(gate)
+        from b200vt import functional
+        try:
+            return functional.lvdm_geglu_forward(self, x)
+        except functional.Unsupported:
+            x, gate = self.proj(x).chunk(2, dim=-1)
+            return x * torch.nn.functional.gelu(gate)
 
 
 class FeedForwardShell(nn.Module):

@@ -343,3 +343,22 @@ def test_groupnorm_channels_last_matches_fp32_reference_and_nchw_kernel(shape, d
     yn = Fn.groupnorm_silu(xn, gw, gb, 32, 1e-5, silu=silu)
     yn.backward(dy)
     assert rel(y, yn) <= tol and rel(x_cl.grad, xn.grad) <= tol
+
+
+@pytest.mark.parametrize("shape", [(3, 70, 2 * 1280), (2, 5, 7, 2 * 64), (1, 81920, 2 * 1280)])
+def test_geglu_matches_exact_gelu_reference(shape):
+    """Fused gated GELU (csrc/geglu.cu; lvdm GEGLU.forward, attention.py:527-529) against x * F.gelu(gate) in fp32, forward and
+    backward; the last shape is the VideoCrafter2 level-0 feed-forward (batch 2 x 16 frames x 40 x 64 tokens, 8 * 320 wide)."""
+    import torch.nn.functional as F
+    import b200vt.ops as ops
+    g = torch.Generator(device="cuda").manual_seed(17)
+    xin = (torch.randn(*shape, device="cuda", generator=g) * 1.5).bfloat16().requires_grad_(True)
+    dy = torch.randn(*shape[:-1], shape[-1] // 2, device="cuda", generator=g).bfloat16()
+    y = ops.geglu_fwd(xin)
+    y.backward(dy)
+    xr = xin.detach().float().requires_grad_(True)
+    a, gate = xr.chunk(2, dim=-1)
+    ref = a * F.gelu(gate)
+    ref.backward(dy.float())
+    rel = lambda u, v: float((u.float() - v).abs().max() / v.abs().max())  # noqa: E731
+    assert rel(y, ref) <= 1e-2 and rel(xin.grad, xr.grad) <= 1e-2

@@ -116,7 +116,7 @@ def test_block_hooks_install_fall_back_and_restore(shims):
     originals = (A.SpatialTransformer.forward, A.BasicTransformerBlock._forward, O3.ResBlock._forward,
                  M.MMDoubleStreamBlock.forward)
     done = P.patch_blocks(wan=False)
-    assert done["lvdm"] == 5 and done["hunyuan"] >= 3
+    assert done["lvdm"] == 6 and done["hunyuan"] >= 3
     assert all(getattr(f, "_b200vt_patched", False) for f in (A.SpatialTransformer.forward, A.TemporalTransformer.forward,
                                                                A.BasicTransformerBlock._forward, O3.ResBlock._forward,
                                                                O3.TemporalConvBlock.forward,

@@ -86,10 +86,15 @@ def attn_torch(m, x, context=None, mask=None):  # attention.py:101-170 (no relat
     return m.to_out(out)
 
 
+def ff_torch(ff, x):  # FeedForward(glu=True) -> GEGLU (attention.py:522-548): chunk / gelu / mul as separate torch ops
+    a, gate = ff.net[0].proj(x).chunk(2, dim=-1)
+    return ff.net[2](ff.net[1](a * F.gelu(gate)))
+
+
 def basic_torch(m, x, context=None, mask=None):  # attention.py:299-310
     x = attn_torch(m.attn1, m.norm1(x), context=None, mask=mask) + x
     x = attn_torch(m.attn2, m.norm2(x), context=context, mask=mask) + x
-    return m.ff(m.norm3(x)) + x
+    return ff_torch(m.ff, m.norm3(x)) + x
 
 
 def spatial_torch(m, x, context):  # attention.py:376-392 (use_linear)

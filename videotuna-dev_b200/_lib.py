@@ -48,6 +48,8 @@ _SIGS = {
                               vp],
     "vt_groupnorm_silu_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                               vp],
+    "vt_geglu_fwd": [vp, vp, C.c_int64, C.c_int, vp],
+    "vt_geglu_bwd": [vp, vp, vp, C.c_int64, C.c_int, vp],
     "vt_groupnorm_nhwc_workspace_bytes": [C.c_int, C.c_int],
     "vt_groupnorm_silu_nhwc_fwd": [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
                                    C.c_int, vp],

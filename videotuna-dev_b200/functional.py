@@ -358,6 +358,15 @@ def qk_rmsnorm_rope(x: Tensor, weight: Optional[Tensor], cos: Optional[Tensor], 
     return y
 
 
+def lvdm_geglu_forward(self, x: Tensor) -> Tensor:
+    """Drop-in body of lvdm GEGLU.forward (attention.py:527-529): the module's own projection, then x * gelu(gate) in one
+    pass over its output (the widest tensor of the UNet) instead of chunk / gelu / mul."""
+    h = self.proj(x)
+    _require(h.is_cuda and h.dtype == torch.bfloat16 and h.shape[-1] % 16 == 0,
+             "fused GEGLU needs a CUDA bf16 projection output (bf16 weights or autocast)")
+    return ops.geglu_fwd(h)
+
+
 def hunyuan_joint_qkv(img_qkv: Tensor, txt_qkv: Tensor, img_q_norm, img_k_norm, txt_q_norm, txt_k_norm,
                       cos: Optional[Tensor], sin: Optional[Tensor]) -> Tuple[Tensor, Tensor, Tensor]:
     """MMDoubleStreamBlock's q/k/v preparation (hyvideo_t2v/modules/models.py:166-194) in one op: img_qkv (B,L,3,H,D) and

@@ -773,6 +773,56 @@ groupnorm_silu_fwd.register_autograd(_gn_backward, setup_context=_gn_setup)
 
 
 # =====================================================================================================================
+# gated GELU (lvdm feed-forward)
+# =====================================================================================================================
+@torch.library.custom_op("b200vt::geglu_fwd", mutates_args=(), device_types="cuda")
+def geglu_fwd(xin: Tensor) -> Tensor:
+    """xin (..., 2F) bf16 = [x | gate] -> x * gelu(gate) (..., F), exact erf GELU (lvdm GEGLU, attention.py:527-529)."""
+    _check_bf16_cuda("xin", xin)
+    xin = xin.contiguous()
+    F2 = xin.shape[-1]
+    M = xin.numel() // F2
+    y = torch.empty((*xin.shape[:-1], F2 // 2), dtype=xin.dtype, device=xin.device)
+    with torch.cuda.device(xin.device):
+        _lib.call("vt_geglu_fwd", _ptr(xin), _ptr(y), C.c_int64(M), F2 // 2, _stream())
+    return y
+
+
+@geglu_fwd.register_fake
+def _(xin):
+    return xin.new_empty((*xin.shape[:-1], xin.shape[-1] // 2))
+
+
+@torch.library.custom_op("b200vt::geglu_bwd", mutates_args=(), device_types="cuda")
+def geglu_bwd(dy: Tensor, xin: Tensor) -> Tensor:
+    xin = xin.contiguous()
+    dy = dy.contiguous().to(xin.dtype)
+    F2 = xin.shape[-1]
+    M = xin.numel() // F2
+    dxin = torch.empty_like(xin)
+    with torch.cuda.device(xin.device):
+        _lib.call("vt_geglu_bwd", _ptr(dy), _ptr(xin), _ptr(dxin), C.c_int64(M), F2 // 2, _stream())
+    return dxin
+
+
+@geglu_bwd.register_fake
+def _(dy, xin):
+    return torch.empty_like(xin, memory_format=torch.contiguous_format)
+
+
+def _geglu_setup(ctx, inputs, output):
+    ctx.save_for_backward(inputs[0])
+
+
+def _geglu_backward(ctx, dy):
+    (xin,) = ctx.saved_tensors
+    return geglu_bwd(dy, xin)
+
+
+geglu_fwd.register_autograd(_geglu_backward, setup_context=_geglu_setup)
+
+
+# =====================================================================================================================
 # self-test hook
 # =====================================================================================================================
 def umma_probe(a: Tensor, b: Tensor, a_mode: int, b_mode: int, n: int = 128, a_desc=(16, 1024, 32),
@@ -852,6 +902,6 @@ _default_fast = "1" if int(_os.environ.get("WORLD_SIZE", "1") or "1") <= 1 else 
 if _os.environ.get("B200VT_EAGER_FAST", _default_fast) != "0":
     for _name in ("attn_fwd", "attn_bwd", "attn_fwd_scatter", "temporal_attn_fwd", "temporal_attn_bwd", "ln_modulate_fwd",
                   "ln_modulate_bwd", "gate_residual_fwd", "gate_residual_bwd", "qk_rmsnorm_rope_fwd", "qk_rmsnorm_rope_bwd",
-                  "groupnorm_silu_fwd", "groupnorm_silu_bwd", "joint_qkv_fwd", "joint_qkv_bwd"):
+                  "groupnorm_silu_fwd", "groupnorm_silu_bwd", "joint_qkv_fwd", "joint_qkv_bwd", "geglu_fwd", "geglu_bwd"):
         if _name in globals():
             globals()[_name] = _make_eager(globals()[_name])

@@ -129,6 +129,7 @@ def patch_blocks(lvdm: bool = True, hunyuan: bool = True, wan: bool = True) -> D
             done["lvdm"] += _patch_method(mod, "BasicTransformerBlock", "_forward", Bk.lvdm_basic_block_forward)
             done["lvdm"] += _patch_method(mod, "SpatialTransformer", "forward", Bk.lvdm_spatial_transformer_forward)
             done["lvdm"] += _patch_method(mod, "TemporalTransformer", "forward", Bk.lvdm_temporal_transformer_forward)
+            done["lvdm"] += _patch_method(mod, "GEGLU", "forward", Fn.lvdm_geglu_forward)
         net = _try_import("videotuna.models.lvdm.modules.networks.openaimodel3d")
         if net is not None:
             done["lvdm"] += _patch_method(net, "ResBlock", "_forward", Bk.lvdm_resblock_forward)

@@ -308,6 +308,9 @@ def parse(argv=None):
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--no-checkpoint", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="capture the whole iteration (forward, backward, optimizer step) into one CUDA graph and replay it "
+                    "(single GPU)")
     ap.add_argument("--optimizer", choices=("none", "adamw"), default="none",
                     help="adamw: one fused AdamW step on the trainable parameters (LoRA adapters for hunyuan, every block "
                     "weight for wan / cogvideox) inside the timed iteration, lr 1e-5 as the reference configs")
@@ -339,8 +342,12 @@ def run(args, manage_dist: bool = True, emit: bool = True):
     ours = args.arm == "ours"
     ckpt = not args.no_checkpoint
 
+    use_graph = bool(getattr(args, "graph", False))
+    assert not (use_graph and world > 1), "--graph is single-GPU"
+
     def run_block(fn, *a):
-        return checkpoint(fn, *a, use_reentrant=False) if ckpt else fn(*a)
+        # under graph capture the checkpoint must not save / restore the RNG state (a host operation); these blocks have no dropout
+        return checkpoint(fn, *a, use_reentrant=False, preserve_rng_state=not use_graph) if ckpt else fn(*a)
 
     opt_state = {}
 
@@ -348,7 +355,8 @@ def run(args, manage_dist: bool = True, emit: bool = True):
         """End of an iteration: the optimizer step of a finetuning iteration (--optimizer adamw), then drop the gradients."""
         if getattr(args, "optimizer", "none") == "adamw":
             if "opt" not in opt_state:
-                opt_state["opt"] = torch.optim.AdamW([p for p in params if p.requires_grad], lr=1e-5, fused=True)
+                opt_state["opt"] = torch.optim.AdamW([p for p in params if p.requires_grad], lr=1e-5, fused=True,
+                                                     capturable=use_graph)
             opt_state["opt"].step()
         for p in params:
             p.grad = None
@@ -490,16 +498,33 @@ def run(args, manage_dist: bool = True, emit: bool = True):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        iteration()
+    graph = None
+    if use_graph:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(max(3, args.warmup)):
+                iteration()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            iteration()
+        graph.replay()
+    else:
+        for _ in range(args.warmup):
+            iteration()
     sync_all()
     torch.cuda.reset_peak_memory_stats()
-    L.profile_enable(True)
+    L.profile_enable(not use_graph)  # per-kernel event timing records events at launch time: not inside a replayed graph
     e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall = time.perf_counter()
     e0_.record()
     for _ in range(args.steps):
-        iteration()
+        if graph is not None:
+            graph.replay()
+        else:
+            iteration()
     e1_.record()
     sync_all()
     t_wall = time.perf_counter() - t_wall
@@ -518,6 +543,7 @@ def run(args, manage_dist: bool = True, emit: bool = True):
             "config": {**layers_desc, "img_tokens": n_img, "txt_tokens": n_txt, "hidden": C, "heads": heads,
                        "block_params": n_params, "trainable_params": sum(p.numel() for p in params),
                        "activation_checkpointing": ckpt, "dtype": "bf16", "optimizer": getattr(args, "optimizer", "none"),
+                       "launch": "one CUDA graph per iteration" if use_graph else "eager",
                        "parallelism": "single" if world == 1 else f"ulysses_sp{world}",
                        "attention": ("b200vt tcgen05 kernels" if ours else (
                            "F.scaled_dot_product_attention (diffusers CogVideoXAttnProcessor2_0)" if args.model == "cogvideox"
@@ -527,7 +553,7 @@ def run(args, manage_dist: bool = True, emit: bool = True):
             "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1),
             "wall_s": round(t_wall, 2),
         }
-        if ours:
+        if ours and not use_graph:
             line["attention_kernel_s_per_it"] = round(attn_ms / 1e3 / args.steps, 4)
             line["attention_share_of_step"] = round(attn_ms / 1e3 / args.steps / s_per_it, 4)
             line["attention_launches_per_it"] = attn_launches / args.steps

@@ -296,18 +296,15 @@ def run(args, emit=True):
         # The whole training step — forward, loss, backward, fused AdamW — captured ONCE into a CUDA graph and replayed:
         # the ~10 000 eager launches of a step (the B200 finishes most of them faster than the host can issue the next) become
         # one graph launch. Static inputs, graph-safe philox for the dropout masks, capturable optimizer.
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(max(3, args.warmup)):
-                step(ours)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            static_loss = step(ours, zero=False)
+        import b200vt.graph as G
+        def graphed():
+            opt.zero_grad(set_to_none=True)  # gradients are None when the capture starts: the captured backward ASSIGNS them
+            return step(ours, zero=False)
+
+        graph = G.GraphedStep(graphed, warmup=max(3, args.warmup))
+        static_loss = graph.result
         for _ in range(2):
-            graph.replay()
+            graph()
     else:
         for _ in range(args.warmup):
             step(ours)
@@ -317,7 +314,7 @@ def run(args, emit=True):
     e0.record()
     for _ in range(args.steps):
         if graph is not None:
-            graph.replay()
+            graph()
             loss = static_loss
         else:
             loss = step(ours)

@@ -626,7 +626,11 @@ def run_ours(args):
         host_out = [torch.empty(t.shape, dtype=torch.bfloat16).pin_memory() for t in (do, q, k, v, tq, tk, tv)]
         del q, k, v, tq, tk, tv, do, leaves
         torch.cuda.empty_cache()
-        n_groups = max(g_ for g_ in (6, 4, 3, 2, 1) if HEADS % g_ == 0 and (HEADS // g_) % world == 0)
+        # head groups of at least 3 heads per rank (a 1-head launch is 931 CTAs = 6.3 waves on 148 SMs: the wave tail and the
+        # per-group exchanges cost more than the finer overlap gains — N = 8 with 3 groups: e2e 7058 vs 8562 device-resident);
+        # with a single group the copies still hide behind the neighbouring steps' kernels (calls pipeline into one another)
+        n_groups = max([g_ for g_ in (6, 4, 3, 2) if HEADS % g_ == 0 and (HEADS // g_) % world == 0
+                        and (HEADS // g_) // world >= 3] or [1])
         host_attn = sp.HostUlyssesAttention(S_loc, TXT_TOKENS, HEADS, HEAD_DIM, head_groups=n_groups)
         hq, hk, hv, htq, htk, htv, hdo = host_in
 

@@ -174,7 +174,20 @@ def run(iters: int = 10, with_torch: bool = True, emit: bool = True):
                 "(tensor < L2)")
         report("groupnorm_silu_fwd[vc2]", shape, n * 4, f_ms, rf_ms, note=note)
         report("groupnorm_silu_bwd[vc2]", shape, n * 6, b_ms, rb_ms, note=note)
-        del xs, dys, ys, yrs
+        # the same tensors channels-last (patch.lvdm_channels_last flow): two sweeps per direction, the second from L2
+        fmt = torch.channels_last if len(shape) == 4 else torch.channels_last_3d
+        xc = [x.detach().contiguous(memory_format=fmt).requires_grad_(True) for x in xs]
+        dc = [d.contiguous(memory_format=fmt) for d in dys]
+        f_ms = timeit(lambda: Fn.groupnorm_silu(xc[nxt()], gw, gb, 32, 1e-5, silu=True), args.iters * 2)
+        yc = [Fn.groupnorm_silu(x, gw, gb, 32, 1e-5, silu=True) for x in xc]
+
+        def bwd_c():
+            i = nxt()
+            return torch.autograd.grad(yc[i], xc[i], dc[i], retain_graph=True)
+        b_ms = timeit(bwd_c, args.iters * 2)
+        report("groupnorm_silu_fwd[vc2, channels_last]", shape, n * 4, f_ms, float("nan"), note="algorithmic bytes: one read + one write")
+        report("groupnorm_silu_bwd[vc2, channels_last]", shape, n * 6, b_ms, float("nan"), note="algorithmic bytes: two reads + one write")
+        del xs, dys, ys, yrs, xc, dc, yc
 
     # ---- temporal micro-attention, N = 16 frames (VideoCrafter2 level 0: 2 x 40 x 64 positions, 5 heads) --------------
     Bt, N, H, D = 5120, 16, 5, 64

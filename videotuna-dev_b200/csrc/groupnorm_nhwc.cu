@@ -19,6 +19,7 @@
 //             per-group gamma-weighted sums;  apply: dx = gz * (rstd*gamma[c]) + x * c2[g] + c0[g] (gz recomputed).
 // A thread owns one 16-byte vector column (8 bf16 / 4 fp32 channels) and walks down the rows, so its accumulators live in
 // registers; blockDim is the largest multiple of C/VEC that fits 512 threads.
+#include <cstdlib>
 #include <cuda_bf16.h>
 
 #include "capi_util.h"
@@ -31,6 +32,17 @@ struct V;
 template <>
 struct V<__nv_bfloat16> {
   static constexpr int VEC = 8;
+  using Raw = uint4;
+  __device__ static Raw load_raw(const __nv_bfloat16* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ static void unpack(const Raw& u, float* f) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __bfloat1622float2(h[i]);
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
   __device__ static void load(const __nv_bfloat16* p, float* f) {
     const uint4 u = *reinterpret_cast<const uint4*>(p);
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -52,6 +64,9 @@ struct V<__nv_bfloat16> {
 template <>
 struct V<float> {
   static constexpr int VEC = 4;
+  using Raw = float4;
+  __device__ static Raw load_raw(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+  __device__ static void unpack(const Raw& v, float* f) { f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w; }
   __device__ static void load(const float* p, float* f) {
     const float4 v = *reinterpret_cast<const float4*>(p);
     f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
@@ -94,41 +109,69 @@ __device__ __forceinline__ RowSplit row_split(int C, int S, int rows_per_cta) {
 // ---- forward ---------------------------------------------------------------------------------------------------------
 // ws: float[N][chunks][G][2] per-CTA partial (sum, sum of squares): plain stores, reduced by the apply kernel's prologue —
 // no memset launch, no global atomics, deterministic.
+// Reduce per-thread per-channel partials over the CTA's `rpp` row groups: every thread stores its VEC values into
+// sm[r][channel] (plain stores), one barrier, then each thread sums one channel over the rpp rows. (Shared-memory float
+// atomics — the first version — are CAS loops: with 12 row groups on one address they cost more than the sweep itself.)
+template <int VEC, int NACC>
+__device__ __forceinline__ void cta_channel_sums(float* sm, const RowSplit& rs, int C, const float (*acc)[VEC], float* out) {
+  // sm: [rpp][NACC][C]; out: [NACC][C] (may alias the first row group's slab only after the barrier: use a separate slab)
+  if (rs.active) {
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) sm[(rs.r * NACC + a) * C + rs.v * VEC + k] = acc[a][k];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < NACC * C; i += blockDim.x) {
+    float t = 0.f;
+    for (int r = 0; r < rs.rpp; ++r) t += sm[r * NACC * C + i];
+    out[i] = t;
+  }
+  __syncthreads();
+}
+
 template <typename T>
 __global__ void gn_nhwc_stats_kernel(const T* __restrict__ x, float* __restrict__ ws, int C, int S, int G, int rows_per_cta) {
   constexpr int VEC = V<T>::VEC;
-  extern __shared__ float sm[];  // [2][C]
+  extern __shared__ float sm[];  // [rpp][2][C] partials, then [2][C] totals
   const int n = blockIdx.y;
   const RowSplit rs = row_split<VEC>(C, S, rows_per_cta);
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-  if (rs.active) {
-    float s1[VEC], s2[VEC];
+  float acc[2][VEC];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) s1[k] = s2[k] = 0.f;
+  for (int k = 0; k < VEC; ++k) acc[0][k] = acc[1][k] = 0.f;
+  if (rs.active) {
     const T* base = x + (static_cast<size_t>(n) * S) * C + rs.v * VEC;
-    for (int row = rs.row0 + rs.r; row < rs.row1; row += rs.rpp) {
+    int row = rs.row0 + rs.r;
+    for (; row + 3 * rs.rpp < rs.row1; row += 4 * rs.rpp) {  // four independent 16-byte loads in flight per thread
+      float f[4][VEC];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) V<T>::load(base + static_cast<size_t>(row + u * rs.rpp) * C, f[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          acc[0][k] += f[u][k];
+          acc[1][k] = fmaf(f[u][k], f[u][k], acc[1][k]);
+        }
+    }
+    for (; row < rs.row1; row += rs.rpp) {
       float f[VEC];
       V<T>::load(base + static_cast<size_t>(row) * C, f);
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
-        s1[k] += f[k];
-        s2[k] = fmaf(f[k], f[k], s2[k]);
+        acc[0][k] += f[k];
+        acc[1][k] = fmaf(f[k], f[k], acc[1][k]);
       }
     }
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      atomicAdd(&sm[rs.v * VEC + k], s1[k]);
-      atomicAdd(&sm[C + rs.v * VEC + k], s2[k]);
-    }
   }
-  __syncthreads();
+  float* tot = sm + static_cast<size_t>(rs.rpp) * 2 * C;
+  cta_channel_sums<VEC, 2>(sm, rs, C, acc, tot);
   const int cpg = C / G;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     float a = 0.f, b = 0.f;
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      a += sm[c];
-      b += sm[C + c];
+      a += tot[c];
+      b += tot[C + c];
     }
     float* dst = ws + ((static_cast<size_t>(n) * gridDim.x + blockIdx.x) * G + g) * 2;
     dst[0] = a;
@@ -136,46 +179,76 @@ __global__ void gn_nhwc_stats_kernel(const T* __restrict__ x, float* __restrict_
   }
 }
 
-// sum of the per-CTA partials of (n, g): every thread that needs a group total walks the (few dozen) chunks
-__device__ __forceinline__ float2 group_total(const float* __restrict__ ws, int n, int g, int G, int chunks) {
-  float a = 0.f, b = 0.f;
-  const float* p = ws + (static_cast<size_t>(n) * chunks * G + g) * 2;
-  for (int c = 0; c < chunks; ++c, p += 2 * G) {
-    a += p[0];
-    b += p[1];
+// Sum one sample's per-CTA partials, ws_n[chunks][w] (w = 2G), into out[w] (shared memory): thread t owns column t % w and
+// every (blockDim / w)-th chunk — coalesced w-float rows, independent loads — and a shared-memory pass joins the slices.
+// scratch: blockDim floats. (One thread per group walking the chunks serially cost 427 dependent L2 loads on the 5-D input:
+// 104 us per CTA of the second sweep.)
+__device__ __forceinline__ void cta_reduce_partials(const float* __restrict__ ws_n, int w, int chunks, float* scratch, float* out) {
+  if (chunks == 1) {
+    for (int i = threadIdx.x; i < w; i += blockDim.x) out[i] = ws_n[i];
+    __syncthreads();
+    return;
   }
-  return make_float2(a, b);
+  const int slices = blockDim.x / w;
+  const int col = threadIdx.x % w, sl = threadIdx.x / w;
+  if (sl < slices) {
+    float acc = 0.f;
+#pragma unroll 4
+    for (int c = sl; c < chunks; c += slices) acc += ws_n[static_cast<size_t>(c) * w + col];
+    scratch[sl * w + col] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < w) {
+    float t = 0.f;
+    for (int i = 0; i < slices; ++i) t += scratch[i * w + threadIdx.x];
+    out[threadIdx.x] = t;
+  }
+  __syncthreads();
 }
 
+// Samples cut into many chunks (the 5-D temporal input: N = 2, 296 chunks each) get their partials summed ONCE by this
+// kernel (one CTA per sample) -> totals[n][G][2]; with <= kInlineChunks chunks the second sweep's prologue does it itself
+// and the launch disappears.
+constexpr int kInlineChunks = 32;
+__global__ void gn_nhwc_finalize_kernel(const float* __restrict__ ws, float* __restrict__ totals, int G, int chunks) {
+  extern __shared__ float sm[];  // [blockDim] scratch + [2G]
+  const int n = blockIdx.x, w = 2 * G;
+  float* out = sm + blockDim.x;
+  cta_reduce_partials(ws + static_cast<size_t>(n) * chunks * w, w, chunks, sm, out);
+  if (threadIdx.x < w) totals[static_cast<size_t>(n) * w + threadIdx.x] = out[threadIdx.x];
+}
+
+// parts: float[N][nparts][G][2] — the first sweep's per-CTA partials (nparts = its chunk count, summed here) or the
+// finalize kernel's totals (nparts = 1).
 template <typename T>
-__global__ void gn_nhwc_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ ws,
+__global__ void gn_nhwc_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ parts, int nparts,
                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                      const float* __restrict__ gamma, const float* __restrict__ beta, int C, int S, int G,
                                      float eps, int apply_silu, int rows_per_cta) {
   constexpr int VEC = V<T>::VEC;
-  extern __shared__ float sm[];  // a[C], d[C]
+  extern __shared__ float sm[];  // a[C], d[C], totals[2G], scratch[blockDim]
   const int n = blockIdx.y;
   const RowSplit rs = row_split<VEC>(C, S, rows_per_cta);
   const int cpg = C / G;
   const float inv = 1.f / (static_cast<float>(cpg) * S);
-  float* gs = sm + 2 * C;  // [G][2]: mean, rstd
+  float* gs = sm + 2 * C;  // [G][2]: sum, sum of squares -> mean, rstd
+  cta_reduce_partials(parts + static_cast<size_t>(n) * nparts * 2 * G, 2 * G, nparts, gs + 2 * G, gs);
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    const float2 t = group_total(ws, n, g, G, gridDim.x);
-    const float m = t.x * inv;
+    const float m = gs[2 * g] * inv;
+    const float r = rsqrtf(fmaxf(gs[2 * g + 1] * inv - m * m, 0.f) + eps);
     gs[2 * g] = m;
-    gs[2 * g + 1] = rsqrtf(fmaxf(t.y * inv - m * m, 0.f) + eps);
+    gs[2 * g + 1] = r;
+    if (blockIdx.x == 0) {
+      mean_out[n * G + g] = m;
+      rstd_out[n * G + g] = r;
+    }
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
-    const float m = gs[2 * g], r = gs[2 * g + 1];
-    const float a = r * (gamma ? gamma[c] : 1.f);
+    const float a = gs[2 * g + 1] * (gamma ? gamma[c] : 1.f);
     sm[c] = a;
-    sm[C + c] = fmaf(-m, a, beta ? beta[c] : 0.f);
-    if (blockIdx.x == 0 && c == g * cpg) {
-      mean_out[n * G + g] = m;
-      rstd_out[n * G + g] = r;
-    }
+    sm[C + c] = fmaf(-gs[2 * g], a, beta ? beta[c] : 0.f);
   }
   __syncthreads();
   if (!rs.active) return;
@@ -186,75 +259,95 @@ __global__ void gn_nhwc_apply_kernel(const T* __restrict__ x, T* __restrict__ y,
     d[k] = sm[C + rs.v * VEC + k];
   }
   const size_t off = (static_cast<size_t>(n) * S) * C + rs.v * VEC;
-  for (int row = rs.row0 + rs.r; row < rs.row1; row += rs.rpp) {
+  auto one = [&](const typename V<T>::Raw& raw, int row) {
     float f[VEC];
-    V<T>::load(x + off + static_cast<size_t>(row) * C, f);
+    V<T>::unpack(raw, f);
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       const float z = fmaf(f[k], a[k], d[k]);
       f[k] = apply_silu ? silu_fast(z) : z;
     }
     V<T>::store(y + off + static_cast<size_t>(row) * C, f);
+  };
+  int row = rs.row0 + rs.r;
+  for (; row + 3 * rs.rpp < rs.row1; row += 4 * rs.rpp) {  // four 16-byte loads in flight per thread
+    typename V<T>::Raw raw[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) raw[u] = V<T>::load_raw(x + off + static_cast<size_t>(row + u * rs.rpp) * C);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) one(raw[u], row + u * rs.rpp);
   }
+  for (; row < rs.row1; row += rs.rpp) one(V<T>::load_raw(x + off + static_cast<size_t>(row) * C), row);
 }
 
 // ---- backward --------------------------------------------------------------------------------------------------------
-// ws: float[N][chunks][G][2] per-CTA partial (sum gz*gamma, sum gz*gamma*xhat), plain stores; dgamma / dbeta accumulate
-// atomically (caller zeroes)
+// z = x*A + D with A = rstd*gamma, D = beta - mean*A;  gz = dy * silu'(z);  xhat = (x - mean) * rstd.
+// sums: per channel  s0 = sum gz,  s1 = sum gz*x  (raw x: two per-channel constants instead of four in registers; the
+//       centring  sum gz*xhat = rstd * (s1 - mean*s0)  happens once per channel in the epilogue)
+//       -> dbeta / dgamma atomics (caller zeroes) and per-CTA per-group gamma-weighted partials in ws (plain stores).
+// apply: dx = rstd * (gz*gamma - m1 - xhat*m2) = gz*A + x*c2 + c0,  c2 = -rstd^2*m2,  c0 = -rstd*m1 - mean*c2.
 template <typename T>
-__global__ void gn_nhwc_bwd_sums_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
+__global__ void __launch_bounds__(512, 2) gn_nhwc_bwd_sums_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
                                         const float* __restrict__ rstd, const float* __restrict__ gamma,
                                         const float* __restrict__ beta, float* __restrict__ ws, float* __restrict__ dgamma,
                                         float* __restrict__ dbeta, int C, int S, int G, int apply_silu, int rows_per_cta) {
   constexpr int VEC = V<T>::VEC;
-  extern __shared__ float sm[];  // [2][C]: sum gz, sum gz*xhat per channel
+  extern __shared__ float sm[];  // [rpp][2][C] partials, then [2][C]: sum gz, sum gz*x per channel
   const int n = blockIdx.y;
   const RowSplit rs = row_split<VEC>(C, S, rows_per_cta);
   const int cpg = C / G;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
+  float acc[2][VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) acc[0][k] = acc[1][k] = 0.f;
   if (rs.active) {
-    float ga[VEC], be[VEC], s1[VEC], s2[VEC], mu[VEC], rs_[VEC];
+    float A[VEC], D[VEC];
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       const int c = rs.v * VEC + k, g = c / cpg;
-      ga[k] = gamma ? gamma[c] : 1.f;
-      be[k] = beta ? beta[c] : 0.f;
-      mu[k] = mean[n * G + g];
-      rs_[k] = rstd[n * G + g];
-      s1[k] = s2[k] = 0.f;
+      A[k] = rstd[n * G + g] * (gamma ? gamma[c] : 1.f);
+      D[k] = fmaf(-mean[n * G + g], A[k], beta ? beta[c] : 0.f);
     }
     const size_t off = (static_cast<size_t>(n) * S) * C + rs.v * VEC;
-    for (int row = rs.row0 + rs.r; row < rs.row1; row += rs.rpp) {
+    auto one = [&](const typename V<T>::Raw& rx, const typename V<T>::Raw& rg) {
       float fx[VEC], fg[VEC];
-      V<T>::load(x + off + static_cast<size_t>(row) * C, fx);
-      V<T>::load(dy + off + static_cast<size_t>(row) * C, fg);
+      V<T>::unpack(rx, fx);
+      V<T>::unpack(rg, fg);
 #pragma unroll
       for (int k = 0; k < VEC; ++k) {
-        const float xh = (fx[k] - mu[k]) * rs_[k];
         float gz = fg[k];
-        if (apply_silu) gz *= dsilu_fast(fmaf(xh, ga[k], be[k]));
-        s1[k] += gz;
-        s2[k] = fmaf(gz, xh, s2[k]);
+        if (apply_silu) gz *= dsilu_fast(fmaf(fx[k], A[k], D[k]));
+        acc[0][k] += gz;
+        acc[1][k] = fmaf(gz, fx[k], acc[1][k]);
       }
+    };
+    int row = rs.row0 + rs.r;
+    for (; row + rs.rpp < rs.row1; row += 2 * rs.rpp) {  // two rows of x and dy in flight per thread (raw: 16 registers)
+      const size_t o0 = off + static_cast<size_t>(row) * C, o1 = o0 + static_cast<size_t>(rs.rpp) * C;
+      const typename V<T>::Raw x0 = V<T>::load_raw(x + o0), g0 = V<T>::load_raw(dy + o0);
+      const typename V<T>::Raw x1 = V<T>::load_raw(x + o1), g1 = V<T>::load_raw(dy + o1);
+      one(x0, g0);
+      one(x1, g1);
     }
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      atomicAdd(&sm[rs.v * VEC + k], s1[k]);
-      atomicAdd(&sm[C + rs.v * VEC + k], s2[k]);
+    if (row < rs.row1) {
+      const size_t o0 = off + static_cast<size_t>(row) * C;
+      one(V<T>::load_raw(x + o0), V<T>::load_raw(dy + o0));
     }
+  }
+  float* tot = sm + static_cast<size_t>(rs.rpp) * 2 * C;
+  cta_channel_sums<VEC, 2>(sm, rs, C, acc, tot);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {  // centre: sum gz*xhat = rstd * (sum gz*x - mean * sum gz)
+    const int g = c / cpg;
+    tot[C + c] = rstd[n * G + g] * fmaf(-mean[n * G + g], tot[c], tot[C + c]);
+    if (dbeta) atomicAdd(&dbeta[c], tot[c]);
+    if (dgamma) atomicAdd(&dgamma[c], tot[C + c]);
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    if (dbeta) atomicAdd(&dbeta[c], sm[c]);
-    if (dgamma) atomicAdd(&dgamma[c], sm[C + c]);
-  }
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     float a = 0.f, b = 0.f;
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
       const float gm = gamma ? gamma[c] : 1.f;
-      a = fmaf(sm[c], gm, a);
-      b = fmaf(sm[C + c], gm, b);
+      a = fmaf(tot[c], gm, a);
+      b = fmaf(tot[C + c], gm, b);
     }
     float* dst = ws + ((static_cast<size_t>(n) * gridDim.x + blockIdx.x) * G + g) * 2;
     dst[0] = a;
@@ -263,54 +356,58 @@ __global__ void gn_nhwc_bwd_sums_kernel(const T* __restrict__ dy, const T* __res
 }
 
 template <typename T>
-__global__ void gn_nhwc_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
+__global__ void __launch_bounds__(512, 2) gn_nhwc_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
                                          const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                         const float* __restrict__ beta, const float* __restrict__ ws, T* __restrict__ dx,
-                                         int C, int S, int G, int apply_silu, int rows_per_cta) {
+                                         const float* __restrict__ beta, const float* __restrict__ parts, int nparts,
+                                         T* __restrict__ dx, int C, int S, int G, int apply_silu, int rows_per_cta) {
   constexpr int VEC = V<T>::VEC;
-  extern __shared__ float sm[];  // [G][2]: group totals
+  extern __shared__ float sm[];  // totals[2G], scratch[blockDim]
   const int n = blockIdx.y;
   const RowSplit rs = row_split<VEC>(C, S, rows_per_cta);
   const int cpg = C / G;
   const float inv = 1.f / (static_cast<float>(cpg) * S);
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    const float2 t = group_total(ws, n, g, G, gridDim.x);
-    sm[2 * g] = t.x;
-    sm[2 * g + 1] = t.y;
-  }
-  __syncthreads();
+  cta_reduce_partials(parts + static_cast<size_t>(n) * nparts * 2 * G, 2 * G, nparts, sm + 2 * G, sm);
   if (!rs.active) return;
-  float ga[VEC], be[VEC], mu[VEC], rr[VEC], rg[VEC], c2[VEC], c0[VEC];
+  float A[VEC], D[VEC], c2[VEC], c0[VEC];
 #pragma unroll
   for (int k = 0; k < VEC; ++k) {
     const int c = rs.v * VEC + k, g = c / cpg;
-    ga[k] = gamma ? gamma[c] : 1.f;
-    be[k] = beta ? beta[c] : 0.f;
-    mu[k] = mean[n * G + g];
-    rr[k] = rstd[n * G + g];
+    const float mu = mean[n * G + g], rr = rstd[n * G + g];
     const float m1 = sm[2 * g] * inv, m2 = sm[2 * g + 1] * inv;
-    rg[k] = rr[k] * ga[k];
-    // dx = rstd * (gz*gamma - m1 - xhat*m2) = gz*rg - rstd*m1 - (x - mu)*rstd^2*m2
-    c2[k] = -rr[k] * rr[k] * m2;
-    c0[k] = -rr[k] * m1 - mu[k] * c2[k];
+    A[k] = rr * (gamma ? gamma[c] : 1.f);
+    D[k] = fmaf(-mu, A[k], beta ? beta[c] : 0.f);
+    c2[k] = -rr * rr * m2;
+    c0[k] = -rr * m1 - mu * c2[k];
   }
   const size_t off = (static_cast<size_t>(n) * S) * C + rs.v * VEC;
-  for (int row = rs.row0 + rs.r; row < rs.row1; row += rs.rpp) {
+  auto one = [&](const typename V<T>::Raw& rx, const typename V<T>::Raw& rg, size_t o) {
     float fx[VEC], fg[VEC];
-    V<T>::load(x + off + static_cast<size_t>(row) * C, fx);
-    V<T>::load(dy + off + static_cast<size_t>(row) * C, fg);
+    V<T>::unpack(rx, fx);
+    V<T>::unpack(rg, fg);
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       float gz = fg[k];
-      if (apply_silu) gz *= dsilu_fast(fmaf((fx[k] - mu[k]) * rr[k], ga[k], be[k]));
-      fx[k] = fmaf(gz, rg[k], fmaf(fx[k], c2[k], c0[k]));
+      if (apply_silu) gz *= dsilu_fast(fmaf(fx[k], A[k], D[k]));
+      fx[k] = fmaf(gz, A[k], fmaf(fx[k], c2[k], c0[k]));
     }
-    V<T>::store(dx + off + static_cast<size_t>(row) * C, fx);
+    V<T>::store(dx + o, fx);
+  };
+  int row = rs.row0 + rs.r;
+  for (; row + rs.rpp < rs.row1; row += 2 * rs.rpp) {
+    const size_t o0 = off + static_cast<size_t>(row) * C, o1 = o0 + static_cast<size_t>(rs.rpp) * C;
+    const typename V<T>::Raw x0 = V<T>::load_raw(x + o0), g0 = V<T>::load_raw(dy + o0);
+    const typename V<T>::Raw x1 = V<T>::load_raw(x + o1), g1 = V<T>::load_raw(dy + o1);
+    one(x0, g0, o0);
+    one(x1, g1, o1);
+  }
+  if (row < rs.row1) {
+    const size_t o0 = off + static_cast<size_t>(row) * C;
+    one(V<T>::load_raw(x + o0), V<T>::load_raw(dy + o0), o0);
   }
 }
 
 struct Plan {
-  int threads, rows_per_cta, chunks;
+  int threads, rows_per_cta, chunks, rpp;
 };
 template <int VEC>
 bool make_plan(int N, int C, int S, Plan* p) {
@@ -319,14 +416,32 @@ bool make_plan(int N, int C, int S, Plan* p) {
   if (vpr > 512) return false;
   p->threads = (512 / vpr) * vpr;
   const int rpp = p->threads / vpr;
-  // ~6 CTAs per SM over the whole grid, at least one pass of rows per CTA
-  int chunks = (148 * 6 + N - 1) / N;
+  p->rpp = rpp;
+  // CTAs per SM over the whole grid: 4 (2 for the few-sample 5-D inputs, whose partials need the finalize launch); at
+  // least eight passes of rows per CTA so the per-CTA prologue / reduction epilogue stays amortised on the small levels
+  // (measured: profiles/r2_s29_gncl.txt). VT_GNCL_CTAS=1..8 overrides.
+  static const int forced = [] {
+    const char* e = getenv("VT_GNCL_CTAS");
+    const int v = e != nullptr ? atoi(e) : 0;
+    return v < 0 ? 0 : (v > 8 ? 8 : v);
+  }();
+  const int per_sm = forced != 0 ? forced : (N < 8 ? 2 : 4);
+  int chunks = (148 * per_sm + N - 1) / N;
   int rows = (S + chunks - 1) / chunks;
   rows = ((rows + rpp - 1) / rpp) * rpp;
-  if (rows < 4 * rpp) rows = 4 * rpp;
+  if (rows < 8 * rpp) rows = 8 * rpp;
   p->rows_per_cta = rows;
   p->chunks = (S + rows - 1) / rows;
   return true;
+}
+
+// finalize launch: a multiple of 2G threads (whole slices), at most 1024
+int finalize_threads(int G) {
+  const int w = 2 * G;
+  int slices = 1024 / w;
+  if (slices > 8) slices = 8;
+  if (slices < 1) slices = 1;
+  return slices * w;
 }
 
 }  // namespace
@@ -338,7 +453,7 @@ extern "C" {
 
 // Workspace: per-CTA partial group sums, float[N][chunks][G][2]; the bound below covers every plan make_plan() can produce.
 int64_t vt_groupnorm_nhwc_workspace_bytes(int N, int G) {
-  return static_cast<int64_t>(N) * ((148 * 6 + N - 1) / N + 1) * G * 2 * sizeof(float);
+  return static_cast<int64_t>(N) * ((148 * 8 + N - 1) / N + 2) * G * 2 * sizeof(float);  // partials (<= 8 CTAs/SM) + totals
 }
 
 int vt_groupnorm_silu_nhwc_fwd(const void* x, void* y, float* mean, float* rstd, const float* gamma, const float* beta,
@@ -354,17 +469,30 @@ int vt_groupnorm_silu_nhwc_fwd(const void* x, void* y, float* mean, float* rstd,
   VT_REQUIRE(ok, VT_ERR_UNSUPPORTED, "channels-last GroupNorm needs C %% %d == 0 and C <= %d (C=%d)", dtype == 0 ? 8 : 4,
              dtype == 0 ? 4096 : 2048, C);
   dim3 grid(p.chunks, N);
-  const size_t smem = 2 * static_cast<size_t>(C) * sizeof(float);
-  const size_t smem_apply = smem + 2 * static_cast<size_t>(G) * sizeof(float);
+  const size_t smem = static_cast<size_t>(p.rpp + 1) * 2 * C * sizeof(float);  // row-group partials + totals
+  const size_t smem_apply = (2 * static_cast<size_t>(C) + 2 * static_cast<size_t>(G) + p.threads) * sizeof(float);
   float* ws = static_cast<float*>(workspace);
+  if (smem > 48 * 1024 && first_on_device(dtype == 0 ? reinterpret_cast<const void*>(gn_nhwc_stats_kernel<__nv_bfloat16>)
+                                                      : reinterpret_cast<const void*>(gn_nhwc_stats_kernel<float>))) {
+    VT_CHECK_CUDA(cudaFuncSetAttribute(gn_nhwc_stats_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VT_CHECK_CUDA(cudaFuncSetAttribute(gn_nhwc_stats_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  }
+  VT_REQUIRE(2 * G <= p.threads, VT_ERR_SHAPE, "G=%d too large", G);
+  const bool fin = p.chunks > kInlineChunks;  // many chunks per sample: sum the partials once, in their own launch
+  const float* parts = fin ? ws + static_cast<size_t>(N) * p.chunks * G * 2 : ws;
+  const int nparts = fin ? 1 : p.chunks;
+  const int fin_threads = finalize_threads(G);
+  const size_t fin_smem = static_cast<size_t>(fin_threads + 2 * G) * sizeof(float);
   if (dtype == 0) {
     gn_nhwc_stats_kernel<__nv_bfloat16><<<grid, p.threads, smem, st>>>(static_cast<const __nv_bfloat16*>(x), ws, C, S, G, p.rows_per_cta);
+    if (fin) gn_nhwc_finalize_kernel<<<N, fin_threads, fin_smem, st>>>(ws, const_cast<float*>(parts), G, p.chunks);
     gn_nhwc_apply_kernel<__nv_bfloat16><<<grid, p.threads, smem_apply, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y),
-                                                                      ws, mean, rstd, gamma, beta, C, S, G, eps, apply_silu, p.rows_per_cta);
+                                                                      parts, nparts, mean, rstd, gamma, beta, C, S, G, eps, apply_silu, p.rows_per_cta);
   } else {
     gn_nhwc_stats_kernel<float><<<grid, p.threads, smem, st>>>(static_cast<const float*>(x), ws, C, S, G, p.rows_per_cta);
-    gn_nhwc_apply_kernel<float><<<grid, p.threads, smem_apply, st>>>(static_cast<const float*>(x), static_cast<float*>(y), ws, mean, rstd,
-                                                              gamma, beta, C, S, G, eps, apply_silu, p.rows_per_cta);
+    if (fin) gn_nhwc_finalize_kernel<<<N, fin_threads, fin_smem, st>>>(ws, const_cast<float*>(parts), G, p.chunks);
+    gn_nhwc_apply_kernel<float><<<grid, p.threads, smem_apply, st>>>(static_cast<const float*>(x), static_cast<float*>(y), parts, nparts, mean,
+                                                              rstd, gamma, beta, C, S, G, eps, apply_silu, p.rows_per_cta);
   }
   VT_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -383,23 +511,36 @@ int vt_groupnorm_silu_nhwc_bwd(const void* dy, const void* x, const float* mean,
   VT_REQUIRE(ok, VT_ERR_UNSUPPORTED, "channels-last GroupNorm needs C %% %d == 0 and C <= %d (C=%d)", dtype == 0 ? 8 : 4,
              dtype == 0 ? 4096 : 2048, C);
   dim3 grid(p.chunks, N);
-  const size_t smem = 2 * static_cast<size_t>(C) * sizeof(float);
-  const size_t smem_g = 2 * static_cast<size_t>(G) * sizeof(float);
+  const size_t smem = static_cast<size_t>(p.rpp + 1) * 2 * C * sizeof(float);  // row-group partials + totals
+  const size_t smem_g = (2 * static_cast<size_t>(G) + p.threads) * sizeof(float);
   float* ws = static_cast<float*>(workspace);
+  if (smem > 48 * 1024 && first_on_device(dtype == 0 ? reinterpret_cast<const void*>(gn_nhwc_bwd_sums_kernel<__nv_bfloat16>)
+                                                      : reinterpret_cast<const void*>(gn_nhwc_bwd_sums_kernel<float>))) {
+    VT_CHECK_CUDA(cudaFuncSetAttribute(gn_nhwc_bwd_sums_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VT_CHECK_CUDA(cudaFuncSetAttribute(gn_nhwc_bwd_sums_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  }
+  VT_REQUIRE(2 * G <= p.threads, VT_ERR_SHAPE, "G=%d too large", G);
+  const bool fin = p.chunks > kInlineChunks;
+  const float* parts = fin ? ws + static_cast<size_t>(N) * p.chunks * G * 2 : ws;
+  const int nparts = fin ? 1 : p.chunks;
+  const int fin_threads = finalize_threads(G);
+  const size_t fin_smem = static_cast<size_t>(fin_threads + 2 * G) * sizeof(float);
   if (dtype == 0) {
     auto a = static_cast<const __nv_bfloat16*>(dy);
     auto b = static_cast<const __nv_bfloat16*>(x);
     gn_nhwc_bwd_sums_kernel<__nv_bfloat16><<<grid, p.threads, smem, st>>>(a, b, mean, rstd, gamma, beta, ws, dgamma, dbeta, C, S, G,
                                                                          apply_silu, p.rows_per_cta);
-    gn_nhwc_bwd_apply_kernel<__nv_bfloat16><<<grid, p.threads, smem_g, st>>>(a, b, mean, rstd, gamma, beta, ws, static_cast<__nv_bfloat16*>(dx),
-                                                                       C, S, G, apply_silu, p.rows_per_cta);
+    if (fin) gn_nhwc_finalize_kernel<<<N, fin_threads, fin_smem, st>>>(ws, const_cast<float*>(parts), G, p.chunks);
+    gn_nhwc_bwd_apply_kernel<__nv_bfloat16><<<grid, p.threads, smem_g, st>>>(a, b, mean, rstd, gamma, beta, parts, nparts,
+                                                                       static_cast<__nv_bfloat16*>(dx), C, S, G, apply_silu, p.rows_per_cta);
   } else {
     auto a = static_cast<const float*>(dy);
     auto b = static_cast<const float*>(x);
     gn_nhwc_bwd_sums_kernel<float><<<grid, p.threads, smem, st>>>(a, b, mean, rstd, gamma, beta, ws, dgamma, dbeta, C, S, G, apply_silu,
                                                                  p.rows_per_cta);
-    gn_nhwc_bwd_apply_kernel<float><<<grid, p.threads, smem_g, st>>>(a, b, mean, rstd, gamma, beta, ws, static_cast<float*>(dx), C, S, G,
-                                                               apply_silu, p.rows_per_cta);
+    if (fin) gn_nhwc_finalize_kernel<<<N, fin_threads, fin_smem, st>>>(ws, const_cast<float*>(parts), G, p.chunks);
+    gn_nhwc_bwd_apply_kernel<float><<<grid, p.threads, smem_g, st>>>(a, b, mean, rstd, gamma, beta, parts, nparts, static_cast<float*>(dx), C,
+                                                               S, G, apply_silu, p.rows_per_cta);
   }
   VT_CHECK_CUDA(cudaGetLastError());
   return 0;

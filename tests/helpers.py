@@ -398,3 +398,28 @@ class CogVideoXBlockShell(nn.Module):
 
 def load_shell(module, sd, device, dtype=torch.bfloat16):
     return _load(module, sd, device, dtype)
+
+
+class PeftLikeLinear(torch.nn.Module):
+    """The attributes and forward of peft.tuners.lora.Linear that matter here (peft is not installed in this image):
+    ModuleDict adapters keyed by name, per-adapter scaling / dropout, `base(x) + lora_B(lora_A(dropout(x))) * scaling`."""
+
+    def __init__(self, base, r=4, alpha=1.0, dropout=0.0, name="default"):
+        super().__init__()
+        self.base_layer = base
+        base.weight.requires_grad_(False)
+        if base.bias is not None:
+            base.bias.requires_grad_(False)
+        self.lora_A = torch.nn.ModuleDict({name: torch.nn.Linear(base.in_features, r, bias=False)})
+        self.lora_B = torch.nn.ModuleDict({name: torch.nn.Linear(r, base.out_features, bias=False)})
+        self.lora_dropout = torch.nn.ModuleDict({name: torch.nn.Dropout(dropout) if dropout > 0 else torch.nn.Identity()})
+        self.scaling = {name: alpha / r}
+        self.active_adapters = [name]
+        self.use_dora = {name: False}
+        self.merged = False
+        self.disable_adapters = False
+        torch.nn.init.normal_(self.lora_B[name].weight, std=0.05)
+
+    def forward(self, x):
+        n = self.active_adapters[0]
+        return self.base_layer(x) + self.lora_B[n](self.lora_A[n](self.lora_dropout[n](x))) * self.scaling[n]

@@ -126,3 +126,52 @@ def test_temporal_kernel_strided_views():
     out = Fn.temporal_attention(q, k, v)
     ref = R.sdpa_blhd(q.float().cpu(), k.float().cpu(), v.float().cpu())
     assert R.max_rel_err(out.float().cpu(), ref) < TOL
+
+
+@pytest.mark.parametrize("kind", ["self", "cross", "temporal"])
+def test_lora_adapters_on_the_projections_dense_gemm_path(kind, monkeypatch):
+    """peft-style LoRA on to_q / to_k / to_v (lvdm/ddpm3d.py:112-117, vc2_t2v_lora.yaml): the drop-in evaluates them as
+    base GEMM + dense-delta GEMM (functional.lora_merged_projections). Output, input gradient and the adapter gradients
+    must match the modules' own forward (B200VT_LORA_MERGE=0 route: same kernels, per-module projections) and the fp32 oracle."""
+    import b200vt.functional as Fn
+    from helpers import PeftLikeLinear
+    dev = torch.device("cuda")
+    torch.manual_seed(11)
+    dim, heads, d = 320, 5, 64
+    b, n = (8, 16) if kind == "temporal" else (2, 640)
+    m = CrossAttentionShell(dim, context_dim=None if kind != "cross" else 1024, heads=heads, dim_head=d)
+    m.to_q, m.to_k, m.to_v = PeftLikeLinear(m.to_q), PeftLikeLinear(m.to_k), PeftLikeLinear(m.to_v)
+    m = m.to(dev, torch.bfloat16)
+    x = torch.randn(b, n, dim, device=dev, dtype=torch.bfloat16)
+    ctx = torch.randn(b, 77, 1024, device=dev, dtype=torch.bfloat16) if kind == "cross" else None
+    gy = torch.randn(b, n, dim, device=dev, dtype=torch.bfloat16)
+
+    def run(merge):
+        monkeypatch.setattr(Fn, "_LORA_MERGE", merge)
+        xr = x.clone().requires_grad_(True)
+        m.zero_grad(set_to_none=True)
+        y = Fn.lvdm_cross_attention_forward(m, xr, context=ctx)
+        y.backward(gy)
+        return y, xr.grad, {k: p.grad.float().clone() for k, p in m.named_parameters() if p.grad is not None}
+
+    y1, dx1, g1 = run(True)
+    y0, dx0, g0 = run(False)
+    assert set(g1) == set(g0) and any("lora_A" in k for k in g1) and not any("base_layer" in k for k in g1)
+    assert R.max_rel_err(y1, y0) <= TOL and R.max_rel_err(dx1, dx0) <= TOL
+    for k in g0:
+        assert R.cosine(g1[k], g0[k]) >= 0.999, k
+    # fp32 oracle of the whole module (adapters included)
+    mf = CrossAttentionShell(dim, context_dim=None if kind != "cross" else 1024, heads=heads, dim_head=d)
+    mf.to_q, mf.to_k, mf.to_v = PeftLikeLinear(mf.to_q), PeftLikeLinear(mf.to_k), PeftLikeLinear(mf.to_v)
+    mf.load_state_dict({k: v.float() for k, v in m.state_dict().items()})
+    mf = mf.to(dev)
+    xf = x.float().requires_grad_(True)
+    cf = xf if ctx is None else ctx.float()
+    q, k, v = mf.to_q(xf), mf.to_k(cf), mf.to_v(cf)
+    o = R.sdpa_blhd(q.view(b, n, heads, d), k.view(b, -1, heads, d), v.view(b, -1, heads, d))
+    yf = mf.to_out(o.reshape(b, n, heads * d))
+    yf.backward(gy.float())
+    assert R.max_rel_err(y1, yf) <= TOL and R.cosine(dx1, xf.grad) >= 0.999
+    for k, p in mf.named_parameters():
+        if p.grad is not None and k in g1:
+            assert R.cosine(g1[k], p.grad) >= 0.999, k

@@ -217,3 +217,45 @@ def test_diffusers_cogvideox_blocks_are_bound_per_instance_with_fallback():
     hs, ehs, temb = torch.randn(1, 8, 128), torch.randn(1, 4, 128), torch.randn(1, 16)
     assert model[0](hs, ehs, temb)[0] == "stock"
     assert model[2](hs, ehs, temb=temb)[0] == "stock"
+
+
+# ---- LoRA projections as dense GEMMs (functional.lora_merged_projections) ------------------------------------------------
+def test_lora_projections_as_dense_gemms_match_the_adapter_forward():
+    import b200vt.functional as Fn
+    from helpers import PeftLikeLinear as _PeftLikeLinear
+    torch.manual_seed(3)
+    lin = lambda bias: _PeftLikeLinear(torch.nn.Linear(48, 32, bias=bias))  # noqa: E731
+    for bias in (False, True):
+        layers = [lin(bias) for _ in range(3)]
+        x = torch.randn(2, 7, 48, requires_grad=True)
+        want = [l(x) for l in layers]
+        gy = [torch.randn_like(w) for w in want]
+        torch.autograd.backward(want, gy)
+        ref = {"x": x.grad.clone(), **{f"{i}{n}": p.grad.clone() for i, l in enumerate(layers) for n, p in l.named_parameters() if p.grad is not None}}
+        x.grad = None
+        for l in layers:
+            l.zero_grad()
+        got = Fn.lora_merged_projections(x, layers)
+        assert got is not None and len(got) == 3
+        for g, w in zip(got, want):
+            torch.testing.assert_close(g, w, rtol=1e-5, atol=1e-5)
+        torch.autograd.backward(got, gy)
+        torch.testing.assert_close(x.grad, ref["x"], rtol=1e-4, atol=1e-5)
+        for i, l in enumerate(layers):
+            for n, p in l.named_parameters():
+                if f"{i}{n}" in ref:
+                    torch.testing.assert_close(p.grad, ref[f"{i}{n}"], rtol=1e-4, atol=1e-5)
+                else:
+                    assert p.grad is None  # frozen base weights stay without gradient
+    # not eligible: plain linears only (nothing to merge), dropout, merged / disabled adapters, trainable base
+    assert Fn.lora_merged_projections(x, [torch.nn.Linear(48, 32)]) is None
+    assert Fn.lora_merged_projections(x, [_PeftLikeLinear(torch.nn.Linear(48, 32), dropout=0.1)]) is None
+    m = lin(False)
+    m.merged = True
+    assert Fn.lora_merged_projections(x, [m]) is None
+    m = lin(False)
+    m.base_layer.weight.requires_grad_(True)
+    assert Fn.lora_merged_projections(x, [m]) is None
+    # a plain nn.Linear next to adapters is carried with a zero delta
+    mixed = Fn.lora_merged_projections(x, [lin(False), torch.nn.Linear(48, 32, bias=False).requires_grad_(False)])
+    assert mixed is not None and mixed[1].shape == (2, 7, 32)

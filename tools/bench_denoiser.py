@@ -314,6 +314,8 @@ def parse(argv=None):
     ap.add_argument("--optimizer", choices=("none", "adamw"), default="none",
                     help="adamw: one fused AdamW step on the trainable parameters (LoRA adapters for hunyuan, every block "
                     "weight for wan / cogvideox) inside the timed iteration, lr 1e-5 as the reference configs")
+    ap.add_argument("--no-grad-sync", action="store_true", help="diagnostic (N > 1): skip the all-reduce of the replicated "
+                    "parameters' gradients, to size its share of the sequence-parallel step")
     ap.add_argument("--tokens-scale", type=float, default=1.0, help="debug: shrink the latent frame count")
     ap.add_argument("--check", action="store_true", help="run one forward+backward of BOTH arms on the same weights and "
                     "print the relative difference of the outputs and input gradients, then exit")
@@ -474,8 +476,9 @@ def run(args, manage_dist: bool = True, emit: bool = True):
             # block b overlap the backward of blocks b-1, b-2, ... (per-block checkpointing produces them block by block)
             def _reduce_when_ready(prm):
                 pending.append(dist.all_reduce(prm.grad, async_op=True))
-            for p in params:
-                p.register_post_accumulate_grad_hook(_reduce_when_ready)
+            if not getattr(args, "no_grad_sync", False):
+                for p in params:
+                    p.register_post_accumulate_grad_hook(_reduce_when_ready)
 
     if args.check:
         (y_a, g_a), (y_b, g_b) = iteration(True), iteration(False)
@@ -553,6 +556,10 @@ def run(args, manage_dist: bool = True, emit: bool = True):
             "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1),
             "wall_s": round(t_wall, 2),
         }
+        if world > 1 and args.model == "wan":
+            nosync = getattr(args, "no_grad_sync", False)
+            line["grad_sync"] = ("skipped (--no-grad-sync diagnostic)" if nosync else
+                                 f"all-reduce of {sum(p.numel() * p.element_size() for p in params) / 1e9:.2f} GB of replicated-parameter gradients per iteration")
         if ours and not use_graph:
             line["attention_kernel_s_per_it"] = round(attn_ms / 1e3 / args.steps, 4)
             line["attention_share_of_step"] = round(attn_ms / 1e3 / args.steps / s_per_it, 4)

@@ -14,7 +14,7 @@ arm = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else 
 args = types.SimpleNamespace(arm=arm, steps=1, warmup=3, no_checkpoint="--no-checkpoint" in sys.argv, check=False,
                              nchw="--nchw" in sys.argv)
 VU.run(args, emit=False)  # builds, warms up
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes="--ops" in sys.argv) as prof:
     VU.run(types.SimpleNamespace(**{**vars(args), "warmup": 1, "steps": 2}), emit=False)
     torch.cuda.synchronize()
 from torch.autograd import DeviceType  # noqa: E402
@@ -37,3 +37,9 @@ for gname, pats in groups.items():
     print(f"  {ms:9.2f} ms  {gname}")
 for k, ms, n in rows[:60]:
     print(f"{ms:10.2f} ms {n:6d}  {k[:120]}")
+if "--ops" in sys.argv:  # which torch ops the remaining stock kernels come from (self device time, grouped by input shapes)
+    print("\n== torch ops by self device time (top 70, with input shapes)")
+    ka = prof.key_averages(group_by_input_shape=True)
+    ops = sorted((e for e in ka if e.key.startswith(("aten::", "b200vt")) or "Backward" in e.key), key=lambda e: -e.self_device_time_total)[:70]
+    for e in ops:
+        print(f"{e.self_device_time_total / 1e3:10.2f} ms {e.count:6d}  {e.key[:40]:40s} {str(e.input_shapes)[:110]}")

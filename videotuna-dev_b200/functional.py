@@ -8,6 +8,7 @@ our own.
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -21,6 +22,7 @@ class Unsupported(NotImplementedError):
 
 
 _HALF = (torch.bfloat16,)
+_LORA_MERGE = os.environ.get("B200VT_LORA_MERGE", "1") != "0"
 
 
 def _require(cond: bool, why: str):
@@ -206,6 +208,119 @@ def wan_flash_attention(q, k, v, q_lens=None, k_lens=None, dropout_p=0., softmax
 # ---------------------------------------------------------------------------------------------------------------------
 # lvdm: CrossAttention.forward  (videotuna/models/lvdm/modules/attention.py:101-170)
 # ---------------------------------------------------------------------------------------------------------------------
+def _lora_parts(layer):
+    """(weight, bias, [(A, B, scaling), ...]) of a projection when it can be evaluated as base GEMM + dense-delta GEMM
+    (lora_merged_projections), else None.
+
+    A plain nn.Linear has no adapters. A peft `lora.Linear` (what `peft.get_peft_model(self.model, LoraConfig(r=4, lora_alpha=1,
+    target_modules=["to_k", "to_v", "to_q"], lora_dropout=0.0))` makes of the projections, lvdm/ddpm3d.py:112-117, 436-440;
+    configs/001_videocrafter2/vc2_t2v_lora.yaml:7-12) qualifies when its forward is exactly
+    `base(x) + sum_a lora_B[a](lora_A[a](x)) * scaling[a]`: adapters enabled and not merged, dropout 0 (nn.Identity),
+    no DoRA, no adapter bias. Anything else returns None and the caller runs the module itself."""
+    if type(layer) is torch.nn.Linear:
+        return layer.weight, layer.bias, []
+    base = getattr(layer, "base_layer", None)
+    A, B = getattr(layer, "lora_A", None), getattr(layer, "lora_B", None)
+    if type(base) is not torch.nn.Linear or A is None or B is None:
+        return None
+    if getattr(layer, "merged", False) or getattr(layer, "disable_adapters", False):
+        return None
+    if isinstance(A, torch.nn.ModuleDict):
+        names = list(getattr(layer, "active_adapters", A.keys()))
+        if any(n not in A for n in names):
+            return None
+        drop, dora = getattr(layer, "lora_dropout", {}), getattr(layer, "use_dora", {})
+        parts = []
+        for n in names:
+            if n in drop and not isinstance(drop[n], torch.nn.Identity):
+                return None
+            if (dora.get(n, False) if isinstance(dora, dict) else dora) or getattr(B[n], "bias", None) is not None:
+                return None
+            parts.append((A[n].weight, B[n].weight, float(layer.scaling[n])))
+        return base.weight, base.bias, parts
+    if getattr(A, "bias", None) is not None or getattr(B, "bias", None) is not None:
+        return None
+    return base.weight, base.bias, [(A.weight, B.weight, float(layer.scaling))]
+
+
+class _LoRADeltaLinear(torch.autograd.Function):
+    """y = x W^T + x D^T (+ bias) with W frozen and D = sum_a s_a B_a A_a the DENSE adapter delta (out x in):
+    two GEMMs, the second accumulating into the first's output in its epilogue (beta = 1) — W and D are rounded to bf16
+    separately, like the reference rounds the base weight and the adapter factors separately, so a delta far below one
+    bf16 ulp of W still reaches the output. Backward: dx = dy W + dy D (same pair), dD = dy^T x (one GEMM, fp32 out)."""
+
+    @staticmethod
+    def forward(ctx, x, w, delta, bias):
+        x2 = x.reshape(-1, x.shape[-1])
+        y = torch.addmm(bias, x2, w.t()) if bias is not None else torch.mm(x2, w.t())
+        y.addmm_(x2, delta.t())
+        ctx.save_for_backward(x2, w, delta)
+        ctx.x_shape = x.shape
+        return y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, delta = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.mm(dy2, w)
+            dx.addmm_(dy2, delta)
+            dx = dx.view(ctx.x_shape)
+        try:
+            dd = torch.mm(dy2.t(), x2, out_dtype=torch.float32)
+        except (TypeError, RuntimeError):
+            dd = torch.mm(dy2.t(), x2)
+        return dx, None, dd.to(delta.dtype), None
+
+
+def lora_merged_projections(x: Tensor, layers) -> Optional[tuple]:
+    """Several LoRA projections of ONE input (to_q / to_k / to_v of self-attention; to_k / to_v of cross-attention) as dense
+    GEMMs:   [y_1 | y_2 | ...] = x [W_1; W_2; ...]^T + x [D_1; D_2; ...]^T,   D_i = s_i B_i A_i   (out x in: tiny next to the
+    activations). Same function and gradients as `base(x) + lora_B(lora_A(x)) * s` — dA = s B^T (dy^T x), dB = s (dy^T x) A^T
+    by autograd through D — but the rank-4 GEMMs over the 81 920-row activations (three per projection and direction,
+    memory-bound and run by cuBLAS at a few % of either roofline: 14 % of the VideoCrafter2 LoRA step,
+    profiles/r2_s31_vc2_profile_cl_nockpt.txt), their scale / add kernels and the three-way input-gradient sum are gone.
+    Returns the outputs as views of one (…, sum out) tensor, or None when a layer does not qualify (_lora_parts)."""
+    parts = [_lora_parts(l) for l in layers]
+    if any(p_ is None for p_ in parts) or not any(p_[2] for p_ in parts):
+        return None
+    if any((p_[1] is None) != (parts[0][1] is None) for p_ in parts):
+        return None
+    if any(p_[0].requires_grad or (p_[1] is not None and p_[1].requires_grad) for p_ in parts):
+        return None  # trainable base weights: the modules' own path
+    dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+    deltas = []
+    for w, _b, adapters in parts:
+        d = None
+        for a, b, s in adapters:
+            t = torch.mm(b.float(), a.float()) * s
+            d = t if d is None else d + t
+        deltas.append(d if d is not None else torch.zeros(w.shape, device=w.device, dtype=torch.float32))
+    sizes = [p_[0].shape[0] for p_ in parts]
+    many = len(parts) > 1
+    w = (torch.cat([p_[0] for p_ in parts], 0) if many else parts[0][0]).to(dt)
+    delta = (torch.cat(deltas, 0) if many else deltas[0]).to(dt)
+    bias = None if parts[0][1] is None else (torch.cat([p_[1] for p_ in parts], 0) if many else parts[0][1]).to(dt)
+    y = _LoRADeltaLinear.apply(x.to(dt), w, delta, bias)
+    return y.split(sizes, dim=-1) if many else (y,)
+
+
+def _lvdm_qkv(self, x, context, is_self_attn):
+    """to_q(x), to_k(context), to_v(context): merged-LoRA GEMMs where the projections are adapters (B200VT_LORA_MERGE=0: the
+    modules' own forwards), the modules themselves otherwise."""
+    if _LORA_MERGE:
+        if is_self_attn:
+            qkv = lora_merged_projections(x, (self.to_q, self.to_k, self.to_v))
+            if qkv is not None:
+                return qkv
+        else:
+            q, kv = lora_merged_projections(x, (self.to_q,)), lora_merged_projections(context, (self.to_k, self.to_v))
+            if q is not None and kv is not None:
+                return q[0], kv[0], kv[1]
+    return self.to_q(x), self.to_k(context), self.to_v(context)
+
+
 def lvdm_cross_attention_forward(self, x, context=None, mask=None):
     """Drop-in body for lvdm `CrossAttention.forward(self, x, context=None, mask=None)`.
 
@@ -216,17 +331,16 @@ def lvdm_cross_attention_forward(self, x, context=None, mask=None):
     """
     is_self_attn = context is None
     h = self.heads
-    q = self.to_q(x)
     context = x if context is None else context
     k_ip = v_ip = None
     if self.img_cross_attention and not is_self_attn:
         context, context_img = context[:, : self.text_context_len, :], context[:, self.text_context_len:, :]
-        k, v = self.to_k(context), self.to_v(context)
+        q, k, v = _lvdm_qkv(self, x, context, False)
         k_ip, v_ip = self.to_k_ip(context_img), self.to_v_ip(context_img)
     else:
         if not is_self_attn:
             context = context[:, : self.text_context_len, :]
-        k, v = self.to_k(context), self.to_v(context)
+        q, k, v = _lvdm_qkv(self, x, context, is_self_attn)
     _require(q.is_cuda and q.dtype == torch.bfloat16, "fp32 / CPU activations stay on the reference path")
     _require(self.dim_head in (64, 128), f"dim_head {self.dim_head} stays on the reference path")
     b, n, _ = q.shape

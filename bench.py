@@ -418,10 +418,11 @@ def denoiser_it_s(world: int):
         for key, arm, graph in (("ours", "ours", False), ("torch", "torch", False), ("ours_cuda_graph", "ours", True)):
             try:
                 r = VU.run(_t.SimpleNamespace(arm=arm, steps=5, warmup=3, no_checkpoint=False, check=False, nchw=False,
-                                              graph=graph), emit=False)
+                                              graph=graph, frozen_bf16=graph), emit=False)
                 rec[key] = {"s_per_it": r["s_per_it"], "it_per_s": r["it_per_s"], "peak_mem_GB": r["peak_mem_GB"],
                             "launch": r["config"]["launch"], "activation_checkpointing": r["config"]["activation_checkpointing"],
-                            "activation_layout": r["config"]["activation_layout"]}
+                            "activation_layout": r["config"]["activation_layout"],
+                            "frozen_weights": r["config"]["frozen_weights"]}
             except Exception as e:  # noqa: BLE001
                 rec[key] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
             import gc
@@ -435,7 +436,8 @@ def denoiser_it_s(world: int):
                             "backward, fused AdamW on rank-4 LoRA adapters; bf16 autocast. `ours` / `torch`: the reference's "
                             "configuration (eager launches, per-block activation checkpointing, use_checkpoint: true), `torch` = "
                             "the reference's op sequence on the same modules and weights; `ours_cuda_graph`: the whole step "
-                            "captured once into a CUDA graph, no checkpointing (fits easily in 180 GB)")
+                            "captured once into a CUDA graph, no checkpointing (fits easily in 180 GB), frozen Conv / Linear weights "
+                            "stored in bf16 once (bit-identical under autocast)")
         out["videocrafter2_320x512x16f_lora_b2"] = rec
     return out
 

@@ -186,14 +186,20 @@ int vt_groupnorm_silu_bwd(const void* dy, const void* x, const float* mean, cons
  * channels_last_3d views of (N, C, *spatial) tensors), the layout the tensor-core convolutions run in and in which lvdm's
  * `b c h w -> b (h w) c` (attention.py:381) is a free view. Same reference callables as vt_groupnorm_silu_fwd/bwd.
  * C % 8 == 0 (bf16; C <= 4096) or C % 4 == 0 (fp32; C <= 2048). workspace: vt_groupnorm_nhwc_workspace_bytes(N, G) bytes,
- * overwritten. dgamma / dbeta accumulate atomically (caller zeroes; nullable). */
+ * overwritten. dgamma / dbeta accumulate atomically (caller zeroes; nullable).
+ * addend (nullable): fp32 per-channel term added to x before the normalisation, GroupNorm(x + e): e[n * addend_stride + c]
+ * with addend_stride = C (per sample: ResBlock's `h + emb_out`, openaimodel3d.py:247-255, plus the preceding convolution's
+ * bias) or 0 (one vector for every sample: a convolution bias, TemporalConvBlock openaimodel3d.py:258-310). It is folded
+ * into the per-channel constants / the statistics' epilogue: the separate broadcast-add passes over the activation vanish.
+ * dx is the gradient of x (= that of x + e); the addend itself gets no gradient here. */
 int64_t vt_groupnorm_nhwc_workspace_bytes(int N, int G);
 int vt_groupnorm_silu_nhwc_fwd(const void* x, void* y, float* mean, float* rstd, const float* gamma, const float* beta,
-                               void* workspace, int N, int C, int S, int G, float eps, int apply_silu, int dtype,
-                               void* stream);
+                               const float* addend, int addend_stride, void* workspace, int N, int C, int S, int G,
+                               float eps, int apply_silu, int dtype, void* stream);
 int vt_groupnorm_silu_nhwc_bwd(const void* dy, const void* x, const float* mean, const float* rstd, void* dx,
-                               const float* gamma, const float* beta, float* dgamma, float* dbeta, void* workspace, int N,
-                               int C, int S, int G, int apply_silu, int dtype, void* stream);
+                               const float* gamma, const float* beta, const float* addend, int addend_stride,
+                               float* dgamma, float* dbeta, void* workspace, int N, int C, int S, int G, int apply_silu,
+                               int dtype, void* stream);
 
 /* Gated GELU of lvdm's feed-forward in one pass: y[m, f] = xin[m, f] * gelu(xin[m, F + f]) (exact erf GELU), xin (M, 2F),
  * y (M, F) bf16 contiguous, F % 8 == 0. Replaces GEGLU.forward after its Linear (lvdm/modules/attention.py:522-529).

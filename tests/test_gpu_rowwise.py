@@ -362,3 +362,45 @@ def test_geglu_matches_exact_gelu_reference(shape):
     ref.backward(dy.float())
     rel = lambda u, v: float((u.float() - v).abs().max() / v.abs().max())  # noqa: E731
     assert rel(y, ref) <= 1e-2 and rel(xin.grad, xr.grad) <= 1e-2
+
+
+@pytest.mark.parametrize("shape", [(4, 320, 12, 16), (3, 960, 5, 8), (2, 320, 16, 6, 8), (33, 64, 9, 7)])
+@pytest.mark.parametrize("per_sample", [True, False])
+@pytest.mark.parametrize("silu", [True, False])
+def test_groupnorm_channels_last_with_folded_addend(shape, per_sample, silu):
+    """GroupNorm(x + e[..., None, None]) with the per-channel term folded into the channels-last kernels (a convolution
+    bias, (C,), and / or ResBlock's timestep embedding, (N, C)) against torch's group_norm of the explicit sum in fp32:
+    output and input gradient; frozen affine parameters take the no-weight-gradient route of the backward."""
+    import torch.nn.functional as F
+    import b200vt.functional as Fn
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(77)
+    N, C = shape[0], shape[1]
+    fmt = torch.channels_last if len(shape) == 4 else torch.channels_last_3d
+    x = (torch.randn(*shape, device=dev, generator=g) * 1.5 + 0.3).to(torch.bfloat16)
+    e = torch.randn((N, C) if per_sample else (C,), device=dev, generator=g) * 0.7
+    gw, gb = 1 + 0.1 * torch.randn(C, device=dev, generator=g), 0.1 * torch.randn(C, device=dev, generator=g)
+    dy = torch.randn(*shape, device=dev, generator=g).to(torch.bfloat16)
+    x_cl = x.contiguous(memory_format=fmt).requires_grad_(True)
+    for frozen in (True, False):
+        x_cl.grad = None
+        wl, bl = gw.clone().requires_grad_(not frozen), gb.clone().requires_grad_(not frozen)
+        y = Fn.groupnorm_silu(x_cl, wl, bl, 32, 1e-5, silu=silu, addend=e)
+        assert y.is_contiguous(memory_format=fmt)
+        y.backward(dy.contiguous(memory_format=fmt))
+        xr = x.detach().float().clone().requires_grad_(True)
+        wr, br = gw.clone().requires_grad_(True), gb.clone().requires_grad_(True)
+        eb = e.view(*e.shape, *([1] * (len(shape) - 2))) if per_sample else e.view(1, C, *([1] * (len(shape) - 2)))
+        ref = F.group_norm(xr + eb, 32, wr, br, 1e-5)
+        ref = F.silu(ref) if silu else ref
+        ref.backward(dy.float())
+        rel = lambda a, b: float((a.float() - b.float()).abs().max() / b.float().abs().max())  # noqa: E731
+        assert rel(y, ref) <= 2e-2 and rel(x_cl.grad, xr.grad) <= 2e-2
+        if frozen:
+            assert wl.grad is None and bl.grad is None
+        else:
+            assert rel(wl.grad, wr.grad) <= 2e-2 and rel(bl.grad, br.grad) <= 2e-2
+    with pytest.raises(Exception):  # an addend that needs a gradient is refused, not silently dropped
+        Fn.groupnorm_silu(x_cl, gw, gb, 32, 1e-5, silu=silu, addend=e.clone().requires_grad_(True))
+    with pytest.raises(RuntimeError):  # NCHW activations: no addend
+        Fn.groupnorm_silu(x.contiguous(), gw, gb, 32, 1e-5, silu=silu, addend=e)

@@ -259,3 +259,16 @@ def test_lora_projections_as_dense_gemms_match_the_adapter_forward():
     # a plain nn.Linear next to adapters is carried with a zero delta
     mixed = Fn.lora_merged_projections(x, [lin(False), torch.nn.Linear(48, 32, bias=False).requires_grad_(False)])
     assert mixed is not None and mixed[1].shape == (2, 7, 32)
+
+
+def test_cast_frozen_weights_touches_only_frozen_conv_and_linear():
+    import b200vt.patch as P
+    net = torch.nn.Sequential(torch.nn.Conv2d(4, 8, 3), torch.nn.GroupNorm(2, 8), torch.nn.Linear(8, 8), torch.nn.Linear(8, 4))
+    for p in net.parameters():
+        p.requires_grad_(False)
+    net[3].weight.requires_grad_(True)  # a trainable tensor (e.g. an adapter) keeps fp32
+    want = net[0].weight.detach().clone().to(torch.bfloat16)
+    n = P.cast_frozen_weights(net)
+    assert n == 5  # conv w+b, linear w+b, last linear's bias
+    assert net[0].weight.dtype == torch.bfloat16 and torch.equal(net[0].weight, want)  # the rounding autocast applies
+    assert net[1].weight.dtype == torch.float32 and net[3].weight.dtype == torch.float32 and net[3].bias.dtype == torch.bfloat16

@@ -245,6 +245,10 @@ def run(args, emit=True):
     if args.arm == "ours" and not getattr(args, "nchw", False):
         import b200vt.patch as P
         P.lvdm_channels_last(net)  # channels-last activation flow of the drop-ins (the reference arm stays NCHW, as it is)
+    frozen_cast = 0
+    if args.arm == "ours" and getattr(args, "frozen_bf16", False):
+        import b200vt.patch as P
+        frozen_cast = P.cast_frozen_weights(net)  # bit-identical under autocast; no per-step weight casts
     params = [p for p in net.parameters() if p.requires_grad]
     g = torch.Generator(device=dev).manual_seed(20230211)
     B, T = 2, 16
@@ -327,7 +331,8 @@ def run(args, emit=True):
                        "unet_params": sum(p.numel() for p in net.parameters()), "trainable_params": sum(p.numel() for p in params),
                        "lora": "rank 4 on to_q/to_k/to_v", "activation_checkpointing": ckpt, "optimizer": "AdamW (fused)",
                        "launch": "one CUDA graph per step" if use_graph else "eager",
-                       "activation_layout": ("channels_last" if args.arm == "ours" and not getattr(args, "nchw", False) else "nchw")},
+                       "activation_layout": ("channels_last" if args.arm == "ours" and not getattr(args, "nchw", False) else "nchw"),
+                       "frozen_weights": "bf16 (cast once; %d tensors)" % frozen_cast if frozen_cast else "fp32, cast by autocast at every use"},
             "peak_mem_GB": round(torch.cuda.max_memory_allocated() / 1e9, 1)}
     if emit:
         print(json.dumps(line), flush=True)
@@ -342,6 +347,9 @@ def parse(argv=None):
     ap.add_argument("--no-checkpoint", action="store_true")
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--nchw", action="store_true", help="ours arm without the channels-last activation flow")
+    ap.add_argument("--frozen-bf16", action="store_true",
+                    help="ours arm: store the frozen Conv / Linear weights in bf16 once (patch.cast_frozen_weights; bit-identical "
+                    "under autocast)")
     ap.add_argument("--graph", action="store_true",
                     help="capture the whole step (forward, loss, backward, AdamW) into one CUDA graph and replay it (implies "
                     "--no-checkpoint)")

@@ -12,7 +12,7 @@ import bench_vc2_unet as VU  # noqa: E402
 
 arm = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("-") else "ours"
 args = types.SimpleNamespace(arm=arm, steps=1, warmup=3, no_checkpoint="--no-checkpoint" in sys.argv, check=False,
-                             nchw="--nchw" in sys.argv)
+                             nchw="--nchw" in sys.argv, frozen_bf16="--frozen-bf16" in sys.argv)
 VU.run(args, emit=False)  # builds, warms up
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes="--ops" in sys.argv) as prof:
     VU.run(types.SimpleNamespace(**{**vars(args), "warmup": 1, "steps": 2}), emit=False)

@@ -51,10 +51,10 @@ _SIGS = {
     "vt_geglu_fwd": [vp, vp, C.c_int64, C.c_int, vp],
     "vt_geglu_bwd": [vp, vp, vp, C.c_int64, C.c_int, vp],
     "vt_groupnorm_nhwc_workspace_bytes": [C.c_int, C.c_int],
-    "vt_groupnorm_silu_nhwc_fwd": [vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int,
-                                   C.c_int, vp],
-    "vt_groupnorm_silu_nhwc_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                   C.c_int, vp],
+    "vt_groupnorm_silu_nhwc_fwd": [vp, vp, vp, vp, vp, vp, vp, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                   C.c_int, C.c_int, vp],
+    "vt_groupnorm_silu_nhwc_bwd": [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   C.c_int, C.c_int, vp],
 }
 # Present only in -DVT_EXPERIMENTS builds of the library (tools/build_variant.sh + B200VT_LIB); see include/b200vt.h.
 _EXPERIMENT_SIGS = {

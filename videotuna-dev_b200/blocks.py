@@ -25,6 +25,7 @@ reference forward                                                          repla
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -348,10 +349,27 @@ def lvdm_basic_block_forward(self, x: Tensor, context: Optional[Tensor] = None, 
     return x
 
 
-def _lvdm_gn(norm: nn.GroupNorm, x: Tensor, silu: bool = False) -> Tensor:
+def _lvdm_gn(norm: nn.GroupNorm, x: Tensor, silu: bool = False, addend: Optional[Tensor] = None) -> Tensor:
     _require(x.is_cuda and x.dtype in (_BF16, torch.float32), "CUDA bf16/fp32 activations only")
     _require(norm.affine, "GroupNorm without affine parameters stays on the reference path")
-    return Fn.groupnorm_silu(x, norm.weight, norm.bias, norm.num_groups, norm.eps, silu=silu)
+    return Fn.groupnorm_silu(x, norm.weight, norm.bias, norm.num_groups, norm.eps, silu=silu, addend=addend)
+
+
+_FOLD_BIAS = os.environ.get("B200VT_GN_FOLD_BIAS", "1") != "0"
+
+
+def _conv_bias_deferred(conv: nn.Module, x: Tensor):
+    """conv(x) WITHOUT its bias and the bias to fold into the next GroupNorm (fp32 (C,)), or (conv(x), None) when the bias
+    cannot be deferred: not a plain Conv2d / Conv3d, no bias, a trainable bias (its gradient would be lost), an activation
+    that is not channels-last (the NCHW GroupNorm kernels take no addend), or B200VT_GN_FOLD_BIAS=0. PyTorch adds a cuDNN
+    convolution's bias in a separate broadcast kernel over the whole activation; deferring it removes that pass."""
+    if (_FOLD_BIAS and type(conv) in (nn.Conv2d, nn.Conv3d) and conv.bias is not None and not conv.bias.requires_grad
+            and _is_cl(x) and x.dtype == _BF16 and conv.out_channels % 8 == 0 and conv.out_channels <= 4096):
+        y = conv._conv_forward(x, conv.weight, None)
+        if _is_cl(y):
+            return y, conv.bias
+        return y + conv.bias.view(1, -1, *([1] * (y.dim() - 2))).to(y.dtype), None
+    return conv(x), None
 
 
 def _is_cl(x: Tensor) -> bool:
@@ -438,17 +456,23 @@ def lvdm_resblock_forward(self, x: Tensor, emb: Tensor, batch_size: Optional[int
     if self.updown:
         h = self.h_upd(h)
         x = self.x_upd(x)
-    h = in_conv(h)
-    emb_out = self.emb_layers(emb).type(h.dtype)
-    while len(emb_out.shape) < len(h.shape):
-        emb_out = emb_out[..., None]
+    emb_out = self.emb_layers(emb)
     out_norm, out_rest = self.out_layers[0], self.out_layers[2:]  # [norm, SiLU, Dropout, conv]
-    if self.use_scale_shift_norm:
-        scale, shift = torch.chunk(emb_out, 2, dim=1)
-        h = _lvdm_gn(out_norm, h) * (1 + scale) + shift
-        h = self.out_layers[1:](h)
+    fold = not self.use_scale_shift_norm and emb_out.dim() == 2 and not (emb_out.requires_grad and torch.is_grad_enabled())
+    h, bias = _conv_bias_deferred(in_conv, h) if fold else (in_conv(h), None)
+    if bias is not None:
+        # GroupNorm(conv(h) + bias + emb_out[..., None, None]) with both broadcast terms folded into the kernel's constants
+        h = out_rest(_lvdm_gn(out_norm, h, silu=True, addend=emb_out.float() + bias.float()))
     else:
-        h = out_rest(_lvdm_gn(out_norm, h + emb_out, silu=True))
+        emb_out = emb_out.type(h.dtype)
+        while len(emb_out.shape) < len(h.shape):
+            emb_out = emb_out[..., None]
+        if self.use_scale_shift_norm:
+            scale, shift = torch.chunk(emb_out, 2, dim=1)
+            h = _lvdm_gn(out_norm, h) * (1 + scale) + shift
+            h = self.out_layers[1:](h)
+        else:
+            h = out_rest(_lvdm_gn(out_norm, h + emb_out, silu=True))
     h = self.skip_connection(x) + h
     if self.use_temporal_conv and batch_size:
         bt, ch, hh, ww = h.shape
@@ -463,11 +487,18 @@ def lvdm_temporal_conv_block_forward(self, x: Tensor) -> Tensor:
     the VideoCrafter2 UNet): four stages of GroupNorm(32) -> SiLU -> [Dropout] -> Conv3d on (b, c, t, h, w) plus the
     identity. Each GroupNorm + SiLU pair is one pass of the 5-D cluster kernel; the (3,1,1) convolutions stay cuDNN."""
     _require(x.is_cuda and x.dtype in (_BF16, torch.float32) and x.dim() == 5, "CUDA bf16/fp32 (b, c, t, h, w) activations only")
-    h = x
-    for stage in (self.conv1, self.conv2, self.conv3, self.conv4):
+    h, bias = x, None
+    stages = (self.conv1, self.conv2, self.conv3, self.conv4)
+    for i, stage in enumerate(stages):
         norm, act = stage[0], stage[1]
         _require(isinstance(norm, nn.GroupNorm) and isinstance(act, nn.SiLU), "unexpected TemporalConvBlock layout")
-        h = stage[2:](_lvdm_gn(norm, h, silu=True))
+        h = _lvdm_gn(norm, h, silu=True, addend=bias)  # the previous convolution's bias rides in this GroupNorm
+        bias = None
+        if i + 1 < len(stages):
+            h = stage[2:-1](h)  # [Dropout]
+            h, bias = _conv_bias_deferred(stage[-1], h)
+        else:
+            h = stage[2:](h)
     return h + x
 
 

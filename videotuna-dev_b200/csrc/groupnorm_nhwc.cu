@@ -131,7 +131,8 @@ __device__ __forceinline__ void cta_channel_sums(float* sm, const RowSplit& rs, 
 }
 
 template <typename T>
-__global__ void gn_nhwc_stats_kernel(const T* __restrict__ x, float* __restrict__ ws, int C, int S, int G, int rows_per_cta) {
+__global__ void gn_nhwc_stats_kernel(const T* __restrict__ x, const float* __restrict__ addend, int addend_stride,
+                                     float* __restrict__ ws, int C, int S, int G, int rows_per_cta) {
   constexpr int VEC = V<T>::VEC;
   extern __shared__ float sm[];  // [rpp][2][C] partials, then [2][C] totals
   const int n = blockIdx.y;
@@ -167,6 +168,15 @@ __global__ void gn_nhwc_stats_kernel(const T* __restrict__ x, float* __restrict_
   float* tot = sm + static_cast<size_t>(rs.rpp) * 2 * C;
   cta_channel_sums<VEC, 2>(sm, rs, C, acc, tot);
   const int cpg = C / G;
+  if (addend != nullptr) {  // statistics of x + e[n][c]:  sum += rows*e,  sum of squares += 2 e sum + rows e^2
+    const float rows = static_cast<float>(max(rs.row1 - rs.row0, 0));
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float e = addend[static_cast<size_t>(n) * addend_stride + c];
+      tot[C + c] += e * fmaf(rows, e, 2.f * tot[c]);
+      tot[c] = fmaf(rows, e, tot[c]);
+    }
+    __syncthreads();
+  }
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     float a = 0.f, b = 0.f;
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
@@ -223,7 +233,8 @@ __global__ void gn_nhwc_finalize_kernel(const float* __restrict__ ws, float* __r
 template <typename T>
 __global__ void gn_nhwc_apply_kernel(const T* __restrict__ x, T* __restrict__ y, const float* __restrict__ parts, int nparts,
                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                     const float* __restrict__ gamma, const float* __restrict__ beta, int C, int S, int G,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     const float* __restrict__ addend, int addend_stride, int C, int S, int G,
                                      float eps, int apply_silu, int rows_per_cta) {
   constexpr int VEC = V<T>::VEC;
   extern __shared__ float sm[];  // a[C], d[C], totals[2G], scratch[blockDim]
@@ -247,8 +258,9 @@ __global__ void gn_nhwc_apply_kernel(const T* __restrict__ x, T* __restrict__ y,
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
     const float a = gs[2 * g + 1] * (gamma ? gamma[c] : 1.f);
+    const float e = addend ? addend[static_cast<size_t>(n) * addend_stride + c] : 0.f;
     sm[c] = a;
-    sm[C + c] = fmaf(-gs[2 * g], a, beta ? beta[c] : 0.f);
+    sm[C + c] = fmaf(e - gs[2 * g], a, beta ? beta[c] : 0.f);  // (x + e - mean) * a + beta
   }
   __syncthreads();
   if (!rs.active) return;
@@ -289,7 +301,8 @@ __global__ void gn_nhwc_apply_kernel(const T* __restrict__ x, T* __restrict__ y,
 template <typename T>
 __global__ void __launch_bounds__(512, 2) gn_nhwc_bwd_sums_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
                                         const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                        const float* __restrict__ beta, float* __restrict__ ws, float* __restrict__ dgamma,
+                                        const float* __restrict__ beta, const float* __restrict__ addend, int addend_stride,
+                                        float* __restrict__ ws, float* __restrict__ dgamma,
                                         float* __restrict__ dbeta, int C, int S, int G, int apply_silu, int rows_per_cta) {
   constexpr int VEC = V<T>::VEC;
   extern __shared__ float sm[];  // [rpp][2][C] partials, then [2][C]: sum gz, sum gz*x per channel
@@ -304,8 +317,9 @@ __global__ void __launch_bounds__(512, 2) gn_nhwc_bwd_sums_kernel(const T* __res
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       const int c = rs.v * VEC + k, g = c / cpg;
+      const float e = addend ? addend[static_cast<size_t>(n) * addend_stride + c] : 0.f;
       A[k] = rstd[n * G + g] * (gamma ? gamma[c] : 1.f);
-      D[k] = fmaf(-mean[n * G + g], A[k], beta ? beta[c] : 0.f);
+      D[k] = fmaf(e - mean[n * G + g], A[k], beta ? beta[c] : 0.f);
     }
     const size_t off = (static_cast<size_t>(n) * S) * C + rs.v * VEC;
     auto one = [&](const typename V<T>::Raw& rx, const typename V<T>::Raw& rg) {
@@ -337,7 +351,8 @@ __global__ void __launch_bounds__(512, 2) gn_nhwc_bwd_sums_kernel(const T* __res
   cta_channel_sums<VEC, 2>(sm, rs, C, acc, tot);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {  // centre: sum gz*xhat = rstd * (sum gz*x - mean * sum gz)
     const int g = c / cpg;
-    tot[C + c] = rstd[n * G + g] * fmaf(-mean[n * G + g], tot[c], tot[C + c]);
+    const float e = addend ? addend[static_cast<size_t>(n) * addend_stride + c] : 0.f;  // sum gz*(x + e) = sum gz*x + e sum gz
+    tot[C + c] = rstd[n * G + g] * fmaf(e - mean[n * G + g], tot[c], tot[C + c]);
     if (dbeta) atomicAdd(&dbeta[c], tot[c]);
     if (dgamma) atomicAdd(&dgamma[c], tot[C + c]);
   }
@@ -358,7 +373,8 @@ __global__ void __launch_bounds__(512, 2) gn_nhwc_bwd_sums_kernel(const T* __res
 template <typename T>
 __global__ void __launch_bounds__(512, 2) gn_nhwc_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean,
                                          const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                         const float* __restrict__ beta, const float* __restrict__ parts, int nparts,
+                                         const float* __restrict__ beta, const float* __restrict__ addend, int addend_stride,
+                                         const float* __restrict__ parts, int nparts,
                                          T* __restrict__ dx, int C, int S, int G, int apply_silu, int rows_per_cta) {
   constexpr int VEC = V<T>::VEC;
   extern __shared__ float sm[];  // totals[2G], scratch[blockDim]
@@ -374,10 +390,11 @@ __global__ void __launch_bounds__(512, 2) gn_nhwc_bwd_apply_kernel(const T* __re
     const int c = rs.v * VEC + k, g = c / cpg;
     const float mu = mean[n * G + g], rr = rstd[n * G + g];
     const float m1 = sm[2 * g] * inv, m2 = sm[2 * g + 1] * inv;
+    const float e = addend ? addend[static_cast<size_t>(n) * addend_stride + c] : 0.f;
     A[k] = rr * (gamma ? gamma[c] : 1.f);
-    D[k] = fmaf(-mu, A[k], beta ? beta[c] : 0.f);
+    D[k] = fmaf(e - mu, A[k], beta ? beta[c] : 0.f);
     c2[k] = -rr * rr * m2;
-    c0[k] = -rr * m1 - mu * c2[k];
+    c0[k] = -rr * m1 - (mu - e) * c2[k];  // (x + e - mu) * c2
   }
   const size_t off = (static_cast<size_t>(n) * S) * C + rs.v * VEC;
   auto one = [&](const typename V<T>::Raw& rx, const typename V<T>::Raw& rg, size_t o) {
@@ -457,7 +474,7 @@ int64_t vt_groupnorm_nhwc_workspace_bytes(int N, int G) {
 }
 
 int vt_groupnorm_silu_nhwc_fwd(const void* x, void* y, float* mean, float* rstd, const float* gamma, const float* beta,
-                               void* workspace, int N, int C, int S, int G, float eps, int apply_silu, int dtype,
+                               const float* addend, int addend_stride, void* workspace, int N, int C, int S, int G, float eps, int apply_silu, int dtype,
                                void* stream) {
   VT_REQUIRE(x && y && mean && rstd && workspace, VT_ERR_NULL, "vt_groupnorm_silu_nhwc_fwd: NULL argument");
   VT_REQUIRE(N > 0 && C > 0 && S > 0 && G > 0 && C % G == 0 && N <= 65535, VT_ERR_SHAPE, "bad shape N=%d C=%d S=%d G=%d", N, C, S, G);
@@ -484,22 +501,26 @@ int vt_groupnorm_silu_nhwc_fwd(const void* x, void* y, float* mean, float* rstd,
   const int fin_threads = finalize_threads(G);
   const size_t fin_smem = static_cast<size_t>(fin_threads + 2 * G) * sizeof(float);
   if (dtype == 0) {
-    gn_nhwc_stats_kernel<__nv_bfloat16><<<grid, p.threads, smem, st>>>(static_cast<const __nv_bfloat16*>(x), ws, C, S, G, p.rows_per_cta);
+    gn_nhwc_stats_kernel<__nv_bfloat16><<<grid, p.threads, smem, st>>>(static_cast<const __nv_bfloat16*>(x), addend, addend_stride, ws, C, S, G,
+                                                                      p.rows_per_cta);
     if (fin) gn_nhwc_finalize_kernel<<<N, fin_threads, fin_smem, st>>>(ws, const_cast<float*>(parts), G, p.chunks);
     gn_nhwc_apply_kernel<__nv_bfloat16><<<grid, p.threads, smem_apply, st>>>(static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y),
-                                                                      parts, nparts, mean, rstd, gamma, beta, C, S, G, eps, apply_silu, p.rows_per_cta);
+                                                                      parts, nparts, mean, rstd, gamma, beta, addend, addend_stride, C, S, G, eps,
+                                                                      apply_silu, p.rows_per_cta);
   } else {
-    gn_nhwc_stats_kernel<float><<<grid, p.threads, smem, st>>>(static_cast<const float*>(x), ws, C, S, G, p.rows_per_cta);
+    gn_nhwc_stats_kernel<float><<<grid, p.threads, smem, st>>>(static_cast<const float*>(x), addend, addend_stride, ws, C, S, G, p.rows_per_cta);
     if (fin) gn_nhwc_finalize_kernel<<<N, fin_threads, fin_smem, st>>>(ws, const_cast<float*>(parts), G, p.chunks);
     gn_nhwc_apply_kernel<float><<<grid, p.threads, smem_apply, st>>>(static_cast<const float*>(x), static_cast<float*>(y), parts, nparts, mean,
-                                                              rstd, gamma, beta, C, S, G, eps, apply_silu, p.rows_per_cta);
+                                                              rstd, gamma, beta, addend, addend_stride, C, S, G, eps, apply_silu,
+                                                              p.rows_per_cta);
   }
   VT_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 int vt_groupnorm_silu_nhwc_bwd(const void* dy, const void* x, const float* mean, const float* rstd, void* dx,
-                               const float* gamma, const float* beta, float* dgamma, float* dbeta, void* workspace, int N,
+                               const float* gamma, const float* beta, const float* addend, int addend_stride, float* dgamma,
+                               float* dbeta, void* workspace, int N,
                                int C, int S, int G, int apply_silu, int dtype, void* stream) {
   VT_REQUIRE(dy && x && mean && rstd && dx && workspace, VT_ERR_NULL, "vt_groupnorm_silu_nhwc_bwd: NULL argument");
   VT_REQUIRE(N > 0 && C > 0 && S > 0 && G > 0 && C % G == 0 && N <= 65535, VT_ERR_SHAPE, "bad shape N=%d C=%d S=%d G=%d", N, C, S, G);
@@ -528,19 +549,20 @@ int vt_groupnorm_silu_nhwc_bwd(const void* dy, const void* x, const float* mean,
   if (dtype == 0) {
     auto a = static_cast<const __nv_bfloat16*>(dy);
     auto b = static_cast<const __nv_bfloat16*>(x);
-    gn_nhwc_bwd_sums_kernel<__nv_bfloat16><<<grid, p.threads, smem, st>>>(a, b, mean, rstd, gamma, beta, ws, dgamma, dbeta, C, S, G,
-                                                                         apply_silu, p.rows_per_cta);
+    gn_nhwc_bwd_sums_kernel<__nv_bfloat16><<<grid, p.threads, smem, st>>>(a, b, mean, rstd, gamma, beta, addend, addend_stride, ws, dgamma,
+                                                                         dbeta, C, S, G, apply_silu, p.rows_per_cta);
     if (fin) gn_nhwc_finalize_kernel<<<N, fin_threads, fin_smem, st>>>(ws, const_cast<float*>(parts), G, p.chunks);
-    gn_nhwc_bwd_apply_kernel<__nv_bfloat16><<<grid, p.threads, smem_g, st>>>(a, b, mean, rstd, gamma, beta, parts, nparts,
-                                                                       static_cast<__nv_bfloat16*>(dx), C, S, G, apply_silu, p.rows_per_cta);
+    gn_nhwc_bwd_apply_kernel<__nv_bfloat16><<<grid, p.threads, smem_g, st>>>(a, b, mean, rstd, gamma, beta, addend, addend_stride, parts,
+                                                                       nparts, static_cast<__nv_bfloat16*>(dx), C, S, G, apply_silu,
+                                                                       p.rows_per_cta);
   } else {
     auto a = static_cast<const float*>(dy);
     auto b = static_cast<const float*>(x);
-    gn_nhwc_bwd_sums_kernel<float><<<grid, p.threads, smem, st>>>(a, b, mean, rstd, gamma, beta, ws, dgamma, dbeta, C, S, G, apply_silu,
-                                                                 p.rows_per_cta);
+    gn_nhwc_bwd_sums_kernel<float><<<grid, p.threads, smem, st>>>(a, b, mean, rstd, gamma, beta, addend, addend_stride, ws, dgamma, dbeta, C,
+                                                                 S, G, apply_silu, p.rows_per_cta);
     if (fin) gn_nhwc_finalize_kernel<<<N, fin_threads, fin_smem, st>>>(ws, const_cast<float*>(parts), G, p.chunks);
-    gn_nhwc_bwd_apply_kernel<float><<<grid, p.threads, smem_g, st>>>(a, b, mean, rstd, gamma, beta, parts, nparts, static_cast<float*>(dx), C,
-                                                               S, G, apply_silu, p.rows_per_cta);
+    gn_nhwc_bwd_apply_kernel<float><<<grid, p.threads, smem_g, st>>>(a, b, mean, rstd, gamma, beta, addend, addend_stride, parts, nparts,
+                                                               static_cast<float*>(dx), C, S, G, apply_silu, p.rows_per_cta);
   }
   VT_CHECK_CUDA(cudaGetLastError());
   return 0;

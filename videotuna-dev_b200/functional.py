@@ -289,6 +289,10 @@ def lora_merged_projections(x: Tensor, layers) -> Optional[tuple]:
         return None
     if any(p_[0].requires_grad or (p_[1] is not None and p_[1].requires_grad) for p_ in parts):
         return None  # trainable base weights: the modules' own path
+    if any(p_[0].shape[0] * p_[0].shape[1] > 1024 * (p_[0].shape[0] + p_[0].shape[1]) for p_ in parts):
+        # The dense delta costs 2 * rows * in * out extra FLOPs per GEMM where the rank-r path moves ~rows * (in + out)
+        # elements: a win for lvdm's 320..1280-wide projections, a loss for e.g. HunyuanVideo's 3072 -> 9216 qkv.
+        return None
     dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
     deltas = []
     for w, _b, adapters in parts:
@@ -505,8 +509,15 @@ def hunyuan_joint_qkv(img_qkv: Tensor, txt_qkv: Tensor, img_q_norm, img_k_norm, 
 
 
 def groupnorm_silu(x: Tensor, weight: Optional[Tensor], bias: Optional[Tensor], groups: int, eps: float,
-                   silu: bool = False) -> Tensor:
-    """GroupNorm with fp32 statistics (+ SiLU) on (N,C,*) bf16/fp32 tensors (lvdm GroupNormSpecific, utils.py:192-203)."""
+                   silu: bool = False, addend: Optional[Tensor] = None) -> Tensor:
+    """GroupNorm with fp32 statistics (+ SiLU) on (N,C,*) bf16/fp32 tensors (lvdm GroupNormSpecific, utils.py:192-203).
+    addend: optional fp32 (C,) or (N, C) term, y = GroupNorm(x + addend[..., None, None]) — a convolution bias and / or
+    ResBlock's timestep embedding folded into the kernel's per-channel constants (channels-last x only; no gradient flows
+    to it: pass it only when it needs none)."""
     _require(x.is_cuda and x.dtype in (torch.bfloat16, torch.float32), "groupnorm needs a CUDA bf16/fp32 tensor")
-    y, _, _ = ops.groupnorm_silu_fwd(x, weight, bias, int(groups), float(eps), bool(silu))
+    if addend is not None:
+        _require(not (addend.requires_grad and torch.is_grad_enabled()), "a GroupNorm addend that needs a gradient is added by the caller")
+        y, _, _ = ops.groupnorm_silu_fwd(x, weight, bias, int(groups), float(eps), bool(silu), addend.detach().float())
+        return y
+    y, _, _ = ops.groupnorm_silu_fwd(x, weight, bias, int(groups), float(eps), bool(silu), None)
     return y

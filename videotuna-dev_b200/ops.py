@@ -688,16 +688,36 @@ def _to_channels_last(t: Tensor) -> Tensor:
     return t if _channels_last(t) else t.movedim(1, -1).contiguous().movedim(-1, 1)
 
 
+def _gn_nhwc(x: Tensor) -> bool:
+    Cc = x.shape[1]
+    return _channels_last(x) and Cc % (8 if x.dtype == torch.bfloat16 else 4) == 0 and Cc <= (4096 if x.dtype == torch.bfloat16 else 2048)
+
+
+def _gn_addend(addend: Optional[Tensor], N: int, Cc: int, nhwc: bool) -> Tuple[Optional[Tensor], int]:
+    """fp32 (C,) or (N, C) term added to x ahead of the normalisation -> (tensor, per-sample stride); channels-last only."""
+    if addend is None:
+        return None, 0
+    if not nhwc:
+        raise RuntimeError("b200vt: GroupNorm with an addend runs on channels-last activations only")
+    if addend.dim() == 1 and addend.shape[0] == Cc:
+        return _f32(addend), 0
+    if addend.dim() == 2 and tuple(addend.shape) == (N, Cc):
+        return _f32(addend), Cc
+    raise RuntimeError(f"b200vt: GroupNorm addend must be (C,) or (N, C) = ({N}, {Cc}), got {tuple(addend.shape)}")
+
+
 @torch.library.custom_op("b200vt::groupnorm_silu_fwd", mutates_args=(), device_types="cuda")
 def groupnorm_silu_fwd(x: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor], groups: int, eps: float,
-                       silu: bool) -> Tuple[Tensor, Tensor, Tensor]:
+                       silu: bool, addend: Optional[Tensor] = None) -> Tuple[Tensor, Tensor, Tensor]:
     """x (N, C, *spatial) bf16/fp32 -> y, mean (N,G), rstd (N,G); statistics in fp32. A channels-last x (torch.channels_last
-    / channels_last_3d) runs the channels-last kernels and y keeps that layout; anything else is made NCHW-contiguous."""
+    / channels_last_3d) runs the channels-last kernels and y keeps that layout; anything else is made NCHW-contiguous.
+    addend (channels-last only): fp32 (C,) or (N, C), y = GroupNorm(x + addend[..., None, None]) without the add pass."""
     if not x.is_cuda:
         raise RuntimeError("b200vt: groupnorm input must be a CUDA tensor (there is no CPU path)")
     N, Cc = x.shape[0], x.shape[1]
     S = x.numel() // (N * Cc)
-    nhwc = _channels_last(x) and Cc % (8 if x.dtype == torch.bfloat16 else 4) == 0 and Cc <= (4096 if x.dtype == torch.bfloat16 else 2048)
+    nhwc = _gn_nhwc(x)
+    e, e_stride = _gn_addend(addend, N, Cc, nhwc)
     if not nhwc:
         x = x.contiguous()
     y = torch.empty_like(x)  # preserves x's (dense) layout
@@ -707,8 +727,8 @@ def groupnorm_silu_fwd(x: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor
     with torch.cuda.device(x.device):
         if nhwc:
             ws = torch.empty((_lib.lib().vt_groupnorm_nhwc_workspace_bytes(N, groups),), dtype=torch.uint8, device=x.device)
-            _lib.call("vt_groupnorm_silu_nhwc_fwd", _ptr(x), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(g), _ptr(b), _ptr(ws), N, Cc,
-                      S, groups, float(eps), int(silu), _gn_dtype(x), _stream())
+            _lib.call("vt_groupnorm_silu_nhwc_fwd", _ptr(x), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(g), _ptr(b), _ptr(e), e_stride,
+                      _ptr(ws), N, Cc, S, groups, float(eps), int(silu), _gn_dtype(x), _stream())
         else:
             _lib.call("vt_groupnorm_silu_fwd", _ptr(x), _ptr(y), _ptr(mean), _ptr(rstd), _ptr(g), _ptr(b), N, Cc, S, groups,
                       float(eps), int(silu), _gn_dtype(x), _stream())
@@ -716,7 +736,7 @@ def groupnorm_silu_fwd(x: Tensor, gamma: Optional[Tensor], beta: Optional[Tensor
 
 
 @groupnorm_silu_fwd.register_fake
-def _(x, gamma, beta, groups, eps, silu):
+def _(x, gamma, beta, groups, eps, silu, addend=None):
     N = x.shape[0]
     y = torch.empty_like(x) if _channels_last(x) else torch.empty_like(x, memory_format=torch.contiguous_format)
     return y, x.new_empty((N, groups), dtype=torch.float32), x.new_empty((N, groups), dtype=torch.float32)
@@ -724,49 +744,61 @@ def _(x, gamma, beta, groups, eps, silu):
 
 @torch.library.custom_op("b200vt::groupnorm_silu_bwd", mutates_args=(), device_types="cuda")
 def groupnorm_silu_bwd(dy: Tensor, x: Tensor, mean: Tensor, rstd: Tensor, gamma: Optional[Tensor],
-                       beta: Optional[Tensor], groups: int, silu: bool) -> Tuple[Tensor, Tensor, Tensor]:
+                       beta: Optional[Tensor], groups: int, silu: bool, addend: Optional[Tensor] = None,
+                       need_wgrad: bool = True) -> Tuple[Tensor, Tensor, Tensor]:
+    """-> dx, dgamma, dbeta (fp32). need_wgrad=False (frozen affine parameters: LoRA finetuning) skips the per-channel
+    atomics and the two zero fills; dgamma / dbeta are then empty (0,) tensors."""
     N, Cc = x.shape[0], x.shape[1]
     S = x.numel() // (N * Cc)
-    nhwc = _channels_last(x) and Cc % (8 if x.dtype == torch.bfloat16 else 4) == 0 and Cc <= (4096 if x.dtype == torch.bfloat16 else 2048)
+    nhwc = _gn_nhwc(x)
+    e, e_stride = _gn_addend(addend, N, Cc, nhwc)
     dy = dy.to(x.dtype)
     if nhwc:
         dy = _to_channels_last(dy)
     else:
         dy, x = dy.contiguous(), x.contiguous()
     dx = torch.empty_like(x)
-    dgamma = torch.zeros((Cc,), dtype=torch.float32, device=x.device)
-    dbeta = torch.zeros_like(dgamma)
+    if need_wgrad:
+        dgamma = torch.zeros((Cc,), dtype=torch.float32, device=x.device)
+        dbeta = torch.zeros_like(dgamma)
+    else:
+        dgamma = torch.empty((0,), dtype=torch.float32, device=x.device)
+        dbeta = torch.empty((0,), dtype=torch.float32, device=x.device)
+    pg, pb = (_ptr(dgamma), _ptr(dbeta)) if need_wgrad else (None, None)
     g, b = _f32(gamma), _f32(beta)
     with torch.cuda.device(x.device):
         if nhwc:
             ws = torch.empty((_lib.lib().vt_groupnorm_nhwc_workspace_bytes(N, groups),), dtype=torch.uint8, device=x.device)
             _lib.call("vt_groupnorm_silu_nhwc_bwd", _ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(g), _ptr(b),
-                      _ptr(dgamma), _ptr(dbeta), _ptr(ws), N, Cc, S, groups, int(silu), _gn_dtype(x), _stream())
+                      _ptr(e), e_stride, pg, pb, _ptr(ws), N, Cc, S, groups, int(silu), _gn_dtype(x), _stream())
         else:
             _lib.call("vt_groupnorm_silu_bwd", _ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(dx), _ptr(g),
-                      _ptr(b), _ptr(dgamma), _ptr(dbeta), N, Cc, S, groups, int(silu), _gn_dtype(x), _stream())
+                      _ptr(b), pg, pb, N, Cc, S, groups, int(silu), _gn_dtype(x), _stream())
     return dx, dgamma, dbeta
 
 
 @groupnorm_silu_bwd.register_fake
-def _(dy, x, mean, rstd, gamma, beta, groups, silu):
-    Cc = x.shape[1]
+def _(dy, x, mean, rstd, gamma, beta, groups, silu, addend=None, need_wgrad=True):
+    Cc = x.shape[1] if need_wgrad else 0
     dx = torch.empty_like(x) if _channels_last(x) else torch.empty_like(x, memory_format=torch.contiguous_format)
     return dx, x.new_empty((Cc,), dtype=torch.float32), x.new_empty((Cc,), dtype=torch.float32)
 
 
 def _gn_setup(ctx, inputs, output):
-    x, gamma, beta, groups, eps, silu = inputs
+    x, gamma, beta, groups, eps, silu, addend = inputs
     y, mean, rstd = output
-    ctx.save_for_backward(x, mean, rstd, gamma, beta)
+    ctx.save_for_backward(x, mean, rstd, gamma, beta, addend)
     ctx.groups, ctx.silu = groups, silu
 
 
 def _gn_backward(ctx, dy, dmean, drstd):
-    x, mean, rstd, gamma, beta = ctx.saved_tensors
-    dx, dgamma, dbeta = groupnorm_silu_bwd(dy, x, mean, rstd, gamma, beta, ctx.groups, ctx.silu)
+    x, mean, rstd, gamma, beta, addend = ctx.saved_tensors
+    if addend is not None and ctx.needs_input_grad[6]:
+        raise RuntimeError("b200vt: the GroupNorm addend carries no gradient (pass it detached, or add it to x yourself)")
+    wg = (gamma is not None and ctx.needs_input_grad[1]) or (beta is not None and ctx.needs_input_grad[2])
+    dx, dgamma, dbeta = groupnorm_silu_bwd(dy, x, mean, rstd, gamma, beta, ctx.groups, ctx.silu, addend, wg)
     return (dx, dgamma.to(gamma.dtype) if gamma is not None and ctx.needs_input_grad[1] else None,
-            dbeta.to(beta.dtype) if beta is not None and ctx.needs_input_grad[2] else None, None, None, None)
+            dbeta.to(beta.dtype) if beta is not None and ctx.needs_input_grad[2] else None, None, None, None, None)
 
 
 groupnorm_silu_fwd.register_autograd(_gn_backward, setup_context=_gn_setup)

@@ -480,6 +480,7 @@ def sp_parity_check(torch, dist, dev, world, S_loc, leaves, do, step_device, nh:
     n_img = L - TXT_TOKENS
 
     def rel(a, b):
+        a, b = a.detach(), b.detach()
         return float((a.float() - b.float()).abs().max() / b.float().abs().max().clamp_min(1e-30))
 
     errs = {"out_img": rel(out[:, :S_loc, :nh], o_ref[:, :S_loc]), "out_txt": rel(out[:, S_loc:, :nh], o_ref[:, n_img:]),

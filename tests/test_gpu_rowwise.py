@@ -404,3 +404,38 @@ def test_groupnorm_channels_last_with_folded_addend(shape, per_sample, silu):
         Fn.groupnorm_silu(x_cl, gw, gb, 32, 1e-5, silu=silu, addend=e.clone().requires_grad_(True))
     with pytest.raises(RuntimeError):  # NCHW activations: no addend
         Fn.groupnorm_silu(x.contiguous(), gw, gb, 32, 1e-5, silu=silu, addend=e)
+
+
+def test_registered_op_route_groupnorm_and_geglu():
+    """The GroupNorm ops (defaulted `addend` / `need_wgrad` arguments, channels-last and NCHW, trainable and frozen affine
+    parameters) and the gated GELU through torch.library's registered ops (what a multi-rank launch uses) against the eager
+    fast path."""
+    import b200vt.ops as ops
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(19)
+    x = torch.randn(3, 64, 6, 10, device=dev, generator=g).bfloat16()
+    dy = torch.randn(3, 64, 6, 10, device=dev, generator=g).bfloat16()
+    e = torch.randn(3, 64, device=dev, generator=g)
+    gw, gb = 1 + 0.1 * torch.randn(64, device=dev, generator=g), 0.1 * torch.randn(64, device=dev, generator=g)
+    for cl, addend, frozen in ((False, None, False), (True, None, False), (True, e, False), (True, e, True)):
+        outs = {}
+        for reg in (True, False):
+            f = ops.groupnorm_silu_fwd.op if reg else ops.groupnorm_silu_fwd
+            xx = (x.contiguous(memory_format=torch.channels_last) if cl else x.clone()).requires_grad_(True)
+            w, b = gw.clone().requires_grad_(not frozen), gb.clone().requires_grad_(not frozen)
+            args = (xx, w, b, 32, 1e-5, True) + ((addend,) if (addend is not None or not reg) else ())
+            y = f(*args)[0]
+            gs = torch.autograd.grad(y, [xx] if frozen else [xx, w, b], dy.contiguous(memory_format=torch.channels_last) if cl else dy)
+            outs[reg] = [y.detach(), *gs]
+        for u, v in zip(outs[True], outs[False]):
+            assert float((u.float() - v.float()).abs().max()) <= 1e-3 * float(v.float().abs().max()) + 1e-6
+    xin = torch.randn(50, 2 * 64, device=dev, generator=g).bfloat16()
+    dz = torch.randn(50, 64, device=dev, generator=g).bfloat16()
+    outs = {}
+    for reg in (True, False):
+        f = ops.geglu_fwd.op if reg else ops.geglu_fwd
+        xi = xin.clone().requires_grad_(True)
+        z = f(xi)
+        outs[reg] = [z.detach(), torch.autograd.grad(z, xi, dz)[0]]
+    for u, v in zip(outs[True], outs[False]):
+        assert torch.equal(u, v)

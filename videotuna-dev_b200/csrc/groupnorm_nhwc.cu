@@ -11,14 +11,18 @@
 // bulk-copy / cluster kernels of groupnorm.cu do not apply.
 //
 // Two streaming sweeps per direction (the second one hits L2: the tensors are 26-105 MB against 126 MB of L2):
-//   forward   stats: per-thread per-channel sum / sum of squares over the CTA's rows -> shared-memory per-channel bins ->
-//             per-CTA per-group partials in a (N, chunks, G, 2) workspace (plain stores: no memset launch, no global
-//             atomics, deterministic), summed over the chunks by every CTA of the second sweep;  apply: y = silu(x * a[c] + d[c]) with a = rstd*gamma,
-//             d = beta - mean*a precomputed per CTA in shared memory.
-//   backward  sums: gz = dy * silu'(z) recomputed from x; per-channel sum gz, sum gz*xhat -> dbeta / dgamma atomics and
-//             per-group gamma-weighted sums;  apply: dx = gz * (rstd*gamma[c]) + x * c2[g] + c0[g] (gz recomputed).
-// A thread owns one 16-byte vector column (8 bf16 / 4 fp32 channels) and walks down the rows, so its accumulators live in
-// registers; blockDim is the largest multiple of C/VEC that fits 512 threads.
+//   forward   stats: per-thread per-channel sum / sum of squares over the CTA's rows (registers) -> tree over the CTA's row
+//             groups in shared memory (plain stores) -> per-CTA per-group partials in a (N, chunks, G, 2) workspace (plain
+//             stores: no memset launch, no global atomics, deterministic). The partials of a sample are joined cooperatively
+//             in the second sweep's prologue (<= 32 chunks) or by the finalize kernel (more: the few-sample 5-D inputs).
+//             apply: y = silu(x * a[c] + d[c]) with a = rstd*gamma, d = beta - mean*a precomputed per CTA in shared memory.
+//   backward  sums: gz = dy * silu'(z), z = x*A + D recomputed from x; per-channel sum gz, sum gz*x (centred to sum gz*xhat
+//             once per channel in the epilogue) -> dbeta / dgamma atomics (skipped for frozen parameters) and per-group
+//             gamma-weighted partials;  apply: dx = gz * A[c] + x * c2[c] + c0[c] (gz recomputed).
+// A thread owns one 16-byte vector column (8 bf16 / 4 fp32 channels) and walks down the rows with 2-4 rows of raw vectors
+// in flight; blockDim is the largest multiple of C/VEC that fits 512 threads. An optional fp32 addend e[n][c] (a
+// convolution bias, ResBlock's timestep embedding) is normalised with x — GroupNorm(x + e) — at no in-loop cost: it enters
+// the per-channel constants, and the statistics' per-CTA epilogue (sum += rows*e, sum of squares += 2 e sum + rows e^2).
 #include <cstdlib>
 #include <cuda_bf16.h>
 

@@ -399,6 +399,21 @@ def denoiser_it_s(world: int):
         if "error" in line:
             out[name] = line
             continue
+        kept = None
+        try:  # the same iteration with selective checkpointing: attention outputs (O, LSE) kept, not recomputed (b200vt.ckpt)
+            a2 = types.SimpleNamespace(**{**vars(a), "keep_attention": True, "warmup": 2})
+            l2 = BD.run(a2, manage_dist=False, emit=False)
+            if l2 is not None:
+                kept = {"s_per_it_measured": l2["s_per_it"], "s_per_it_full_stack": round(l2["s_per_it"] * scale, 3),
+                        "it_per_s_full_stack": round(1.0 / (l2["s_per_it"] * scale), 5), "peak_mem_GB": l2["peak_mem_GB"],
+                        "attention_share_of_step": l2.get("attention_share_of_step"),
+                        "checkpointing": "per block, selective: the attention forward's outputs stay resident (torch selective "
+                                         "activation checkpointing, policy b200vt.ckpt.attention_saving_policy); the backward "
+                                         "receives the same O and LSE a recomputed forward would produce"}
+        except Exception as e:  # noqa: BLE001
+            kept = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+        gc.collect()
+        torch.cuda.empty_cache()
         out[name] = {"s_per_it_measured": line["s_per_it"], "blocks_measured": note,
                      "s_per_it_full_stack": round(line["s_per_it"] * scale, 3),
                      "it_per_s_full_stack": round(1.0 / (line["s_per_it"] * scale), 5),
@@ -407,6 +422,8 @@ def denoiser_it_s(world: int):
                      "iteration": "forward + backward + fused AdamW step on the trainable parameters, per-block activation checkpointing",
                      "attention_share_of_step": line.get("attention_share_of_step"),
                      "attention_tflops_in_step": line.get("attention_tflops_in_step"), "peak_mem_GB": line["peak_mem_GB"]}
+        if kept is not None:
+            out[name]["attention_outputs_kept"] = kept
     if world == 1:
         # BASELINE config 2: the whole VideoCrafter2 3D-UNet LoRA step (tools/bench_vc2_unet.py), ours and the reference's
         # op sequence on the same weights (data parallel model: measured at 1 GPU)

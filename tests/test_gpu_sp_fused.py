@@ -140,3 +140,60 @@ def test_wan_usp_attention_two_gpus_matches_single_gpu():
     for rank in (0, 1):
         e = result[rank]
         assert e["out"] <= 2e-2 and e["dx"] <= 2e-2 and e["dw"] <= 3e-2, (rank, e)
+
+
+def _ckpt_worker(rank, world, port, result):
+    """Selective checkpointing (b200vt.ckpt) around sequence-parallel attention with the fused exchange: the op that holds the
+    symmetric-memory barriers, the scatter kernel and the copy-out is kept as a whole, so a checkpointed region's backward
+    re-runs neither — on every rank alike — and outputs (bit for bit) / gradients (to rounding) equal the un-checkpointed run."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), B200VT_SP_FUSED="1")
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import b200vt._lib as L
+        import b200vt.ckpt as CK
+        import b200vt.sp as sp
+        S, H, D, T = 512, 4, 128, 64
+        g = torch.Generator(device="cuda").manual_seed(100 + rank)
+        loc = [torch.randn(1, S, H, D, device="cuda", dtype=torch.bfloat16, generator=g) for _ in range(3)]
+        g0 = torch.Generator(device="cuda").manual_seed(7)
+        txt = [torch.randn(1, T, H, D, device="cuda", dtype=torch.bfloat16, generator=g0) for _ in range(3)]
+        d_out = torch.randn(1, S + T, H, D, device="cuda", dtype=torch.bfloat16, generator=g)
+        lin = torch.nn.Linear(D, D).cuda().bfloat16()
+        attn = sp.UlyssesAttention()
+
+        def region(q, k, v, tq, tk, tv):
+            o = attn(None, lin(q), k, v, joint_tensor_query=tq, joint_tensor_key=tk, joint_tensor_value=tv, joint_strategy="rear")
+            return lin(o)
+
+        outs = {}
+        for mode in ("none", "selective"):
+            ins = [t.clone().requires_grad_(True) for t in loc + txt]
+            lin.zero_grad(set_to_none=True)
+            L.profile_enable(True)
+            y = region(*ins) if mode == "none" else CK.checkpoint(region, *ins)
+            y.backward(d_out)
+            torch.cuda.synchronize()
+            n_fwd = L.profile_read(L.K_ATTN_FWD)[1]
+            L.profile_enable(False)
+            outs[mode] = ([y.detach()] + [t.grad for t in ins] + [lin.weight.grad.clone()], n_fwd)
+        # (dQ is accumulated over the key tiles by fp32 reduce-adds in arrival order: equal to rounding, not bit for bit)
+        same = torch.equal(outs["none"][0][0], outs["selective"][0][0]) and all(
+            float((a.float() - b.float()).abs().max()) <= 1e-2 * float(b.float().abs().max()) + 1e-6
+            for a, b in zip(outs["none"][0], outs["selective"][0]))
+        result[rank] = {"same": bool(same), "fwd_launches": (outs["none"][1], outs["selective"][1])}
+    finally:
+        dist.destroy_process_group()
+
+
+def test_selective_checkpoint_with_fused_exchange_two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    result = mgr.dict()
+    mp.spawn(_ckpt_worker, args=(2, 29621, result), nprocs=2, join=True)
+    for rank in (0, 1):
+        assert result[rank]["same"], result[rank]
+        assert result[rank]["fwd_launches"] == (1, 1), result[rank]  # kept: no second forward launch in the backward

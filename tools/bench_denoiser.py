@@ -308,6 +308,9 @@ def parse(argv=None):
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--no-checkpoint", action="store_true")
+    ap.add_argument("--keep-attention", action="store_true",
+                    help="ours arm, with checkpointing: selective activation checkpointing that keeps the attention outputs (O, "
+                    "LSE) instead of recomputing the attention forward in the backward pass (b200vt.ckpt)")
     ap.add_argument("--graph", action="store_true",
                     help="capture the whole iteration (forward, backward, optimizer step) into one CUDA graph and replay it "
                     "(single GPU)")
@@ -347,9 +350,18 @@ def run(args, manage_dist: bool = True, emit: bool = True):
     use_graph = bool(getattr(args, "graph", False))
     assert not (use_graph and world > 1), "--graph is single-GPU"
 
+    keep_attn = bool(getattr(args, "keep_attention", False)) and ckpt and ours
+    if keep_attn:
+        import b200vt.ckpt as CK
+        import b200vt.sp  # noqa: F401  (registers the sequence-parallel attention op the policy also keeps)
+
     def run_block(fn, *a):
         # under graph capture the checkpoint must not save / restore the RNG state (a host operation); these blocks have no dropout
-        return checkpoint(fn, *a, use_reentrant=False, preserve_rng_state=not use_graph) if ckpt else fn(*a)
+        if not ckpt:
+            return fn(*a)
+        if keep_attn:  # selective: the attention outputs (O, LSE) stay resident, everything else is recomputed
+            return checkpoint(fn, *a, use_reentrant=False, preserve_rng_state=not use_graph, context_fn=CK.context_fn)
+        return checkpoint(fn, *a, use_reentrant=False, preserve_rng_state=not use_graph)
 
     opt_state = {}
 
@@ -387,10 +399,7 @@ def run(args, manage_dist: bool = True, emit: bool = True):
         n_params = sum(p.numel() for b in (*dbl, *sgl) for p in b.parameters())
         layers_desc = {"double": nd, "single": ns}
         attn_flops = 14.0 * heads * float(n_img + n_txt) ** 2 * (C // heads) * (nd + ns)
-        if ckpt:
-            attn_exec = attn_flops * 18.0 / 14.0
-        else:
-            attn_exec = attn_flops
+        attn_exec = attn_flops * (18.0 / 14.0 if ckpt and not keep_attn else 1.0)
 
         def iteration(ours=ours):
             img, txt = img0.detach().requires_grad_(True), txt0.detach().requires_grad_(True)
@@ -419,7 +428,7 @@ def run(args, manage_dist: bool = True, emit: bool = True):
         n_params = sum(p.numel() for p in params)
         layers_desc = {"layers": nl}
         attn_flops = 14.0 * heads * float(n_img + n_txt) ** 2 * (C // heads) * nl
-        attn_exec = attn_flops * (18.0 / 14.0 if ckpt else 1.0)
+        attn_exec = attn_flops * (18.0 / 14.0 if ckpt and not keep_attn else 1.0)
 
         def iteration(ours=ours):
             h = leaf = h0.detach().requires_grad_(True)
@@ -455,7 +464,7 @@ def run(args, manage_dist: bool = True, emit: bool = True):
         n_params = sum(p.numel() for p in params)
         layers_desc = {"layers": nl}
         attn_flops = 14.0 * heads * (float(n_img) ** 2 + float(n_img) * n_txt) * (C // heads) * nl
-        attn_exec = attn_flops * (18.0 / 14.0 if ckpt else 1.0)
+        attn_exec = attn_flops * (18.0 / 14.0 if ckpt and not keep_attn else 1.0)
 
         def iteration(ours=ours):
             x = leaf = x0.detach().requires_grad_(True)
@@ -545,7 +554,7 @@ def run(args, manage_dist: bool = True, emit: bool = True):
             "it_per_s": round(1.0 / s_per_it, 5), "s_per_it": round(s_per_it, 4), "steps": args.steps, "warmup": args.warmup,
             "config": {**layers_desc, "img_tokens": n_img, "txt_tokens": n_txt, "hidden": C, "heads": heads,
                        "block_params": n_params, "trainable_params": sum(p.numel() for p in params),
-                       "activation_checkpointing": ckpt, "dtype": "bf16", "optimizer": getattr(args, "optimizer", "none"),
+                       "activation_checkpointing": ("per block, attention outputs kept (selective)" if keep_attn else ckpt), "dtype": "bf16", "optimizer": getattr(args, "optimizer", "none"),
                        "launch": "one CUDA graph per iteration" if use_graph else "eager",
                        "parallelism": "single" if world == 1 else f"ulysses_sp{world}",
                        "attention": ("b200vt tcgen05 kernels" if ours else (

@@ -22,7 +22,7 @@ from __future__ import annotations
 import importlib
 import math
 import os
-from typing import Callable, Optional
+from typing import Callable, Optional, Tuple
 
 import torch
 import torch.distributed as dist
@@ -194,6 +194,37 @@ class _PeerBuffers:
         return cls._cache[key]
 
 
+_GROUPS: dict = {}  # id(group) -> group: process groups cannot travel through an op schema
+
+
+@torch.library.custom_op("b200vt::ulysses_attn_fwd", mutates_args=(), device_types="cuda")
+def ulysses_attn_fwd(q: Tensor, k: Tensor, v: Tensor, softmax_scale: float, n_img: int,
+                     group_key: int) -> Tuple[Tensor, Tensor, Tensor]:
+    """Head-sharded attention with the head -> sequence exchange of its output fused into the kernel epilogue, as ONE op:
+    symmetric-memory barrier, `attn_fwd_scatter` (peer stores over NVLink), barrier, copy of the received rows out of the
+    symmetric buffer. Returns (out_seq (1, L/P, H, D), o (1, L [+ T], H/P, D) head layout, lse). One op so that selective
+    activation checkpointing (ckpt.py) can keep all three and skip the barriers, the kernel and the copy on every rank alike."""
+    from . import ops
+    group = _GROUPS[group_key]
+    P, r = _world(group), _rank(group)
+    _, Ltot, Hp, D = q.shape
+    s_loc = n_img // P
+    pb = _PeerBuffers.get(group, s_loc, Hp * P, D, q.device)
+    ptrs = [a + r * Hp * D * 2 for a in pb.ptrs]  # this rank's head slot inside every destination row
+    pb.handle.barrier(channel=0)                   # every rank has consumed the previous contents of its buffer
+    o, lse = ops.attn_fwd_scatter(q, k, v, None, float(softmax_scale), pb.buf, ptrs, s_loc, Hp * P * D, D)
+    pb.handle.barrier(channel=1)                   # all peers' stores into this rank's buffer are complete
+    return pb.buf.unsqueeze(0).clone(), o, lse
+
+
+@ulysses_attn_fwd.register_fake
+def _(q, k, v, softmax_scale, n_img, group_key):
+    _, Ltot, Hp, D = q.shape
+    P = _world(_GROUPS[group_key])
+    return (q.new_empty((1, n_img // P, Hp * P, D)), q.new_empty((1, Ltot, Hp, D)),
+            q.new_empty((1, Hp, Ltot), dtype=torch.float32))
+
+
 class _FusedAttnExchange(torch.autograd.Function):
     """out_seq (1, L/P, H, D) = head_to_seq(attention(q, k, v)) for head-sharded q, k, v (1, L [+ T], H/P, D), with the
     exchange done by the kernel epilogue. Backward: the adjoint exchange of dO (NCCL all-to-all, `seq_to_head`) followed
@@ -202,18 +233,12 @@ class _FusedAttnExchange(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, q, k, v, group, scale, n_img):
-        from . import ops
-        P, r = _world(group), _rank(group)
-        _, Ltot, Hp, D = q.shape
-        s_loc = n_img // P
-        pb = _PeerBuffers.get(group, s_loc, Hp * P, D, q.device)
-        ptrs = [a + r * Hp * D * 2 for a in pb.ptrs]  # this rank's head slot inside every destination row
-        pb.handle.barrier(channel=0)                   # every rank has consumed the previous contents of its buffer
-        o, lse = ops.attn_fwd_scatter(q, k, v, None, float(scale), pb.buf, ptrs, s_loc, Hp * P * D, D)
-        pb.handle.barrier(channel=1)                   # all peers' stores into this rank's buffer are complete
+        key = id(group)
+        _GROUPS.setdefault(key, group)
+        out_seq, o, lse = ulysses_attn_fwd(q, k, v, float(scale), int(n_img), key)
         ctx.save_for_backward(q, k, v, o, lse)
         ctx.group, ctx.scale, ctx.n_img = group, scale, n_img
-        return pb.buf.unsqueeze(0).clone(), o[:, n_img:]
+        return out_seq, o[:, n_img:]
 
     @staticmethod
     def backward(ctx, d_seq, d_txt):

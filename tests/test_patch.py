@@ -272,3 +272,33 @@ def test_cast_frozen_weights_touches_only_frozen_conv_and_linear():
     assert n == 5  # conv w+b, linear w+b, last linear's bias
     assert net[0].weight.dtype == torch.bfloat16 and torch.equal(net[0].weight, want)  # the rounding autocast applies
     assert net[1].weight.dtype == torch.float32 and net[3].weight.dtype == torch.float32 and net[3].bias.dtype == torch.bfloat16
+
+
+def test_ckpt_policy_and_checkpoint_wrapper():
+    """b200vt.ckpt on CPU: the policy keeps exactly the attention forward ops, ckpt.checkpoint runs torch's non-reentrant
+    checkpoint with that policy, and keep_attention_in_checkpoints() wraps / restores torch.utils.checkpoint.checkpoint."""
+    import torch.utils.checkpoint as tuc
+    import b200vt.ckpt as CK
+    import b200vt.sp  # noqa: F401  (registers b200vt::ulysses_attn_fwd)
+    keep, redo = tuc.CheckpointPolicy.MUST_SAVE, tuc.CheckpointPolicy.PREFER_RECOMPUTE
+    assert CK.attention_saving_policy(None, torch.ops.b200vt.attn_fwd.default) == keep
+    assert CK.attention_saving_policy(None, torch.ops.b200vt.ulysses_attn_fwd.default) == keep
+    assert CK.attention_saving_policy(None, torch.ops.b200vt.attn_bwd.default) == redo
+    assert CK.attention_saving_policy(None, torch.ops.aten.mm.default) == redo
+    lin = torch.nn.Linear(8, 8)
+    x = torch.randn(2, 8, requires_grad=True)
+    want = torch.autograd.grad(lin(x).sum(), x)[0]
+    got = torch.autograd.grad(CK.checkpoint(lin, x).sum(), x)[0]
+    torch.testing.assert_close(got, want)
+    with pytest.raises(ValueError):
+        CK.checkpoint(lin, x, use_reentrant=True)
+    CK.keep_attention_in_checkpoints()
+    try:
+        assert getattr(tuc.checkpoint, "_b200vt_wrapped", False)
+        for reentrant in (False, True):
+            x.grad = None
+            torch.utils.checkpoint.checkpoint(lin, x, use_reentrant=reentrant).sum().backward()
+            torch.testing.assert_close(x.grad, want)
+    finally:
+        CK.keep_attention_in_checkpoints(False)
+    assert tuc.checkpoint is CK._ORIGINAL

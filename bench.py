@@ -388,32 +388,39 @@ def denoiser_it_s(world: int):
         import gc
 
         import torch
-        try:
-            line = BD.run(a, manage_dist=False, emit=False)
-        except Exception as e:  # noqa: BLE001
-            line = {"error": f"{type(e).__name__}: {str(e)[:200]}"} if int(os.environ.get("RANK", "0")) == 0 else None
-        gc.collect()
-        torch.cuda.empty_cache()
-        if line is None:
+
+        def run_variant(ns):
+            """One tools/bench_denoiser.py run. EVERY rank executes it (the iteration contains collectives); only rank 0
+            gets a record back. Returns (record or None, error string or None)."""
+            rec, err = None, None
+            try:
+                rec = BD.run(ns, manage_dist=False, emit=False)
+            except Exception as e:  # noqa: BLE001
+                err = f"{type(e).__name__}: {str(e)[:200]}"
+            gc.collect()
+            torch.cuda.empty_cache()
+            return rec, err
+
+        line, err = run_variant(a)
+        # the same iteration with selective checkpointing: attention outputs (O, LSE) kept, not recomputed (b200vt.ckpt).
+        # Run by ALL ranks, before any rank-dependent `continue` below (rank 0 alone holds the records).
+        l2, err2 = (None, "skipped: the full-recompute run failed") if err is not None else run_variant(
+            types.SimpleNamespace(**{**vars(a), "keep_attention": True, "warmup": 2}))
+        if int(os.environ.get("RANK", "0")) != 0:
             continue
-        if "error" in line:
-            out[name] = line
+        if err is not None or line is None:
+            out[name] = {"error": err or "no record"}
             continue
         kept = None
-        try:  # the same iteration with selective checkpointing: attention outputs (O, LSE) kept, not recomputed (b200vt.ckpt)
-            a2 = types.SimpleNamespace(**{**vars(a), "keep_attention": True, "warmup": 2})
-            l2 = BD.run(a2, manage_dist=False, emit=False)
-            if l2 is not None:
-                kept = {"s_per_it_measured": l2["s_per_it"], "s_per_it_full_stack": round(l2["s_per_it"] * scale, 3),
-                        "it_per_s_full_stack": round(1.0 / (l2["s_per_it"] * scale), 5), "peak_mem_GB": l2["peak_mem_GB"],
-                        "attention_share_of_step": l2.get("attention_share_of_step"),
-                        "checkpointing": "per block, selective: the attention forward's outputs stay resident (torch selective "
-                                         "activation checkpointing, policy b200vt.ckpt.attention_saving_policy); the backward "
-                                         "receives the same O and LSE a recomputed forward would produce"}
-        except Exception as e:  # noqa: BLE001
-            kept = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
-        gc.collect()
-        torch.cuda.empty_cache()
+        if l2 is not None:
+            kept = {"s_per_it_measured": l2["s_per_it"], "s_per_it_full_stack": round(l2["s_per_it"] * scale, 3),
+                    "it_per_s_full_stack": round(1.0 / (l2["s_per_it"] * scale), 5), "peak_mem_GB": l2["peak_mem_GB"],
+                    "attention_share_of_step": l2.get("attention_share_of_step"),
+                    "checkpointing": "per block, selective: the attention forward's outputs stay resident (torch selective "
+                                     "activation checkpointing, policy b200vt.ckpt.attention_saving_policy); the backward "
+                                     "receives the same O and LSE a recomputed forward would produce"}
+        elif err2 is not None:
+            kept = {"error": err2}
         out[name] = {"s_per_it_measured": line["s_per_it"], "blocks_measured": note,
                      "s_per_it_full_stack": round(line["s_per_it"] * scale, 3),
                      "it_per_s_full_stack": round(1.0 / (line["s_per_it"] * scale), 5),

@@ -51,7 +51,8 @@ def _worker(rank, world, port, B, L, T, H, D, result_q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("B,L,T,H,D", [(1, 24, 0, 4, 8), (1, 24, 6, 4, 8), (2, 16, 5, 2, 8)])
+# (1, 24, 6, 3, 8) and (1, 16, 0, 5, 8): head counts that do not divide the world size are padded with zero heads
+@pytest.mark.parametrize("B,L,T,H,D", [(1, 24, 0, 4, 8), (1, 24, 6, 4, 8), (2, 16, 5, 2, 8), (1, 24, 6, 3, 8), (1, 16, 0, 5, 8)])
 def test_ulysses_world2_matches_unsharded(B, L, T, H, D):
     world = 2
     ctx = mp.get_context("spawn")

@@ -300,7 +300,19 @@ class UlyssesAttention:
         P, r = _world(self.group), _rank(self.group)
         H = query.shape[2]
         if H % P != 0:
-            raise ValueError(f"Ulysses needs num_heads % world_size == 0 (H={H}, P={P})")
+            # Head counts that do not divide the group size (CogVideoX-2B: 30 heads on 4 or 8 GPUs): pad with zero heads up
+            # to the next multiple — a zero head attends uniformly over zero values, contributes nothing, costs
+            # (pad / H) extra attention FLOPs (2 of 32 there) — and drop them from the result; gradients flow through the pad.
+            pad = P - H % P
+
+            def padh(t):
+                return None if t is None else torch.nn.functional.pad(t, (0, 0, 0, pad))
+
+            out = self(attn, padh(query), padh(key), padh(value), dropout_p=dropout_p, softmax_scale=softmax_scale,
+                       causal=causal, window_size=window_size, joint_tensor_query=padh(joint_tensor_query),
+                       joint_tensor_key=padh(joint_tensor_key), joint_tensor_value=padh(joint_tensor_value),
+                       joint_strategy=joint_strategy)
+            return out[:, :, :H]
         Hp = H // P
         T = joint_tensor_query.shape[1] if has_joint else 0
         q = seq_to_head(query, self.group, rear=T)

@@ -302,3 +302,27 @@ def test_ckpt_policy_and_checkpoint_wrapper():
     finally:
         CK.keep_attention_in_checkpoints(False)
     assert tuc.checkpoint is CK._ORIGINAL
+
+
+def test_groupnorm_ops_bind_defaulted_arguments_under_fake_tensors():
+    """The GroupNorm ops gained defaulted arguments (`addend`, `need_wgrad`): traced / fake-tensor calls with the old six
+    positional arguments must still bind (torch fills the defaults before setup_context), the layout of the fake output
+    must follow the input's (channels-last stays channels-last), and the backward formula must return one entry per input."""
+    import types
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    import b200vt.ops as ops
+    with FakeTensorMode():
+        for cl, use_e, frozen, nargs in ((False, False, False, 6), (True, False, False, 6), (True, True, False, 7), (True, True, True, 7)):
+            x = torch.empty(3, 64, 6, 10, device="cuda", dtype=torch.bfloat16)
+            if cl:
+                x = x.contiguous(memory_format=torch.channels_last)
+            w, b = torch.empty(64, device="cuda"), torch.empty(64, device="cuda")
+            e = torch.empty(3, 64, device="cuda") if use_e else None
+            args = (x, w, b, 32, 1e-5, True) + ((e,) if nargs == 7 else ())
+            y, mean, rstd = ops.groupnorm_silu_fwd(*args)
+            assert y.shape == x.shape and y.stride() == x.stride() and mean.shape == (3, 32)
+            ctx = types.SimpleNamespace(saved_tensors=(x, mean, rstd, w, b, e), groups=32, silu=True,
+                                        needs_input_grad=(True, not frozen, not frozen, False, False, False, False))
+            out = ops._gn_backward(ctx, torch.empty_like(y), None, None)
+            assert len(out) == 7 and out[0].shape == x.shape and out[0].stride() == x.stride()
+            assert (out[1] is None and out[2] is None) if frozen else (out[1].shape == (64,) and out[2].shape == (64,))

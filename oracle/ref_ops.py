@@ -453,3 +453,42 @@ def max_rel_err(y: Tensor, ref: Tensor) -> float:
 def cosine(a: Tensor, b: Tensor) -> float:
     a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
     return float(torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-30))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Approximations the CUDA kernels use inside otherwise exact formulas, restated in float32 numpy so that their error
+# bounds are pinned on the CPU (tests/test_oracle_golden.py) — test infrastructure like the rest of this file.
+# ---------------------------------------------------------------------------------------------------------------------
+def erf_abramowitz_stegun_f32(x):
+    """erf(x) by Abramowitz & Stegun 7.1.26 in float32, as csrc/geglu.cu evaluates it (the exact-GELU of lvdm's GEGLU,
+    lvdm/modules/attention.py:522-529 -> F.gelu). Published bound: |error| <= 1.5e-7 in exact arithmetic; 5.3e-7 as evaluated here in float32."""
+    import numpy as np
+    x = np.asarray(x, dtype=np.float32)
+    ax = np.abs(x)
+    t = (np.float32(1.0) / (np.float32(0.3275911) * ax + np.float32(1.0))).astype(np.float32)
+    p = np.float32(1.061405429) * t + np.float32(-1.453152027)
+    p = p * t + np.float32(1.421413741)
+    p = p * t + np.float32(-0.284496736)
+    p = p * t + np.float32(0.254829592)
+    e = np.float32(1.0) - p * t * np.exp(-(ax * ax), dtype=np.float32)
+    return np.copysign(e, x).astype(np.float32)
+
+
+def gelu_and_grad_f32(g):
+    """(gelu(g), d gelu / dg) from the approximation above, as geglu.cu's gelu_f / dgelu_f."""
+    import numpy as np
+    g = np.asarray(g, dtype=np.float32)
+    cdf = np.float32(0.5) * (np.float32(1.0) + erf_abramowitz_stegun_f32(g * np.float32(0.70710678118654752)))
+    pdf = np.float32(0.3989422804014327) * np.exp(np.float32(-0.5) * g * g, dtype=np.float32)
+    return (g * cdf).astype(np.float32), (cdf + g * pdf).astype(np.float32)
+
+
+def silu_and_grad_by_tanh_f32(z):
+    """silu(z) = h + h tanh(h), h = z / 2;  silu'(z) = s (1 + z (1 - s)), s = (1 + tanh(h)) / 2 — the one-transcendental forms
+    of csrc/groupnorm*.cu (exact identities; the kernels evaluate tanh with `tanh.approx.f32`)."""
+    import numpy as np
+    z = np.asarray(z, dtype=np.float32)
+    h = np.float32(0.5) * z
+    th = np.tanh(h, dtype=np.float32)
+    s = np.float32(0.5) * th + np.float32(0.5)
+    return (h * th + h).astype(np.float32), (s * (z * (np.float32(1.0) - s) + np.float32(1.0))).astype(np.float32)

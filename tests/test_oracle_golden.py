@@ -138,3 +138,28 @@ def test_chunked_attention_reference_equals_explicit_softmax_and_autograd():
             assert R.max_rel_err(got[:n], want) < TOL
             assert n == 150 or float(got[n:].abs().max()) == 0.0
         assert n == 150 or float(o[n:].abs().max()) == 0.0
+
+
+def test_kernel_side_approximations_are_within_their_stated_bounds():
+    """The closed forms the CUDA kernels evaluate inside exact formulas (oracle restatements in float32 numpy): erf by
+    Abramowitz-Stegun 7.1.26 (GEGLU: exact-erf GELU and its derivative) and SiLU / SiLU' through one tanh (GroupNorm+SiLU),
+    against float64 references over the whole useful range."""
+    import math
+
+    import numpy as np
+    from oracle import ref_ops as R
+    x = np.linspace(-6.0, 6.0, 200001)
+    exact = np.array([math.erf(v) for v in x])
+    # published bound 1.5e-7 in exact arithmetic; evaluated in float32 (coefficients, exp, the final 1 - ...) 5.3e-7
+    assert np.abs(R.erf_abramowitz_stegun_f32(x).astype(np.float64) - exact).max() <= 6e-7
+    g = np.linspace(-12.0, 12.0, 200001)
+    cdf = 0.5 * (1.0 + np.array([math.erf(v / math.sqrt(2.0)) for v in g]))
+    pdf = np.exp(-0.5 * g * g) / math.sqrt(2.0 * math.pi)
+    y, dy = R.gelu_and_grad_f32(g)
+    assert np.abs(y.astype(np.float64) - g * cdf).max() <= 2e-6      # far below one bf16 ulp of the output
+    assert np.abs(dy.astype(np.float64) - (cdf + g * pdf)).max() <= 2e-6
+    z = np.linspace(-30.0, 30.0, 200001)
+    sig = 1.0 / (1.0 + np.exp(-z))
+    s, ds = R.silu_and_grad_by_tanh_f32(z)
+    assert np.abs(s.astype(np.float64) - z * sig).max() <= 4e-6
+    assert np.abs(ds.astype(np.float64) - sig * (1.0 + z * (1.0 - sig))).max() <= 2e-6

@@ -7,7 +7,8 @@
 // (profiles/r2_s17_vc2_profile_channels_last.txt: GeluCUDAKernel, BinaryFunctor mul, GeluBackward): the projection output
 // is the widest tensor of the UNet, (b*t*h*w, 8*C), and the unfused form reads / writes it ~10 times. Here: forward reads
 // 2F and writes F elements per row; backward reads 3F and writes 2F. HBM-bound (bf16): 6 B per output element forward, 10 B
-// backward. Exact (erf) GELU as F.gelu's default: erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7), one MUFU.EX2 + one
+// backward. Exact (erf) GELU as F.gelu's default: erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7 in exact arithmetic, 5.3e-7 in
+// float32: oracle/ref_ops.py erf_abramowitz_stegun_f32, tests/test_oracle_golden.py), one MUFU.EX2 + one
 // MUFU.RCP per element.
 #include <cuda_bf16.h>
 

@@ -163,3 +163,16 @@ def test_kernel_side_approximations_are_within_their_stated_bounds():
     s, ds = R.silu_and_grad_by_tanh_f32(z)
     assert np.abs(s.astype(np.float64) - z * sig).max() <= 4e-6
     assert np.abs(ds.astype(np.float64) - sig * (1.0 + z * (1.0 - sig))).max() <= 2e-6
+
+
+def test_fma_pipe_exp2_polynomial_error_bound():
+    """csrc/sm100_ptx.cuh ex2_poly2 (restated bit for bit in float32 numpy): relative error against 2^x over the softmax's
+    argument range (x <= 0 after the running maximum is subtracted; down to the -125 clamp), and the clamp itself."""
+    import numpy as np
+    from oracle import ref_ops as R
+    x = np.concatenate([np.linspace(-124.9, 0.0, 400001), np.linspace(0.0, 20.0, 50001)])
+    got = R.ex2_poly_f32(x).astype(np.float64)
+    want = np.exp2(x.astype(np.float32).astype(np.float64))
+    assert np.abs(got / want - 1.0).max() <= 7.5e-5
+    assert float(R.ex2_poly_f32(np.array([-np.inf]))[0]) == float(R.ex2_poly_f32(np.array([-125.0]))[0]) < 3e-38
+    assert abs(float(R.ex2_poly_f32(np.array([0.0]))[0]) - 1.0) <= 7.5e-5

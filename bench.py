@@ -366,6 +366,28 @@ def library_baselines(torch, dev):
     return out
 
 
+def start_extras_watchdog(rank: int, limit_s: float, emit_headline):
+    """A daemon timer for the multi-rank extras: if they have not finished (and cancelled it) after `limit_s`, rank 0 calls
+    `emit_headline()` — which prints the json line from the values measured before the extras — and every rank leaves with
+    exit code 0 (the others 15 s later, so that rank 0's line is out first). A hung collective cannot be interrupted from
+    Python; leaving the process is the only way to hand the driver a line instead of a timeout."""
+    import threading
+
+    def fire():
+        if rank == 0:
+            try:
+                emit_headline()
+            except Exception as e:  # noqa: BLE001
+                print(json.dumps({"error": f"watchdog: {type(e).__name__}: {str(e)[:200]}"}), flush=True)
+        sys.stdout.flush()
+        os._exit(0)
+
+    t = threading.Timer(limit_s + (0.0 if rank == 0 else 15.0), fire)
+    t.daemon = True
+    t.start()
+    return t
+
+
 def denoiser_it_s(world: int):
     """Finetuning iterations (forward + backward + AdamW step) of DiT block stacks (tools/bench_denoiser.py code path,
     `ours` arm: the reference blocks' constructors with the b200vt drop-in forwards, per-block activation checkpointing,
@@ -676,8 +698,91 @@ def run_ours(args):
     gc.collect()
     torch.cuda.empty_cache()
 
+    def finish(extras, extras_clk, final=True):
+        """Rank 0: build and print THE json line from values that all exist before the extras run (pure Python for N > 1:
+        no CUDA call), so the extras watchdog below can still emit the headline if a multi-rank extra ever hangs."""
+        # ---- roofline of the dominant kernel (tensor-pipe bound) -----------------------------------------------------
+        peaks = measured_peaks()
+        heads_loc = HEADS // world
+        kern = {}
+        for name, (ms, n) in prof.items():
+            if n:
+                kern[name] = {"avg_ms": ms / n, "launches_per_step": n / args.steps}
+        fl = {"attn_fwd": flops_fwd(SEQ, SEQ, heads_loc), "attn_bwd": 2.5 * flops_fwd(SEQ, SEQ, heads_loc)}
+        dom = max((n for n in ("attn_fwd", "attn_bwd") if n in kern), key=lambda n: kern[n]["avg_ms"])
+        achieved = fl[dom] / (kern[dom]["avg_ms"] * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as fh:
+                traffic = json.load(fh).get(f"{dom}@k1_h{heads_loc}")
+        traffic_source = ("profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of "
+                          "this kernel at this shape (a profiler counter: cannot be measured inside the timed run)"
+                          if traffic is not None else "no ncu capture committed for this head count")
+        roofline = {
+            "bound": "tensor", "kernel": f"{dom}_kernel<128>", "achieved": round(achieved, 1),
+            "peak": peaks["sustained"], "unit": UNIT, "frac": round(achieved / peaks["sustained"], 4),
+            "peak_kind": "sustained bf16 cuBLAS, " + peaks["source"], "frac_of_burst": round(achieved / peaks["burst"], 4),
+            "traffic": traffic, "traffic_source": traffic_source,
+            "kernels": {n: {"avg_ms": round(kk["avg_ms"], 3), "launches_per_step": kk["launches_per_step"],
+                            **({"tflops": round(fl[n] / (kk["avg_ms"] * 1e-3) / 1e12, 1)} if n in fl else {})}
+                        for n, kk in kern.items()},
+            "step_frac_of_sustained": round(value / world / peaks["sustained"], 4),
+        }
+        gpu_launches = int(sum(n for _, n in prof.values()))
+
+        # ---- the other BASELINE.json configurations, attention only (N = 1; context for the reader, not the headline) ----
+        others = None
+        if world == 1:
+            others = other_configs(torch, dev)
+
+        # ---- CPU baseline (N = 1 only): oracle port of the reference's torch path on a bounded sample ----------------
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            lq, lk, heads, _ = cpu_size_sample(target_s=12.0)
+            tf, dt = cpu_time_sample(lq, lk, heads, steps=1, warmup=0)
+            cpu = {"value": round(tf, 4), "unit": UNIT, "cores": host_threads(), "kind": cpu_attention_fn()[1],
+                   "sample": sample_text(lq, lk, heads) + f"; {dt:.1f} s"}
+
+        line = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "B": 1, "L": SEQ, "img_tokens": IMG_TOKENS, "txt_tokens": TXT_TOKENS,
+                       "H": HEADS, "D": HEAD_DIM, "flops_per_step": step_flops,
+                       "parallelism": "single" if world == 1 else f"ulysses_sp{world}",
+                       **({} if world == 1 else {"exchange": (
+                           "q/k/v + gradients: NCCL all_to_all; forward O: peer stores from the attention epilogue "
+                           "(symmetric memory over NVLink)" if fused_exchange else "NCCL all_to_all")}),
+                       "l2": "inputs (4 x 731 MB) exceed the 126 MB L2; no flush needed"},
+            "clocks": clk,
+            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps,
+                    "api": ("functional.HostAttention (head-group pipeline)" if world == 1
+                            else "sp.HostUlyssesAttention (head-group pipeline: copy-in || all-to-all + attention + backward || copy-out)")},
+            "gpu_launches": gpu_launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            **({"other_configs": others} if others else {}),
+            **({"sp_parity": sp_parity} if sp_parity is not None else {}),
+            **extras,
+            **({"extras_clocks": extras_clk} if extras_clk is not None else {}),
+        }
+        print(json.dumps(line), flush=True)
+        if final and world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+
     # ---- the metric's second half and the claims around the headline, measured in this run (all ranks take part) -----
     extras, extras_clk = {}, None
+    watchdog = None
+    if world > 1 and not args.no_extras:
+        # The extras at N > 1 are multi-rank iterations full of collectives: if one of them ever hangs, rank 0 still prints
+        # the complete headline line (without the extras) and every rank exits 0, instead of the whole run timing out.
+        limit_s = float(os.environ.get("B200VT_BENCH_EXTRAS_TIMEOUT_S", "900"))
+        note = {"denoiser_it_s": {"error": f"the multi-rank extras did not finish within {limit_s:.0f} s (watchdog); the "
+                                           "headline keys of this line are complete"}}
+        watchdog = start_extras_watchdog(rank, limit_s, lambda: finish(note, None, final=False))
     if not args.no_extras:
         xclocks = ClockSampler(local)
         if rank == 0:
@@ -695,6 +800,8 @@ def run_ours(args):
                 gc.collect()
                 torch.cuda.empty_cache()
         extras_clk = xclocks.stop() if rank == 0 else None
+    if watchdog is not None:
+        watchdog.cancel()
 
     if rank != 0:
         if world > 1:
@@ -702,77 +809,7 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (tensor-pipe bound) -----------------------------------------------------
-    peaks = measured_peaks()
-    heads_loc = HEADS // world
-    kern = {}
-    for name, (ms, n) in prof.items():
-        if n:
-            kern[name] = {"avg_ms": ms / n, "launches_per_step": n / args.steps}
-    fl = {"attn_fwd": flops_fwd(SEQ, SEQ, heads_loc), "attn_bwd": 2.5 * flops_fwd(SEQ, SEQ, heads_loc)}
-    dom = max((n for n in ("attn_fwd", "attn_bwd") if n in kern), key=lambda n: kern[n]["avg_ms"])
-    achieved = fl[dom] / (kern[dom]["avg_ms"] * 1e-3) / 1e12
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as fh:
-            traffic = json.load(fh).get(f"{dom}@k1_h{heads_loc}")
-    traffic_source = ("profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of "
-                      "this kernel at this shape (a profiler counter: cannot be measured inside the timed run)"
-                      if traffic is not None else "no ncu capture committed for this head count")
-    roofline = {
-        "bound": "tensor", "kernel": f"{dom}_kernel<128>", "achieved": round(achieved, 1),
-        "peak": peaks["sustained"], "unit": UNIT, "frac": round(achieved / peaks["sustained"], 4),
-        "peak_kind": "sustained bf16 cuBLAS, " + peaks["source"], "frac_of_burst": round(achieved / peaks["burst"], 4),
-        "traffic": traffic, "traffic_source": traffic_source,
-        "kernels": {n: {"avg_ms": round(kk["avg_ms"], 3), "launches_per_step": kk["launches_per_step"],
-                        **({"tflops": round(fl[n] / (kk["avg_ms"] * 1e-3) / 1e12, 1)} if n in fl else {})}
-                    for n, kk in kern.items()},
-        "step_frac_of_sustained": round(value / world / peaks["sustained"], 4),
-    }
-    gpu_launches = int(sum(n for _, n in prof.values()))
-
-    # ---- the other BASELINE.json configurations, attention only (N = 1; context for the reader, not the headline) ----
-    others = None
-    if world == 1:
-        others = other_configs(torch, dev)
-
-    # ---- CPU baseline (N = 1 only): oracle port of the reference's torch path on a bounded sample ----------------
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        lq, lk, heads, _ = cpu_size_sample(target_s=12.0)
-        tf, dt = cpu_time_sample(lq, lk, heads, steps=1, warmup=0)
-        cpu = {"value": round(tf, 4), "unit": UNIT, "cores": host_threads(), "kind": cpu_attention_fn()[1],
-               "sample": sample_text(lq, lk, heads) + f"; {dt:.1f} s"}
-
-    line = {
-        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "B": 1, "L": SEQ, "img_tokens": IMG_TOKENS, "txt_tokens": TXT_TOKENS,
-                   "H": HEADS, "D": HEAD_DIM, "flops_per_step": step_flops,
-                   "parallelism": "single" if world == 1 else f"ulysses_sp{world}",
-                   **({} if world == 1 else {"exchange": (
-                       "q/k/v + gradients: NCCL all_to_all; forward O: peer stores from the attention epilogue "
-                       "(symmetric memory over NVLink)" if fused_exchange else "NCCL all_to_all")}),
-                   "l2": "inputs (4 x 731 MB) exceed the 126 MB L2; no flush needed"},
-        "clocks": clk,
-        "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps,
-                "api": ("functional.HostAttention (head-group pipeline)" if world == 1
-                        else "sp.HostUlyssesAttention (head-group pipeline: copy-in || all-to-all + attention + backward || copy-out)")},
-        "gpu_launches": gpu_launches,
-        "roofline": roofline,
-        "cpu_baseline": cpu,
-        **({"other_configs": others} if others else {}),
-        **({"sp_parity": sp_parity} if sp_parity is not None else {}),
-        **extras,
-        **({"extras_clocks": extras_clk} if extras_clk is not None else {}),
-    }
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    finish(extras, extras_clk)
 
 
 def main():

@@ -65,3 +65,37 @@ def test_every_rank_enters_every_denoiser_run():
     assert out["hunyuanvideo_720x1280x129f_lora"]["attention_outputs_kept"]["s_per_it_full_stack"] == 10.0
     assert "error" in out["wan2.1_t2v_14b_480x832x81f"]["attention_outputs_kept"]
     assert out["wan2.1_t2v_14b_480x832x81f"]["s_per_it_full_stack"] == 5.0
+
+
+def _hung_process(q):
+    sys.path.insert(0, ROOT)
+    import json
+    import time
+
+    import bench
+    bench.start_extras_watchdog(0, 1.0, lambda: print(json.dumps({"metric": "headline", "value": 1.0}), flush=True))
+    q.put("armed")
+    time.sleep(120)  # a hung collective, as far as Python can tell
+    q.put("not reached")
+
+
+def test_extras_watchdog_emits_the_headline_and_exits_zero(capfd):
+    """bench.start_extras_watchdog: a process stuck after arming the watchdog prints the headline line and exits 0; a process
+    that cancels it in time is left alone."""
+    import time
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+    p = ctx.Process(target=_hung_process, args=(q,))
+    t0 = time.time()
+    p.start()
+    assert q.get(timeout=60) == "armed"
+    p.join(timeout=30)
+    assert p.exitcode == 0 and time.time() - t0 < 60
+    assert '"metric": "headline"' in capfd.readouterr().out
+    sys.path.insert(0, ROOT)
+    import bench
+    fired = []
+    t = bench.start_extras_watchdog(1, 0.2, lambda: fired.append(1))  # rank != 0: 15 s later; cancelled long before
+    t.cancel()
+    time.sleep(0.5)
+    assert not fired and not t.is_alive()

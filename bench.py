@@ -779,7 +779,7 @@ def run_ours(args):
     if world > 1 and not args.no_extras:
         # The extras at N > 1 are multi-rank iterations full of collectives: if one of them ever hangs, rank 0 still prints
         # the complete headline line (without the extras) and every rank exits 0, instead of the whole run timing out.
-        limit_s = float(os.environ.get("B200VT_BENCH_EXTRAS_TIMEOUT_S", "900"))
+        limit_s = float(os.environ.get("B200VT_BENCH_EXTRAS_TIMEOUT_S", "480"))
         note = {"denoiser_it_s": {"error": f"the multi-rank extras did not finish within {limit_s:.0f} s (watchdog); the "
                                            "headline keys of this line are complete"}}
         watchdog = start_extras_watchdog(rank, limit_s, lambda: finish(note, None, final=False))
